@@ -1,0 +1,81 @@
+/*
+ * mecano_oracle.h -- CPU restatement of Mecano's RNEA / ABA / CRBA calculators.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker / the timed CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (ihmcrobotics/mecano, pure Java) cannot be run in
+ * this environment (no JDK) and its tests hold no golden vectors for this path
+ * (SURVEY.md section 8c).  This oracle is pinned instead against
+ *   (i)  the reference's own randomized invariants at the reference's tolerances
+ *        (ForwardDynamicsCalculatorTest.java:38-41, 767-1003), and
+ *   (ii) an independently written textbook (Featherstone, dense 6x6) formulation
+ *        in tests/featherstone_np.py.
+ *
+ * Conventions (all from the reference):
+ *   - spatial vectors are angular-first [wx wy wz | vx vy vz]
+ *     (spatial/interfaces/SpatialVectorReadOnly.java:268-272)
+ *   - a transform (R,t) attached to a child frame maps child coords to parent coords
+ *   - SixDoF configuration is [qx qy qz qs | x y z], velocity-like vectors are the
+ *     body-frame twist (multiBodySystem/interfaces/SixDoFJointReadOnly.java:21-26)
+ *   - bodies are listed in Mecano's depth-first pre-order, children in insertion
+ *     order (multiBodySystem/iterators/JointIterator.java:153-162)
+ */
+#ifndef MECANO_ORACLE_H
+#define MECANO_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MO_REVOLUTE = 0, MO_PRISMATIC = 1, MO_SIXDOF = 2 };
+
+/* flags for mo_rnea (InverseDynamicsCalculator.java:291-306) */
+enum { MO_NO_CORIOLIS = 1, MO_NO_ACCELERATIONS = 2 };
+
+typedef struct mo_tree
+{
+   int nb;              /* number of non-root bodies (= number of joints) */
+   int nv;              /* degrees of freedom */
+   int nq;              /* configuration entries */
+   const int *parent;   /* [nb] parent body, -1 = root body (elevator) */
+   const int *jtype;    /* [nb] MO_REVOLUTE / MO_PRISMATIC / MO_SIXDOF */
+   const double *axis;  /* [nb][3] unit joint axis (ignored for SixDoF) */
+   const double *off_R; /* [nb][9] row-major rotation of frameBeforeJoint in parent's frameAfterJoint */
+   const double *off_p; /* [nb][3] translation of the same */
+   const double *com_R; /* [nb][9] inertia pose: bodyFixedFrame (CoM frame) in frameAfterJoint */
+   const double *com_p; /* [nb][3] */
+   const double *J;     /* [nb][9] moment of inertia about the CoM, in bodyFixedFrame */
+   const double *mass;  /* [nb] */
+   const int *dof_off;  /* [nb] first row of this joint in the nv-vectors */
+   const int *cfg_off;  /* [nb] first row of this joint in the nq-vector */
+} mo_tree;
+
+/* Single-state calculators.  fext may be NULL; otherwise [nb][6], the external wrench on each body
+ * expressed in that body's CoM frame (InverseDynamicsCalculator.java:819, :946). */
+void mo_rnea(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *qdd, const double *fext,
+             int flags, double *tau);
+void mo_aba(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *tau, const double *fext,
+            double *qdd);
+void mo_crba(const mo_tree *t, const double *q, double *M /* [nv][nv] row-major */);
+
+/* By-products used by the tests to mirror ForwardDynamicsCalculatorTest: per-body spatial accelerations
+ * (expressed in each body's CoM frame) from RNEA pass one, [nb][6]. */
+void mo_rnea_body_accelerations(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *qdd,
+                                int flags, double *acc);
+
+/* Batched drivers, DoF-major / state-minor buffers x[k*ld + s] (same layout as the C-ABI).
+ * fext (nullable) is [(6*nb)][ld].  M is entry-major [(i*nv+j)*ld + s].  nthreads<=0 -> all cores. */
+void mo_rnea_batch(const mo_tree *t, const double *gravity3, long n, long ld, const double *q, const double *qd, const double *qdd,
+                   const double *fext, int flags, double *tau, int nthreads);
+void mo_aba_batch(const mo_tree *t, const double *gravity3, long n, long ld, const double *q, const double *qd, const double *tau,
+                  const double *fext, double *qdd, int nthreads);
+void mo_crba_batch(const mo_tree *t, long n, long ld, const double *q, double *M, int nthreads);
+
+int mo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
