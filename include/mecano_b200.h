@@ -1,0 +1,173 @@
+/*
+ * mecano_b200.h -- C ABI of the B200-native batched rigid-body dynamics engine.
+ *
+ * This is the drop-in boundary for Mecano's three recursive calculators evaluated at N joint
+ * states in one call.  Mecano (pure Java) has no FFI of its own; the interface replaced is the
+ * public API of the calculators ("M/" = /root/reference/src/main/java/us/ihmc/mecano/):
+ *
+ *   mecano_b200_create            <- new InverseDynamicsCalculator(MultiBodySystemReadOnly)      M/algorithms/InverseDynamicsCalculator.java:201-251
+ *                                    new ForwardDynamicsCalculator(MultiBodySystemReadOnly)      M/algorithms/ForwardDynamicsCalculator.java:128-222
+ *                                    new CompositeRigidBodyMassMatrixCalculator(...)             M/algorithms/CompositeRigidBodyMassMatrixCalculator.java:182-266
+ *                                    (the "flatten the tree once" step; tables in JointMatrixIndexProvider order,
+ *                                     M/multiBodySystem/interfaces/JointMatrixIndexProvider.java:71-101)
+ *   mecano_b200_set_gravity       <- setGravitationalAcceleration(x, y, z)                       InverseDynamicsCalculator.java:397-403, ForwardDynamicsCalculator.java:313-319
+ *   mecano_b200_rnea[_host]       <- InverseDynamicsCalculator.compute(DMatrix) + getJointTauMatrix()            :496-501, :567-570
+ *                                    (+ setExternalWrench :469-472, setConsiderCoriolisAndCentrifugalForces /
+ *                                     setConsiderJointAccelerations :291-306)
+ *   mecano_b200_aba[_host]        <- ForwardDynamicsCalculator.compute(DMatrix) + getJointAccelerationMatrix()   :508-520, :556-567
+ *   mecano_b200_crba[_host]       <- CompositeRigidBodyMassMatrixCalculator.reset() + getMassMatrix()            :286-291, :344-348
+ *
+ * The state (q, qd, qdd, tau), which Mecano keeps inside the joint objects and the frame tree
+ * (OneDoFJoint.java:81-87, RigidBodyBasics.java:104-112), is an explicit argument here:
+ * "set state -> updateFramesRecursively() -> compute()" is fused into each kernel.
+ *
+ * Buffers are DoF-major / state-minor:  x[k * ld + s], k = Mecano DoF (or configuration) row,
+ * s = state, ld >= n_states.  A Java DMatrixRMaj(nDoFs, N) has exactly this layout.
+ * SixDoF rows: configuration [qx qy qz qs x y z]; velocity-like rows [wx wy wz vx vy vz] in the
+ * joint's frameAfterJoint (SixDoFJointReadOnly.java:21-26).  All spatial vectors angular-first.
+ *
+ * There is no CPU fallback: every compute entry point runs hand-written sm_100a kernels or fails.
+ * All functions return 0 on success, <0 for an argument / topology error, >0 for a CUDA error
+ * (the cudaError_t value); mecano_b200_last_error() gives the text.  Nothing throws across the ABI.
+ */
+#ifndef MECANO_B200_H
+#define MECANO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MECANO_B200_VERSION 100
+
+/* joint types (M/multiBodySystem/{RevoluteJoint,PrismaticJoint,SixDoFJoint}.java) */
+#define MECANO_B200_REVOLUTE 0
+#define MECANO_B200_PRISMATIC 1
+#define MECANO_B200_SIXDOF 2
+
+/* status codes */
+#define MECANO_B200_OK 0
+#define MECANO_B200_ERR_INVALID_ARGUMENT (-1)
+#define MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY (-2)
+#define MECANO_B200_ERR_SHAPE (-3)
+#define MECANO_B200_ERR_NO_DEVICE (-4)
+#define MECANO_B200_ERR_TOO_LARGE (-5)
+
+/* flags for mecano_b200_rnea (mirror InverseDynamicsCalculator.java:291-306) */
+#define MECANO_B200_RNEA_NO_CORIOLIS 0x1u      /* setConsiderCoriolisAndCentrifugalForces(false) */
+#define MECANO_B200_RNEA_NO_ACCELERATIONS 0x2u /* setConsiderJointAccelerations(false) */
+
+/* mass-matrix layouts for mecano_b200_crba */
+#define MECANO_B200_CRBA_ENTRY_MAJOR 0x0u /* M[(i*nv + j) * ld + s]   (default, coalesced) */
+#define MECANO_B200_CRBA_STATE_MAJOR 0x1u /* M[s * nv*nv + i*nv + j]  (Mecano's per-state dense DMatrixRMaj) */
+
+/* kernel selection */
+#define MECANO_B200_VARIANT_AUTO 0
+#define MECANO_B200_VARIANT_THREAD 1 /* one thread per state */
+#define MECANO_B200_VARIANT_WARP 2   /* one warp-lane group per state (small batches / large trees) */
+
+#define MECANO_B200_ALGO_RNEA 0
+#define MECANO_B200_ALGO_ABA 1
+#define MECANO_B200_ALGO_CRBA 2
+
+typedef struct mecano_b200_handle mecano_b200_handle;
+
+/*
+ * Flattened, level-ordered description of one kinematic tree: what the Java host builds once from a
+ * MultiBodySystemReadOnly.  Body b (0 <= b < n_bodies) is the successor of joint b; the root body
+ * (elevator) is not listed and is referred to as parent -1.  Bodies must be listed so that
+ * parent[b] < b (level order satisfies this).  level_start is optional (may be NULL).
+ */
+typedef struct mecano_b200_tree_desc
+{
+   int32_t struct_size; /* sizeof(mecano_b200_tree_desc), for ABI evolution */
+   int32_t n_bodies;
+   int32_t n_dofs;   /* MultiBodySystemTools.computeDegreesOfFreedom */
+   int32_t n_cfg;    /* configuration rows: 1 per OneDoF joint, 7 per SixDoF joint */
+   int32_t n_levels; /* 0 if level_start == NULL */
+   const int32_t *level_start; /* [n_levels + 1] first body of each tree level */
+   const int32_t *parent;      /* [n_bodies] */
+   const int32_t *joint_type;  /* [n_bodies] MECANO_B200_REVOLUTE / PRISMATIC / SIXDOF */
+   const double *axis;         /* [n_bodies][3] unit joint axis in frameAfterJoint (ignored for SixDoF) */
+   const double *offset_rot;   /* [n_bodies][9] row-major rotation: frameBeforeJoint in the parent's frameAfterJoint */
+   const double *offset_pos;   /* [n_bodies][3] */
+   const double *com_rot;      /* [n_bodies][9] inertia pose: bodyFixedFrame (CoM frame) in frameAfterJoint */
+   const double *com_pos;      /* [n_bodies][3] */
+   const double *inertia;      /* [n_bodies][9] symmetric moment of inertia about the CoM, in bodyFixedFrame */
+   const double *mass;         /* [n_bodies] */
+   const int32_t *dof_offset;  /* [n_bodies] JointMatrixIndexProvider row of the joint's first DoF */
+   const int32_t *cfg_offset;  /* [n_bodies] row of the joint's first configuration entry */
+} mecano_b200_tree_desc;
+
+typedef struct mecano_b200_kernel_info
+{
+   int32_t variant;            /* MECANO_B200_VARIANT_THREAD / WARP actually selected for this batch size */
+   int32_t block_threads;
+   int32_t states_per_block;
+   int32_t regs_per_thread;
+   int32_t static_smem_bytes;
+   int32_t dynamic_smem_bytes;
+   int32_t local_bytes_per_thread;
+   int32_t blocks_per_sm;      /* occupancy reported by the runtime */
+   int32_t sm_count;
+   int32_t stack_doubles;      /* per-state stack slots held in shared memory */
+   int32_t max_depth;
+   int32_t reserved;
+   double bytes_per_state;     /* algorithmic HBM bytes per state */
+} mecano_b200_kernel_info;
+
+int mecano_b200_version(void);
+int mecano_b200_device_count(void);
+
+/* Build the constant tables / traversal programs for one tree on one device. */
+int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b200_handle **out);
+void mecano_b200_destroy(mecano_b200_handle *h);
+const char *mecano_b200_last_error(const mecano_b200_handle *h); /* h may be NULL: error of the last failed create */
+
+int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double gz);
+int mecano_b200_set_variant(mecano_b200_handle *h, int variant);
+int mecano_b200_n_dofs(const mecano_b200_handle *h);
+int mecano_b200_n_cfg(const mecano_b200_handle *h);
+int mecano_b200_n_bodies(const mecano_b200_handle *h);
+
+/*
+ * Device-pointer entry points.  All pointers are device memory on the handle's device, 8-byte
+ * aligned; `stream` is a cudaStream_t (NULL = default stream).  Calls are asynchronous.
+ * fext (nullable): external wrench on each body expressed in that body's CoM frame,
+ * [(6 * b + c) * ld + s], b in the order of the tree description (InverseDynamicsCalculator.java:819, :946).
+ */
+int mecano_b200_rnea(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
+                     const double *fext, double *tau, uint32_t flags, void *stream);
+int mecano_b200_aba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
+                    const double *fext, double *qdd, uint32_t flags, void *stream);
+int mecano_b200_crba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout,
+                     void *stream);
+
+/*
+ * Host-pointer entry points (what a JNI / Panama binding calls with DMatrixRMaj.data): inputs are
+ * staged host -> device in chunks, the kernels run, results are copied back; the call returns when
+ * the outputs are complete.  Pinned (page-locked) host memory makes the copies asynchronous and
+ * overlapped; pageable memory works too.
+ */
+int mecano_b200_rnea_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
+                          const double *fext, double *tau, uint32_t flags);
+int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
+                         const double *fext, double *qdd, uint32_t flags);
+int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
+
+/* Introspection for the benchmark / roofline report. */
+int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info);
+
+/* Roofline denominators measured on the handle-less device: FP64 FMA chain and a read+write copy. */
+int mecano_b200_measure_fp64_peak(int device, double *tflops);
+int mecano_b200_measure_hbm_peak(int device, double *gbytes_per_s);
+
+/* Pinned host memory helpers for bindings that cannot allocate it themselves. */
+int mecano_b200_host_alloc(void **ptr, int64_t bytes);
+int mecano_b200_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

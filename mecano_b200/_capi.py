@@ -1,0 +1,94 @@
+"""ctypes binding of the C ABI (include/mecano_b200.h).
+
+The shared library holds hand-written sm_100a kernels only.  If it is missing this module raises at
+import time: there is no CPU fallback and none is wanted.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmecano_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "mecano_b200: %s not found. Build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+        "or make -C mecano_b200/csrc). There is no CPU fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_dp = ctypes.POINTER(ctypes.c_double)
+c_ip = ctypes.POINTER(ctypes.c_int32)
+c_vp = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_u32 = ctypes.c_uint32
+
+REVOLUTE, PRISMATIC, SIXDOF = 0, 1, 2
+RNEA_NO_CORIOLIS, RNEA_NO_ACCELERATIONS = 1, 2
+CRBA_ENTRY_MAJOR, CRBA_STATE_MAJOR = 0, 1
+ALGO_RNEA, ALGO_ABA, ALGO_CRBA = 0, 1, 2
+
+
+class TreeDesc(ctypes.Structure):
+    """mecano_b200_tree_desc"""
+    _fields_ = [
+        ("struct_size", ctypes.c_int32), ("n_bodies", ctypes.c_int32), ("n_dofs", ctypes.c_int32), ("n_cfg", ctypes.c_int32),
+        ("n_levels", ctypes.c_int32), ("level_start", c_ip), ("parent", c_ip), ("joint_type", c_ip), ("axis", c_dp),
+        ("offset_rot", c_dp), ("offset_pos", c_dp), ("com_rot", c_dp), ("com_pos", c_dp), ("inertia", c_dp), ("mass", c_dp),
+        ("dof_offset", c_ip), ("cfg_offset", c_ip),
+    ]
+
+
+class KernelInfo(ctypes.Structure):
+    """mecano_b200_kernel_info"""
+    _fields_ = [
+        ("variant", ctypes.c_int32), ("block_threads", ctypes.c_int32), ("states_per_block", ctypes.c_int32),
+        ("regs_per_thread", ctypes.c_int32), ("static_smem_bytes", ctypes.c_int32), ("dynamic_smem_bytes", ctypes.c_int32),
+        ("local_bytes_per_thread", ctypes.c_int32), ("blocks_per_sm", ctypes.c_int32), ("sm_count", ctypes.c_int32),
+        ("stack_doubles", ctypes.c_int32), ("max_depth", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("bytes_per_state", ctypes.c_double),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_ if name != "reserved"}
+
+
+EXPORTS = [
+    "mecano_b200_version", "mecano_b200_device_count", "mecano_b200_create", "mecano_b200_destroy", "mecano_b200_last_error",
+    "mecano_b200_set_gravity", "mecano_b200_set_variant", "mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies",
+    "mecano_b200_rnea", "mecano_b200_aba", "mecano_b200_crba", "mecano_b200_rnea_host", "mecano_b200_aba_host",
+    "mecano_b200_crba_host", "mecano_b200_kernel_info_get", "mecano_b200_measure_fp64_peak", "mecano_b200_measure_hbm_peak",
+    "mecano_b200_host_alloc", "mecano_b200_host_free",
+]
+
+lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
+lib.mecano_b200_destroy.argtypes = [c_vp]
+lib.mecano_b200_destroy.restype = None
+lib.mecano_b200_last_error.argtypes = [c_vp]
+lib.mecano_b200_last_error.restype = ctypes.c_char_p
+lib.mecano_b200_set_gravity.argtypes = [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+lib.mecano_b200_set_variant.argtypes = [c_vp, ctypes.c_int]
+for _f in ("mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies"):
+    getattr(lib, _f).argtypes = [c_vp]
+lib.mecano_b200_rnea.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp]
+lib.mecano_b200_aba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp]
+lib.mecano_b200_crba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32, c_vp]
+lib.mecano_b200_rnea_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
+lib.mecano_b200_aba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
+lib.mecano_b200_crba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32]
+lib.mecano_b200_kernel_info_get.argtypes = [c_vp, ctypes.c_int, c_i64, ctypes.POINTER(KernelInfo)]
+lib.mecano_b200_measure_fp64_peak.argtypes = [ctypes.c_int, c_dp]
+lib.mecano_b200_measure_hbm_peak.argtypes = [ctypes.c_int, c_dp]
+lib.mecano_b200_host_alloc.argtypes = [ctypes.POINTER(c_vp), c_i64]
+lib.mecano_b200_host_free.argtypes = [c_vp]
+
+
+class MecanoB200Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("mecano_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = lib.mecano_b200_last_error(handle)
+        raise MecanoB200Error(rc, msg.decode() if msg else "")

@@ -1,0 +1,696 @@
+// algorithms.cuh -- one state of RNEA / ABA / CRBA, written once against a small "context" policy so
+// that the same source is (a) inlined into the sm_100a kernels (kernels.cu) and (b) compiled for the
+// host by the kernel-source emulation harness that the no-GPU tests use (tests/emu).
+//
+// What each routine restates (M/ = /root/reference/src/main/java/us/ihmc/mecano/):
+//   rnea_state : InverseDynamicsCalculator.compute()            M/algorithms/InverseDynamicsCalculator.java:496-501, 873-966
+//   aba_state  : ForwardDynamicsCalculator.compute()            M/algorithms/ForwardDynamicsCalculator.java:508-520, 1085-1310
+//   crba_state : CompositeRigidBodyMassMatrixCalculator         M/algorithms/CompositeRigidBodyMassMatrixCalculator.java:588-667, 700-707, 772-797
+// including the "set state -> updateFramesRecursively()" prologue (RigidBodyBasics.java:104-112,
+// MovingReferenceFrame.java:279-311) which Mecano keeps in the frame tree and which is fused here.
+//
+// Unlike the reference (CoM frames for RNEA, through-the-root frame changes) everything is expressed
+// in the canonical joint frames of program.h with local parent<->child transforms; results are
+// frame-independent and agree with the oracle to round-off.
+//
+// Context policy (all methods inline):
+//   T   ld_q(row) ld_qd(row) ld_x(row)      inputs in Mecano row order (x = qdd for RNEA, tau for ABA)
+//   T   ld_fext(ext_body, comp)             external wrench rows
+//   void st_out(row, T)                     tau (RNEA) / qdd (ABA)
+//   void st_M(row, col, T)                  mass-matrix entry (CRBA)
+//   T   stk_ld(i) / void stk_st(i, T)       per-state stack (shared memory on the GPU)
+//   T   aux_ld(i) / aux_st, rec_ld / rec_st per-state branch-save and record areas (local memory)
+//   const T* cst(body)                      constant record of a body (shared memory on the GPU)
+#pragma once
+#include "program.h"
+#include "spatial.cuh"
+
+namespace mb
+{
+MB_HD void mb_sincos(double x, double *s, double *c)
+{
+#if defined(__CUDA_ARCH__)
+   sincos(x, s, c);
+#else
+   *s = sin(x);
+   *c = cos(x);
+#endif
+}
+MB_HD void mb_sincos(float x, float *s, float *c)
+{
+#if defined(__CUDA_ARCH__)
+   sincosf(x, s, c);
+#else
+   *s = sinf(x);
+   *c = cosf(x);
+#endif
+}
+
+template <class T> MB_HD M3T<T> ld_m3(const T *p)
+{
+   M3T<T> r;
+   r.xx = p[0]; r.xy = p[1]; r.xz = p[2]; r.yx = p[3]; r.yy = p[4]; r.yz = p[5]; r.zx = p[6]; r.zy = p[7]; r.zz = p[8];
+   return r;
+}
+template <class T> MB_HD V3T<T> ld_v3(const T *p) { return v3<T>(p[0], p[1], p[2]); }
+template <class T> MB_HD RbiT<T> ld_rbi(const T *c)
+{
+   RbiT<T> r;
+   r.I.xx = c[MB_C_I + 0]; r.I.xy = c[MB_C_I + 1]; r.I.xz = c[MB_C_I + 2]; r.I.yy = c[MB_C_I + 3]; r.I.yz = c[MB_C_I + 4]; r.I.zz = c[MB_C_I + 5];
+   r.h = ld_v3(c + MB_C_H);
+   r.m = c[MB_C_M];
+   return r;
+}
+
+// ---- stack helpers
+template <class T, class Ctx> MB_HD void stk_st_sv(Ctx &c, int i, const SvT<T> &v)
+{
+   c.stk_st(i + 0, v.a.x); c.stk_st(i + 1, v.a.y); c.stk_st(i + 2, v.a.z);
+   c.stk_st(i + 3, v.l.x); c.stk_st(i + 4, v.l.y); c.stk_st(i + 5, v.l.z);
+}
+template <class T, class Ctx> MB_HD SvT<T> stk_ld_sv(Ctx &c, int i)
+{
+   SvT<T> v;
+   v.a = v3<T>(c.stk_ld(i + 0), c.stk_ld(i + 1), c.stk_ld(i + 2));
+   v.l = v3<T>(c.stk_ld(i + 3), c.stk_ld(i + 4), c.stk_ld(i + 5));
+   return v;
+}
+template <class T, class Ctx> MB_HD void aux_st_sv(Ctx &c, int i, const SvT<T> &v)
+{
+   c.aux_st(i + 0, v.a.x); c.aux_st(i + 1, v.a.y); c.aux_st(i + 2, v.a.z);
+   c.aux_st(i + 3, v.l.x); c.aux_st(i + 4, v.l.y); c.aux_st(i + 5, v.l.z);
+}
+template <class T, class Ctx> MB_HD SvT<T> aux_ld_sv(Ctx &c, int i)
+{
+   SvT<T> v;
+   v.a = v3<T>(c.aux_ld(i + 0), c.aux_ld(i + 1), c.aux_ld(i + 2));
+   v.l = v3<T>(c.aux_ld(i + 3), c.aux_ld(i + 4), c.aux_ld(i + 5));
+   return v;
+}
+
+// Joint parameters: what must be kept to rebuild the joint transform on the way back up.
+template <class T> struct JpT
+{
+   T s, c;      // revolute: sin/cos; prismatic: s = q
+   XfT<T> X;    // SixDoF: the whole transform
+};
+
+// (a1) joint transform X_J(q) composed with the fixed offset (MecanoFactories.java:231-260,
+// PrismaticJointReadOnly.java:18-22, FloatingJointReadOnly.java:34-37), in canonical frames
+template <class T, class Ctx> MB_HD XfT<T> joint_transform(Ctx &c, const MbBody &B, const T *C, JpT<T> &jp)
+{
+   XfT<T> X;
+   const M3T<T> R0 = ld_m3(C + MB_C_R);
+   const V3T<T> p0 = ld_v3(C + MB_C_P);
+   if (B.jtype == MB_REVOLUTE)
+   {
+      mb_sincos(c.ld_q(B.cfg_off), &jp.s, &jp.c);
+      X.R = mul_rz(R0, jp.s, jp.c);
+      X.p = p0;
+   }
+   else if (B.jtype == MB_PRISMATIC)
+   {
+      jp.s = c.ld_q(B.cfg_off);
+      X.R = R0;
+      X.p = p0 + jp.s * v3<T>(R0.xz, R0.yz, R0.zz);
+   }
+   else
+   {
+      const int r = B.cfg_off;
+      const M3T<T> Rq = quat_to_rot(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3));
+      X.R = mul(R0, Rq);
+      X.p = p0 + mul(R0, v3<T>(c.ld_q(r + 4), c.ld_q(r + 5), c.ld_q(r + 6)));
+      jp.X = X;
+   }
+   return X;
+}
+
+template <class T> MB_HD XfT<T> rebuild_transform(int jtype, const T *C, const JpT<T> &jp)
+{
+   if (jtype == MB_SIXDOF)
+      return jp.X;
+   XfT<T> X;
+   const M3T<T> R0 = ld_m3(C + MB_C_R);
+   const V3T<T> p0 = ld_v3(C + MB_C_P);
+   if (jtype == MB_REVOLUTE)
+   {
+      X.R = mul_rz(R0, jp.s, jp.c);
+      X.p = p0;
+   }
+   else
+   {
+      X.R = R0;
+      X.p = p0 + jp.s * v3<T>(R0.xz, R0.yz, R0.zz);
+   }
+   return X;
+}
+
+template <class T, class Ctx> MB_HD void stk_st_jp(Ctx &c, int i, int jtype, const JpT<T> &jp)
+{
+   if (jtype == MB_REVOLUTE)
+   {
+      c.stk_st(i, jp.s);
+      c.stk_st(i + 1, jp.c);
+   }
+   else if (jtype == MB_PRISMATIC)
+      c.stk_st(i, jp.s);
+   else
+   {
+      const M3T<T> &R = jp.X.R;
+      c.stk_st(i + 0, R.xx); c.stk_st(i + 1, R.xy); c.stk_st(i + 2, R.xz);
+      c.stk_st(i + 3, R.yx); c.stk_st(i + 4, R.yy); c.stk_st(i + 5, R.yz);
+      c.stk_st(i + 6, R.zx); c.stk_st(i + 7, R.zy); c.stk_st(i + 8, R.zz);
+      c.stk_st(i + 9, jp.X.p.x); c.stk_st(i + 10, jp.X.p.y); c.stk_st(i + 11, jp.X.p.z);
+   }
+}
+template <class T, class Ctx> MB_HD void stk_ld_jp(Ctx &c, int i, int jtype, JpT<T> &jp)
+{
+   if (jtype == MB_REVOLUTE)
+   {
+      jp.s = c.stk_ld(i);
+      jp.c = c.stk_ld(i + 1);
+   }
+   else if (jtype == MB_PRISMATIC)
+      jp.s = c.stk_ld(i);
+   else
+   {
+      M3T<T> &R = jp.X.R;
+      R.xx = c.stk_ld(i + 0); R.xy = c.stk_ld(i + 1); R.xz = c.stk_ld(i + 2);
+      R.yx = c.stk_ld(i + 3); R.yy = c.stk_ld(i + 4); R.yz = c.stk_ld(i + 5);
+      R.zx = c.stk_ld(i + 6); R.zy = c.stk_ld(i + 7); R.zz = c.stk_ld(i + 8);
+      jp.X.p = v3<T>(c.stk_ld(i + 9), c.stk_ld(i + 10), c.stk_ld(i + 11));
+   }
+}
+
+// S * x for the joint (motion subspace in canonical frames: revolute [e_z;0], prismatic [0;e_z], SixDoF 1_6;
+// JointReadOnly.java:201-207, MecanoTools.java:964-995)
+template <class T, class F> MB_HD SvT<T> joint_motion(int jtype, int row, F ld)
+{
+   SvT<T> r = sv_zero<T>();
+   if (jtype == MB_REVOLUTE)
+      r.a.z = ld(row);
+   else if (jtype == MB_PRISMATIC)
+      r.l.z = ld(row);
+   else
+   {
+      r.a = v3<T>(ld(row), ld(row + 1), ld(row + 2));
+      r.l = v3<T>(ld(row + 3), ld(row + 4), ld(row + 5));
+   }
+   return r;
+}
+
+// external wrench on a body, given in its CoM frame, re-expressed in the canonical joint frame
+template <class T, class Ctx> MB_HD SvT<T> external_wrench(Ctx &c, const MbBody &B, const T *C)
+{
+   SvT<T> w, r;
+   const int e = B.ext_index;
+   w.a = v3<T>(c.ld_fext(e, 0), c.ld_fext(e, 1), c.ld_fext(e, 2));
+   w.l = v3<T>(c.ld_fext(e, 3), c.ld_fext(e, 4), c.ld_fext(e, 5));
+   const M3T<T> E = ld_m3(C + MB_C_E);
+   r.l = mul(E, w.l);
+   r.a = mul(E, w.a) + cross(ld_v3(C + MB_C_C), r.l);
+   return r;
+}
+
+// ======================================================================================== RNEA
+template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav, bool use_qd, bool use_qdd)
+{
+   SvT<T> v = sv_zero<T>(), a = sv_zero<T>(), f = sv_zero<T>();
+   XfT<T> X;
+   JpT<T> jp;
+   X.R = M3T<T>();
+   X.p = v3<T>(0, 0, 0);
+   const int nops = P.nops;
+   for (int k = 0; k < nops; k++)
+   {
+      const uint32_t w = P.op[k];
+      const int i = MB_OP_BODY(w);
+      const MbBody &B = P.body[i];
+      const T *C = c.cst(i);
+      if (!(w & MB_OP_ASCEND))
+      {
+         // ---- pass one for body i (InverseDynamicsCalculator.java:873-917)
+         SvT<T> vp, ap;
+         if (w & MB_F_ROOT_PARENT)
+         {
+            vp = sv_zero<T>();
+            ap = sv_zero<T>();
+            ap.l = v3<T>(-grav[0], -grav[1], -grav[2]); // root acceleration = -gravity (:397-403)
+         }
+         else if (w & MB_F_LOAD_PARENT)
+         {
+            const int pa = P.body[B.parent].aux;
+            vp = aux_ld_sv<T>(c, pa);
+            ap = aux_ld_sv<T>(c, pa + 6);
+         }
+         else
+         {
+            vp = v;
+            ap = a;
+         }
+         X = joint_transform<T>(c, B, C, jp);
+         SvT<T> vj = sv_zero<T>(), aj = sv_zero<T>();
+         if (use_qd)
+            vj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_qd(r); });
+         if (use_qdd)
+            aj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_x(r); });
+         v = motion_to_child(X, vp) + vj;
+         a = motion_to_child(X, ap) + cross_motion(v, vj) + aj;
+         // Newton-Euler (SpatialInertiaReadOnly.java:229-296), about the joint-frame origin
+         const RbiT<T> I = ld_rbi(C);
+         f = mul(I, a) + cross_force(v, mul(I, v));
+         if (FEXT)
+            f = f - external_wrench<T>(c, B, C); // :946
+         if (!(w & MB_F_LEAF))
+         {
+            stk_st_sv<T>(c, B.slot, f);
+            stk_st_jp<T>(c, B.slot + 6, B.jtype, jp);
+         }
+         if (w & MB_F_SAVE_STATE)
+         {
+            aux_st_sv<T>(c, B.aux, v);
+            aux_st_sv<T>(c, B.aux + 6, a);
+         }
+      }
+      else
+      {
+         // ---- pass two for body i (:930-966); f holds the wrench of the whole subtree
+         if (!(w & MB_F_LEAF))
+         {
+            stk_ld_jp<T>(c, B.slot + 6, B.jtype, jp);
+            X = rebuild_transform<T>(B.jtype, C, jp);
+         }
+         if (B.jtype == MB_REVOLUTE)
+            c.st_out(B.dof_off, f.a.z); // tau = S^T W (:952-958)
+         else if (B.jtype == MB_PRISMATIC)
+            c.st_out(B.dof_off, f.l.z);
+         else
+         {
+            c.st_out(B.dof_off + 0, f.a.x); c.st_out(B.dof_off + 1, f.a.y); c.st_out(B.dof_off + 2, f.a.z);
+            c.st_out(B.dof_off + 3, f.l.x); c.st_out(B.dof_off + 4, f.l.y); c.st_out(B.dof_off + 5, f.l.z);
+         }
+         if (!(w & MB_F_ROOT_PARENT))
+         {
+            const int ps = P.body[B.parent].slot;
+            f = stk_ld_sv<T>(c, ps) + force_to_parent(X, f); // addJointWrenchFromChild (:961-966)
+            if (w & MB_F_STORE_ACC)
+               stk_st_sv<T>(c, ps, f);
+         }
+      }
+   }
+}
+
+// ======================================================================================== ABA
+template <class T, class Ctx> MB_HD void aux_st_abi(Ctx &c, int i, const AbiT<T> &I, const SvT<T> &p)
+{
+   c.aux_st(i + 0, I.A.xx); c.aux_st(i + 1, I.A.xy); c.aux_st(i + 2, I.A.xz); c.aux_st(i + 3, I.A.yy); c.aux_st(i + 4, I.A.yz); c.aux_st(i + 5, I.A.zz);
+   c.aux_st(i + 6, I.C.xx); c.aux_st(i + 7, I.C.xy); c.aux_st(i + 8, I.C.xz); c.aux_st(i + 9, I.C.yx); c.aux_st(i + 10, I.C.yy); c.aux_st(i + 11, I.C.yz);
+   c.aux_st(i + 12, I.C.zx); c.aux_st(i + 13, I.C.zy); c.aux_st(i + 14, I.C.zz);
+   c.aux_st(i + 15, I.L.xx); c.aux_st(i + 16, I.L.xy); c.aux_st(i + 17, I.L.xz); c.aux_st(i + 18, I.L.yy); c.aux_st(i + 19, I.L.yz); c.aux_st(i + 20, I.L.zz);
+   aux_st_sv<T>(c, i + 21, p);
+}
+template <class T, class Ctx> MB_HD void aux_ld_abi(Ctx &c, int i, AbiT<T> &I, SvT<T> &p)
+{
+   I.A.xx = c.aux_ld(i + 0); I.A.xy = c.aux_ld(i + 1); I.A.xz = c.aux_ld(i + 2); I.A.yy = c.aux_ld(i + 3); I.A.yz = c.aux_ld(i + 4); I.A.zz = c.aux_ld(i + 5);
+   I.C.xx = c.aux_ld(i + 6); I.C.xy = c.aux_ld(i + 7); I.C.xz = c.aux_ld(i + 8); I.C.yx = c.aux_ld(i + 9); I.C.yy = c.aux_ld(i + 10); I.C.yz = c.aux_ld(i + 11);
+   I.C.zx = c.aux_ld(i + 12); I.C.zy = c.aux_ld(i + 13); I.C.zz = c.aux_ld(i + 14);
+   I.L.xx = c.aux_ld(i + 15); I.L.xy = c.aux_ld(i + 16); I.L.xz = c.aux_ld(i + 17); I.L.yy = c.aux_ld(i + 18); I.L.yz = c.aux_ld(i + 19); I.L.zz = c.aux_ld(i + 20);
+   p = aux_ld_sv<T>(c, i + 21);
+}
+
+template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P, Ctx &c, const T *grav)
+{
+   SvT<T> v = sv_zero<T>(), vj = sv_zero<T>(), pacc = sv_zero<T>();
+   AbiT<T> acc = AbiT<T>();
+   XfT<T> X;
+   JpT<T> jp;
+   X.R = M3T<T>();
+   X.p = v3<T>(0, 0, 0);
+   const int nops = P.nops;
+   // ---- passes one and two interleaved along the depth-first traversal
+   for (int k = 0; k < nops; k++)
+   {
+      const uint32_t w = P.op[k];
+      const int i = MB_OP_BODY(w);
+      const MbBody &B = P.body[i];
+      const T *C = c.cst(i);
+      if (!(w & MB_OP_ASCEND))
+      {
+         // twist of the body (the frame tree's lazy twist-of-frame, MovingReferenceFrame.java:279-311)
+         SvT<T> vp;
+         if (w & MB_F_ROOT_PARENT)
+            vp = sv_zero<T>();
+         else if (w & MB_F_LOAD_PARENT)
+            vp = stk_ld_sv<T>(c, P.body[B.parent].slot);
+         else
+            vp = v;
+         X = joint_transform<T>(c, B, C, jp);
+         vj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_qd(r); });
+         v = motion_to_child(X, vp) + vj;
+         if (!(w & MB_F_LEAF))
+         {
+            stk_st_sv<T>(c, B.slot, v);
+            const int njp = mb_jp_size(B.jtype);
+            stk_st_jp<T>(c, B.slot + 6, B.jtype, jp);
+            if (B.jtype == MB_REVOLUTE)
+               c.stk_st(B.slot + 6 + njp, vj.a.z);
+            else if (B.jtype == MB_PRISMATIC)
+               c.stk_st(B.slot + 6 + njp, vj.l.z);
+            else
+               stk_st_sv<T>(c, B.slot + 6 + njp, vj);
+         }
+      }
+      else
+      {
+         if (!(w & MB_F_LEAF))
+         {
+            v = stk_ld_sv<T>(c, B.slot);
+            const int njp = mb_jp_size(B.jtype);
+            stk_ld_jp<T>(c, B.slot + 6, B.jtype, jp);
+            X = rebuild_transform<T>(B.jtype, C, jp);
+            vj = sv_zero<T>();
+            if (B.jtype == MB_REVOLUTE)
+               vj.a.z = c.stk_ld(B.slot + 6 + njp);
+            else if (B.jtype == MB_PRISMATIC)
+               vj.l.z = c.stk_ld(B.slot + 6 + njp);
+            else
+               vj = stk_ld_sv<T>(c, B.slot + 6 + njp);
+         }
+         // pass one quantities (ForwardDynamicsCalculator.java:1109-1118): bias wrench and bias acceleration
+         const RbiT<T> I = ld_rbi(C);
+         SvT<T> pA = cross_force(v, mul(I, v));
+         if (FEXT)
+            pA = pA - external_wrench<T>(c, B, C);
+         const SvT<T> cb = cross_motion(v, vj);
+         // pass two (:1136-1254)
+         AbiT<T> IA = abi_from_rbi(I);
+         if (!(w & MB_F_LEAF))
+         {
+            IA = IA + acc;
+            pA = pA + pacc;
+         }
+         AbiT<T> Ia;
+         SvT<T> pa;
+         const bool to_parent = !(w & MB_F_ROOT_PARENT);
+         if (B.jtype != MB_SIXDOF)
+         {
+            SvT<T> U;
+            T D, u;
+            const T tau = c.ld_x(B.dof_off);
+            if (B.jtype == MB_REVOLUTE)
+            {
+               U.a = v3<T>(IA.A.xz, IA.A.yz, IA.A.zz);
+               U.l = v3<T>(IA.C.zx, IA.C.zy, IA.C.zz);
+               D = IA.A.zz;
+               u = tau - pA.a.z;
+            }
+            else
+            {
+               U.a = v3<T>(IA.C.xz, IA.C.yz, IA.C.zz);
+               U.l = v3<T>(IA.L.xz, IA.L.yz, IA.L.zz);
+               D = IA.L.zz;
+               u = tau - pA.l.z;
+            }
+            const T Dinv = (T)1 / D;
+            SvT<T> g;
+            g.a = Dinv * U.a;
+            g.l = Dinv * U.l;
+            const T k0 = Dinv * u;
+            // record for pass three: qdd = k0 - g . a'
+            c.rec_st(B.rec + 0, g.a.x); c.rec_st(B.rec + 1, g.a.y); c.rec_st(B.rec + 2, g.a.z);
+            c.rec_st(B.rec + 3, g.l.x); c.rec_st(B.rec + 4, g.l.y); c.rec_st(B.rec + 5, g.l.z);
+            c.rec_st(B.rec + 6, k0);
+            c.rec_st(B.rec + 7, jp.s);
+            if (B.jtype == MB_REVOLUTE)
+               c.rec_st(B.rec + 8, jp.c);
+            if (to_parent)
+            {
+               Ia = abi_downdate(IA, U, g);       // I^a = I^A - U D^-1 U^T
+               pa = pA + mul(Ia, cb);             // p^a = p^A + I^a c + U D^-1 u
+               pa.a = pa.a + k0 * U.a;
+               pa.l = pa.l + k0 * U.l;
+            }
+         }
+         else
+         {
+            SvT<T> tau6 = joint_motion<T>(MB_SIXDOF, B.dof_off, [&](int r) { return c.ld_x(r); });
+            // D = I^A, U = I^A: a_i = D^-1 u, and the joint transmits nothing but tau to its parent
+            const SvT<T> x = abi_solve(IA, tau6 - pA);
+            c.rec_st(B.rec + 0, x.a.x); c.rec_st(B.rec + 1, x.a.y); c.rec_st(B.rec + 2, x.a.z);
+            c.rec_st(B.rec + 3, x.l.x); c.rec_st(B.rec + 4, x.l.y); c.rec_st(B.rec + 5, x.l.z);
+            c.rec_st(B.rec + 6, X.R.xx); c.rec_st(B.rec + 7, X.R.xy); c.rec_st(B.rec + 8, X.R.xz);
+            c.rec_st(B.rec + 9, X.R.yx); c.rec_st(B.rec + 10, X.R.yy); c.rec_st(B.rec + 11, X.R.yz);
+            c.rec_st(B.rec + 12, X.R.zx); c.rec_st(B.rec + 13, X.R.zy); c.rec_st(B.rec + 14, X.R.zz);
+            c.rec_st(B.rec + 15, X.p.x); c.rec_st(B.rec + 16, X.p.y); c.rec_st(B.rec + 17, X.p.z);
+            if (to_parent)
+            {
+               Ia = AbiT<T>();
+               pa = tau6;
+            }
+         }
+         if (to_parent)
+         {
+            const AbiT<T> K = abi_to_parent(X, Ia); // :1159-1165
+            const SvT<T> Pp = force_to_parent(X, pa);
+            const int pa_off = P.body[B.parent].aux;
+            if (w & MB_F_FIRST_CHILD)
+            {
+               acc = K;
+               pacc = Pp;
+            }
+            else
+            {
+               aux_ld_abi<T>(c, pa_off, acc, pacc);
+               acc = acc + K;
+               pacc = pacc + Pp;
+            }
+            if (w & MB_F_STORE_ACC)
+               aux_st_abi<T>(c, pa_off, acc, pacc);
+         }
+      }
+   }
+   // ---- pass three (:1259-1310), root to leaves, in the same depth-first order
+   SvT<T> a = sv_zero<T>();
+   v = sv_zero<T>();
+   for (int k = 0; k < nops; k++)
+   {
+      const uint32_t w = P.op[k];
+      if (w & MB_OP_ASCEND)
+         continue;
+      const int i = MB_OP_BODY(w);
+      const MbBody &B = P.body[i];
+      const T *C = c.cst(i);
+      SvT<T> vp, ap;
+      if (w & MB_F_ROOT_PARENT)
+      {
+         vp = sv_zero<T>();
+         ap = sv_zero<T>();
+         ap.l = v3<T>(-grav[0], -grav[1], -grav[2]);
+      }
+      else if (w & MB_F_LOAD_PARENT)
+      {
+         const int pa_off = P.body[B.parent].aux;
+         vp = aux_ld_sv<T>(c, pa_off);
+         ap = aux_ld_sv<T>(c, pa_off + 6);
+      }
+      else
+      {
+         vp = v;
+         ap = a;
+      }
+      vj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_qd(r); });
+      if (B.jtype != MB_SIXDOF)
+      {
+         SvT<T> g;
+         g.a = v3<T>(c.rec_ld(B.rec + 0), c.rec_ld(B.rec + 1), c.rec_ld(B.rec + 2));
+         g.l = v3<T>(c.rec_ld(B.rec + 3), c.rec_ld(B.rec + 4), c.rec_ld(B.rec + 5));
+         const T k0 = c.rec_ld(B.rec + 6);
+         jp.s = c.rec_ld(B.rec + 7);
+         if (B.jtype == MB_REVOLUTE)
+            jp.c = c.rec_ld(B.rec + 8);
+         X = rebuild_transform<T>(B.jtype, C, jp);
+         v = motion_to_child(X, vp) + vj;
+         const SvT<T> a1 = motion_to_child(X, ap) + cross_motion(v, vj); // a' = X^-1 a_parent + c
+         const T qdd = k0 - (dot(g.a, a1.a) + dot(g.l, a1.l));            // D^-1 (u - U^T a')
+         c.st_out(B.dof_off, qdd);
+         a = a1;
+         if (B.jtype == MB_REVOLUTE)
+            a.a.z += qdd;
+         else
+            a.l.z += qdd;
+      }
+      else
+      {
+         SvT<T> x;
+         x.a = v3<T>(c.rec_ld(B.rec + 0), c.rec_ld(B.rec + 1), c.rec_ld(B.rec + 2));
+         x.l = v3<T>(c.rec_ld(B.rec + 3), c.rec_ld(B.rec + 4), c.rec_ld(B.rec + 5));
+         X.R.xx = c.rec_ld(B.rec + 6); X.R.xy = c.rec_ld(B.rec + 7); X.R.xz = c.rec_ld(B.rec + 8);
+         X.R.yx = c.rec_ld(B.rec + 9); X.R.yy = c.rec_ld(B.rec + 10); X.R.yz = c.rec_ld(B.rec + 11);
+         X.R.zx = c.rec_ld(B.rec + 12); X.R.zy = c.rec_ld(B.rec + 13); X.R.zz = c.rec_ld(B.rec + 14);
+         X.p = v3<T>(c.rec_ld(B.rec + 15), c.rec_ld(B.rec + 16), c.rec_ld(B.rec + 17));
+         v = motion_to_child(X, vp) + vj;
+         const SvT<T> a1 = motion_to_child(X, ap) + cross_motion(v, vj);
+         const SvT<T> qdd = x - a1;
+         c.st_out(B.dof_off + 0, qdd.a.x); c.st_out(B.dof_off + 1, qdd.a.y); c.st_out(B.dof_off + 2, qdd.a.z);
+         c.st_out(B.dof_off + 3, qdd.l.x); c.st_out(B.dof_off + 4, qdd.l.y); c.st_out(B.dof_off + 5, qdd.l.z);
+         a = x;
+      }
+      if (w & MB_F_SAVE_STATE)
+      {
+         aux_st_sv<T>(c, B.aux, v);
+         aux_st_sv<T>(c, B.aux + 6, a);
+      }
+   }
+}
+
+// ======================================================================================== CRBA
+template <class T, class Ctx> MB_HD void aux_st_rbi(Ctx &c, int i, const RbiT<T> &I)
+{
+   c.aux_st(i + 0, I.I.xx); c.aux_st(i + 1, I.I.xy); c.aux_st(i + 2, I.I.xz); c.aux_st(i + 3, I.I.yy); c.aux_st(i + 4, I.I.yz); c.aux_st(i + 5, I.I.zz);
+   c.aux_st(i + 6, I.h.x); c.aux_st(i + 7, I.h.y); c.aux_st(i + 8, I.h.z); c.aux_st(i + 9, I.m);
+}
+template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
+{
+   RbiT<T> I;
+   I.I.xx = c.aux_ld(i + 0); I.I.xy = c.aux_ld(i + 1); I.I.xz = c.aux_ld(i + 2); I.I.yy = c.aux_ld(i + 3); I.I.yz = c.aux_ld(i + 4); I.I.zz = c.aux_ld(i + 5);
+   I.h = v3<T>(c.aux_ld(i + 6), c.aux_ld(i + 7), c.aux_ld(i + 8));
+   I.m = c.aux_ld(i + 9);
+   return I;
+}
+
+// write the mass-matrix entries coupling force column F (already expressed in body j's frame) of DoF
+// row `di` with the DoFs of body j, symmetrically (setSymmetricEntry, :704-705, :790-791)
+template <class T, class Ctx> MB_HD void crba_project(Ctx &c, const MbBody &Bj, int di, const SvT<T> &F)
+{
+   if (Bj.jtype == MB_REVOLUTE)
+   {
+      c.st_M(Bj.dof_off, di, F.a.z);
+      c.st_M(di, Bj.dof_off, F.a.z);
+   }
+   else if (Bj.jtype == MB_PRISMATIC)
+   {
+      c.st_M(Bj.dof_off, di, F.l.z);
+      c.st_M(di, Bj.dof_off, F.l.z);
+   }
+   else
+   {
+      const T e[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+      {
+         c.st_M(Bj.dof_off + r, di, e[r]);
+         c.st_M(di, Bj.dof_off + r, e[r]);
+      }
+   }
+}
+
+// walk from body i up to the root, transforming F and filling the off-diagonal blocks (:772-797)
+template <class T, class Ctx> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int i, int di, const XfT<T> &Xi, SvT<T> F)
+{
+   XfT<T> Xc = Xi;
+   int j = i;
+   while (P.body[j].parent >= 0)
+   {
+      F = force_to_parent(Xc, F);
+      j = P.body[j].parent;
+      const MbBody &Bj = P.body[j];
+      crba_project<T>(c, Bj, di, F);
+      if (Bj.parent >= 0)
+      {
+         JpT<T> jpj;
+         stk_ld_jp<T>(c, Bj.slot, Bj.jtype, jpj);
+         Xc = rebuild_transform<T>(Bj.jtype, c.cst(j), jpj);
+      }
+   }
+}
+
+template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
+{
+   RbiT<T> acc = RbiT<T>();
+   XfT<T> X;
+   JpT<T> jp;
+   X.R = M3T<T>();
+   X.p = v3<T>(0, 0, 0);
+   const int nops = P.nops;
+   for (int k = 0; k < nops; k++)
+   {
+      const uint32_t w = P.op[k];
+      const int i = MB_OP_BODY(w);
+      const MbBody &B = P.body[i];
+      const T *C = c.cst(i);
+      if (!(w & MB_OP_ASCEND))
+      {
+         X = joint_transform<T>(c, B, C, jp);
+         if (!(w & MB_F_LEAF))
+            stk_st_jp<T>(c, B.slot, B.jtype, jp);
+         continue;
+      }
+      if (!(w & MB_F_LEAF))
+      {
+         stk_ld_jp<T>(c, B.slot, B.jtype, jp);
+         X = rebuild_transform<T>(B.jtype, C, jp);
+      }
+      // composite inertia of the subtree, about this joint frame (:648-661)
+      RbiT<T> Ic = ld_rbi(C);
+      if (!(w & MB_F_LEAF))
+         Ic = Ic + acc;
+      // unit momenta F = Ic S (:663-667), diagonal block (:700-707), ancestors (:772-797)
+      if (B.jtype == MB_REVOLUTE)
+      {
+         SvT<T> F;
+         F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
+         F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
+         c.st_M(B.dof_off, B.dof_off, F.a.z);
+         crba_walk<T>(P, c, i, B.dof_off, X, F);
+      }
+      else if (B.jtype == MB_PRISMATIC)
+      {
+         SvT<T> F;
+         F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
+         F.l = v3<T>((T)0, (T)0, Ic.m);
+         c.st_M(B.dof_off, B.dof_off, F.l.z);
+         crba_walk<T>(P, c, i, B.dof_off, X, F);
+      }
+      else
+      {
+#pragma unroll 1
+         for (int col = 0; col < 6; col++)
+         {
+            SvT<T> e = sv_zero<T>();
+            if (col == 0) e.a.x = 1; else if (col == 1) e.a.y = 1; else if (col == 2) e.a.z = 1;
+            else if (col == 3) e.l.x = 1; else if (col == 4) e.l.y = 1; else e.l.z = 1;
+            const SvT<T> F = mul(Ic, e);
+            const int di = B.dof_off + col;
+            c.st_M(B.dof_off + 0, di, F.a.x); c.st_M(B.dof_off + 1, di, F.a.y); c.st_M(B.dof_off + 2, di, F.a.z);
+            c.st_M(B.dof_off + 3, di, F.l.x); c.st_M(B.dof_off + 4, di, F.l.y); c.st_M(B.dof_off + 5, di, F.l.z);
+            if (B.parent >= 0)
+               crba_walk<T>(P, c, i, di, X, F);
+         }
+      }
+      // entries coupling this joint with joints of unrelated branches are zero (massMatrix.zero(), :296)
+      for (int j = 0; j < i; j++)
+      {
+         const MbBody &Bj = P.body[j];
+         if (Bj.subtree_end > i)
+            continue; // ancestor: filled by the walk
+         for (int r = 0; r < Bj.ndof; r++)
+            for (int s = 0; s < B.ndof; s++)
+            {
+               c.st_M(Bj.dof_off + r, B.dof_off + s, (T)0);
+               c.st_M(B.dof_off + s, Bj.dof_off + r, (T)0);
+            }
+      }
+      if (!(w & MB_F_ROOT_PARENT))
+      {
+         const RbiT<T> K = rbi_to_parent(X, Ic); // childInertia.applyTransform(child.transformToParent) (:658)
+         const int pa_off = P.body[B.parent].aux;
+         if (w & MB_F_FIRST_CHILD)
+            acc = K;
+         else
+            acc = aux_ld_rbi<T>(c, pa_off) + K;
+         if (w & MB_F_STORE_ACC)
+            aux_st_rbi<T>(c, pa_off, acc);
+      }
+   }
+}
+} // namespace mb

@@ -1,0 +1,369 @@
+// api.cu -- the C ABI declared in include/mecano_b200.h.  Host-side plumbing only: argument checks,
+// handle lifetime, kernel planning, and the chunked host<->device pipeline behind the *_host entry
+// points.  There is deliberately no CPU compute path in this library: every compute entry point ends
+// in a kernel launch or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/mecano_b200.h"
+#include "flatten.h"
+#include "kernels.h"
+
+struct mecano_b200_handle
+{
+   int device = 0;
+   mb::FlatTree tree;
+   double *d_consts = nullptr;
+   double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
+   mb::LaunchPlan plan[3];
+   int variant = MECANO_B200_VARIANT_AUTO;
+   std::string error;
+   // host pipeline (lazy)
+   cudaStream_t streams[2] = {nullptr, nullptr};
+   cudaEvent_t done[2] = {nullptr, nullptr};
+   double *stage[2] = {nullptr, nullptr};
+   size_t stage_doubles = 0;
+   std::mutex mu;
+};
+
+namespace
+{
+std::string g_create_error;
+std::mutex g_create_mu;
+
+int fail(mecano_b200_handle *h, int code, const std::string &msg)
+{
+   if (h)
+      h->error = msg;
+   else
+   {
+      std::lock_guard<std::mutex> lk(g_create_mu);
+      g_create_error = msg;
+   }
+   return code;
+}
+
+int cuda_fail(mecano_b200_handle *h, cudaError_t e, const char *what)
+{
+   return fail(h, (int)e > 0 ? (int)e : 1, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define MB_CUDA(h, call)                                  \
+   do                                                     \
+   {                                                      \
+      cudaError_t e_ = (call);                            \
+      if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); \
+   } while (0)
+
+int check_batch(mecano_b200_handle *h, int64_t n, int64_t ld)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   if (n < 0) return fail(h, MECANO_B200_ERR_SHAPE, "n_states must be >= 0");
+   if (ld < n) return fail(h, MECANO_B200_ERR_SHAPE, "ld must be >= n_states");
+   return MECANO_B200_OK;
+}
+
+int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
+        double *out, uint32_t flags, cudaStream_t stream)
+{
+   if (h->variant == MECANO_B200_VARIANT_WARP)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the warp-per-state variant is not built in this version");
+   mb::KernelArgs a;
+   a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
+   a.consts = h->d_consts;
+   a.n = n; a.ld = ld;
+   a.grav[0] = h->gravity[0]; a.grav[1] = h->gravity[1]; a.grav[2] = h->gravity[2];
+   a.flags = flags;
+   a.nv = h->tree.nv;
+   MB_CUDA(h, mb::launch_thread_kernel(algo, h->tree.prog[algo], a, h->plan[algo], stream));
+   return MECANO_B200_OK;
+}
+
+int ensure_pipeline(mecano_b200_handle *h, size_t doubles_per_slot)
+{
+   for (int i = 0; i < 2; i++)
+   {
+      if (!h->streams[i]) MB_CUDA(h, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+      if (!h->done[i]) MB_CUDA(h, cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming));
+   }
+   if (doubles_per_slot > h->stage_doubles)
+   {
+      for (int i = 0; i < 2; i++)
+      {
+         if (h->stage[i]) cudaFree(h->stage[i]);
+         h->stage[i] = nullptr;
+      }
+      h->stage_doubles = 0;
+      for (int i = 0; i < 2; i++)
+         MB_CUDA(h, cudaMalloc(&h->stage[i], doubles_per_slot * sizeof(double)));
+      h->stage_doubles = doubles_per_slot;
+   }
+   return MECANO_B200_OK;
+}
+
+// rows x [s0, s0 + w) of a host matrix with leading dimension ld  <->  rows x w device matrix (ld = chunk)
+cudaError_t copy_rows(double *dst, size_t dpitch, const double *src, size_t spitch, size_t w, size_t rows, cudaMemcpyKind kind, cudaStream_t s)
+{
+   return cudaMemcpy2DAsync(dst, dpitch * sizeof(double), src, spitch * sizeof(double), w * sizeof(double), rows, kind, s);
+}
+
+// Host-pointer pipeline: two slots, each with its own stream; H2D of chunk k+1 overlaps the kernel and D2H of chunk k.
+int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
+             double *out, uint32_t flags)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (!q || !out || (algo != MB_CRBA && (!qd || !x)))
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   if (n == 0) return MECANO_B200_OK;
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_CUDA(h, cudaSetDevice(h->device));
+   const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
+   const bool state_major = algo == MB_CRBA && (flags & MECANO_B200_CRBA_STATE_MAJOR);
+   const size_t in_rows = algo == MB_CRBA ? nq : nq + 2 * nv + (fext ? 6 * nb : 0);
+   const size_t out_rows = algo == MB_CRBA ? nv * nv : nv;
+   // chunk: ~64 MB of rows per slot, at least 4096 states, multiple of 256
+   size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)(in_rows + out_rows));
+   chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
+   chunk = std::min<size_t>(chunk, ((size_t)n + 255) & ~(size_t)255);
+   rc = ensure_pipeline(h, (in_rows + out_rows) * chunk);
+   if (rc) return rc;
+   int slot = 0;
+   for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk, slot ^= 1)
+   {
+      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
+      cudaStream_t st = h->streams[slot];
+      double *dq = h->stage[slot], *dqd = dq + nq * chunk, *dx = dqd + nv * chunk, *df = dx + nv * chunk;
+      double *dout = h->stage[slot] + in_rows * chunk;
+      // the slot is reused every other chunk: stream order already serialises it
+      MB_CUDA(h, copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, st));
+      if (algo != MB_CRBA)
+      {
+         MB_CUDA(h, copy_rows(dqd, chunk, qd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
+         MB_CUDA(h, copy_rows(dx, chunk, x + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
+         if (fext) MB_CUDA(h, copy_rows(df, chunk, fext + s0, (size_t)ld, w, 6 * nb, cudaMemcpyHostToDevice, st));
+      }
+      else
+         dout = dq + nq * chunk;
+      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st);
+      if (rc) return rc;
+      if (state_major)
+         MB_CUDA(h, cudaMemcpyAsync(out + (size_t)s0 * nv * nv, dout, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+      else
+         MB_CUDA(h, copy_rows(out + s0, (size_t)ld, dout, chunk, w, out_rows, cudaMemcpyDeviceToHost, st));
+   }
+   MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
+   MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+   return MECANO_B200_OK;
+}
+} // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int mecano_b200_version(void) { return MECANO_B200_VERSION; }
+
+int mecano_b200_device_count(void)
+{
+   int n = 0;
+   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+   return n;
+}
+
+int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b200_handle **out)
+{
+   if (!out) return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "out handle pointer is NULL");
+   *out = nullptr;
+   mecano_b200_handle *h = new mecano_b200_handle();
+   std::string err;
+   int rc = mb::flatten_tree(desc, h->tree, err);
+   if (rc != MECANO_B200_OK)
+   {
+      delete h;
+      return fail(nullptr, rc, err);
+   }
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+   {
+      delete h;
+      return fail(nullptr, MECANO_B200_ERR_NO_DEVICE,
+                  std::string("no CUDA device available (this engine has no CPU fallback)") + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : ""));
+   }
+   if (device < 0 || device >= ndev)
+   {
+      delete h;
+      return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "device index out of range");
+   }
+   h->device = device;
+   auto bail = [&](cudaError_t ce, const char *what) {
+      std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
+      if (h->d_consts) cudaFree(h->d_consts);
+      delete h;
+      return fail(nullptr, (int)ce, m);
+   };
+   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+   const size_t bytes = h->tree.consts.size() * sizeof(double);
+   if ((e = cudaMalloc(&h->d_consts, bytes)) != cudaSuccess) return bail(e, "cudaMalloc(consts)");
+   if ((e = cudaMemcpy(h->d_consts, h->tree.consts.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(consts)");
+   for (int algo = 0; algo < 3; algo++)
+   {
+      bool fits = false;
+      if ((e = mb::plan_thread_kernel(algo, h->tree.prog[algo], false, h->plan[algo], &fits)) != cudaSuccess) return bail(e, "kernel planning");
+      if (!fits)
+      {
+         cudaFree(h->d_consts);
+         delete h;
+         return fail(nullptr, MECANO_B200_ERR_TOO_LARGE, "tree exceeds the compiled per-state work areas (branch nesting / depth too large)");
+      }
+   }
+   *out = h;
+   return MECANO_B200_OK;
+}
+
+void mecano_b200_destroy(mecano_b200_handle *h)
+{
+   if (!h) return;
+   cudaSetDevice(h->device);
+   for (int i = 0; i < 2; i++)
+   {
+      if (h->stage[i]) cudaFree(h->stage[i]);
+      if (h->done[i]) cudaEventDestroy(h->done[i]);
+      if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+   }
+   if (h->d_consts) cudaFree(h->d_consts);
+   delete h;
+}
+
+const char *mecano_b200_last_error(const mecano_b200_handle *h)
+{
+   if (h) return h->error.c_str();
+   return g_create_error.c_str();
+}
+
+int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double gz)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   h->gravity[0] = gx; h->gravity[1] = gy; h->gravity[2] = gz;
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_set_variant(mecano_b200_handle *h, int variant)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   if (variant != MECANO_B200_VARIANT_AUTO && variant != MECANO_B200_VARIANT_THREAD)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unsupported variant (the warp-per-state variant is not built in this version)");
+   h->variant = variant;
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_n_dofs(const mecano_b200_handle *h) { return h ? h->tree.nv : -1; }
+int mecano_b200_n_cfg(const mecano_b200_handle *h) { return h ? h->tree.nq : -1; }
+int mecano_b200_n_bodies(const mecano_b200_handle *h) { return h ? h->tree.nb : -1; }
+
+int mecano_b200_rnea(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd, const double *fext,
+                     double *tau, uint32_t flags, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (!q || !qd || !qdd || !tau) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream);
+}
+
+int mecano_b200_aba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau, const double *fext,
+                    double *qdd, uint32_t flags, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (!q || !qd || !tau || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   return run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, flags, (cudaStream_t)stream);
+}
+
+int mecano_b200_crba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (!q || !M) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   return run(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, M, layout, (cudaStream_t)stream);
+}
+
+int mecano_b200_rnea_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd,
+                          const double *fext, double *tau, uint32_t flags)
+{
+   return run_host(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags);
+}
+
+int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau,
+                         const double *fext, double *qdd, uint32_t flags)
+{
+   return run_host(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, flags);
+}
+
+int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout)
+{
+   return run_host(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, M, layout);
+}
+
+int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info)
+{
+   (void)n_states;
+   if (!h || !info || algo < 0 || algo > 2) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   const mb::LaunchPlan &p = h->plan[algo];
+   const MbProgram &P = h->tree.prog[algo];
+   std::memset(info, 0, sizeof *info);
+   info->variant = MECANO_B200_VARIANT_THREAD;
+   info->block_threads = p.block;
+   info->states_per_block = p.block;
+   info->regs_per_thread = p.regs;
+   info->static_smem_bytes = p.static_smem;
+   info->dynamic_smem_bytes = (int32_t)p.smem;
+   info->local_bytes_per_thread = p.local_bytes;
+   info->blocks_per_sm = p.blocks_per_sm;
+   cudaDeviceGetAttribute(&info->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+   info->stack_doubles = P.stack_doubles;
+   info->max_depth = P.max_depth;
+   const double nq = P.nq, nv = P.nv;
+   info->bytes_per_state = algo == MB_CRBA ? 8.0 * (nq + nv * nv) : 8.0 * (nq + 3.0 * nv);
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_measure_fp64_peak(int device, double *tflops)
+{
+   if (!tflops) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   cudaError_t e = cudaSetDevice(device);
+   if (e == cudaSuccess) e = mb::measure_fp64_peak(tflops);
+   return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
+int mecano_b200_measure_hbm_peak(int device, double *gbs)
+{
+   if (!gbs) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   cudaError_t e = cudaSetDevice(device);
+   if (e == cudaSuccess) e = mb::measure_hbm_peak(gbs);
+   return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
+int mecano_b200_host_alloc(void **ptr, int64_t bytes)
+{
+   if (!ptr || bytes < 0) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   cudaError_t e = cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault);
+   return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
+int mecano_b200_host_free(void *ptr)
+{
+   cudaError_t e = cudaFreeHost(ptr);
+   return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

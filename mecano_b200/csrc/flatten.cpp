@@ -1,0 +1,409 @@
+// flatten.cpp -- see flatten.h.  Plain host C++ (no CUDA).
+#include "flatten.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace mb
+{
+namespace
+{
+struct M3
+{
+   double m[9];
+};
+
+M3 identity()
+{
+   M3 r{};
+   r.m[0] = r.m[4] = r.m[8] = 1.0;
+   return r;
+}
+
+M3 mul(const M3 &a, const M3 &b)
+{
+   M3 r{};
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+         r.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+   return r;
+}
+
+M3 transpose(const M3 &a)
+{
+   M3 r{};
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+         r.m[3 * i + j] = a.m[3 * j + i];
+   return r;
+}
+
+void mulv(const M3 &a, const double *x, double *y)
+{
+   double t[3];
+   for (int i = 0; i < 3; i++)
+      t[i] = a.m[3 * i] * x[0] + a.m[3 * i + 1] * x[1] + a.m[3 * i + 2] * x[2];
+   y[0] = t[0];
+   y[1] = t[1];
+   y[2] = t[2];
+}
+
+// rotation Q with Q e_z = u (|u| = 1): shortest arc
+M3 align_z_to(const double *u)
+{
+   const double c = u[2];
+   if (c > 1.0 - 1e-14)
+      return identity();
+   if (c < -1.0 + 1e-14)
+   {
+      M3 r = identity();
+      r.m[4] = -1.0;
+      r.m[8] = -1.0; // rotation by pi about x
+      return r;
+   }
+   // v = e_z x u = (-uy, ux, 0); Q = I + [v]x + [v]x^2 / (1 + c)
+   const double vx = -u[1], vy = u[0];
+   const double k = 1.0 / (1.0 + c);
+   M3 K{};
+   K.m[0] = 0; K.m[1] = 0; K.m[2] = vy;
+   K.m[3] = 0; K.m[4] = 0; K.m[5] = -vx;
+   K.m[6] = -vy; K.m[7] = vx; K.m[8] = 0;
+   M3 K2 = mul(K, K);
+   M3 r = identity();
+   for (int i = 0; i < 9; i++)
+      r.m[i] += K.m[i] + k * K2.m[i];
+   return r;
+}
+
+int slot_size(int algo, int jtype)
+{
+   const int jp = mb_jp_size(jtype);
+   const int nd = jtype == MB_SIXDOF ? 6 : 1;
+   switch (algo)
+   {
+      case MB_RNEA: return 6 + jp;       // accumulated wrench + joint parameters
+      case MB_ABA: return 6 + jp + nd;   // twist + joint parameters + joint velocity
+      default: return jp;                // CRBA: joint parameters only
+   }
+}
+
+int aux_size(int algo)
+{
+   switch (algo)
+   {
+      case MB_RNEA: return 12; // twist + spatial acceleration of a branching body
+      case MB_ABA: return 27;  // articulated inertia (6 + 9 + 6) + bias wrench (6); reused for (v, a) in pass three
+      default: return 10;      // composite inertia (6 + 3 + 1)
+   }
+}
+
+int rec_size(int jtype) { return jtype == MB_SIXDOF ? 18 : 9; }
+} // namespace
+
+int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err)
+{
+   if (!d)
+   {
+      err = "tree description is NULL";
+      return MECANO_B200_ERR_INVALID_ARGUMENT;
+   }
+   if (d->struct_size != (int32_t)sizeof(mecano_b200_tree_desc))
+   {
+      err = "mecano_b200_tree_desc.struct_size mismatch (ABI version)";
+      return MECANO_B200_ERR_INVALID_ARGUMENT;
+   }
+   const int nb = d->n_bodies;
+   if (nb <= 0)
+   {
+      err = "tree has no joints";
+      return MECANO_B200_ERR_INVALID_ARGUMENT;
+   }
+   if (nb > MB_MAX_BODIES)
+   {
+      err = "tree has more than " + std::to_string(MB_MAX_BODIES) + " bodies";
+      return MECANO_B200_ERR_TOO_LARGE;
+   }
+   if (!d->parent || !d->joint_type || !d->axis || !d->offset_rot || !d->offset_pos || !d->com_rot || !d->com_pos || !d->inertia
+       || !d->mass || !d->dof_offset || !d->cfg_offset)
+   {
+      err = "tree description has a NULL table";
+      return MECANO_B200_ERR_INVALID_ARGUMENT;
+   }
+
+   // ---- validation
+   int nv = 0, nq = 0;
+   for (int b = 0; b < nb; b++)
+   {
+      const int jt = d->joint_type[b];
+      if (jt != MECANO_B200_REVOLUTE && jt != MECANO_B200_PRISMATIC && jt != MECANO_B200_SIXDOF)
+      {
+         err = "body " + std::to_string(b) + ": unsupported joint type " + std::to_string(jt)
+               + " (only RevoluteJoint, PrismaticJoint, SixDoFJoint; no CPU fallback)";
+         return MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY;
+      }
+      if (d->parent[b] < -1 || d->parent[b] >= b)
+      {
+         err = "body " + std::to_string(b) + ": parent index must satisfy -1 <= parent < body (kinematic loops are not supported)";
+         return MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY;
+      }
+      nv += jt == MECANO_B200_SIXDOF ? 6 : 1;
+      nq += jt == MECANO_B200_SIXDOF ? 7 : 1;
+      if (jt != MECANO_B200_SIXDOF)
+      {
+         const double *u = d->axis + 3 * b;
+         const double n = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+         if (!(n > 1e-12))
+         {
+            err = "body " + std::to_string(b) + ": zero joint axis";
+            return MECANO_B200_ERR_INVALID_ARGUMENT;
+         }
+      }
+      const double *J = d->inertia + 9 * b;
+      const double scale = std::fabs(J[0]) + std::fabs(J[4]) + std::fabs(J[8]) + 1e-300;
+      if (std::fabs(J[1] - J[3]) > 1e-9 * scale || std::fabs(J[2] - J[6]) > 1e-9 * scale || std::fabs(J[5] - J[7]) > 1e-9 * scale)
+      {
+         err = "body " + std::to_string(b) + ": moment of inertia is not symmetric";
+         return MECANO_B200_ERR_INVALID_ARGUMENT;
+      }
+   }
+   if (nv != d->n_dofs || nq != d->n_cfg)
+   {
+      err = "n_dofs / n_cfg do not match the joint types";
+      return MECANO_B200_ERR_SHAPE;
+   }
+   {
+      std::vector<char> used_v(nv, 0), used_q(nq, 0);
+      for (int b = 0; b < nb; b++)
+      {
+         const int nd = d->joint_type[b] == MECANO_B200_SIXDOF ? 6 : 1, nc = d->joint_type[b] == MECANO_B200_SIXDOF ? 7 : 1;
+         if (d->dof_offset[b] < 0 || d->dof_offset[b] + nd > nv || d->cfg_offset[b] < 0 || d->cfg_offset[b] + nc > nq)
+         {
+            err = "body " + std::to_string(b) + ": dof/cfg offset out of range";
+            return MECANO_B200_ERR_SHAPE;
+         }
+         for (int k = 0; k < nd; k++)
+            if (used_v[d->dof_offset[b] + k]++)
+            {
+               err = "dof offsets overlap";
+               return MECANO_B200_ERR_SHAPE;
+            }
+         for (int k = 0; k < nc; k++)
+            if (used_q[d->cfg_offset[b] + k]++)
+            {
+               err = "cfg offsets overlap";
+               return MECANO_B200_ERR_SHAPE;
+            }
+      }
+   }
+
+   // ---- depth-first pre-order, children visited in increasing DoF row (Mecano's insertion order,
+   //      JointIterator.java:153-162 / JointMatrixIndexProvider.java:77-101)
+   std::vector<std::vector<int>> children(nb + 1);
+   for (int b = 0; b < nb; b++)
+      children[d->parent[b] + 1].push_back(b);
+   for (auto &c : children)
+      std::sort(c.begin(), c.end(), [&](int a, int b) { return d->dof_offset[a] < d->dof_offset[b]; });
+   std::vector<int> order; // internal -> caller index
+   order.reserve(nb);
+   {
+      std::vector<int> stack(children[0].rbegin(), children[0].rend());
+      while (!stack.empty())
+      {
+         const int b = stack.back();
+         stack.pop_back();
+         order.push_back(b);
+         for (auto it = children[b + 1].rbegin(); it != children[b + 1].rend(); ++it)
+            stack.push_back(*it);
+      }
+   }
+   out = FlatTree();
+   out.nb = nb;
+   out.nv = nv;
+   out.nq = nq;
+   out.internal_of.assign(nb, -1);
+   for (int i = 0; i < nb; i++)
+      out.internal_of[order[i]] = i;
+
+   // ---- canonical frames and constant records
+   std::vector<M3> Q(nb);
+   out.consts.assign((size_t)nb * MB_CONST_STRIDE, 0.0);
+   std::vector<int> parent_i(nb), nchild(nb, 0), depth(nb, 0), subtree_end(nb, 0);
+   for (int i = 0; i < nb; i++)
+   {
+      const int b = order[i];
+      const int pb = d->parent[b];
+      parent_i[i] = pb < 0 ? -1 : out.internal_of[pb];
+      if (parent_i[i] >= 0)
+      {
+         nchild[parent_i[i]]++;
+         depth[i] = depth[parent_i[i]] + 1;
+      }
+      out.max_depth = std::max(out.max_depth, depth[i] + 1);
+
+      double u[3] = {0, 0, 1};
+      if (d->joint_type[b] != MECANO_B200_SIXDOF)
+      {
+         const double *a = d->axis + 3 * b;
+         const double n = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+         u[0] = a[0] / n; u[1] = a[1] / n; u[2] = a[2] / n;
+         Q[i] = align_z_to(u);
+      }
+      else
+         Q[i] = identity();
+
+      M3 RT, Rc;
+      std::memcpy(RT.m, d->offset_rot + 9 * b, sizeof RT.m);
+      std::memcpy(Rc.m, d->com_rot + 9 * b, sizeof Rc.m);
+      const M3 QpT = parent_i[i] < 0 ? identity() : transpose(Q[parent_i[i]]);
+      const M3 R = mul(mul(QpT, RT), Q[i]);
+      double p[3];
+      mulv(QpT, d->offset_pos + 3 * b, p);
+      const M3 QiT = transpose(Q[i]);
+      const M3 E = mul(QiT, Rc);
+      double c[3];
+      mulv(QiT, d->com_pos + 3 * b, c);
+      M3 J;
+      std::memcpy(J.m, d->inertia + 9 * b, sizeof J.m);
+      // symmetrise (validated above)
+      J.m[3] = J.m[1] = 0.5 * (J.m[1] + J.m[3]);
+      J.m[6] = J.m[2] = 0.5 * (J.m[2] + J.m[6]);
+      J.m[7] = J.m[5] = 0.5 * (J.m[5] + J.m[7]);
+      const M3 Ib = mul(mul(E, J), transpose(E));
+      const double m = d->mass[b];
+      const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+      double *rec = out.consts.data() + (size_t)i * MB_CONST_STRIDE;
+      std::memcpy(rec + MB_C_R, R.m, sizeof R.m);
+      std::memcpy(rec + MB_C_P, p, sizeof p);
+      rec[MB_C_I + 0] = Ib.m[0] + m * (cc - c[0] * c[0]);
+      rec[MB_C_I + 1] = 0.5 * (Ib.m[1] + Ib.m[3]) - m * c[0] * c[1];
+      rec[MB_C_I + 2] = 0.5 * (Ib.m[2] + Ib.m[6]) - m * c[0] * c[2];
+      rec[MB_C_I + 3] = Ib.m[4] + m * (cc - c[1] * c[1]);
+      rec[MB_C_I + 4] = 0.5 * (Ib.m[5] + Ib.m[7]) - m * c[1] * c[2];
+      rec[MB_C_I + 5] = Ib.m[8] + m * (cc - c[2] * c[2]);
+      rec[MB_C_H + 0] = m * c[0];
+      rec[MB_C_H + 1] = m * c[1];
+      rec[MB_C_H + 2] = m * c[2];
+      rec[MB_C_M] = m;
+      std::memcpy(rec + MB_C_E, E.m, sizeof E.m);
+      std::memcpy(rec + MB_C_C, c, sizeof c);
+   }
+   for (int i = nb - 1; i >= 0; i--)
+   {
+      if (subtree_end[i] == 0)
+         subtree_end[i] = i + 1;
+      if (parent_i[i] >= 0)
+         subtree_end[parent_i[i]] = std::max(subtree_end[parent_i[i]], subtree_end[i]);
+   }
+
+   // ---- level tables (warp-per-state variant)
+   out.level_of = depth;
+   out.level_order.resize(nb);
+   for (int i = 0; i < nb; i++)
+      out.level_order[i] = i;
+   std::stable_sort(out.level_order.begin(), out.level_order.end(), [&](int a, int b) { return depth[a] < depth[b]; });
+   out.level_start.assign(out.max_depth + 1, 0);
+   for (int i = 0; i < nb; i++)
+      out.level_start[depth[i] + 1]++;
+   for (int l = 0; l < out.max_depth; l++)
+      out.level_start[l + 1] += out.level_start[l];
+
+   // ---- traversal programs
+   for (int algo = 0; algo < 3; algo++)
+   {
+      MbProgram &P = out.prog[algo];
+      std::memset(&P, 0, sizeof P);
+      P.nb = nb;
+      P.nv = nv;
+      P.nq = nq;
+      P.max_depth = out.max_depth;
+      int rec = 0;
+      for (int i = 0; i < nb; i++)
+      {
+         MbBody &B = P.body[i];
+         const int b = order[i];
+         B.parent = parent_i[i];
+         B.jtype = d->joint_type[b];
+         B.dof_off = d->dof_offset[b];
+         B.cfg_off = d->cfg_offset[b];
+         B.subtree_end = subtree_end[i];
+         B.ext_index = b;
+         B.depth = depth[i];
+         B.ndof = B.jtype == MB_SIXDOF ? 6 : 1;
+         // stack slot: leaves keep everything in registers; others stack up along the current path
+         const int pslot = parent_i[i] < 0 ? 0 : P.body[parent_i[i]].slot + (nchild[parent_i[i]] > 0 ? slot_size(algo, P.body[parent_i[i]].jtype) : 0);
+         B.slot = pslot;
+         if (nchild[i] > 0)
+            P.stack_doubles = std::max(P.stack_doubles, B.slot + slot_size(algo, B.jtype));
+         // branch save area, nested like a stack of branching ancestors
+         int paux = 0;
+         for (int a = parent_i[i]; a >= 0; a = parent_i[a])
+            if (nchild[a] >= 2)
+               paux += aux_size(algo);
+         B.aux = nchild[i] >= 2 ? paux : -1;
+         if (nchild[i] >= 2)
+            P.aux_doubles = std::max(P.aux_doubles, paux + aux_size(algo));
+         B.rec = rec;
+         rec += rec_size(B.jtype);
+      }
+      P.rec_doubles = algo == MB_ABA ? rec : 0;
+
+      // ops: iterative DFS emitting DESCEND on entry and ASCEND on exit
+      int nops = 0;
+      std::vector<int> path;            // bodies whose subtree is open
+      std::vector<int> done_children(nb, 0);
+      int prev_descend = -2;            // body of the previous op if it was a DESCEND, else -2
+      for (int i = 0; i < nb; i++)
+      {
+         // close finished subtrees
+         while (!path.empty() && subtree_end[path.back()] <= i)
+         {
+            const int c = path.back();
+            path.pop_back();
+            uint32_t w = MB_OP_ASCEND | ((uint32_t)c << 8);
+            if (nchild[c] == 0) w |= MB_F_LEAF;
+            const int p = parent_i[c];
+            if (p < 0)
+               w |= MB_F_ROOT_PARENT;
+            else
+            {
+               if (done_children[p] == 0) w |= MB_F_FIRST_CHILD;
+               done_children[p]++;
+               if (done_children[p] < nchild[p]) w |= MB_F_STORE_ACC;
+            }
+            P.op[nops++] = w;
+            prev_descend = -2;
+         }
+         uint32_t w = ((uint32_t)i << 8);
+         if (nchild[i] == 0) w |= MB_F_LEAF;
+         if (nchild[i] >= 2) w |= MB_F_SAVE_STATE;
+         if (parent_i[i] < 0)
+            w |= MB_F_ROOT_PARENT;
+         else if (prev_descend != parent_i[i])
+            w |= MB_F_LOAD_PARENT;
+         P.op[nops++] = w;
+         prev_descend = i;
+         path.push_back(i);
+      }
+      while (!path.empty())
+      {
+         const int c = path.back();
+         path.pop_back();
+         uint32_t w = MB_OP_ASCEND | ((uint32_t)c << 8);
+         if (nchild[c] == 0) w |= MB_F_LEAF;
+         const int p = parent_i[c];
+         if (p < 0)
+            w |= MB_F_ROOT_PARENT;
+         else
+         {
+            if (done_children[p] == 0) w |= MB_F_FIRST_CHILD;
+            done_children[p]++;
+            if (done_children[p] < nchild[p]) w |= MB_F_STORE_ACC;
+         }
+         P.op[nops++] = w;
+      }
+      P.nops = nops;
+   }
+   return MECANO_B200_OK;
+}
+} // namespace mb

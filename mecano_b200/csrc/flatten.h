@@ -1,0 +1,27 @@
+// flatten.h -- host-side construction of the kernel tables from a mecano_b200_tree_desc.
+// The analogue of Mecano's calculator constructors mirroring the body tree into RecursionStep objects
+// (M/algorithms/InverseDynamicsCalculator.java:253-282, ForwardDynamicsCalculator.java:198-222,
+//  CompositeRigidBodyMassMatrixCalculator.java:242-266), done once per handle.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/mecano_b200.h"
+#include "program.h"
+
+namespace mb
+{
+struct FlatTree
+{
+   int nb = 0, nv = 0, nq = 0, max_depth = 0;
+   std::vector<double> consts;      // [nb][MB_CONST_STRIDE], internal (DFS) order
+   std::vector<int> internal_of;    // caller's body index -> internal index
+   std::vector<int> level_of;       // internal index -> tree level (0 = attached to the root body)
+   std::vector<int> level_order;    // internal indices sorted by level (for the warp-per-state variant)
+   std::vector<int> level_start;    // [n_levels + 1] into level_order
+   MbProgram prog[3];               // MB_RNEA, MB_ABA, MB_CRBA
+};
+
+// Returns MECANO_B200_OK or a negative error code; `err` receives the message.
+int flatten_tree(const mecano_b200_tree_desc *desc, FlatTree &out, std::string &err);
+} // namespace mb

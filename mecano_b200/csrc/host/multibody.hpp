@@ -1,0 +1,479 @@
+// multibody.hpp -- host-side mirror (C++) of the part of Mecano's model API that the hot path needs:
+// RigidBody, RevoluteJoint, PrismaticJoint, SixDoFJoint, MultiBodySystem + JointMatrixIndexProvider, the
+// flattener producing the level-ordered tables of include/mecano_b200.h, and the synthetic generators of
+// MultiBodySystemRandomTools.  ("M/" = /root/reference/src/main/java/us/ihmc/mecano/)
+//
+//   RigidBody          M/multiBodySystem/RigidBody.java:79-182
+//   RevoluteJoint      M/multiBodySystem/RevoluteJoint.java:42-74
+//   PrismaticJoint     M/multiBodySystem/PrismaticJoint.java:34-51
+//   SixDoFJoint        M/multiBodySystem/SixDoFJoint.java:52-70
+//   MultiBodySystem    M/multiBodySystem/interfaces/MultiBodySystemBasics.java:76-142, MultiBodySystemReadOnly.java:167-205
+//   index provider     M/multiBodySystem/interfaces/JointMatrixIndexProvider.java:71-123
+//   joint order        M/multiBodySystem/iterators/JointIterator.java:130-177 (depth-first pre-order, children in insertion order)
+//
+// Differences that follow from batching: joints hold no state (q, qd, qdd, tau are N-column matrices handed to
+// the calculators) and there is no ReferenceFrame tree (the kernels rebuild frames from q for every state).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/mecano_b200.h"
+
+namespace mecano
+{
+struct Vector3D
+{
+   double x = 0, y = 0, z = 0;
+};
+
+struct Matrix3D
+{
+   double m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; // row-major
+   static Matrix3D diagonal(double a, double b, double c)
+   {
+      Matrix3D r;
+      r.m[0] = a; r.m[4] = b; r.m[8] = c;
+      return r;
+   }
+};
+
+struct RigidBodyTransform
+{
+   Matrix3D rotation;
+   Vector3D translation;
+   RigidBodyTransform() = default;
+   RigidBodyTransform(const Matrix3D &R, const Vector3D &t) : rotation(R), translation(t) {}
+   explicit RigidBodyTransform(const Vector3D &t) : translation(t) {}
+};
+
+class ScrewTheoryException : public std::runtime_error // M/exceptions/ScrewTheoryException.java
+{
+ public:
+   using std::runtime_error::runtime_error;
+};
+
+class RigidBody;
+
+enum class JointType { Revolute = MECANO_B200_REVOLUTE, Prismatic = MECANO_B200_PRISMATIC, SixDoF = MECANO_B200_SIXDOF };
+
+class Joint
+{
+ public:
+   virtual ~Joint() = default;
+   const std::string &getName() const { return name_; }
+   RigidBody *getPredecessor() const { return predecessor_; }
+   RigidBody *getSuccessor() const { return successor_; }
+   JointType getType() const { return type_; }
+   virtual int getDegreesOfFreedom() const = 0;
+   virtual int getConfigurationMatrixSize() const = 0;
+   const Vector3D &getJointAxis() const { return axis_; }
+   // transform from frameBeforeJoint to the predecessor's frameAfterJoint (identity when constructed with null)
+   const RigidBodyTransform &getTransformToParent() const { return transformToParent_; }
+   void setSuccessor(RigidBody *successor) { successor_ = successor; }
+
+ protected:
+   Joint(std::string name, RigidBody *predecessor, const RigidBodyTransform *transformToParent, JointType type);
+   std::string name_;
+   RigidBody *predecessor_;
+   RigidBody *successor_ = nullptr;
+   RigidBodyTransform transformToParent_;
+   JointType type_;
+   Vector3D axis_{0, 0, 1};
+};
+
+class RigidBody
+{
+ public:
+   // root body ("elevator"), RigidBody.java:79-82
+   explicit RigidBody(std::string name) : name_(std::move(name)) {}
+   // RigidBody(name, parentJoint, Ixx, Iyy, Izz, mass, centerOfMassOffset), RigidBody.java:123-128
+   RigidBody(std::string name, Joint *parentJoint, double Ixx, double Iyy, double Izz, double mass, const Vector3D &centerOfMassOffset)
+       : RigidBody(std::move(name), parentJoint, Matrix3D::diagonal(Ixx, Iyy, Izz), mass, RigidBodyTransform(centerOfMassOffset))
+   {
+   }
+   // RigidBody(name, parentJoint, momentOfInertia, mass, centerOfMassOffset), RigidBody.java:141-146
+   RigidBody(std::string name, Joint *parentJoint, const Matrix3D &momentOfInertia, double mass, const Vector3D &centerOfMassOffset)
+       : RigidBody(std::move(name), parentJoint, momentOfInertia, mass, RigidBodyTransform(centerOfMassOffset))
+   {
+   }
+   // RigidBody(name, parentJoint, momentOfInertia, mass, inertiaPose), RigidBody.java:163-168
+   RigidBody(std::string name, Joint *parentJoint, const Matrix3D &momentOfInertia, double mass, const RigidBodyTransform &inertiaPose)
+       : name_(std::move(name)), parentJoint_(parentJoint), momentOfInertia_(momentOfInertia), mass_(mass), inertiaPose_(inertiaPose)
+   {
+      if (!parentJoint)
+         throw std::invalid_argument("parentJoint can not be null");
+      parentJoint->setSuccessor(this);
+   }
+   const std::string &getName() const { return name_; }
+   bool isRootBody() const { return parentJoint_ == nullptr; }
+   Joint *getParentJoint() const { return parentJoint_; }
+   const std::vector<Joint *> &getChildrenJoints() const { return children_; }
+   void addChildJoint(Joint *j) { children_.push_back(j); }
+   const Matrix3D &getMomentOfInertia() const { return momentOfInertia_; }
+   double getMass() const { return mass_; }
+   const RigidBodyTransform &getInertiaPose() const { return inertiaPose_; }
+
+ private:
+   std::string name_;
+   Joint *parentJoint_ = nullptr;
+   std::vector<Joint *> children_;
+   Matrix3D momentOfInertia_;
+   double mass_ = 0;
+   RigidBodyTransform inertiaPose_;
+};
+
+inline Joint::Joint(std::string name, RigidBody *predecessor, const RigidBodyTransform *transformToParent, JointType type)
+    : name_(std::move(name)), predecessor_(predecessor), type_(type)
+{
+   if (!predecessor)
+      throw std::invalid_argument("predecessor can not be null");
+   if (transformToParent)
+      transformToParent_ = *transformToParent;
+   predecessor->addChildJoint(this);
+}
+
+class OneDoFJoint : public Joint
+{
+ public:
+   int getDegreesOfFreedom() const override { return 1; }
+   int getConfigurationMatrixSize() const override { return 1; }
+
+ protected:
+   OneDoFJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform *transformToParent, const Vector3D &axis, JointType type)
+       : Joint(std::move(name), predecessor, transformToParent, type)
+   {
+      const double n = std::sqrt(axis.x * axis.x + axis.y * axis.y + axis.z * axis.z);
+      if (!(n > 0))
+         throw std::invalid_argument("joint axis can not be zero");
+      axis_ = Vector3D{axis.x / n, axis.y / n, axis.z / n};
+   }
+};
+
+class RevoluteJoint : public OneDoFJoint
+{
+ public:
+   RevoluteJoint(std::string name, RigidBody *predecessor, const Vector3D &jointAxis)
+       : OneDoFJoint(std::move(name), predecessor, nullptr, jointAxis, JointType::Revolute) {}
+   RevoluteJoint(std::string name, RigidBody *predecessor, const Vector3D &jointOffset, const Vector3D &jointAxis)
+       : RevoluteJoint(std::move(name), predecessor, RigidBodyTransform(jointOffset), jointAxis) {}
+   RevoluteJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform &transformToParent, const Vector3D &jointAxis)
+       : OneDoFJoint(std::move(name), predecessor, &transformToParent, jointAxis, JointType::Revolute) {}
+};
+
+class PrismaticJoint : public OneDoFJoint
+{
+ public:
+   PrismaticJoint(std::string name, RigidBody *predecessor, const Vector3D &jointOffset, const Vector3D &jointAxis)
+       : PrismaticJoint(std::move(name), predecessor, RigidBodyTransform(jointOffset), jointAxis) {}
+   PrismaticJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform &transformToParent, const Vector3D &jointAxis)
+       : OneDoFJoint(std::move(name), predecessor, &transformToParent, jointAxis, JointType::Prismatic) {}
+};
+
+class SixDoFJoint : public Joint
+{
+ public:
+   SixDoFJoint(std::string name, RigidBody *predecessor) : Joint(std::move(name), predecessor, nullptr, JointType::SixDoF) {}
+   SixDoFJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform &transformToParent)
+       : Joint(std::move(name), predecessor, &transformToParent, JointType::SixDoF) {}
+   int getDegreesOfFreedom() const override { return 6; }
+   int getConfigurationMatrixSize() const override { return 7; }
+};
+
+// MultiBodySystemBasics.toMultiBodySystemBasics(rootBody) + JointMatrixIndexProvider
+class MultiBodySystem
+{
+ public:
+   static MultiBodySystem toMultiBodySystemBasics(RigidBody *rootBody)
+   {
+      if (!rootBody)
+         throw std::invalid_argument("rootBody can not be null");
+      MultiBodySystem s;
+      s.root_ = rootBody;
+      // SubtreeStreams.fromChildren: depth-first pre-order (JointIterator.java:153-162)
+      std::vector<Joint *> stack(rootBody->getChildrenJoints().rbegin(), rootBody->getChildrenJoints().rend());
+      while (!stack.empty())
+      {
+         Joint *j = stack.back();
+         stack.pop_back();
+         if (!j->getSuccessor())
+            throw ScrewTheoryException("joint " + j->getName() + " has no successor");
+         s.dofIndex_.push_back(s.nDoFs_);
+         s.cfgIndex_.push_back(s.nCfg_);
+         s.nDoFs_ += j->getDegreesOfFreedom();
+         s.nCfg_ += j->getConfigurationMatrixSize();
+         s.joints_.push_back(j);
+         const auto &ch = j->getSuccessor()->getChildrenJoints();
+         for (auto it = ch.rbegin(); it != ch.rend(); ++it)
+            stack.push_back(*it);
+      }
+      return s;
+   }
+   RigidBody *getRootBody() const { return root_; }
+   const std::vector<Joint *> &getJointsToConsider() const { return joints_; } // == getIndexedJointsInOrder()
+   int getNumberOfDoFs() const { return nDoFs_; }
+   int getConfigurationMatrixSize() const { return nCfg_; }
+   int indexOf(const Joint *j) const
+   {
+      for (size_t i = 0; i < joints_.size(); i++)
+         if (joints_[i] == j)
+            return (int)i;
+      return -1;
+   }
+   // JointMatrixIndexProvider.getJointDoFIndices / getJointConfigurationIndices: first row of the joint
+   int getJointDoFIndex(const Joint *j) const { return dofIndex_.at((size_t)indexOf(j)); }
+   int getJointConfigurationIndex(const Joint *j) const { return cfgIndex_.at((size_t)indexOf(j)); }
+   int dofIndexAt(size_t i) const { return dofIndex_[i]; }
+   int cfgIndexAt(size_t i) const { return cfgIndex_[i]; }
+
+ private:
+   RigidBody *root_ = nullptr;
+   std::vector<Joint *> joints_;
+   std::vector<int> dofIndex_, cfgIndex_;
+   int nDoFs_ = 0, nCfg_ = 0;
+};
+
+// Level-ordered parent / joint-type / axis / inertia / transform tables: the argument of mecano_b200_create.
+struct FlatTables
+{
+   std::vector<int32_t> level_start, parent, joint_type, dof_offset, cfg_offset;
+   std::vector<double> axis, offset_rot, offset_pos, com_rot, com_pos, inertia, mass;
+   std::vector<int> body_of_joint; // DFS joint index -> row in the tables
+   mecano_b200_tree_desc desc{};
+
+   static FlatTables flatten(const MultiBodySystem &sys)
+   {
+      FlatTables f;
+      const auto &joints = sys.getJointsToConsider();
+      const int nb = (int)joints.size();
+      std::vector<int> depth(nb), parent_dfs(nb);
+      int nlev = 0;
+      for (int i = 0; i < nb; i++)
+      {
+         RigidBody *pred = joints[i]->getPredecessor();
+         parent_dfs[i] = pred->isRootBody() ? -1 : sys.indexOf(pred->getParentJoint());
+         depth[i] = parent_dfs[i] < 0 ? 0 : depth[parent_dfs[i]] + 1;
+         nlev = std::max(nlev, depth[i] + 1);
+      }
+      std::vector<int> order; // table row -> DFS joint index, level by level
+      f.level_start.assign(nlev + 1, 0);
+      for (int l = 0; l < nlev; l++)
+      {
+         f.level_start[l] = (int)order.size();
+         for (int i = 0; i < nb; i++)
+            if (depth[i] == l)
+               order.push_back(i);
+      }
+      f.level_start[nlev] = nb;
+      f.body_of_joint.assign(nb, -1);
+      for (int r = 0; r < nb; r++)
+         f.body_of_joint[order[r]] = r;
+      for (int r = 0; r < nb; r++)
+      {
+         const int i = order[r];
+         const Joint *j = joints[i];
+         const RigidBody *b = j->getSuccessor();
+         f.parent.push_back(parent_dfs[i] < 0 ? -1 : f.body_of_joint[parent_dfs[i]]);
+         f.joint_type.push_back((int)j->getType());
+         f.dof_offset.push_back(sys.dofIndexAt(i));
+         f.cfg_offset.push_back(sys.cfgIndexAt(i));
+         f.axis.insert(f.axis.end(), {j->getJointAxis().x, j->getJointAxis().y, j->getJointAxis().z});
+         const RigidBodyTransform &T = j->getTransformToParent();
+         f.offset_rot.insert(f.offset_rot.end(), T.rotation.m, T.rotation.m + 9);
+         f.offset_pos.insert(f.offset_pos.end(), {T.translation.x, T.translation.y, T.translation.z});
+         const RigidBodyTransform &P = b->getInertiaPose();
+         f.com_rot.insert(f.com_rot.end(), P.rotation.m, P.rotation.m + 9);
+         f.com_pos.insert(f.com_pos.end(), {P.translation.x, P.translation.y, P.translation.z});
+         f.inertia.insert(f.inertia.end(), b->getMomentOfInertia().m, b->getMomentOfInertia().m + 9);
+         f.mass.push_back(b->getMass());
+      }
+      f.bind(sys.getNumberOfDoFs(), sys.getConfigurationMatrixSize());
+      return f;
+   }
+
+   void bind(int ndofs, int ncfg)
+   {
+      desc.struct_size = (int32_t)sizeof(mecano_b200_tree_desc);
+      desc.n_bodies = (int32_t)parent.size();
+      desc.n_dofs = ndofs;
+      desc.n_cfg = ncfg;
+      desc.n_levels = (int32_t)level_start.size() - 1;
+      desc.level_start = level_start.data();
+      desc.parent = parent.data();
+      desc.joint_type = joint_type.data();
+      desc.axis = axis.data();
+      desc.offset_rot = offset_rot.data();
+      desc.offset_pos = offset_pos.data();
+      desc.com_rot = com_rot.data();
+      desc.com_pos = com_pos.data();
+      desc.inertia = inertia.data();
+      desc.mass = mass.data();
+      desc.dof_offset = dof_offset.data();
+      desc.cfg_offset = cfg_offset.data();
+   }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Synthetic generators with Mecano's distributions (MultiBodySystemRandomTools.java:483-496, 908-923,
+// 1211-1231, 1365-1371; MecanoRandomTools.java:623-647).  java.util.Random / Euclid's random tools are not
+// reproducible here, so a fixed 64-bit generator (splitmix64) is used and the seed is reported by the bench.
+class Random
+{
+ public:
+   explicit Random(uint64_t seed) : s_(seed) {}
+   uint64_t nextLong()
+   {
+      uint64_t z = (s_ += 0x9e3779b97f4a7c15ull);
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      return z ^ (z >> 31);
+   }
+   double nextDouble() { return (double)(nextLong() >> 11) * (1.0 / 9007199254740992.0); }
+   double nextDouble(double lo, double hi) { return lo + (hi - lo) * nextDouble(); }
+   int nextInt(int bound) { return (int)(nextLong() % (uint64_t)bound); }
+   double nextGaussian()
+   {
+      const double u1 = 1.0 - nextDouble(), u2 = nextDouble();
+      return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2);
+   }
+
+ private:
+   uint64_t s_;
+};
+
+// Owns the joints and bodies of one generated (or hand-built) system.
+class MultiBodyArena
+{
+ public:
+   RigidBody *newRootBody(const std::string &name = "elevator")
+   {
+      bodies_.push_back(std::make_unique<RigidBody>(name));
+      return bodies_.back().get();
+   }
+   template <class J, class... A> J *newJoint(A &&...a)
+   {
+      auto p = std::make_unique<J>(std::forward<A>(a)...);
+      J *raw = p.get();
+      joints_.push_back(std::move(p));
+      return raw;
+   }
+   template <class... A> RigidBody *newRigidBody(A &&...a)
+   {
+      bodies_.push_back(std::make_unique<RigidBody>(std::forward<A>(a)...));
+      return bodies_.back().get();
+   }
+
+ private:
+   std::vector<std::unique_ptr<RigidBody>> bodies_;
+   std::vector<std::unique_ptr<Joint>> joints_;
+};
+
+namespace MultiBodySystemRandomTools
+{
+inline Vector3D nextVector3D(Random &r) { return Vector3D{r.nextDouble(-1, 1), r.nextDouble(-1, 1), r.nextDouble(-1, 1)}; }
+inline Vector3D nextUnitVector3D(Random &r)
+{
+   double x, y, z, n;
+   do
+   {
+      x = r.nextGaussian(); y = r.nextGaussian(); z = r.nextGaussian();
+      n = std::sqrt(x * x + y * y + z * z);
+   } while (n < 1e-6);
+   return Vector3D{x / n, y / n, z / n};
+}
+inline Matrix3D nextRotationMatrix(Random &r)
+{
+   double q[4], n = 0;
+   for (double &v : q) { v = r.nextGaussian(); n += v * v; }
+   n = std::sqrt(n);
+   const double x = q[0] / n, y = q[1] / n, z = q[2] / n, s = q[3] / n;
+   Matrix3D R;
+   R.m[0] = 1 - 2 * (y * y + z * z); R.m[1] = 2 * (x * y - s * z); R.m[2] = 2 * (x * z + s * y);
+   R.m[3] = 2 * (x * y + s * z); R.m[4] = 1 - 2 * (x * x + z * z); R.m[5] = 2 * (y * z - s * x);
+   R.m[6] = 2 * (x * z - s * y); R.m[7] = 2 * (y * z + s * x); R.m[8] = 1 - 2 * (x * x + y * y);
+   return R;
+}
+inline RigidBodyTransform nextRigidBodyTransform(Random &r) { return RigidBodyTransform(nextRotationMatrix(r), nextVector3D(r)); }
+// MecanoRandomTools.nextSymmetricPositiveDefiniteMatrix3D(random, 1e-4, 2.0, 0.5): L L^T
+inline Matrix3D nextSymmetricPositiveDefiniteMatrix3D(Random &r, double minDiag = 1e-4, double maxDiag = 2.0, double offDiag = 0.5)
+{
+   double L[9] = {0};
+   L[0] = r.nextDouble(minDiag, maxDiag);
+   L[3] = r.nextDouble(-offDiag, offDiag);
+   L[4] = r.nextDouble(minDiag, maxDiag);
+   L[6] = r.nextDouble(-offDiag, offDiag);
+   L[7] = r.nextDouble(-offDiag, offDiag);
+   L[8] = r.nextDouble(minDiag, maxDiag);
+   Matrix3D M;
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+         M.m[3 * i + j] = L[3 * i] * L[3 * j] + L[3 * i + 1] * L[3 * j + 1] + L[3 * i + 2] * L[3 * j + 2];
+   return M;
+}
+// nextRigidBody, MultiBodySystemRandomTools.java:1365-1371
+inline RigidBody *nextRigidBody(Random &r, MultiBodyArena &a, const std::string &name, Joint *parentJoint)
+{
+   const Matrix3D I = nextSymmetricPositiveDefiniteMatrix3D(r);
+   const double mass = 0.1 + r.nextDouble();
+   const Vector3D com = nextVector3D(r);
+   return a.newRigidBody(name, parentJoint, I, mass, com);
+}
+// nextRevoluteJoint / nextPrismaticJoint, :1211-1231 (null offset for joints attached to the root body)
+inline Joint *nextOneDoFJoint(Random &r, MultiBodyArena &a, const std::string &name, RigidBody *predecessor, bool prismatic)
+{
+   const Vector3D axis = nextUnitVector3D(r);
+   if (predecessor->isRootBody())
+   {
+      if (prismatic) return a.newJoint<PrismaticJoint>(name, predecessor, RigidBodyTransform(), axis);
+      return a.newJoint<RevoluteJoint>(name, predecessor, axis);
+   }
+   const RigidBodyTransform T = nextRigidBodyTransform(r);
+   if (prismatic) return a.newJoint<PrismaticJoint>(name, predecessor, T, axis);
+   return a.newJoint<RevoluteJoint>(name, predecessor, T, axis);
+}
+// nextRevoluteJointChain / nextOneDoFJointChain, :483-496
+inline RigidBody *nextOneDoFJointChain(Random &r, MultiBodyArena &a, const std::string &prefix, RigidBody *root, int n, double prismaticFraction = 0.0)
+{
+   RigidBody *pred = root;
+   for (int i = 0; i < n; i++)
+   {
+      Joint *j = nextOneDoFJoint(r, a, prefix + "Joint" + std::to_string(i), pred, r.nextDouble() < prismaticFraction);
+      pred = nextRigidBody(r, a, prefix + "Body" + std::to_string(i), j);
+   }
+   return pred;
+}
+// nextRevoluteJointTree / nextOneDoFJointTree, :908-923
+inline void nextOneDoFJointTree(Random &r, MultiBodyArena &a, const std::string &prefix, RigidBody *root, int n, double prismaticFraction = 0.0)
+{
+   std::vector<RigidBody *> successors;
+   RigidBody *pred = root;
+   for (int i = 0; i < n; i++)
+   {
+      Joint *j = nextOneDoFJoint(r, a, prefix + "Joint" + std::to_string(i), pred, r.nextDouble() < prismaticFraction);
+      successors.push_back(nextRigidBody(r, a, prefix + "Body" + std::to_string(i), j));
+      pred = successors[(size_t)r.nextInt((int)successors.size())];
+   }
+}
+// RandomFloatingRevoluteJointChain, :1380-1486
+inline RigidBody *nextFloatingBase(Random &r, MultiBodyArena &a, RigidBody *elevator, const std::string &name = "root")
+{
+   SixDoFJoint *j = a.newJoint<SixDoFJoint>(name + "Joint", elevator);
+   return nextRigidBody(r, a, name + "Body", j);
+}
+// Humanoid of SURVEY.md 8(d): SixDoF pelvis, 2 legs x 6, spine 3, 2 arms x 7 on the last spine body, neck
+// (2 revolute -> 37 DoF "H37", 1 -> 36 DoF "H36").
+inline void nextHumanoid(Random &r, MultiBodyArena &a, RigidBody *elevator, int neckJoints = 2)
+{
+   RigidBody *pelvis = nextFloatingBase(r, a, elevator, "pelvis");
+   nextOneDoFJointChain(r, a, "leftLeg", pelvis, 6);
+   nextOneDoFJointChain(r, a, "rightLeg", pelvis, 6);
+   RigidBody *chest = nextOneDoFJointChain(r, a, "spine", pelvis, 3);
+   nextOneDoFJointChain(r, a, "leftArm", chest, 7);
+   nextOneDoFJointChain(r, a, "rightArm", chest, 7);
+   nextOneDoFJointChain(r, a, "neck", chest, neckJoints);
+}
+} // namespace MultiBodySystemRandomTools
+} // namespace mecano

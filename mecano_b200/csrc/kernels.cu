@@ -1,0 +1,280 @@
+// kernels.cu -- sm_100a kernels: one thread per state (thread-per-state variant).
+//
+// Layout of one block:
+//   * the traversal program and topology tables arrive as a __grid_constant__ kernel parameter, i.e.
+//     they live in the constant bank and are read with uniform (warp-wide) LDC;
+//   * the per-body constant records (fixed transforms, inertias) are staged once into shared memory
+//     and read as broadcasts;
+//   * each thread owns one state: its spatial quantities stay in fp64 registers, and the data that
+//     must survive from the downward to the upward sweep lives in a per-thread stack in shared memory,
+//     laid out state-minor (stack[slot * blockDim + tid]) so that a warp touches 32 consecutive
+//     doubles: conflict-free;
+//   * q / qd / qdd / tau / wrench buffers are DoF-major, state-minor in HBM, so every global access of
+//     a warp is one fully used 256-byte segment.
+// No tensor cores: the recursion is not a dense contraction.
+#include <algorithm>
+#include <cstdio>
+#include <type_traits>
+
+#include "algorithms.cuh"
+#include "kernels.h"
+
+namespace mb
+{
+namespace
+{
+template <int AUXN, int RECN> struct GpuCtx
+{
+   const double *q, *qd, *x, *fext;
+   double *out;
+   long long ld, s;
+   int nv;
+   double *stk;       // shared memory, already offset by threadIdx.x
+   int stride;        // blockDim.x
+   const double *cb;  // shared memory constant records
+   double aux[AUXN > 0 ? AUXN : 1];
+   double rec[RECN > 0 ? RECN : 1];
+
+   __device__ __forceinline__ double ld_q(int r) const { return __ldg(q + r * ld + s); }
+   __device__ __forceinline__ double ld_qd(int r) const { return __ldg(qd + r * ld + s); }
+   __device__ __forceinline__ double ld_x(int r) const { return __ldg(x + r * ld + s); }
+   __device__ __forceinline__ double ld_fext(int b, int k) const { return __ldg(fext + (6 * b + k) * ld + s); }
+   __device__ __forceinline__ void st_out(int r, double v) { out[r * ld + s] = v; }
+   __device__ __forceinline__ void st_M(int r, int c, double v) { __stcs(out + ((long long)r * nv + c) * ld + s, v); }
+   __device__ __forceinline__ double stk_ld(int i) const { return stk[i * stride]; }
+   __device__ __forceinline__ void stk_st(int i, double v) { stk[i * stride] = v; }
+   __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
+   __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
+   __device__ __forceinline__ double rec_ld(int i) const { return rec[i]; }
+   __device__ __forceinline__ void rec_st(int i, double v) { rec[i] = v; }
+   __device__ __forceinline__ const double *cst(int b) const { return cb + b * MB_CONST_STRIDE; }
+};
+
+// state-major mass-matrix output (Mecano's per-state dense layout): uncoalesced, provided for drop-in use
+template <int AUXN, int RECN> struct GpuCtxStateMajor : GpuCtx<AUXN, RECN>
+{
+   __device__ __forceinline__ void st_M(int r, int c, double v) { this->out[this->s * (long long)this->nv * this->nv + (long long)r * this->nv + c] = v; }
+};
+
+template <int ALGO, bool FEXT, bool STATE_MAJOR, int AUXN, int RECN>
+__global__ void __launch_bounds__(256) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
+{
+   extern __shared__ double smem[];
+   const int ncst = P.nb * MB_CONST_STRIDE;
+   for (int i = threadIdx.x; i < ncst; i += blockDim.x)
+      smem[i] = a.consts[i];
+   __syncthreads();
+   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   if (s >= a.n)
+      return;
+   typedef typename std::conditional<STATE_MAJOR, GpuCtxStateMajor<AUXN, RECN>, GpuCtx<AUXN, RECN>>::type Ctx;
+   Ctx c;
+   c.q = a.q; c.qd = a.qd; c.x = a.x; c.fext = a.fext; c.out = a.out;
+   c.ld = a.ld; c.s = s; c.nv = a.nv;
+   c.stk = smem + ((ncst + 1) & ~1) + threadIdx.x;
+   c.stride = blockDim.x;
+   c.cb = smem;
+   if constexpr (ALGO == MB_RNEA)
+      rnea_state<double, Ctx, FEXT>(P, c, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+   else if constexpr (ALGO == MB_ABA)
+      aba_state<double, Ctx, FEXT>(P, c, a.grav);
+   else
+      crba_state<double, Ctx>(P, c);
+}
+
+// compiled work-area classes (local memory per thread): {aux, rec}
+//   class 0: up to 4 nested branching bodies, 32 one-DoF-equivalent records (humanoids)
+//   class 1: up to 16 nested branching bodies, 128 bodies
+constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
+constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
+constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
+constexpr int kAbaRec0 = 9 * 33 + 9, kAbaRec1 = 9 * 128 + 18;
+
+typedef void (*KernelFn)(const MbProgram, const KernelArgs);
+
+KernelFn pick(int algo, bool fext, bool state_major, int cls)
+{
+   if (algo == MB_RNEA)
+   {
+      if (cls == 0) return fext ? thread_kernel<MB_RNEA, true, false, kRnaAux0, 0> : thread_kernel<MB_RNEA, false, false, kRnaAux0, 0>;
+      return fext ? thread_kernel<MB_RNEA, true, false, kRnaAux1, 0> : thread_kernel<MB_RNEA, false, false, kRnaAux1, 0>;
+   }
+   if (algo == MB_ABA)
+   {
+      if (cls == 0) return fext ? thread_kernel<MB_ABA, true, false, kAbaAux0, kAbaRec0> : thread_kernel<MB_ABA, false, false, kAbaAux0, kAbaRec0>;
+      return fext ? thread_kernel<MB_ABA, true, false, kAbaAux1, kAbaRec1> : thread_kernel<MB_ABA, false, false, kAbaAux1, kAbaRec1>;
+   }
+   if (cls == 0) return state_major ? thread_kernel<MB_CRBA, false, true, kCrbAux0, 0> : thread_kernel<MB_CRBA, false, false, kCrbAux0, 0>;
+   return state_major ? thread_kernel<MB_CRBA, false, true, kCrbAux1, 0> : thread_kernel<MB_CRBA, false, false, kCrbAux1, 0>;
+}
+
+int class_of(int algo, const MbProgram &P)
+{
+   const int aux0 = algo == MB_RNEA ? kRnaAux0 : (algo == MB_ABA ? kAbaAux0 : kCrbAux0);
+   const int aux1 = algo == MB_RNEA ? kRnaAux1 : (algo == MB_ABA ? kAbaAux1 : kCrbAux1);
+   const int rec0 = algo == MB_ABA ? kAbaRec0 : 0, rec1 = algo == MB_ABA ? kAbaRec1 : 0;
+   if (P.aux_doubles <= aux0 && P.rec_doubles <= rec0) return 0;
+   if (P.aux_doubles <= aux1 && P.rec_doubles <= rec1) return 1;
+   return -1;
+}
+
+size_t smem_bytes(const MbProgram &P, int block)
+{
+   const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
+   return sizeof(double) * ((size_t)ncst + (size_t)std::max(P.stack_doubles, 1) * block);
+}
+} // namespace
+
+cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPlan &plan, bool *fits)
+{
+   *fits = false;
+   const int cls = class_of(algo, P);
+   if (cls < 0)
+      return cudaSuccess;
+   int dev = 0, max_optin = 0;
+   cudaError_t e = cudaGetDevice(&dev);
+   if (e != cudaSuccess) return e;
+   e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+   if (e != cudaSuccess) return e;
+   // every variant of this algorithm/class gets the opt-in so that later launches cannot fail on it
+   for (int f = 0; f < 2; f++)
+      for (int sm = 0; sm < 2; sm++)
+      {
+         e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, sm != 0, cls), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+         if (e != cudaSuccess) return e;
+      }
+   KernelFn fn = pick(algo, fext, false, cls);
+   const int cand[] = {256, 224, 192, 160, 128, 96, 64, 32};
+   int best_threads = 0;
+   for (int b : cand)
+   {
+      const size_t sm = smem_bytes(P, b);
+      if (sm > (size_t)max_optin)
+         continue;
+      int nblk = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, (const void *)fn, b, sm);
+      if (e != cudaSuccess) return e;
+      if (nblk * b > best_threads)
+      {
+         best_threads = nblk * b;
+         plan.block = b;
+         plan.smem = sm;
+         plan.blocks_per_sm = nblk;
+      }
+   }
+   if (best_threads == 0)
+      return cudaSuccess; // the stack of even a 32-state block does not fit in shared memory
+   cudaFuncAttributes attr;
+   e = cudaFuncGetAttributes(&attr, (const void *)fn);
+   if (e != cudaSuccess) return e;
+   plan.size_class = cls;
+   plan.regs = attr.numRegs;
+   plan.local_bytes = (int)attr.localSizeBytes;
+   plan.static_smem = (int)attr.sharedSizeBytes;
+   *fits = true;
+   return cudaSuccess;
+}
+
+cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs &a, const LaunchPlan &plan, cudaStream_t stream)
+{
+   if (a.n <= 0)
+      return cudaSuccess;
+   const bool state_major = algo == MB_CRBA && (a.flags & 1u);
+   KernelFn fn = pick(algo, a.fext != nullptr, state_major, plan.size_class);
+   const long long nblocks = (a.n + plan.block - 1) / plan.block;
+   fn<<<(unsigned)nblocks, plan.block, plan.smem, stream>>>(P, a);
+   return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------- roofline denominators
+namespace
+{
+__global__ void __launch_bounds__(256) dfma_chain_kernel(double *out, int iters, double seed)
+{
+   // 8 independent FMA chains per thread: enough ILP to saturate the FP64 pipe at modest occupancy
+   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+   const double m = 1.0000001, b = 1e-9;
+   for (int i = 0; i < iters; i++)
+   {
+      a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+      a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+   }
+   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, long long n2)
+{
+   const long long stride = (long long)gridDim.x * blockDim.x;
+   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+      dst[i] = src[i];
+}
+} // namespace
+
+cudaError_t measure_fp64_peak(double *tflops)
+{
+   int dev = 0, sms = 0;
+   cudaError_t e = cudaGetDevice(&dev);
+   if (e != cudaSuccess) return e;
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+   double *out = nullptr;
+   e = cudaMalloc(&out, sizeof(double) * blocks * threads);
+   if (e != cudaSuccess) return e;
+   cudaEvent_t t0, t1;
+   cudaEventCreate(&t0);
+   cudaEventCreate(&t1);
+   double best = 0;
+   for (int rep = 0; rep < 6; rep++)
+   {
+      cudaEventRecord(t0);
+      dfma_chain_kernel<<<blocks, threads>>>(out, iters, 1.0 + rep);
+      cudaEventRecord(t1);
+      e = cudaEventSynchronize(t1);
+      if (e != cudaSuccess) break;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+   }
+   cudaEventDestroy(t0);
+   cudaEventDestroy(t1);
+   cudaFree(out);
+   *tflops = best;
+   return e;
+}
+
+cudaError_t measure_hbm_peak(double *gbs)
+{
+   const long long bytes = 1ll << 31; // 2 GiB each way, far beyond L2
+   double2 *src = nullptr, *dst = nullptr;
+   cudaError_t e = cudaMalloc(&src, bytes);
+   if (e != cudaSuccess) return e;
+   e = cudaMalloc(&dst, bytes);
+   if (e != cudaSuccess) { cudaFree(src); return e; }
+   cudaMemset(src, 1, bytes);
+   int dev = 0, sms = 0;
+   cudaGetDevice(&dev);
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   cudaEvent_t t0, t1;
+   cudaEventCreate(&t0);
+   cudaEventCreate(&t1);
+   double best = 0;
+   for (int rep = 0; rep < 6; rep++)
+   {
+      cudaEventRecord(t0);
+      copy_kernel<<<sms * 16, 256>>>(src, dst, bytes / (long long)sizeof(double2));
+      cudaEventRecord(t1);
+      e = cudaEventSynchronize(t1);
+      if (e != cudaSuccess) break;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, t0, t1);
+      if (rep > 0) best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
+   }
+   cudaEventDestroy(t0);
+   cudaEventDestroy(t1);
+   cudaFree(src);
+   cudaFree(dst);
+   *gbs = best;
+   return e;
+}
+} // namespace mb

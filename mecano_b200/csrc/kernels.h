@@ -1,0 +1,41 @@
+// kernels.h -- launch interface between the C-ABI layer (api.cu) and the sm_100a kernels (kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "program.h"
+
+namespace mb
+{
+struct KernelArgs
+{
+   const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
+   double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
+   const double *consts;            // device copy of the per-body constant records
+   long long n, ld;
+   double grav[3];
+   uint32_t flags;
+   int32_t nv;
+};
+
+struct LaunchPlan
+{
+   int block = 0;        // threads per block (= states per block for the thread-per-state variant)
+   size_t smem = 0;      // dynamic shared memory per block
+   int size_class = 0;   // 0: small local work areas, 1: large
+   int blocks_per_sm = 0;
+   int regs = 0;
+   int local_bytes = 0;
+   int static_smem = 0;
+};
+
+// Picks the block size / size class for one algorithm and opts the kernel into large shared memory.
+// Returns cudaSuccess or an error; *fits == false if the tree exceeds the compiled work-area classes.
+cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPlan &plan, bool *fits);
+
+cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs &a, const LaunchPlan &plan, cudaStream_t stream);
+
+// roofline denominators
+cudaError_t measure_fp64_peak(double *tflops);
+cudaError_t measure_hbm_peak(double *gbs);
+} // namespace mb

@@ -1,0 +1,80 @@
+// program.h -- the flattened tree as the kernels see it: per-body constant records (staged in shared
+// memory) and a depth-first "traversal program" (kernel parameter => constant bank).
+//
+// One thread evaluates one state by executing the program: DESCEND(i) ops propagate kinematics from
+// the parent to body i, ASCEND(i) ops run once the whole subtree of i is finished and fold the
+// subtree's force / inertia into the parent.  Interleaving the two sweeps this way means the data
+// that must survive between them only has to be kept for the bodies on the current root-to-leaf
+// path (a stack as deep as the tree) instead of for every body, which is what lets the per-state
+// working set live in shared memory ("working set").
+//
+// Internal frames: every 1-DoF joint frame is re-expressed at flatten time so that the joint axis is
+// the local z axis (a constant rotation Q_i absorbed into the fixed offsets and inertias).  Joint
+// scalars (q, qd, qdd, tau) are invariant under this; SixDoF joints keep Q = identity so that their
+// 6-vectors stay in Mecano's frameAfterJoint.
+#pragma once
+#include <stdint.h>
+
+#define MB_MAX_BODIES 128
+#define MB_MAX_OPS (2 * MB_MAX_BODIES)
+
+// joint types (after canonicalisation the 1-DoF axis is always +z)
+#define MB_REVOLUTE 0
+#define MB_PRISMATIC 1
+#define MB_SIXDOF 2
+
+// per-body constant record, in doubles
+#define MB_C_R 0    // [9] row-major rotation of the joint's zero-configuration frame in the parent frame
+#define MB_C_P 9    // [3] translation of the same
+#define MB_C_I 12   // [6] inertia about the frame origin: xx xy xz yy yz zz
+#define MB_C_H 18   // [3] first moment h = m * c
+#define MB_C_M 21   // [1] mass
+#define MB_C_E 22   // [9] rotation CoM frame -> internal frame (for external wrenches)
+#define MB_C_C 31   // [3] CoM position in the internal frame
+#define MB_CONST_STRIDE 34
+
+// op word: bit0 kind, bits 1..7 flags, bits 8..23 body
+#define MB_OP_ASCEND 0x1u
+#define MB_F_LEAF 0x2u         // body has no children (DESCEND keeps its data in registers; ASCEND follows immediately)
+#define MB_F_LOAD_PARENT 0x4u  // DESCEND: the parent's kinematic state must be reloaded (a sibling subtree ran in between)
+#define MB_F_SAVE_STATE 0x8u   // DESCEND: body has >= 2 children, save its kinematic state for the later ones
+#define MB_F_ROOT_PARENT 0x10u // the parent is the root body
+#define MB_F_STORE_ACC 0x20u   // ASCEND: more siblings follow, write the parent's accumulator back
+#define MB_F_FIRST_CHILD 0x40u // ASCEND: first finished child of the parent (accumulator starts from the parent's own term)
+#define MB_OP_BODY(w) (((w) >> 8) & 0xffffu)
+
+struct MbBody
+{
+   int32_t parent;      // internal index, -1 = root body
+   int32_t jtype;
+   int32_t dof_off;     // Mecano DoF row of the first DoF
+   int32_t cfg_off;     // Mecano configuration row
+   int32_t slot;        // base of this body's stack slot (doubles), shared-memory stack
+   int32_t aux;         // base of this body's branch save area (doubles), local memory; -1 if none
+   int32_t rec;         // base of this body's pass-three record (ABA), local memory
+   int32_t subtree_end; // one past the last internal index of this body's subtree
+   int32_t ext_index;   // index of this body in the caller's tree description (external wrench rows)
+   int32_t depth;
+   int32_t ndof;
+   int32_t pad;
+};
+
+struct MbProgram
+{
+   int32_t nb, nops, nv, nq;
+   int32_t stack_doubles; // shared-memory stack per state
+   int32_t aux_doubles;   // local-memory branch save area per state
+   int32_t rec_doubles;   // local-memory record area per state (ABA)
+   int32_t max_depth;
+   MbBody body[MB_MAX_BODIES];
+   uint32_t op[MB_MAX_OPS];
+};
+
+// stack slot sizes (doubles) per algorithm: joint parameters needed to rebuild the joint transform
+// on the way up: revolute (sin, cos), prismatic (q), SixDoF (R[9], p[3])
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int mb_jp_size(int jtype) { return jtype == MB_REVOLUTE ? 2 : (jtype == MB_PRISMATIC ? 1 : 12); }
+
+enum MbAlgo { MB_RNEA = 0, MB_ABA = 1, MB_CRBA = 2 };

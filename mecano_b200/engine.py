@@ -1,0 +1,164 @@
+"""Low-level engine: one handle = one flattened tree on one device.  Thin, allocation-free wrapper
+over the C ABI for torch CUDA tensors (device entry points) and numpy / pinned arrays (host entry
+points).  Buffers are [rows, n_states] float64 with unit stride along states (ld = stride of rows)."""
+import ctypes
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+
+
+def _dev_ptr_ld(t, rows, n):
+    """(pointer, ld) of a torch CUDA tensor [rows, n] float64 with contiguous states."""
+    import torch
+
+    if t is None:
+        return None, None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64):
+        raise TypeError("expected a float64 CUDA tensor")
+    if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n:
+        raise ValueError("expected shape [%d, %d], got %s" % (rows, n, tuple(t.shape)))
+    if n > 1 and t.stride(1) != 1:
+        raise ValueError("states must be contiguous (stride 1 along dim 1)")
+    return t.data_ptr(), (t.stride(0) if rows > 1 else max(n, t.stride(0)))
+
+
+def _host_ptr_ld(a, rows, n):
+    if a is None:
+        return None, None
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float64):
+        raise TypeError("expected a float64 numpy array")
+    if a.ndim != 2 or a.shape[0] != rows or a.shape[1] != n:
+        raise ValueError("expected shape [%d, %d], got %s" % (rows, n, a.shape))
+    if n > 1 and a.strides[1] != 8:
+        raise ValueError("states must be contiguous")
+    return a.ctypes.data, (a.strides[0] // 8 if rows > 1 else max(n, a.strides[0] // 8))
+
+
+def _same_ld(lds):
+    lds = [l for l in lds if l is not None]
+    if any(l != lds[0] for l in lds):
+        raise ValueError("all buffers of one call must share the same leading dimension")
+    return lds[0]
+
+
+class Engine:
+    def __init__(self, desc, device=0, keepalive=None):
+        """desc: _capi.TreeDesc (level-ordered tables)."""
+        self._h = ctypes.c_void_p()
+        self._keep = keepalive
+        rc = lib.mecano_b200_create(ctypes.byref(desc), int(device), ctypes.byref(self._h))
+        if rc != 0:
+            msg = lib.mecano_b200_last_error(None)
+            raise _capi.MecanoB200Error(rc, msg.decode() if msg else "")
+        self.device = int(device)
+        self.nv = lib.mecano_b200_n_dofs(self._h)
+        self.nq = lib.mecano_b200_n_cfg(self._h)
+        self.nb = lib.mecano_b200_n_bodies(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.mecano_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_gravity(self, gx, gy, gz):
+        check(lib.mecano_b200_set_gravity(self._h, float(gx), float(gy), float(gz)), self._h)
+
+    def kernel_info(self, algo, n_states=0):
+        info = _capi.KernelInfo()
+        check(lib.mecano_b200_kernel_info_get(self._h, int(algo), int(n_states), ctypes.byref(info)), self._h)
+        return info.as_dict()
+
+    @staticmethod
+    def _stream():
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+
+    # ---- device entry points (asynchronous on torch's current stream)
+    def rnea(self, q, qd, qdd, tau, fext=None, flags=0):
+        n = q.shape[1]
+        pq, l0 = _dev_ptr_ld(q, self.nq, n)
+        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
+        pqdd, l2 = _dev_ptr_ld(qdd, self.nv, n)
+        pt, l3 = _dev_ptr_ld(tau, self.nv, n)
+        pf, l4 = _dev_ptr_ld(fext, 6 * self.nb, n)
+        check(lib.mecano_b200_rnea(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags, self._stream()), self._h)
+        return tau
+
+    def aba(self, q, qd, tau, qdd, fext=None, flags=0):
+        n = q.shape[1]
+        pq, l0 = _dev_ptr_ld(q, self.nq, n)
+        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
+        pt, l2 = _dev_ptr_ld(tau, self.nv, n)
+        pqdd, l3 = _dev_ptr_ld(qdd, self.nv, n)
+        pf, l4 = _dev_ptr_ld(fext, 6 * self.nb, n)
+        check(lib.mecano_b200_aba(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pt, pf, pqdd, flags, self._stream()), self._h)
+        return qdd
+
+    def crba(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
+        """M: [nv*nv, n] (entry-major) or [n, nv*nv] (state-major) float64 CUDA tensor."""
+        n = q.shape[1]
+        pq, ld = _dev_ptr_ld(q, self.nq, n)
+        if layout == _capi.CRBA_ENTRY_MAJOR:
+            pm, lm = _dev_ptr_ld(M, self.nv * self.nv, n)
+            ld = _same_ld([ld, lm])
+        else:
+            if tuple(M.shape) != (n, self.nv * self.nv) or not M.is_contiguous():
+                raise ValueError("state-major mass matrix must be a contiguous [n, nv*nv] tensor")
+            pm = M.data_ptr()
+        check(lib.mecano_b200_crba(self._h, n, ld, pq, pm, layout, self._stream()), self._h)
+        return M
+
+    # ---- host entry points (synchronous; inputs/outputs in host memory, pinned for full speed)
+    def rnea_host(self, q, qd, qdd, tau, fext=None, flags=0):
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        pqd, l1 = _host_ptr_ld(qd, self.nv, n)
+        pqdd, l2 = _host_ptr_ld(qdd, self.nv, n)
+        pt, l3 = _host_ptr_ld(tau, self.nv, n)
+        pf, l4 = _host_ptr_ld(fext, 6 * self.nb, n)
+        check(lib.mecano_b200_rnea_host(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags), self._h)
+        return tau
+
+    def aba_host(self, q, qd, tau, qdd, fext=None, flags=0):
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        pqd, l1 = _host_ptr_ld(qd, self.nv, n)
+        pt, l2 = _host_ptr_ld(tau, self.nv, n)
+        pqdd, l3 = _host_ptr_ld(qdd, self.nv, n)
+        pf, l4 = _host_ptr_ld(fext, 6 * self.nb, n)
+        check(lib.mecano_b200_aba_host(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pt, pf, pqdd, flags), self._h)
+        return qdd
+
+    def crba_host(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
+        n = q.shape[1]
+        pq, ld = _host_ptr_ld(q, self.nq, n)
+        if layout == _capi.CRBA_ENTRY_MAJOR:
+            pm, lm = _host_ptr_ld(M, self.nv * self.nv, n)
+            ld = _same_ld([ld, lm])
+        else:
+            if M.shape != (n, self.nv * self.nv) or not M.flags.c_contiguous:
+                raise ValueError("state-major mass matrix must be a contiguous [n, nv*nv] array")
+            pm = M.ctypes.data
+        check(lib.mecano_b200_crba_host(self._h, n, ld, pq, pm, layout), self._h)
+        return M
+
+
+def measure_fp64_peak(device=0):
+    v = ctypes.c_double()
+    check(lib.mecano_b200_measure_fp64_peak(device, ctypes.byref(v)))
+    return v.value
+
+
+def measure_hbm_peak(device=0):
+    v = ctypes.c_double()
+    check(lib.mecano_b200_measure_hbm_peak(device, ctypes.byref(v)))
+    return v.value

@@ -1,0 +1,96 @@
+// emu.cpp -- kernel-source emulation harness (TEST INFRASTRUCTURE, never shipped or loaded by the product).
+// Compiles the exact per-state algorithm templates that the sm_100a kernels inline
+// (mecano_b200/csrc/algorithms.cuh) plus the host flattener for the CPU, so that the no-GPU test suite can
+// check the kernel mathematics and the traversal programs against the oracle.  The product library
+// (libmecano_b200.so) contains no such host path: its entry points launch CUDA kernels or fail.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../mecano_b200/csrc/algorithms.cuh"
+#include "../../mecano_b200/csrc/flatten.h"
+
+namespace
+{
+template <class T> struct CpuCtx
+{
+   const double *q, *qd, *x, *fext;
+   double *out, *M;
+   long ld, s;
+   int nv;
+   T *stk, *aux, *rec;
+   const T *consts;
+   T ld_q(int r) const { return (T)q[r * ld + s]; }
+   T ld_qd(int r) const { return (T)qd[r * ld + s]; }
+   T ld_x(int r) const { return (T)x[r * ld + s]; }
+   T ld_fext(int b, int k) const { return (T)fext[(6 * b + k) * ld + s]; }
+   void st_out(int r, T v) { out[r * ld + s] = (double)v; }
+   void st_M(int r, int c, T v) { M[((long)r * nv + c) * ld + s] = (double)v; }
+   T stk_ld(int i) const { return stk[i]; }
+   void stk_st(int i, T v) { stk[i] = v; }
+   T aux_ld(int i) const { return aux[i]; }
+   void aux_st(int i, T v) { aux[i] = v; }
+   T rec_ld(int i) const { return rec[i]; }
+   void rec_st(int i, T v) { rec[i] = v; }
+   const T *cst(int b) const { return consts + (size_t)b * MB_CONST_STRIDE; }
+};
+
+template <class T>
+int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *x,
+        const double *fext, double *out, unsigned flags, char *err, int errlen)
+{
+   mb::FlatTree ft;
+   std::string e;
+   int rc = mb::flatten_tree(d, ft, e);
+   if (rc != 0)
+   {
+      if (err) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
+      return rc;
+   }
+   const MbProgram &P = ft.prog[algo];
+   std::vector<T> consts(ft.consts.begin(), ft.consts.end());
+   // poison the work areas so that a read-before-write shows up as NaN
+   const T nan = (T)(0.0 / 0.0);
+   std::vector<T> stk(P.stack_doubles + 1, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 1, nan);
+   const T grav[3] = {(T)g[0], (T)g[1], (T)g[2]};
+   for (long s = 0; s < n; s++)
+   {
+      std::fill(stk.begin(), stk.end(), nan);
+      std::fill(aux.begin(), aux.end(), nan);
+      std::fill(rec.begin(), rec.end(), nan);
+      CpuCtx<T> c{q, qd, x, fext, out, out, ld, s, ft.nv, stk.data(), aux.data(), rec.data(), consts.data()};
+      if (algo == MB_RNEA)
+      {
+         if (fext) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav, !(flags & 1u), !(flags & 2u));
+         else mb::rnea_state<T, CpuCtx<T>, false>(P, c, grav, !(flags & 1u), !(flags & 2u));
+      }
+      else if (algo == MB_ABA)
+      {
+         if (fext) mb::aba_state<T, CpuCtx<T>, true>(P, c, grav);
+         else mb::aba_state<T, CpuCtx<T>, false>(P, c, grav);
+      }
+      else
+         mb::crba_state<T, CpuCtx<T>>(P, c);
+   }
+   return 0;
+}
+} // namespace
+
+extern "C" int emu_run(int algo, int fp32, const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd,
+                       const double *x, const double *fext, double *out, unsigned flags, char *err, int errlen)
+{
+   return fp32 ? run<float>(algo, d, g, n, ld, q, qd, x, fext, out, flags, err, errlen)
+               : run<double>(algo, d, g, n, ld, q, qd, x, fext, out, flags, err, errlen);
+}
+
+extern "C" int emu_program_info(const mecano_b200_tree_desc *d, int algo, int *out8)
+{
+   mb::FlatTree ft;
+   std::string e;
+   int rc = mb::flatten_tree(d, ft, e);
+   if (rc != 0) return rc;
+   const MbProgram &P = ft.prog[algo];
+   out8[0] = P.nb; out8[1] = P.nops; out8[2] = P.stack_doubles; out8[3] = P.aux_doubles; out8[4] = P.rec_doubles; out8[5] = P.max_depth;
+   out8[6] = P.nv; out8[7] = P.nq;
+   return 0;
+}

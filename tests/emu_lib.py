@@ -1,0 +1,140 @@
+"""ctypes binding to the kernel-source emulation harness (tests/emu).  Test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_EMU = os.path.join(_HERE, "emu")
+_CSRC = os.path.join(os.path.dirname(_HERE), "mecano_b200", "csrc")
+_LIB = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+
+
+class TreeDescC(ctypes.Structure):
+    """mirror of mecano_b200_tree_desc (include/mecano_b200.h)"""
+    _fields_ = [
+        ("struct_size", ctypes.c_int32), ("n_bodies", ctypes.c_int32), ("n_dofs", ctypes.c_int32), ("n_cfg", ctypes.c_int32),
+        ("n_levels", ctypes.c_int32), ("level_start", _ip), ("parent", _ip), ("joint_type", _ip), ("axis", _dp),
+        ("offset_rot", _dp), ("offset_pos", _dp), ("com_rot", _dp), ("com_pos", _dp), ("inertia", _dp), ("mass", _dp),
+        ("dof_offset", _ip), ("cfg_offset", _ip),
+    ]
+
+
+def level_order(tree):
+    """Re-list the bodies of a TreeDesc level by level (what the Java host hands to the C-ABI)."""
+    nb = tree.nb
+    depth = np.zeros(nb, dtype=np.int64)
+    for i in range(nb):
+        depth[i] = 0 if tree.parent[i] < 0 else depth[tree.parent[i]] + 1
+    order = np.argsort(depth, kind="stable")
+    new_of = np.empty(nb, dtype=np.int64)
+    new_of[order] = np.arange(nb)
+    parent = np.array([-1 if tree.parent[o] < 0 else new_of[tree.parent[o]] for o in order], dtype=np.int32)
+    nlev = int(depth.max()) + 1
+    level_start = np.zeros(nlev + 1, dtype=np.int32)
+    for dpt in depth:
+        level_start[dpt + 1] += 1
+    level_start = np.cumsum(level_start).astype(np.int32)
+    return order, parent, level_start
+
+
+def tree_desc_c(tree, level_ordered=True):
+    """Build the C struct (and keep the arrays alive) from a tests.treedesc.TreeDesc."""
+    if level_ordered:
+        order, parent, level_start = level_order(tree)
+    else:
+        order, parent, level_start = np.arange(tree.nb), tree.parent.copy(), np.zeros(1, np.int32)
+    keep = {
+        "level_start": np.ascontiguousarray(level_start, np.int32),
+        "parent": np.ascontiguousarray(parent, np.int32),
+        "joint_type": np.ascontiguousarray(tree.jtype[order], np.int32),
+        "axis": np.ascontiguousarray(tree.axis[order]),
+        "offset_rot": np.ascontiguousarray(tree.off_R[order]),
+        "offset_pos": np.ascontiguousarray(tree.off_p[order]),
+        "com_rot": np.ascontiguousarray(tree.com_R[order]),
+        "com_pos": np.ascontiguousarray(tree.com_p[order]),
+        "inertia": np.ascontiguousarray(tree.J[order]),
+        "mass": np.ascontiguousarray(tree.mass[order]),
+        "dof_offset": np.ascontiguousarray(tree.dof_off[order], np.int32),
+        "cfg_offset": np.ascontiguousarray(tree.cfg_off[order], np.int32),
+    }
+    d = TreeDescC()
+    d.struct_size = ctypes.sizeof(TreeDescC)
+    d.n_bodies, d.n_dofs, d.n_cfg = tree.nb, tree.nv, tree.nq
+    d.n_levels = len(level_start) - 1 if level_ordered else 0
+    d.level_start = keep["level_start"].ctypes.data_as(_ip) if level_ordered else None
+    for name in ("parent", "joint_type", "dof_offset", "cfg_offset"):
+        setattr(d, name, keep[name].ctypes.data_as(_ip))
+    for name in ("axis", "offset_rot", "offset_pos", "com_rot", "com_pos", "inertia", "mass"):
+        setattr(d, name, keep[name].ctypes.data_as(_dp))
+    return d, keep, order
+
+
+def build():
+    src = [os.path.join(_EMU, "emu.cpp"), os.path.join(_CSRC, "flatten.cpp")]
+    out = os.path.join(_EMU, "libmecano_emu.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++"] + src + ["-o", out])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        out = os.path.join(_EMU, "libmecano_emu.so")
+        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh")]
+        if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(f) for f in deps):
+            build()
+        _LIB = ctypes.CDLL(out)
+    return _LIB
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+class Emu:
+    RNEA, ABA, CRBA = 0, 1, 2
+
+    def __init__(self, tree, gravity=(0.0, 0.0, -9.81), fp32=False, level_ordered=True):
+        self.tree = tree
+        self.desc, self._keep, self.order = tree_desc_c(tree, level_ordered)
+        self.g = np.ascontiguousarray(gravity, dtype=np.float64)
+        self.fp32 = int(fp32)
+        self.lib = lib()
+
+    def _fext_rows(self, fext, n):
+        """fext [nb_tree_order, 6, n] -> rows in the order of the C description."""
+        if fext is None:
+            return None
+        return np.ascontiguousarray(fext[self.order].reshape(6 * self.tree.nb, n))
+
+    def _run(self, algo, q, qd, x, fext, out, flags=0):
+        n = q.shape[1]
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_run(algo, self.fp32, ctypes.byref(self.desc), _d(self.g), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(qd), _d(x),
+                              _d(fext), _d(out), ctypes.c_uint(flags), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_run rc=%d: %s" % (rc, err.value.decode()))
+        return out
+
+    def rnea(self, q, qd, qdd, fext=None, flags=0):
+        n = q.shape[1]
+        return self._run(0, q, qd, qdd, self._fext_rows(fext, n), np.full((self.tree.nv, n), np.nan), flags)
+
+    def aba(self, q, qd, tau, fext=None):
+        n = q.shape[1]
+        return self._run(1, q, qd, tau, self._fext_rows(fext, n), np.full((self.tree.nv, n), np.nan))
+
+    def crba(self, q):
+        n = q.shape[1]
+        nv = self.tree.nv
+        return self._run(2, q, None, None, None, np.full((nv * nv, n), np.nan)).reshape(nv, nv, n)
+
+    def program_info(self, algo):
+        out = (ctypes.c_int * 8)()
+        rc = self.lib.emu_program_info(ctypes.byref(self.desc), algo, out)
+        assert rc == 0
+        return dict(zip(("nb", "nops", "stack", "aux", "rec", "max_depth", "nv", "nq"), list(out)))
