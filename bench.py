@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- batched RNEA / ABA / CRBA states/sec on the 37-DoF humanoid (fp64), the metric of BASELINE.json.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" evaluates all three calculators (InverseDynamicsCalculator, ForwardDynamicsCalculator,
+CompositeRigidBodyMassMatrixCalculator) once on a batch of synthetic random states of the H37 humanoid tree
+(SixDoF + 31 revolute joints: 32 bodies, 37 DoF, 38 configuration rows); a state counts as processed when all
+three have been evaluated.  `value` = states of all ranks / (max-over-ranks time per step), inputs resident in HBM.
+Per-GPU work is fixed (weak scaling); ranks own disjoint slices and there is no collective on the data path.
+
+Rank 0 prints ONE JSON line (see the task contract): metric/value/unit/..., `roofline` for the dominant kernel
+(CRBA, HBM-bound) plus per-kernel details under `kernels`, `cpu_baseline` (the C oracle port timed on the host
+cores on a bounded sample), `e2e` (the same step through the host-pointer C-ABI entry points: pinned host buffers,
+H2D + kernels + D2H inside the timed region) and `clocks`.
+
+`--impl reference`: Mecano itself is Java and no JVM exists on these boxes, so the reference arm
+times the reference-faithful C restatement (oracle/, "port") multithreaded on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HUMANOID_SEED = 20251017
+STATE_SEED = 1234
+GRAVITY = (0.0, 0.0, -9.81)
+METRIC = "RNEA+ABA+CRBA states/sec (37-DoF humanoid, fp64)"
+UNIT = "states/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--states", type=int, default=1 << 20, help="states per GPU (weak scaling)")
+    p.add_argument("--neck", type=int, default=2, help="2 -> H37 (37 DoF), 1 -> H36 (36 DoF)")
+    p.add_argument("--cpu-sample", type=int, default=32768, help="states in the bounded CPU-baseline sample")
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-cpu", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(neck, n):
+    return "H%d humanoid (SixDoF + %d revolute, %d bodies), %d states/GPU, RNEA+ABA+CRBA per step" % (36 + (neck == 2), 29 + neck, 30 + neck, n)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_system(neck):
+    import mecano_b200 as mb
+
+    elevator = mb.RigidBody("elevator")
+    mb.MultiBodySystemRandomTools.nextHumanoid(HUMANOID_SEED, elevator, neck)
+    return mb.MultiBodySystem.toMultiBodySystemBasics(elevator)
+
+
+def oracle_for(system):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import treedesc
+
+    tree = treedesc.TreeDesc(**system.describe()).contiguous()
+    return oracle_lib.Oracle(tree, gravity=GRAVITY), oracle_lib
+
+
+def cpu_step(oracle, q, qd, qdd, tau, nthreads=0):
+    """The reference path for one batch: ID, FD and the mass matrix, one calculator instance per thread."""
+    oracle.rnea_batch(q, qd, qdd, nthreads=nthreads)
+    oracle.aba_batch(q, qd, tau, nthreads=nthreads)
+    oracle.crba_batch(q, nthreads=nthreads)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import mecano_b200 as mb
+
+    system = build_system(args.neck)
+    oracle, oracle_lib = oracle_for(system)
+    cores = oracle_lib.lib().mo_max_threads()
+    n = args.cpu_sample
+    rng = np.random.default_rng(STATE_SEED)
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, system, n)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_step(oracle, q[:, :2048].copy(), qd[:, :2048].copy(), qdd[:, :2048].copy(), tau[:, :2048].copy())
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(oracle, q, qd, qdd, tau)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n / dt
+    sample = "%d states of the same workload per step (bounded sample), C restatement of Mecano (oracle/), %d threads" % (n, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.neck, args.states), "sample_states_per_step": n,
+                   "note": "Mecano is Java; no JVM on this box: reference arm = reference-faithful C port on host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import mecano_b200 as mb
+    from mecano_b200 import sharding
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    system = build_system(args.neck)
+    nv, nq, nb = system.getNumberOfDoFs(), system.getConfigurationMatrixSize(), system.getNumberOfJoints()
+    n = args.states
+    ident = mb.InverseDynamicsCalculator(system, device=local_rank)
+    fdyn = mb.ForwardDynamicsCalculator(system, device=local_rank)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank)
+    for c in (ident, fdyn):
+        c.setGravitationalAcceleration(*GRAVITY)
+
+    # synthetic states generated on the device for the device-resident measurement (seed differs per rank: disjoint slices)
+    gen = torch.Generator(device=dev).manual_seed(STATE_SEED + rank)
+    q = (torch.rand((nq, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * np.pi
+    quat = torch.randn((4, n), dtype=torch.float64, device=dev, generator=gen)
+    q[0:4] = quat / quat.norm(dim=0, keepdim=True)
+    q[4:7] = torch.rand((3, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qdd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    tau_in = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    tau = torch.empty((nv, n), dtype=torch.float64, device=dev)
+    qdd_out = torch.empty((nv, n), dtype=torch.float64, device=dev)
+    M = torch.empty((nv * nv, n), dtype=torch.float64, device=dev)
+
+    def step(events=None):
+        if events is not None:
+            events[0].record()
+        ident.compute(q, qd, qdd, tau)
+        if events is not None:
+            events[1].record()
+        fdyn.compute(q, qd, tau_in, qdd_out)
+        if events is not None:
+            events[2].record()
+        crba.getMassMatrix(q, M)
+        if events is not None:
+            events[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_stop = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for k in range(args.steps):
+        step(evs[k])
+    t_stop.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_total = t_start.elapsed_time(t_stop)
+    ms_step = sharding.max_over_ranks(ms_total / args.steps, dev)
+    per_kernel_ms = {name: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)]))
+                     for i, name in enumerate(("rnea", "aba", "crba"))}
+    per_kernel_ms = {k: sharding.max_over_ranks(v, dev) for k, v in per_kernel_ms.items()}
+    value = n * world / (ms_step * 1e-3)
+
+    # ---- roofline (rank 0 numbers; every rank runs the same kernels on the same amount of work)
+    peaks, peak_src = measured_peaks()
+    hbm_peak = float(peaks["hbm_gbs"])
+    fp64_peak = mb.measure_fp64_peak(local_rank) if rank == 0 else 0.0
+    flops_path = os.path.join(ROOT, "profiles", "algorithmic_flops.json")
+    flops = json.load(open(flops_path)) if os.path.exists(flops_path) else {}
+    key = "H%d" % nv
+    kernels = {}
+    for name, calc in (("rnea", ident), ("aba", fdyn), ("crba", crba)):
+        info = calc.kernelInfo(n)
+        ms = per_kernel_ms[name]
+        gbs = info["bytes_per_state"] * n / (ms * 1e-3) / 1e9
+        entry = {"ms": ms, "states_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_state": info["bytes_per_state"], "achieved_gbs": gbs,
+                 "hbm_frac": gbs / hbm_peak, "block_threads": info["block_threads"], "regs": info["regs_per_thread"],
+                 "smem_bytes": info["dynamic_smem_bytes"], "blocks_per_sm": info["blocks_per_sm"]}
+        fl = flops.get(key, {}).get(name)
+        if fl and fp64_peak:
+            tf = fl * n / (ms * 1e-3) / 1e12
+            entry.update({"algorithmic_flops_per_state": fl, "achieved_tflops": tf, "fp64_frac": tf / fp64_peak})
+        kernels[name] = entry
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    # the dominant kernel is reported against the roofline that binds it: CRBA -> HBM (write-dominated)
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels[dom]["achieved_gbs"] / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "fp64_peak_tflops_measured_live": fp64_peak}
+    traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(traffic_path):
+        tr = json.load(open(traffic_path)).get(dom)
+        if tr:
+            roofline["traffic"] = tr["bytes_per_state"] * n
+            roofline["traffic_note"] = tr.get("note")
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.neck, n), "states_per_gpu": n, "n_dofs": nv, "n_cfg": nq, "n_bodies": nb,
+                       "parallelism": "disjoint state slices per GPU, no collective", "l2": "inputs (%.2f GB/step) and outputs larger than L2; no explicit flush"
+                       % (8.0 * (3 * nq + 4 * nv) * n / 1e9), "humanoid_seed": HUMANOID_SEED, "mass_matrix_layout": "entry-major [nv*nv][N]"},
+            "roofline": roofline, "kernels": kernels, "gpu_launches": 3 * args.steps, "clocks": clocks,
+        }
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        oracle, oracle_lib = oracle_for(system)
+        cores = oracle_lib.lib().mo_max_threads()
+        ns = args.cpu_sample
+        hq, hqd, hqdd, htau = (x[:, :ns].cpu().numpy().copy() for x in (q, qd, qdd, tau_in))
+        cpu_step(oracle, hq[:, :1024].copy(), hqd[:, :1024].copy(), hqdd[:, :1024].copy(), htau[:, :1024].copy())
+        t0 = time.perf_counter()
+        cpu_step(oracle, hq, hqd, hqdd, htau)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "first %d states of the same batch, one pass of RNEA+ABA+CRBA, C restatement of Mecano (oracle/), one instance per thread" % ns}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+
+    # ---- end to end: the same step through the host-pointer C-ABI entry points with pinned host buffers
+    if not args.no_e2e:
+        hn = n
+        pin = lambda rows: torch.empty((rows, hn), dtype=torch.float64).pin_memory()  # noqa: E731
+        hq, hqd, hqdd, htau_in = pin(nq), pin(nv), pin(nv), pin(nv)
+        hq.copy_(q.cpu()); hqd.copy_(qd.cpu()); hqdd.copy_(qdd.cpu()); htau_in.copy_(tau_in.cpu())
+        htau, hqdd_out, hM = pin(nv), pin(nv), pin(nv * nv)
+        nq_, nqd_, nqdd_, ntau_in, ntau, nqdd_out, nM = (t.numpy() for t in (hq, hqd, hqdd, htau_in, htau, hqdd_out, hM))
+
+        def host_step():
+            ident.compute(nq_, nqd_, nqdd_, ntau)
+            fdyn.compute(nq_, nqd_, ntau_in, nqdd_out)
+            crba.getMassMatrix(nq_, nM)
+
+        host_step()  # warm-up (allocates the staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            host_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        dt = sharding.max_over_ranks(dt, dev)
+        if rank == 0:
+            line["e2e"] = {"value": hn * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+                           "h2d_bytes_per_step": int(8 * (nq * 3 + nv * 4) * hn), "d2h_bytes_per_step": int(8 * (2 * nv + nv * nv) * hn),
+                           "api": "InverseDynamicsCalculator.compute / ForwardDynamicsCalculator.compute / CompositeRigidBodyMassMatrixCalculator.getMassMatrix "
+                                  "on pinned host matrices -> mecano_b200_{rnea,aba,crba}_host", "check": float(np.abs(ntau).max())}
+    elif rank == 0:
+        line["e2e"] = None
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

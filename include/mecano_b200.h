@@ -98,6 +98,9 @@ typedef struct mecano_b200_tree_desc
    const double *mass;         /* [n_bodies] */
    const int32_t *dof_offset;  /* [n_bodies] JointMatrixIndexProvider row of the joint's first DoF */
    const int32_t *cfg_offset;  /* [n_bodies] row of the joint's first configuration entry */
+   const int32_t *wrench_index; /* [n_bodies] or NULL: body b's external wrench occupies rows [6 w, 6 w + 6) of fext, w = wrench_index[b]
+                                   (NULL: w = b).  The Java host passes the joint's JointMatrixIndexProvider rank here so that fext
+                                   is in Mecano joint order like every other matrix. */
 } mecano_b200_tree_desc;
 
 typedef struct mecano_b200_kernel_info
@@ -135,7 +138,8 @@ int mecano_b200_n_bodies(const mecano_b200_handle *h);
  * Device-pointer entry points.  All pointers are device memory on the handle's device, 8-byte
  * aligned; `stream` is a cudaStream_t (NULL = default stream).  Calls are asynchronous.
  * fext (nullable): external wrench on each body expressed in that body's CoM frame,
- * [(6 * b + c) * ld + s], b in the order of the tree description (InverseDynamicsCalculator.java:819, :946).
+ * [(6 * w + c) * ld + s], w = wrench_index[b] (default: b, the order of the tree description)
+ * (InverseDynamicsCalculator.java:819, :946).
  */
 int mecano_b200_rnea(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
                      const double *fext, double *tau, uint32_t flags, void *stream);

@@ -1,0 +1,66 @@
+/*
+ * mecano_b200_model.h -- C view of the C++ host-side model mirror (mecano_b200/csrc/host/multibody.hpp),
+ * so that non-C++ hosts (the Python package, tests) can build a MultiBodySystem the way Mecano code does
+ * and obtain the level-ordered tables for mecano_b200_create().  A Java host does not need this header:
+ * it flattens its own MultiBodySystemReadOnly.
+ *
+ * Mirrors: RigidBody / RevoluteJoint / PrismaticJoint / SixDoFJoint constructors
+ * (M/multiBodySystem/*.java), MultiBodySystemBasics.toMultiBodySystemBasics
+ * (M/multiBodySystem/interfaces/MultiBodySystemBasics.java:76-142), and the generators of
+ * M/tools/MultiBodySystemRandomTools.java.
+ *
+ * Bodies are referred to by integer ids: 0 is the root body (elevator); the successor of the k-th
+ * created joint has id k + 1.  All functions return >= 0 on success and < 0 on error.
+ */
+#ifndef MECANO_B200_MODEL_H
+#define MECANO_B200_MODEL_H
+
+#include <stdint.h>
+
+#include "mecano_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mecano_model mecano_model;
+
+mecano_model *mecano_model_create(const char *root_body_name);
+void mecano_model_destroy(mecano_model *m);
+const char *mecano_model_last_error(const mecano_model *m);
+
+/* Joints.  transform12 = row-major rotation (9) + translation (3) of frameBeforeJoint in the predecessor's
+ * frameAfterJoint, or NULL for identity.  Returns the joint id (>= 0). */
+int mecano_model_add_revolute_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12, const double *axis3);
+int mecano_model_add_prismatic_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12, const double *axis3);
+int mecano_model_add_sixdof_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
+/* RigidBody(name, parentJoint, momentOfInertia, mass, inertiaPose).  Returns the body id (= joint id + 1). */
+int mecano_model_add_rigid_body(mecano_model *m, const char *name, int parent_joint, const double *inertia9, double mass, const double *inertia_pose12);
+
+/* MultiBodySystemRandomTools generators (seeded splitmix64; Mecano's distributions).  Each appends to the model. */
+int mecano_model_next_one_dof_joint_chain(mecano_model *m, uint64_t seed, int predecessor_body, int n_joints, double prismatic_fraction);
+int mecano_model_next_one_dof_joint_tree(mecano_model *m, uint64_t seed, int predecessor_body, int n_joints, double prismatic_fraction);
+int mecano_model_next_floating_base(mecano_model *m, uint64_t seed, int predecessor_body); /* returns the new body id */
+int mecano_model_next_humanoid(mecano_model *m, uint64_t seed, int neck_joints);
+
+/* toMultiBodySystemBasics(rootBody): fixes the joint order / index provider and builds the tables. */
+int mecano_model_finalize(mecano_model *m);
+int mecano_model_n_joints(const mecano_model *m);
+int mecano_model_n_dofs(const mecano_model *m);
+int mecano_model_n_cfg(const mecano_model *m);
+/* joint ids in JointMatrixIndexProvider order, and their first DoF / configuration rows */
+int mecano_model_joint_order(const mecano_model *m, int32_t *joint_ids, int32_t *dof_index, int32_t *cfg_index);
+/* per joint (by id): type, predecessor body id, axis, transform, and its successor's inertia parameters */
+int mecano_model_joint_info(const mecano_model *m, int joint, int32_t *type, int32_t *predecessor_body, double *axis3, double *transform12,
+                            double *inertia9, double *mass, double *inertia_pose12);
+const char *mecano_model_joint_name(const mecano_model *m, int joint);
+const char *mecano_model_body_name(const mecano_model *m, int body);
+/* level-ordered tables (valid until the model is destroyed) */
+const mecano_b200_tree_desc *mecano_model_tables(const mecano_model *m);
+/* row of joint `joint` in the level-ordered tables */
+int mecano_model_table_row(const mecano_model *m, int joint);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -34,7 +34,7 @@ class TreeDesc(ctypes.Structure):
         ("struct_size", ctypes.c_int32), ("n_bodies", ctypes.c_int32), ("n_dofs", ctypes.c_int32), ("n_cfg", ctypes.c_int32),
         ("n_levels", ctypes.c_int32), ("level_start", c_ip), ("parent", c_ip), ("joint_type", c_ip), ("axis", c_dp),
         ("offset_rot", c_dp), ("offset_pos", c_dp), ("com_rot", c_dp), ("com_pos", c_dp), ("inertia", c_dp), ("mass", c_dp),
-        ("dof_offset", c_ip), ("cfg_offset", c_ip),
+        ("dof_offset", c_ip), ("cfg_offset", c_ip), ("wrench_index", c_ip),
     ]
 
 

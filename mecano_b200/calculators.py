@@ -1,0 +1,180 @@
+"""Batched mirrors of Mecano's three calculators (Python face; the C++ face is csrc/host/calculators.hpp).
+
+    InverseDynamicsCalculator                 M/algorithms/InverseDynamicsCalculator.java:201-251, 291-306, 343-403, 469-472, 496-501, 567-570
+    ForwardDynamicsCalculator                 M/algorithms/ForwardDynamicsCalculator.java:128-196, 313-319, 508-520, 556-567
+    CompositeRigidBodyMassMatrixCalculator    M/algorithms/CompositeRigidBodyMassMatrixCalculator.java:182-233, 286-291, 344-348
+
+Same names, argument meaning and error behaviour as the reference; the batching changes are that the joint state
+is passed explicitly as [rows, N] matrices (Mecano reads it from the joint objects) and that results come back as
+[rows, N] matrices.  Inputs may be float64 torch CUDA tensors (device path, asynchronous on the current stream) or
+float64 numpy arrays (host path through the *_host C-ABI entry points, which stage through the GPU).  There is no
+CPU implementation behind these classes.
+"""
+import numpy as np
+
+from . import _capi
+from .engine import Engine
+from .multibody import MultiBodySystem, RigidBody
+
+
+class MatrixDimensionException(ValueError):
+    """EJML's MatrixDimensionException (ForwardDynamicsCalculator.java:522-533)."""
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _BatchedCalculator:
+    def __init__(self, input, device=0):
+        if isinstance(input, RigidBody):  # InverseDynamicsCalculator(RigidBodyReadOnly rootBody), :186
+            input = MultiBodySystem.toMultiBodySystemBasics(input)
+        self._input = input
+        self._engine = Engine(input.tables().contents, device, keepalive=input)
+        self._fext = None
+        self._gravity = (0.0, 0.0, 0.0)
+
+    def getInput(self):
+        return self._input
+
+    def setGravitationalAcceleration(self, *gravity):
+        """setGravitationalAcceleration(gz) | (gx, gy, gz) | (tuple3)  (InverseDynamicsCalculator.java:343-403)"""
+        if len(gravity) == 1:
+            g = gravity[0]
+            g = (0.0, 0.0, float(g)) if np.isscalar(g) else tuple(float(v) for v in g)
+        else:
+            g = tuple(float(v) for v in gravity)
+        if len(g) != 3:
+            raise ValueError("gravity must have 3 components")
+        self._gravity = g
+        self._engine.set_gravity(*g)
+
+    def setExternalWrenches(self, wrenches):
+        """External wrench on the successor of every joint, [6 * nJoints, N] in JointMatrixIndexProvider order, each
+        expressed in its body's CoM frame (setExternalWrench, InverseDynamicsCalculator.java:469-472, :819)."""
+        self._fext = wrenches
+
+    def setExternalWrenchesToZero(self):
+        self._fext = None
+
+    def _check(self, name, m, rows, n):
+        if m is None or m.ndim != 2 or m.shape[0] != rows or m.shape[1] != n:
+            raise MatrixDimensionException("%s: expected a %d x %d matrix, got %s" % (name, rows, n, None if m is None else tuple(m.shape)))
+
+    def _empty_like(self, ref, rows, n, match_ld=True):
+        """Output matrix with the same leading dimension as `ref` (all matrices of one call share it)."""
+        if _is_torch(ref):
+            import torch
+
+            ld = max(n, ref.stride(0)) if (match_ld and ref.dim() == 2 and ref.shape[0] > 1) else n
+            return torch.empty((rows, ld), dtype=torch.float64, device=ref.device)[:, :n]
+        ld = max(n, ref.strides[0] // 8) if (match_ld and ref.ndim == 2 and ref.shape[0] > 1) else n
+        return np.empty((rows, ld), dtype=np.float64)[:, :n]
+
+    def kernelInfo(self, n_states=0):
+        return self._engine.kernel_info(self._ALGO, n_states)
+
+
+class InverseDynamicsCalculator(_BatchedCalculator):
+    _ALGO = _capi.ALGO_RNEA
+
+    def __init__(self, input, device=0):
+        super().__init__(input, device)
+        self._coriolis = True
+        self._accelerations = True
+        self._tau = None
+
+    def setConsiderCoriolisAndCentrifugalForces(self, value):
+        self._coriolis = bool(value)
+
+    def setConsiderJointAccelerations(self, value):
+        self._accelerations = bool(value)
+
+    def areCoriolisAndCentrifugalForcesConsidered(self):
+        return self._coriolis
+
+    def areJointAccelerationsConsidered(self):
+        return self._accelerations
+
+    def compute(self, q, qd, qdd, tau=None):
+        """compute(jointAccelerationMatrix) for N states; returns getJointTauMatrix() ([nDoFs, N])."""
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        self._check("q", q, nq, n)
+        self._check("qd", qd, nv, n)
+        self._check("qdd", qdd, nv, n)
+        if tau is None:
+            tau = self._empty_like(q, nv, n)
+        self._check("tau", tau, nv, n)
+        if self._fext is not None:
+            self._check("externalWrenches", self._fext, 6 * self._input.getNumberOfJoints(), n)
+        flags = (0 if self._coriolis else _capi.RNEA_NO_CORIOLIS) | (0 if self._accelerations else _capi.RNEA_NO_ACCELERATIONS)
+        if _is_torch(q):
+            self._engine.rnea(q, qd, qdd, tau, fext=self._fext, flags=flags)
+        else:
+            self._engine.rnea_host(q, qd, qdd, tau, fext=self._fext, flags=flags)
+        self._tau = tau
+        return tau
+
+    def getJointTauMatrix(self):
+        return self._tau
+
+
+class ForwardDynamicsCalculator(_BatchedCalculator):
+    _ALGO = _capi.ALGO_ABA
+
+    def __init__(self, input, device=0):
+        super().__init__(input, device)
+        self._qdd = None
+
+    def compute(self, q, qd, tau, qdd=None):
+        """compute(jointTauMatrix) for N states; returns getJointAccelerationMatrix() ([nDoFs, N])."""
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        self._check("q", q, nq, n)
+        self._check("qd", qd, nv, n)
+        self._check("tau", tau, nv, n)
+        if qdd is None:
+            qdd = self._empty_like(q, nv, n)
+        self._check("qdd", qdd, nv, n)
+        if self._fext is not None:
+            self._check("externalWrenches", self._fext, 6 * self._input.getNumberOfJoints(), n)
+        if _is_torch(q):
+            self._engine.aba(q, qd, tau, qdd, fext=self._fext)
+        else:
+            self._engine.aba_host(q, qd, tau, qdd, fext=self._fext)
+        self._qdd = qdd
+        return qdd
+
+    def getJointAccelerationMatrix(self):
+        return self._qdd
+
+
+class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
+    _ALGO = _capi.ALGO_CRBA
+
+    def __init__(self, input, device=0):
+        super().__init__(input, device)
+        self._M = None
+
+    def reset(self):
+        """Mecano caches the mass matrix until reset(); the batched calculator recomputes on every getMassMatrix(q)."""
+        self._M = None
+
+    def getMassMatrix(self, q, massMatrix=None, stateMajor=False):
+        """Mass matrices for N states.  Default layout [nDoFs*nDoFs, N] (entry (i, j) of state s at [i*nDoFs + j, s]);
+        stateMajor=True gives [N, nDoFs*nDoFs], i.e. one Mecano-style dense row-major nDoFs x nDoFs matrix per state."""
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        self._check("q", q, nq, n)
+        shape = (n, nv * nv) if stateMajor else (nv * nv, n)
+        if massMatrix is None:
+            massMatrix = self._empty_like(q, *shape, match_ld=not stateMajor)
+        self._check("massMatrix", massMatrix, *shape)
+        layout = _capi.CRBA_STATE_MAJOR if stateMajor else _capi.CRBA_ENTRY_MAJOR
+        if _is_torch(q):
+            self._engine.crba(q, massMatrix, layout)
+        else:
+            self._engine.crba_host(q, massMatrix, layout)
+        self._M = massMatrix
+        return massMatrix

@@ -97,20 +97,20 @@ template <class T> struct JpT
 
 // (a1) joint transform X_J(q) composed with the fixed offset (MecanoFactories.java:231-260,
 // PrismaticJointReadOnly.java:18-22, FloatingJointReadOnly.java:34-37), in canonical frames
-template <class T, class Ctx> MB_HD XfT<T> joint_transform(Ctx &c, const MbBody &B, const T *C, JpT<T> &jp)
+template <class T, class Ctx> MB_HD XfT<T> joint_transform(Ctx &c, const MbBody &B, const T *C, JpT<T> &jp, T q1)
 {
    XfT<T> X;
    const M3T<T> R0 = ld_m3(C + MB_C_R);
    const V3T<T> p0 = ld_v3(C + MB_C_P);
    if (B.jtype == MB_REVOLUTE)
    {
-      mb_sincos(c.ld_q(B.cfg_off), &jp.s, &jp.c);
+      mb_sincos(q1, &jp.s, &jp.c);
       X.R = mul_rz(R0, jp.s, jp.c);
       X.p = p0;
    }
    else if (B.jtype == MB_PRISMATIC)
    {
-      jp.s = c.ld_q(B.cfg_off);
+      jp.s = q1;
       X.R = R0;
       X.p = p0 + jp.s * v3<T>(R0.xz, R0.yz, R0.zz);
    }
@@ -199,6 +199,29 @@ template <class T, class F> MB_HD SvT<T> joint_motion(int jtype, int row, F ld)
    return r;
 }
 
+// S * x with the scalar of a 1-DoF joint already in a register (SixDoF joints load their six rows)
+template <class T, class F> MB_HD SvT<T> joint_motion_pf(int jtype, int row, T x1, F ld)
+{
+   SvT<T> r = sv_zero<T>();
+   if (jtype == MB_REVOLUTE)
+      r.a.z = x1;
+   else if (jtype == MB_PRISMATIC)
+      r.l.z = x1;
+   else
+   {
+      r.a = v3<T>(ld(row), ld(row + 1), ld(row + 2));
+      r.l = v3<T>(ld(row + 3), ld(row + 4), ld(row + 5));
+   }
+   return r;
+}
+
+// Software prefetch: while op k runs, the global loads of op k+1 (the scalars of a 1-DoF joint) are already in
+// flight, so their HBM latency overlaps one whole body of arithmetic instead of stalling the warp.
+template <class T> struct PfT
+{
+   T q, qd, x;
+};
+
 // external wrench on a body, given in its CoM frame, re-expressed in the canonical joint frame
 template <class T, class Ctx> MB_HD SvT<T> external_wrench(Ctx &c, const MbBody &B, const T *C)
 {
@@ -221,12 +244,28 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
    X.R = M3T<T>();
    X.p = v3<T>(0, 0, 0);
    const int nops = P.nops;
+   PfT<T> pf;
+   pf.q = pf.qd = pf.x = (T)0;
+   auto prefetch = [&](uint32_t wn) {
+      if (wn & MB_OP_ASCEND)
+         return;
+      const MbBody &Bn = P.body[MB_OP_BODY(wn)];
+      if (Bn.jtype == MB_SIXDOF)
+         return;
+      pf.q = c.ld_q(Bn.cfg_off);
+      if (use_qd) pf.qd = c.ld_qd(Bn.dof_off);
+      if (use_qdd) pf.x = c.ld_x(Bn.dof_off);
+   };
+   prefetch(P.op[0]);
    for (int k = 0; k < nops; k++)
    {
       const uint32_t w = P.op[k];
       const int i = MB_OP_BODY(w);
       const MbBody &B = P.body[i];
       const T *C = c.cst(i);
+      const PfT<T> cur = pf;
+      if (k + 1 < nops)
+         prefetch(P.op[k + 1]);
       if (!(w & MB_OP_ASCEND))
       {
          // ---- pass one for body i (InverseDynamicsCalculator.java:873-917)
@@ -248,12 +287,12 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
             vp = v;
             ap = a;
          }
-         X = joint_transform<T>(c, B, C, jp);
+         X = joint_transform<T>(c, B, C, jp, cur.q);
          SvT<T> vj = sv_zero<T>(), aj = sv_zero<T>();
          if (use_qd)
-            vj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_qd(r); });
+            vj = joint_motion_pf<T>(B.jtype, B.dof_off, cur.qd, [&](int r) { return c.ld_qd(r); });
          if (use_qdd)
-            aj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_x(r); });
+            aj = joint_motion_pf<T>(B.jtype, B.dof_off, cur.x, [&](int r) { return c.ld_x(r); });
          v = motion_to_child(X, vp) + vj;
          a = motion_to_child(X, ap) + cross_motion(v, vj) + aj;
          // Newton-Euler (SpatialInertiaReadOnly.java:229-296), about the joint-frame origin
@@ -327,6 +366,21 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
    X.R = M3T<T>();
    X.p = v3<T>(0, 0, 0);
    const int nops = P.nops;
+   PfT<T> pf;
+   pf.q = pf.qd = pf.x = (T)0;
+   auto prefetch = [&](uint32_t wn) {
+      const MbBody &Bn = P.body[MB_OP_BODY(wn)];
+      if (Bn.jtype == MB_SIXDOF)
+         return;
+      if (wn & MB_OP_ASCEND)
+         pf.x = c.ld_x(Bn.dof_off); // tau of the joint whose subtree is about to be folded
+      else
+      {
+         pf.q = c.ld_q(Bn.cfg_off);
+         pf.qd = c.ld_qd(Bn.dof_off);
+      }
+   };
+   prefetch(P.op[0]);
    // ---- passes one and two interleaved along the depth-first traversal
    for (int k = 0; k < nops; k++)
    {
@@ -334,6 +388,9 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       const int i = MB_OP_BODY(w);
       const MbBody &B = P.body[i];
       const T *C = c.cst(i);
+      const PfT<T> cur = pf;
+      if (k + 1 < nops)
+         prefetch(P.op[k + 1]);
       if (!(w & MB_OP_ASCEND))
       {
          // twist of the body (the frame tree's lazy twist-of-frame, MovingReferenceFrame.java:279-311)
@@ -344,8 +401,8 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
             vp = stk_ld_sv<T>(c, P.body[B.parent].slot);
          else
             vp = v;
-         X = joint_transform<T>(c, B, C, jp);
-         vj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_qd(r); });
+         X = joint_transform<T>(c, B, C, jp, cur.q);
+         vj = joint_motion_pf<T>(B.jtype, B.dof_off, cur.qd, [&](int r) { return c.ld_qd(r); });
          v = motion_to_child(X, vp) + vj;
          if (!(w & MB_F_LEAF))
          {
@@ -396,7 +453,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
          {
             SvT<T> U;
             T D, u;
-            const T tau = c.ld_x(B.dof_off);
+            const T tau = cur.x;
             if (B.jtype == MB_REVOLUTE)
             {
                U.a = v3<T>(IA.A.xz, IA.A.yz, IA.A.zz);
@@ -472,11 +529,26 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
    // ---- pass three (:1259-1310), root to leaves, in the same depth-first order
    SvT<T> a = sv_zero<T>();
    v = sv_zero<T>();
+   auto prefetch3 = [&](int from) {
+      for (int kk = from; kk < nops; kk++)
+      {
+         const uint32_t wn = P.op[kk];
+         if (wn & MB_OP_ASCEND)
+            continue;
+         const MbBody &Bn = P.body[MB_OP_BODY(wn)];
+         if (Bn.jtype != MB_SIXDOF)
+            pf.qd = c.ld_qd(Bn.dof_off);
+         return;
+      }
+   };
+   prefetch3(0);
    for (int k = 0; k < nops; k++)
    {
       const uint32_t w = P.op[k];
       if (w & MB_OP_ASCEND)
          continue;
+      const T qd1 = pf.qd;
+      prefetch3(k + 1);
       const int i = MB_OP_BODY(w);
       const MbBody &B = P.body[i];
       const T *C = c.cst(i);
@@ -498,7 +570,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
          vp = v;
          ap = a;
       }
-      vj = joint_motion<T>(B.jtype, B.dof_off, [&](int r) { return c.ld_qd(r); });
+      vj = joint_motion_pf<T>(B.jtype, B.dof_off, qd1, [&](int r) { return c.ld_qd(r); });
       if (B.jtype != MB_SIXDOF)
       {
          SvT<T> g;
@@ -612,15 +684,27 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
    X.R = M3T<T>();
    X.p = v3<T>(0, 0, 0);
    const int nops = P.nops;
+   T pq = (T)0;
+   auto prefetch = [&](uint32_t wn) {
+      if (wn & MB_OP_ASCEND)
+         return;
+      const MbBody &Bn = P.body[MB_OP_BODY(wn)];
+      if (Bn.jtype != MB_SIXDOF)
+         pq = c.ld_q(Bn.cfg_off);
+   };
+   prefetch(P.op[0]);
    for (int k = 0; k < nops; k++)
    {
       const uint32_t w = P.op[k];
       const int i = MB_OP_BODY(w);
       const MbBody &B = P.body[i];
       const T *C = c.cst(i);
+      const T q1 = pq;
+      if (k + 1 < nops)
+         prefetch(P.op[k + 1]);
       if (!(w & MB_OP_ASCEND))
       {
-         X = joint_transform<T>(c, B, C, jp);
+         X = joint_transform<T>(c, B, C, jp, q1);
          if (!(w & MB_F_LEAF))
             stk_st_jp<T>(c, B.slot, B.jtype, jp);
          continue;

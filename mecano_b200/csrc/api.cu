@@ -119,9 +119,9 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
 {
    int rc = check_batch(h, n, ld);
    if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
    if (!q || !out || (algo != MB_CRBA && (!qd || !x)))
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   if (n == 0) return MECANO_B200_OK;
    std::lock_guard<std::mutex> lk(h->mu);
    MB_CUDA(h, cudaSetDevice(h->device));
    const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
@@ -272,6 +272,7 @@ int mecano_b200_rnea(mecano_b200_handle *h, int64_t n, int64_t ld, const double 
 {
    int rc = check_batch(h, n, ld);
    if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK; /* empty batch: nothing to do, pointers may be NULL */
    if (!q || !qd || !qdd || !tau) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    MB_CUDA(h, cudaSetDevice(h->device));
    return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream);
@@ -282,6 +283,7 @@ int mecano_b200_aba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *
 {
    int rc = check_batch(h, n, ld);
    if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !tau || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    MB_CUDA(h, cudaSetDevice(h->device));
    return run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, flags, (cudaStream_t)stream);
@@ -291,6 +293,7 @@ int mecano_b200_crba(mecano_b200_handle *h, int64_t n, int64_t ld, const double 
 {
    int rc = check_batch(h, n, ld);
    if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
    if (!q || !M) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    MB_CUDA(h, cudaSetDevice(h->device));
    return run(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, M, layout, (cudaStream_t)stream);

@@ -167,6 +167,16 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          return MECANO_B200_ERR_INVALID_ARGUMENT;
       }
    }
+   if (d->wrench_index)
+   {
+      std::vector<char> used(nb, 0);
+      for (int b = 0; b < nb; b++)
+         if (d->wrench_index[b] < 0 || d->wrench_index[b] >= nb || used[d->wrench_index[b]]++)
+         {
+            err = "wrench_index must be a permutation of 0..n_bodies-1";
+            return MECANO_B200_ERR_SHAPE;
+         }
+   }
    if (nv != d->n_dofs || nq != d->n_cfg)
    {
       err = "n_dofs / n_cfg do not match the joint types";
@@ -327,7 +337,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          B.dof_off = d->dof_offset[b];
          B.cfg_off = d->cfg_offset[b];
          B.subtree_end = subtree_end[i];
-         B.ext_index = b;
+         B.ext_index = d->wrench_index ? d->wrench_index[b] : b;
          B.depth = depth[i];
          B.ndof = B.jtype == MB_SIXDOF ? 6 : 1;
          // stack slot: leaves keep everything in registers; others stack up along the current path

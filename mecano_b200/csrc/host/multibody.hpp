@@ -239,7 +239,7 @@ class MultiBodySystem
 // Level-ordered parent / joint-type / axis / inertia / transform tables: the argument of mecano_b200_create.
 struct FlatTables
 {
-   std::vector<int32_t> level_start, parent, joint_type, dof_offset, cfg_offset;
+   std::vector<int32_t> level_start, parent, joint_type, dof_offset, cfg_offset, wrench_index;
    std::vector<double> axis, offset_rot, offset_pos, com_rot, com_pos, inertia, mass;
    std::vector<int> body_of_joint; // DFS joint index -> row in the tables
    mecano_b200_tree_desc desc{};
@@ -280,6 +280,7 @@ struct FlatTables
          f.joint_type.push_back((int)j->getType());
          f.dof_offset.push_back(sys.dofIndexAt(i));
          f.cfg_offset.push_back(sys.cfgIndexAt(i));
+         f.wrench_index.push_back(i); // external wrenches are handed over in joint (index-provider) order
          f.axis.insert(f.axis.end(), {j->getJointAxis().x, j->getJointAxis().y, j->getJointAxis().z});
          const RigidBodyTransform &T = j->getTransformToParent();
          f.offset_rot.insert(f.offset_rot.end(), T.rotation.m, T.rotation.m + 9);
@@ -313,6 +314,7 @@ struct FlatTables
       desc.mass = mass.data();
       desc.dof_offset = dof_offset.data();
       desc.cfg_offset = cfg_offset.data();
+      desc.wrench_index = wrench_index.empty() ? nullptr : wrench_index.data();
    }
 };
 

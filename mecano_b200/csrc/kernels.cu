@@ -19,21 +19,25 @@
 #include "algorithms.cuh"
 #include "kernels.h"
 
+// the dynamic shared memory of a block: [constant records | per-thread stack, state-minor]
+extern __shared__ double mb_smem[];
+
 namespace mb
 {
 namespace
 {
-template <int AUXN, int RECN> struct GpuCtx
+// BLOCK (threads per block = stack stride) is a compile-time constant so that stack addresses are
+// base + immediate; shared memory is addressed through the mb_smem symbol so that the compiler emits
+// LDS/STS (a pointer kept in a struct degrades to generic LD/ST).
+template <int BLOCK> struct GpuCtx
 {
    const double *q, *qd, *x, *fext;
    double *out;
    long long ld, s;
    int nv;
-   double *stk;       // shared memory, already offset by threadIdx.x
-   int stride;        // blockDim.x
-   const double *cb;  // shared memory constant records
-   double aux[AUXN > 0 ? AUXN : 1];
-   double rec[RECN > 0 ? RECN : 1];
+   int stk0;     // index in mb_smem of stack slot 0 of this thread
+   double *aux;  // local memory
+   double *rec;  // local memory
 
    __device__ __forceinline__ double ld_q(int r) const { return __ldg(q + r * ld + s); }
    __device__ __forceinline__ double ld_qd(int r) const { return __ldg(qd + r * ld + s); }
@@ -41,39 +45,40 @@ template <int AUXN, int RECN> struct GpuCtx
    __device__ __forceinline__ double ld_fext(int b, int k) const { return __ldg(fext + (6 * b + k) * ld + s); }
    __device__ __forceinline__ void st_out(int r, double v) { out[r * ld + s] = v; }
    __device__ __forceinline__ void st_M(int r, int c, double v) { __stcs(out + ((long long)r * nv + c) * ld + s, v); }
-   __device__ __forceinline__ double stk_ld(int i) const { return stk[i * stride]; }
-   __device__ __forceinline__ void stk_st(int i, double v) { stk[i * stride] = v; }
+   __device__ __forceinline__ double stk_ld(int i) const { return mb_smem[stk0 + i * BLOCK]; }
+   __device__ __forceinline__ void stk_st(int i, double v) { mb_smem[stk0 + i * BLOCK] = v; }
    __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
    __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
    __device__ __forceinline__ double rec_ld(int i) const { return rec[i]; }
    __device__ __forceinline__ void rec_st(int i, double v) { rec[i] = v; }
-   __device__ __forceinline__ const double *cst(int b) const { return cb + b * MB_CONST_STRIDE; }
+   __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
 };
 
 // state-major mass-matrix output (Mecano's per-state dense layout): uncoalesced, provided for drop-in use
-template <int AUXN, int RECN> struct GpuCtxStateMajor : GpuCtx<AUXN, RECN>
+template <int BLOCK> struct GpuCtxStateMajor : GpuCtx<BLOCK>
 {
    __device__ __forceinline__ void st_M(int r, int c, double v) { this->out[this->s * (long long)this->nv * this->nv + (long long)r * this->nv + c] = v; }
 };
 
-template <int ALGO, bool FEXT, bool STATE_MAJOR, int AUXN, int RECN>
-__global__ void __launch_bounds__(256) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
+template <int ALGO, bool FEXT, bool STATE_MAJOR, int BLOCK, int AUXN, int RECN>
+__global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
 {
-   extern __shared__ double smem[];
    const int ncst = P.nb * MB_CONST_STRIDE;
-   for (int i = threadIdx.x; i < ncst; i += blockDim.x)
-      smem[i] = a.consts[i];
+   for (int i = threadIdx.x; i < ncst; i += BLOCK)
+      mb_smem[i] = a.consts[i];
    __syncthreads();
-   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+   const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
    if (s >= a.n)
       return;
-   typedef typename std::conditional<STATE_MAJOR, GpuCtxStateMajor<AUXN, RECN>, GpuCtx<AUXN, RECN>>::type Ctx;
+   double aux[AUXN > 0 ? AUXN : 1];
+   double rec[RECN > 0 ? RECN : 1];
+   typedef typename std::conditional<STATE_MAJOR, GpuCtxStateMajor<BLOCK>, GpuCtx<BLOCK>>::type Ctx;
    Ctx c;
    c.q = a.q; c.qd = a.qd; c.x = a.x; c.fext = a.fext; c.out = a.out;
    c.ld = a.ld; c.s = s; c.nv = a.nv;
-   c.stk = smem + ((ncst + 1) & ~1) + threadIdx.x;
-   c.stride = blockDim.x;
-   c.cb = smem;
+   c.stk0 = ((ncst + 1) & ~1) + threadIdx.x;
+   c.aux = aux;
+   c.rec = rec;
    if constexpr (ALGO == MB_RNEA)
       rnea_state<double, Ctx, FEXT>(P, c, a.grav, !(a.flags & 1u), !(a.flags & 2u));
    else if constexpr (ALGO == MB_ABA)
@@ -83,29 +88,38 @@ __global__ void __launch_bounds__(256) thread_kernel(const __grid_constant__ MbP
 }
 
 // compiled work-area classes (local memory per thread): {aux, rec}
-//   class 0: up to 4 nested branching bodies, 32 one-DoF-equivalent records (humanoids)
-//   class 1: up to 16 nested branching bodies, 128 bodies
+//   class 0: up to 4 nested branching bodies, 32 one-DoF-equivalent records (humanoids); blocks of 256 / 128
+//   class 1: up to 16 nested branching bodies, 128 bodies; blocks of 128 / 64 / 32 (deeper stacks)
 constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
 constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
 constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
 constexpr int kAbaRec0 = 9 * 33 + 9, kAbaRec1 = 9 * 128 + 18;
+constexpr int kNumCfg = 5;
+constexpr int kCfgClass[kNumCfg] = {0, 0, 1, 1, 1};
+constexpr int kCfgBlock[kNumCfg] = {256, 128, 128, 64, 32};
 
 typedef void (*KernelFn)(const MbProgram, const KernelArgs);
 
-KernelFn pick(int algo, bool fext, bool state_major, int cls)
+template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
 {
-   if (algo == MB_RNEA)
+   constexpr int a0 = ALGO == MB_RNEA ? kRnaAux0 : (ALGO == MB_ABA ? kAbaAux0 : kCrbAux0);
+   constexpr int a1 = ALGO == MB_RNEA ? kRnaAux1 : (ALGO == MB_ABA ? kAbaAux1 : kCrbAux1);
+   constexpr int r0 = ALGO == MB_ABA ? kAbaRec0 : 0, r1 = ALGO == MB_ABA ? kAbaRec1 : 0;
+   switch (cfg)
    {
-      if (cls == 0) return fext ? thread_kernel<MB_RNEA, true, false, kRnaAux0, 0> : thread_kernel<MB_RNEA, false, false, kRnaAux0, 0>;
-      return fext ? thread_kernel<MB_RNEA, true, false, kRnaAux1, 0> : thread_kernel<MB_RNEA, false, false, kRnaAux1, 0>;
+      case 0: return thread_kernel<ALGO, FEXT, SM, 256, a0, r0>;
+      case 1: return thread_kernel<ALGO, FEXT, SM, 128, a0, r0>;
+      case 2: return thread_kernel<ALGO, FEXT, SM, 128, a1, r1>;
+      case 3: return thread_kernel<ALGO, FEXT, SM, 64, a1, r1>;
+      default: return thread_kernel<ALGO, FEXT, SM, 32, a1, r1>;
    }
-   if (algo == MB_ABA)
-   {
-      if (cls == 0) return fext ? thread_kernel<MB_ABA, true, false, kAbaAux0, kAbaRec0> : thread_kernel<MB_ABA, false, false, kAbaAux0, kAbaRec0>;
-      return fext ? thread_kernel<MB_ABA, true, false, kAbaAux1, kAbaRec1> : thread_kernel<MB_ABA, false, false, kAbaAux1, kAbaRec1>;
-   }
-   if (cls == 0) return state_major ? thread_kernel<MB_CRBA, false, true, kCrbAux0, 0> : thread_kernel<MB_CRBA, false, false, kCrbAux0, 0>;
-   return state_major ? thread_kernel<MB_CRBA, false, true, kCrbAux1, 0> : thread_kernel<MB_CRBA, false, false, kCrbAux1, 0>;
+}
+
+KernelFn pick(int algo, bool fext, bool state_major, int cfg)
+{
+   if (algo == MB_RNEA) return fext ? pick_cfg<MB_RNEA, true, false>(cfg) : pick_cfg<MB_RNEA, false, false>(cfg);
+   if (algo == MB_ABA) return fext ? pick_cfg<MB_ABA, true, false>(cfg) : pick_cfg<MB_ABA, false, false>(cfg);
+   return state_major ? pick_cfg<MB_CRBA, false, true>(cfg) : pick_cfg<MB_CRBA, false, false>(cfg);
 }
 
 int class_of(int algo, const MbProgram &P)
@@ -136,38 +150,41 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    if (e != cudaSuccess) return e;
    e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
    if (e != cudaSuccess) return e;
-   // every variant of this algorithm/class gets the opt-in so that later launches cannot fail on it
-   for (int f = 0; f < 2; f++)
-      for (int sm = 0; sm < 2; sm++)
-      {
-         e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, sm != 0, cls), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
-         if (e != cudaSuccess) return e;
-      }
-   KernelFn fn = pick(algo, fext, false, cls);
-   const int cand[] = {256, 224, 192, 160, 128, 96, 64, 32};
    int best_threads = 0;
-   for (int b : cand)
+   for (int cfg = 0; cfg < kNumCfg; cfg++)
    {
+      if (kCfgClass[cfg] < cls)
+         continue; // work areas too small
+      const int b = kCfgBlock[cfg];
       const size_t sm = smem_bytes(P, b);
       if (sm > (size_t)max_optin)
          continue;
+      // every variant of this configuration gets the opt-in so that later launches cannot fail on it
+      for (int f = 0; f < 2; f++)
+         for (int st = 0; st < 2; st++)
+         {
+            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st != 0, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+            if (e != cudaSuccess) return e;
+         }
+      KernelFn fn = pick(algo, fext, false, cfg);
       int nblk = 0;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, (const void *)fn, b, sm);
       if (e != cudaSuccess) return e;
+      // prefer more resident states; on ties the smaller work-area class (first in the table) wins
       if (nblk * b > best_threads)
       {
          best_threads = nblk * b;
          plan.block = b;
          plan.smem = sm;
          plan.blocks_per_sm = nblk;
+         plan.size_class = cfg;
       }
    }
    if (best_threads == 0)
       return cudaSuccess; // the stack of even a 32-state block does not fit in shared memory
    cudaFuncAttributes attr;
-   e = cudaFuncGetAttributes(&attr, (const void *)fn);
+   e = cudaFuncGetAttributes(&attr, (const void *)pick(algo, fext, false, plan.size_class));
    if (e != cudaSuccess) return e;
-   plan.size_class = cls;
    plan.regs = attr.numRegs;
    plan.local_bytes = (int)attr.localSizeBytes;
    plan.static_smem = (int)attr.sharedSizeBytes;

@@ -20,7 +20,7 @@ class TreeDescC(ctypes.Structure):
         ("struct_size", ctypes.c_int32), ("n_bodies", ctypes.c_int32), ("n_dofs", ctypes.c_int32), ("n_cfg", ctypes.c_int32),
         ("n_levels", ctypes.c_int32), ("level_start", _ip), ("parent", _ip), ("joint_type", _ip), ("axis", _dp),
         ("offset_rot", _dp), ("offset_pos", _dp), ("com_rot", _dp), ("com_pos", _dp), ("inertia", _dp), ("mass", _dp),
-        ("dof_offset", _ip), ("cfg_offset", _ip),
+        ("dof_offset", _ip), ("cfg_offset", _ip), ("wrench_index", _ip),
     ]
 
 

@@ -1,0 +1,84 @@
+"""CPU tests of the kernel mathematics: the per-state algorithm templates that the sm_100a kernels inline
+(mecano_b200/csrc/algorithms.cuh) are compiled for the host by tests/emu and compared with the oracle.  This is test
+infrastructure: the product library has no host compute path."""
+import numpy as np
+import pytest
+
+import emu_lib as el
+import oracle_lib as ol
+import treedesc as td
+
+TOL = 1e-9  # north_star: <= 1e-9 relative error in fp64
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
+
+
+def trees(rng):
+    return [
+        td.chain(rng, 1), td.chain(rng, 7), td.chain(rng, 6, prismatic_fraction=1.0), td.random_tree(rng, 30, prismatic_fraction=0.4),
+        td.chain(rng, 0, floating=True), td.chain(rng, 15, floating=True), td.random_tree(rng, 45, floating=True, com_rotation=True, prismatic_fraction=0.2),
+        td.random_tree(rng, 12, floating=True, axis_aligned=True), td.humanoid(rng, 2), td.humanoid(rng, 1), td.random_tree(rng, 100, floating=True),
+        td.chain(rng, 60),
+    ]
+
+
+@pytest.mark.parametrize("idx", range(12))
+def test_emulated_kernels_match_oracle(idx):
+    rng = np.random.default_rng(300 + idx)
+    t = trees(rng)[idx]
+    g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
+    o, e = ol.Oracle(t, gravity=g), el.Emu(t, gravity=g)
+    n = 6
+    q, qd, qdd, tau = td.random_states(rng, t, n)
+    fext = rng.uniform(-1, 1, size=(t.nb, 6, n))
+    fo = np.ascontiguousarray(fext.reshape(6 * t.nb, n))
+    assert rel(e.rnea(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < TOL
+    assert rel(e.rnea(q, qd, qdd, fext), o.rnea_batch(q, qd, qdd, fo)) < TOL
+    assert rel(e.rnea(q, qd, qdd, flags=1), o.rnea_batch(q, qd, qdd, flags=1)) < TOL
+    assert rel(e.rnea(q, qd, qdd, flags=2), o.rnea_batch(q, qd, qdd, flags=2)) < TOL
+    assert rel(e.rnea(q, qd, qdd, flags=3), o.rnea_batch(q, qd, qdd, flags=3)) < TOL
+    assert rel(e.aba(q, qd, tau), o.aba_batch(q, qd, tau)) < TOL
+    assert rel(e.aba(q, qd, tau, fext), o.aba_batch(q, qd, tau, fo)) < TOL
+    M = e.crba(q)
+    assert not np.isnan(M).any(), "every mass-matrix entry must be written (zeros included)"
+    assert rel(M, o.crba_batch(q)) < TOL
+
+
+def test_table_order_does_not_matter():
+    """The C-ABI accepts any topological listing of the bodies (level order from the Java host, or DFS)."""
+    rng = np.random.default_rng(9)
+    t = td.random_tree(rng, 20, floating=True, prismatic_fraction=0.3)
+    q, qd, qdd, tau = td.random_states(rng, t, 4)
+    a = el.Emu(t, level_ordered=True)
+    b = el.Emu(t, level_ordered=False)
+    assert np.array_equal(a.rnea(q, qd, qdd), b.rnea(q, qd, qdd))
+    assert np.array_equal(a.aba(q, qd, tau), b.aba(q, qd, tau))
+    assert np.array_equal(a.crba(q), b.crba(q))
+
+
+def test_fp32_variant_tolerance():
+    """The optional fp32 instantiation is reported separately with its own tolerance (1e-4..1e-3
+    relative on these trees)."""
+    rng = np.random.default_rng(10)
+    t = td.humanoid(rng, 2)
+    o, e = ol.Oracle(t), el.Emu(t, fp32=True)
+    q, qd, qdd, tau = td.random_states(rng, t, 8)
+    assert rel(e.rnea(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < 2e-4
+    assert rel(e.crba(q), o.crba_batch(q)) < 2e-4
+    assert rel(e.aba(q, qd, tau), o.aba_batch(q, qd, tau)) < 5e-2
+
+
+def test_stack_sizes_follow_depth_not_body_count():
+    """The interleaved traversal keeps per-state data only for the current root-to-leaf path."""
+    rng = np.random.default_rng(11)
+    h37 = el.Emu(td.humanoid(rng, 2))
+    big = el.Emu(td.random_tree(rng, 100, floating=True))
+    for algo, per_level in ((0, 8), (1, 9), (2, 2)):
+        info = h37.program_info(algo)
+        assert info["nops"] == 2 * info["nb"]
+        # SixDoF root slot is larger by 10 (12 transform entries instead of sin/cos) (+5 joint velocities for ABA)
+        assert info["stack"] <= per_level * (info["max_depth"] - 1) + 16
+        assert big.program_info(algo)["stack"] <= per_level * big.program_info(algo)["max_depth"] + 16
+    assert h37.program_info(1)["rec"] == 9 * 31 + 18

@@ -1,0 +1,248 @@
+"""GPU parity tests (run with -m gpu on a B200): every kernel, through the calculator API and the C ABI underneath,
+against the CPU oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's
+full sizes -- through the size-independent invariants of the reference's own tests (FD o ID = id,
+M qdd + ID(qdd = 0) = ID(qdd)).  Tolerance: 1e-9 relative in fp64 (north_star), error idiom of
+ForwardDynamicsCalculatorTest.java:1099-1107."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import treedesc as td
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
+
+
+@pytest.fixture(scope="module")
+def torch_dev():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device; the product has no CPU fallback"
+    return torch, torch.device("cuda:0")
+
+
+def build(kind, seed, n_joints=0, prismatic=0.0, floating=False):
+    import mecano_b200 as mb
+
+    e = mb.RigidBody("elevator")
+    base = e
+    if kind == "humanoid":
+        mb.MultiBodySystemRandomTools.nextHumanoid(seed, e, n_joints)
+    else:
+        if floating:
+            base = mb.MultiBodySystemRandomTools.nextFloatingBase(seed + 1000, e).getSuccessor()
+        if kind == "chain":
+            mb.MultiBodySystemRandomTools.nextOneDoFJointChain(seed, base, n_joints, prismatic)
+        else:
+            mb.MultiBodySystemRandomTools.nextOneDoFJointTree(seed, base, n_joints, prismatic)
+    s = mb.MultiBodySystem.toMultiBodySystemBasics(e)
+    return s, td.TreeDesc(**s.describe()).contiguous()
+
+
+CASES = [
+    ("A7 revolute chain", dict(kind="chain", seed=1, n_joints=7)),
+    ("single joint", dict(kind="chain", seed=2, n_joints=1)),
+    ("prismatic chain", dict(kind="chain", seed=3, n_joints=6, prismatic=1.0)),
+    ("one-dof tree 30", dict(kind="tree", seed=4, n_joints=30, prismatic=0.4)),
+    ("floating + chain 20", dict(kind="chain", seed=5, n_joints=20, floating=True)),
+    ("floating + tree 50", dict(kind="tree", seed=6, n_joints=50, floating=True, prismatic=0.2)),
+    ("H37", dict(kind="humanoid", seed=7, n_joints=2)),
+    ("H36", dict(kind="humanoid", seed=8, n_joints=1)),
+    ("tree 100", dict(kind="tree", seed=9, n_joints=100, floating=True)),
+    ("deep chain 60", dict(kind="chain", seed=10, n_joints=60)),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_kernels_match_oracle(torch_dev, idx):
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(1000 + idx)
+    g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
+    o = ol.Oracle(t, gravity=g)
+    n = 777  # ragged: not a multiple of the block size
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    fext = np.ascontiguousarray(rng.uniform(-1, 1, size=(6 * t.nb, n)))
+    tq, tqd, tqdd, ttau, tf = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, tau, fext))
+    nv = t.nv
+
+    ident = mb.InverseDynamicsCalculator(s)
+    ident.setGravitationalAcceleration(g)
+    assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd)) < TOL, name
+    ident.setExternalWrenches(tf)
+    assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd, fext)) < TOL, name
+    ident.setExternalWrenchesToZero()
+    ident.setConsiderCoriolisAndCentrifugalForces(False)
+    assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd, flags=1)) < TOL, name
+    ident.setConsiderJointAccelerations(False)
+    assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd, flags=3)) < TOL, name
+
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    fdyn.setGravitationalAcceleration(*g)
+    assert rel(fdyn.compute(tq, tqd, ttau).cpu().numpy(), o.aba_batch(q, qd, tau)) < TOL, name
+    fdyn.setExternalWrenches(tf)
+    assert rel(fdyn.compute(tq, tqd, ttau).cpu().numpy(), o.aba_batch(q, qd, tau, fext)) < TOL, name
+
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    Mo = o.crba_batch(q)
+    M = crba.getMassMatrix(tq, torch.full((nv * nv, n), float("nan"), dtype=torch.float64, device=dev))
+    assert not torch.isnan(M).any(), "every entry of the dense matrix must be written"
+    assert rel(M.cpu().numpy().reshape(nv, nv, n), Mo) < TOL, name
+    Ms = crba.getMassMatrix(tq, stateMajor=True)  # Mecano's per-state dense layout
+    assert rel(Ms.cpu().numpy().reshape(n, nv, nv).transpose(1, 2, 0), Mo) < TOL, name
+
+
+def test_host_entry_points_and_leading_dimension(torch_dev):
+    """*_host entry points (numpy in, numpy out), with ld > n, plus empty and single-state batches."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="tree", seed=21, n_joints=25, floating=True, prismatic=0.3)
+    o = ol.Oracle(t, gravity=(0, 0, -9.81))
+    rng = np.random.default_rng(21)
+    n, ld = 5000, 5120
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, ld)
+    ident = mb.InverseDynamicsCalculator(s)
+    ident.setGravitationalAcceleration(-9.81)
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    fdyn.setGravitationalAcceleration(-9.81)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    out = np.full((t.nv, ld), np.nan)
+    ident.compute(q[:, :n], qd[:, :n], qdd[:, :n], out[:, :n])
+    assert np.isnan(out[:, n:]).all(), "columns beyond n must not be touched"
+    assert rel(out[:, :n], o.rnea_batch(q[:, :n], qd[:, :n], qdd[:, :n])) < TOL
+    assert rel(fdyn.compute(q[:, :n], qd[:, :n], tau[:, :n]), o.aba_batch(q[:, :n], qd[:, :n], tau[:, :n])) < TOL
+    ns = 300
+    assert rel(crba.getMassMatrix(q[:, :ns]).reshape(t.nv, t.nv, ns), o.crba_batch(q[:, :ns])) < TOL
+    assert rel(crba.getMassMatrix(np.ascontiguousarray(q[:, :ns]), stateMajor=True).reshape(ns, t.nv, t.nv).transpose(1, 2, 0), o.crba_batch(q[:, :ns])) < TOL
+    # device path with ld > n
+    tq, tqd, tqdd = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd))
+    tout = torch.full((t.nv, ld), float("nan"), dtype=torch.float64, device=dev)
+    ident.compute(tq[:, :n], tqd[:, :n], tqdd[:, :n], tout[:, :n])
+    assert torch.isnan(tout[:, n:]).all()
+    assert rel(tout[:, :n].cpu().numpy(), out[:, :n]) == 0.0, "host and device entry points run the same kernel"
+    # empty and single-state batches
+    assert ident.compute(tq[:, :0], tqd[:, :0], tqdd[:, :0]).shape == (t.nv, 0)
+    one = ident.compute(tq[:, :1], tqd[:, :1], tqdd[:, :1]).cpu().numpy()
+    assert rel(one, out[:, :1]) == 0.0
+
+
+def test_error_behaviour(torch_dev):
+    """Shape errors raise like EJML's MatrixDimensionException (ForwardDynamicsCalculator.java:522-533)."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="chain", seed=30, n_joints=4)
+    ident = mb.InverseDynamicsCalculator(s)
+    good = torch.zeros((4, 10), dtype=torch.float64, device=dev)
+    with pytest.raises(mb.MatrixDimensionException):
+        ident.compute(good, good, torch.zeros((5, 10), dtype=torch.float64, device=dev))
+    with pytest.raises(mb.MatrixDimensionException):
+        ident.compute(good, good[:, :9], good)
+    with pytest.raises(TypeError):
+        ident.compute(good, good, good.float())
+    ident.setExternalWrenches(torch.zeros((6 * 3, 10), dtype=torch.float64, device=dev))
+    with pytest.raises(mb.MatrixDimensionException):
+        ident.compute(good, good, good)
+
+
+def test_golden_fixtures_on_gpu(torch_dev):
+    """The committed regression vectors (tests/golden, generated by the oracle) through the raw C ABI."""
+    import mecano_b200 as mb
+    from mecano_b200 import _capi
+
+    import emu_lib as el
+
+    torch, dev = torch_dev
+    data = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz"))
+    for name in sorted({k.split("/")[0] for k in data.files}):
+        t = td.TreeDesc(**{f: data["%s/%s" % (name, f)] for f in ("parent", "jtype", "axis", "off_R", "off_p", "com_R", "com_p", "J", "mass", "dof_off", "cfg_off")},
+                        nb=int(data[name + "/dims"][0]), nv=int(data[name + "/dims"][1]), nq=int(data[name + "/dims"][2])).contiguous()
+        d, keep, order = el.tree_desc_c(t)  # level-ordered tables, wrench rows in table order
+        e = mb.Engine(_capi.TreeDesc.from_buffer_copy(bytes(d)), 0, keepalive=keep)
+        e.set_gravity(*data[name + "/gravity"])
+        q, qd, qdd, tau, fext = (data["%s/%s" % (name, f)] for f in ("q", "qd", "qdd", "tau", "fext"))
+        n = q.shape[1]
+        fe = np.ascontiguousarray(fext.reshape(t.nb, 6, n)[order].reshape(6 * t.nb, n))
+        tq, tqd, tqdd, ttau, tf = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (q, qd, qdd, tau, fe))
+        out = torch.empty_like(tqd)
+        assert rel(e.rnea(tq, tqd, tqdd, out, fext=tf).cpu().numpy(), data[name + "/rnea"]) < TOL
+        assert rel(e.aba(tq, tqd, ttau, out, fext=tf).cpu().numpy(), data[name + "/aba"]) < TOL
+        M = torch.empty((t.nv * t.nv, n), dtype=torch.float64, device=dev)
+        assert rel(e.crba(tq, M).cpu().numpy().reshape(t.nv, t.nv, n), data[name + "/crba"]) < TOL
+        e.close()
+
+
+def test_baseline_config_2_a7_65536_states_per_state(torch_dev):
+    """BASELINE.json configs[1]: batched RNEA, 7-DoF revolute arm, 65,536 random states, verified per state."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="chain", seed=65536, n_joints=7)
+    n = 65536
+    rng = np.random.default_rng(65536)
+    q, qd, qdd, _ = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    ident = mb.InverseDynamicsCalculator(s)
+    ident.setGravitationalAcceleration(-9.81)
+    tau = ident.compute(*(torch.from_numpy(x).to(dev) for x in (q, qd, qdd))).cpu().numpy()
+    ref = ol.Oracle(t, gravity=(0, 0, -9.81)).rnea_batch(q, qd, qdd)
+    per_state = np.max(np.abs(tau - ref), axis=0) / np.maximum(1.0, np.max(np.abs(ref), axis=0))
+    assert per_state.max() < TOL
+
+
+@pytest.mark.parametrize("neck", [2, 1])
+def test_baseline_configs_3_4_humanoid_1m_states_invariants(torch_dev, neck):
+    """BASELINE.json configs[2..3]: ABA and CRBA on the humanoid at 1M states.  Checked on device through the reference's
+    invariants (size-independent), and against the oracle on a strided sample of 512 states."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="humanoid", seed=99, n_joints=neck)
+    nv, nq, n = t.nv, t.nq, 1 << 20
+    gen = torch.Generator(device=dev).manual_seed(5)
+    q = (torch.rand((nq, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * np.pi
+    quat = torch.randn((4, n), dtype=torch.float64, device=dev, generator=gen)
+    q[0:4] = quat / quat.norm(dim=0, keepdim=True)
+    q[4:7] = torch.rand((3, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qdd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    ident = mb.InverseDynamicsCalculator(s)
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    ident.setGravitationalAcceleration(-9.81)
+    fdyn.setGravitationalAcceleration(-9.81)
+    tau = ident.compute(q, qd, qdd)
+    back = fdyn.compute(q, qd, tau)
+    # FD(ID(qdd)) == qdd  (ForwardDynamicsCalculatorTest.java:223-251, tolerance 4e-11 scaled by max(1, ||expected||))
+    scale = torch.clamp(qdd.norm(dim=0), min=1.0)
+    assert float(((back - qdd).abs().max(dim=0).values / scale).max()) < 1e-9
+    # M qdd + ID(qdd = 0) == ID(qdd)  (:904-1003), in chunks to bound memory
+    ident.setConsiderJointAccelerations(False)
+    bias = ident.compute(q, qd, qdd)
+    chunk = 1 << 17
+    worst = 0.0
+    for a in range(0, n, chunk):
+        M = crba.getMassMatrix(q[:, a:a + chunk].contiguous()).reshape(nv, nv, -1)
+        lhs = torch.einsum("ijs,js->is", M, qdd[:, a:a + chunk]) + bias[:, a:a + chunk]
+        sc = torch.clamp(tau[:, a:a + chunk].norm(dim=0), min=1.0)
+        worst = max(worst, float(((lhs - tau[:, a:a + chunk]).abs().max(dim=0).values / sc).max()))
+        assert float((M - M.transpose(0, 1)).abs().max()) == 0.0, "symmetric entries are written from one value"
+    assert worst < 1e-9
+    # strided sample against the oracle
+    idx = torch.arange(0, n, n // 512, device=dev)
+    hq, hqd, hqdd, htau, hback = (x[:, idx].cpu().numpy().copy() for x in (q, qd, qdd, tau, back))
+    o = ol.Oracle(t, gravity=(0, 0, -9.81))
+    assert rel(htau, o.rnea_batch(hq, hqd, hqdd)) < TOL
+    assert rel(hback, o.aba_batch(hq, hqd, htau)) < TOL
+    Ms = crba.getMassMatrix(q[:, idx].contiguous()).cpu().numpy().reshape(nv, nv, -1)
+    assert rel(Ms, o.crba_batch(hq)) < TOL
