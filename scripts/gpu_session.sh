@@ -1,0 +1,19 @@
+#!/bin/bash
+# One GPU-box session: parity tests, a bench line, the ncu launch list and one full capture per kernel.
+# Usage (from the repo root, under gpurun): bash scripts/gpu_session.sh <tag>
+TAG=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${TAG}_pytest.log
+tail -5 gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
+echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
+cat gpurun_out/${TAG}_bench_ref.json
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
+   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:thread_kernel -c 3 -f -o gpurun_out/${TAG}_prof \
+   python scripts/prof_run.py 1048576 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
+tail -3 gpurun_out/${TAG}_ncu_full.log
+ls -la gpurun_out
