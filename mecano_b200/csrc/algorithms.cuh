@@ -24,70 +24,24 @@
 #pragma once
 #include "program.h"
 #include "spatial.cuh"
+#include "jointmath.cuh"
+#include "rnea.cuh"
 
 namespace mb
 {
-MB_HD void mb_sincos(double x, double *s, double *c)
-{
-#if defined(__CUDA_ARCH__)
-   sincos(x, s, c);
-#else
-   *s = sin(x);
-   *c = cos(x);
-#endif
-}
-MB_HD void mb_sincos(float x, float *s, float *c)
-{
-#if defined(__CUDA_ARCH__)
-   sincosf(x, s, c);
-#else
-   *s = sinf(x);
-   *c = cosf(x);
-#endif
-}
-
-template <class T> MB_HD M3T<T> ld_m3(const T *p)
-{
-   M3T<T> r;
-   r.xx = p[0]; r.xy = p[1]; r.xz = p[2]; r.yx = p[3]; r.yy = p[4]; r.yz = p[5]; r.zx = p[6]; r.zy = p[7]; r.zz = p[8];
-   return r;
-}
-template <class T> MB_HD V3T<T> ld_v3(const T *p) { return v3<T>(p[0], p[1], p[2]); }
-template <class T> MB_HD RbiT<T> ld_rbi(const T *c)
-{
-   RbiT<T> r;
-   r.I.xx = c[MB_C_I + 0]; r.I.xy = c[MB_C_I + 1]; r.I.xz = c[MB_C_I + 2]; r.I.yy = c[MB_C_I + 3]; r.I.yz = c[MB_C_I + 4]; r.I.zz = c[MB_C_I + 5];
-   r.h = ld_v3(c + MB_C_H);
-   r.m = c[MB_C_M];
-   return r;
-}
-
 // ---- stack helpers
-template <class T, class Ctx> MB_HD void stk_st_sv(Ctx &c, int i, const SvT<T> &v)
+template <class T, class Ctx> MB_HD void stk1_st_sv(Ctx &c, int i, const SvT<T> &v)
 {
    c.stk_st(i + 0, v.a.x); c.stk_st(i + 1, v.a.y); c.stk_st(i + 2, v.a.z);
    c.stk_st(i + 3, v.l.x); c.stk_st(i + 4, v.l.y); c.stk_st(i + 5, v.l.z);
 }
-template <class T, class Ctx> MB_HD SvT<T> stk_ld_sv(Ctx &c, int i)
+template <class T, class Ctx> MB_HD SvT<T> stk1_ld_sv(Ctx &c, int i)
 {
    SvT<T> v;
    v.a = v3<T>(c.stk_ld(i + 0), c.stk_ld(i + 1), c.stk_ld(i + 2));
    v.l = v3<T>(c.stk_ld(i + 3), c.stk_ld(i + 4), c.stk_ld(i + 5));
    return v;
 }
-template <class T, class Ctx> MB_HD void aux_st_sv(Ctx &c, int i, const SvT<T> &v)
-{
-   c.aux_st(i + 0, v.a.x); c.aux_st(i + 1, v.a.y); c.aux_st(i + 2, v.a.z);
-   c.aux_st(i + 3, v.l.x); c.aux_st(i + 4, v.l.y); c.aux_st(i + 5, v.l.z);
-}
-template <class T, class Ctx> MB_HD SvT<T> aux_ld_sv(Ctx &c, int i)
-{
-   SvT<T> v;
-   v.a = v3<T>(c.aux_ld(i + 0), c.aux_ld(i + 1), c.aux_ld(i + 2));
-   v.l = v3<T>(c.aux_ld(i + 3), c.aux_ld(i + 4), c.aux_ld(i + 5));
-   return v;
-}
-
 // Joint parameters: what must be kept to rebuild the joint transform on the way back up.
 template <class T> struct JpT
 {
@@ -223,7 +177,7 @@ template <class T> struct PfT
 };
 
 // external wrench on a body, given in its CoM frame, re-expressed in the canonical joint frame
-template <class T, class Ctx> MB_HD SvT<T> external_wrench(Ctx &c, const MbBody &B, const T *C)
+template <class T, class Ctx> MB_HD SvT<T> external_wrench_b(Ctx &c, const MbBody &B, const T *C)
 {
    SvT<T> w, r;
    const int e = B.ext_index;
@@ -233,110 +187,6 @@ template <class T, class Ctx> MB_HD SvT<T> external_wrench(Ctx &c, const MbBody 
    r.l = mul(E, w.l);
    r.a = mul(E, w.a) + cross(ld_v3(C + MB_C_C), r.l);
    return r;
-}
-
-// ======================================================================================== RNEA
-template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav, bool use_qd, bool use_qdd)
-{
-   SvT<T> v = sv_zero<T>(), a = sv_zero<T>(), f = sv_zero<T>();
-   XfT<T> X;
-   JpT<T> jp;
-   X.R = M3T<T>();
-   X.p = v3<T>(0, 0, 0);
-   const int nops = P.nops;
-   PfT<T> pf;
-   pf.q = pf.qd = pf.x = (T)0;
-   auto prefetch = [&](uint32_t wn) {
-      if (wn & MB_OP_ASCEND)
-         return;
-      const MbBody &Bn = P.body[MB_OP_BODY(wn)];
-      if (Bn.jtype == MB_SIXDOF)
-         return;
-      pf.q = c.ld_q(Bn.cfg_off);
-      if (use_qd) pf.qd = c.ld_qd(Bn.dof_off);
-      if (use_qdd) pf.x = c.ld_x(Bn.dof_off);
-   };
-   prefetch(P.op[0]);
-   for (int k = 0; k < nops; k++)
-   {
-      const uint32_t w = P.op[k];
-      const int i = MB_OP_BODY(w);
-      const MbBody &B = P.body[i];
-      const T *C = c.cst(i);
-      const PfT<T> cur = pf;
-      if (k + 1 < nops)
-         prefetch(P.op[k + 1]);
-      if (!(w & MB_OP_ASCEND))
-      {
-         // ---- pass one for body i (InverseDynamicsCalculator.java:873-917)
-         SvT<T> vp, ap;
-         if (w & MB_F_ROOT_PARENT)
-         {
-            vp = sv_zero<T>();
-            ap = sv_zero<T>();
-            ap.l = v3<T>(-grav[0], -grav[1], -grav[2]); // root acceleration = -gravity (:397-403)
-         }
-         else if (w & MB_F_LOAD_PARENT)
-         {
-            const int pa = P.body[B.parent].aux;
-            vp = aux_ld_sv<T>(c, pa);
-            ap = aux_ld_sv<T>(c, pa + 6);
-         }
-         else
-         {
-            vp = v;
-            ap = a;
-         }
-         X = joint_transform<T>(c, B, C, jp, cur.q);
-         SvT<T> vj = sv_zero<T>(), aj = sv_zero<T>();
-         if (use_qd)
-            vj = joint_motion_pf<T>(B.jtype, B.dof_off, cur.qd, [&](int r) { return c.ld_qd(r); });
-         if (use_qdd)
-            aj = joint_motion_pf<T>(B.jtype, B.dof_off, cur.x, [&](int r) { return c.ld_x(r); });
-         v = motion_to_child(X, vp) + vj;
-         a = motion_to_child(X, ap) + cross_motion(v, vj) + aj;
-         // Newton-Euler (SpatialInertiaReadOnly.java:229-296), about the joint-frame origin
-         const RbiT<T> I = ld_rbi(C);
-         f = mul(I, a) + cross_force(v, mul(I, v));
-         if (FEXT)
-            f = f - external_wrench<T>(c, B, C); // :946
-         if (!(w & MB_F_LEAF))
-         {
-            stk_st_sv<T>(c, B.slot, f);
-            stk_st_jp<T>(c, B.slot + 6, B.jtype, jp);
-         }
-         if (w & MB_F_SAVE_STATE)
-         {
-            aux_st_sv<T>(c, B.aux, v);
-            aux_st_sv<T>(c, B.aux + 6, a);
-         }
-      }
-      else
-      {
-         // ---- pass two for body i (:930-966); f holds the wrench of the whole subtree
-         if (!(w & MB_F_LEAF))
-         {
-            stk_ld_jp<T>(c, B.slot + 6, B.jtype, jp);
-            X = rebuild_transform<T>(B.jtype, C, jp);
-         }
-         if (B.jtype == MB_REVOLUTE)
-            c.st_out(B.dof_off, f.a.z); // tau = S^T W (:952-958)
-         else if (B.jtype == MB_PRISMATIC)
-            c.st_out(B.dof_off, f.l.z);
-         else
-         {
-            c.st_out(B.dof_off + 0, f.a.x); c.st_out(B.dof_off + 1, f.a.y); c.st_out(B.dof_off + 2, f.a.z);
-            c.st_out(B.dof_off + 3, f.l.x); c.st_out(B.dof_off + 4, f.l.y); c.st_out(B.dof_off + 5, f.l.z);
-         }
-         if (!(w & MB_F_ROOT_PARENT))
-         {
-            const int ps = P.body[B.parent].slot;
-            f = stk_ld_sv<T>(c, ps) + force_to_parent(X, f); // addJointWrenchFromChild (:961-966)
-            if (w & MB_F_STORE_ACC)
-               stk_st_sv<T>(c, ps, f);
-         }
-      }
-   }
 }
 
 // ======================================================================================== ABA
@@ -398,7 +248,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
          if (w & MB_F_ROOT_PARENT)
             vp = sv_zero<T>();
          else if (w & MB_F_LOAD_PARENT)
-            vp = stk_ld_sv<T>(c, P.body[B.parent].slot);
+            vp = stk1_ld_sv<T>(c, P.body[B.parent].slot);
          else
             vp = v;
          X = joint_transform<T>(c, B, C, jp, cur.q);
@@ -406,7 +256,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
          v = motion_to_child(X, vp) + vj;
          if (!(w & MB_F_LEAF))
          {
-            stk_st_sv<T>(c, B.slot, v);
+            stk1_st_sv<T>(c, B.slot, v);
             const int njp = mb_jp_size(B.jtype);
             stk_st_jp<T>(c, B.slot + 6, B.jtype, jp);
             if (B.jtype == MB_REVOLUTE)
@@ -414,14 +264,14 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
             else if (B.jtype == MB_PRISMATIC)
                c.stk_st(B.slot + 6 + njp, vj.l.z);
             else
-               stk_st_sv<T>(c, B.slot + 6 + njp, vj);
+               stk1_st_sv<T>(c, B.slot + 6 + njp, vj);
          }
       }
       else
       {
          if (!(w & MB_F_LEAF))
          {
-            v = stk_ld_sv<T>(c, B.slot);
+            v = stk1_ld_sv<T>(c, B.slot);
             const int njp = mb_jp_size(B.jtype);
             stk_ld_jp<T>(c, B.slot + 6, B.jtype, jp);
             X = rebuild_transform<T>(B.jtype, C, jp);
@@ -431,13 +281,13 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
             else if (B.jtype == MB_PRISMATIC)
                vj.l.z = c.stk_ld(B.slot + 6 + njp);
             else
-               vj = stk_ld_sv<T>(c, B.slot + 6 + njp);
+               vj = stk1_ld_sv<T>(c, B.slot + 6 + njp);
          }
          // pass one quantities (ForwardDynamicsCalculator.java:1109-1118): bias wrench and bias acceleration
          const RbiT<T> I = ld_rbi(C);
          SvT<T> pA = cross_force(v, mul(I, v));
          if (FEXT)
-            pA = pA - external_wrench<T>(c, B, C);
+            pA = pA - external_wrench_b<T>(c, B, C);
          const SvT<T> cb = cross_motion(v, vj);
          // pass two (:1136-1254)
          AbiT<T> IA = abi_from_rbi(I);

@@ -99,6 +99,71 @@ int aux_size(int algo)
 }
 
 int rec_size(int jtype) { return jtype == MB_SIXDOF ? 18 : 9; }
+
+// v2 stack slots, in double2 units (rnea.cuh / aba.cuh / crba.cuh)
+int slot2_size(int algo, int jtype, bool root_parent)
+{
+   switch (algo)
+   {
+      case MB_RNEA: // wrench (3) + sin/cos (1); SixDoF: wrench (3) + transform (6) unless attached to the root body
+         return jtype == MB_SIXDOF ? (root_parent ? 3 : 9) : 4;
+      case MB_ABA: // twist (3) + sin/cos (1) + joint velocity (1); SixDoF: twist (3) + transform (6) + joint twist (3)
+         return jtype == MB_SIXDOF ? 12 : 5;
+      default: // CRBA: sin/cos (1); SixDoF: transform (6)
+         return jtype == MB_SIXDOF ? 6 : 1;
+   }
+}
+
+// Pre-decode the op words into MbOp2 records (program.h).
+void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
+{
+   const int nb = P.nb;
+   std::vector<int> slot2(nb, 0);
+   P.stack2 = 1;
+   for (int i = 0; i < nb; i++)
+   {
+      const MbBody &B = P.body[i];
+      int s = 0;
+      if (B.parent >= 0)
+      {
+         const MbBody &Bp = P.body[B.parent];
+         s = slot2[B.parent] + slot2_size(algo, Bp.jtype, Bp.parent < 0);
+      }
+      slot2[i] = s;
+      // leaves keep their data in registers, except SixDoF joints which always use their slot
+      if (nchild[i] > 0 || B.jtype == MB_SIXDOF)
+         P.stack2 = std::max(P.stack2, s + slot2_size(algo, B.jtype, B.parent < 0));
+   }
+   std::memset(P.op2, 0, sizeof P.op2);
+   for (int k = 0; k < P.nops; k++)
+   {
+      const uint32_t w = P.op[k];
+      const int i = MB_OP_BODY(w);
+      const MbBody &B = P.body[i];
+      MbOp2 &o = P.op2[k];
+      o.code = (uint8_t)((w & MB_OP_ASCEND) | ((uint32_t)B.jtype << 1));
+      o.flags = (uint8_t)((w & 0xfeu) >> 1);
+      o.body = (uint8_t)i;
+      o.cfg = (uint16_t)B.cfg_off;
+      o.dof = (uint16_t)B.dof_off;
+      o.slot = (uint16_t)slot2[i];
+      o.pslot = (uint16_t)(B.parent >= 0 ? slot2[B.parent] : 0);
+      o.aux = (uint16_t)(B.aux >= 0 ? B.aux : 0);
+      o.paux = (uint16_t)(B.parent >= 0 && P.body[B.parent].aux >= 0 ? P.body[B.parent].aux : 0);
+   }
+   // trailing records: ASCEND of a SixDoF joint can never be mistaken for a 1-DoF DESCEND by the look-ahead
+   for (int k = P.nops; k < P.nops + 4; k++)
+      P.op2[k].code = (uint8_t)(MB2_ASCEND | (MB_SIXDOF << 1));
+   for (int k = 0; k < P.nops; k++)
+   {
+      const MbOp2 &n1 = P.op2[k + 1], &n2 = P.op2[k + 2];
+      if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) == MB_REVOLUTE)
+         P.op2[k].code |= MB2_SC;
+      (void)n2;
+      if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) != MB_SIXDOF)
+         P.op2[k].pf |= 1u;
+   }
+}
 } // namespace
 
 int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err)
@@ -413,6 +478,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          P.op[nops++] = w;
       }
       P.nops = nops;
+      build_op2(algo, P, nchild);
    }
    return MECANO_B200_OK;
 }

@@ -1,0 +1,219 @@
+// jointmath.cuh -- helpers shared by the per-algorithm state routines (rnea.cuh, aba.cuh, crba.cuh): constant-record
+// loads, joint transforms in canonical frames, stack / save-area accessors.
+//
+// Context policy (all methods inline; GPU: kernels.cu, host emulation: tests/emu/emu.cpp):
+//   T    ld_q(row) ld_qd(row) ld_x(row)          inputs in Mecano row order (x = qdd for RNEA, tau for ABA)
+//   T    ld_fext(ext_body, comp)                 external wrench rows
+//   void st_out(row, T)                          tau (RNEA) / qdd (ABA)
+//   void st_M(row, col, T)                       mass-matrix entry (CRBA)
+//   void stk_ld2(slot2, j, T&, T&) / stk_st2     per-state stack of double2 (shared memory on the GPU)
+//   T    aux_ld(i) / aux_st, rec_ld / rec_st     per-state branch-save and record areas (local memory)
+//   const T* cst(body)                           constant record of a body (shared memory on the GPU)
+#pragma once
+#include "program.h"
+#include "spatial.cuh"
+#include <string.h>
+
+namespace mb
+{
+// ---- sin/cos
+// Branch-free double-precision sincos for |x| <= MB_SINCOS_FAST_LIMIT, so that it can be scheduled inside the same
+// basic block as the spatial algebra of an op (the CUDA library routine carries a Payne-Hanek slow-path call that
+// splits the block).  Cody-Waite reduction by pi/2 in three FMA steps, then the fdlibm kernel polynomials
+// (|r| <= pi/4, error < 1 ulp).  Arguments beyond the limit are first brought into range by mb_reduce_angle(), off
+// the hot path.  Java's Math.sin/cos (what Mecano calls through Euclid, MecanoFactories.java:231-260) are specified
+// to 1 ulp; the difference is far below the 1e-9 parity tolerance.
+#define MB_SINCOS_FAST_LIMIT 1.0e5
+#if defined(__CUDA_ARCH__)
+#define MB_CONST_TABLE static __constant__
+#else
+#define MB_CONST_TABLE static const
+#endif
+MB_CONST_TABLE double mb_sc_tab[18] = {
+   6.36619772367581382433e-01,                                                             // 0: 2/pi
+   1.57079632679489655800e+00, 6.12323399573676603587e-17, -1.49738490485916983151e-33,    // 1-3: pi/2 split (hi, mid, lo)
+   -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,   // 4-9: S1..S6
+   2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+   4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,    // 10-15: C1..C6
+   -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+   6755399441055744.0, 0.0};                                                               // 16: 1.5 * 2^52 (round-to-integer magic)
+
+MB_HD double mb_fma(double a, double b, double c)
+{
+#if defined(__CUDA_ARCH__)
+   return __fma_rn(a, b, c);
+#else
+   return fma(a, b, c);
+#endif
+}
+
+MB_HD void mb_sincos(double x, double *sn, double *cs)
+{
+   const double *t = mb_sc_tab;
+   // k = round(x * 2/pi): the integer lands in the low mantissa bits of kd + magic
+   const double km = mb_fma(x, t[0], t[16]);
+   const double kd = km - t[16];
+#if defined(__CUDA_ARCH__)
+   const int k = __double2loint(km);
+#else
+   long long kb;
+   memcpy(&kb, &km, sizeof kb);
+   const int k = (int)(kb & 0xffffffffll);
+#endif
+   double r = mb_fma(kd, -t[1], x);
+   r = mb_fma(kd, -t[2], r);
+   r = mb_fma(kd, -t[3], r);
+   const double z = r * r;
+   double ps = mb_fma(z, t[9], t[8]);
+   double pc = mb_fma(z, t[15], t[14]);
+   ps = mb_fma(z, ps, t[7]);
+   pc = mb_fma(z, pc, t[13]);
+   ps = mb_fma(z, ps, t[6]);
+   pc = mb_fma(z, pc, t[12]);
+   ps = mb_fma(z, ps, t[5]);
+   pc = mb_fma(z, pc, t[11]);
+   ps = mb_fma(z, ps, t[4]);
+   pc = mb_fma(z, pc, t[10]);
+   const double sr = mb_fma(z * r, ps, r);                    // sin(r)
+   const double cr = mb_fma(z, mb_fma(z, pc, -0.5), 1.0);     // cos(r)
+   // quadrant
+   const double s0 = (k & 1) ? cr : sr, c0 = (k & 1) ? sr : cr;
+   *sn = (k & 2) ? -s0 : s0;
+   *cs = ((k + 1) & 2) ? -c0 : c0;
+}
+MB_HD void mb_sincos(float x, float *s, float *c)
+{
+#if defined(__CUDA_ARCH__)
+   sincosf(x, s, c);
+#else
+   *s = sinf(x);
+   *c = cosf(x);
+#endif
+}
+// Bring an angle of any magnitude into the fast range without losing accuracy (rare path, separate block).
+MB_HD double mb_reduce_angle(double x)
+{
+   if (!(fabs(x) > MB_SINCOS_FAST_LIMIT))
+      return x;
+   double s, c;
+#if defined(__CUDA_ARCH__)
+   sincos(x, &s, &c);
+#else
+   s = sin(x);
+   c = cos(x);
+#endif
+   return atan2(s, c);
+}
+MB_HD float mb_reduce_angle(float x) { return x; }
+
+MB_HD bool mb2_is_1dof_descend(const MbOp2 &o) { return !(o.code & MB2_ASCEND) && MB2_JT(o.code) != MB_SIXDOF; }
+
+template <class T> MB_HD M3T<T> ld_m3(const T *p)
+{
+   M3T<T> r;
+   r.xx = p[0]; r.xy = p[1]; r.xz = p[2]; r.yx = p[3]; r.yy = p[4]; r.yz = p[5]; r.zx = p[6]; r.zy = p[7]; r.zz = p[8];
+   return r;
+}
+template <class T> MB_HD V3T<T> ld_v3(const T *p) { return v3<T>(p[0], p[1], p[2]); }
+template <class T> MB_HD RbiT<T> ld_rbi(const T *c)
+{
+   RbiT<T> r;
+   r.I.xx = c[MB_C_I + 0]; r.I.xy = c[MB_C_I + 1]; r.I.xz = c[MB_C_I + 2]; r.I.yy = c[MB_C_I + 3]; r.I.yz = c[MB_C_I + 4]; r.I.zz = c[MB_C_I + 5];
+   r.h = ld_v3(c + MB_C_H);
+   r.m = c[MB_C_M];
+   return r;
+}
+
+// (a1) joint transform X_J(q) composed with the fixed offset, canonical frames (axis = +z):
+// revolute (MecanoFactories.java:231-260): R = R0 Rz(q), p = p0;  prismatic (PrismaticJointReadOnly.java:18-22): R = R0, p = p0 + q R0 e_z
+template <class T, bool REV> MB_HD XfT<T> joint_xf_1dof(const T *C, T s, T c)
+{
+   XfT<T> X;
+   const M3T<T> R0 = ld_m3(C + MB_C_R);
+   const V3T<T> p0 = ld_v3(C + MB_C_P);
+   if (REV)
+   {
+      X.R = mul_rz(R0, s, c);
+      X.p = p0;
+   }
+   else
+   {
+      X.R = R0;
+      X.p = p0 + s * v3<T>(R0.xz, R0.yz, R0.zz);
+   }
+   return X;
+}
+
+// SixDoF (FloatingJointReadOnly.java:34-37): R = R0 R(quat), p = p0 + R0 pos; configuration rows [qx qy qz qs x y z]
+template <class T, class Ctx> MB_HD XfT<T> joint_xf_6dof(Ctx &c, const T *C, int r)
+{
+   XfT<T> X;
+   const M3T<T> R0 = ld_m3(C + MB_C_R);
+   const V3T<T> p0 = ld_v3(C + MB_C_P);
+   const M3T<T> Rq = quat_to_rot(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3));
+   X.R = mul(R0, Rq);
+   X.p = p0 + mul(R0, v3<T>(c.ld_q(r + 4), c.ld_q(r + 5), c.ld_q(r + 6)));
+   return X;
+}
+
+template <class T, class F> MB_HD SvT<T> ld_sv6(int row, F ld)
+{
+   SvT<T> r;
+   r.a = v3<T>(ld(row), ld(row + 1), ld(row + 2));
+   r.l = v3<T>(ld(row + 3), ld(row + 4), ld(row + 5));
+   return r;
+}
+
+template <class T, class Ctx> MB_HD void aux_st_sv(Ctx &c, int i, const SvT<T> &v)
+{
+   c.aux_st(i + 0, v.a.x); c.aux_st(i + 1, v.a.y); c.aux_st(i + 2, v.a.z);
+   c.aux_st(i + 3, v.l.x); c.aux_st(i + 4, v.l.y); c.aux_st(i + 5, v.l.z);
+}
+template <class T, class Ctx> MB_HD SvT<T> aux_ld_sv(Ctx &c, int i)
+{
+   SvT<T> v;
+   v.a = v3<T>(c.aux_ld(i + 0), c.aux_ld(i + 1), c.aux_ld(i + 2));
+   v.l = v3<T>(c.aux_ld(i + 3), c.aux_ld(i + 4), c.aux_ld(i + 5));
+   return v;
+}
+
+template <class T, class Ctx> MB_HD void stk_st_sv(Ctx &c, int slot2, const SvT<T> &v)
+{
+   c.stk_st2(slot2, 0, v.a.x, v.a.y);
+   c.stk_st2(slot2, 1, v.a.z, v.l.x);
+   c.stk_st2(slot2, 2, v.l.y, v.l.z);
+}
+template <class T, class Ctx> MB_HD SvT<T> stk_ld_sv(Ctx &c, int slot2)
+{
+   SvT<T> v;
+   c.stk_ld2(slot2, 0, v.a.x, v.a.y);
+   c.stk_ld2(slot2, 1, v.a.z, v.l.x);
+   c.stk_ld2(slot2, 2, v.l.y, v.l.z);
+   return v;
+}
+// a whole transform on the stack: 6 double2
+template <class T, class Ctx> MB_HD void stk_st_xf(Ctx &c, int slot2, const XfT<T> &X)
+{
+   c.stk_st2(slot2, 0, X.R.xx, X.R.xy); c.stk_st2(slot2, 1, X.R.xz, X.R.yx); c.stk_st2(slot2, 2, X.R.yy, X.R.yz);
+   c.stk_st2(slot2, 3, X.R.zx, X.R.zy); c.stk_st2(slot2, 4, X.R.zz, X.p.x); c.stk_st2(slot2, 5, X.p.y, X.p.z);
+}
+template <class T, class Ctx> MB_HD XfT<T> stk_ld_xf(Ctx &c, int slot2)
+{
+   XfT<T> X;
+   c.stk_ld2(slot2, 0, X.R.xx, X.R.xy); c.stk_ld2(slot2, 1, X.R.xz, X.R.yx); c.stk_ld2(slot2, 2, X.R.yy, X.R.yz);
+   c.stk_ld2(slot2, 3, X.R.zx, X.R.zy); c.stk_ld2(slot2, 4, X.R.zz, X.p.x); c.stk_ld2(slot2, 5, X.p.y, X.p.z);
+   return X;
+}
+
+// external wrench on a body, given in its CoM frame (InverseDynamicsCalculator.java:819), re-expressed in the canonical joint frame
+template <class T, class Ctx> MB_HD SvT<T> external_wrench(Ctx &c, int e, const T *C)
+{
+   SvT<T> w, r;
+   w.a = v3<T>(c.ld_fext(e, 0), c.ld_fext(e, 1), c.ld_fext(e, 2));
+   w.l = v3<T>(c.ld_fext(e, 3), c.ld_fext(e, 4), c.ld_fext(e, 5));
+   const M3T<T> E = ld_m3(C + MB_C_E);
+   r.l = mul(E, w.l);
+   r.a = mul(E, w.a) + cross(ld_v3(C + MB_C_C), r.l);
+   return r;
+}
+} // namespace mb

@@ -54,6 +54,46 @@ template <int BLOCK> struct GpuCtx
    __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
 };
 
+// v2 context (rnea.cuh): per-thread base pointers (one IMAD.WIDE per global access), stack of double2 (LDS.128 / STS.128)
+template <int BLOCK> struct GpuCtx2
+{
+   const char *qb, *qdb, *xb, *fb;
+   char *ob;
+   unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
+   int stk0;     // index (double2 units) of stack slot 0 of this thread
+   double *aux;
+
+   __device__ __forceinline__ double ld_q(int r) const { return __ldg((const double *)(qb + (unsigned long long)(unsigned)r * ld8)); }
+   __device__ __forceinline__ double ld_qd(int r) const { return __ldg((const double *)(qdb + (unsigned long long)(unsigned)r * ld8)); }
+   __device__ __forceinline__ double ld_x(int r) const { return __ldg((const double *)(xb + (unsigned long long)(unsigned)r * ld8)); }
+   __device__ __forceinline__ double ld_fext(int b, int k) const { return __ldg((const double *)(fb + (unsigned long long)(unsigned)(6 * b + k) * ld8)); }
+   __device__ __forceinline__ void st_out(int r, double v) { *(double *)(ob + (unsigned long long)(unsigned)r * ld8) = v; }
+   __device__ __forceinline__ void stk_ld2(int slot2, int j, double &a, double &b) const
+   {
+      const double2 t = reinterpret_cast<const double2 *>(mb_smem)[stk0 + (slot2 + j) * BLOCK];
+      a = t.x;
+      b = t.y;
+   }
+   __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b) { reinterpret_cast<double2 *>(mb_smem)[stk0 + (slot2 + j) * BLOCK] = make_double2(a, b); }
+   __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
+   __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
+   __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
+   // prefetch ring: [stage][q | qd | x][BLOCK] doubles in shared memory, filled by cp.async (LDGSTS)
+   int ring0; // index (doubles) of this thread's element of stage 0, row 0
+   __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, bool use_qd, bool use_x) const
+   {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(mb_smem + ring0 + stage * 3 * BLOCK);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
+      if (use_qd)
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+      if (use_x)
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 2 * BLOCK * 8), "l"(xb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+   }
+   __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+   template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+   __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_smem[ring0 + (stage * 3 + j) * BLOCK]; }
+};
+
 // state-major mass-matrix output (Mecano's per-state dense layout): uncoalesced, provided for drop-in use
 template <int BLOCK> struct GpuCtxStateMajor : GpuCtx<BLOCK>
 {
@@ -80,7 +120,16 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    c.aux = aux;
    c.rec = rec;
    if constexpr (ALGO == MB_RNEA)
-      rnea_state<double, Ctx, FEXT>(P, c, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+   {
+      GpuCtx2<BLOCK> c2;
+      c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
+      c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
+      c2.ld8 = (unsigned)(a.ld * 8);
+      c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
+      c2.ring0 = ((ncst + 1) & ~1) + 2 * P.stack2 * BLOCK + threadIdx.x;
+      c2.aux = aux;
+      rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+   }
    else if constexpr (ALGO == MB_ABA)
       aba_state<double, Ctx, FEXT>(P, c, a.grav);
    else
@@ -94,9 +143,9 @@ constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
 constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
 constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
 constexpr int kAbaRec0 = 9 * 33 + 9, kAbaRec1 = 9 * 128 + 18;
-constexpr int kNumCfg = 5;
-constexpr int kCfgClass[kNumCfg] = {0, 0, 1, 1, 1};
-constexpr int kCfgBlock[kNumCfg] = {256, 128, 128, 64, 32};
+constexpr int kNumCfg = 8;
+constexpr int kCfgClass[kNumCfg] = {0, 0, 0, 0, 0, 1, 1, 1};
+constexpr int kCfgBlock[kNumCfg] = {384, 320, 256, 192, 128, 128, 64, 32};
 
 typedef void (*KernelFn)(const MbProgram, const KernelArgs);
 
@@ -107,10 +156,13 @@ template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
    constexpr int r0 = ALGO == MB_ABA ? kAbaRec0 : 0, r1 = ALGO == MB_ABA ? kAbaRec1 : 0;
    switch (cfg)
    {
-      case 0: return thread_kernel<ALGO, FEXT, SM, 256, a0, r0>;
-      case 1: return thread_kernel<ALGO, FEXT, SM, 128, a0, r0>;
-      case 2: return thread_kernel<ALGO, FEXT, SM, 128, a1, r1>;
-      case 3: return thread_kernel<ALGO, FEXT, SM, 64, a1, r1>;
+      case 0: return thread_kernel<ALGO, FEXT, SM, 384, a0, r0>;
+      case 1: return thread_kernel<ALGO, FEXT, SM, 320, a0, r0>;
+      case 2: return thread_kernel<ALGO, FEXT, SM, 256, a0, r0>;
+      case 3: return thread_kernel<ALGO, FEXT, SM, 192, a0, r0>;
+      case 4: return thread_kernel<ALGO, FEXT, SM, 128, a0, r0>;
+      case 5: return thread_kernel<ALGO, FEXT, SM, 128, a1, r1>;
+      case 6: return thread_kernel<ALGO, FEXT, SM, 64, a1, r1>;
       default: return thread_kernel<ALGO, FEXT, SM, 32, a1, r1>;
    }
 }
@@ -132,9 +184,11 @@ int class_of(int algo, const MbProgram &P)
    return -1;
 }
 
-size_t smem_bytes(const MbProgram &P, int block)
+size_t smem_bytes(int algo, const MbProgram &P, int block)
 {
    const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
+   if (algo == MB_RNEA)
+      return sizeof(double) * ((size_t)ncst + (2 * (size_t)P.stack2 + 3 * MB_PF_STAGES) * block);
    return sizeof(double) * ((size_t)ncst + (size_t)std::max(P.stack_doubles, 1) * block);
 }
 } // namespace
@@ -156,7 +210,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       if (kCfgClass[cfg] < cls)
          continue; // work areas too small
       const int b = kCfgBlock[cfg];
-      const size_t sm = smem_bytes(P, b);
+      const size_t sm = smem_bytes(algo, P, b);
       if (sm > (size_t)max_optin)
          continue;
       // every variant of this configuration gets the opt-in so that later launches cannot fail on it

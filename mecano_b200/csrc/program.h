@@ -59,15 +59,41 @@ struct MbBody
    int32_t pad;
 };
 
+// Pre-decoded traversal record (16 bytes, one LDC.128 per op): everything an op needs, so that the kernels never
+// chase MbBody fields.  Stack offsets are in double2 units (the shared-memory stack is an array of double2,
+// state-minor), save-area offsets in doubles.
+//   code: bit0 ASCEND, bits1-2 joint type, bit3 SC (this op also evaluates sin/cos for the next 1-DoF DESCEND)
+struct MbOp2
+{
+   uint8_t code;
+   uint8_t flags;   // MB_F_* >> 1  (LEAF 0x1, LOAD_PARENT 0x2, SAVE_STATE 0x4, ROOT_PARENT 0x8, STORE_ACC 0x10, FIRST_CHILD 0x20)
+   uint8_t body;    // internal body index (constant record)
+   uint8_t pf;      // bit0: op k+1 is a 1-DoF DESCEND (its configuration is read from the prefetch ring during this op)
+   uint16_t cfg, dof;    // Mecano configuration / DoF row of the joint
+   uint16_t slot, pslot; // own / parent stack slot (double2 units)
+   uint16_t aux, paux;   // own / parent save area (doubles)
+};
+#define MB2_ASCEND 0x1u
+#define MB2_JT(code) (((code) >> 1) & 3u)
+#define MB2_SC 0x8u
+#define MB2_LEAF 0x1u
+#define MB2_LOAD_PARENT 0x2u
+#define MB2_SAVE_STATE 0x4u
+#define MB2_ROOT_PARENT 0x8u
+#define MB2_STORE_ACC 0x10u
+#define MB2_FIRST_CHILD 0x20u
+
 struct MbProgram
 {
    int32_t nb, nops, nv, nq;
+   int32_t stack2;        // v2 stack size per state in double2 units
    int32_t stack_doubles; // shared-memory stack per state
    int32_t aux_doubles;   // local-memory branch save area per state
    int32_t rec_doubles;   // local-memory record area per state (ABA)
    int32_t max_depth;
    MbBody body[MB_MAX_BODIES];
    uint32_t op[MB_MAX_OPS];
+   MbOp2 op2[MB_MAX_OPS + 4]; // trailing no-op records so that the look-ahead never reads past the end
 };
 
 // stack slot sizes (doubles) per algorithm: joint parameters needed to rebuild the joint transform

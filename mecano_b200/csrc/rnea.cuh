@@ -1,0 +1,244 @@
+// rnea.cuh -- one state of the recursive Newton-Euler algorithm (InverseDynamicsCalculator.compute(),
+// M/algorithms/InverseDynamicsCalculator.java:496-501, passOne :873-917, passTwo :930-966), including the
+// "set state -> updateFramesRecursively()" prologue that Mecano keeps in the frame tree
+// (RigidBodyBasics.java:104-112, MovingReferenceFrame.java:279-311).
+//
+// Shape of the code (what the sm_100a kernel needs; the host emulation harness compiles the same source):
+//   * the traversal program is pre-decoded into 16-byte records (MbOp2); each record is dispatched to a
+//     straight-line routine specialised on <joint type, SC>, so the FP64 work of one op sits in one basic block;
+//   * scalars are software-pipelined two ops deep: while op k runs, the q/qd/qdd of op k+2 are in flight from
+//     HBM and the sin/cos of op k+1 (the only long serial FP64 chain) is evaluated next to op k's spatial
+//     algebra (the SC variants), which gives the in-order SM independent work to issue;
+//   * per-level data (accumulated wrench + sin/cos) lives on a shared-memory stack of double2, state-minor.
+#pragma once
+#include "program.h"
+#include "spatial.cuh"
+#include "jointmath.cuh"
+
+namespace mb
+{
+// scalars travelling through the software pipeline
+template <class T> struct RneaPipe
+{
+   T s, c;   // current op: sin/cos (prismatic: s = q)
+   T qd, x;  // current op: joint velocity, joint acceleration (read from the prefetch ring at the top of the op)
+   T mq;     // next op: raw configuration (read from the prefetch ring)
+   T ls, lc; // sin/cos of the last DESCEND (a leaf's ASCEND follows immediately and reuses them)
+};
+
+template <class T, class Ctx, bool FEXT, bool REV, bool SC>
+MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp, T &ns, T &nc)
+{
+   if (SC)
+      mb_sincos(pp.mq, &ns, &nc);
+   const T *C = c.cst(o.body);
+   const XfT<T> X = joint_xf_1dof<T, REV>(C, pp.s, pp.c);
+   // pass one (:873-917): twist and acceleration of the body, in its joint frame
+   v = motion_to_child(X, v);
+   a = motion_to_child(X, a);
+   if (REV)
+   {
+      // a += v x (S qd) + S qdd with S = [e_z; 0]
+      a.a.x += v.a.y * pp.qd; a.a.y -= v.a.x * pp.qd;
+      a.l.x += v.l.y * pp.qd; a.l.y -= v.l.x * pp.qd;
+      v.a.z += pp.qd;
+      a.a.z += pp.x;
+   }
+   else
+   {
+      // S = [0; e_z]: v x (S qd) = [0; w x e_z qd]
+      a.l.x += v.a.y * pp.qd; a.l.y -= v.a.x * pp.qd;
+      v.l.z += pp.qd;
+      a.l.z += pp.x;
+   }
+   // Newton-Euler (SpatialInertiaReadOnly.java:229-296), about the joint-frame origin
+   const RbiT<T> I = ld_rbi(C);
+   f = mul(I, a) + cross_force(v, mul(I, v));
+   if (FEXT)
+      f = f - external_wrench<T>(c, ext, C); // :946
+   pp.ls = pp.s;
+   pp.lc = pp.c;
+   if (!(o.flags & MB2_LEAF))
+   {
+      c.stk_st2(o.slot, 0, f.a.x, f.a.y);
+      c.stk_st2(o.slot, 1, f.a.z, f.l.x);
+      c.stk_st2(o.slot, 2, f.l.y, f.l.z);
+      c.stk_st2(o.slot, 3, pp.s, pp.c);
+   }
+   if (o.flags & MB2_SAVE_STATE)
+   {
+      aux_st_sv<T>(c, o.aux, v);
+      aux_st_sv<T>(c, o.aux + 6, a);
+   }
+}
+
+template <class T, class Ctx, bool REV, bool SC>
+MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, SvT<T> &f, RneaPipe<T> &pp, T &ns, T &nc)
+{
+   if (SC)
+      mb_sincos(pp.mq, &ns, &nc);
+   // pass two (:930-966); f holds the wrench of the whole subtree
+   c.st_out(o.dof, REV ? f.a.z : f.l.z); // tau = S^T W (:952-958)
+   if (!(o.flags & MB2_ROOT_PARENT))
+   {
+      T s = pp.ls, cs = pp.lc;
+      if (!(o.flags & MB2_LEAF))
+         c.stk_ld2(o.slot, 3, s, cs);
+      const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), s, cs);
+      SvT<T> acc;
+      c.stk_ld2(o.pslot, 0, acc.a.x, acc.a.y);
+      c.stk_ld2(o.pslot, 1, acc.a.z, acc.l.x);
+      c.stk_ld2(o.pslot, 2, acc.l.y, acc.l.z);
+      f = acc + force_to_parent(X, f); // addJointWrenchFromChild (:961-966)
+      if (o.flags & MB2_STORE_ACC)
+      {
+         c.stk_st2(o.pslot, 0, f.a.x, f.a.y);
+         c.stk_st2(o.pslot, 1, f.a.z, f.l.x);
+         c.stk_st2(o.pslot, 2, f.l.y, f.l.z);
+      }
+   }
+}
+
+template <class T, class Ctx, bool FEXT>
+MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &a, SvT<T> &f, bool use_qd, bool use_qdd)
+{
+   const T *C = c.cst(o.body);
+   const XfT<T> X = joint_xf_6dof<T>(c, C, o.cfg);
+   SvT<T> vj = sv_zero<T>(), aj = sv_zero<T>();
+   if (use_qd)
+      vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
+   if (use_qdd)
+      aj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
+   v = motion_to_child(X, v) + vj;
+   a = motion_to_child(X, a) + cross_motion(v, vj) + aj;
+   const RbiT<T> I = ld_rbi(C);
+   f = mul(I, a) + cross_force(v, mul(I, v));
+   if (FEXT)
+      f = f - external_wrench<T>(c, ext, C);
+   c.stk_st2(o.slot, 0, f.a.x, f.a.y);
+   c.stk_st2(o.slot, 1, f.a.z, f.l.x);
+   c.stk_st2(o.slot, 2, f.l.y, f.l.z);
+   if (!(o.flags & MB2_ROOT_PARENT))
+      stk_st_xf<T>(c, o.slot + 3, X);
+   if (o.flags & MB2_SAVE_STATE)
+   {
+      aux_st_sv<T>(c, o.aux, v);
+      aux_st_sv<T>(c, o.aux + 6, a);
+   }
+}
+
+template <class T, class Ctx> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o, SvT<T> &f)
+{
+   c.st_out(o.dof + 0, f.a.x); c.st_out(o.dof + 1, f.a.y); c.st_out(o.dof + 2, f.a.z);
+   c.st_out(o.dof + 3, f.l.x); c.st_out(o.dof + 4, f.l.y); c.st_out(o.dof + 5, f.l.z);
+   if (!(o.flags & MB2_ROOT_PARENT))
+   {
+      const XfT<T> X = stk_ld_xf<T>(c, o.slot + 3);
+      SvT<T> acc;
+      c.stk_ld2(o.pslot, 0, acc.a.x, acc.a.y);
+      c.stk_ld2(o.pslot, 1, acc.a.z, acc.l.x);
+      c.stk_ld2(o.pslot, 2, acc.l.y, acc.l.z);
+      f = acc + force_to_parent(X, f);
+      if (o.flags & MB2_STORE_ACC)
+      {
+         c.stk_st2(o.pslot, 0, f.a.x, f.a.y);
+         c.stk_st2(o.pslot, 1, f.a.z, f.l.x);
+         c.stk_st2(o.pslot, 2, f.l.y, f.l.z);
+      }
+   }
+}
+
+// Prefetch ring (Ctx::pf_*): MB_PF_STAGES slots of (q, qd, x) per state.  Op k issues the asynchronous copies of
+// op k + MB_PF_DIST (cp.async on the GPU: no register and no scoreboard is held while the data is in flight),
+// evaluates the sin/cos of op k + 1 and consumes the velocity / acceleration of op k.
+#define MB_PF_STAGES 4
+#define MB_PF_DIST 3
+
+template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav, bool use_qd, bool use_qdd)
+{
+   SvT<T> v = sv_zero<T>(), a = sv_zero<T>(), f = sv_zero<T>();
+   RneaPipe<T> pp;
+   pp.s = pp.qd = pp.x = pp.mq = pp.ls = (T)0;
+   pp.c = pp.lc = (T)1;
+   const int nops = P.nops;
+   // prologue: scalars of ops 0 .. MB_PF_DIST-1
+#pragma unroll
+   for (int k = 0; k < MB_PF_DIST; k++)
+   {
+      const MbOp2 o = P.op2[k];
+      if (mb2_is_1dof_descend(o))
+         c.pf_issue(k, o.cfg, o.dof, use_qd, use_qdd);
+      c.pf_commit();
+   }
+   c.template pf_wait<0>();
+   {
+      const MbOp2 o0 = P.op2[0];
+      if (mb2_is_1dof_descend(o0))
+      {
+         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+         else pp.s = q0;
+      }
+   }
+#pragma unroll 1
+   for (int k = 0; k < nops; k++)
+   {
+      const MbOp2 o = P.op2[k];
+      {
+         const MbOp2 od = P.op2[k + MB_PF_DIST];
+         if (mb2_is_1dof_descend(od))
+            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, use_qd, use_qdd);
+         c.pf_commit();
+         c.template pf_wait<MB_PF_DIST - 1>(); // everything up to the group of op k + 1 has landed
+      }
+      pp.qd = pp.x = pp.mq = (T)0;
+      if (mb2_is_1dof_descend(o))
+      {
+         if (use_qd) pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+         if (use_qdd) pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+      }
+      if (o.pf & 1u) // op k + 1 is a 1-DoF DESCEND
+         pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0)); // no-op unless |q| > MB_SINCOS_FAST_LIMIT
+      // kinematic state of the parent: carried in registers along a chain, otherwise the root acceleration
+      // (= -gravity, InverseDynamicsCalculator.java:397-403) or the state saved by the branching ancestor
+      if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+      {
+         if (o.flags & MB2_ROOT_PARENT)
+         {
+            v = sv_zero<T>();
+            a = sv_zero<T>();
+            a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
+         }
+         else
+         {
+            v = aux_ld_sv<T>(c, o.paux);
+            a = aux_ld_sv<T>(c, o.paux + 6);
+         }
+      }
+      const int ext = FEXT ? P.body[o.body].ext_index : 0;
+      T ns = pp.mq, nc = (T)1; // prismatic next op: "s" carries q
+      switch (o.code & 0xfu)
+      {
+         case 0 | (MB_REVOLUTE << 1): rnea_descend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, a, f, pp, ns, nc); break;
+         case 0 | (MB_REVOLUTE << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, a, f, pp, ns, nc); break;
+         case 1 | (MB_REVOLUTE << 1): rnea_ascend_1dof<T, Ctx, true, false>(c, o, f, pp, ns, nc); break;
+         case 1 | (MB_REVOLUTE << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, true, true>(c, o, f, pp, ns, nc); break;
+         case 0 | (MB_PRISMATIC << 1): rnea_descend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, a, f, pp, ns, nc); break;
+         case 0 | (MB_PRISMATIC << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, a, f, pp, ns, nc); break;
+         case 1 | (MB_PRISMATIC << 1): rnea_ascend_1dof<T, Ctx, false, false>(c, o, f, pp, ns, nc); break;
+         case 1 | (MB_PRISMATIC << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, false, true>(c, o, f, pp, ns, nc); break;
+         default:
+            if (o.code & MB2_SC)
+               mb_sincos(pp.mq, &ns, &nc);
+            if (o.code & MB2_ASCEND)
+               rnea_ascend_6dof<T, Ctx>(c, o, f);
+            else
+               rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f, use_qd, use_qdd);
+            break;
+      }
+      pp.s = ns;
+      pp.c = nc;
+   }
+   c.template pf_wait<0>();
+}
+} // namespace mb

@@ -3,6 +3,7 @@
 // (mecano_b200/csrc/algorithms.cuh) plus the host flattener for the CPU, so that the no-GPU test suite can
 // check the kernel mathematics and the traversal programs against the oracle.  The product library
 // (libmecano_b200.so) contains no such host path: its entry points launch CUDA kernels or fail.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -26,6 +27,18 @@ template <class T> struct CpuCtx
    T ld_fext(int b, int k) const { return (T)fext[(6 * b + k) * ld + s]; }
    void st_out(int r, T v) { out[r * ld + s] = (double)v; }
    void st_M(int r, int c, T v) { M[((long)r * nv + c) * ld + s] = (double)v; }
+   void stk_ld2(int slot2, int j, T &a, T &b) const { a = stk[2 * (slot2 + j)]; b = stk[2 * (slot2 + j) + 1]; }
+   void stk_st2(int slot2, int j, T a, T b) { stk[2 * (slot2 + j)] = a; stk[2 * (slot2 + j) + 1] = b; }
+   T ring[4][3];
+   void pf_issue(int stage, int cfg, int dof, bool use_qd, bool use_x)
+   {
+      ring[stage][0] = ld_q(cfg);
+      if (use_qd) ring[stage][1] = ld_qd(dof);
+      if (use_x) ring[stage][2] = ld_x(dof);
+   }
+   void pf_commit() {}
+   template <int N> void pf_wait() {}
+   T pf_ld(int stage, int j) const { return ring[stage][j]; }
    T stk_ld(int i) const { return stk[i]; }
    void stk_st(int i, T v) { stk[i] = v; }
    T aux_ld(int i) const { return aux[i]; }
@@ -51,7 +64,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
    std::vector<T> consts(ft.consts.begin(), ft.consts.end());
    // poison the work areas so that a read-before-write shows up as NaN
    const T nan = (T)(0.0 / 0.0);
-   std::vector<T> stk(P.stack_doubles + 1, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 1, nan);
+   std::vector<T> stk(std::max(P.stack_doubles, 2 * P.stack2) + 2, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 1, nan);
    const T grav[3] = {(T)g[0], (T)g[1], (T)g[2]};
    for (long s = 0; s < n; s++)
    {
