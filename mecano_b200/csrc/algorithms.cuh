@@ -26,6 +26,7 @@
 #include "spatial.cuh"
 #include "jointmath.cuh"
 #include "rnea.cuh"
+#include "crba.cuh"
 
 namespace mb
 {
@@ -465,166 +466,4 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
    }
 }
 
-// ======================================================================================== CRBA
-template <class T, class Ctx> MB_HD void aux_st_rbi(Ctx &c, int i, const RbiT<T> &I)
-{
-   c.aux_st(i + 0, I.I.xx); c.aux_st(i + 1, I.I.xy); c.aux_st(i + 2, I.I.xz); c.aux_st(i + 3, I.I.yy); c.aux_st(i + 4, I.I.yz); c.aux_st(i + 5, I.I.zz);
-   c.aux_st(i + 6, I.h.x); c.aux_st(i + 7, I.h.y); c.aux_st(i + 8, I.h.z); c.aux_st(i + 9, I.m);
-}
-template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
-{
-   RbiT<T> I;
-   I.I.xx = c.aux_ld(i + 0); I.I.xy = c.aux_ld(i + 1); I.I.xz = c.aux_ld(i + 2); I.I.yy = c.aux_ld(i + 3); I.I.yz = c.aux_ld(i + 4); I.I.zz = c.aux_ld(i + 5);
-   I.h = v3<T>(c.aux_ld(i + 6), c.aux_ld(i + 7), c.aux_ld(i + 8));
-   I.m = c.aux_ld(i + 9);
-   return I;
-}
-
-// write the mass-matrix entries coupling force column F (already expressed in body j's frame) of DoF
-// row `di` with the DoFs of body j, symmetrically (setSymmetricEntry, :704-705, :790-791)
-template <class T, class Ctx> MB_HD void crba_project(Ctx &c, const MbBody &Bj, int di, const SvT<T> &F)
-{
-   if (Bj.jtype == MB_REVOLUTE)
-   {
-      c.st_M(Bj.dof_off, di, F.a.z);
-      c.st_M(di, Bj.dof_off, F.a.z);
-   }
-   else if (Bj.jtype == MB_PRISMATIC)
-   {
-      c.st_M(Bj.dof_off, di, F.l.z);
-      c.st_M(di, Bj.dof_off, F.l.z);
-   }
-   else
-   {
-      const T e[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
-#pragma unroll
-      for (int r = 0; r < 6; r++)
-      {
-         c.st_M(Bj.dof_off + r, di, e[r]);
-         c.st_M(di, Bj.dof_off + r, e[r]);
-      }
-   }
-}
-
-// walk from body i up to the root, transforming F and filling the off-diagonal blocks (:772-797)
-template <class T, class Ctx> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int i, int di, const XfT<T> &Xi, SvT<T> F)
-{
-   XfT<T> Xc = Xi;
-   int j = i;
-   while (P.body[j].parent >= 0)
-   {
-      F = force_to_parent(Xc, F);
-      j = P.body[j].parent;
-      const MbBody &Bj = P.body[j];
-      crba_project<T>(c, Bj, di, F);
-      if (Bj.parent >= 0)
-      {
-         JpT<T> jpj;
-         stk_ld_jp<T>(c, Bj.slot, Bj.jtype, jpj);
-         Xc = rebuild_transform<T>(Bj.jtype, c.cst(j), jpj);
-      }
-   }
-}
-
-template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
-{
-   RbiT<T> acc = RbiT<T>();
-   XfT<T> X;
-   JpT<T> jp;
-   X.R = M3T<T>();
-   X.p = v3<T>(0, 0, 0);
-   const int nops = P.nops;
-   T pq = (T)0;
-   auto prefetch = [&](uint32_t wn) {
-      if (wn & MB_OP_ASCEND)
-         return;
-      const MbBody &Bn = P.body[MB_OP_BODY(wn)];
-      if (Bn.jtype != MB_SIXDOF)
-         pq = c.ld_q(Bn.cfg_off);
-   };
-   prefetch(P.op[0]);
-   for (int k = 0; k < nops; k++)
-   {
-      const uint32_t w = P.op[k];
-      const int i = MB_OP_BODY(w);
-      const MbBody &B = P.body[i];
-      const T *C = c.cst(i);
-      const T q1 = pq;
-      if (k + 1 < nops)
-         prefetch(P.op[k + 1]);
-      if (!(w & MB_OP_ASCEND))
-      {
-         X = joint_transform<T>(c, B, C, jp, q1);
-         if (!(w & MB_F_LEAF))
-            stk_st_jp<T>(c, B.slot, B.jtype, jp);
-         continue;
-      }
-      if (!(w & MB_F_LEAF))
-      {
-         stk_ld_jp<T>(c, B.slot, B.jtype, jp);
-         X = rebuild_transform<T>(B.jtype, C, jp);
-      }
-      // composite inertia of the subtree, about this joint frame (:648-661)
-      RbiT<T> Ic = ld_rbi(C);
-      if (!(w & MB_F_LEAF))
-         Ic = Ic + acc;
-      // unit momenta F = Ic S (:663-667), diagonal block (:700-707), ancestors (:772-797)
-      if (B.jtype == MB_REVOLUTE)
-      {
-         SvT<T> F;
-         F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
-         F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
-         c.st_M(B.dof_off, B.dof_off, F.a.z);
-         crba_walk<T>(P, c, i, B.dof_off, X, F);
-      }
-      else if (B.jtype == MB_PRISMATIC)
-      {
-         SvT<T> F;
-         F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
-         F.l = v3<T>((T)0, (T)0, Ic.m);
-         c.st_M(B.dof_off, B.dof_off, F.l.z);
-         crba_walk<T>(P, c, i, B.dof_off, X, F);
-      }
-      else
-      {
-#pragma unroll 1
-         for (int col = 0; col < 6; col++)
-         {
-            SvT<T> e = sv_zero<T>();
-            if (col == 0) e.a.x = 1; else if (col == 1) e.a.y = 1; else if (col == 2) e.a.z = 1;
-            else if (col == 3) e.l.x = 1; else if (col == 4) e.l.y = 1; else e.l.z = 1;
-            const SvT<T> F = mul(Ic, e);
-            const int di = B.dof_off + col;
-            c.st_M(B.dof_off + 0, di, F.a.x); c.st_M(B.dof_off + 1, di, F.a.y); c.st_M(B.dof_off + 2, di, F.a.z);
-            c.st_M(B.dof_off + 3, di, F.l.x); c.st_M(B.dof_off + 4, di, F.l.y); c.st_M(B.dof_off + 5, di, F.l.z);
-            if (B.parent >= 0)
-               crba_walk<T>(P, c, i, di, X, F);
-         }
-      }
-      // entries coupling this joint with joints of unrelated branches are zero (massMatrix.zero(), :296)
-      for (int j = 0; j < i; j++)
-      {
-         const MbBody &Bj = P.body[j];
-         if (Bj.subtree_end > i)
-            continue; // ancestor: filled by the walk
-         for (int r = 0; r < Bj.ndof; r++)
-            for (int s = 0; s < B.ndof; s++)
-            {
-               c.st_M(Bj.dof_off + r, B.dof_off + s, (T)0);
-               c.st_M(B.dof_off + s, Bj.dof_off + r, (T)0);
-            }
-      }
-      if (!(w & MB_F_ROOT_PARENT))
-      {
-         const RbiT<T> K = rbi_to_parent(X, Ic); // childInertia.applyTransform(child.transformToParent) (:658)
-         const int pa_off = P.body[B.parent].aux;
-         if (w & MB_F_FIRST_CHILD)
-            acc = K;
-         else
-            acc = aux_ld_rbi<T>(c, pa_off) + K;
-         if (w & MB_F_STORE_ACC)
-            aux_st_rbi<T>(c, pa_off, acc);
-      }
-   }
-}
 } // namespace mb

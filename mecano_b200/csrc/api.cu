@@ -20,6 +20,7 @@ struct mecano_b200_handle
    int device = 0;
    mb::FlatTree tree;
    double *d_consts = nullptr;
+   uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[3];
    int variant = MECANO_B200_VARIANT_AUTO;
@@ -77,6 +78,8 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    mb::KernelArgs a;
    a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
    a.consts = h->d_consts;
+   a.zero_entries = h->d_zero;
+   a.n_zero = (int32_t)h->tree.zero_entries.size();
    a.n = n; a.ld = ld;
    a.grav[0] = h->gravity[0]; a.grav[1] = h->gravity[1]; a.grav[2] = h->gravity[2];
    a.flags = flags;
@@ -205,6 +208,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
    auto bail = [&](cudaError_t ce, const char *what) {
       std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
       if (h->d_consts) cudaFree(h->d_consts);
+      if (h->d_zero) cudaFree(h->d_zero);
       delete h;
       return fail(nullptr, (int)ce, m);
    };
@@ -212,6 +216,12 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
    const size_t bytes = h->tree.consts.size() * sizeof(double);
    if ((e = cudaMalloc(&h->d_consts, bytes)) != cudaSuccess) return bail(e, "cudaMalloc(consts)");
    if ((e = cudaMemcpy(h->d_consts, h->tree.consts.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(consts)");
+   if (!h->tree.zero_entries.empty())
+   {
+      const size_t zb = h->tree.zero_entries.size() * sizeof(uint16_t);
+      if ((e = cudaMalloc(&h->d_zero, zb)) != cudaSuccess) return bail(e, "cudaMalloc(zero entries)");
+      if ((e = cudaMemcpy(h->d_zero, h->tree.zero_entries.data(), zb, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(zero entries)");
+   }
    for (int algo = 0; algo < 3; algo++)
    {
       bool fits = false;
@@ -219,6 +229,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       if (!fits)
       {
          cudaFree(h->d_consts);
+         if (h->d_zero) cudaFree(h->d_zero);
          delete h;
          return fail(nullptr, MECANO_B200_ERR_TOO_LARGE, "tree exceeds the compiled per-state work areas (branch nesting / depth too large)");
       }
@@ -238,6 +249,7 @@ void mecano_b200_destroy(mecano_b200_handle *h)
       if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
    }
    if (h->d_consts) cudaFree(h->d_consts);
+   if (h->d_zero) cudaFree(h->d_zero);
    delete h;
 }
 

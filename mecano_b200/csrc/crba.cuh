@@ -1,0 +1,220 @@
+// crba.cuh -- one state of the composite-rigid-body algorithm: the joint-space mass matrix
+// (CompositeRigidBodyMassMatrixCalculator, M/algorithms/CompositeRigidBodyMassMatrixCalculator.java:
+//  reset()/getMassMatrix() :286-303, :344-348; computeMassMatrix() :588-667, :700-707, :772-797).
+//
+// The kernel is bound by the HBM write of the dense nv x nv result, so the code is organised around the stores:
+//   * the structural zeros (joints of unrelated branches; massMatrix.zero() :296) come from a list of entry indices
+//     built at flatten time and are written first, fire-and-forget;
+//   * every non-zero entry costs one integer multiply-add for the entry index, one for the address, one store;
+//   * the only per-level state is sin/cos on the shared-memory stack; the ancestor walk re-applies
+//     R0 * Rz(q) to the unit momentum without materialising the rotation matrix.
+#pragma once
+#include "jointmath.cuh"
+
+namespace mb
+{
+template <class T, class Ctx> MB_HD void aux_st_rbi(Ctx &c, int i, const RbiT<T> &I)
+{
+   c.aux_st(i + 0, I.I.xx); c.aux_st(i + 1, I.I.xy); c.aux_st(i + 2, I.I.xz); c.aux_st(i + 3, I.I.yy); c.aux_st(i + 4, I.I.yz); c.aux_st(i + 5, I.I.zz);
+   c.aux_st(i + 6, I.h.x); c.aux_st(i + 7, I.h.y); c.aux_st(i + 8, I.h.z); c.aux_st(i + 9, I.m);
+}
+template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
+{
+   RbiT<T> I;
+   I.I.xx = c.aux_ld(i + 0); I.I.xy = c.aux_ld(i + 1); I.I.xz = c.aux_ld(i + 2); I.I.yy = c.aux_ld(i + 3); I.I.yz = c.aux_ld(i + 4); I.I.zz = c.aux_ld(i + 5);
+   I.h = v3<T>(c.aux_ld(i + 6), c.aux_ld(i + 7), c.aux_ld(i + 8));
+   I.m = c.aux_ld(i + 9);
+   return I;
+}
+
+// F expressed in the parent of a 1-DoF joint: (R0 Rz(q), p0) applied to a force vector without forming the matrix
+template <class T, bool REV> MB_HD SvT<T> force_up_1dof(const T *C, T s, T cs, const SvT<T> &f)
+{
+   const M3T<T> R0 = ld_m3(C + MB_C_R);
+   V3T<T> p = ld_v3(C + MB_C_P);
+   SvT<T> g = f, r;
+   if (REV)
+   {
+      g.a.x = cs * f.a.x - s * f.a.y; g.a.y = s * f.a.x + cs * f.a.y;
+      g.l.x = cs * f.l.x - s * f.l.y; g.l.y = s * f.l.x + cs * f.l.y;
+   }
+   else
+      p = p + s * v3<T>(R0.xz, R0.yz, R0.zz);
+   r.l = mul(R0, g.l);
+   r.a = mul(R0, g.a) + cross(p, r.l);
+   return r;
+}
+
+// M[dof_j .. , col] = S_j^T F and the mirrored entries (setSymmetricEntry, :704-705, :790-791)
+template <class T, class Ctx> MB_HD void crba_project(Ctx &c, int jt, int dj, int col, const SvT<T> &F)
+{
+   const int nv = c.n_dofs();
+   if (jt == MB_REVOLUTE)
+   {
+      c.st_M(dj * nv + col, F.a.z);
+      c.st_M(col * nv + dj, F.a.z);
+   }
+   else if (jt == MB_PRISMATIC)
+   {
+      c.st_M(dj * nv + col, F.l.z);
+      c.st_M(col * nv + dj, F.l.z);
+   }
+   else
+   {
+      const T e[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+#pragma unroll
+      for (int r = 0; r < 6; r++)
+      {
+         c.st_M((dj + r) * nv + col, e[r]);
+         c.st_M(col * nv + dj + r, e[r]);
+      }
+   }
+}
+
+// walk from body b (whose force column F is expressed in its own frame, transform given by (s, cs) / the stack) up to
+// the root, filling the off-diagonal blocks of column `col` (:772-797)
+template <class T, class Ctx> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int b, int col, T s, T cs, SvT<T> F)
+{
+   MbWalk w = P.walk[b];
+   while (!(w.flags & 1u)) // until the parent is the root body
+   {
+      const T *C = c.cst(b);
+      if (w.jtype == MB_REVOLUTE)
+         F = force_up_1dof<T, true>(C, s, cs, F);
+      else if (w.jtype == MB_PRISMATIC)
+         F = force_up_1dof<T, false>(C, s, cs, F);
+      else
+         F = force_to_parent(stk_ld_xf<T>(c, w.slot), F);
+      b = w.parent;
+      w = P.walk[b];
+      crba_project<T>(c, w.jtype, w.dof, col, F);
+      if (w.jtype != MB_SIXDOF)
+         c.stk_ld2(w.slot, 0, s, cs);
+   }
+}
+
+template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
+{
+   // entries coupling joints of unrelated branches are zero
+   c.zero_fill();
+   RbiT<T> acc = RbiT<T>();
+   T s = (T)0, cs = (T)1, ls = (T)0, lc = (T)1, mq = (T)0;
+   const int nops = P.nops;
+   const int nv = c.n_dofs();
+#pragma unroll
+   for (int k = 0; k < MB_PF_DIST; k++)
+   {
+      const MbOp2 o = P.op2[k];
+      if (mb2_is_1dof_descend(o))
+         c.pf_issue(k, o.cfg, o.dof, false, false);
+      c.pf_commit();
+   }
+   c.template pf_wait<0>();
+   {
+      const MbOp2 o0 = P.op2[0];
+      if (mb2_is_1dof_descend(o0))
+      {
+         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &s, &cs);
+         else s = q0;
+      }
+   }
+#pragma unroll 1
+   for (int k = 0; k < nops; k++)
+   {
+      const MbOp2 o = P.op2[k];
+      {
+         const MbOp2 od = P.op2[k + MB_PF_DIST];
+         if (mb2_is_1dof_descend(od))
+            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, false, false);
+         c.pf_commit();
+         c.template pf_wait<MB_PF_DIST - 1>();
+      }
+      mq = (T)0;
+      if (o.pf & 1u)
+         mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+      T ns = mq, nc = (T)1;
+      if (o.code & MB2_SC)
+         mb_sincos(mq, &ns, &nc);
+      const int jt = MB2_JT(o.code);
+      const T *C = c.cst(o.body);
+      if (!(o.code & MB2_ASCEND))
+      {
+         // ---- joint transform of body i (the frame update of updateFramesRecursively())
+         if (jt == MB_SIXDOF)
+            stk_st_xf<T>(c, o.slot, joint_xf_6dof<T>(c, C, o.cfg));
+         else
+         {
+            ls = s;
+            lc = cs;
+            if (!(o.flags & MB2_LEAF))
+               c.stk_st2(o.slot, 0, s, cs);
+         }
+      }
+      else
+      {
+         // ---- composite inertia of the subtree, about this joint frame (:648-661)
+         RbiT<T> Ic = ld_rbi(C);
+         if (!(o.flags & MB2_LEAF))
+            Ic = Ic + acc;
+         T js = ls, jc = lc;
+         if (jt != MB_SIXDOF && !(o.flags & MB2_LEAF))
+            c.stk_ld2(o.slot, 0, js, jc);
+         const int d = o.dof;
+         // unit momenta F = Ic S (:663-667), diagonal block (:700-707), ancestors (:772-797)
+         if (jt == MB_REVOLUTE)
+         {
+            SvT<T> F;
+            F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
+            F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
+            c.st_M(d * nv + d, F.a.z);
+            if (!(o.flags & MB2_ROOT_PARENT))
+               crba_walk<T>(P, c, o.body, d, js, jc, F);
+         }
+         else if (jt == MB_PRISMATIC)
+         {
+            SvT<T> F;
+            F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
+            F.l = v3<T>((T)0, (T)0, Ic.m);
+            c.st_M(d * nv + d, F.l.z);
+            if (!(o.flags & MB2_ROOT_PARENT))
+               crba_walk<T>(P, c, o.body, d, js, jc, F);
+         }
+         else
+         {
+#pragma unroll 1
+            for (int col = 0; col < 6; col++)
+            {
+               SvT<T> e = sv_zero<T>();
+               if (col == 0) e.a.x = 1; else if (col == 1) e.a.y = 1; else if (col == 2) e.a.z = 1;
+               else if (col == 3) e.l.x = 1; else if (col == 4) e.l.y = 1; else e.l.z = 1;
+               const SvT<T> F = mul(Ic, e);
+               const int dc = d + col;
+               c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
+               c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
+               if (!(o.flags & MB2_ROOT_PARENT))
+                  crba_walk<T>(P, c, o.body, dc, js, jc, F);
+            }
+         }
+         if (!(o.flags & MB2_ROOT_PARENT))
+         {
+            // childInertia.applyTransform(child.transformToParent) (:658)
+            XfT<T> X;
+            if (jt == MB_REVOLUTE) X = joint_xf_1dof<T, true>(C, js, jc);
+            else if (jt == MB_PRISMATIC) X = joint_xf_1dof<T, false>(C, js, jc);
+            else X = stk_ld_xf<T>(c, o.slot);
+            const RbiT<T> K = rbi_to_parent(X, Ic);
+            if (o.flags & MB2_FIRST_CHILD)
+               acc = K;
+            else
+               acc = aux_ld_rbi<T>(c, o.paux) + K;
+            if (o.flags & MB2_STORE_ACC)
+               aux_st_rbi<T>(c, o.paux, acc);
+         }
+      }
+      s = ns;
+      cs = nc;
+   }
+   c.template pf_wait<0>();
+}
+} // namespace mb

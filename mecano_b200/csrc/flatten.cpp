@@ -151,6 +151,17 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       o.aux = (uint16_t)(B.aux >= 0 ? B.aux : 0);
       o.paux = (uint16_t)(B.parent >= 0 && P.body[B.parent].aux >= 0 ? P.body[B.parent].aux : 0);
    }
+   for (int i = 0; i < nb; i++)
+   {
+      const MbBody &B = P.body[i];
+      MbWalk &w = P.walk[i];
+      w.jtype = (uint8_t)B.jtype;
+      w.flags = (uint8_t)(B.parent < 0 ? 1 : 0);
+      w.parent = (uint8_t)(B.parent < 0 ? 0 : B.parent);
+      w.pad = 0;
+      w.dof = (uint16_t)B.dof_off;
+      w.slot = (uint16_t)slot2[i];
+   }
    // trailing records: ASCEND of a SixDoF joint can never be mistaken for a 1-DoF DESCEND by the look-ahead
    for (int k = P.nops; k < P.nops + 4; k++)
       P.op2[k].code = (uint8_t)(MB2_ASCEND | (MB_SIXDOF << 1));
@@ -183,6 +194,11 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
    {
       err = "tree has no joints";
       return MECANO_B200_ERR_INVALID_ARGUMENT;
+   }
+   if ((long)d->n_dofs * d->n_dofs > 65535)
+   {
+      err = "mass matrix has more than 65535 entries";
+      return MECANO_B200_ERR_TOO_LARGE;
    }
    if (nb > MB_MAX_BODIES)
    {
@@ -479,6 +495,24 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
       }
       P.nops = nops;
       build_op2(algo, P, nchild);
+   }
+   // ---- structural zeros of the mass matrix: DoF pairs of bodies on unrelated branches
+   {
+      const MbProgram &P = out.prog[MB_CRBA];
+      for (int i = 0; i < nb; i++)
+         for (int j = 0; j < nb; j++)
+         {
+            if (i == j)
+               continue;
+            const bool related = (j > i && j < subtree_end[i]) || (i > j && i < subtree_end[j]);
+            if (related)
+               continue;
+            for (int r = 0; r < P.body[i].ndof; r++)
+               for (int s = 0; s < P.body[j].ndof; s++)
+                  out.zero_entries.push_back((uint16_t)((P.body[i].dof_off + r) * nv + P.body[j].dof_off + s));
+         }
+      while (!out.zero_entries.empty() && out.zero_entries.size() % 8 != 0)
+         out.zero_entries.push_back(out.zero_entries.back());
    }
    return MECANO_B200_OK;
 }

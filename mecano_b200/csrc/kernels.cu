@@ -78,6 +78,24 @@ template <int BLOCK> struct GpuCtx2
    __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
    __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
    __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
+   // mass matrix: entry e = row * nv + col lives at mbase + e * mstride (entry-major: mstride = ld8; state-major: 8)
+   char *mbase;
+   unsigned mstride;
+   int nv;
+   const uint4 *zlist;
+   int nz8;
+   __device__ __forceinline__ int n_dofs() const { return nv; }
+   __device__ __forceinline__ void st_M(int e, double v) const { __stcs((double *)(mbase + (unsigned long long)(unsigned)e * mstride), v); }
+   __device__ __forceinline__ void zero_fill() const
+   {
+#pragma unroll 1
+      for (int k = 0; k < nz8; k++)
+      {
+         const uint4 u = __ldg(zlist + k);
+         st_M(u.x & 0xffffu, 0.0); st_M(u.x >> 16, 0.0); st_M(u.y & 0xffffu, 0.0); st_M(u.y >> 16, 0.0);
+         st_M(u.z & 0xffffu, 0.0); st_M(u.z >> 16, 0.0); st_M(u.w & 0xffffu, 0.0); st_M(u.w >> 16, 0.0);
+      }
+   }
    // prefetch ring: [stage][q | qd | x][BLOCK] doubles in shared memory, filled by cp.async (LDGSTS)
    int ring0; // index (doubles) of this thread's element of stage 0, row 0
    __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, bool use_qd, bool use_x) const
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    c.stk0 = ((ncst + 1) & ~1) + threadIdx.x;
    c.aux = aux;
    c.rec = rec;
-   if constexpr (ALGO == MB_RNEA)
+   if constexpr (ALGO == MB_RNEA || ALGO == MB_CRBA)
    {
       GpuCtx2<BLOCK> c2;
       c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
@@ -128,12 +146,18 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
       c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
       c2.ring0 = ((ncst + 1) & ~1) + 2 * P.stack2 * BLOCK + threadIdx.x;
       c2.aux = aux;
-      rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+      c2.nv = a.nv;
+      c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
+      c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
+      c2.zlist = (const uint4 *)a.zero_entries;
+      c2.nz8 = a.n_zero >> 3;
+      if constexpr (ALGO == MB_RNEA)
+         rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+      else
+         crba_state<double, GpuCtx2<BLOCK>>(P, c2);
    }
    else if constexpr (ALGO == MB_ABA)
       aba_state<double, Ctx, FEXT>(P, c, a.grav);
-   else
-      crba_state<double, Ctx>(P, c);
 }
 
 // compiled work-area classes (local memory per thread): {aux, rec}
@@ -187,7 +211,7 @@ int class_of(int algo, const MbProgram &P)
 size_t smem_bytes(int algo, const MbProgram &P, int block)
 {
    const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
-   if (algo == MB_RNEA)
+   if (algo == MB_RNEA || algo == MB_CRBA)
       return sizeof(double) * ((size_t)ncst + (2 * (size_t)P.stack2 + 3 * MB_PF_STAGES) * block);
    return sizeof(double) * ((size_t)ncst + (size_t)std::max(P.stack_doubles, 1) * block);
 }

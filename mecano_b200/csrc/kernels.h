@@ -12,6 +12,8 @@ struct KernelArgs
    const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
    double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
    const double *consts;            // device copy of the per-body constant records
+   const uint16_t *zero_entries;    // CRBA: structurally zero mass-matrix entries (multiple of 8, 16-byte aligned)
+   int32_t n_zero;
    long long n, ld;
    double grav[3];
    uint32_t flags;

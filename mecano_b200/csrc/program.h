@@ -83,6 +83,17 @@ struct MbOp2
 #define MB2_STORE_ACC 0x10u
 #define MB2_FIRST_CHILD 0x20u
 
+// per-body record for the CRBA ancestor walk (8 bytes)
+struct MbWalk
+{
+   uint8_t jtype;
+   uint8_t flags;  // bit0: the parent is the root body
+   uint8_t parent; // internal index of the parent body
+   uint8_t pad;
+   uint16_t dof;   // Mecano DoF row
+   uint16_t slot;  // stack slot (double2 units)
+};
+
 struct MbProgram
 {
    int32_t nb, nops, nv, nq;
@@ -93,6 +104,7 @@ struct MbProgram
    int32_t max_depth;
    MbBody body[MB_MAX_BODIES];
    uint32_t op[MB_MAX_OPS];
+   MbWalk walk[MB_MAX_BODIES];
    MbOp2 op2[MB_MAX_OPS + 4]; // trailing no-op records so that the look-ahead never reads past the end
 };
 

@@ -26,7 +26,10 @@ template <class T> struct CpuCtx
    T ld_x(int r) const { return (T)x[r * ld + s]; }
    T ld_fext(int b, int k) const { return (T)fext[(6 * b + k) * ld + s]; }
    void st_out(int r, T v) { out[r * ld + s] = (double)v; }
-   void st_M(int r, int c, T v) { M[((long)r * nv + c) * ld + s] = (double)v; }
+   void st_M(int e, T v) { M[(long)e * ld + s] = (double)v; }
+   int n_dofs() const { return nv; }
+   const std::vector<uint16_t> *zl;
+   void zero_fill() { for (uint16_t e : *zl) st_M(e, (T)0); }
    void stk_ld2(int slot2, int j, T &a, T &b) const { a = stk[2 * (slot2 + j)]; b = stk[2 * (slot2 + j) + 1]; }
    void stk_st2(int slot2, int j, T a, T b) { stk[2 * (slot2 + j)] = a; stk[2 * (slot2 + j) + 1] = b; }
    T ring[4][3];
@@ -72,6 +75,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       std::fill(aux.begin(), aux.end(), nan);
       std::fill(rec.begin(), rec.end(), nan);
       CpuCtx<T> c{q, qd, x, fext, out, out, ld, s, ft.nv, stk.data(), aux.data(), rec.data(), consts.data()};
+      c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
          if (fext) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav, !(flags & 1u), !(flags & 2u));
