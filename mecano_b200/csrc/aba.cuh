@@ -1,0 +1,418 @@
+// aba.cuh -- one state of the articulated-body algorithm (ForwardDynamicsCalculator.compute(),
+// M/algorithms/ForwardDynamicsCalculator.java:508-520; passOne :1085-1127, passTwo :1136-1254, passThree :1259-1310;
+// ArticulatedBodyInertia.java:176-186, :359-375), with the frame update fused in like rnea.cuh.
+//
+// Passes one and two are interleaved along the depth-first traversal (DESCEND = twist of the body, ASCEND =
+// articulated inertia / bias force folded into the parent), so only the current root-to-leaf path is live on the
+// shared-memory stack; pass three is a second, DESCEND-only sweep.  What pass three needs from pass two
+// (g = U / D and k0 = u / D, seven doubles per body) goes through per-thread local memory, whose footprint is
+// bounded by the resident threads and therefore stays in L2; sin/cos and the twists are recomputed instead.
+#pragma once
+#include "jointmath.cuh"
+
+namespace mb
+{
+#define MB_ABA_REC 7 // doubles per body in the pass-three record
+
+template <class T> struct AbaPipe
+{
+   T s, c;        // current op: sin/cos (prismatic: s = q)
+   T qd, x;       // current op: joint velocity, joint effort
+   T mq;          // next op: raw configuration
+   T ls, lc;      // sin/cos of the last DESCEND (leaf)
+};
+
+template <class T, class Ctx> MB_HD void aux_st_abi(Ctx &c, int i, const AbiT<T> &I, const SvT<T> &p)
+{
+   c.aux_st(i + 0, I.A.xx); c.aux_st(i + 1, I.A.xy); c.aux_st(i + 2, I.A.xz); c.aux_st(i + 3, I.A.yy); c.aux_st(i + 4, I.A.yz); c.aux_st(i + 5, I.A.zz);
+   c.aux_st(i + 6, I.C.xx); c.aux_st(i + 7, I.C.xy); c.aux_st(i + 8, I.C.xz); c.aux_st(i + 9, I.C.yx); c.aux_st(i + 10, I.C.yy); c.aux_st(i + 11, I.C.yz);
+   c.aux_st(i + 12, I.C.zx); c.aux_st(i + 13, I.C.zy); c.aux_st(i + 14, I.C.zz);
+   c.aux_st(i + 15, I.L.xx); c.aux_st(i + 16, I.L.xy); c.aux_st(i + 17, I.L.xz); c.aux_st(i + 18, I.L.yy); c.aux_st(i + 19, I.L.yz); c.aux_st(i + 20, I.L.zz);
+   aux_st_sv<T>(c, i + 21, p);
+}
+template <class T, class Ctx> MB_HD void aux_ld_abi(Ctx &c, int i, AbiT<T> &I, SvT<T> &p)
+{
+   I.A.xx = c.aux_ld(i + 0); I.A.xy = c.aux_ld(i + 1); I.A.xz = c.aux_ld(i + 2); I.A.yy = c.aux_ld(i + 3); I.A.yz = c.aux_ld(i + 4); I.A.zz = c.aux_ld(i + 5);
+   I.C.xx = c.aux_ld(i + 6); I.C.xy = c.aux_ld(i + 7); I.C.xz = c.aux_ld(i + 8); I.C.yx = c.aux_ld(i + 9); I.C.yy = c.aux_ld(i + 10); I.C.yz = c.aux_ld(i + 11);
+   I.C.zx = c.aux_ld(i + 12); I.C.zy = c.aux_ld(i + 13); I.C.zz = c.aux_ld(i + 14);
+   I.L.xx = c.aux_ld(i + 15); I.L.xy = c.aux_ld(i + 16); I.L.xz = c.aux_ld(i + 17); I.L.yy = c.aux_ld(i + 18); I.L.yz = c.aux_ld(i + 19); I.L.zz = c.aux_ld(i + 20);
+   p = aux_ld_sv<T>(c, i + 21);
+}
+
+// ---- pass one: twist of the body (the frame tree's lazy twist-of-frame, MovingReferenceFrame.java:279-311)
+template <class T, class Ctx, bool REV, bool SC>
+MB_HD void aba_descend_1dof(Ctx &c, const MbOp2 o, SvT<T> &v, AbaPipe<T> &pp, T &ns, T &nc)
+{
+   if (SC)
+      mb_sincos(pp.mq, &ns, &nc);
+   const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), pp.s, pp.c);
+   v = motion_to_child(X, v);
+   if (REV) v.a.z += pp.qd;
+   else v.l.z += pp.qd;
+   pp.ls = pp.s;
+   pp.lc = pp.c;
+   if (!(o.flags & MB2_LEAF))
+   {
+      stk_st_sv<T>(c, o.slot, v);
+      c.stk_st2(o.slot, 3, pp.s, pp.c);
+   }
+}
+
+// ---- pass one quantities (bias wrench / bias acceleration, :1109-1118) and pass two (:1136-1254) for body i
+template <class T, class Ctx, bool FEXT, bool REV, bool SC>
+MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp, T &ns, T &nc)
+{
+   if (SC)
+      mb_sincos(pp.mq, &ns, &nc);
+   const T *C = c.cst(o.body);
+   T s = pp.ls, cs = pp.lc;
+   SvT<T> vb = v;
+   if (!(o.flags & MB2_LEAF))
+   {
+      vb = stk_ld_sv<T>(c, o.slot);
+      c.stk_ld2(o.slot, 3, s, cs);
+   }
+   const T qd = pp.qd, tau = pp.x;
+   const RbiT<T> I = ld_rbi(C);
+   SvT<T> pA = cross_force(vb, mul(I, vb));
+   if (FEXT)
+      pA = pA - external_wrench<T>(c, ext, C);
+   AbiT<T> IA = abi_from_rbi(I);
+   if (!(o.flags & MB2_LEAF))
+   {
+      IA = IA + acc;
+      pA = pA + pacc;
+   }
+   SvT<T> U;
+   T D, u;
+   if (REV)
+   {
+      U.a = v3<T>(IA.A.xz, IA.A.yz, IA.A.zz);
+      U.l = v3<T>(IA.C.zx, IA.C.zy, IA.C.zz);
+      D = IA.A.zz;
+      u = tau - pA.a.z;
+   }
+   else
+   {
+      U.a = v3<T>(IA.C.xz, IA.C.yz, IA.C.zz);
+      U.l = v3<T>(IA.L.xz, IA.L.yz, IA.L.zz);
+      D = IA.L.zz;
+      u = tau - pA.l.z;
+   }
+   const T Dinv = mb_rcp(D);
+   SvT<T> g;
+   g.a = Dinv * U.a;
+   g.l = Dinv * U.l;
+   const T k0 = Dinv * u;
+   // record for pass three: qdd = k0 - g . a'
+   const int r = o.body * MB_ABA_REC;
+   c.rec_st(r + 0, g.a.x); c.rec_st(r + 1, g.a.y); c.rec_st(r + 2, g.a.z);
+   c.rec_st(r + 3, g.l.x); c.rec_st(r + 4, g.l.y); c.rec_st(r + 5, g.l.z);
+   c.rec_st(r + 6, k0);
+   if (!(o.flags & MB2_ROOT_PARENT))
+   {
+      // bias acceleration c = v x (S qd): only x / y components
+      T cax, cay, clx, cly;
+      if (REV)
+      {
+         cax = vb.a.y * qd; cay = -(vb.a.x * qd);
+         clx = vb.l.y * qd; cly = -(vb.l.x * qd);
+      }
+      else
+      {
+         cax = (T)0; cay = (T)0;
+         clx = vb.a.y * qd; cly = -(vb.a.x * qd);
+      }
+      const AbiT<T> Ia = abi_downdate(IA, U, g); // I^a = I^A - U D^-1 U^T
+      SvT<T> pa = pA;                            // p^a = p^A + I^a c + U D^-1 u
+      pa.a.x += Ia.A.xx * cax + Ia.A.xy * cay + Ia.C.xx * clx + Ia.C.xy * cly + k0 * U.a.x;
+      pa.a.y += Ia.A.xy * cax + Ia.A.yy * cay + Ia.C.yx * clx + Ia.C.yy * cly + k0 * U.a.y;
+      pa.a.z += Ia.A.xz * cax + Ia.A.yz * cay + Ia.C.zx * clx + Ia.C.zy * cly + k0 * U.a.z;
+      pa.l.x += Ia.C.xx * cax + Ia.C.yx * cay + Ia.L.xx * clx + Ia.L.xy * cly + k0 * U.l.x;
+      pa.l.y += Ia.C.xy * cax + Ia.C.yy * cay + Ia.L.xy * clx + Ia.L.yy * cly + k0 * U.l.y;
+      pa.l.z += Ia.C.xz * cax + Ia.C.yz * cay + Ia.L.xz * clx + Ia.L.yz * cly + k0 * U.l.z;
+      const XfT<T> X = joint_xf_1dof<T, REV>(C, s, cs);
+      const AbiT<T> K = abi_to_parent(X, Ia); // :1159-1165
+      const SvT<T> Pp = force_to_parent(X, pa);
+      if (o.flags & MB2_FIRST_CHILD)
+      {
+         acc = K;
+         pacc = Pp;
+      }
+      else
+      {
+         aux_ld_abi<T>(c, o.paux, acc, pacc);
+         acc = acc + K;
+         pacc = pacc + Pp;
+      }
+      if (o.flags & MB2_STORE_ACC)
+         aux_st_abi<T>(c, o.paux, acc, pacc);
+   }
+}
+
+template <class T, class Ctx> MB_HD void aba_descend_6dof(Ctx &c, const MbOp2 o, SvT<T> &v)
+{
+   const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
+   const SvT<T> vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
+   v = motion_to_child(X, v) + vj;
+   stk_st_sv<T>(c, o.slot, v);
+   if (!(o.flags & MB2_ROOT_PARENT))
+      stk_st_xf<T>(c, o.slot + 3, X);
+}
+
+template <class T, class Ctx, bool FEXT>
+MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> &pacc)
+{
+   const T *C = c.cst(o.body);
+   const SvT<T> vb = stk_ld_sv<T>(c, o.slot);
+   const RbiT<T> I = ld_rbi(C);
+   SvT<T> pA = cross_force(vb, mul(I, vb));
+   if (FEXT)
+      pA = pA - external_wrench<T>(c, ext, C);
+   AbiT<T> IA = abi_from_rbi(I);
+   if (!(o.flags & MB2_LEAF))
+   {
+      IA = IA + acc;
+      pA = pA + pacc;
+   }
+   const SvT<T> tau6 = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
+   // D = I^A, U = I^A: a_i = D^-1 u, and the joint transmits nothing but tau to its parent
+   const SvT<T> x = abi_solve(IA, tau6 - pA);
+   const int r = o.body * MB_ABA_REC;
+   c.rec_st(r + 0, x.a.x); c.rec_st(r + 1, x.a.y); c.rec_st(r + 2, x.a.z);
+   c.rec_st(r + 3, x.l.x); c.rec_st(r + 4, x.l.y); c.rec_st(r + 5, x.l.z);
+   if (!(o.flags & MB2_ROOT_PARENT))
+   {
+      const XfT<T> X = stk_ld_xf<T>(c, o.slot + 3);
+      const SvT<T> Pp = force_to_parent(X, tau6);
+      if (o.flags & MB2_FIRST_CHILD)
+      {
+         acc = AbiT<T>();
+         pacc = Pp;
+      }
+      else
+      {
+         aux_ld_abi<T>(c, o.paux, acc, pacc);
+         pacc = pacc + Pp;
+      }
+      if (o.flags & MB2_STORE_ACC)
+         aux_st_abi<T>(c, o.paux, acc, pacc);
+   }
+}
+
+// ---- pass three (:1259-1310): accelerations, root to leaves
+template <class T, class Ctx, bool REV, bool SC>
+MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp, T &ns, T &nc)
+{
+   if (SC)
+      mb_sincos(pp.mq, &ns, &nc);
+   const int r = o.body * MB_ABA_REC;
+   SvT<T> g;
+   g.a = v3<T>(c.rec_ld(r + 0), c.rec_ld(r + 1), c.rec_ld(r + 2));
+   g.l = v3<T>(c.rec_ld(r + 3), c.rec_ld(r + 4), c.rec_ld(r + 5));
+   const T k0 = c.rec_ld(r + 6);
+   const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), pp.s, pp.c);
+   v = motion_to_child(X, v);
+   a = motion_to_child(X, a); // a' = X^-1 a_parent + c
+   const T qd = pp.qd;
+   if (REV)
+   {
+      a.a.x += v.a.y * qd; a.a.y -= v.a.x * qd;
+      a.l.x += v.l.y * qd; a.l.y -= v.l.x * qd;
+      v.a.z += qd;
+   }
+   else
+   {
+      a.l.x += v.a.y * qd; a.l.y -= v.a.x * qd;
+      v.l.z += qd;
+   }
+   const T qdd = k0 - (dot(g.a, a.a) + dot(g.l, a.l)); // D^-1 (u - U^T a')
+   c.st_out(o.dof, qdd);
+   if (REV) a.a.z += qdd;
+   else a.l.z += qdd;
+   if (o.flags & MB2_SAVE_STATE)
+   {
+      aux_st_sv<T>(c, o.aux, v);
+      aux_st_sv<T>(c, o.aux + 6, a);
+   }
+}
+
+template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, SvT<T> &v, SvT<T> &a)
+{
+   const int r = o.body * MB_ABA_REC;
+   SvT<T> x;
+   x.a = v3<T>(c.rec_ld(r + 0), c.rec_ld(r + 1), c.rec_ld(r + 2));
+   x.l = v3<T>(c.rec_ld(r + 3), c.rec_ld(r + 4), c.rec_ld(r + 5));
+   const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
+   const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
+   v = motion_to_child(X, v) + vj;
+   const SvT<T> a1 = motion_to_child(X, a) + cross_motion(v, vj);
+   const SvT<T> qdd = x - a1;
+   c.st_out(o.dof + 0, qdd.a.x); c.st_out(o.dof + 1, qdd.a.y); c.st_out(o.dof + 2, qdd.a.z);
+   c.st_out(o.dof + 3, qdd.l.x); c.st_out(o.dof + 4, qdd.l.y); c.st_out(o.dof + 5, qdd.l.z);
+   a = x;
+   if (o.flags & MB2_SAVE_STATE)
+   {
+      aux_st_sv<T>(c, o.aux, v);
+      aux_st_sv<T>(c, o.aux + 6, a);
+   }
+}
+
+// which scalars an op needs from the prefetch ring: DESCEND q + qd, ASCEND qd + tau
+MB_HD int aba_pf_mask(const MbOp2 &o) { return MB2_JT(o.code) == MB_SIXDOF ? 0 : ((o.code & MB2_ASCEND) ? 6 : 3); }
+
+template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P, Ctx &c, const T *grav)
+{
+   SvT<T> v = sv_zero<T>(), pacc = sv_zero<T>();
+   AbiT<T> acc = AbiT<T>();
+   AbaPipe<T> pp;
+   pp.s = pp.qd = pp.x = pp.mq = pp.ls = (T)0;
+   pp.c = pp.lc = (T)1;
+   const int nops = P.nops;
+   // =========================== passes one and two, interleaved
+#pragma unroll
+   for (int k = 0; k < MB_PF_DIST; k++)
+   {
+      const MbOp2 o = P.op2[k];
+      const int m = aba_pf_mask(o);
+      if (m)
+         c.pf_issue(k, o.cfg, o.dof, m);
+      c.pf_commit();
+   }
+   c.template pf_wait<0>();
+   {
+      const MbOp2 o0 = P.op2[0];
+      if (mb2_is_1dof_descend(o0))
+      {
+         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+         else pp.s = q0;
+      }
+   }
+#pragma unroll 1
+   for (int k = 0; k < nops; k++)
+   {
+      const MbOp2 o = P.op2[k];
+      {
+         const MbOp2 od = P.op2[k + MB_PF_DIST];
+         const int m = aba_pf_mask(od);
+         if (m)
+            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, m);
+         c.pf_commit();
+         c.template pf_wait<MB_PF_DIST - 1>();
+      }
+      pp.qd = pp.x = pp.mq = (T)0;
+      if (MB2_JT(o.code) != MB_SIXDOF)
+      {
+         pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+         if (o.code & MB2_ASCEND)
+            pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+      }
+      if (o.pf & 1u)
+         pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+      // twist of the parent: carried along a chain, zero for the root body, otherwise on the parent's stack slot
+      if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+      {
+         if (o.flags & MB2_ROOT_PARENT)
+            v = sv_zero<T>();
+         else
+            v = stk_ld_sv<T>(c, o.pslot);
+      }
+      const int ext = FEXT ? P.body[o.body].ext_index : 0;
+      T ns = pp.mq, nc = (T)1;
+      switch (o.code & 0xfu)
+      {
+         case 0 | (MB_REVOLUTE << 1): aba_descend_1dof<T, Ctx, true, false>(c, o, v, pp, ns, nc); break;
+         case 0 | (MB_REVOLUTE << 1) | MB2_SC: aba_descend_1dof<T, Ctx, true, true>(c, o, v, pp, ns, nc); break;
+         case 1 | (MB_REVOLUTE << 1): aba_ascend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+         case 1 | (MB_REVOLUTE << 1) | MB2_SC: aba_ascend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+         case 0 | (MB_PRISMATIC << 1): aba_descend_1dof<T, Ctx, false, false>(c, o, v, pp, ns, nc); break;
+         case 0 | (MB_PRISMATIC << 1) | MB2_SC: aba_descend_1dof<T, Ctx, false, true>(c, o, v, pp, ns, nc); break;
+         case 1 | (MB_PRISMATIC << 1): aba_ascend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+         case 1 | (MB_PRISMATIC << 1) | MB2_SC: aba_ascend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+         default:
+            if (o.code & MB2_SC)
+               mb_sincos(pp.mq, &ns, &nc);
+            if (o.code & MB2_ASCEND)
+               aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
+            else
+               aba_descend_6dof<T, Ctx>(c, o, v);
+            break;
+      }
+      pp.s = ns;
+      pp.c = nc;
+   }
+   c.template pf_wait<0>();
+   // =========================== pass three: DESCEND records only (P.op3), same software pipeline
+   SvT<T> a = sv_zero<T>();
+   v = sv_zero<T>();
+   const int nb = P.nb;
+#pragma unroll
+   for (int k = 0; k < MB_PF_DIST; k++)
+   {
+      const MbOp2 o = P.op3[k];
+      if (mb2_is_1dof_descend(o))
+         c.pf_issue(k, o.cfg, o.dof, 3);
+      c.pf_commit();
+   }
+   c.template pf_wait<0>();
+   {
+      const MbOp2 o0 = P.op3[0];
+      pp.s = (T)0;
+      pp.c = (T)1;
+      if (mb2_is_1dof_descend(o0))
+      {
+         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+         else pp.s = q0;
+      }
+   }
+#pragma unroll 1
+   for (int k = 0; k < nb; k++)
+   {
+      const MbOp2 o = P.op3[k];
+      {
+         const MbOp2 od = P.op3[k + MB_PF_DIST];
+         if (mb2_is_1dof_descend(od))
+            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, 3);
+         c.pf_commit();
+         c.template pf_wait<MB_PF_DIST - 1>();
+      }
+      pp.qd = pp.mq = (T)0;
+      if (MB2_JT(o.code) != MB_SIXDOF)
+         pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      if (o.pf & 1u)
+         pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+      if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
+      {
+         if (o.flags & MB2_ROOT_PARENT)
+         {
+            v = sv_zero<T>();
+            a = sv_zero<T>();
+            a.l = v3<T>(-grav[0], -grav[1], -grav[2]); // root acceleration = -gravity (ForwardDynamicsCalculator.java:313-319)
+         }
+         else
+         {
+            v = aux_ld_sv<T>(c, o.paux);
+            a = aux_ld_sv<T>(c, o.paux + 6);
+         }
+      }
+      T ns = pp.mq, nc = (T)1;
+      switch (o.code & 0xfu)
+      {
+         case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false>(c, o, v, a, pp, ns, nc); break;
+         case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true>(c, o, v, a, pp, ns, nc); break;
+         case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false>(c, o, v, a, pp, ns, nc); break;
+         case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true>(c, o, v, a, pp, ns, nc); break;
+         default:
+            if (o.code & MB2_SC)
+               mb_sincos(pp.mq, &ns, &nc);
+            aba_pass3_6dof<T, Ctx>(c, o, v, a);
+            break;
+      }
+      pp.s = ns;
+      pp.c = nc;
+   }
+   c.template pf_wait<0>();
+}
+} // namespace mb

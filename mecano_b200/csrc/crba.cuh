@@ -106,7 +106,7 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
    {
       const MbOp2 o = P.op2[k];
       if (mb2_is_1dof_descend(o))
-         c.pf_issue(k, o.cfg, o.dof, false, false);
+         c.pf_issue(k, o.cfg, o.dof, 1);
       c.pf_commit();
    }
    c.template pf_wait<0>();
@@ -126,7 +126,7 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
       {
          const MbOp2 od = P.op2[k + MB_PF_DIST];
          if (mb2_is_1dof_descend(od))
-            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, false, false);
+            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, 1);
          c.pf_commit();
          c.template pf_wait<MB_PF_DIST - 1>();
       }

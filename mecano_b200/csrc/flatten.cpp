@@ -107,8 +107,8 @@ int slot2_size(int algo, int jtype, bool root_parent)
    {
       case MB_RNEA: // wrench (3) + sin/cos (1); SixDoF: wrench (3) + transform (6) unless attached to the root body
          return jtype == MB_SIXDOF ? (root_parent ? 3 : 9) : 4;
-      case MB_ABA: // twist (3) + sin/cos (1) + joint velocity (1); SixDoF: twist (3) + transform (6) + joint twist (3)
-         return jtype == MB_SIXDOF ? 12 : 5;
+      case MB_ABA: // twist (3) + sin/cos (1); SixDoF: twist (3) + transform (6) unless attached to the root body
+         return jtype == MB_SIXDOF ? (root_parent ? 3 : 9) : 4;
       default: // CRBA: sin/cos (1); SixDoF: transform (6)
          return jtype == MB_SIXDOF ? 6 : 1;
    }
@@ -165,15 +165,28 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
    // trailing records: ASCEND of a SixDoF joint can never be mistaken for a 1-DoF DESCEND by the look-ahead
    for (int k = P.nops; k < P.nops + 4; k++)
       P.op2[k].code = (uint8_t)(MB2_ASCEND | (MB_SIXDOF << 1));
+   // pass-three list: DESCEND records in order
+   int n3 = 0;
    for (int k = 0; k < P.nops; k++)
+      if (!(P.op2[k].code & MB2_ASCEND))
+         P.op3[n3++] = P.op2[k];
+   for (int k = n3; k < n3 + 4; k++)
    {
-      const MbOp2 &n1 = P.op2[k + 1], &n2 = P.op2[k + 2];
-      if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) == MB_REVOLUTE)
-         P.op2[k].code |= MB2_SC;
-      (void)n2;
-      if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) != MB_SIXDOF)
-         P.op2[k].pf |= 1u;
+      std::memset(&P.op3[k], 0, sizeof(MbOp2));
+      P.op3[k].code = (uint8_t)(MB2_ASCEND | (MB_SIXDOF << 1));
    }
+   auto look_ahead = [](MbOp2 *ops, int n) {
+      for (int k = 0; k < n; k++)
+      {
+         const MbOp2 &n1 = ops[k + 1];
+         if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) == MB_REVOLUTE)
+            ops[k].code |= MB2_SC;
+         if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) != MB_SIXDOF)
+            ops[k].pf |= 1u;
+      }
+   };
+   look_ahead(P.op2, P.nops);
+   look_ahead(P.op3, n3);
 }
 } // namespace
 
@@ -437,7 +450,8 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          B.rec = rec;
          rec += rec_size(B.jtype);
       }
-      P.rec_doubles = algo == MB_ABA ? rec : 0;
+      (void)rec;
+      P.rec_doubles = algo == MB_ABA ? 7 * nb : 0; // MB_ABA_REC per body (aba.cuh)
 
       // ops: iterative DFS emitting DESCEND on entry and ASCEND on exit
       int nops = 0;

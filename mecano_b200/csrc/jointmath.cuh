@@ -106,6 +106,24 @@ MB_HD double mb_reduce_angle(double x)
 }
 MB_HD float mb_reduce_angle(float x) { return x; }
 
+// Reciprocal without the library's special-case branch (which would split the basic block of an ABA op): hardware
+// seed (rcp.approx.ftz.f64, ~2^-20) + three Newton steps.  Used for the joint-space inertia D = S^T I^A S of a
+// 1-DoF joint, a well-scaled positive number.
+MB_HD double mb_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+   double r;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+   r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+   r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+   r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+   return r;
+#else
+   return 1.0 / x;
+#endif
+}
+MB_HD float mb_rcp(float x) { return 1.0f / x; }
+
 MB_HD bool mb2_is_1dof_descend(const MbOp2 &o) { return !(o.code & MB2_ASCEND) && MB2_JT(o.code) != MB_SIXDOF; }
 
 template <class T> MB_HD M3T<T> ld_m3(const T *p)

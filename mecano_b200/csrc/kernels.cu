@@ -26,42 +26,17 @@ namespace mb
 {
 namespace
 {
-// BLOCK (threads per block = stack stride) is a compile-time constant so that stack addresses are
-// base + immediate; shared memory is addressed through the mb_smem symbol so that the compiler emits
-// LDS/STS (a pointer kept in a struct degrades to generic LD/ST).
-template <int BLOCK> struct GpuCtx
-{
-   const double *q, *qd, *x, *fext;
-   double *out;
-   long long ld, s;
-   int nv;
-   int stk0;     // index in mb_smem of stack slot 0 of this thread
-   double *aux;  // local memory
-   double *rec;  // local memory
-
-   __device__ __forceinline__ double ld_q(int r) const { return __ldg(q + r * ld + s); }
-   __device__ __forceinline__ double ld_qd(int r) const { return __ldg(qd + r * ld + s); }
-   __device__ __forceinline__ double ld_x(int r) const { return __ldg(x + r * ld + s); }
-   __device__ __forceinline__ double ld_fext(int b, int k) const { return __ldg(fext + (6 * b + k) * ld + s); }
-   __device__ __forceinline__ void st_out(int r, double v) { out[r * ld + s] = v; }
-   __device__ __forceinline__ void st_M(int r, int c, double v) { __stcs(out + ((long long)r * nv + c) * ld + s, v); }
-   __device__ __forceinline__ double stk_ld(int i) const { return mb_smem[stk0 + i * BLOCK]; }
-   __device__ __forceinline__ void stk_st(int i, double v) { mb_smem[stk0 + i * BLOCK] = v; }
-   __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
-   __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
-   __device__ __forceinline__ double rec_ld(int i) const { return rec[i]; }
-   __device__ __forceinline__ void rec_st(int i, double v) { rec[i] = v; }
-   __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
-};
-
-// v2 context (rnea.cuh): per-thread base pointers (one IMAD.WIDE per global access), stack of double2 (LDS.128 / STS.128)
+// BLOCK (threads per block = stack stride) is a compile-time constant so that stack addresses are base + immediate;
+// shared memory is addressed through the mb_smem symbol so that the compiler emits LDS/STS (a pointer kept in a
+// struct degrades to generic LD/ST).
+// Per-thread context: per-thread base pointers (one IMAD.WIDE per global access), stack of double2 (LDS.128 / STS.128)
 template <int BLOCK> struct GpuCtx2
 {
    const char *qb, *qdb, *xb, *fb;
    char *ob;
    unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
    int stk0;     // index (double2 units) of stack slot 0 of this thread
-   double *aux;
+   double *aux, *rec; // local memory
 
    __device__ __forceinline__ double ld_q(int r) const { return __ldg((const double *)(qb + (unsigned long long)(unsigned)r * ld8)); }
    __device__ __forceinline__ double ld_qd(int r) const { return __ldg((const double *)(qdb + (unsigned long long)(unsigned)r * ld8)); }
@@ -77,6 +52,8 @@ template <int BLOCK> struct GpuCtx2
    __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b) { reinterpret_cast<double2 *>(mb_smem)[stk0 + (slot2 + j) * BLOCK] = make_double2(a, b); }
    __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
    __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
+   __device__ __forceinline__ double rec_ld(int i) const { return rec[i]; }
+   __device__ __forceinline__ void rec_st(int i, double v) { rec[i] = v; }
    __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
    // mass matrix: entry e = row * nv + col lives at mbase + e * mstride (entry-major: mstride = ld8; state-major: 8)
    char *mbase;
@@ -98,24 +75,20 @@ template <int BLOCK> struct GpuCtx2
    }
    // prefetch ring: [stage][q | qd | x][BLOCK] doubles in shared memory, filled by cp.async (LDGSTS)
    int ring0; // index (doubles) of this thread's element of stage 0, row 0
-   __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, bool use_qd, bool use_x) const
+   // mask: 1 = q[cfg], 2 = qd[dof], 4 = x[dof]
+   __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, int mask) const
    {
       const unsigned dst = (unsigned)__cvta_generic_to_shared(mb_smem + ring0 + stage * 3 * BLOCK);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
-      if (use_qd)
+      if (mask & 1)
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
+      if (mask & 2)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
-      if (use_x)
+      if (mask & 4)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 2 * BLOCK * 8), "l"(xb + (unsigned long long)(unsigned)dof * ld8) : "memory");
    }
    __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
    template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
    __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_smem[ring0 + (stage * 3 + j) * BLOCK]; }
-};
-
-// state-major mass-matrix output (Mecano's per-state dense layout): uncoalesced, provided for drop-in use
-template <int BLOCK> struct GpuCtxStateMajor : GpuCtx<BLOCK>
-{
-   __device__ __forceinline__ void st_M(int r, int c, double v) { this->out[this->s * (long long)this->nv * this->nv + (long long)r * this->nv + c] = v; }
 };
 
 template <int ALGO, bool FEXT, bool STATE_MAJOR, int BLOCK, int AUXN, int RECN>
@@ -130,34 +103,25 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
       return;
    double aux[AUXN > 0 ? AUXN : 1];
    double rec[RECN > 0 ? RECN : 1];
-   typedef typename std::conditional<STATE_MAJOR, GpuCtxStateMajor<BLOCK>, GpuCtx<BLOCK>>::type Ctx;
-   Ctx c;
-   c.q = a.q; c.qd = a.qd; c.x = a.x; c.fext = a.fext; c.out = a.out;
-   c.ld = a.ld; c.s = s; c.nv = a.nv;
-   c.stk0 = ((ncst + 1) & ~1) + threadIdx.x;
-   c.aux = aux;
-   c.rec = rec;
-   if constexpr (ALGO == MB_RNEA || ALGO == MB_CRBA)
-   {
-      GpuCtx2<BLOCK> c2;
-      c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
-      c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
-      c2.ld8 = (unsigned)(a.ld * 8);
-      c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
-      c2.ring0 = ((ncst + 1) & ~1) + 2 * P.stack2 * BLOCK + threadIdx.x;
-      c2.aux = aux;
-      c2.nv = a.nv;
-      c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
-      c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
-      c2.zlist = (const uint4 *)a.zero_entries;
-      c2.nz8 = a.n_zero >> 3;
-      if constexpr (ALGO == MB_RNEA)
-         rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
-      else
-         crba_state<double, GpuCtx2<BLOCK>>(P, c2);
-   }
+   GpuCtx2<BLOCK> c2;
+   c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
+   c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
+   c2.ld8 = (unsigned)(a.ld * 8);
+   c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
+   c2.ring0 = ((ncst + 1) & ~1) + 2 * P.stack2 * BLOCK + threadIdx.x;
+   c2.aux = aux;
+   c2.rec = rec;
+   c2.nv = a.nv;
+   c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
+   c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
+   c2.zlist = (const uint4 *)a.zero_entries;
+   c2.nz8 = a.n_zero >> 3;
+   if constexpr (ALGO == MB_RNEA)
+      rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
    else if constexpr (ALGO == MB_ABA)
-      aba_state<double, Ctx, FEXT>(P, c, a.grav);
+      aba_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav);
+   else
+      crba_state<double, GpuCtx2<BLOCK>>(P, c2);
 }
 
 // compiled work-area classes (local memory per thread): {aux, rec}
@@ -166,7 +130,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
 constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
 constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
 constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
-constexpr int kAbaRec0 = 9 * 33 + 9, kAbaRec1 = 9 * 128 + 18;
+constexpr int kAbaRec0 = MB_ABA_REC * 33, kAbaRec1 = MB_ABA_REC * 128;
 constexpr int kNumCfg = 8;
 constexpr int kCfgClass[kNumCfg] = {0, 0, 0, 0, 0, 1, 1, 1};
 constexpr int kCfgBlock[kNumCfg] = {384, 320, 256, 192, 128, 128, 64, 32};
@@ -211,9 +175,8 @@ int class_of(int algo, const MbProgram &P)
 size_t smem_bytes(int algo, const MbProgram &P, int block)
 {
    const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
-   if (algo == MB_RNEA || algo == MB_CRBA)
-      return sizeof(double) * ((size_t)ncst + (2 * (size_t)P.stack2 + 3 * MB_PF_STAGES) * block);
-   return sizeof(double) * ((size_t)ncst + (size_t)std::max(P.stack_doubles, 1) * block);
+   (void)algo;
+   return sizeof(double) * ((size_t)ncst + (2 * (size_t)P.stack2 + 3 * MB_PF_STAGES) * block);
 }
 } // namespace
 

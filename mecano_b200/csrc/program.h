@@ -105,6 +105,7 @@ struct MbProgram
    MbBody body[MB_MAX_BODIES];
    uint32_t op[MB_MAX_OPS];
    MbWalk walk[MB_MAX_BODIES];
+   MbOp2 op3[MB_MAX_BODIES + 4]; // ABA pass three: the DESCEND records only, with their own SC / pf look-ahead bits
    MbOp2 op2[MB_MAX_OPS + 4]; // trailing no-op records so that the look-ahead never reads past the end
 };
 

@@ -161,13 +161,14 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
    pp.s = pp.qd = pp.x = pp.mq = pp.ls = (T)0;
    pp.c = pp.lc = (T)1;
    const int nops = P.nops;
+   const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
    // prologue: scalars of ops 0 .. MB_PF_DIST-1
 #pragma unroll
    for (int k = 0; k < MB_PF_DIST; k++)
    {
       const MbOp2 o = P.op2[k];
       if (mb2_is_1dof_descend(o))
-         c.pf_issue(k, o.cfg, o.dof, use_qd, use_qdd);
+         c.pf_issue(k, o.cfg, o.dof, pfmask);
       c.pf_commit();
    }
    c.template pf_wait<0>();
@@ -187,7 +188,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
       {
          const MbOp2 od = P.op2[k + MB_PF_DIST];
          if (mb2_is_1dof_descend(od))
-            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, use_qd, use_qdd);
+            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, pfmask);
          c.pf_commit();
          c.template pf_wait<MB_PF_DIST - 1>(); // everything up to the group of op k + 1 has landed
       }

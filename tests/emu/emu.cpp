@@ -33,11 +33,12 @@ template <class T> struct CpuCtx
    void stk_ld2(int slot2, int j, T &a, T &b) const { a = stk[2 * (slot2 + j)]; b = stk[2 * (slot2 + j) + 1]; }
    void stk_st2(int slot2, int j, T a, T b) { stk[2 * (slot2 + j)] = a; stk[2 * (slot2 + j) + 1] = b; }
    T ring[4][3];
-   void pf_issue(int stage, int cfg, int dof, bool use_qd, bool use_x)
+   void pf_issue(int stage, int cfg, int dof, int mask)
    {
-      ring[stage][0] = ld_q(cfg);
-      if (use_qd) ring[stage][1] = ld_qd(dof);
-      if (use_x) ring[stage][2] = ld_x(dof);
+      const T nan = (T)(0.0 / 0.0);
+      ring[stage][0] = (mask & 1) ? ld_q(cfg) : nan;
+      ring[stage][1] = (mask & 2) ? ld_qd(dof) : nan;
+      ring[stage][2] = (mask & 4) ? ld_x(dof) : nan;
    }
    void pf_commit() {}
    template <int N> void pf_wait() {}
@@ -107,7 +108,7 @@ extern "C" int emu_program_info(const mecano_b200_tree_desc *d, int algo, int *o
    int rc = mb::flatten_tree(d, ft, e);
    if (rc != 0) return rc;
    const MbProgram &P = ft.prog[algo];
-   out8[0] = P.nb; out8[1] = P.nops; out8[2] = P.stack_doubles; out8[3] = P.aux_doubles; out8[4] = P.rec_doubles; out8[5] = P.max_depth;
+   out8[0] = P.nb; out8[1] = P.nops; out8[2] = 2 * P.stack2; out8[3] = P.aux_doubles; out8[4] = P.rec_doubles; out8[5] = P.max_depth;
    out8[6] = P.nv; out8[7] = P.nq;
    return 0;
 }

@@ -75,10 +75,11 @@ def test_stack_sizes_follow_depth_not_body_count():
     rng = np.random.default_rng(11)
     h37 = el.Emu(td.humanoid(rng, 2))
     big = el.Emu(td.random_tree(rng, 100, floating=True))
-    for algo, per_level in ((0, 8), (1, 9), (2, 2)):
+    # per level (doubles): RNEA wrench + sin/cos, ABA twist + sin/cos, CRBA sin/cos; leaves keep theirs in registers
+    for algo, per_level in ((0, 8), (1, 8), (2, 2)):
         info = h37.program_info(algo)
         assert info["nops"] == 2 * info["nb"]
-        # SixDoF root slot is larger by 10 (12 transform entries instead of sin/cos) (+5 joint velocities for ABA)
         assert info["stack"] <= per_level * (info["max_depth"] - 1) + 16
         assert big.program_info(algo)["stack"] <= per_level * big.program_info(algo)["max_depth"] + 16
-    assert h37.program_info(1)["rec"] == 9 * 31 + 18
+    assert h37.program_info(0)["stack"] == 6 + 8 * 9  # pelvis wrench, then 3 spine + 6 non-leaf arm levels
+    assert h37.program_info(1)["rec"] == 7 * 32
