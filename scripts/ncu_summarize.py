@@ -17,8 +17,8 @@ from collections import OrderedDict, defaultdict
 
 def short(name):
     name = re.sub(r"\(anonymous namespace\)::|<unnamed>::", "", name)
-    m = re.search(r"([a-z_0-9]+_kernel[a-z_0-9]*<[^>]*>)", name)
-    if m:
+    m = re.search(r"((?:thread|warp|dfma_chain|copy)_kernel[a-z_0-9]*(?:<[^>]*>)?)", name)
+    if m and "at::" not in name:
         return "mb::" + m.group(1).replace("(int)", "").replace("(bool)", "")
     m = re.match(r"void ([A-Za-z_0-9:]+)", name)
     return (m.group(1) if m else name)[:70]

@@ -8,6 +8,40 @@
 #include <string>
 #include <vector>
 
+#include <math.h>
+
+// ---- counting scalar: instantiating the per-state routines with it yields the ALGORITHMIC operation count of the
+// local-transform formulation: add / sub / mul / div = 1 flop each (so a fused multiply-add = 2), a
+// sin/cos pair counted separately.  Defined before the algorithm headers so that their overload sets see it.
+struct Cnt
+{
+   double v;
+   Cnt() : v(0) {}
+   Cnt(double x) : v(x) {}
+   explicit operator double() const { return v; }
+};
+struct CntTotals
+{
+   long add, mul, div, sincos;
+};
+static thread_local CntTotals g_cnt = {0, 0, 0, 0};
+inline Cnt operator+(Cnt a, Cnt b) { g_cnt.add++; return Cnt(a.v + b.v); }
+inline Cnt operator-(Cnt a, Cnt b) { g_cnt.add++; return Cnt(a.v - b.v); }
+inline Cnt operator*(Cnt a, Cnt b) { g_cnt.mul++; return Cnt(a.v * b.v); }
+inline Cnt operator/(Cnt a, Cnt b) { g_cnt.div++; return Cnt(a.v / b.v); }
+inline Cnt operator-(Cnt a) { return Cnt(-a.v); }
+inline Cnt &operator+=(Cnt &a, Cnt b) { a = a + b; return a; }
+inline Cnt &operator-=(Cnt &a, Cnt b) { a = a - b; return a; }
+inline Cnt &operator*=(Cnt &a, Cnt b) { a = a * b; return a; }
+inline bool operator>(Cnt a, Cnt b) { return a.v > b.v; }
+inline bool operator<(Cnt a, Cnt b) { return a.v < b.v; }
+namespace mb
+{
+inline void mb_sincos(Cnt x, Cnt *s, Cnt *c) { g_cnt.sincos++; *s = Cnt(sin(x.v)); *c = Cnt(cos(x.v)); }
+inline Cnt mb_rcp(Cnt x) { g_cnt.div++; return Cnt(1.0 / x.v); }
+inline Cnt mb_reduce_angle(Cnt x) { return x; }
+} // namespace mb
+
 #include "../../mecano_b200/csrc/algorithms.cuh"
 #include "../../mecano_b200/csrc/flatten.h"
 
@@ -99,6 +133,22 @@ extern "C" int emu_run(int algo, int fp32, const mecano_b200_tree_desc *d, const
 {
    return fp32 ? run<float>(algo, d, g, n, ld, q, qd, x, fext, out, flags, err, errlen)
                : run<double>(algo, d, g, n, ld, q, qd, x, fext, out, flags, err, errlen);
+}
+
+// Algorithmic operation counts of one state: out5 = {add, mul, div, sincos, flops = add + mul + div}
+extern "C" int emu_count_flops(int algo, const mecano_b200_tree_desc *d, const double *q, const double *qd, const double *x, long *out5)
+{
+   const double g[3] = {0, 0, -9.81};
+   mb::FlatTree ft;
+   std::string e;
+   int rc = mb::flatten_tree(d, ft, e);
+   if (rc != 0) return rc;
+   std::vector<double> out((size_t)ft.nv * ft.nv + ft.nv, 0.0);
+   g_cnt = {0, 0, 0, 0};
+   rc = run<Cnt>(algo, d, g, 1, 1, q, qd, x, nullptr, out.data(), 0, nullptr, 0);
+   out5[0] = g_cnt.add; out5[1] = g_cnt.mul; out5[2] = g_cnt.div; out5[3] = g_cnt.sincos;
+   out5[4] = g_cnt.add + g_cnt.mul + g_cnt.div;
+   return rc;
 }
 
 extern "C" int emu_program_info(const mecano_b200_tree_desc *d, int algo, int *out8)

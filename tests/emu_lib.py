@@ -84,7 +84,7 @@ def lib():
     global _LIB
     if _LIB is None:
         out = os.path.join(_EMU, "libmecano_emu.so")
-        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh")]
+        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh", "jointmath.cuh", "rnea.cuh", "aba.cuh", "crba.cuh")]
         if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(f) for f in deps):
             build()
         _LIB = ctypes.CDLL(out)
@@ -132,6 +132,14 @@ class Emu:
         n = q.shape[1]
         nv = self.tree.nv
         return self._run(2, q, None, None, None, np.full((nv * nv, n), np.nan)).reshape(nv, nv, n)
+
+    def count_flops(self, algo, q, qd, x):
+        """Algorithmic operation counts of one state (counting-scalar instantiation of the kernel routines)."""
+        out = (ctypes.c_long * 5)()
+        q1, qd1, x1 = (np.ascontiguousarray(a[:, :1]) for a in (q, qd, x))
+        rc = self.lib.emu_count_flops(algo, ctypes.byref(self.desc), _d(q1), _d(qd1), _d(x1), out)
+        assert rc == 0
+        return dict(zip(("add", "mul", "div", "sincos", "flops"), list(out)))
 
     def program_info(self, algo):
         out = (ctypes.c_int * 8)()
