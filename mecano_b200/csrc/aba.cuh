@@ -12,7 +12,7 @@
 
 namespace mb
 {
-#define MB_ABA_REC 7 // doubles per body in the pass-three record
+#define MB_ABA_REC 8 // doubles per body in the pass-three record (four double2: g.a, g.l, k0, pad)
 
 template <class T> struct AbaPipe
 {
@@ -105,10 +105,11 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    g.l = Dinv * U.l;
    const T k0 = Dinv * u;
    // record for pass three: qdd = k0 - g . a'
-   const int r = o.body * MB_ABA_REC;
-   c.rec_st(r + 0, g.a.x); c.rec_st(r + 1, g.a.y); c.rec_st(r + 2, g.a.z);
-   c.rec_st(r + 3, g.l.x); c.rec_st(r + 4, g.l.y); c.rec_st(r + 5, g.l.z);
-   c.rec_st(r + 6, k0);
+   const int r = o.body * (MB_ABA_REC / 2);
+   c.rec_st2(r + 0, g.a.x, g.a.y);
+   c.rec_st2(r + 1, g.a.z, g.l.x);
+   c.rec_st2(r + 2, g.l.y, g.l.z);
+   c.rec_st2(r + 3, k0, (T)0);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       // bias acceleration c = v x (S qd): only x / y components
@@ -178,9 +179,11 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
    const SvT<T> tau6 = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
    // D = I^A, U = I^A: a_i = D^-1 u, and the joint transmits nothing but tau to its parent
    const SvT<T> x = abi_solve(IA, tau6 - pA);
-   const int r = o.body * MB_ABA_REC;
-   c.rec_st(r + 0, x.a.x); c.rec_st(r + 1, x.a.y); c.rec_st(r + 2, x.a.z);
-   c.rec_st(r + 3, x.l.x); c.rec_st(r + 4, x.l.y); c.rec_st(r + 5, x.l.z);
+   const int r = o.body * (MB_ABA_REC / 2);
+   c.rec_st2(r + 0, x.a.x, x.a.y);
+   c.rec_st2(r + 1, x.a.z, x.l.x);
+   c.rec_st2(r + 2, x.l.y, x.l.z);
+   c.rec_st2(r + 3, (T)0, (T)0);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       const XfT<T> X = stk_ld_xf<T>(c, o.slot + 3);
@@ -202,15 +205,16 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
 
 // ---- pass three (:1259-1310): accelerations, root to leaves
 template <class T, class Ctx, bool REV, bool SC>
-MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp, T &ns, T &nc)
+MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp, T &ns, T &nc)
 {
    if (SC)
       mb_sincos(pp.mq, &ns, &nc);
-   const int r = o.body * MB_ABA_REC;
    SvT<T> g;
-   g.a = v3<T>(c.rec_ld(r + 0), c.rec_ld(r + 1), c.rec_ld(r + 2));
-   g.l = v3<T>(c.rec_ld(r + 3), c.rec_ld(r + 4), c.rec_ld(r + 5));
-   const T k0 = c.rec_ld(r + 6);
+   T k0, pad;
+   c.pf3_ld2(st, 1, g.a.x, g.a.y);
+   c.pf3_ld2(st, 2, g.a.z, g.l.x);
+   c.pf3_ld2(st, 3, g.l.y, g.l.z);
+   c.pf3_ld2(st, 4, k0, pad);
    const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), pp.s, pp.c);
    v = motion_to_child(X, v);
    a = motion_to_child(X, a); // a' = X^-1 a_parent + c
@@ -237,12 +241,12 @@ MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, SvT<T> &v, SvT<T> &a, AbaPipe<T
    }
 }
 
-template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, SvT<T> &v, SvT<T> &a)
+template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a)
 {
-   const int r = o.body * MB_ABA_REC;
    SvT<T> x;
-   x.a = v3<T>(c.rec_ld(r + 0), c.rec_ld(r + 1), c.rec_ld(r + 2));
-   x.l = v3<T>(c.rec_ld(r + 3), c.rec_ld(r + 4), c.rec_ld(r + 5));
+   c.pf3_ld2(st, 1, x.a.x, x.a.y);
+   c.pf3_ld2(st, 2, x.a.z, x.l.x);
+   c.pf3_ld2(st, 3, x.l.y, x.l.z);
    const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
    const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
    v = motion_to_child(X, v) + vj;
@@ -343,7 +347,9 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       pp.c = nc;
    }
    c.template pf_wait<0>();
-   // =========================== pass three: DESCEND records only (P.op3), same software pipeline
+   c.pass_fence(); // the records written above are read back below (same thread)
+   // =========================== pass three: DESCEND records only (P.op3).  Same software pipeline, but the ring
+   // (Ctx::pf3_*, overlaid on the now idle stack area) also carries the pass-two record of each body
    SvT<T> a = sv_zero<T>();
    v = sv_zero<T>();
    const int nb = P.nb;
@@ -351,8 +357,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
    for (int k = 0; k < MB_PF_DIST; k++)
    {
       const MbOp2 o = P.op3[k];
-      if (mb2_is_1dof_descend(o))
-         c.pf_issue(k, o.cfg, o.dof, 3);
+      c.pf3_issue(k, o.cfg, o.dof, o.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o) ? 3 : 0);
       c.pf_commit();
    }
    c.template pf_wait<0>();
@@ -362,7 +367,9 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       pp.c = (T)1;
       if (mb2_is_1dof_descend(o0))
       {
-         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+         T q0, qd0;
+         c.pf3_ld2(0, 0, q0, qd0);
+         q0 = mb_reduce_angle(q0);
          if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
          else pp.s = q0;
       }
@@ -373,16 +380,23 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       const MbOp2 o = P.op3[k];
       {
          const MbOp2 od = P.op3[k + MB_PF_DIST];
-         if (mb2_is_1dof_descend(od))
-            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, 3);
+         c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, od.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(od) ? 3 : 0);
          c.pf_commit();
          c.template pf_wait<MB_PF_DIST - 1>();
       }
+      const int st = k & (MB_PF_STAGES - 1);
       pp.qd = pp.mq = (T)0;
       if (MB2_JT(o.code) != MB_SIXDOF)
-         pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      {
+         T qq;
+         c.pf3_ld2(st, 0, qq, pp.qd);
+      }
       if (o.pf & 1u)
-         pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+      {
+         T qdn;
+         c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
+         pp.mq = mb_reduce_angle(pp.mq);
+      }
       if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
       {
          if (o.flags & MB2_ROOT_PARENT)
@@ -400,14 +414,14 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       T ns = pp.mq, nc = (T)1;
       switch (o.code & 0xfu)
       {
-         case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false>(c, o, v, a, pp, ns, nc); break;
-         case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true>(c, o, v, a, pp, ns, nc); break;
-         case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false>(c, o, v, a, pp, ns, nc); break;
-         case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true>(c, o, v, a, pp, ns, nc); break;
+         case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false>(c, o, st, v, a, pp, ns, nc); break;
+         case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true>(c, o, st, v, a, pp, ns, nc); break;
+         case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false>(c, o, st, v, a, pp, ns, nc); break;
+         case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true>(c, o, st, v, a, pp, ns, nc); break;
          default:
             if (o.code & MB2_SC)
                mb_sincos(pp.mq, &ns, &nc);
-            aba_pass3_6dof<T, Ctx>(c, o, v, a);
+            aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
             break;
       }
       pp.s = ns;

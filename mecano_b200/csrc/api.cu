@@ -21,6 +21,7 @@ struct mecano_b200_handle
    mb::FlatTree tree;
    double *d_consts = nullptr;
    uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
+   double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[3];
    int variant = MECANO_B200_VARIANT_AUTO;
@@ -71,13 +72,19 @@ int check_batch(mecano_b200_handle *h, int64_t n, int64_t ld)
 }
 
 int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
-        double *out, uint32_t flags, cudaStream_t stream)
+        double *out, uint32_t flags, cudaStream_t stream, int ws_slot = 0)
 {
+   if (n > (int64_t)1 << 28 || ld > (int64_t)1 << 28)
+      return fail(h, MECANO_B200_ERR_TOO_LARGE, "more than 2^28 states (or ld > 2^28) in one call: split the batch");
+   if (algo == MB_ABA && !h->d_ws[ws_slot] && h->plan[MB_ABA].ws_doubles)
+      MB_CUDA(h, cudaMalloc(&h->d_ws[ws_slot], h->plan[MB_ABA].ws_doubles * sizeof(double)));
    if (h->variant == MECANO_B200_VARIANT_WARP)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the warp-per-state variant is not built in this version");
    mb::KernelArgs a;
    a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
    a.consts = h->d_consts;
+   a.ws = h->d_ws[ws_slot];
+   a.ws_ld = 0;
    a.zero_entries = h->d_zero;
    a.n_zero = (int32_t)h->tree.zero_entries.size();
    a.n = n; a.ld = ld;
@@ -154,7 +161,7 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
       }
       else
          dout = dq + nq * chunk;
-      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st);
+      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, 1 + slot);
       if (rc) return rc;
       if (state_major)
          MB_CUDA(h, cudaMemcpyAsync(out + (size_t)s0 * nv * nv, dout, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -250,6 +257,8 @@ void mecano_b200_destroy(mecano_b200_handle *h)
    }
    if (h->d_consts) cudaFree(h->d_consts);
    if (h->d_zero) cudaFree(h->d_zero);
+   for (int i = 0; i < 3; i++)
+      if (h->d_ws[i]) cudaFree(h->d_ws[i]);
    delete h;
 }
 

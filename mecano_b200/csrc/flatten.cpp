@@ -134,6 +134,8 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       if (nchild[i] > 0 || B.jtype == MB_SIXDOF)
          P.stack2 = std::max(P.stack2, s + slot2_size(algo, B.jtype, B.parent < 0));
    }
+   if (algo == MB_ABA)
+      P.stack2 = std::max(P.stack2, 20); // pass three overlays a 4-stage x 5-row ring of double2 on the stack area
    std::memset(P.op2, 0, sizeof P.op2);
    for (int k = 0; k < P.nops; k++)
    {
@@ -451,7 +453,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          rec += rec_size(B.jtype);
       }
       (void)rec;
-      P.rec_doubles = algo == MB_ABA ? 7 * nb : 0; // MB_ABA_REC per body (aba.cuh)
+      P.rec_doubles = algo == MB_ABA ? 8 * nb : 0; // MB_ABA_REC per body (aba.cuh)
 
       // ops: iterative DFS emitting DESCEND on entry and ASCEND on exit
       int nops = 0;

@@ -36,7 +36,7 @@ template <int BLOCK> struct GpuCtx2
    char *ob;
    unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
    int stk0;     // index (double2 units) of stack slot 0 of this thread
-   double *aux, *rec; // local memory
+   double *aux; // local memory
 
    __device__ __forceinline__ double ld_q(int r) const { return __ldg((const double *)(qb + (unsigned long long)(unsigned)r * ld8)); }
    __device__ __forceinline__ double ld_qd(int r) const { return __ldg((const double *)(qdb + (unsigned long long)(unsigned)r * ld8)); }
@@ -52,8 +52,32 @@ template <int BLOCK> struct GpuCtx2
    __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b) { reinterpret_cast<double2 *>(mb_smem)[stk0 + (slot2 + j) * BLOCK] = make_double2(a, b); }
    __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
    __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
-   __device__ __forceinline__ double rec_ld(int i) const { return rec[i]; }
-   __device__ __forceinline__ void rec_st(int i, double v) { rec[i] = v; }
+   // ABA pass-two records: global workspace of double2, one column per resident thread (coalesced 16-byte accesses),
+   // read back in pass three through the ring below with cp.async.cg (L2, the coherence point of the earlier stores)
+   double2 *wsb;       // workspace + column of this thread
+   long long ws_ld;
+   int ring3_0;        // index (double2) of this thread's element of stage 0, row 0 of the pass-three ring
+   __device__ __forceinline__ void rec_st2(int i2, double a, double b) { wsb[i2 * ws_ld] = make_double2(a, b); }
+   // pass-three ring: [stage][(q, qd) | rec0 .. rec3][BLOCK] double2, overlaid on the (then idle) stack area
+   __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
+   {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double2 *>(mb_smem) + ring3_0 + stage * 5 * BLOCK);
+      if (mask & 1)
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
+      if (mask & 2)
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+      const double2 *src = wsb + rec2 * ws_ld;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(src + j * ws_ld) : "memory");
+   }
+   __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const
+   {
+      const double2 t = reinterpret_cast<const double2 *>(mb_smem)[ring3_0 + (stage * 5 + row) * BLOCK];
+      a = t.x;
+      b = t.y;
+   }
+   __device__ __forceinline__ void pass_fence() const { __threadfence(); }
    __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
    // mass matrix: entry e = row * nv + col lives at mbase + e * mstride (entry-major: mstride = ld8; state-major: 8)
    char *mbase;
@@ -98,30 +122,37 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    for (int i = threadIdx.x; i < ncst; i += BLOCK)
       mb_smem[i] = a.consts[i];
    __syncthreads();
-   const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
-   if (s >= a.n)
-      return;
    double aux[AUXN > 0 ? AUXN : 1];
-   double rec[RECN > 0 ? RECN : 1];
    GpuCtx2<BLOCK> c2;
-   c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
-   c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
    c2.ld8 = (unsigned)(a.ld * 8);
    c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
+   c2.ring3_0 = c2.stk0;
    c2.ring0 = ((ncst + 1) & ~1) + 2 * P.stack2 * BLOCK + threadIdx.x;
    c2.aux = aux;
-   c2.rec = rec;
    c2.nv = a.nv;
-   c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
    c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
    c2.zlist = (const uint4 *)a.zero_entries;
    c2.nz8 = a.n_zero >> 3;
-   if constexpr (ALGO == MB_RNEA)
-      rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
-   else if constexpr (ALGO == MB_ABA)
-      aba_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav);
-   else
-      crba_state<double, GpuCtx2<BLOCK>>(P, c2);
+   c2.wsb = reinterpret_cast<double2 *>(a.ws) + ((long long)blockIdx.x * BLOCK + threadIdx.x);
+   c2.ws_ld = a.ws_ld;
+   // persistent grid: each block walks over tiles of BLOCK states.  The per-state areas (stack, rings) are private to a
+   // thread and the constant records are read-only, so the threads of a block never synchronise again.
+   const long long ntiles = (a.n + BLOCK - 1) / BLOCK;
+   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+   {
+      const long long s = tile * BLOCK + threadIdx.x;
+      if (s >= a.n)
+         break;
+      c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
+      c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
+      c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
+      if constexpr (ALGO == MB_RNEA)
+         rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+      else if constexpr (ALGO == MB_ABA)
+         aba_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav);
+      else
+         crba_state<double, GpuCtx2<BLOCK>>(P, c2);
+   }
 }
 
 // compiled work-area classes (local memory per thread): {aux, rec}
@@ -226,6 +257,10 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    cudaFuncAttributes attr;
    e = cudaFuncGetAttributes(&attr, (const void *)pick(algo, fext, false, plan.size_class));
    if (e != cudaSuccess) return e;
+   int sms = 0;
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   plan.grid = sms * plan.blocks_per_sm;
+   plan.ws_doubles = algo == MB_ABA ? (size_t)plan.grid * plan.block * (size_t)std::max(P.rec_doubles, 1) : 0;
    plan.regs = attr.numRegs;
    plan.local_bytes = (int)attr.localSizeBytes;
    plan.static_smem = (int)attr.sharedSizeBytes;
@@ -239,8 +274,13 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
       return cudaSuccess;
    const bool state_major = algo == MB_CRBA && (a.flags & 1u);
    KernelFn fn = pick(algo, a.fext != nullptr, state_major, plan.size_class);
-   const long long nblocks = (a.n + plan.block - 1) / plan.block;
-   fn<<<(unsigned)nblocks, plan.block, plan.smem, stream>>>(P, a);
+   const long long ntiles = (a.n + plan.block - 1) / plan.block;
+   // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread);
+   // RNEA and CRBA measured faster with one block per tile (hardware block scheduling keeps the SMs evenly loaded)
+   const unsigned grid = algo == MB_ABA ? (unsigned)std::min<long long>(ntiles, plan.grid) : (unsigned)ntiles;
+   KernelArgs b = a;
+   b.ws_ld = (long long)plan.grid * plan.block;
+   fn<<<grid, plan.block, plan.smem, stream>>>(P, b);
    return cudaGetLastError();
 }
 

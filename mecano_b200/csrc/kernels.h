@@ -12,6 +12,8 @@ struct KernelArgs
    const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
    double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
    const double *consts;            // device copy of the per-body constant records
+   double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid
+   long long ws_ld;
    const uint16_t *zero_entries;    // CRBA: structurally zero mass-matrix entries (multiple of 8, 16-byte aligned)
    int32_t n_zero;
    long long n, ld;
@@ -29,6 +31,8 @@ struct LaunchPlan
    int regs = 0;
    int local_bytes = 0;
    int static_smem = 0;
+   int grid = 0;         // persistent grid: resident blocks on the whole device
+   size_t ws_doubles = 0; // ABA workspace size for that grid
 };
 
 // Picks the block size / size class for one algorithm and opts the kernel into large shared memory.

@@ -82,7 +82,18 @@ template <class T> struct CpuCtx
    T aux_ld(int i) const { return aux[i]; }
    void aux_st(int i, T v) { aux[i] = v; }
    T rec_ld(int i) const { return rec[i]; }
-   void rec_st(int i, T v) { rec[i] = v; }
+   void rec_st2(int i2, T a, T b) { rec[2 * i2] = a; rec[2 * i2 + 1] = b; }
+   T ring3[4][10];
+   void pf3_issue(int stage, int cfg, int dof, int rec2, int mask)
+   {
+      const T nan = (T)(0.0 / 0.0);
+      ring3[stage][0] = (mask & 1) ? ld_q(cfg) : nan;
+      ring3[stage][1] = (mask & 2) ? ld_qd(dof) : nan;
+      for (int j = 0; j < 8; j++)
+         ring3[stage][2 + j] = rec[2 * rec2 + j];
+   }
+   void pf3_ld2(int stage, int row, T &a, T &b) const { a = ring3[stage][2 * row]; b = ring3[stage][2 * row + 1]; }
+   void pass_fence() const {}
    const T *cst(int b) const { return consts + (size_t)b * MB_CONST_STRIDE; }
 };
 
@@ -102,7 +113,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
    std::vector<T> consts(ft.consts.begin(), ft.consts.end());
    // poison the work areas so that a read-before-write shows up as NaN
    const T nan = (T)(0.0 / 0.0);
-   std::vector<T> stk(std::max(P.stack_doubles, 2 * P.stack2) + 2, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 1, nan);
+   std::vector<T> stk(std::max(P.stack_doubles, 2 * P.stack2) + 2, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 64, nan);
    const T grav[3] = {(T)g[0], (T)g[1], (T)g[2]};
    for (long s = 0; s < n; s++)
    {
