@@ -269,7 +269,8 @@ def main():
         gbs = info["bytes_per_state"] * n / (ms * 1e-3) / 1e9
         entry = {"ms": ms, "states_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_state": info["bytes_per_state"], "achieved_gbs": gbs,
                  "hbm_frac": gbs / hbm_peak, "block_threads": info["block_threads"], "regs": info["regs_per_thread"],
-                 "smem_bytes": info["dynamic_smem_bytes"], "blocks_per_sm": info["blocks_per_sm"]}
+                 "smem_bytes": info["dynamic_smem_bytes"], "blocks_per_sm": info["blocks_per_sm"],
+                 "tmem_stack_slots": info["tmem_stack_slots"], "specialized": info["specialized"]}
         fl = flops.get(key, {}).get(name)
         if fl and fp64_peak:
             tf = fl * n / (ms * 1e-3) / 1e12

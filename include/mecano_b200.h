@@ -53,6 +53,7 @@ extern "C" {
 #define MECANO_B200_ERR_SHAPE (-3)
 #define MECANO_B200_ERR_NO_DEVICE (-4)
 #define MECANO_B200_ERR_TOO_LARGE (-5)
+#define MECANO_B200_ERR_JIT (-6) /* tree-specialised kernel could not be generated / compiled / loaded */
 
 /* flags for mecano_b200_rnea (mirror InverseDynamicsCalculator.java:291-306) */
 #define MECANO_B200_RNEA_NO_CORIOLIS 0x1u      /* setConsiderCoriolisAndCentrifugalForces(false) */
@@ -116,8 +117,12 @@ typedef struct mecano_b200_kernel_info
    int32_t sm_count;
    int32_t stack_doubles;      /* per-state stack slots held in shared memory */
    int32_t max_depth;
-   int32_t reserved;
+   int32_t specialized;        /* 0: generic kernel (traversal program interpreted); 1: tree-specialised kernel compiled by
+                                  mecano_b200_specialize(); 2: the same, loaded from the cubin cache */
    double bytes_per_state;     /* algorithmic HBM bytes per state */
+   int32_t tmem_stack_slots;   /* per-state stack slots (16 bytes each) held in tensor memory instead of shared memory */
+   int32_t reserved;
+   double jit_seconds;         /* time mecano_b200_specialize() spent on this kernel (generate + NVRTC + load) */
 } mecano_b200_kernel_info;
 
 int mecano_b200_version(void);
@@ -130,6 +135,20 @@ const char *mecano_b200_last_error(const mecano_b200_handle *h); /* h may be NUL
 
 int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double gz);
 int mecano_b200_set_variant(mecano_b200_handle *h, int variant);
+
+/*
+ * Compile kernels specialised for this tree (bit mask of 1 << MECANO_B200_ALGO_*).  A Mecano calculator mirrors the body
+ * tree into recursion-step objects in its constructor (InverseDynamicsCalculator.java:253-282); this is the same step taken
+ * further: the traversal is unrolled into straight-line CUDA C++ with the tree's constants as literals and compiled with
+ * NVRTC for sm_100a (seconds; cubins are cached under $MECANO_B200_CACHE, default ~/.cache/mecano_b200).  Optional: without
+ * it every call runs the generic kernels, which interpret the same traversal program.  Calls with external wrenches or
+ * non-default flags always use the generic kernels.  Unrolled code only pays while it fits the instruction caches: algorithms
+ * whose estimated code size is too large (RNEA beyond ~20 bodies, ABA beyond ~9) are skipped and keep the generic kernel
+ * (mecano_b200_kernel_info.specialized tells which one runs); CRBA is never specialised (HBM-bound).  Results of the two paths
+ * agree to round-off (same routines, different instruction scheduling).
+ */
+#define MECANO_B200_SPECIALIZE_FORCE 0x100u /* also unroll trees whose code exceeds the instruction caches (slower; for measurements) */
+int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask);
 int mecano_b200_n_dofs(const mecano_b200_handle *h);
 int mecano_b200_n_cfg(const mecano_b200_handle *h);
 int mecano_b200_n_bodies(const mecano_b200_handle *h);
@@ -166,6 +185,18 @@ int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_state
 /* Roofline denominators measured on the handle-less device: FP64 FMA chain and a read+write copy. */
 int mecano_b200_measure_fp64_peak(int device, double *tflops);
 int mecano_b200_measure_hbm_peak(int device, double *gbytes_per_s);
+
+/*
+ * The CUDA C++ text of the tree-specialised kernel that mecano_b200_create() compiles for this tree (debugging,
+ * build-time checks; works without a GPU).  tmem_slots = stack slots held in tensor memory (0 = shared memory only).
+ * Writes at most `capacity` bytes (NUL-terminated) and reports the full size in *needed.
+ */
+int mecano_b200_generate_source(const mecano_b200_tree_desc *desc, int algo, int block_threads, int tmem_slots, char *buf, int64_t capacity,
+                                int64_t *needed);
+
+/* Generates the specialised source for (desc, algo) and compiles it with NVRTC to an sm_100a cubin without loading it:
+ * the "does the run-time compiled path build" check; needs no GPU. */
+int mecano_b200_jit_check(const mecano_b200_tree_desc *desc, int algo, int block_threads, int tmem_slots, int64_t *cubin_bytes);
 
 /* Pinned host memory helpers for bindings that cannot allocate it themselves. */
 int mecano_b200_host_alloc(void **ptr, int64_t bytes);

@@ -44,8 +44,9 @@ class KernelInfo(ctypes.Structure):
         ("variant", ctypes.c_int32), ("block_threads", ctypes.c_int32), ("states_per_block", ctypes.c_int32),
         ("regs_per_thread", ctypes.c_int32), ("static_smem_bytes", ctypes.c_int32), ("dynamic_smem_bytes", ctypes.c_int32),
         ("local_bytes_per_thread", ctypes.c_int32), ("blocks_per_sm", ctypes.c_int32), ("sm_count", ctypes.c_int32),
-        ("stack_doubles", ctypes.c_int32), ("max_depth", ctypes.c_int32), ("reserved", ctypes.c_int32),
-        ("bytes_per_state", ctypes.c_double),
+        ("stack_doubles", ctypes.c_int32), ("max_depth", ctypes.c_int32), ("specialized", ctypes.c_int32),
+        ("bytes_per_state", ctypes.c_double), ("tmem_stack_slots", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("jit_seconds", ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -57,7 +58,7 @@ EXPORTS = [
     "mecano_b200_set_gravity", "mecano_b200_set_variant", "mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies",
     "mecano_b200_rnea", "mecano_b200_aba", "mecano_b200_crba", "mecano_b200_rnea_host", "mecano_b200_aba_host",
     "mecano_b200_crba_host", "mecano_b200_kernel_info_get", "mecano_b200_measure_fp64_peak", "mecano_b200_measure_hbm_peak",
-    "mecano_b200_host_alloc", "mecano_b200_host_free",
+    "mecano_b200_host_alloc", "mecano_b200_host_free", "mecano_b200_generate_source", "mecano_b200_jit_check", "mecano_b200_specialize",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -67,6 +68,8 @@ lib.mecano_b200_last_error.argtypes = [c_vp]
 lib.mecano_b200_last_error.restype = ctypes.c_char_p
 lib.mecano_b200_set_gravity.argtypes = [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
 lib.mecano_b200_set_variant.argtypes = [c_vp, ctypes.c_int]
+lib.mecano_b200_specialize.argtypes = [c_vp, c_u32]
+lib.mecano_b200_jit_check.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_i64)]
 for _f in ("mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies"):
     getattr(lib, _f).argtypes = [c_vp]
 lib.mecano_b200_rnea.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp]
@@ -80,6 +83,7 @@ lib.mecano_b200_measure_fp64_peak.argtypes = [ctypes.c_int, c_dp]
 lib.mecano_b200_measure_hbm_peak.argtypes = [ctypes.c_int, c_dp]
 lib.mecano_b200_host_alloc.argtypes = [ctypes.POINTER(c_vp), c_i64]
 lib.mecano_b200_host_free.argtypes = [c_vp]
+lib.mecano_b200_generate_source.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_i64, ctypes.POINTER(c_i64)]
 
 
 class MecanoB200Error(RuntimeError):

@@ -74,6 +74,13 @@ class _BatchedCalculator:
     def kernelInfo(self, n_states=0):
         return self._engine.kernel_info(self._ALGO, n_states)
 
+    def specialize(self, force=False):
+        """Optional second half of the constructor: compile a kernel unrolled for this tree (mecano_b200_specialize).
+        Trees whose unrolled code would overflow the instruction caches keep the generic kernel; kernelInfo()["specialized"]
+        tells which one runs.  Returns self."""
+        self._engine.specialize([self._ALGO], force=force)
+        return self
+
 
 class InverseDynamicsCalculator(_BatchedCalculator):
     _ALGO = _capi.ALGO_RNEA

@@ -265,167 +265,306 @@ template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, i
 // which scalars an op needs from the prefetch ring: DESCEND q + qd, ASCEND qd + tau
 MB_HD int aba_pf_mask(const MbOp2 &o) { return MB2_JT(o.code) == MB_SIXDOF ? 0 : ((o.code & MB2_ASCEND) ? 6 : 3); }
 
-template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P, Ctx &c, const T *grav)
+// ---- one op of passes one + two (the body of the interpreter loop; see rnea_op for the role of the literal arguments)
+template <class T, class Ctx, bool FEXT>
+MB_HD void aba_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int ext, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
 {
-   SvT<T> v = sv_zero<T>(), pacc = sv_zero<T>();
-   AbiT<T> acc = AbiT<T>();
-   AbaPipe<T> pp;
+   c.op_sync(k);
+   c.stk_fence();
+   {
+      const int m = aba_pf_mask(od);
+      if (m)
+         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, m);
+      c.pf_commit();
+      c.template pf_wait<MB_PF_DIST - 1>();
+   }
+   pp.qd = pp.x = pp.mq = (T)0;
+   if (MB2_JT(o.code) != MB_SIXDOF)
+   {
+      pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      if (o.code & MB2_ASCEND)
+         pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+   }
+   if (o.pf & 1u)
+      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+   // twist of the parent: carried along a chain, zero for the root body, otherwise on the parent's stack slot
+   if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+   {
+      if (o.flags & MB2_ROOT_PARENT)
+         v = sv_zero<T>();
+      else
+         v = stk_ld_sv<T>(c, o.pslot);
+   }
+   T ns = pp.mq, nc = (T)1;
+   switch (o.code & 0xfu)
+   {
+      case 0 | (MB_REVOLUTE << 1): aba_descend_1dof<T, Ctx, true, false>(c, o, v, pp, ns, nc); break;
+      case 0 | (MB_REVOLUTE << 1) | MB2_SC: aba_descend_1dof<T, Ctx, true, true>(c, o, v, pp, ns, nc); break;
+      case 1 | (MB_REVOLUTE << 1): aba_ascend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+      case 1 | (MB_REVOLUTE << 1) | MB2_SC: aba_ascend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+      case 0 | (MB_PRISMATIC << 1): aba_descend_1dof<T, Ctx, false, false>(c, o, v, pp, ns, nc); break;
+      case 0 | (MB_PRISMATIC << 1) | MB2_SC: aba_descend_1dof<T, Ctx, false, true>(c, o, v, pp, ns, nc); break;
+      case 1 | (MB_PRISMATIC << 1): aba_ascend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+      case 1 | (MB_PRISMATIC << 1) | MB2_SC: aba_ascend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
+      default:
+         if (o.code & MB2_SC)
+            mb_sincos(pp.mq, &ns, &nc);
+         if (o.code & MB2_ASCEND)
+            aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
+         else
+            aba_descend_6dof<T, Ctx>(c, o, v);
+         break;
+   }
+   pp.s = ns;
+   pp.c = nc;
+}
+
+template <class T, class Ctx>
+MB_HD void aba_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
+{
+   static_assert(MB_PF_DIST == 3, "prologue written for a prefetch distance of 3");
+   v = sv_zero<T>(); pacc = sv_zero<T>();
+   acc = AbiT<T>();
    pp.s = pp.qd = pp.x = pp.mq = pp.ls = (T)0;
    pp.c = pp.lc = (T)1;
-   const int nops = P.nops;
-   // =========================== passes one and two, interleaved
-#pragma unroll
-   for (int k = 0; k < MB_PF_DIST; k++)
-   {
-      const MbOp2 o = P.op2[k];
-      const int m = aba_pf_mask(o);
-      if (m)
-         c.pf_issue(k, o.cfg, o.dof, m);
-      c.pf_commit();
-   }
+   if (aba_pf_mask(o0)) c.pf_issue(0, o0.cfg, o0.dof, aba_pf_mask(o0));
+   c.pf_commit();
+   if (aba_pf_mask(o1)) c.pf_issue(1, o1.cfg, o1.dof, aba_pf_mask(o1));
+   c.pf_commit();
+   if (aba_pf_mask(o2)) c.pf_issue(2, o2.cfg, o2.dof, aba_pf_mask(o2));
+   c.pf_commit();
    c.template pf_wait<0>();
+   if (mb2_is_1dof_descend(o0))
    {
-      const MbOp2 o0 = P.op2[0];
-      if (mb2_is_1dof_descend(o0))
-      {
-         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
-         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
-         else pp.s = q0;
-      }
+      const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+      else pp.s = q0;
    }
-#pragma unroll 1
-   for (int k = 0; k < nops; k++)
-   {
-      const MbOp2 o = P.op2[k];
-      {
-         const MbOp2 od = P.op2[k + MB_PF_DIST];
-         const int m = aba_pf_mask(od);
-         if (m)
-            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, m);
-         c.pf_commit();
-         c.template pf_wait<MB_PF_DIST - 1>();
-      }
-      pp.qd = pp.x = pp.mq = (T)0;
-      if (MB2_JT(o.code) != MB_SIXDOF)
-      {
-         pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
-         if (o.code & MB2_ASCEND)
-            pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
-      }
-      if (o.pf & 1u)
-         pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
-      // twist of the parent: carried along a chain, zero for the root body, otherwise on the parent's stack slot
-      if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
-      {
-         if (o.flags & MB2_ROOT_PARENT)
-            v = sv_zero<T>();
-         else
-            v = stk_ld_sv<T>(c, o.pslot);
-      }
-      const int ext = FEXT ? P.body[o.body].ext_index : 0;
-      T ns = pp.mq, nc = (T)1;
-      switch (o.code & 0xfu)
-      {
-         case 0 | (MB_REVOLUTE << 1): aba_descend_1dof<T, Ctx, true, false>(c, o, v, pp, ns, nc); break;
-         case 0 | (MB_REVOLUTE << 1) | MB2_SC: aba_descend_1dof<T, Ctx, true, true>(c, o, v, pp, ns, nc); break;
-         case 1 | (MB_REVOLUTE << 1): aba_ascend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
-         case 1 | (MB_REVOLUTE << 1) | MB2_SC: aba_ascend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
-         case 0 | (MB_PRISMATIC << 1): aba_descend_1dof<T, Ctx, false, false>(c, o, v, pp, ns, nc); break;
-         case 0 | (MB_PRISMATIC << 1) | MB2_SC: aba_descend_1dof<T, Ctx, false, true>(c, o, v, pp, ns, nc); break;
-         case 1 | (MB_PRISMATIC << 1): aba_ascend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
-         case 1 | (MB_PRISMATIC << 1) | MB2_SC: aba_ascend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, acc, pacc, pp, ns, nc); break;
-         default:
-            if (o.code & MB2_SC)
-               mb_sincos(pp.mq, &ns, &nc);
-            if (o.code & MB2_ASCEND)
-               aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
-            else
-               aba_descend_6dof<T, Ctx>(c, o, v);
-            break;
-      }
-      pp.s = ns;
-      pp.c = nc;
-   }
+}
+
+// ---- pass three: DESCEND records only.  Same software pipeline, but the ring (Ctx::pf3_*, overlaid on the now idle
+// stack area) also carries the pass-two record of each body
+template <class T, class Ctx>
+MB_HD void aba_pass3_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+{
    c.template pf_wait<0>();
-   c.pass_fence(); // the records written above are read back below (same thread)
-   // =========================== pass three: DESCEND records only (P.op3).  Same software pipeline, but the ring
-   // (Ctx::pf3_*, overlaid on the now idle stack area) also carries the pass-two record of each body
-   SvT<T> a = sv_zero<T>();
+   c.pass_fence(); // the records written in pass two are read back below (same thread)
+   a = sv_zero<T>();
    v = sv_zero<T>();
-   const int nb = P.nb;
-#pragma unroll
-   for (int k = 0; k < MB_PF_DIST; k++)
-   {
-      const MbOp2 o = P.op3[k];
-      c.pf3_issue(k, o.cfg, o.dof, o.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o) ? 3 : 0);
-      c.pf_commit();
-   }
+   c.pf3_issue(0, o0.cfg, o0.dof, o0.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o0) ? 3 : 0);
+   c.pf_commit();
+   c.pf3_issue(1, o1.cfg, o1.dof, o1.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o1) ? 3 : 0);
+   c.pf_commit();
+   c.pf3_issue(2, o2.cfg, o2.dof, o2.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o2) ? 3 : 0);
+   c.pf_commit();
    c.template pf_wait<0>();
+   pp.s = (T)0;
+   pp.c = (T)1;
+   if (mb2_is_1dof_descend(o0))
    {
-      const MbOp2 o0 = P.op3[0];
-      pp.s = (T)0;
-      pp.c = (T)1;
-      if (mb2_is_1dof_descend(o0))
+      T q0, qd0;
+      c.pf3_ld2(0, 0, q0, qd0);
+      q0 = mb_reduce_angle(q0);
+      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+      else pp.s = q0;
+   }
+}
+
+template <class T, class Ctx>
+MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+{
+   c.op_sync(k);
+   c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, od.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(od) ? 3 : 0);
+   c.pf_commit();
+   c.template pf_wait<MB_PF_DIST - 1>();
+   const int st = k & (MB_PF_STAGES - 1);
+   pp.qd = pp.mq = (T)0;
+   if (MB2_JT(o.code) != MB_SIXDOF)
+   {
+      T qq;
+      c.pf3_ld2(st, 0, qq, pp.qd);
+   }
+   if (o.pf & 1u)
+   {
+      T qdn;
+      c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
+      pp.mq = mb_reduce_angle(pp.mq);
+   }
+   if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
+   {
+      if (o.flags & MB2_ROOT_PARENT)
       {
-         T q0, qd0;
-         c.pf3_ld2(0, 0, q0, qd0);
-         q0 = mb_reduce_angle(q0);
-         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
-         else pp.s = q0;
+         v = sv_zero<T>();
+         a = sv_zero<T>();
+         a.l = v3<T>(-grav[0], -grav[1], -grav[2]); // root acceleration = -gravity (ForwardDynamicsCalculator.java:313-319)
+      }
+      else
+      {
+         v = aux_ld_sv<T>(c, o.paux);
+         a = aux_ld_sv<T>(c, o.paux + 6);
       }
    }
-#pragma unroll 1
-   for (int k = 0; k < nb; k++)
+   T ns = pp.mq, nc = (T)1;
+   switch (o.code & 0xfu)
    {
-      const MbOp2 o = P.op3[k];
+      case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true>(c, o, st, v, a, pp, ns, nc); break;
+      default:
+         if (o.code & MB2_SC)
+            mb_sincos(pp.mq, &ns, &nc);
+         aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
+         break;
+   }
+   pp.s = ns;
+   pp.c = nc;
+}
+
+// ---- run steps: as aba_op / aba_pass3_op with the kind (ASCEND / joint type / SC) fixed at compile time (see rnea.cuh)
+template <class T, class Ctx, bool FEXT, int KIND>
+MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
+{
+   constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0;
+   constexpr int JT = (KIND >> 1) & 3;
+   const MbOp2 o = P.op2[k];
+   c.stk_fence();
+   {
+      const MbOp2 od = P.op2[k + MB_PF_DIST];
+      const int m = aba_pf_mask(od);
+      if (m)
+         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, m);
+      c.pf_commit();
+      c.template pf_wait<MB_PF_DIST - 1>();
+   }
+   pp.qd = pp.x = pp.mq = (T)0;
+   if (JT != MB_SIXDOF)
+   {
+      pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      if (ASC)
+         pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+   }
+   if (o.pf & 1u)
+      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+   if (!ASC && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+   {
+      if (o.flags & MB2_ROOT_PARENT)
+         v = sv_zero<T>();
+      else
+         v = stk_ld_sv<T>(c, o.pslot);
+   }
+   const int ext = FEXT ? P.body[o.body].ext_index : 0;
+   T ns = pp.mq, nc = (T)1;
+   if (JT == MB_SIXDOF)
+   {
+      if (SC) mb_sincos(pp.mq, &ns, &nc);
+      if (ASC) aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
+      else aba_descend_6dof<T, Ctx>(c, o, v);
+   }
+   else if (ASC)
+      aba_ascend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, SC>(c, o, ext, v, acc, pacc, pp, ns, nc);
+   else
+      aba_descend_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, v, pp, ns, nc);
+   pp.s = ns;
+   pp.c = nc;
+}
+
+template <class T, class Ctx, int KIND>
+MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+{
+   constexpr bool SC = (KIND & MB2_SC) != 0;
+   constexpr int JT = (KIND >> 1) & 3;
+   const MbOp2 o = P.op3[k];
+   {
+      const MbOp2 od = P.op3[k + MB_PF_DIST];
+      c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, od.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(od) ? 3 : 0);
+      c.pf_commit();
+      c.template pf_wait<MB_PF_DIST - 1>();
+   }
+   const int st = k & (MB_PF_STAGES - 1);
+   pp.qd = pp.mq = (T)0;
+   if (JT != MB_SIXDOF)
+   {
+      T qq;
+      c.pf3_ld2(st, 0, qq, pp.qd);
+   }
+   if (o.pf & 1u)
+   {
+      T qdn;
+      c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
+      pp.mq = mb_reduce_angle(pp.mq);
+   }
+   if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
+   {
+      if (o.flags & MB2_ROOT_PARENT)
       {
-         const MbOp2 od = P.op3[k + MB_PF_DIST];
-         c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, od.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(od) ? 3 : 0);
-         c.pf_commit();
-         c.template pf_wait<MB_PF_DIST - 1>();
+         v = sv_zero<T>();
+         a = sv_zero<T>();
+         a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
       }
-      const int st = k & (MB_PF_STAGES - 1);
-      pp.qd = pp.mq = (T)0;
-      if (MB2_JT(o.code) != MB_SIXDOF)
+      else
       {
-         T qq;
-         c.pf3_ld2(st, 0, qq, pp.qd);
+         v = aux_ld_sv<T>(c, o.paux);
+         a = aux_ld_sv<T>(c, o.paux + 6);
       }
-      if (o.pf & 1u)
+   }
+   T ns = pp.mq, nc = (T)1;
+   if (JT == MB_SIXDOF)
+   {
+      if (SC) mb_sincos(pp.mq, &ns, &nc);
+      aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
+   }
+   else
+      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, st, v, a, pp, ns, nc);
+   pp.s = ns;
+   pp.c = nc;
+}
+
+template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P, Ctx &c, const T *grav)
+{
+   SvT<T> v, pacc, a;
+   AbiT<T> acc;
+   AbaPipe<T> pp;
+   // =========================== passes one and two, interleaved; one tight loop per run of same-kind ops
+   aba_begin<T, Ctx>(c, P.op2[0], P.op2[1], P.op2[2], v, acc, pacc, pp);
+   const int nruns = P.nruns;
+#pragma unroll 1
+   for (int r = 0; r < nruns; r++)
+   {
+      const MbRun R = P.run[r];
+      int k = R.k0;
+      const int k1 = k + R.n;
+#define MB_RUN_CASE(KIND)                                                                          \
+   case KIND:                                                                                       \
+      _Pragma("unroll 1") do { aba_run_step<T, Ctx, FEXT, KIND>(P, c, k, v, acc, pacc, pp); } while (++k < k1); \
+      break;
+      switch (R.kind)
       {
-         T qdn;
-         c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
-         pp.mq = mb_reduce_angle(pp.mq);
+         MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
+         MB_RUN_CASE(8) MB_RUN_CASE(9) MB_RUN_CASE(10) MB_RUN_CASE(11) MB_RUN_CASE(12) MB_RUN_CASE(13)
+         default: break;
       }
-      if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
+#undef MB_RUN_CASE
+   }
+   // =========================== pass three
+   aba_pass3_begin<T, Ctx>(c, P.op3[0], P.op3[1], P.op3[2], v, a, pp);
+   const int nruns3 = P.nruns3;
+#pragma unroll 1
+   for (int r = 0; r < nruns3; r++)
+   {
+      const MbRun R = P.run3[r];
+      int k = R.k0;
+      const int k1 = k + R.n;
+#define MB_RUN_CASE(KIND)                                                                       \
+   case KIND:                                                                                    \
+      _Pragma("unroll 1") do { aba_pass3_run_step<T, Ctx, KIND>(P, c, k, grav, v, a, pp); } while (++k < k1); \
+      break;
+      switch (R.kind)
       {
-         if (o.flags & MB2_ROOT_PARENT)
-         {
-            v = sv_zero<T>();
-            a = sv_zero<T>();
-            a.l = v3<T>(-grav[0], -grav[1], -grav[2]); // root acceleration = -gravity (ForwardDynamicsCalculator.java:313-319)
-         }
-         else
-         {
-            v = aux_ld_sv<T>(c, o.paux);
-            a = aux_ld_sv<T>(c, o.paux + 6);
-         }
+         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4) MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
+         default: break;
       }
-      T ns = pp.mq, nc = (T)1;
-      switch (o.code & 0xfu)
-      {
-         case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false>(c, o, st, v, a, pp, ns, nc); break;
-         case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true>(c, o, st, v, a, pp, ns, nc); break;
-         case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false>(c, o, st, v, a, pp, ns, nc); break;
-         case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true>(c, o, st, v, a, pp, ns, nc); break;
-         default:
-            if (o.code & MB2_SC)
-               mb_sincos(pp.mq, &ns, &nc);
-            aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
-            break;
-      }
-      pp.s = ns;
-      pp.c = nc;
+#undef MB_RUN_CASE
    }
    c.template pf_wait<0>();
 }

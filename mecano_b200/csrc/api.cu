@@ -13,7 +13,9 @@
 
 #include "../../include/mecano_b200.h"
 #include "flatten.h"
+#include "jit.h"
 #include "kernels.h"
+#include "specialize.h"
 
 struct mecano_b200_handle
 {
@@ -22,6 +24,8 @@ struct mecano_b200_handle
    double *d_consts = nullptr;
    uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
    double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
+   size_t ws_doubles[3] = {0, 0, 0};
+   mb::SpecKernel spec[3];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[3];
    int variant = MECANO_B200_VARIANT_AUTO;
@@ -76,10 +80,28 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
 {
    if (n > (int64_t)1 << 28 || ld > (int64_t)1 << 28)
       return fail(h, MECANO_B200_ERR_TOO_LARGE, "more than 2^28 states (or ld > 2^28) in one call: split the batch");
-   if (algo == MB_ABA && !h->d_ws[ws_slot] && h->plan[MB_ABA].ws_doubles)
-      MB_CUDA(h, cudaMalloc(&h->d_ws[ws_slot], h->plan[MB_ABA].ws_doubles * sizeof(double)));
    if (h->variant == MECANO_B200_VARIANT_WARP)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the warp-per-state variant is not built in this version");
+   // the tree-specialised kernel covers the common call (no external wrenches, default flags / layout); everything else
+   // runs the generic kernels
+   const mb::SpecKernel &sk = h->spec[algo];
+   const bool use_spec = sk.ready() && !fext && flags == 0;
+   if (algo == MB_ABA)
+   {
+      const size_t need = use_spec ? (size_t)sk.grid * sk.opt.block * (size_t)std::max(h->tree.prog[MB_ABA].rec_doubles, 1) : h->plan[MB_ABA].ws_doubles;
+      if (h->ws_doubles[ws_slot] < need)
+      {
+         if (h->d_ws[ws_slot])
+         {
+            MB_CUDA(h, cudaStreamSynchronize(stream));
+            MB_CUDA(h, cudaFree(h->d_ws[ws_slot]));
+            h->d_ws[ws_slot] = nullptr;
+            h->ws_doubles[ws_slot] = 0;
+         }
+         MB_CUDA(h, cudaMalloc(&h->d_ws[ws_slot], need * sizeof(double)));
+         h->ws_doubles[ws_slot] = need;
+      }
+   }
    mb::KernelArgs a;
    a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
    a.consts = h->d_consts;
@@ -91,8 +113,33 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.grav[0] = h->gravity[0]; a.grav[1] = h->gravity[1]; a.grav[2] = h->gravity[2];
    a.flags = flags;
    a.nv = h->tree.nv;
+   if (use_spec)
+   {
+      const long long ntiles = (n + sk.opt.block - 1) / sk.opt.block;
+      // ABA: persistent grid (workspace column per resident thread); RNEA / CRBA: one block per tile
+      const unsigned grid = algo == MB_ABA ? (unsigned)std::min<long long>(ntiles, sk.grid) : (unsigned)ntiles;
+      a.ws_ld = (long long)sk.grid * sk.opt.block;
+      MB_CUDA(h, mb::spec_launch(sk, a, grid, stream));
+      return MECANO_B200_OK;
+   }
    MB_CUDA(h, mb::launch_thread_kernel(algo, h->tree.prog[algo], a, h->plan[algo], stream));
    return MECANO_B200_OK;
+}
+
+// "rnea=512:32,aba=256:0" -> block size and TMEM stack slots of the specialised kernel of one algorithm
+bool spec_cfg_from_env(int algo, mb::SpecOptions &opt)
+{
+   const char *e = getenv("MECANO_B200_SPEC_CFG");
+   if (!e) return false;
+   const char *key = algo == MB_RNEA ? "rnea=" : (algo == MB_ABA ? "aba=" : "crba=");
+   const char *p = strstr(e, key);
+   if (!p) return false;
+   int b = 0, tm = 0, sync = 1;
+   if (sscanf(p + strlen(key), "%d:%d:%d", &b, &tm, &sync) < 1 || b < 32 || b > 1024 || (b & 31)) return false;
+   opt.block = b;
+   opt.tm = tm;
+   opt.sync_every = sync;
+   return true;
 }
 
 int ensure_pipeline(mecano_b200_handle *h, size_t doubles_per_slot)
@@ -258,7 +305,10 @@ void mecano_b200_destroy(mecano_b200_handle *h)
    if (h->d_consts) cudaFree(h->d_consts);
    if (h->d_zero) cudaFree(h->d_zero);
    for (int i = 0; i < 3; i++)
+   {
       if (h->d_ws[i]) cudaFree(h->d_ws[i]);
+      mb::spec_unload(h->spec[i]);
+   }
    delete h;
 }
 
@@ -281,6 +331,51 @@ int mecano_b200_set_variant(mecano_b200_handle *h, int variant)
    if (variant != MECANO_B200_VARIANT_AUTO && variant != MECANO_B200_VARIANT_THREAD)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unsupported variant (the warp-per-state variant is not built in this version)");
    h->variant = variant;
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_CUDA(h, cudaSetDevice(h->device));
+   for (int algo = 0; algo < 3; algo++)
+   {
+      if (!(algo_mask & (1u << algo)) || h->spec[algo].ready())
+         continue;
+      if (algo == MB_CRBA)
+         continue; // bound by the HBM write of the mass matrix: the generic kernel is already at the roof
+      const MbProgram &P = h->tree.prog[algo];
+      // Unrolled code is fetched once per tile of states; beyond ~100 KB it no longer fits the instruction caches and the
+      // block becomes fetch-bound (measured: 32-body humanoid RNEA 172 KB -> 0.78x, 15-body tree 81 KB -> 1.42x of the generic
+      // kernel; profiles/r01g_spec.jsonl).  Estimated size: RNEA ~5.4 KB, ABA ~12 KB of SASS per body.
+      const double est_kb = h->tree.nb * (algo == MB_RNEA ? 5.4 : 12.0);
+      if (est_kb > 110.0 && !(algo_mask & MECANO_B200_SPECIALIZE_FORCE))
+         continue;
+      mb::SpecOptions opt;
+      // defaults from the launch-configuration sweep (profiles/): RNEA 16 warps with a TMEM stack, ABA 8 warps in shared memory
+      if (algo == MB_RNEA) { opt.block = 512; opt.tm = 32; }
+      else { opt.block = 256; opt.tm = 0; }
+      spec_cfg_from_env(algo, opt);
+      if (opt.tm * 4 > (512 / ((opt.block + 127) / 128) & ~3))
+         return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "MECANO_B200_SPEC_CFG: TMEM slots exceed the columns of one warp");
+      std::string err;
+      int rc = MECANO_B200_ERR_TOO_LARGE;
+      // shrink the block until the shared-memory part of the stack fits
+      for (int b = opt.block; b >= 64 && rc == MECANO_B200_ERR_TOO_LARGE; b >>= 1)
+      {
+         mb::SpecOptions o2 = opt;
+         o2.block = b;
+         o2.tm = opt.tm > 0 ? std::min(opt.tm * (opt.block / b), 128) : 0;
+         int max_optin = 0;
+         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+         if (mb::spec_smem_bytes(algo, P, o2.block, o2.tm) + 1024 > (size_t)max_optin)
+            continue;
+         rc = mb::spec_build(algo, h->tree, o2, h->spec[algo], err);
+      }
+      if (rc != MECANO_B200_OK)
+         return fail(h, rc, "specialize: " + err);
+   }
    return MECANO_B200_OK;
 }
 
@@ -345,13 +440,31 @@ int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_state
    const MbProgram &P = h->tree.prog[algo];
    std::memset(info, 0, sizeof *info);
    info->variant = MECANO_B200_VARIANT_THREAD;
-   info->block_threads = p.block;
-   info->states_per_block = p.block;
-   info->regs_per_thread = p.regs;
-   info->static_smem_bytes = p.static_smem;
-   info->dynamic_smem_bytes = (int32_t)p.smem;
-   info->local_bytes_per_thread = p.local_bytes;
-   info->blocks_per_sm = p.blocks_per_sm;
+   const mb::SpecKernel &sk = h->spec[algo];
+   if (sk.ready())
+   {
+      info->block_threads = sk.opt.block;
+      info->states_per_block = sk.opt.block;
+      info->regs_per_thread = sk.regs;
+      info->static_smem_bytes = sk.static_smem;
+      info->dynamic_smem_bytes = (int32_t)sk.smem;
+      info->local_bytes_per_thread = sk.local_bytes;
+      info->blocks_per_sm = sk.blocks_per_sm;
+      info->specialized = 1 + (sk.from_cache ? 1 : 0);
+      info->tmem_stack_slots = sk.opt.tm;
+      info->jit_seconds = sk.compile_seconds;
+   }
+   else
+   {
+      info->block_threads = p.block;
+      info->states_per_block = p.block;
+      info->regs_per_thread = p.regs;
+      info->static_smem_bytes = p.static_smem;
+      info->dynamic_smem_bytes = (int32_t)p.smem;
+      info->local_bytes_per_thread = p.local_bytes;
+      info->blocks_per_sm = p.blocks_per_sm;
+      info->tmem_stack_slots = p.tm;
+   }
    cudaDeviceGetAttribute(&info->sm_count, cudaDevAttrMultiProcessorCount, h->device);
    info->stack_doubles = P.stack_doubles;
    info->max_depth = P.max_depth;
@@ -374,6 +487,44 @@ int mecano_b200_measure_hbm_peak(int device, double *gbs)
    cudaError_t e = cudaSetDevice(device);
    if (e == cudaSuccess) e = mb::measure_hbm_peak(gbs);
    return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
+int mecano_b200_generate_source(const mecano_b200_tree_desc *desc, int algo, int block_threads, int tmem_slots, char *buf, int64_t capacity, int64_t *needed)
+{
+   if (algo < 0 || algo > 2) return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "algo must be 0 (RNEA), 1 (ABA) or 2 (CRBA)");
+   mb::FlatTree tree;
+   std::string err;
+   int rc = mb::flatten_tree(desc, tree, err);
+   if (rc != MECANO_B200_OK) return fail(nullptr, rc, err);
+   mb::SpecOptions opt;
+   opt.block = block_threads > 0 ? block_threads : 256;
+   opt.tm = tmem_slots;
+   const std::string src = mb::generate_source(algo, tree, opt);
+   if (needed) *needed = (int64_t)src.size() + 1;
+   if (buf && capacity > 0)
+   {
+      const size_t n = std::min<size_t>(src.size(), (size_t)capacity - 1);
+      std::memcpy(buf, src.data(), n);
+      buf[n] = 0;
+   }
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_jit_check(const mecano_b200_tree_desc *desc, int algo, int block_threads, int tmem_slots, int64_t *cubin_bytes)
+{
+   if (algo < 0 || algo > 2) return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "algo must be 0 (RNEA), 1 (ABA) or 2 (CRBA)");
+   mb::FlatTree tree;
+   std::string err;
+   int rc = mb::flatten_tree(desc, tree, err);
+   if (rc != MECANO_B200_OK) return fail(nullptr, rc, err);
+   mb::SpecOptions opt;
+   opt.block = block_threads > 0 ? block_threads : 256;
+   opt.tm = tmem_slots;
+   size_t bytes = 0;
+   rc = mb::spec_compile_only(mb::generate_source(algo, tree, opt), &bytes, err);
+   if (cubin_bytes) *cubin_bytes = (int64_t)bytes;
+   if (rc != MECANO_B200_OK) return fail(nullptr, rc, err);
+   return MECANO_B200_OK;
 }
 
 int mecano_b200_host_alloc(void **ptr, int64_t bytes)

@@ -123,6 +123,7 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
    for (int k = 0; k < nops; k++)
    {
       const MbOp2 o = P.op2[k];
+      c.stk_fence();
       {
          const MbOp2 od = P.op2[k + MB_PF_DIST];
          if (mb2_is_1dof_descend(od))

@@ -189,6 +189,25 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
    };
    look_ahead(P.op2, P.nops);
    look_ahead(P.op3, n3);
+   auto make_runs = [](const MbOp2 *ops, int n, MbRun *runs) {
+      int nr = 0;
+      for (int k = 0; k < n; k++)
+      {
+         const uint8_t kind = ops[k].code & 0xfu;
+         if (nr > 0 && runs[nr - 1].kind == kind && runs[nr - 1].n < 255)
+            runs[nr - 1].n++;
+         else
+         {
+            runs[nr].kind = kind;
+            runs[nr].n = 1;
+            runs[nr].k0 = (uint16_t)k;
+            nr++;
+         }
+      }
+      return nr;
+   };
+   P.nruns = make_runs(P.op2, P.nops, P.run);
+   P.nruns3 = make_runs(P.op3, n3, P.run3);
 }
 } // namespace
 

@@ -12,7 +12,9 @@
 #pragma once
 #include "program.h"
 #include "spatial.cuh"
+#if !defined(__CUDACC_RTC__)
 #include <string.h>
+#endif
 
 namespace mb
 {
@@ -90,19 +92,24 @@ MB_HD void mb_sincos(float x, float *s, float *c)
    *c = cosf(x);
 #endif
 }
-// Bring an angle of any magnitude into the fast range without losing accuracy (rare path, separate block).
+// Bring an angle of any magnitude into the fast range without losing accuracy.  The rare path is kept out of line so
+// that it does not sit in the instruction stream of every op (the unrolled, tree-specialised kernels are bound by
+// instruction fetch).
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ static double mb_reduce_angle_slow(double x)
+{
+   double s, c;
+   sincos(x, &s, &c);
+   return atan2(s, c);
+}
+#else
+inline double mb_reduce_angle_slow(double x) { return atan2(sin(x), cos(x)); }
+#endif
 MB_HD double mb_reduce_angle(double x)
 {
    if (!(fabs(x) > MB_SINCOS_FAST_LIMIT))
       return x;
-   double s, c;
-#if defined(__CUDA_ARCH__)
-   sincos(x, &s, &c);
-#else
-   s = sin(x);
-   c = cos(x);
-#endif
-   return atan2(s, c);
+   return mb_reduce_angle_slow(x);
 }
 MB_HD float mb_reduce_angle(float x) { return x; }
 

@@ -1,0 +1,23 @@
+// kernel_args.h -- the argument block every kernel takes (generic and tree-specialised).  No host headers: the
+// specialised sources are compiled by NVRTC.
+#pragma once
+#include "program.h"
+
+namespace mb
+{
+struct KernelArgs
+{
+   const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
+   double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
+   const double *consts;            // device copy of the per-body constant records
+   double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid
+   long long ws_ld;
+   const uint16_t *zero_entries;    // CRBA: structurally zero mass-matrix entries (multiple of 8, 16-byte aligned)
+   int32_t n_zero;
+   long long n, ld;
+   double grav[3];
+   uint32_t flags;
+   int32_t nv;
+};
+
+} // namespace mb

@@ -14,145 +14,31 @@
 // No tensor cores: the recursion is not a dense contraction.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
-#include "algorithms.cuh"
+#include "gpu_ctx.cuh"
 #include "kernels.h"
-
-// the dynamic shared memory of a block: [constant records | per-thread stack, state-minor]
-extern __shared__ double mb_smem[];
 
 namespace mb
 {
 namespace
 {
-// BLOCK (threads per block = stack stride) is a compile-time constant so that stack addresses are base + immediate;
-// shared memory is addressed through the mb_smem symbol so that the compiler emits LDS/STS (a pointer kept in a
-// struct degrades to generic LD/ST).
-// Per-thread context: per-thread base pointers (one IMAD.WIDE per global access), stack of double2 (LDS.128 / STS.128)
-template <int BLOCK> struct GpuCtx2
-{
-   const char *qb, *qdb, *xb, *fb;
-   char *ob;
-   unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
-   int stk0;     // index (double2 units) of stack slot 0 of this thread
-   double *aux; // local memory
-
-   __device__ __forceinline__ double ld_q(int r) const { return __ldg((const double *)(qb + (unsigned long long)(unsigned)r * ld8)); }
-   __device__ __forceinline__ double ld_qd(int r) const { return __ldg((const double *)(qdb + (unsigned long long)(unsigned)r * ld8)); }
-   __device__ __forceinline__ double ld_x(int r) const { return __ldg((const double *)(xb + (unsigned long long)(unsigned)r * ld8)); }
-   __device__ __forceinline__ double ld_fext(int b, int k) const { return __ldg((const double *)(fb + (unsigned long long)(unsigned)(6 * b + k) * ld8)); }
-   __device__ __forceinline__ void st_out(int r, double v) { *(double *)(ob + (unsigned long long)(unsigned)r * ld8) = v; }
-   __device__ __forceinline__ void stk_ld2(int slot2, int j, double &a, double &b) const
-   {
-      const double2 t = reinterpret_cast<const double2 *>(mb_smem)[stk0 + (slot2 + j) * BLOCK];
-      a = t.x;
-      b = t.y;
-   }
-   __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b) { reinterpret_cast<double2 *>(mb_smem)[stk0 + (slot2 + j) * BLOCK] = make_double2(a, b); }
-   __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
-   __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
-   // ABA pass-two records: global workspace of double2, one column per resident thread (coalesced 16-byte accesses),
-   // read back in pass three through the ring below with cp.async.cg (L2, the coherence point of the earlier stores)
-   double2 *wsb;       // workspace + column of this thread
-   long long ws_ld;
-   int ring3_0;        // index (double2) of this thread's element of stage 0, row 0 of the pass-three ring
-   __device__ __forceinline__ void rec_st2(int i2, double a, double b) { wsb[i2 * ws_ld] = make_double2(a, b); }
-   // pass-three ring: [stage][(q, qd) | rec0 .. rec3][BLOCK] double2, overlaid on the (then idle) stack area
-   __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
-   {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double2 *>(mb_smem) + ring3_0 + stage * 5 * BLOCK);
-      if (mask & 1)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
-      if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
-      const double2 *src = wsb + rec2 * ws_ld;
-#pragma unroll
-      for (int j = 0; j < 4; j++)
-         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(src + j * ws_ld) : "memory");
-   }
-   __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const
-   {
-      const double2 t = reinterpret_cast<const double2 *>(mb_smem)[ring3_0 + (stage * 5 + row) * BLOCK];
-      a = t.x;
-      b = t.y;
-   }
-   __device__ __forceinline__ void pass_fence() const { __threadfence(); }
-   __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
-   // mass matrix: entry e = row * nv + col lives at mbase + e * mstride (entry-major: mstride = ld8; state-major: 8)
-   char *mbase;
-   unsigned mstride;
-   int nv;
-   const uint4 *zlist;
-   int nz8;
-   __device__ __forceinline__ int n_dofs() const { return nv; }
-   __device__ __forceinline__ void st_M(int e, double v) const { __stcs((double *)(mbase + (unsigned long long)(unsigned)e * mstride), v); }
-   __device__ __forceinline__ void zero_fill() const
-   {
-#pragma unroll 1
-      for (int k = 0; k < nz8; k++)
-      {
-         const uint4 u = __ldg(zlist + k);
-         st_M(u.x & 0xffffu, 0.0); st_M(u.x >> 16, 0.0); st_M(u.y & 0xffffu, 0.0); st_M(u.y >> 16, 0.0);
-         st_M(u.z & 0xffffu, 0.0); st_M(u.z >> 16, 0.0); st_M(u.w & 0xffffu, 0.0); st_M(u.w >> 16, 0.0);
-      }
-   }
-   // prefetch ring: [stage][q | qd | x][BLOCK] doubles in shared memory, filled by cp.async (LDGSTS)
-   int ring0; // index (doubles) of this thread's element of stage 0, row 0
-   // mask: 1 = q[cfg], 2 = qd[dof], 4 = x[dof]
-   __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, int mask) const
-   {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(mb_smem + ring0 + stage * 3 * BLOCK);
-      if (mask & 1)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
-      if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
-      if (mask & 4)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 2 * BLOCK * 8), "l"(xb + (unsigned long long)(unsigned)dof * ld8) : "memory");
-   }
-   __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
-   template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-   __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_smem[ring0 + (stage * 3 + j) * BLOCK]; }
-};
-
-template <int ALGO, bool FEXT, bool STATE_MAJOR, int BLOCK, int AUXN, int RECN>
+template <int ALGO, bool FEXT, bool STATE_MAJOR, int BLOCK, int AUXN, int RECN, int TM>
 __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
 {
    const int ncst = P.nb * MB_CONST_STRIDE;
    for (int i = threadIdx.x; i < ncst; i += BLOCK)
       mb_smem[i] = a.consts[i];
-   __syncthreads();
-   double aux[AUXN > 0 ? AUXN : 1];
-   GpuCtx2<BLOCK> c2;
-   c2.ld8 = (unsigned)(a.ld * 8);
-   c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
-   c2.ring3_0 = c2.stk0;
-   c2.ring0 = ((ncst + 1) & ~1) + 2 * P.stack2 * BLOCK + threadIdx.x;
-   c2.aux = aux;
-   c2.nv = a.nv;
-   c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
-   c2.zlist = (const uint4 *)a.zero_entries;
-   c2.nz8 = a.n_zero >> 3;
-   c2.wsb = reinterpret_cast<double2 *>(a.ws) + ((long long)blockIdx.x * BLOCK + threadIdx.x);
-   c2.ws_ld = a.ws_ld;
-   // persistent grid: each block walks over tiles of BLOCK states.  The per-state areas (stack, rings) are private to a
-   // thread and the constant records are read-only, so the threads of a block never synchronise again.
-   const long long ntiles = (a.n + BLOCK - 1) / BLOCK;
-   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
-   {
-      const long long s = tile * BLOCK + threadIdx.x;
-      if (s >= a.n)
-         break;
-      c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
-      c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
-      c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
+   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, P.stack2, [&](GpuCtx2<BLOCK, TM> &c2) {
       if constexpr (ALGO == MB_RNEA)
-         rnea_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+         rnea_state<double, GpuCtx2<BLOCK, TM>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
       else if constexpr (ALGO == MB_ABA)
-         aba_state<double, GpuCtx2<BLOCK>, FEXT>(P, c2, a.grav);
+         aba_state<double, GpuCtx2<BLOCK, TM>, FEXT>(P, c2, a.grav);
       else
-         crba_state<double, GpuCtx2<BLOCK>>(P, c2);
-   }
+         crba_state<double, GpuCtx2<BLOCK, TM>>(P, c2);
+   });
 }
 
 // compiled work-area classes (local memory per thread): {aux, rec}
@@ -162,9 +48,14 @@ constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
 constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
 constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
 constexpr int kAbaRec0 = MB_ABA_REC * 33, kAbaRec1 = MB_ABA_REC * 128;
-constexpr int kNumCfg = 8;
-constexpr int kCfgClass[kNumCfg] = {0, 0, 0, 0, 0, 1, 1, 1};
-constexpr int kCfgBlock[kNumCfg] = {384, 320, 256, 192, 128, 128, 64, 32};
+// launch configurations: threads per block, work-area class, stack slots (double2) held in tensor memory
+struct Cfg
+{
+   int block, cls, tm;
+};
+constexpr int kNumCfg = 14;
+constexpr Cfg kCfg[kNumCfg] = {{512, 0, 32}, {384, 0, 42}, {320, 0, 42}, {256, 0, 64}, {384, 0, 0}, {320, 0, 0}, {256, 0, 0},
+                               {192, 0, 0},  {128, 0, 0},  {256, 1, 64}, {128, 1, 128}, {128, 1, 0}, {64, 1, 0},  {32, 1, 0}};
 
 typedef void (*KernelFn)(const MbProgram, const KernelArgs);
 
@@ -175,14 +66,11 @@ template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
    constexpr int r0 = ALGO == MB_ABA ? kAbaRec0 : 0, r1 = ALGO == MB_ABA ? kAbaRec1 : 0;
    switch (cfg)
    {
-      case 0: return thread_kernel<ALGO, FEXT, SM, 384, a0, r0>;
-      case 1: return thread_kernel<ALGO, FEXT, SM, 320, a0, r0>;
-      case 2: return thread_kernel<ALGO, FEXT, SM, 256, a0, r0>;
-      case 3: return thread_kernel<ALGO, FEXT, SM, 192, a0, r0>;
-      case 4: return thread_kernel<ALGO, FEXT, SM, 128, a0, r0>;
-      case 5: return thread_kernel<ALGO, FEXT, SM, 128, a1, r1>;
-      case 6: return thread_kernel<ALGO, FEXT, SM, 64, a1, r1>;
-      default: return thread_kernel<ALGO, FEXT, SM, 32, a1, r1>;
+#define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, kCfg[i].tm>;
+      MB_CFG_CASE(0) MB_CFG_CASE(1) MB_CFG_CASE(2) MB_CFG_CASE(3) MB_CFG_CASE(4) MB_CFG_CASE(5) MB_CFG_CASE(6)
+      MB_CFG_CASE(7) MB_CFG_CASE(8) MB_CFG_CASE(9) MB_CFG_CASE(10) MB_CFG_CASE(11) MB_CFG_CASE(12)
+#undef MB_CFG_CASE
+      default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, kCfg[13].tm>;
    }
 }
 
@@ -203,11 +91,25 @@ int class_of(int algo, const MbProgram &P)
    return -1;
 }
 
-size_t smem_bytes(int algo, const MbProgram &P, int block)
+size_t smem_bytes(int algo, const MbProgram &P, int block, int tm)
 {
    const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
-   (void)algo;
-   return sizeof(double) * ((size_t)ncst + (2 * (size_t)P.stack2 + 3 * MB_PF_STAGES) * block);
+   const int smem_slots = std::max(P.stack2 - tm, algo == MB_ABA ? 20 : 0);
+   size_t bytes = sizeof(double) * ((size_t)ncst + (2 * (size_t)smem_slots + 3 * MB_PF_STAGES) * block);
+   // a block with a TMEM stack allocates all 512 columns: keep it alone on its SM (a second block would spin in tcgen05.alloc)
+   if (tm > 0)
+      bytes = std::max<size_t>(bytes, 120 * 1024);
+   return bytes;
+}
+
+// MECANO_B200_CFG="rnea=0,aba=5,crba=6" pins the launch configuration per algorithm (profiling / sweeps)
+int forced_cfg(int algo)
+{
+   const char *e = getenv("MECANO_B200_CFG");
+   if (!e) return -1;
+   const char *key = algo == MB_RNEA ? "rnea=" : (algo == MB_ABA ? "aba=" : "crba=");
+   const char *p = strstr(e, key);
+   return p ? atoi(p + strlen(key)) : -1;
 }
 } // namespace
 
@@ -223,33 +125,54 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    e = cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
    if (e != cudaSuccess) return e;
    int best_threads = 0;
+   const int forced = forced_cfg(algo);
    for (int cfg = 0; cfg < kNumCfg; cfg++)
    {
-      if (kCfgClass[cfg] < cls)
+      if (kCfg[cfg].cls < cls)
          continue; // work areas too small
-      const int b = kCfgBlock[cfg];
-      const size_t sm = smem_bytes(algo, P, b);
+      if (forced >= 0 && cfg != forced)
+         continue;
+      // measured (profiles/r01f_cfg_sweep.jsonl): the TMEM stack pays off where registers allow 16 warps per SM (RNEA);
+      // ABA is register-bound at 8 warps and CRBA store-bound, both lose to the shared-memory stack
+      if (forced < 0 && kCfg[cfg].tm > 0 && algo != MB_RNEA)
+         continue;
+      const int b = kCfg[cfg].block;
+      const size_t sm = smem_bytes(algo, P, b, kCfg[cfg].tm);
       if (sm > (size_t)max_optin)
          continue;
       // every variant of this configuration gets the opt-in so that later launches cannot fail on it
+      KernelFn fn = pick(algo, fext, false, cfg);
+      cudaFuncAttributes fa;
+      e = cudaFuncGetAttributes(&fa, (const void *)fn);
+      if (e != cudaSuccess) return e;
+      const int max_dyn = max_optin - (int)fa.sharedSizeBytes;
+      if (sm > (size_t)max_dyn)
+         continue;
       for (int f = 0; f < 2; f++)
          for (int st = 0; st < 2; st++)
          {
-            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st != 0, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin);
+            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st != 0, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
             if (e != cudaSuccess) return e;
          }
-      KernelFn fn = pick(algo, fext, false, cfg);
       int nblk = 0;
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, (const void *)fn, b, sm);
       if (e != cudaSuccess) return e;
-      // prefer more resident states; on ties the smaller work-area class (first in the table) wins
-      if (nblk * b > best_threads)
+      if (kCfg[cfg].tm > 0 && nblk > 1)
+         nblk = 1; // cannot happen (smem_bytes), but a TMEM block must be alone on its SM
+      // register spills cost more than the extra warps bring: a configuration whose kernel spills beyond its declared
+      // work area only competes if nothing else fits
+      const int auxn = algo == MB_RNEA ? (kCfg[cfg].cls ? kRnaAux1 : kRnaAux0) : (algo == MB_ABA ? (kCfg[cfg].cls ? kAbaAux1 : kAbaAux0) : (kCfg[cfg].cls ? kCrbAux1 : kCrbAux0));
+      const bool spills = (long)fa.localSizeBytes > 8l * auxn + 128;
+      const int score = spills && forced < 0 ? 1 : nblk * b;
+      // prefer more resident states; on ties the first configuration in the table wins
+      if (nblk > 0 && score > best_threads)
       {
-         best_threads = nblk * b;
+         best_threads = score;
          plan.block = b;
          plan.smem = sm;
          plan.blocks_per_sm = nblk;
          plan.size_class = cfg;
+         plan.tm = kCfg[cfg].tm;
       }
    }
    if (best_threads == 0)
@@ -277,7 +200,8 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread);
    // RNEA and CRBA measured faster with one block per tile (hardware block scheduling keeps the SMs evenly loaded)
-   const unsigned grid = algo == MB_ABA ? (unsigned)std::min<long long>(ntiles, plan.grid) : (unsigned)ntiles;
+   static const bool persist_all = getenv("MECANO_B200_PERSIST") != nullptr;
+   const unsigned grid = (algo == MB_ABA || persist_all) ? (unsigned)std::min<long long>(ntiles, plan.grid) : (unsigned)ntiles;
    KernelArgs b = a;
    b.ws_ld = (long long)plan.grid * plan.block;
    fn<<<grid, plan.block, plan.smem, stream>>>(P, b);

@@ -3,29 +3,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernel_args.h"
 #include "program.h"
 
 namespace mb
 {
-struct KernelArgs
-{
-   const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
-   double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
-   const double *consts;            // device copy of the per-body constant records
-   double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid
-   long long ws_ld;
-   const uint16_t *zero_entries;    // CRBA: structurally zero mass-matrix entries (multiple of 8, 16-byte aligned)
-   int32_t n_zero;
-   long long n, ld;
-   double grav[3];
-   uint32_t flags;
-   int32_t nv;
-};
-
 struct LaunchPlan
 {
    int block = 0;        // threads per block (= states per block for the thread-per-state variant)
    size_t smem = 0;      // dynamic shared memory per block
+   int tm = 0;           // stack slots held in tensor memory
    int size_class = 0;   // 0: small local work areas, 1: large
    int blocks_per_sm = 0;
    int regs = 0;

@@ -13,7 +13,16 @@
 // scalars (q, qd, qdd, tau) are invariant under this; SixDoF joints keep Q = identity so that their
 // 6-vectors stay in Mecano's frameAfterJoint.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (tree-specialised kernels, jit.cpp) has no host headers
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef unsigned int uint32_t;
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 
 #define MB_MAX_BODIES 128
 #define MB_MAX_OPS (2 * MB_MAX_BODIES)
@@ -94,9 +103,20 @@ struct MbWalk
    uint16_t slot;  // stack slot (double2 units)
 };
 
+// A run: consecutive ops of the same kind (code & 0xf: ASCEND bit, joint type, SC bit).  The kernels execute a run as one
+// tight loop over a routine specialised on the kind, instead of dispatching every op through a switch: the loop-carried
+// spatial quantities then stay in the same registers from op to op (the per-op switch cost ~40 register moves per op).
+struct MbRun
+{
+   uint8_t kind; // MbOp2::code & 0xf
+   uint8_t n;    // number of ops
+   uint16_t k0;  // first op
+};
+
 struct MbProgram
 {
    int32_t nb, nops, nv, nq;
+   int32_t nruns, nruns3, pad0, pad1;
    int32_t stack2;        // v2 stack size per state in double2 units
    int32_t stack_doubles; // shared-memory stack per state
    int32_t aux_doubles;   // local-memory branch save area per state
@@ -105,6 +125,8 @@ struct MbProgram
    MbBody body[MB_MAX_BODIES];
    uint32_t op[MB_MAX_OPS];
    MbWalk walk[MB_MAX_BODIES];
+   MbRun run[MB_MAX_OPS];        // runs of op2
+   MbRun run3[MB_MAX_BODIES];    // runs of op3
    MbOp2 op3[MB_MAX_BODIES + 4]; // ABA pass three: the DESCEND records only, with their own SC / pf look-ahead bits
    MbOp2 op2[MB_MAX_OPS + 4]; // trailing no-op records so that the look-ahead never reads past the end
 };

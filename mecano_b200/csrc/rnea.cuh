@@ -154,91 +154,173 @@ template <class T, class Ctx> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o,
 #define MB_PF_STAGES 4
 #define MB_PF_DIST 3
 
-template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav, bool use_qd, bool use_qdd)
+// One op of the traversal program: the body of the interpreter loop below, and the unit the tree-specialised kernels
+// (specialize.cpp) are generated from -- there every argument except the context and the carried state is a literal, so
+// the flag tests, the dispatch switch and all table lookups fold away at compile time.
+//   k: index of the op (selects the prefetch-ring stage);  o: this op;  od: op k + MB_PF_DIST (its scalars are issued now)
+template <class T, class Ctx, bool FEXT>
+MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int ext, const T *grav, const bool use_qd, const bool use_qdd, SvT<T> &v,
+                   SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
 {
-   SvT<T> v = sv_zero<T>(), a = sv_zero<T>(), f = sv_zero<T>();
-   RneaPipe<T> pp;
+   const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
+   c.op_sync(k);
+   c.stk_fence();
+   if (mb2_is_1dof_descend(od))
+      c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, pfmask);
+   c.pf_commit();
+   c.template pf_wait<MB_PF_DIST - 1>(); // everything up to the group of op k + 1 has landed
+   pp.qd = pp.x = pp.mq = (T)0;
+   if (mb2_is_1dof_descend(o))
+   {
+      if (use_qd) pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      if (use_qdd) pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+   }
+   if (o.pf & 1u) // op k + 1 is a 1-DoF DESCEND
+      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0)); // no-op unless |q| > MB_SINCOS_FAST_LIMIT
+   // kinematic state of the parent: carried in registers along a chain, otherwise the root acceleration
+   // (= -gravity, InverseDynamicsCalculator.java:397-403) or the state saved by the branching ancestor
+   if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+   {
+      if (o.flags & MB2_ROOT_PARENT)
+      {
+         v = sv_zero<T>();
+         a = sv_zero<T>();
+         a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
+      }
+      else
+      {
+         v = aux_ld_sv<T>(c, o.paux);
+         a = aux_ld_sv<T>(c, o.paux + 6);
+      }
+   }
+   T ns = pp.mq, nc = (T)1; // prismatic next op: "s" carries q
+   switch (o.code & 0xfu)
+   {
+      case 0 | (MB_REVOLUTE << 1): rnea_descend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, a, f, pp, ns, nc); break;
+      case 0 | (MB_REVOLUTE << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, a, f, pp, ns, nc); break;
+      case 1 | (MB_REVOLUTE << 1): rnea_ascend_1dof<T, Ctx, true, false>(c, o, f, pp, ns, nc); break;
+      case 1 | (MB_REVOLUTE << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, true, true>(c, o, f, pp, ns, nc); break;
+      case 0 | (MB_PRISMATIC << 1): rnea_descend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, a, f, pp, ns, nc); break;
+      case 0 | (MB_PRISMATIC << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, a, f, pp, ns, nc); break;
+      case 1 | (MB_PRISMATIC << 1): rnea_ascend_1dof<T, Ctx, false, false>(c, o, f, pp, ns, nc); break;
+      case 1 | (MB_PRISMATIC << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, false, true>(c, o, f, pp, ns, nc); break;
+      default:
+         if (o.code & MB2_SC)
+            mb_sincos(pp.mq, &ns, &nc);
+         if (o.code & MB2_ASCEND)
+            rnea_ascend_6dof<T, Ctx>(c, o, f);
+         else
+            rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f, use_qd, use_qdd);
+         break;
+   }
+   pp.s = ns;
+   pp.c = nc;
+}
+
+// prologue: the scalars of ops 0 .. MB_PF_DIST-1 are requested, the sin/cos of op 0 evaluated
+template <class T, class Ctx>
+MB_HD void rnea_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, const bool use_qd, const bool use_qdd, SvT<T> &v, SvT<T> &a, SvT<T> &f,
+                      RneaPipe<T> &pp)
+{
+   static_assert(MB_PF_DIST == 3, "prologue written for a prefetch distance of 3");
+   v = sv_zero<T>(); a = sv_zero<T>(); f = sv_zero<T>();
    pp.s = pp.qd = pp.x = pp.mq = pp.ls = (T)0;
    pp.c = pp.lc = (T)1;
-   const int nops = P.nops;
    const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
-   // prologue: scalars of ops 0 .. MB_PF_DIST-1
-#pragma unroll
-   for (int k = 0; k < MB_PF_DIST; k++)
-   {
-      const MbOp2 o = P.op2[k];
-      if (mb2_is_1dof_descend(o))
-         c.pf_issue(k, o.cfg, o.dof, pfmask);
-      c.pf_commit();
-   }
+   if (mb2_is_1dof_descend(o0)) c.pf_issue(0, o0.cfg, o0.dof, pfmask);
+   c.pf_commit();
+   if (mb2_is_1dof_descend(o1)) c.pf_issue(1, o1.cfg, o1.dof, pfmask);
+   c.pf_commit();
+   if (mb2_is_1dof_descend(o2)) c.pf_issue(2, o2.cfg, o2.dof, pfmask);
+   c.pf_commit();
    c.template pf_wait<0>();
+   if (mb2_is_1dof_descend(o0))
    {
-      const MbOp2 o0 = P.op2[0];
-      if (mb2_is_1dof_descend(o0))
+      const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
+      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+      else pp.s = q0;
+   }
+}
+
+// One op inside a run: the same steps as rnea_op with the kind (ASCEND / joint type / SC) fixed at compile time, so a run
+// is a tight loop over one straight-line routine.
+template <class T, class Ctx, bool FEXT, int KIND>
+MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, const bool use_qd, const bool use_qdd, const int pfmask, SvT<T> &v,
+                         SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
+{
+   constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0;
+   constexpr int JT = (KIND >> 1) & 3;
+   const MbOp2 o = P.op2[k];
+   c.stk_fence();
+   {
+      const MbOp2 od = P.op2[k + MB_PF_DIST];
+      if (mb2_is_1dof_descend(od))
+         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, pfmask);
+      c.pf_commit();
+      c.template pf_wait<MB_PF_DIST - 1>();
+   }
+   pp.qd = pp.x = pp.mq = (T)0;
+   if (!ASC && JT != MB_SIXDOF)
+   {
+      if (use_qd) pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      if (use_qdd) pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+   }
+   if (o.pf & 1u)
+      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+   if (!ASC && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+   {
+      if (o.flags & MB2_ROOT_PARENT)
       {
-         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
-         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
-         else pp.s = q0;
+         v = sv_zero<T>();
+         a = sv_zero<T>();
+         a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
+      }
+      else
+      {
+         v = aux_ld_sv<T>(c, o.paux);
+         a = aux_ld_sv<T>(c, o.paux + 6);
       }
    }
-#pragma unroll 1
-   for (int k = 0; k < nops; k++)
+   const int ext = FEXT ? P.body[o.body].ext_index : 0;
+   T ns = pp.mq, nc = (T)1;
+   if (JT == MB_SIXDOF)
    {
-      const MbOp2 o = P.op2[k];
+      if (SC) mb_sincos(pp.mq, &ns, &nc);
+      if (ASC) rnea_ascend_6dof<T, Ctx>(c, o, f);
+      else rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f, use_qd, use_qdd);
+   }
+   else if (ASC)
+      rnea_ascend_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, f, pp, ns, nc);
+   else
+      rnea_descend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, SC>(c, o, ext, v, a, f, pp, ns, nc);
+   pp.s = ns;
+   pp.c = nc;
+}
+
+template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav, bool use_qd, bool use_qdd)
+{
+   SvT<T> v, a, f;
+   RneaPipe<T> pp;
+   rnea_begin<T, Ctx>(c, P.op2[0], P.op2[1], P.op2[2], use_qd, use_qdd, v, a, f, pp);
+   const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
+   const int nruns = P.nruns;
+#pragma unroll 1
+   for (int r = 0; r < nruns; r++)
+   {
+      const MbRun R = P.run[r];
+      int k = R.k0;
+      const int k1 = k + R.n;
+#define MB_RUN_CASE(KIND)                                                                                  \
+   case KIND:                                                                                               \
+      _Pragma("unroll 1") do { rnea_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, use_qd, use_qdd, pfmask, v, a, f, pp); } while (++k < k1); \
+      break;
+      switch (R.kind)
       {
-         const MbOp2 od = P.op2[k + MB_PF_DIST];
-         if (mb2_is_1dof_descend(od))
-            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, pfmask);
-         c.pf_commit();
-         c.template pf_wait<MB_PF_DIST - 1>(); // everything up to the group of op k + 1 has landed
+         MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
+         MB_RUN_CASE(8) MB_RUN_CASE(9) MB_RUN_CASE(10) MB_RUN_CASE(11) MB_RUN_CASE(12) MB_RUN_CASE(13)
+         default: break;
       }
-      pp.qd = pp.x = pp.mq = (T)0;
-      if (mb2_is_1dof_descend(o))
-      {
-         if (use_qd) pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
-         if (use_qdd) pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
-      }
-      if (o.pf & 1u) // op k + 1 is a 1-DoF DESCEND
-         pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0)); // no-op unless |q| > MB_SINCOS_FAST_LIMIT
-      // kinematic state of the parent: carried in registers along a chain, otherwise the root acceleration
-      // (= -gravity, InverseDynamicsCalculator.java:397-403) or the state saved by the branching ancestor
-      if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
-      {
-         if (o.flags & MB2_ROOT_PARENT)
-         {
-            v = sv_zero<T>();
-            a = sv_zero<T>();
-            a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
-         }
-         else
-         {
-            v = aux_ld_sv<T>(c, o.paux);
-            a = aux_ld_sv<T>(c, o.paux + 6);
-         }
-      }
-      const int ext = FEXT ? P.body[o.body].ext_index : 0;
-      T ns = pp.mq, nc = (T)1; // prismatic next op: "s" carries q
-      switch (o.code & 0xfu)
-      {
-         case 0 | (MB_REVOLUTE << 1): rnea_descend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, a, f, pp, ns, nc); break;
-         case 0 | (MB_REVOLUTE << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, a, f, pp, ns, nc); break;
-         case 1 | (MB_REVOLUTE << 1): rnea_ascend_1dof<T, Ctx, true, false>(c, o, f, pp, ns, nc); break;
-         case 1 | (MB_REVOLUTE << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, true, true>(c, o, f, pp, ns, nc); break;
-         case 0 | (MB_PRISMATIC << 1): rnea_descend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, a, f, pp, ns, nc); break;
-         case 0 | (MB_PRISMATIC << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, a, f, pp, ns, nc); break;
-         case 1 | (MB_PRISMATIC << 1): rnea_ascend_1dof<T, Ctx, false, false>(c, o, f, pp, ns, nc); break;
-         case 1 | (MB_PRISMATIC << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, false, true>(c, o, f, pp, ns, nc); break;
-         default:
-            if (o.code & MB2_SC)
-               mb_sincos(pp.mq, &ns, &nc);
-            if (o.code & MB2_ASCEND)
-               rnea_ascend_6dof<T, Ctx>(c, o, f);
-            else
-               rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f, use_qd, use_qdd);
-            break;
-      }
-      pp.s = ns;
-      pp.c = nc;
+#undef MB_RUN_CASE
    }
    c.template pf_wait<0>();
 }

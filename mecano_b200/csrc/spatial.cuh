@@ -14,7 +14,9 @@
 #define MB_HD inline
 #endif
 
+#if !defined(__CUDACC_RTC__)
 #include <math.h>
+#endif
 
 namespace mb
 {

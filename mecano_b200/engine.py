@@ -71,6 +71,14 @@ class Engine:
     def set_gravity(self, gx, gy, gz):
         check(lib.mecano_b200_set_gravity(self._h, float(gx), float(gy), float(gz)), self._h)
 
+    def specialize(self, algos=("rnea", "aba", "crba"), force=False):
+        """Compile tree-specialised kernels (mecano_b200_specialize): seconds per algorithm, cached on disk.  Algorithms whose
+        unrolled code would not fit the instruction caches keep the generic kernel unless force=True."""
+        mask = 0x100 if force else 0
+        for a in algos:
+            mask |= 1 << {"rnea": 0, "aba": 1, "crba": 2}[a] if isinstance(a, str) else 1 << int(a)
+        check(lib.mecano_b200_specialize(self._h, mask), self._h)
+
     def kernel_info(self, algo, n_states=0):
         info = _capi.KernelInfo()
         check(lib.mecano_b200_kernel_info_get(self._h, int(algo), int(n_states), ctypes.byref(info)), self._h)

@@ -21,6 +21,8 @@ t = td.humanoid(np.random.default_rng(1))
 d, keep, order = el.tree_desc_c(t)
 e = mecano_b200.Engine(_capi.TreeDesc.from_buffer_copy(bytes(d)), 0, keepalive=keep)
 e.set_gravity(0, 0, -9.81)
+if os.environ.get("MECANO_B200_SPECIALIZE"):
+    e.specialize([a for a in algos if a != "crba"], force=True)
 dev = torch.device("cuda:0")
 gen = torch.Generator(device=dev).manual_seed(0)
 tq = (torch.rand((t.nq, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * np.pi

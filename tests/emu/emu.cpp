@@ -75,6 +75,8 @@ template <class T> struct CpuCtx
       ring[stage][2] = (mask & 4) ? ld_x(dof) : nan;
    }
    void pf_commit() {}
+   void stk_fence() const {}
+   void op_sync(int) const {}
    template <int N> void pf_wait() {}
    T pf_ld(int stage, int j) const { return ring[stage][j]; }
    T stk_ld(int i) const { return stk[i]; }

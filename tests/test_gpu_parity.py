@@ -246,3 +246,72 @@ def test_baseline_configs_3_4_humanoid_1m_states_invariants(torch_dev, neck):
     assert rel(hback, o.aba_batch(hq, hqd, htau)) < TOL
     Ms = crba.getMassMatrix(q[:, idx].contiguous()).cpu().numpy().reshape(nv, nv, -1)
     assert rel(Ms, o.crba_batch(hq)) < TOL
+
+
+SPEC_CASES = [
+    ("A7 revolute chain", dict(kind="chain", seed=1, n_joints=7)),
+    ("prismatic chain", dict(kind="chain", seed=3, n_joints=6, prismatic=1.0)),
+    ("floating + mixed chain 6", dict(kind="chain", seed=31, n_joints=6, floating=True, prismatic=0.3)),
+    ("one-dof tree 15", dict(kind="tree", seed=32, n_joints=15, prismatic=0.2)),
+]
+
+
+@pytest.mark.parametrize("idx", range(len(SPEC_CASES)))
+def test_tree_specialised_kernels_match_oracle(torch_dev, idx, tmp_path, monkeypatch):
+    """mecano_b200_specialize(): kernels unrolled for one tree and compiled by NVRTC at run time, against the oracle and
+    against the generic kernels, ragged batch; then again through the cubin cache."""
+    import mecano_b200 as mb
+
+    monkeypatch.setenv("MECANO_B200_CACHE", str(tmp_path))
+    torch, dev = torch_dev
+    name, kw = SPEC_CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(2000 + idx)
+    g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
+    o = ol.Oracle(t, gravity=g)
+    n = 1000 + 13
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    tq, tqd, tqdd, ttau = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, tau))
+    for attempt in range(2):  # 0: compiled, 1: loaded from the cache
+        ident = mb.InverseDynamicsCalculator(s)
+        ident.setGravitationalAcceleration(g)
+        generic = ident.compute(tq, tqd, tqdd).cpu().numpy()
+        ident.specialize(force=True)
+        info = ident.kernelInfo()
+        assert info["specialized"] == 1 + attempt, (name, info)
+        out = torch.full((t.nv, n + 19), float("nan"), dtype=torch.float64, device=dev)  # ld > n: the tail must stay NaN
+        lead = [torch.empty((x.shape[0], n + 19), dtype=torch.float64, device=dev) for x in (tq, tqd, tqdd)]
+        for dst, src in zip(lead, (tq, tqd, tqdd)):
+            dst[:, :n] = src
+        res = ident.compute(lead[0][:, :n], lead[1][:, :n], lead[2][:, :n], out[:, :n]).cpu().numpy()
+        assert torch.isnan(out[:, n:]).all(), "specialised kernel wrote beyond n_states"
+        assert rel(res, o.rnea_batch(q, qd, qdd)) < TOL, name
+        assert rel(res, generic) < 1e-12, name
+        # calls the specialised kernel does not cover fall back to the generic kernels of the same handle
+        ident.setConsiderCoriolisAndCentrifugalForces(False)
+        assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd, flags=1)) < TOL, name
+
+        fdyn = mb.ForwardDynamicsCalculator(s)
+        fdyn.setGravitationalAcceleration(*g)
+        generic = fdyn.compute(tq, tqd, ttau).cpu().numpy()
+        fdyn.specialize(force=True)
+        assert fdyn.kernelInfo()["specialized"] == 1 + attempt, name
+        res = fdyn.compute(tq, tqd, ttau).cpu().numpy()
+        assert rel(res, o.aba_batch(q, qd, tau)) < TOL, name
+        assert rel(res, generic) < 1e-10, name
+
+
+def test_specialize_policy(torch_dev, tmp_path, monkeypatch):
+    """Large trees keep the generic kernel (unrolled code would not fit the instruction caches) unless forced; CRBA is never
+    specialised; small trees are."""
+    import mecano_b200 as mb
+
+    monkeypatch.setenv("MECANO_B200_CACHE", str(tmp_path))
+    s, _ = build(kind="humanoid", seed=7, n_joints=2)
+    ident = mb.InverseDynamicsCalculator(s).specialize()
+    assert ident.kernelInfo()["specialized"] == 0
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s).specialize(force=True)
+    assert crba.kernelInfo()["specialized"] == 0
+    s7, _ = build(kind="chain", seed=1, n_joints=7)
+    assert mb.InverseDynamicsCalculator(s7).specialize().kernelInfo()["specialized"] >= 1
+    assert mb.ForwardDynamicsCalculator(s7).specialize().kernelInfo()["specialized"] >= 1
