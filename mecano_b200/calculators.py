@@ -74,6 +74,12 @@ class _BatchedCalculator:
     def kernelInfo(self, n_states=0):
         return self._engine.kernel_info(self._ALGO, n_states)
 
+    def setKernelVariant(self, variant):
+        """"auto" (default: by batch size), "thread" (one thread per state) or "warp" (one warp per state, lane = body, trees
+        of up to 32 bodies; for small batches)."""
+        self._engine.set_variant({"auto": 0, "thread": 1, "warp": 2}[variant] if isinstance(variant, str) else int(variant))
+        return self
+
     def specialize(self, force=False):
         """Optional second half of the constructor: compile a kernel unrolled for this tree (mecano_b200_specialize).
         Trees whose unrolled code would overflow the instruction caches keep the generic kernel; kernelInfo()["specialized"]

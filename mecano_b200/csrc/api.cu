@@ -23,12 +23,16 @@ struct mecano_b200_handle
    mb::FlatTree tree;
    double *d_consts = nullptr;
    uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
+   MbProgram *d_prog = nullptr; // [3] device copies of the traversal programs (warp-per-state kernels)
    double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
    size_t ws_doubles[3] = {0, 0, 0};
    mb::SpecKernel spec[3];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[3];
    int variant = MECANO_B200_VARIANT_AUTO;
+   int max_children = 1, max_ndof = 1, sm_count = 148;
+   bool warp_ok = false;             // the tree fits the warp-per-state variant (<= 32 bodies)
+   int64_t warp_below[3] = {0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
    std::string error;
    // host pipeline (lazy)
    cudaStream_t streams[2] = {nullptr, nullptr};
@@ -80,8 +84,27 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
 {
    if (n > (int64_t)1 << 28 || ld > (int64_t)1 << 28)
       return fail(h, MECANO_B200_ERR_TOO_LARGE, "more than 2^28 states (or ld > 2^28) in one call: split the batch");
-   if (h->variant == MECANO_B200_VARIANT_WARP)
-      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the warp-per-state variant is not built in this version");
+   // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
+   // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
+   const bool use_warp = h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]);
+   if (use_warp)
+   {
+      if (!h->warp_ok)
+         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body)");
+      mb::KernelArgs wa;
+      wa.q = q; wa.qd = qd; wa.x = x; wa.fext = fext; wa.out = out;
+      wa.consts = h->d_consts;
+      wa.ws = nullptr;
+      wa.ws_ld = 0;
+      wa.zero_entries = h->d_zero;
+      wa.n_zero = (int32_t)h->tree.zero_entries.size();
+      wa.n = n; wa.ld = ld;
+      wa.grav[0] = h->gravity[0]; wa.grav[1] = h->gravity[1]; wa.grav[2] = h->gravity[2];
+      wa.flags = flags;
+      wa.nv = h->tree.nv;
+      MB_CUDA(h, mb::launch_warp_kernel(algo, h->d_prog + algo, wa, h->max_children, h->max_ndof, h->sm_count, stream));
+      return MECANO_B200_OK;
+   }
    // the tree-specialised kernel covers the common call (no external wrenches, default flags / layout); everything else
    // runs the generic kernels
    const mb::SpecKernel &sk = h->spec[algo];
@@ -263,6 +286,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
       if (h->d_consts) cudaFree(h->d_consts);
       if (h->d_zero) cudaFree(h->d_zero);
+      if (h->d_prog) cudaFree(h->d_prog);
       delete h;
       return fail(nullptr, (int)ce, m);
    };
@@ -288,6 +312,29 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
          return fail(nullptr, MECANO_B200_ERR_TOO_LARGE, "tree exceeds the compiled per-state work areas (branch nesting / depth too large)");
       }
    }
+   {
+      const MbProgram &P = h->tree.prog[MB_RNEA];
+      std::vector<int> nchild(P.nb, 0);
+      for (int i = 0; i < P.nb; i++)
+      {
+         if (P.body[i].parent >= 0) nchild[P.body[i].parent]++;
+         h->max_ndof = std::max(h->max_ndof, P.body[i].ndof);
+      }
+      for (int i = 0; i < P.nb; i++) h->max_children = std::max(h->max_children, nchild[i]);
+      cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+      h->warp_ok = mb::warp_variant_supports(P);
+      if (h->warp_ok)
+      {
+         if ((e = cudaMalloc(&h->d_prog, 3 * sizeof(MbProgram))) != cudaSuccess) return bail(e, "cudaMalloc(programs)");
+         if ((e = cudaMemcpy(h->d_prog, h->tree.prog, 3 * sizeof(MbProgram), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(programs)");
+      }
+      // crossover batch sizes: linear in the body count through the measured crossovers of A7 (7 bodies) and H37 (32 bodies),
+      // kernel-only times (profiles/r01h_batch_sweep_graph.jsonl): RNEA 3 k / 8 k, ABA 2 k / 3 k, CRBA 2.5 k / 4 k states.
+      // MECANO_B200_WARP_BELOW overrides all three
+      h->warp_below[MB_RNEA] = 2048 + 192 * P.nb; h->warp_below[MB_ABA] = 1536 + 48 * P.nb; h->warp_below[MB_CRBA] = 2048 + 64 * P.nb;
+      if (const char *e = getenv("MECANO_B200_WARP_BELOW"))
+         h->warp_below[0] = h->warp_below[1] = h->warp_below[2] = atoll(e);
+   }
    *out = h;
    return MECANO_B200_OK;
 }
@@ -304,6 +351,7 @@ void mecano_b200_destroy(mecano_b200_handle *h)
    }
    if (h->d_consts) cudaFree(h->d_consts);
    if (h->d_zero) cudaFree(h->d_zero);
+   if (h->d_prog) cudaFree(h->d_prog);
    for (int i = 0; i < 3; i++)
    {
       if (h->d_ws[i]) cudaFree(h->d_ws[i]);
@@ -328,8 +376,10 @@ int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double 
 int mecano_b200_set_variant(mecano_b200_handle *h, int variant)
 {
    if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
-   if (variant != MECANO_B200_VARIANT_AUTO && variant != MECANO_B200_VARIANT_THREAD)
-      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unsupported variant (the warp-per-state variant is not built in this version)");
+   if (variant != MECANO_B200_VARIANT_AUTO && variant != MECANO_B200_VARIANT_THREAD && variant != MECANO_B200_VARIANT_WARP)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown variant");
+   if (variant == MECANO_B200_VARIANT_WARP && !h->warp_ok)
+      return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body)");
    h->variant = variant;
    return MECANO_B200_OK;
 }
@@ -434,8 +484,25 @@ int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const do
 
 int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info)
 {
-   (void)n_states;
    if (!h || !info || algo < 0 || algo > 2) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   const bool warp = h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n_states > 0 && n_states < h->warp_below[algo]);
+   if (warp)
+   {
+      std::memset(info, 0, sizeof *info);
+      cudaFuncAttributes fa;
+      MB_CUDA(h, mb::warp_kernel_attributes(algo, false, &fa));
+      info->variant = MECANO_B200_VARIANT_WARP;
+      info->block_threads = 128;
+      info->states_per_block = 4;
+      info->regs_per_thread = fa.numRegs;
+      info->local_bytes_per_thread = (int32_t)fa.localSizeBytes;
+      info->static_smem_bytes = (int32_t)fa.sharedSizeBytes;
+      info->sm_count = h->sm_count;
+      info->max_depth = h->tree.prog[algo].max_depth;
+      const double nq = h->tree.nq, nv = h->tree.nv;
+      info->bytes_per_state = algo == MB_CRBA ? 8.0 * (nq + nv * nv) : 8.0 * (nq + 3.0 * nv);
+      return MECANO_B200_OK;
+   }
    const mb::LaunchPlan &p = h->plan[algo];
    const MbProgram &P = h->tree.prog[algo];
    std::memset(info, 0, sizeof *info);

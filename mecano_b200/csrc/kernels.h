@@ -28,6 +28,11 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
 
 cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs &a, const LaunchPlan &plan, cudaStream_t stream);
 
+// warp-per-state variant (warp_kernels.cu): lane = body, trees of up to 32 bodies
+bool warp_variant_supports(const MbProgram &P);
+cudaError_t launch_warp_kernel(int algo, const MbProgram *device_program, const KernelArgs &a, int max_children, int max_ndof, int sm_count, cudaStream_t stream);
+cudaError_t warp_kernel_attributes(int algo, bool fext, cudaFuncAttributes *attr);
+
 // roofline denominators
 cudaError_t measure_fp64_peak(double *tflops);
 cudaError_t measure_hbm_peak(double *gbs);

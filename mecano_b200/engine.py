@@ -71,6 +71,10 @@ class Engine:
     def set_gravity(self, gx, gy, gz):
         check(lib.mecano_b200_set_gravity(self._h, float(gx), float(gy), float(gz)), self._h)
 
+    def set_variant(self, variant):
+        """0 = auto (by batch size), 1 = one thread per state, 2 = one warp per state (trees of up to 32 bodies)."""
+        check(lib.mecano_b200_set_variant(self._h, int(variant)), self._h)
+
     def specialize(self, algos=("rnea", "aba", "crba"), force=False):
         """Compile tree-specialised kernels (mecano_b200_specialize): seconds per algorithm, cached on disk.  Algorithms whose
         unrolled code would not fit the instruction caches keep the generic kernel unless force=True."""

@@ -1,5 +1,5 @@
 """Kernel timing sweep over trees and batch sizes (BASELINE.json config 5): prints one JSON line per (tree, algorithm, n).
-Usage: python scripts/gpu_sweep.py [trees=h37,chain31f,...] [algos=rnea,aba,crba] [n=1048576,...] [out.jsonl]"""
+Usage: python scripts/gpu_sweep.py [trees=h37,chain31f,...] [algos=rnea,aba,crba] [n=1048576,...] [out.jsonl] [variants=thread,warp]"""
 import json
 import os
 import sys
@@ -35,7 +35,8 @@ def main():
     trees = (sys.argv[1] if len(sys.argv) > 1 else "h37").split(",")
     algos = (sys.argv[2] if len(sys.argv) > 2 else "rnea,aba,crba").split(",")
     ns = [int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else "1048576").split(",")]
-    out = open(sys.argv[4], "a") if len(sys.argv) > 4 else None
+    out = open(sys.argv[4], "a") if len(sys.argv) > 4 and sys.argv[4] != "-" else None
+    variants = (sys.argv[5] if len(sys.argv) > 5 else "thread").split(",")
     dev = torch.device("cuda:0")
     for name in trees:
         t = make(name, np.random.default_rng(1))
@@ -52,21 +53,48 @@ def main():
             r = torch.empty_like(tqd)
             M = torch.empty((t.nv * t.nv, n), dtype=torch.float64, device=dev) if "crba" in algos else None
             fns = {"rnea": lambda: e.rnea(tq, tqd, tx, r), "aba": lambda: e.aba(tq, tqd, tx, r), "crba": lambda: e.crba(tq, M)}
-            for a in algos:
+            for a, variant in [(a, v) for a in algos for v in variants]:
+                if variant == "warp" and t.nb > 32:
+                    continue
+                e.set_variant({"auto": 0, "thread": 1, "warp": 2}[variant])
+                if variant != "warp" and os.environ.get("MECANO_B200_SPECIALIZE"):
+                    e.specialize([a])
                 fn = fns[a]
                 for _ in range(3):
                     fn()
                 torch.cuda.synchronize()
                 reps = 10
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-                ev[0].record()
-                for i in range(reps):
-                    fn()
-                    ev[i + 1].record()
-                torch.cuda.synchronize()
-                ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]))
-                info = e.kernel_info({"rnea": 0, "aba": 1, "crba": 2}[a])
-                line = {"tree": name, "nb": t.nb, "nv": t.nv, "algo": a, "n": n, "ms": ms, "states_per_s": n / (ms * 1e-3),
+                if os.environ.get("MECANO_B200_SWEEP_GRAPH"):
+                    # launch-latency regime: time the kernels alone by replaying a CUDA graph of `per` back-to-back launches
+                    per = 20
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        fn()
+                        gr = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(gr, stream=side):
+                            for _ in range(per):
+                                fn()
+                    torch.cuda.current_stream().wait_stream(side)
+                    gr.replay()
+                    torch.cuda.synchronize()
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+                    ev[0].record()
+                    for i in range(reps):
+                        gr.replay()
+                        ev[i + 1].record()
+                    torch.cuda.synchronize()
+                    ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)])) / per
+                else:
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+                    ev[0].record()
+                    for i in range(reps):
+                        fn()
+                        ev[i + 1].record()
+                    torch.cuda.synchronize()
+                    ms = float(np.median([ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]))
+                info = e.kernel_info({"rnea": 0, "aba": 1, "crba": 2}[a], n)
+                line = {"tree": name, "nb": t.nb, "nv": t.nv, "algo": a, "variant": variant, "timing": "graph" if os.environ.get("MECANO_B200_SWEEP_GRAPH") else "launch", "specialized": info["specialized"], "n": n, "ms": ms, "states_per_s": n / (ms * 1e-3),
                         "ns_per_state_body": ms * 1e6 / n / t.nb, "gbs": info["bytes_per_state"] * n / (ms * 1e-3) / 1e9,
                         "block": info["block_threads"], "regs": info["regs_per_thread"], "smem": info["dynamic_smem_bytes"],
                         "blocks_per_sm": info["blocks_per_sm"], "depth": info["max_depth"]}

@@ -60,13 +60,19 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", ["thread", "warp"])
 @pytest.mark.parametrize("idx", range(len(CASES)))
-def test_kernels_match_oracle(torch_dev, idx):
+def test_kernels_match_oracle(torch_dev, idx, variant):
     import mecano_b200 as mb
 
     torch, dev = torch_dev
     name, kw = CASES[idx]
     s, t = build(**kw)
+    if variant == "warp" and t.nb > 32:
+        # one lane per body: larger trees are refused, never silently rerouted
+        with pytest.raises(mb.MecanoB200Error):
+            mb.InverseDynamicsCalculator(s).setKernelVariant("warp")
+        return
     rng = np.random.default_rng(1000 + idx)
     g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
     o = ol.Oracle(t, gravity=g)
@@ -76,8 +82,9 @@ def test_kernels_match_oracle(torch_dev, idx):
     tq, tqd, tqdd, ttau, tf = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, tau, fext))
     nv = t.nv
 
-    ident = mb.InverseDynamicsCalculator(s)
+    ident = mb.InverseDynamicsCalculator(s).setKernelVariant(variant)
     ident.setGravitationalAcceleration(g)
+    assert ident.kernelInfo(n)["variant"] == {"thread": 1, "warp": 2}[variant]
     assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd)) < TOL, name
     ident.setExternalWrenches(tf)
     assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd, fext)) < TOL, name
@@ -87,13 +94,13 @@ def test_kernels_match_oracle(torch_dev, idx):
     ident.setConsiderJointAccelerations(False)
     assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd, flags=3)) < TOL, name
 
-    fdyn = mb.ForwardDynamicsCalculator(s)
+    fdyn = mb.ForwardDynamicsCalculator(s).setKernelVariant(variant)
     fdyn.setGravitationalAcceleration(*g)
     assert rel(fdyn.compute(tq, tqd, ttau).cpu().numpy(), o.aba_batch(q, qd, tau)) < TOL, name
     fdyn.setExternalWrenches(tf)
     assert rel(fdyn.compute(tq, tqd, ttau).cpu().numpy(), o.aba_batch(q, qd, tau, fext)) < TOL, name
 
-    crba = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant(variant)
     Mo = o.crba_batch(q)
     M = crba.getMassMatrix(tq, torch.full((nv * nv, n), float("nan"), dtype=torch.float64, device=dev))
     assert not torch.isnan(M).any(), "every entry of the dense matrix must be written"
