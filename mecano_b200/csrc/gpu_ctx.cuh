@@ -20,7 +20,10 @@ namespace mb
 // thread's stack live in TMEM instead: a warp owns the 32 lanes of its lane quarter (warp % 4) and a private range of
 // columns, a double2 is four 32-bit columns, lane = thread: tcgen05.st/ld.32x32b.x4 (STTM/LDTM, scoreboarded like any
 // load).  Slots >= TM stay in shared memory.  scripts/microbench/tmem_stack.cu measures the round trip.
-template <int BLOCK, int TM> struct GpuCtx2
+// ROWS: rows of the prefetch ring per stage -- RNEA (q, qd, qdd), ABA (q | tau, qd: an op never needs q and tau together), CRBA (q)
+__host__ __device__ constexpr int ring_rows(int algo) { return algo == MB_RNEA ? 3 : (algo == MB_ABA ? 2 : 1); }
+
+template <int BLOCK, int TM, int ROWS> struct GpuCtx2
 {
    const char *qb, *qdb, *xb, *fb;
    char *ob;
@@ -153,17 +156,17 @@ template <int BLOCK, int TM> struct GpuCtx2
    // mask: 1 = q[cfg], 2 = qd[dof], 4 = x[dof]
    __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, int mask) const
    {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(mb_smem + ring0 + stage * 3 * BLOCK);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(mb_smem + ring0 + stage * ROWS * BLOCK);
       if (mask & 1)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
       if (mask & 2)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
       if (mask & 4)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 2 * BLOCK * 8), "l"(xb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(xb + (unsigned long long)(unsigned)dof * ld8) : "memory");
    }
    __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
    template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-   __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_smem[ring0 + (stage * 3 + j) * BLOCK]; }
+   __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_smem[ring0 + (stage * ROWS + ((j == 2 && ROWS < 3) ? 0 : j)) * BLOCK]; }
 };
 
 // columns of tensor memory one warp owns when BLOCK / 32 warps share the four lane quarters
@@ -191,7 +194,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    if (TM > 0)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
    double aux[AUXN > 0 ? AUXN : 1];
-   GpuCtx2<BLOCK, TM> c2;
+   GpuCtx2<BLOCK, TM, ring_rows(ALGO)> c2;
    c2.ld8 = (unsigned)(a.ld * 8);
    c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
    c2.ring3_0 = c2.stk0;
@@ -218,7 +221,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
    {
       long long s = tile * BLOCK + threadIdx.x;
-      if (GpuCtx2<BLOCK, TM>::kClamp)
+      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO)>::kClamp)
       {
          // tcgen05.ld/st are warp-collective (.sync.aligned): padding lanes run a clamped state and store nothing
          c2.active = s < a.n;

@@ -31,13 +31,14 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    const int ncst = P.nb * MB_CONST_STRIDE;
    for (int i = threadIdx.x; i < ncst; i += BLOCK)
       mb_smem[i] = a.consts[i];
-   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, P.stack2, [&](GpuCtx2<BLOCK, TM> &c2) {
+   using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
+   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, P.stack2, [&](Ctx &c2) {
       if constexpr (ALGO == MB_RNEA)
-         rnea_state<double, GpuCtx2<BLOCK, TM>, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+         rnea_state<double, Ctx, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
       else if constexpr (ALGO == MB_ABA)
-         aba_state<double, GpuCtx2<BLOCK, TM>, FEXT>(P, c2, a.grav);
+         aba_state<double, Ctx, FEXT>(P, c2, a.grav);
       else
-         crba_state<double, GpuCtx2<BLOCK, TM>>(P, c2);
+         crba_state<double, Ctx>(P, c2);
    });
 }
 
@@ -95,7 +96,7 @@ size_t smem_bytes(int algo, const MbProgram &P, int block, int tm)
 {
    const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
    const int smem_slots = std::max(P.stack2 - tm, algo == MB_ABA ? 20 : 0);
-   size_t bytes = sizeof(double) * ((size_t)ncst + (2 * (size_t)smem_slots + 3 * MB_PF_STAGES) * block);
+   size_t bytes = sizeof(double) * ((size_t)ncst + (2 * (size_t)smem_slots + ring_rows(algo) * MB_PF_STAGES) * block);
    // a block with a TMEM stack allocates all 512 columns: keep it alone on its SM (a second block would spin in tcgen05.alloc)
    if (tm > 0)
       bytes = std::max<size_t>(bytes, 120 * 1024);
@@ -163,7 +164,10 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       // work area only competes if nothing else fits
       const int auxn = algo == MB_RNEA ? (kCfg[cfg].cls ? kRnaAux1 : kRnaAux0) : (algo == MB_ABA ? (kCfg[cfg].cls ? kAbaAux1 : kAbaAux0) : (kCfg[cfg].cls ? kCrbAux1 : kCrbAux0));
       const bool spills = (long)fa.localSizeBytes > 8l * auxn + 128;
-      const int score = spills && forced < 0 ? 1 : nblk * b;
+      // warps that do not split evenly over the four sub-partitions lose more than they bring (ABA 320 threads: 3.44 ms,
+      // 256 threads: 2.23 ms; profiles/r01i_cfg_sweep.jsonl): such block sizes only compete if nothing else fits
+      const bool uneven = ((nblk * b) % 128) != 0 && nblk * b > 128;
+      const int score = (spills || uneven) && forced < 0 ? 1 + (uneven ? 1 : 0) : nblk * b;
       // prefer more resident states; on ties the first configuration in the table wins
       if (nblk > 0 && score > best_threads)
       {
