@@ -157,3 +157,31 @@ def test_slices_cover_the_batch():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         sharding.slice_for_rank(10, 2, 2)
+
+
+def test_tree_specialised_source_generates_and_compiles_without_a_gpu():
+    """mecano_b200_generate_source / mecano_b200_jit_check: the run-time compiled path (specialize.cpp + NVRTC) for a
+    7-joint arm with a floating base; no device involved."""
+    e = mb.RigidBody("elevator")
+    base = mb.MultiBodySystemRandomTools.nextFloatingBase(5, e).getSuccessor()
+    mb.MultiBodySystemRandomTools.nextOneDoFJointChain(6, base, 5, 0.4)
+    s = mb.MultiBodySystem.toMultiBodySystemBasics(e)
+    need = ctypes.c_int64()
+    assert _capi.lib.mecano_b200_generate_source(s.tables(), 0, 256, 0, None, 0, ctypes.byref(need)) == 0
+    buf = ctypes.create_string_buffer(need.value)
+    assert _capi.lib.mecano_b200_generate_source(s.tables(), 0, 256, 0, buf, need.value, None) == 0
+    src = buf.value.decode()
+    assert "mb_spec_kernel" in src and src.count("rnea_op<") == 2 * s.getNumberOfJoints()  # one DESCEND + one ASCEND per joint
+    for algo, block, tm in ((0, 512, 32), (1, 256, 0)):
+        n = ctypes.c_int64()
+        rc = _capi.lib.mecano_b200_jit_check(s.tables(), algo, block, tm, ctypes.byref(n))
+        if rc != 0 and b"libnvrtc not found" in _capi.lib.mecano_b200_last_error(None):
+            pytest.skip("NVRTC is not installed on this machine")
+        assert rc == 0, _capi.lib.mecano_b200_last_error(None).decode()
+        assert n.value > 10000
+    # unknown algorithm
+    assert _capi.lib.mecano_b200_jit_check(s.tables(), 7, 256, 0, None) == _capi_err("INVALID_ARGUMENT")
+
+
+def _capi_err(name):
+    return {"INVALID_ARGUMENT": -1, "UNSUPPORTED_TOPOLOGY": -2, "SHAPE": -3, "NO_DEVICE": -4, "TOO_LARGE": -5, "JIT": -6}[name]
