@@ -53,8 +53,8 @@ MB_HD void aba_descend_1dof(Ctx &c, const MbOp2 o, SvT<T> &v, AbaPipe<T> &pp, T 
    pp.lc = pp.c;
    if (!(o.flags & MB2_LEAF))
    {
-      stk_st_sv<T>(c, o.slot, v);
-      c.stk_st2(o.slot, 3, pp.s, pp.c);
+      c.acc_st(o.slot, o.wslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
+      c.jp_st2(o.slot, o.nslot, 0, pp.s, pp.c);
    }
 }
 
@@ -64,16 +64,16 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
 {
    if (SC)
       mb_sincos(pp.mq, &ns, &nc);
-   const T *C = c.cst(o.body);
+   const auto C = c.cst(o.body);
    T s = pp.ls, cs = pp.lc;
    SvT<T> vb = v;
    if (!(o.flags & MB2_LEAF))
    {
-      vb = stk_ld_sv<T>(c, o.slot);
-      c.stk_ld2(o.slot, 3, s, cs);
+      c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
+      c.jp_ld2(o.slot, o.nslot, 0, s, cs);
    }
    const T qd = pp.qd, tau = pp.x;
-   const RbiT<T> I = ld_rbi(C);
+   const RbiT<T> I = ld_rbi<T>(C);
    SvT<T> pA = cross_force(vb, mul(I, vb));
    if (FEXT)
       pA = pA - external_wrench<T>(c, ext, C);
@@ -156,17 +156,18 @@ template <class T, class Ctx> MB_HD void aba_descend_6dof(Ctx &c, const MbOp2 o,
    const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
    const SvT<T> vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
    v = motion_to_child(X, v) + vj;
-   stk_st_sv<T>(c, o.slot, v);
+   c.acc_st(o.slot, o.wslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))
-      stk_st_xf<T>(c, o.slot + 3, X);
+      jp_st_xf<T>(c, o.slot, o.nslot, X);
 }
 
 template <class T, class Ctx, bool FEXT>
 MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> &pacc)
 {
-   const T *C = c.cst(o.body);
-   const SvT<T> vb = stk_ld_sv<T>(c, o.slot);
-   const RbiT<T> I = ld_rbi(C);
+   const auto C = c.cst(o.body);
+   SvT<T> vb;
+   c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
+   const RbiT<T> I = ld_rbi<T>(C);
    SvT<T> pA = cross_force(vb, mul(I, vb));
    if (FEXT)
       pA = pA - external_wrench<T>(c, ext, C);
@@ -186,7 +187,7 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
    c.rec_st2(r + 3, (T)0, (T)0);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
-      const XfT<T> X = stk_ld_xf<T>(c, o.slot + 3);
+      const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
       const SvT<T> Pp = force_to_parent(X, tau6);
       if (o.flags & MB2_FIRST_CHILD)
       {
@@ -293,7 +294,7 @@ MB_HD void aba_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int 
       if (o.flags & MB2_ROOT_PARENT)
          v = sv_zero<T>();
       else
-         v = stk_ld_sv<T>(c, o.pslot);
+         c.acc_ld(o.pslot, o.pwslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
    }
    T ns = pp.mq, nc = (T)1;
    switch (o.code & 0xfu)
@@ -451,7 +452,7 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
       if (o.flags & MB2_ROOT_PARENT)
          v = sv_zero<T>();
       else
-         v = stk_ld_sv<T>(c, o.pslot);
+         c.acc_ld(o.pslot, o.pwslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
    }
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;

@@ -407,6 +407,8 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
       if (algo == MB_RNEA) { opt.block = 512; opt.tm = 32; }
       else { opt.block = 256; opt.tm = 0; }
       spec_cfg_from_env(algo, opt);
+      if (!mb_tm_fits(algo, P, opt.tm))
+         opt.tm = 0; // the wide stack area of a deep tree does not fit the TMEM columns of one warp: shared memory only
       if (opt.tm * 4 > (512 / ((opt.block + 127) / 128) & ~3))
          return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "MECANO_B200_SPEC_CFG: TMEM slots exceed the columns of one warp");
       std::string err;
@@ -417,6 +419,8 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
          mb::SpecOptions o2 = opt;
          o2.block = b;
          o2.tm = opt.tm > 0 ? std::min(opt.tm * (opt.block / b), 128) : 0;
+         if (!mb_tm_fits(algo, P, o2.tm))
+            o2.tm = 0;
          int max_optin = 0;
          cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
          if (mb::spec_smem_bytes(algo, P, o2.block, o2.tm) + 1024 > (size_t)max_optin)

@@ -28,10 +28,11 @@ template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
 }
 
 // F expressed in the parent of a 1-DoF joint: (R0 Rz(q), p0) applied to a force vector without forming the matrix
-template <class T, bool REV> MB_HD SvT<T> force_up_1dof(const T *C, T s, T cs, const SvT<T> &f)
+template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T s, T cs, const SvT<T> &f)
 {
-   const M3T<T> R0 = ld_m3(C + MB_C_R);
-   V3T<T> p = ld_v3(C + MB_C_P);
+   M3T<T> R0;
+   V3T<T> p;
+   ld_xf0<T>(C, R0, p);
    SvT<T> g = f, r;
    if (REV)
    {
@@ -78,7 +79,7 @@ template <class T, class Ctx> MB_HD void crba_walk(const MbProgram &P, Ctx &c, i
    MbWalk w = P.walk[b];
    while (!(w.flags & 1u)) // until the parent is the root body
    {
-      const T *C = c.cst(b);
+      const auto C = c.cst(b);
       if (w.jtype == MB_REVOLUTE)
          F = force_up_1dof<T, true>(C, s, cs, F);
       else if (w.jtype == MB_PRISMATIC)
@@ -138,7 +139,7 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
       if (o.code & MB2_SC)
          mb_sincos(mq, &ns, &nc);
       const int jt = MB2_JT(o.code);
-      const T *C = c.cst(o.body);
+      const auto C = c.cst(o.body);
       if (!(o.code & MB2_ASCEND))
       {
          // ---- joint transform of body i (the frame update of updateFramesRecursively())
@@ -155,7 +156,7 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
       else
       {
          // ---- composite inertia of the subtree, about this joint frame (:648-661)
-         RbiT<T> Ic = ld_rbi(C);
+         RbiT<T> Ic = ld_rbi<T>(C);
          if (!(o.flags & MB2_LEAF))
             Ic = Ic + acc;
          T js = ls, jc = lc;

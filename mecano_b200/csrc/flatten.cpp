@@ -118,8 +118,9 @@ int slot2_size(int algo, int jtype, bool root_parent)
 void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
 {
    const int nb = P.nb;
-   std::vector<int> slot2(nb, 0);
+   std::vector<int> slot2(nb, 0), wslot(nb, 0), nslot(nb, 0);
    P.stack2 = 1;
+   P.wstack2 = P.nstack2 = 0;
    for (int i = 0; i < nb; i++)
    {
       const MbBody &B = P.body[i];
@@ -128,11 +129,23 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       {
          const MbBody &Bp = P.body[B.parent];
          s = slot2[B.parent] + slot2_size(algo, Bp.jtype, Bp.parent < 0);
+         if (algo != MB_CRBA)
+         {
+            wslot[i] = wslot[B.parent] + 3;
+            nslot[i] = nslot[B.parent] + slot2_size(algo, Bp.jtype, Bp.parent < 0) - 3;
+         }
       }
       slot2[i] = s;
       // leaves keep their data in registers, except SixDoF joints which always use their slot
       if (nchild[i] > 0 || B.jtype == MB_SIXDOF)
+      {
          P.stack2 = std::max(P.stack2, s + slot2_size(algo, B.jtype, B.parent < 0));
+         if (algo != MB_CRBA)
+         {
+            P.wstack2 = std::max(P.wstack2, wslot[i] + 3);
+            P.nstack2 = std::max(P.nstack2, nslot[i] + slot2_size(algo, B.jtype, B.parent < 0) - 3);
+         }
+      }
    }
    if (algo == MB_ABA)
       P.stack2 = std::max(P.stack2, 20); // pass three overlays a 4-stage x 5-row ring of double2 on the stack area
@@ -152,6 +165,9 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       o.pslot = (uint16_t)(B.parent >= 0 ? slot2[B.parent] : 0);
       o.aux = (uint16_t)(B.aux >= 0 ? B.aux : 0);
       o.paux = (uint16_t)(B.parent >= 0 && P.body[B.parent].aux >= 0 ? P.body[B.parent].aux : 0);
+      o.wslot = (uint16_t)wslot[i];
+      o.pwslot = (uint16_t)(B.parent >= 0 ? wslot[B.parent] : 0);
+      o.nslot = (uint16_t)nslot[i];
    }
    for (int i = 0; i < nb; i++)
    {

@@ -11,6 +11,16 @@ extern __shared__ double mb_smem[];
 
 namespace mb
 {
+// 32-bit shared-space address of the dynamic shared memory, taken from the symbol: a constant in SASS.  Going through
+// __cvta_generic_to_shared() instead makes the compiler derive every LDS/STS address from the generic window base
+// (S2UR SR_CgaCtaId + 3 uniform instructions, re-materialised several times per op).
+__device__ __forceinline__ unsigned mb_smem_u32()
+{
+   unsigned a;
+   asm("mov.u32 %0, mb_smem;" : "=r"(a));
+   return a;
+}
+
 // BLOCK (threads per block = stack stride) is a compile-time constant so that stack addresses are base + immediate;
 // shared memory is addressed through the mb_smem symbol so that the compiler emits LDS/STS (a pointer kept in a
 // struct degrades to generic LD/ST).
@@ -23,60 +33,124 @@ namespace mb
 // ROWS: rows of the prefetch ring per stage -- RNEA (q, qd, qdd), ABA (q | tau, qd: an op never needs q and tau together), CRBA (q)
 __host__ __device__ constexpr int ring_rows(int algo) { return algo == MB_RNEA ? 3 : (algo == MB_ABA ? 2 : 1); }
 
+// handle of a constant record in shared memory (Ctx::cst): 32-bit shared address of the record
+struct SmemCst
+{
+   unsigned a;
+};
+__device__ __forceinline__ void cst_ld2(const SmemCst C, int i2, double &a, double &b)
+{
+   // not volatile: the records are read-only once staged, so the loads may be scheduled, merged and dropped freely
+   asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(C.a + 16u * (unsigned)i2));
+}
+
+// All shared-memory traffic of the per-state routines goes through ld/st.shared with explicit 32-bit addresses
+// (base register + immediate in SASS).  The accesses to per-thread areas are `asm volatile` without a memory clobber:
+// they stay ordered among themselves (and with the cp.async / tcgen05 statements), which is all a private stack needs.
+__device__ __forceinline__ void mb_lds2(unsigned addr, double &a, double &b) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr)); }
+__device__ __forceinline__ void mb_sts2(unsigned addr, double a, double b) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b)); }
+__device__ __forceinline__ double mb_lds1(unsigned addr)
+{
+   double a;
+   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr));
+   return a;
+}
+// row `r` of a DoF-major buffer: base + r * ld8 as one IMAD.WIDE.U32
+__device__ __forceinline__ const char *mb_row(const char *base, unsigned r, unsigned ld8)
+{
+   unsigned long long p;
+   asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(r), "r"(ld8), "l"((unsigned long long)base));
+   return (const char *)p;
+}
+
+__device__ __forceinline__ double mb_ldg(const char *p)
+{
+   double v;
+   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+   return v;
+}
+__device__ __forceinline__ void mb_stg(const char *p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void mb_stg_cs(const char *p, double v) { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+
 template <int BLOCK, int TM, int ROWS> struct GpuCtx2
 {
    const char *qb, *qdb, *xb, *fb;
    char *ob;
    unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
-   int stk0;     // index (double2 units) of shared-memory stack slot TM of this thread
-   unsigned tm0; // TMEM address (lane quarter << 16 | first column) of stack slot 0 of this warp
-   // warp-collective tcgen05.ld/st and the block barriers of specialised kernels need every thread to run every op
+   unsigned sb;  // shared address of this thread's element of shared-memory stack slot 0
+   unsigned rb;  // shared address of this thread's element of stage 0, row 0 of the prefetch ring
+   unsigned cb;  // shared address of the constant records
+   unsigned tm0; // TMEM address (lane quarter << 16 | first column) of wide slot 0 of this warp
+   // warp-collective tcgen05.ld/st and the block barriers of specialised kernels need every thread to run every op: the
+   // padding lanes of the last tile run the last state again and store the same values to the same addresses
 #if defined(MB_SPEC)
    static constexpr bool kClamp = true;
 #else
    static constexpr bool kClamp = TM > 0;
 #endif
-   bool active;  // false for the padding lanes of the last tile (they compute on a clamped state and store nothing)
+   bool active;  // false for the padding lanes of the last tile (CRBA: they store nothing)
    double *aux; // local memory
 
-   __device__ __forceinline__ double ld_q(int r) const { return __ldg((const double *)(qb + (unsigned long long)(unsigned)r * ld8)); }
-   __device__ __forceinline__ double ld_qd(int r) const { return __ldg((const double *)(qdb + (unsigned long long)(unsigned)r * ld8)); }
-   __device__ __forceinline__ double ld_x(int r) const { return __ldg((const double *)(xb + (unsigned long long)(unsigned)r * ld8)); }
-   __device__ __forceinline__ double ld_fext(int b, int k) const { return __ldg((const double *)(fb + (unsigned long long)(unsigned)(6 * b + k) * ld8)); }
-   __device__ __forceinline__ void st_out(int r, double v)
+   __device__ __forceinline__ double ld_q(int r) const { return mb_ldg(mb_row(qb, (unsigned)r, ld8)); }
+   __device__ __forceinline__ double ld_qd(int r) const { return mb_ldg(mb_row(qdb, (unsigned)r, ld8)); }
+   __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(mb_row(xb, (unsigned)r, ld8)); }
+   __device__ __forceinline__ double ld_fext(int b, int k) const { return mb_ldg(mb_row(fb, (unsigned)(6 * b + k), ld8)); }
+   __device__ __forceinline__ void st_out(int r, double v) { mb_stg(mb_row(ob, (unsigned)r, ld8), v); }
+   // ---- general stack access (CRBA; shared memory)
+   __device__ __forceinline__ void stk_ld2(int slot2, int j, double &a, double &b) const { mb_lds2(sb + (unsigned)((slot2 + j) * (BLOCK * 16)), a, b); }
+   __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b) { mb_sts2(sb + (unsigned)((slot2 + j) * (BLOCK * 16)), a, b); }
+   // ---- split stack access (RNEA / ABA, MbOp2::wslot / nslot).  Tensor memory as stack space: these kernels issue no
+   // tcgen05.mma, so the 256 KB of TMEM per SM would sit idle while shared memory caps the resident states.  With TM > 0
+   // the wide area (the 6-vectors) lives in TMEM: a warp owns the 32 lanes of its lane quarter (warp % 4) and a private
+   // range of columns, a double is two 32-bit columns, lane = thread: tcgen05.st/ld.32x32b.x2 (STTM/LDTM on aligned
+   // register pairs, i.e. on the doubles where they are; scoreboarded like any load).  The narrow area stays in shared memory.
+   __device__ __forceinline__ void acc_ld(int slot2, int wslot, double &x0, double &x1, double &x2, double &x3, double &x4, double &x5) const
    {
-      if (!kClamp || active)
-         *(double *)(ob + (unsigned long long)(unsigned)r * ld8) = v;
-   }
-   __device__ __forceinline__ void stk_ld2(int slot2, int j, double &a, double &b) const
-   {
-      const int sl = slot2 + j;
-      if (TM > 0 && sl < TM)
+      if (TM > 0)
       {
-         int r0, r1, r2, r3;
-         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(tm0 + 4u * (unsigned)sl) : "memory");
-         asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3)::"memory");
-         a = __hiloint2double(r1, r0);
-         b = __hiloint2double(r3, r2);
+         const unsigned t = tm0 + 4u * (unsigned)wslot;
+         unsigned r[12];
+#pragma unroll
+         for (int i = 0; i < 6; i++)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[2 * i]), "=r"(r[2 * i + 1]) : "r"(t + 2u * i));
+         asm volatile("tcgen05.wait::ld.sync.aligned;"
+                      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]));
+         x0 = __hiloint2double(r[1], r[0]); x1 = __hiloint2double(r[3], r[2]); x2 = __hiloint2double(r[5], r[4]);
+         x3 = __hiloint2double(r[7], r[6]); x4 = __hiloint2double(r[9], r[8]); x5 = __hiloint2double(r[11], r[10]);
       }
       else
       {
-         const double2 t = reinterpret_cast<const double2 *>(mb_smem)[stk0 + (sl - TM) * BLOCK];
-         a = t.x;
-         b = t.y;
+         const unsigned t = sb + (unsigned)(slot2 * (BLOCK * 16));
+         mb_lds2(t, x0, x1);
+         mb_lds2(t + BLOCK * 16, x2, x3);
+         mb_lds2(t + 2 * BLOCK * 16, x4, x5);
       }
    }
-   __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b)
+   __device__ __forceinline__ void acc_st(int slot2, int wslot, double x0, double x1, double x2, double x3, double x4, double x5)
    {
-      const int sl = slot2 + j;
-      if (TM > 0 && sl < TM)
+      if (TM > 0)
       {
-         asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tm0 + 4u * (unsigned)sl), "r"(__double2loint(a)), "r"(__double2hiint(a)),
-                      "r"(__double2loint(b)), "r"(__double2hiint(b))
-                      : "memory");
+         const unsigned t = tm0 + 4u * (unsigned)wslot;
+         const double x[6] = {x0, x1, x2, x3, x4, x5};
+#pragma unroll
+         for (int i = 0; i < 6; i++)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t + 2u * i), "r"(__double2loint(x[i])), "r"(__double2hiint(x[i])));
       }
       else
-         reinterpret_cast<double2 *>(mb_smem)[stk0 + (sl - TM) * BLOCK] = make_double2(a, b);
+      {
+         const unsigned t = sb + (unsigned)(slot2 * (BLOCK * 16));
+         mb_sts2(t, x0, x1);
+         mb_sts2(t + BLOCK * 16, x2, x3);
+         mb_sts2(t + 2 * BLOCK * 16, x4, x5);
+      }
+   }
+   __device__ __forceinline__ void jp_ld2(int slot2, int nslot, int j, double &a, double &b) const
+   {
+      mb_lds2(sb + (unsigned)((TM > 0 ? nslot + j : slot2 + 3 + j) * (BLOCK * 16)), a, b);
+   }
+   __device__ __forceinline__ void jp_st2(int slot2, int nslot, int j, double a, double b)
+   {
+      mb_sts2(sb + (unsigned)((TM > 0 ? nslot + j : slot2 + 3 + j) * (BLOCK * 16)), a, b);
    }
    // Tree-specialised kernels are straight-line code far larger than the instruction caches (L0 6 KB, L1.5 32 KB): left
    // alone, the warps of a block drift apart and each streams its own copy of the code from L2 (no_instructions was 46 %
@@ -101,33 +175,27 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    // read back in pass three through the ring below with cp.async.cg (L2, the coherence point of the earlier stores)
    double2 *wsb;       // workspace + column of this thread
    long long ws_ld;
-   int ring3_0;        // index (double2) of this thread's element of stage 0, row 0 of the pass-three ring
    __device__ __forceinline__ void rec_st2(int i2, double a, double b) { wsb[i2 * ws_ld] = make_double2(a, b); }
    // pass-three ring: [stage][(q, qd) | rec0 .. rec3][BLOCK] double2, overlaid on the (then idle) stack area
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
    {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<double2 *>(mb_smem) + ring3_0 + stage * 5 * BLOCK);
+      const unsigned dst = sb + (unsigned)(stage * (5 * BLOCK * 16));
       if (mask & 1)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
       if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(mb_row(qdb, (unsigned)dof, ld8)) : "memory");
       const double2 *src = wsb + rec2 * ws_ld;
 #pragma unroll
       for (int j = 0; j < 4; j++)
          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(src + j * ws_ld) : "memory");
    }
-   __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const
-   {
-      const double2 t = reinterpret_cast<const double2 *>(mb_smem)[ring3_0 + (stage * 5 + row) * BLOCK];
-      a = t.x;
-      b = t.y;
-   }
+   __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const { mb_lds2(sb + (unsigned)((stage * 5 + row) * (BLOCK * 16)), a, b); }
    __device__ __forceinline__ void pass_fence() const { __threadfence(); }
 #if defined(MB_SPEC)
    // tree-specialised kernels: the constant records are literals in the generated source (constant-bank operands)
    __device__ __forceinline__ const double *cst(int b) const { return mb_spec_consts + b * MB_CONST_STRIDE; }
 #else
-   __device__ __forceinline__ const double *cst(int b) const { return mb_smem + b * MB_CONST_STRIDE; }
+   __device__ __forceinline__ SmemCst cst(int b) const { return SmemCst{cb + (unsigned)(b * (MB_CONST_STRIDE * 8))}; }
 #endif
    // mass matrix: entry e = row * nv + col lives at mbase + e * mstride (entry-major: mstride = ld8; state-major: 8)
    char *mbase;
@@ -139,7 +207,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    __device__ __forceinline__ void st_M(int e, double v) const
    {
       if (!kClamp || active)
-         __stcs((double *)(mbase + (unsigned long long)(unsigned)e * mstride), v);
+         mb_stg_cs(mb_row(mbase, (unsigned)e, mstride), v);
    }
    __device__ __forceinline__ void zero_fill() const
    {
@@ -152,21 +220,20 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       }
    }
    // prefetch ring: [stage][q | qd | x][BLOCK] doubles in shared memory, filled by cp.async (LDGSTS)
-   int ring0; // index (doubles) of this thread's element of stage 0, row 0
    // mask: 1 = q[cfg], 2 = qd[dof], 4 = x[dof]
    __device__ __forceinline__ void pf_issue(int stage, int cfg, int dof, int mask) const
    {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(mb_smem + ring0 + stage * ROWS * BLOCK);
+      const unsigned dst = rb + (unsigned)(stage * (ROWS * BLOCK * 8));
       if (mask & 1)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(qb + (unsigned long long)(unsigned)cfg * ld8) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
       if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(qdb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(mb_row(qdb, (unsigned)dof, ld8)) : "memory");
       if (mask & 4)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(xb + (unsigned long long)(unsigned)dof * ld8) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(mb_row(xb, (unsigned)dof, ld8)) : "memory");
    }
    __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
    template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-   __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_smem[ring0 + (stage * ROWS + ((j == 2 && ROWS < 3) ? 0 : j)) * BLOCK]; }
+   __device__ __forceinline__ double pf_ld(int stage, int j) const { return mb_lds1(rb + (unsigned)((stage * ROWS + ((j == 2 && ROWS < 3) ? 0 : j)) * (BLOCK * 8))); }
 };
 
 // columns of tensor memory one warp owns when BLOCK / 32 warps share the four lane quarters
@@ -176,9 +243,10 @@ __host__ __device__ constexpr int tm_warp_cols(int block) { return (512 / ((bloc
 // state.  ncst = doubles of constant records staged at the front of shared memory (0 for specialised kernels),
 // stack2 = stack slots (double2) per state.
 template <int ALGO, bool STATE_MAJOR, int BLOCK, int AUXN, int TM, class Body>
-__device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int ncst, const int stack2, Body body)
+__device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int ncst, const int smem_slots, Body body)
 {
    static_assert(TM * 4 <= tm_warp_cols(BLOCK), "TMEM stack slots exceed the columns of one warp");
+   static_assert(TM == 0 || ALGO != MB_CRBA, "CRBA keeps its (narrow-only) stack in shared memory");
    __shared__ unsigned tm_base_s;
    if (TM > 0)
    {
@@ -196,16 +264,21 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    double aux[AUXN > 0 ? AUXN : 1];
    GpuCtx2<BLOCK, TM, ring_rows(ALGO)> c2;
    c2.ld8 = (unsigned)(a.ld * 8);
-   c2.stk0 = (((ncst + 1) & ~1) >> 1) + threadIdx.x;
-   c2.ring3_0 = c2.stk0;
-   // shared-memory stack slots: what does not fit in TMEM; ABA overlays its pass-three ring (20 double2) on them
-   const int smem_slots = max(stack2 - TM, ALGO == MB_ABA ? 20 : 0);
-   c2.ring0 = ((ncst + 1) & ~1) + 2 * smem_slots * BLOCK + threadIdx.x;
+   // mb_smem_u32() names the symbol in inline PTX only: one (never executed) C++ reference makes sure it is declared in
+   // the module even when nothing else touches it (tree-specialised kernels stage no constant records)
+   if (a.n < 0)
+      mb_smem[0] = 0.0;
+   // [constant records | stack: smem_slots x BLOCK double2 (mb_smem_stack_slots) | prefetch ring]
+   c2.cb = mb_smem_u32();
+   c2.sb = c2.cb + 8u * (unsigned)((ncst + 1) & ~1) + 16u * threadIdx.x;
+   c2.rb = c2.cb + 8u * (unsigned)(((ncst + 1) & ~1) + 2 * smem_slots * BLOCK) + 8u * threadIdx.x;
    c2.tm0 = 0;
    if (TM > 0)
    {
       const unsigned warp = threadIdx.x >> 5;
       c2.tm0 = tm_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (unsigned)tm_warp_cols(BLOCK);
+      // warp-uniform by construction; the shuffle lets ptxas keep it (and the per-op addresses derived from it) in uniform registers
+      c2.tm0 = __shfl_sync(0xffffffffu, c2.tm0, 0);
    }
    c2.active = true;
    c2.aux = aux;

@@ -7,6 +7,8 @@
 //   void st_out(row, T)                          tau (RNEA) / qdd (ABA)
 //   void st_M(row, col, T)                       mass-matrix entry (CRBA)
 //   void stk_ld2(slot2, j, T&, T&) / stk_st2     per-state stack of double2 (shared memory on the GPU)
+//   void acc_ld(slot2, wslot, T& x6) / acc_st    RNEA / ABA: the first three double2 of a slot ("wide" area, MbOp2::wslot)
+//   void jp_ld2(slot2, nslot, j, T&, T&) / jp_st2  RNEA / ABA: the rest of a slot ("narrow" area, MbOp2::nslot), j = 0, 1, ..
 //   T    aux_ld(i) / aux_st, rec_ld / rec_st     per-state branch-save and record areas (local memory)
 //   const T* cst(body)                           constant record of a body (shared memory on the GPU)
 #pragma once
@@ -140,22 +142,47 @@ template <class T> MB_HD M3T<T> ld_m3(const T *p)
    return r;
 }
 template <class T> MB_HD V3T<T> ld_v3(const T *p) { return v3<T>(p[0], p[1], p[2]); }
-template <class T> MB_HD RbiT<T> ld_rbi(const T *c)
+
+// Constant records are read through a handle `C` (what Ctx::cst(body) returns) and the free function
+// cst_ld2(C, i2, a, b): doubles 2 * i2 and 2 * i2 + 1 of the record.  A plain pointer is a handle (warp kernels, host
+// emulation, specialised kernels); the thread-per-state GPU context returns a 32-bit shared-memory address and
+// reads with ld.shared.v2.f64 (gpu_ctx.cuh).
+template <class T> MB_HD void cst_ld2(const T *C, int i2, T &a, T &b)
 {
+   a = C[2 * i2];
+   b = C[2 * i2 + 1];
+}
+// fixed offset of the joint: R0 (doubles 0..8), p0 (9..11)
+template <class T, class CP> MB_HD void ld_xf0(const CP C, M3T<T> &R0, V3T<T> &p0)
+{
+   cst_ld2(C, 0, R0.xx, R0.xy); cst_ld2(C, 1, R0.xz, R0.yx); cst_ld2(C, 2, R0.yy, R0.yz);
+   cst_ld2(C, 3, R0.zx, R0.zy); cst_ld2(C, 4, R0.zz, p0.x); cst_ld2(C, 5, p0.y, p0.z);
+}
+// inertia about the joint-frame origin: I (12..17), h (18..20), m (21)
+template <class T, class CP> MB_HD RbiT<T> ld_rbi(const CP C)
+{
+   static_assert(MB_C_I == 12 && MB_C_H == 18 && MB_C_M == 21, "record layout");
    RbiT<T> r;
-   r.I.xx = c[MB_C_I + 0]; r.I.xy = c[MB_C_I + 1]; r.I.xz = c[MB_C_I + 2]; r.I.yy = c[MB_C_I + 3]; r.I.yz = c[MB_C_I + 4]; r.I.zz = c[MB_C_I + 5];
-   r.h = ld_v3(c + MB_C_H);
-   r.m = c[MB_C_M];
+   cst_ld2(C, 6, r.I.xx, r.I.xy); cst_ld2(C, 7, r.I.xz, r.I.yy); cst_ld2(C, 8, r.I.yz, r.I.zz);
+   cst_ld2(C, 9, r.h.x, r.h.y); cst_ld2(C, 10, r.h.z, r.m);
    return r;
+}
+// CoM pose in the joint frame: E (22..30), c (31..33)
+template <class T, class CP> MB_HD void ld_com(const CP C, M3T<T> &E, V3T<T> &cp)
+{
+   static_assert(MB_C_E == 22 && MB_C_C == 31, "record layout");
+   cst_ld2(C, 11, E.xx, E.xy); cst_ld2(C, 12, E.xz, E.yx); cst_ld2(C, 13, E.yy, E.yz);
+   cst_ld2(C, 14, E.zx, E.zy); cst_ld2(C, 15, E.zz, cp.x); cst_ld2(C, 16, cp.y, cp.z);
 }
 
 // (a1) joint transform X_J(q) composed with the fixed offset, canonical frames (axis = +z):
 // revolute (MecanoFactories.java:231-260): R = R0 Rz(q), p = p0;  prismatic (PrismaticJointReadOnly.java:18-22): R = R0, p = p0 + q R0 e_z
-template <class T, bool REV> MB_HD XfT<T> joint_xf_1dof(const T *C, T s, T c)
+template <class T, bool REV, class CP> MB_HD XfT<T> joint_xf_1dof(const CP C, T s, T c)
 {
    XfT<T> X;
-   const M3T<T> R0 = ld_m3(C + MB_C_R);
-   const V3T<T> p0 = ld_v3(C + MB_C_P);
+   M3T<T> R0;
+   V3T<T> p0;
+   ld_xf0<T>(C, R0, p0);
    if (REV)
    {
       X.R = mul_rz(R0, s, c);
@@ -170,11 +197,12 @@ template <class T, bool REV> MB_HD XfT<T> joint_xf_1dof(const T *C, T s, T c)
 }
 
 // SixDoF (FloatingJointReadOnly.java:34-37): R = R0 R(quat), p = p0 + R0 pos; configuration rows [qx qy qz qs x y z]
-template <class T, class Ctx> MB_HD XfT<T> joint_xf_6dof(Ctx &c, const T *C, int r)
+template <class T, class Ctx, class CP> MB_HD XfT<T> joint_xf_6dof(Ctx &c, const CP C, int r)
 {
    XfT<T> X;
-   const M3T<T> R0 = ld_m3(C + MB_C_R);
-   const V3T<T> p0 = ld_v3(C + MB_C_P);
+   M3T<T> R0;
+   V3T<T> p0;
+   ld_xf0<T>(C, R0, p0);
    const M3T<T> Rq = quat_to_rot(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3));
    X.R = mul(R0, Rq);
    X.p = p0 + mul(R0, v3<T>(c.ld_q(r + 4), c.ld_q(r + 5), c.ld_q(r + 6)));
@@ -230,15 +258,31 @@ template <class T, class Ctx> MB_HD XfT<T> stk_ld_xf(Ctx &c, int slot2)
    return X;
 }
 
+// the narrow part of a SixDoF slot: the joint transform, 6 double2
+template <class T, class Ctx> MB_HD void jp_st_xf(Ctx &c, int slot2, int nslot, const XfT<T> &X)
+{
+   c.jp_st2(slot2, nslot, 0, X.R.xx, X.R.xy); c.jp_st2(slot2, nslot, 1, X.R.xz, X.R.yx); c.jp_st2(slot2, nslot, 2, X.R.yy, X.R.yz);
+   c.jp_st2(slot2, nslot, 3, X.R.zx, X.R.zy); c.jp_st2(slot2, nslot, 4, X.R.zz, X.p.x); c.jp_st2(slot2, nslot, 5, X.p.y, X.p.z);
+}
+template <class T, class Ctx> MB_HD XfT<T> jp_ld_xf(Ctx &c, int slot2, int nslot)
+{
+   XfT<T> X;
+   c.jp_ld2(slot2, nslot, 0, X.R.xx, X.R.xy); c.jp_ld2(slot2, nslot, 1, X.R.xz, X.R.yx); c.jp_ld2(slot2, nslot, 2, X.R.yy, X.R.yz);
+   c.jp_ld2(slot2, nslot, 3, X.R.zx, X.R.zy); c.jp_ld2(slot2, nslot, 4, X.R.zz, X.p.x); c.jp_ld2(slot2, nslot, 5, X.p.y, X.p.z);
+   return X;
+}
+
 // external wrench on a body, given in its CoM frame (InverseDynamicsCalculator.java:819), re-expressed in the canonical joint frame
-template <class T, class Ctx> MB_HD SvT<T> external_wrench(Ctx &c, int e, const T *C)
+template <class T, class Ctx, class CP> MB_HD SvT<T> external_wrench(Ctx &c, int e, const CP C)
 {
    SvT<T> w, r;
    w.a = v3<T>(c.ld_fext(e, 0), c.ld_fext(e, 1), c.ld_fext(e, 2));
    w.l = v3<T>(c.ld_fext(e, 3), c.ld_fext(e, 4), c.ld_fext(e, 5));
-   const M3T<T> E = ld_m3(C + MB_C_E);
+   M3T<T> E;
+   V3T<T> cp;
+   ld_com<T>(C, E, cp);
    r.l = mul(E, w.l);
-   r.a = mul(E, w.a) + cross(ld_v3(C + MB_C_C), r.l);
+   r.a = mul(E, w.a) + cross(cp, r.l);
    return r;
 }
 } // namespace mb

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    for (int i = threadIdx.x; i < ncst; i += BLOCK)
       mb_smem[i] = a.consts[i];
    using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
-   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, P.stack2, [&](Ctx &c2) {
+   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), [&](Ctx &c2) {
       if constexpr (ALGO == MB_RNEA)
          rnea_state<double, Ctx, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
       else if constexpr (ALGO == MB_ABA)
@@ -67,11 +67,12 @@ template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
    constexpr int r0 = ALGO == MB_ABA ? kAbaRec0 : 0, r1 = ALGO == MB_ABA ? kAbaRec1 : 0;
    switch (cfg)
    {
-#define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, kCfg[i].tm>;
+      // CRBA has no wide stack area: its TMEM configurations are never planned (mb_tm_fits) and alias the shared-memory kernels
+#define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, ALGO == MB_CRBA ? 0 : kCfg[i].tm>;
       MB_CFG_CASE(0) MB_CFG_CASE(1) MB_CFG_CASE(2) MB_CFG_CASE(3) MB_CFG_CASE(4) MB_CFG_CASE(5) MB_CFG_CASE(6)
       MB_CFG_CASE(7) MB_CFG_CASE(8) MB_CFG_CASE(9) MB_CFG_CASE(10) MB_CFG_CASE(11) MB_CFG_CASE(12)
 #undef MB_CFG_CASE
-      default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, kCfg[13].tm>;
+      default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, ALGO == MB_CRBA ? 0 : kCfg[13].tm>;
    }
 }
 
@@ -95,7 +96,7 @@ int class_of(int algo, const MbProgram &P)
 size_t smem_bytes(int algo, const MbProgram &P, int block, int tm)
 {
    const int ncst = (P.nb * MB_CONST_STRIDE + 1) & ~1;
-   const int smem_slots = std::max(P.stack2 - tm, algo == MB_ABA ? 20 : 0);
+   const int smem_slots = mb_smem_stack_slots(algo, P, tm);
    size_t bytes = sizeof(double) * ((size_t)ncst + (2 * (size_t)smem_slots + ring_rows(algo) * MB_PF_STAGES) * block);
    // a block with a TMEM stack allocates all 512 columns: keep it alone on its SM (a second block would spin in tcgen05.alloc)
    if (tm > 0)
@@ -137,6 +138,8 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       // ABA is register-bound at 8 warps and CRBA store-bound, both lose to the shared-memory stack
       if (forced < 0 && kCfg[cfg].tm > 0 && algo != MB_RNEA)
          continue;
+      if (!mb_tm_fits(algo, P, kCfg[cfg].tm))
+         continue; // the wide stack area (three double2 per level of the tree) exceeds the TMEM columns of one warp
       const int b = kCfg[cfg].block;
       const size_t sm = smem_bytes(algo, P, b, kCfg[cfg].tm);
       if (sm > (size_t)max_optin)

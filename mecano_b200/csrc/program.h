@@ -68,7 +68,7 @@ struct MbBody
    int32_t pad;
 };
 
-// Pre-decoded traversal record (16 bytes, one LDC.128 per op): everything an op needs, so that the kernels never
+// Pre-decoded traversal record (24 bytes): everything an op needs, so that the kernels never
 // chase MbBody fields.  Stack offsets are in double2 units (the shared-memory stack is an array of double2,
 // state-minor), save-area offsets in doubles.
 //   code: bit0 ASCEND, bits1-2 joint type, bit3 SC (this op also evaluates sin/cos for the next 1-DoF DESCEND)
@@ -81,6 +81,11 @@ struct MbOp2
    uint16_t cfg, dof;    // Mecano configuration / DoF row of the joint
    uint16_t slot, pslot; // own / parent stack slot (double2 units)
    uint16_t aux, paux;   // own / parent save area (doubles)
+   // split view of the same slot (RNEA / ABA): its first three double2 (the 6-vector that is read back and accumulated)
+   // counted in a "wide" area, the rest (sin/cos or a SixDoF transform) in a "narrow" one.  A context may place the two
+   // areas in different memories (tensor memory / shared memory) and still address them without a run-time test.
+   uint16_t wslot, pwslot; // own / parent index in the wide area (double2 units)
+   uint16_t nslot, pad;    // own index in the narrow area (double2 units)
 };
 #define MB2_ASCEND 0x1u
 #define MB2_JT(code) (((code) >> 1) & 3u)
@@ -116,7 +121,8 @@ struct MbRun
 struct MbProgram
 {
    int32_t nb, nops, nv, nq;
-   int32_t nruns, nruns3, pad0, pad1;
+   int32_t nruns, nruns3;
+   int32_t wstack2, nstack2; // sizes of the wide / narrow stack areas per state (double2 units), see MbOp2
    int32_t stack2;        // v2 stack size per state in double2 units
    int32_t stack_doubles; // shared-memory stack per state
    int32_t aux_doubles;   // local-memory branch save area per state
@@ -139,3 +145,21 @@ __host__ __device__
 static inline int mb_jp_size(int jtype) { return jtype == MB_REVOLUTE ? 2 : (jtype == MB_PRISMATIC ? 1 : 12); }
 
 enum MbAlgo { MB_RNEA = 0, MB_ABA = 1, MB_CRBA = 2 };
+
+// Shared-memory stack slots (double2 per state) of a thread-per-state block.  With a tensor-memory stack (tm > 0 slots,
+// RNEA / ABA) the wide area lives in TMEM and only the narrow one in shared memory.  ABA overlays its pass-three ring
+// (4 stages x 5 rows) on the stack area.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int mb_smem_stack_slots(int algo, const MbProgram &P, int tm)
+{
+   int s = (tm > 0 && algo != MB_CRBA) ? P.nstack2 : P.stack2;
+   if (algo == MB_ABA && s < 20)
+      s = 20;
+   return s < 1 ? 1 : s;
+}
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline bool mb_tm_fits(int algo, const MbProgram &P, int tm) { return tm == 0 || (algo != MB_CRBA && P.wstack2 <= tm); }

@@ -31,7 +31,7 @@ MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
 {
    if (SC)
       mb_sincos(pp.mq, &ns, &nc);
-   const T *C = c.cst(o.body);
+   const auto C = c.cst(o.body);
    const XfT<T> X = joint_xf_1dof<T, REV>(C, pp.s, pp.c);
    // pass one (:873-917): twist and acceleration of the body, in its joint frame
    v = motion_to_child(X, v);
@@ -52,7 +52,7 @@ MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
       a.l.z += pp.x;
    }
    // Newton-Euler (SpatialInertiaReadOnly.java:229-296), about the joint-frame origin
-   const RbiT<T> I = ld_rbi(C);
+   const RbiT<T> I = ld_rbi<T>(C);
    f = mul(I, a) + cross_force(v, mul(I, v));
    if (FEXT)
       f = f - external_wrench<T>(c, ext, C); // :946
@@ -60,10 +60,8 @@ MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
    pp.lc = pp.c;
    if (!(o.flags & MB2_LEAF))
    {
-      c.stk_st2(o.slot, 0, f.a.x, f.a.y);
-      c.stk_st2(o.slot, 1, f.a.z, f.l.x);
-      c.stk_st2(o.slot, 2, f.l.y, f.l.z);
-      c.stk_st2(o.slot, 3, pp.s, pp.c);
+      c.acc_st(o.slot, o.wslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
+      c.jp_st2(o.slot, o.nslot, 0, pp.s, pp.c);
    }
    if (o.flags & MB2_SAVE_STATE)
    {
@@ -83,26 +81,20 @@ MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, SvT<T> &f, RneaPipe<T> &pp, T
    {
       T s = pp.ls, cs = pp.lc;
       if (!(o.flags & MB2_LEAF))
-         c.stk_ld2(o.slot, 3, s, cs);
+         c.jp_ld2(o.slot, o.nslot, 0, s, cs);
       const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), s, cs);
       SvT<T> acc;
-      c.stk_ld2(o.pslot, 0, acc.a.x, acc.a.y);
-      c.stk_ld2(o.pslot, 1, acc.a.z, acc.l.x);
-      c.stk_ld2(o.pslot, 2, acc.l.y, acc.l.z);
+      c.acc_ld(o.pslot, o.pwslot, acc.a.x, acc.a.y, acc.a.z, acc.l.x, acc.l.y, acc.l.z);
       f = acc + force_to_parent(X, f); // addJointWrenchFromChild (:961-966)
       if (o.flags & MB2_STORE_ACC)
-      {
-         c.stk_st2(o.pslot, 0, f.a.x, f.a.y);
-         c.stk_st2(o.pslot, 1, f.a.z, f.l.x);
-         c.stk_st2(o.pslot, 2, f.l.y, f.l.z);
-      }
+         c.acc_st(o.pslot, o.pwslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
    }
 }
 
 template <class T, class Ctx, bool FEXT>
 MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &a, SvT<T> &f, bool use_qd, bool use_qdd)
 {
-   const T *C = c.cst(o.body);
+   const auto C = c.cst(o.body);
    const XfT<T> X = joint_xf_6dof<T>(c, C, o.cfg);
    SvT<T> vj = sv_zero<T>(), aj = sv_zero<T>();
    if (use_qd)
@@ -111,15 +103,13 @@ MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
       aj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
    v = motion_to_child(X, v) + vj;
    a = motion_to_child(X, a) + cross_motion(v, vj) + aj;
-   const RbiT<T> I = ld_rbi(C);
+   const RbiT<T> I = ld_rbi<T>(C);
    f = mul(I, a) + cross_force(v, mul(I, v));
    if (FEXT)
       f = f - external_wrench<T>(c, ext, C);
-   c.stk_st2(o.slot, 0, f.a.x, f.a.y);
-   c.stk_st2(o.slot, 1, f.a.z, f.l.x);
-   c.stk_st2(o.slot, 2, f.l.y, f.l.z);
+   c.acc_st(o.slot, o.wslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))
-      stk_st_xf<T>(c, o.slot + 3, X);
+      jp_st_xf<T>(c, o.slot, o.nslot, X);
    if (o.flags & MB2_SAVE_STATE)
    {
       aux_st_sv<T>(c, o.aux, v);
@@ -133,18 +123,12 @@ template <class T, class Ctx> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o,
    c.st_out(o.dof + 3, f.l.x); c.st_out(o.dof + 4, f.l.y); c.st_out(o.dof + 5, f.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
-      const XfT<T> X = stk_ld_xf<T>(c, o.slot + 3);
+      const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
       SvT<T> acc;
-      c.stk_ld2(o.pslot, 0, acc.a.x, acc.a.y);
-      c.stk_ld2(o.pslot, 1, acc.a.z, acc.l.x);
-      c.stk_ld2(o.pslot, 2, acc.l.y, acc.l.z);
+      c.acc_ld(o.pslot, o.pwslot, acc.a.x, acc.a.y, acc.a.z, acc.l.x, acc.l.y, acc.l.z);
       f = acc + force_to_parent(X, f);
       if (o.flags & MB2_STORE_ACC)
-      {
-         c.stk_st2(o.pslot, 0, f.a.x, f.a.y);
-         c.stk_st2(o.pslot, 1, f.a.z, f.l.x);
-         c.stk_st2(o.pslot, 2, f.l.y, f.l.z);
-      }
+         c.acc_st(o.pslot, o.pwslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
    }
 }
 

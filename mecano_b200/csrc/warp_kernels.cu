@@ -120,7 +120,7 @@ template <bool FEXT> __device__ __forceinline__ Lane lane_setup(const MbProgram 
    const double *C = consts + (size_t)b * MB_CONST_STRIDE;
    L.X0.R = ld_m3(C + MB_C_R);
    L.X0.p = ld_v3(C + MB_C_P);
-   L.I = ld_rbi(C);
+   L.I = ld_rbi<double>(C);
    if (FEXT)
    {
       L.E = ld_m3(C + MB_C_E);

@@ -66,6 +66,20 @@ template <class T> struct CpuCtx
    void zero_fill() { for (uint16_t e : *zl) st_M(e, (T)0); }
    void stk_ld2(int slot2, int j, T &a, T &b) const { a = stk[2 * (slot2 + j)]; b = stk[2 * (slot2 + j) + 1]; }
    void stk_st2(int slot2, int j, T a, T b) { stk[2 * (slot2 + j)] = a; stk[2 * (slot2 + j) + 1] = b; }
+   // split view of a slot (MbOp2::wslot / nslot): the wide area behind the combined stack so that both index sets are exercised
+   T *wide, *narrow;
+   void acc_ld(int, int wslot, T &x0, T &x1, T &x2, T &x3, T &x4, T &x5) const
+   {
+      const T *p = wide + 2 * wslot;
+      x0 = p[0]; x1 = p[1]; x2 = p[2]; x3 = p[3]; x4 = p[4]; x5 = p[5];
+   }
+   void acc_st(int, int wslot, T x0, T x1, T x2, T x3, T x4, T x5)
+   {
+      T *p = wide + 2 * wslot;
+      p[0] = x0; p[1] = x1; p[2] = x2; p[3] = x3; p[4] = x4; p[5] = x5;
+   }
+   void jp_ld2(int, int nslot, int j, T &a, T &b) const { a = narrow[2 * (nslot + j)]; b = narrow[2 * (nslot + j) + 1]; }
+   void jp_st2(int, int nslot, int j, T a, T b) { narrow[2 * (nslot + j)] = a; narrow[2 * (nslot + j) + 1] = b; }
    T ring[4][3];
    void pf_issue(int stage, int cfg, int dof, int mask)
    {
@@ -116,13 +130,18 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
    // poison the work areas so that a read-before-write shows up as NaN
    const T nan = (T)(0.0 / 0.0);
    std::vector<T> stk(std::max(P.stack_doubles, 2 * P.stack2) + 2, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 64, nan);
+   std::vector<T> wide(2 * P.wstack2 + 2, nan), narrow(2 * P.nstack2 + 2, nan);
    const T grav[3] = {(T)g[0], (T)g[1], (T)g[2]};
    for (long s = 0; s < n; s++)
    {
       std::fill(stk.begin(), stk.end(), nan);
       std::fill(aux.begin(), aux.end(), nan);
       std::fill(rec.begin(), rec.end(), nan);
+      std::fill(wide.begin(), wide.end(), nan);
+      std::fill(narrow.begin(), narrow.end(), nan);
       CpuCtx<T> c{q, qd, x, fext, out, out, ld, s, ft.nv, stk.data(), aux.data(), rec.data(), consts.data()};
+      c.wide = wide.data();
+      c.narrow = narrow.data();
       c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
