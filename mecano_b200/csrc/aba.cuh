@@ -266,36 +266,40 @@ template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, i
 // which scalars an op needs from the prefetch ring: DESCEND q + qd, ASCEND qd + tau
 MB_HD int aba_pf_mask(const MbOp2 &o) { return MB2_JT(o.code) == MB_SIXDOF ? 0 : ((o.code & MB2_ASCEND) ? 6 : 3); }
 
-// ---- one op of passes one + two (the body of the interpreter loop; see rnea_op for the role of the literal arguments)
-template <class T, class Ctx, bool FEXT>
-MB_HD void aba_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int ext, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
+// ---- the part of an op of passes one + two that does not depend on its kind (see rnea_pre)
+template <class T, class Ctx>
+MB_HD void aba_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const bool asc, SvT<T> &v, AbaPipe<T> &pp)
 {
-   c.op_sync(k);
    c.stk_fence();
-   {
-      const int m = aba_pf_mask(od);
-      if (m)
-         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, m);
-      c.pf_commit();
-      c.template pf_wait<MB_PF_DIST - 1>();
-   }
+   if (o.pf & (MB2_PF_D1 | MB2_PF_A1))
+      c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, (o.pf & MB2_PF_A1) ? 6 : 3);
+   c.pf_commit();
+   c.template pf_wait<MB_PF_DIST - 1>();
    pp.qd = pp.x = pp.mq = (T)0;
-   if (MB2_JT(o.code) != MB_SIXDOF)
+   if (onedof)
    {
       pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
-      if (o.code & MB2_ASCEND)
+      if (asc)
          pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
    }
-   if (o.pf & 1u)
+   if (o.pf & MB2_PF_NEXT1)
       pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
    // twist of the parent: carried along a chain, zero for the root body, otherwise on the parent's stack slot
-   if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+   if (!asc && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
    {
       if (o.flags & MB2_ROOT_PARENT)
          v = sv_zero<T>();
       else
          c.acc_ld(o.pslot, o.pwslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
    }
+}
+
+// ---- one op of passes one + two (the unit the tree-specialised kernels are generated from; see rnea_op)
+template <class T, class Ctx, bool FEXT>
+MB_HD void aba_op(Ctx &c, const int k, const MbOp2 o, const int ext, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
+{
+   c.op_sync(k);
+   aba_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, (o.code & MB2_ASCEND) != 0, v, pp);
    T ns = pp.mq, nc = (T)1;
    switch (o.code & 0xfu)
    {
@@ -371,21 +375,21 @@ MB_HD void aba_pass3_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o
    }
 }
 
+// ---- the kind-independent part of a pass-three op
 template <class T, class Ctx>
-MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
-   c.op_sync(k);
-   c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, od.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(od) ? 3 : 0);
+   c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, o.pfbody * (MB_ABA_REC / 2), (o.pf & MB2_PF_D1) ? 3 : 0);
    c.pf_commit();
    c.template pf_wait<MB_PF_DIST - 1>();
    const int st = k & (MB_PF_STAGES - 1);
    pp.qd = pp.mq = (T)0;
-   if (MB2_JT(o.code) != MB_SIXDOF)
+   if (onedof)
    {
       T qq;
       c.pf3_ld2(st, 0, qq, pp.qd);
    }
-   if (o.pf & 1u)
+   if (o.pf & MB2_PF_NEXT1)
    {
       T qdn;
       c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
@@ -405,6 +409,14 @@ MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, cons
          a = aux_ld_sv<T>(c, o.paux + 6);
       }
    }
+}
+
+template <class T, class Ctx>
+MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+{
+   c.op_sync(k);
+   aba_pass3_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, grav, v, a, pp);
+   const int st = k & (MB_PF_STAGES - 1);
    T ns = pp.mq, nc = (T)1;
    switch (o.code & 0xfu)
    {
@@ -429,31 +441,7 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
    constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0;
    constexpr int JT = (KIND >> 1) & 3;
    const MbOp2 o = P.op2[k];
-   c.stk_fence();
-   {
-      const MbOp2 od = P.op2[k + MB_PF_DIST];
-      const int m = aba_pf_mask(od);
-      if (m)
-         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, m);
-      c.pf_commit();
-      c.template pf_wait<MB_PF_DIST - 1>();
-   }
-   pp.qd = pp.x = pp.mq = (T)0;
-   if (JT != MB_SIXDOF)
-   {
-      pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
-      if (ASC)
-         pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
-   }
-   if (o.pf & 1u)
-      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
-   if (!ASC && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
-   {
-      if (o.flags & MB2_ROOT_PARENT)
-         v = sv_zero<T>();
-      else
-         c.acc_ld(o.pslot, o.pwslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
-   }
+   aba_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, ASC, v, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
    if (JT == MB_SIXDOF)
@@ -476,39 +464,8 @@ MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *
    constexpr bool SC = (KIND & MB2_SC) != 0;
    constexpr int JT = (KIND >> 1) & 3;
    const MbOp2 o = P.op3[k];
-   {
-      const MbOp2 od = P.op3[k + MB_PF_DIST];
-      c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, od.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(od) ? 3 : 0);
-      c.pf_commit();
-      c.template pf_wait<MB_PF_DIST - 1>();
-   }
+   aba_pass3_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, grav, v, a, pp);
    const int st = k & (MB_PF_STAGES - 1);
-   pp.qd = pp.mq = (T)0;
-   if (JT != MB_SIXDOF)
-   {
-      T qq;
-      c.pf3_ld2(st, 0, qq, pp.qd);
-   }
-   if (o.pf & 1u)
-   {
-      T qdn;
-      c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
-      pp.mq = mb_reduce_angle(pp.mq);
-   }
-   if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
-   {
-      if (o.flags & MB2_ROOT_PARENT)
-      {
-         v = sv_zero<T>();
-         a = sv_zero<T>();
-         a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
-      }
-      else
-      {
-         v = aux_ld_sv<T>(c, o.paux);
-         a = aux_ld_sv<T>(c, o.paux + 6);
-      }
-   }
    T ns = pp.mq, nc = (T)1;
    if (JT == MB_SIXDOF)
    {

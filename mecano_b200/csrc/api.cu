@@ -24,6 +24,8 @@ struct mecano_b200_handle
    double *d_consts = nullptr;
    uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
    MbProgram *d_prog = nullptr; // [3] device copies of the traversal programs (warp-per-state kernels)
+   double *d_zero_row = nullptr; // one row of zeros: stands in for qd / qdd when RNEA ignores velocities / accelerations
+   size_t zero_row_doubles = 0;
    double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
    size_t ws_doubles[3] = {0, 0, 0};
    mb::SpecKernel spec[3];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
@@ -99,6 +101,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.zero_entries = h->d_zero;
       wa.n_zero = (int32_t)h->tree.zero_entries.size();
       wa.n = n; wa.ld = ld;
+      wa.ld_qd = wa.ld_x = ld;
       wa.grav[0] = h->gravity[0]; wa.grav[1] = h->gravity[1]; wa.grav[2] = h->gravity[2];
       wa.flags = flags;
       wa.nv = h->tree.nv;
@@ -133,6 +136,28 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.zero_entries = h->d_zero;
    a.n_zero = (int32_t)h->tree.zero_entries.size();
    a.n = n; a.ld = ld;
+   a.ld_qd = a.ld_x = ld;
+   if (algo == MB_RNEA && (flags & (MECANO_B200_RNEA_NO_CORIOLIS | MECANO_B200_RNEA_NO_ACCELERATIONS)))
+   {
+      // setConsiderCoriolisAndCentrifugalForces(false) / setConsiderJointAccelerations(false) (InverseDynamicsCalculator.java:
+      // 291-306) = the same recursion with zero joint velocities / accelerations: one row of zeros with stride 0 replaces the
+      // input, so the kernels carry no flag tests
+      if (h->zero_row_doubles < (size_t)n)
+      {
+         if (h->d_zero_row)
+         {
+            MB_CUDA(h, cudaDeviceSynchronize());
+            MB_CUDA(h, cudaFree(h->d_zero_row));
+            h->d_zero_row = nullptr;
+            h->zero_row_doubles = 0;
+         }
+         MB_CUDA(h, cudaMalloc(&h->d_zero_row, (size_t)n * sizeof(double)));
+         MB_CUDA(h, cudaMemset(h->d_zero_row, 0, (size_t)n * sizeof(double)));
+         h->zero_row_doubles = (size_t)n;
+      }
+      if (flags & MECANO_B200_RNEA_NO_CORIOLIS) { a.qd = h->d_zero_row; a.ld_qd = 0; }
+      if (flags & MECANO_B200_RNEA_NO_ACCELERATIONS) { a.x = h->d_zero_row; a.ld_x = 0; }
+   }
    a.grav[0] = h->gravity[0]; a.grav[1] = h->gravity[1]; a.grav[2] = h->gravity[2];
    a.flags = flags;
    a.nv = h->tree.nv;
@@ -349,6 +374,7 @@ void mecano_b200_destroy(mecano_b200_handle *h)
       if (h->done[i]) cudaEventDestroy(h->done[i]);
       if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
    }
+   if (h->d_zero_row) cudaFree(h->d_zero_row);
    if (h->d_consts) cudaFree(h->d_consts);
    if (h->d_zero) cudaFree(h->d_zero);
    if (h->d_prog) cudaFree(h->d_prog);

@@ -125,15 +125,12 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
    {
       const MbOp2 o = P.op2[k];
       c.stk_fence();
-      {
-         const MbOp2 od = P.op2[k + MB_PF_DIST];
-         if (mb2_is_1dof_descend(od))
-            c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, 1);
-         c.pf_commit();
-         c.template pf_wait<MB_PF_DIST - 1>();
-      }
+      if (o.pf & MB2_PF_D1)
+         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, 1);
+      c.pf_commit();
+      c.template pf_wait<MB_PF_DIST - 1>();
       mq = (T)0;
-      if (o.pf & 1u)
+      if (o.pf & MB2_PF_NEXT1)
          mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
       T ns = mq, nc = (T)1;
       if (o.code & MB2_SC)

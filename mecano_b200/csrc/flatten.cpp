@@ -200,7 +200,14 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
          if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) == MB_REVOLUTE)
             ops[k].code |= MB2_SC;
          if (!(n1.code & MB2_ASCEND) && MB2_JT(n1.code) != MB_SIXDOF)
-            ops[k].pf |= 1u;
+            ops[k].pf |= MB2_PF_NEXT1;
+         // what op k requests for op k + 3 (MB_PF_DIST, rnea.cuh); the trailing records are SixDoF ASCENDs: nothing
+         const MbOp2 &nd = ops[k + 3];
+         if (MB2_JT(nd.code) != MB_SIXDOF)
+            ops[k].pf |= (nd.code & MB2_ASCEND) ? MB2_PF_A1 : MB2_PF_D1;
+         ops[k].pfcfg = nd.cfg;
+         ops[k].pfdof = nd.dof;
+         ops[k].pfbody = nd.body;
       }
    };
    look_ahead(P.op2, P.nops);

@@ -77,6 +77,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    const char *qb, *qdb, *xb, *fb;
    char *ob;
    unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
+   unsigned ld8d, ld8x; // the same for qd and x (0: one row of zeros stands in for every row)
    unsigned sb;  // shared address of this thread's element of shared-memory stack slot 0
    unsigned rb;  // shared address of this thread's element of stage 0, row 0 of the prefetch ring
    unsigned cb;  // shared address of the constant records
@@ -92,8 +93,8 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    double *aux; // local memory
 
    __device__ __forceinline__ double ld_q(int r) const { return mb_ldg(mb_row(qb, (unsigned)r, ld8)); }
-   __device__ __forceinline__ double ld_qd(int r) const { return mb_ldg(mb_row(qdb, (unsigned)r, ld8)); }
-   __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(mb_row(xb, (unsigned)r, ld8)); }
+   __device__ __forceinline__ double ld_qd(int r) const { return mb_ldg(mb_row(qdb, (unsigned)r, ld8d)); }
+   __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(mb_row(xb, (unsigned)r, ld8x)); }
    __device__ __forceinline__ double ld_fext(int b, int k) const { return mb_ldg(mb_row(fb, (unsigned)(6 * b + k), ld8)); }
    __device__ __forceinline__ void st_out(int r, double v) { mb_stg(mb_row(ob, (unsigned)r, ld8), v); }
    // ---- general stack access (CRBA; shared memory)
@@ -183,7 +184,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       if (mask & 1)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
       if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(mb_row(qdb, (unsigned)dof, ld8)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(mb_row(qdb, (unsigned)dof, ld8d)) : "memory");
       const double2 *src = wsb + rec2 * ws_ld;
 #pragma unroll
       for (int j = 0; j < 4; j++)
@@ -227,9 +228,9 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       if (mask & 1)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
       if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(mb_row(qdb, (unsigned)dof, ld8)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(mb_row(qdb, (unsigned)dof, ld8d)) : "memory");
       if (mask & 4)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(mb_row(xb, (unsigned)dof, ld8)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(mb_row(xb, (unsigned)dof, ld8x)) : "memory");
    }
    __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
    template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -264,6 +265,8 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    double aux[AUXN > 0 ? AUXN : 1];
    GpuCtx2<BLOCK, TM, ring_rows(ALGO)> c2;
    c2.ld8 = (unsigned)(a.ld * 8);
+   c2.ld8d = (unsigned)(a.ld_qd * 8);
+   c2.ld8x = (unsigned)(a.ld_x * 8);
    // mb_smem_u32() names the symbol in inline PTX only: one (never executed) C++ reference makes sure it is declared in
    // the module even when nothing else touches it (tree-specialised kernels stage no constant records)
    if (a.n < 0)

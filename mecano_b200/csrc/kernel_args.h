@@ -15,6 +15,7 @@ struct KernelArgs
    const uint16_t *zero_entries;    // CRBA: structurally zero mass-matrix entries (multiple of 8, 16-byte aligned)
    int32_t n_zero;
    long long n, ld;
+   long long ld_qd, ld_x; // row strides of qd and x (normally ld; 0 when the launcher substitutes one row of zeros)
    double grav[3];
    uint32_t flags;
    int32_t nv;

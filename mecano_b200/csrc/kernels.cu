@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
    thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), [&](Ctx &c2) {
       if constexpr (ALGO == MB_RNEA)
-         rnea_state<double, Ctx, FEXT>(P, c2, a.grav, !(a.flags & 1u), !(a.flags & 2u));
+         rnea_state<double, Ctx, FEXT>(P, c2, a.grav);
       else if constexpr (ALGO == MB_ABA)
          aba_state<double, Ctx, FEXT>(P, c2, a.grav);
       else

@@ -68,7 +68,7 @@ struct MbBody
    int32_t pad;
 };
 
-// Pre-decoded traversal record (24 bytes): everything an op needs, so that the kernels never
+// Pre-decoded traversal record (28 bytes): everything an op needs, so that the kernels never
 // chase MbBody fields.  Stack offsets are in double2 units (the shared-memory stack is an array of double2,
 // state-minor), save-area offsets in doubles.
 //   code: bit0 ASCEND, bits1-2 joint type, bit3 SC (this op also evaluates sin/cos for the next 1-DoF DESCEND)
@@ -77,7 +77,7 @@ struct MbOp2
    uint8_t code;
    uint8_t flags;   // MB_F_* >> 1  (LEAF 0x1, LOAD_PARENT 0x2, SAVE_STATE 0x4, ROOT_PARENT 0x8, STORE_ACC 0x10, FIRST_CHILD 0x20)
    uint8_t body;    // internal body index (constant record)
-   uint8_t pf;      // bit0: op k+1 is a 1-DoF DESCEND (its configuration is read from the prefetch ring during this op)
+   uint8_t pf;      // MB2_PF_*: what this op does for the ops ahead of it in the software pipeline
    uint16_t cfg, dof;    // Mecano configuration / DoF row of the joint
    uint16_t slot, pslot; // own / parent stack slot (double2 units)
    uint16_t aux, paux;   // own / parent save area (doubles)
@@ -85,8 +85,13 @@ struct MbOp2
    // counted in a "wide" area, the rest (sin/cos or a SixDoF transform) in a "narrow" one.  A context may place the two
    // areas in different memories (tensor memory / shared memory) and still address them without a run-time test.
    uint16_t wslot, pwslot; // own / parent index in the wide area (double2 units)
-   uint16_t nslot, pad;    // own index in the narrow area (double2 units)
+   uint16_t nslot;         // own index in the narrow area (double2 units)
+   uint16_t pfbody;        // body of op k + MB_PF_DIST (ABA pass three: its pass-two record)
+   uint16_t pfcfg, pfdof;  // configuration / DoF row of op k + MB_PF_DIST (requested during this op)
 };
+#define MB2_PF_NEXT1 0x1u // op k+1 is a 1-DoF DESCEND (its configuration is read from the prefetch ring during this op)
+#define MB2_PF_D1 0x2u    // op k + MB_PF_DIST is a 1-DoF DESCEND
+#define MB2_PF_A1 0x4u    // op k + MB_PF_DIST is a 1-DoF ASCEND
 #define MB2_ASCEND 0x1u
 #define MB2_JT(code) (((code) >> 1) & 3u)
 #define MB2_SC 0x8u

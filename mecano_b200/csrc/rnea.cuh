@@ -92,15 +92,12 @@ MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, SvT<T> &f, RneaPipe<T> &pp, T
 }
 
 template <class T, class Ctx, bool FEXT>
-MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &a, SvT<T> &f, bool use_qd, bool use_qdd)
+MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &a, SvT<T> &f)
 {
    const auto C = c.cst(o.body);
    const XfT<T> X = joint_xf_6dof<T>(c, C, o.cfg);
-   SvT<T> vj = sv_zero<T>(), aj = sv_zero<T>();
-   if (use_qd)
-      vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
-   if (use_qdd)
-      aj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
+   const SvT<T> vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
+   const SvT<T> aj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
    v = motion_to_child(X, v) + vj;
    a = motion_to_child(X, a) + cross_motion(v, vj) + aj;
    const RbiT<T> I = ld_rbi<T>(C);
@@ -134,36 +131,34 @@ template <class T, class Ctx> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o,
 
 // Prefetch ring (Ctx::pf_*): MB_PF_STAGES slots of (q, qd, x) per state.  Op k issues the asynchronous copies of
 // op k + MB_PF_DIST (cp.async on the GPU: no register and no scoreboard is held while the data is in flight),
-// evaluates the sin/cos of op k + 1 and consumes the velocity / acceleration of op k.
+// evaluates the sin/cos of op k + 1 and consumes the velocity / acceleration of op k.  What op k has to request for
+// op k + MB_PF_DIST is pre-decoded into its own record (MbOp2::pf bits, pfcfg, pfdof).
+// setConsiderCoriolisAndCentrifugalForces(false) / setConsiderJointAccelerations(false) (:291-306) never reach this
+// code: the launcher substitutes a zero row with stride 0 for qd / qdd, which is the same computation.
 #define MB_PF_STAGES 4
 #define MB_PF_DIST 3
 
-// One op of the traversal program: the body of the interpreter loop below, and the unit the tree-specialised kernels
-// (specialize.cpp) are generated from -- there every argument except the context and the carried state is a literal, so
-// the flag tests, the dispatch switch and all table lookups fold away at compile time.
-//   k: index of the op (selects the prefetch-ring stage);  o: this op;  od: op k + MB_PF_DIST (its scalars are issued now)
-template <class T, class Ctx, bool FEXT>
-MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int ext, const T *grav, const bool use_qd, const bool use_qdd, SvT<T> &v,
-                   SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
+// The part of an op that does not depend on its kind: prefetch of op k + MB_PF_DIST, scalars of op k, raw angle of op
+// k + 1, kinematic state of the parent.  DESC1: op k is a 1-DoF DESCEND;  DESC: op k is a DESCEND.
+template <class T, class Ctx>
+MB_HD void rnea_pre(Ctx &c, const int k, const MbOp2 &o, const bool desc1, const bool desc, const T *grav, SvT<T> &v, SvT<T> &a, RneaPipe<T> &pp)
 {
-   const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
-   c.op_sync(k);
    c.stk_fence();
-   if (mb2_is_1dof_descend(od))
-      c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, pfmask);
+   if (o.pf & MB2_PF_D1)
+      c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, 7);
    c.pf_commit();
    c.template pf_wait<MB_PF_DIST - 1>(); // everything up to the group of op k + 1 has landed
    pp.qd = pp.x = pp.mq = (T)0;
-   if (mb2_is_1dof_descend(o))
+   if (desc1)
    {
-      if (use_qd) pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
-      if (use_qdd) pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
+      pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
+      pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
    }
-   if (o.pf & 1u) // op k + 1 is a 1-DoF DESCEND
+   if (o.pf & MB2_PF_NEXT1) // op k + 1 is a 1-DoF DESCEND
       pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0)); // no-op unless |q| > MB_SINCOS_FAST_LIMIT
    // kinematic state of the parent: carried in registers along a chain, otherwise the root acceleration
    // (= -gravity, InverseDynamicsCalculator.java:397-403) or the state saved by the branching ancestor
-   if (!(o.code & MB2_ASCEND) && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
+   if (desc && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
    {
       if (o.flags & MB2_ROOT_PARENT)
       {
@@ -177,6 +172,16 @@ MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int
          a = aux_ld_sv<T>(c, o.paux + 6);
       }
    }
+}
+
+// One op of the traversal program: the unit the tree-specialised kernels (specialize.cpp) are generated from -- there
+// every argument except the context and the carried state is a literal, so the flag tests, the dispatch switch and all
+// table lookups fold away at compile time.   k: index of the op (selects the prefetch-ring stage);  o: this op
+template <class T, class Ctx, bool FEXT>
+MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const int ext, const T *grav, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
+{
+   c.op_sync(k);
+   rnea_pre<T, Ctx>(c, k, o, mb2_is_1dof_descend(o), !(o.code & MB2_ASCEND), grav, v, a, pp);
    T ns = pp.mq, nc = (T)1; // prismatic next op: "s" carries q
    switch (o.code & 0xfu)
    {
@@ -194,7 +199,7 @@ MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int
          if (o.code & MB2_ASCEND)
             rnea_ascend_6dof<T, Ctx>(c, o, f);
          else
-            rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f, use_qd, use_qdd);
+            rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f);
          break;
    }
    pp.s = ns;
@@ -203,19 +208,17 @@ MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const MbOp2 od, const int
 
 // prologue: the scalars of ops 0 .. MB_PF_DIST-1 are requested, the sin/cos of op 0 evaluated
 template <class T, class Ctx>
-MB_HD void rnea_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, const bool use_qd, const bool use_qdd, SvT<T> &v, SvT<T> &a, SvT<T> &f,
-                      RneaPipe<T> &pp)
+MB_HD void rnea_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
 {
    static_assert(MB_PF_DIST == 3, "prologue written for a prefetch distance of 3");
    v = sv_zero<T>(); a = sv_zero<T>(); f = sv_zero<T>();
    pp.s = pp.qd = pp.x = pp.mq = pp.ls = (T)0;
    pp.c = pp.lc = (T)1;
-   const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
-   if (mb2_is_1dof_descend(o0)) c.pf_issue(0, o0.cfg, o0.dof, pfmask);
+   if (mb2_is_1dof_descend(o0)) c.pf_issue(0, o0.cfg, o0.dof, 7);
    c.pf_commit();
-   if (mb2_is_1dof_descend(o1)) c.pf_issue(1, o1.cfg, o1.dof, pfmask);
+   if (mb2_is_1dof_descend(o1)) c.pf_issue(1, o1.cfg, o1.dof, 7);
    c.pf_commit();
-   if (mb2_is_1dof_descend(o2)) c.pf_issue(2, o2.cfg, o2.dof, pfmask);
+   if (mb2_is_1dof_descend(o2)) c.pf_issue(2, o2.cfg, o2.dof, 7);
    c.pf_commit();
    c.template pf_wait<0>();
    if (mb2_is_1dof_descend(o0))
@@ -229,49 +232,19 @@ MB_HD void rnea_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, co
 // One op inside a run: the same steps as rnea_op with the kind (ASCEND / joint type / SC) fixed at compile time, so a run
 // is a tight loop over one straight-line routine.
 template <class T, class Ctx, bool FEXT, int KIND>
-MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, const bool use_qd, const bool use_qdd, const int pfmask, SvT<T> &v,
-                         SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
+MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
 {
    constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0;
    constexpr int JT = (KIND >> 1) & 3;
    const MbOp2 o = P.op2[k];
-   c.stk_fence();
-   {
-      const MbOp2 od = P.op2[k + MB_PF_DIST];
-      if (mb2_is_1dof_descend(od))
-         c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), od.cfg, od.dof, pfmask);
-      c.pf_commit();
-      c.template pf_wait<MB_PF_DIST - 1>();
-   }
-   pp.qd = pp.x = pp.mq = (T)0;
-   if (!ASC && JT != MB_SIXDOF)
-   {
-      if (use_qd) pp.qd = c.pf_ld(k & (MB_PF_STAGES - 1), 1);
-      if (use_qdd) pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
-   }
-   if (o.pf & 1u)
-      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
-   if (!ASC && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
-   {
-      if (o.flags & MB2_ROOT_PARENT)
-      {
-         v = sv_zero<T>();
-         a = sv_zero<T>();
-         a.l = v3<T>(-grav[0], -grav[1], -grav[2]);
-      }
-      else
-      {
-         v = aux_ld_sv<T>(c, o.paux);
-         a = aux_ld_sv<T>(c, o.paux + 6);
-      }
-   }
+   rnea_pre<T, Ctx>(c, k, o, !ASC && JT != MB_SIXDOF, !ASC, grav, v, a, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
    if (JT == MB_SIXDOF)
    {
       if (SC) mb_sincos(pp.mq, &ns, &nc);
       if (ASC) rnea_ascend_6dof<T, Ctx>(c, o, f);
-      else rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f, use_qd, use_qdd);
+      else rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f);
    }
    else if (ASC)
       rnea_ascend_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, f, pp, ns, nc);
@@ -281,12 +254,11 @@ MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav,
    pp.c = nc;
 }
 
-template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav, bool use_qd, bool use_qdd)
+template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &P, Ctx &c, const T *grav)
 {
    SvT<T> v, a, f;
    RneaPipe<T> pp;
-   rnea_begin<T, Ctx>(c, P.op2[0], P.op2[1], P.op2[2], use_qd, use_qdd, v, a, f, pp);
-   const int pfmask = 1 | (use_qd ? 2 : 0) | (use_qdd ? 4 : 0);
+   rnea_begin<T, Ctx>(c, P.op2[0], P.op2[1], P.op2[2], v, a, f, pp);
    const int nruns = P.nruns;
 #pragma unroll 1
    for (int r = 0; r < nruns; r++)
@@ -296,7 +268,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
       const int k1 = k + R.n;
 #define MB_RUN_CASE(KIND)                                                                                  \
    case KIND:                                                                                               \
-      _Pragma("unroll 1") do { rnea_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, use_qd, use_qdd, pfmask, v, a, f, pp); } while (++k < k1); \
+      _Pragma("unroll 1") do { rnea_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a, f, pp); } while (++k < k1); \
       break;
       switch (R.kind)
       {

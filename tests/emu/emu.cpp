@@ -52,12 +52,13 @@ template <class T> struct CpuCtx
    const double *q, *qd, *x, *fext;
    double *out, *M;
    long ld, s;
+   long ldd, ldx; // row strides of qd / x (0: a single row of zeros, the way the launcher handles the RNEA flags)
    int nv;
    T *stk, *aux, *rec;
    const T *consts;
    T ld_q(int r) const { return (T)q[r * ld + s]; }
-   T ld_qd(int r) const { return (T)qd[r * ld + s]; }
-   T ld_x(int r) const { return (T)x[r * ld + s]; }
+   T ld_qd(int r) const { return (T)qd[r * ldd + s]; }
+   T ld_x(int r) const { return (T)x[r * ldx + s]; }
    T ld_fext(int b, int k) const { return (T)fext[(6 * b + k) * ld + s]; }
    void st_out(int r, T v) { out[r * ld + s] = (double)v; }
    void st_M(int e, T v) { M[(long)e * ld + s] = (double)v; }
@@ -132,6 +133,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
    std::vector<T> stk(std::max(P.stack_doubles, 2 * P.stack2) + 2, nan), aux(P.aux_doubles + 1, nan), rec(P.rec_doubles + 64, nan);
    std::vector<T> wide(2 * P.wstack2 + 2, nan), narrow(2 * P.nstack2 + 2, nan);
    const T grav[3] = {(T)g[0], (T)g[1], (T)g[2]};
+   const std::vector<double> zero_row((size_t)std::max(n, 1l), 0.0);
    for (long s = 0; s < n; s++)
    {
       std::fill(stk.begin(), stk.end(), nan);
@@ -139,14 +141,16 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       std::fill(rec.begin(), rec.end(), nan);
       std::fill(wide.begin(), wide.end(), nan);
       std::fill(narrow.begin(), narrow.end(), nan);
-      CpuCtx<T> c{q, qd, x, fext, out, out, ld, s, ft.nv, stk.data(), aux.data(), rec.data(), consts.data()};
+      CpuCtx<T> c{q, qd, x, fext, out, out, ld, s, ld, ld, ft.nv, stk.data(), aux.data(), rec.data(), consts.data()};
+      if (algo == MB_RNEA && (flags & 1u)) { c.qd = zero_row.data(); c.ldd = 0; } // api.cu: run()
+      if (algo == MB_RNEA && (flags & 2u)) { c.x = zero_row.data(); c.ldx = 0; }
       c.wide = wide.data();
       c.narrow = narrow.data();
       c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
-         if (fext) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav, !(flags & 1u), !(flags & 2u));
-         else mb::rnea_state<T, CpuCtx<T>, false>(P, c, grav, !(flags & 1u), !(flags & 2u));
+         if (fext) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav);
+         else mb::rnea_state<T, CpuCtx<T>, false>(P, c, grav);
       }
       else if (algo == MB_ABA)
       {
