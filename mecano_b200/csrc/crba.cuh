@@ -27,25 +27,6 @@ template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
    return I;
 }
 
-// F expressed in the parent of a 1-DoF joint: (R0 Rz(q), p0) applied to a force vector without forming the matrix
-template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T s, T cs, const SvT<T> &f)
-{
-   M3T<T> R0;
-   V3T<T> p;
-   ld_xf0<T>(C, R0, p);
-   SvT<T> g = f, r;
-   if (REV)
-   {
-      g.a.x = cs * f.a.x - s * f.a.y; g.a.y = s * f.a.x + cs * f.a.y;
-      g.l.x = cs * f.l.x - s * f.l.y; g.l.y = s * f.l.x + cs * f.l.y;
-   }
-   else
-      p = p + s * v3<T>(R0.xz, R0.yz, R0.zz);
-   r.l = mul(R0, g.l);
-   r.a = mul(R0, g.a) + cross(p, r.l);
-   return r;
-}
-
 // M[dof_j .. , col] = S_j^T F and the mirrored entries (setSymmetricEntry, :704-705, :790-791)
 template <class T, class Ctx> MB_HD void crba_project(Ctx &c, int jt, int dj, int col, const SvT<T> &F)
 {

@@ -167,6 +167,15 @@ template <class T, class CP> MB_HD RbiT<T> ld_rbi(const CP C)
    cst_ld2(C, 9, r.h.x, r.h.y); cst_ld2(C, 10, r.h.z, r.m);
    return r;
 }
+// the body as Newton-Euler sees it: inertia about the CoM J (34..39), CoM position c (31..33), mass (21)
+template <class T, class CP> MB_HD void ld_com_inertia(const CP C, S3T<T> &J, V3T<T> &cp, T &m)
+{
+   static_assert(MB_C_J == 34 && MB_C_C == 31 && MB_C_M == 21, "record layout");
+   T u0, u1;
+   cst_ld2(C, 17, J.xx, J.xy); cst_ld2(C, 18, J.xz, J.yy); cst_ld2(C, 19, J.yz, J.zz);
+   cst_ld2(C, 15, u0, cp.x); cst_ld2(C, 16, cp.y, cp.z);
+   cst_ld2(C, 10, u1, m);
+}
 // CoM pose in the joint frame: E (22..30), c (31..33)
 template <class T, class CP> MB_HD void ld_com(const CP C, M3T<T> &E, V3T<T> &cp)
 {
@@ -194,6 +203,25 @@ template <class T, bool REV, class CP> MB_HD XfT<T> joint_xf_1dof(const CP C, T 
       X.p = p0 + s * v3<T>(R0.xz, R0.yz, R0.zz);
    }
    return X;
+}
+
+// F expressed in the parent of a 1-DoF joint: (R0 Rz(q), p0) applied to a force vector without forming the matrix
+template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T s, T cs, const SvT<T> &f)
+{
+   M3T<T> R0;
+   V3T<T> p;
+   ld_xf0<T>(C, R0, p);
+   SvT<T> g = f, r;
+   if (REV)
+   {
+      g.a.x = cs * f.a.x - s * f.a.y; g.a.y = s * f.a.x + cs * f.a.y;
+      g.l.x = cs * f.l.x - s * f.l.y; g.l.y = s * f.l.x + cs * f.l.y;
+   }
+   else
+      p = p + s * v3<T>(R0.xz, R0.yz, R0.zz);
+   r.l = mul(R0, g.l);
+   r.a = mul(R0, g.a) + cross(p, r.l);
+   return r;
 }
 
 // SixDoF (FloatingJointReadOnly.java:34-37): R = R0 R(quat), p = p0 + R0 pos; configuration rows [qx qy qz qs x y z]

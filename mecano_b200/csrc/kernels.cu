@@ -134,10 +134,8 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
          continue; // work areas too small
       if (forced >= 0 && cfg != forced)
          continue;
-      // measured (profiles/r01f_cfg_sweep.jsonl): the TMEM stack pays off where registers allow 16 warps per SM (RNEA);
-      // ABA is register-bound at 8 warps and CRBA store-bound, both lose to the shared-memory stack
-      if (forced < 0 && kCfg[cfg].tm > 0 && algo != MB_RNEA)
-         continue;
+      // measured (profiles/r01l_cfg_sweep.jsonl): the TMEM stack buys RNEA 16 warps per SM (0.69 vs 0.99 ms) and ABA 12
+      // (384 threads at 168 registers: 1.97 vs 2.10 ms; 512 threads would need 128 registers and spills: 2.96 ms)
       if (!mb_tm_fits(algo, P, kCfg[cfg].tm))
          continue; // the wide stack area (three double2 per level of the tree) exceeds the TMEM columns of one warp
       const int b = kCfg[cfg].block;

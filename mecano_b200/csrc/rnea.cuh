@@ -52,8 +52,11 @@ MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
       a.l.z += pp.x;
    }
    // Newton-Euler (SpatialInertiaReadOnly.java:229-296), about the joint-frame origin
-   const RbiT<T> I = ld_rbi<T>(C);
-   f = mul(I, a) + cross_force(v, mul(I, v));
+   S3T<T> J;
+   V3T<T> cp;
+   T m;
+   ld_com_inertia<T>(C, J, cp, m);
+   f = newton_euler(J, cp, m, v, a);
    if (FEXT)
       f = f - external_wrench<T>(c, ext, C); // :946
    pp.ls = pp.s;
@@ -82,10 +85,9 @@ MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, SvT<T> &f, RneaPipe<T> &pp, T
       T s = pp.ls, cs = pp.lc;
       if (!(o.flags & MB2_LEAF))
          c.jp_ld2(o.slot, o.nslot, 0, s, cs);
-      const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), s, cs);
       SvT<T> acc;
       c.acc_ld(o.pslot, o.pwslot, acc.a.x, acc.a.y, acc.a.z, acc.l.x, acc.l.y, acc.l.z);
-      f = acc + force_to_parent(X, f); // addJointWrenchFromChild (:961-966)
+      f = acc + force_up_1dof<T, REV>(c.cst(o.body), s, cs, f); // addJointWrenchFromChild (:961-966)
       if (o.flags & MB2_STORE_ACC)
          c.acc_st(o.pslot, o.pwslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
    }
@@ -100,8 +102,11 @@ MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
    const SvT<T> aj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
    v = motion_to_child(X, v) + vj;
    a = motion_to_child(X, a) + cross_motion(v, vj) + aj;
-   const RbiT<T> I = ld_rbi<T>(C);
-   f = mul(I, a) + cross_force(v, mul(I, v));
+   S3T<T> J;
+   V3T<T> cp;
+   T m;
+   ld_com_inertia<T>(C, J, cp, m);
+   f = newton_euler(J, cp, m, v, a);
    if (FEXT)
       f = f - external_wrench<T>(c, ext, C);
    c.acc_st(o.slot, o.wslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);

@@ -132,6 +132,19 @@ MB_T SvT<T> mul(const RbiT<T> &I, const SvT<T> &m)
    r.l = I.m * m.l + cross(m.a, I.h);
    return r;
 }
+// Newton-Euler wrench of a rigid body about the frame origin, from the quantities at its centre of mass
+// (SpatialInertiaReadOnly.computeDynamicWrench :229-296, MecanoTools.computeDynamicMomentFast :571 / ForceFast :728, then
+// shifted from the CoM to the origin): with vc = v + w x c, ac = a + wd x c (spatial acceleration a, wd of the origin)
+//   f = m (ac + w x vc),   n = J wd + w x (J w) + c x f      == I a + v x* (I v) with I about the origin, in fewer operations
+MB_T SvT<T> newton_euler(const S3T<T> &J, const V3T<T> &c, T m, const SvT<T> &v, const SvT<T> &a)
+{
+   const V3T<T> vc = v.l + cross(v.a, c);
+   const V3T<T> ac = a.l + cross(a.a, c);
+   SvT<T> r;
+   r.l = m * (ac + cross(v.a, vc));
+   r.a = mul(J, a.a) + cross(v.a, mul(J, v.a)) + cross(c, r.l);
+   return r;
+}
 // IA * m for an articulated inertia
 MB_T SvT<T> mul(const AbiT<T> &I, const SvT<T> &m)
 {
