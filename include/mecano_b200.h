@@ -179,6 +179,20 @@ int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, co
                          const double *fext, double *qdd, uint32_t flags);
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
 
+/*
+ * State integrator: MultiBodySystemStateIntegrator(dt).doubleIntegrateFromAcceleration(joints)
+ * (M/tools/MultiBodySystemStateIntegrator.java:365-470; one-DoF joints :710-733, floating joints :503-560), the step that
+ * follows ForwardDynamicsCalculator.compute() + writeComputedJointAccelerations() in a simulation loop, for N states:
+ *   one-DoF:  q += dt qd + dt^2/2 qdd,  qd += dt qdd
+ *   SixDoF:   SE(3) update of the pose from the body-frame twist / spatial acceleration; the twist and the linear rows of
+ *             the acceleration are re-expressed in the new body frame exactly as the Java code leaves them in the joint
+ * q [n_cfg][ld], qd [n_dofs][ld] and qdd [n_dofs][ld] are updated IN PLACE (qdd: SixDoF linear rows only).  Device / host
+ * pointer variants like the calculators.  Keeping q, qd on the device between mecano_b200_aba and mecano_b200_integrate
+ * gives batched simulation roll-outs with no host round trip.
+ */
+int mecano_b200_integrate(mecano_b200_handle *h, int64_t n_states, int64_t ld, double dt, double *q, double *qd, double *qdd, void *stream);
+int mecano_b200_integrate_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, double dt, double *q, double *qd, double *qdd);
+
 /* Introspection for the benchmark / roofline report. */
 int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info);
 

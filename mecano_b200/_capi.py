@@ -58,7 +58,7 @@ EXPORTS = [
     "mecano_b200_set_gravity", "mecano_b200_set_variant", "mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies",
     "mecano_b200_rnea", "mecano_b200_aba", "mecano_b200_crba", "mecano_b200_rnea_host", "mecano_b200_aba_host",
     "mecano_b200_crba_host", "mecano_b200_kernel_info_get", "mecano_b200_measure_fp64_peak", "mecano_b200_measure_hbm_peak",
-    "mecano_b200_host_alloc", "mecano_b200_host_free", "mecano_b200_generate_source", "mecano_b200_jit_check", "mecano_b200_specialize",
+    "mecano_b200_integrate", "mecano_b200_integrate_host", "mecano_b200_host_alloc", "mecano_b200_host_free", "mecano_b200_generate_source", "mecano_b200_jit_check", "mecano_b200_specialize",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -78,6 +78,8 @@ lib.mecano_b200_crba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32, c_vp]
 lib.mecano_b200_rnea_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
 lib.mecano_b200_aba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
 lib.mecano_b200_crba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32]
+lib.mecano_b200_integrate.argtypes = [c_vp, c_i64, c_i64, ctypes.c_double, c_vp, c_vp, c_vp, c_vp]
+lib.mecano_b200_integrate_host.argtypes = [c_vp, c_i64, c_i64, ctypes.c_double, c_vp, c_vp, c_vp]
 lib.mecano_b200_kernel_info_get.argtypes = [c_vp, ctypes.c_int, c_i64, ctypes.POINTER(KernelInfo)]
 lib.mecano_b200_measure_fp64_peak.argtypes = [ctypes.c_int, c_dp]
 lib.mecano_b200_measure_hbm_peak.argtypes = [ctypes.c_int, c_dp]

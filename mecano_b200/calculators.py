@@ -191,3 +191,37 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
             self._engine.crba_host(q, massMatrix, layout)
         self._M = massMatrix
         return massMatrix
+
+
+class MultiBodySystemStateIntegrator:
+    """Batched mirror of M/tools/MultiBodySystemStateIntegrator.java (:26-70 constructor / setIntegrationDT, :365-470
+    doubleIntegrateFromAcceleration): q, qd and the SixDoF rows of qdd of N states are updated in place on the GPU.  The
+    reference reads and writes the joint objects of one system; here the system is given once and the state matrices
+    ([nCfg, N], [nDoFs, N], [nDoFs, N], JointMatrixIndexProvider order) per call."""
+
+    def __init__(self, input, dt=float("nan"), device=0, engine=None):
+        if isinstance(input, RigidBody):
+            input = MultiBodySystem.toMultiBodySystemBasics(input)
+        self._input = input
+        self._engine = engine if engine is not None else Engine(input.tables().contents, device, keepalive=input)
+        self.setIntegrationDT(dt)
+
+    def setIntegrationDT(self, dt):
+        self._dt = float(dt)
+
+    def getIntegrationDT(self):
+        return self._dt
+
+    def doubleIntegrateFromAcceleration(self, q, qd, qdd):
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        for name, m, rows in (("q", q, nq), ("qd", qd, nv), ("qdd", qdd, nv)):
+            if m is None or m.ndim != 2 or m.shape[0] != rows or m.shape[1] != n:
+                raise MatrixDimensionException("%s: expected a %d x %d matrix, got %s" % (name, rows, n, None if m is None else tuple(m.shape)))
+        if self._dt != self._dt:
+            raise ValueError("integration dt has not been set")
+        if _is_torch(q):
+            self._engine.integrate(self._dt, q, qd, qdd)
+        else:
+            self._engine.integrate_host(self._dt, q, qd, qdd)
+        return q, qd

@@ -433,7 +433,7 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
       if (algo == MB_RNEA) { opt.block = 512; opt.tm = 32; }
       else { opt.block = 256; opt.tm = 0; }
       spec_cfg_from_env(algo, opt);
-      if (!mb_tm_fits(algo, P, opt.tm))
+      if (!mb_tm_fits(algo, P, opt.tm, opt.block))
          opt.tm = 0; // the wide stack area of a deep tree does not fit the TMEM columns of one warp: shared memory only
       if (opt.tm * 4 > (512 / ((opt.block + 127) / 128) & ~3))
          return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "MECANO_B200_SPEC_CFG: TMEM slots exceed the columns of one warp");
@@ -445,7 +445,7 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
          mb::SpecOptions o2 = opt;
          o2.block = b;
          o2.tm = opt.tm > 0 ? std::min(opt.tm * (opt.block / b), 128) : 0;
-         if (!mb_tm_fits(algo, P, o2.tm))
+         if (!mb_tm_fits(algo, P, o2.tm, o2.block))
             o2.tm = 0;
          int max_optin = 0;
          cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
@@ -505,6 +505,65 @@ int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const dou
                          const double *fext, double *qdd, uint32_t flags)
 {
    return run_host(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, flags);
+}
+
+int mecano_b200_integrate(mecano_b200_handle *h, int64_t n, int64_t ld, double dt, double *q, double *qd, double *qdd, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   if (!(dt == dt)) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "dt is NaN");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   mb::IntegrateJoints J;
+   const MbProgram &P = h->tree.prog[MB_RNEA];
+   J.nb = P.nb;
+   for (int i = 0; i < P.nb; i++)
+   {
+      J.cfg[i] = (uint16_t)P.body[i].cfg_off;
+      J.dof[i] = (uint16_t)P.body[i].dof_off;
+      J.type[i] = (uint8_t)P.body[i].jtype;
+   }
+   mb::IntegrateArgs a;
+   a.q = q; a.qd = qd; a.qdd = qdd;
+   a.n = n; a.ld = ld;
+   a.dt = dt;
+   MB_CUDA(h, mb::launch_integrate_kernel(J, a, h->sm_count, (cudaStream_t)stream));
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_integrate_host(mecano_b200_handle *h, int64_t n, int64_t ld, double dt, double *q, double *qd, double *qdd)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_CUDA(h, cudaSetDevice(h->device));
+   const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + 2 * nv;
+   size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)rows);
+   chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
+   chunk = std::min<size_t>(chunk, ((size_t)n + 255) & ~(size_t)255);
+   rc = ensure_pipeline(h, rows * chunk);
+   if (rc) return rc;
+   int slot = 0;
+   for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk, slot ^= 1)
+   {
+      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
+      cudaStream_t st = h->streams[slot];
+      double *dq = h->stage[slot], *dqd = dq + nq * chunk, *dx = dqd + nv * chunk;
+      MB_CUDA(h, copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, st));
+      MB_CUDA(h, copy_rows(dqd, chunk, qd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
+      MB_CUDA(h, copy_rows(dx, chunk, qdd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
+      rc = mecano_b200_integrate(h, (int64_t)w, (int64_t)chunk, dt, dq, dqd, dx, st);
+      if (rc) return rc;
+      MB_CUDA(h, copy_rows(q + s0, (size_t)ld, dq, chunk, w, nq, cudaMemcpyDeviceToHost, st));
+      MB_CUDA(h, copy_rows(qd + s0, (size_t)ld, dqd, chunk, w, nv, cudaMemcpyDeviceToHost, st));
+      MB_CUDA(h, copy_rows(qdd + s0, (size_t)ld, dx, chunk, w, nv, cudaMemcpyDeviceToHost, st));
+   }
+   MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
+   MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+   return MECANO_B200_OK;
 }
 
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout)

@@ -82,6 +82,8 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    unsigned rb;  // shared address of this thread's element of stage 0, row 0 of the prefetch ring
    unsigned cb;  // shared address of the constant records
    unsigned tm0; // TMEM address (lane quarter << 16 | first column) of wide slot 0 of this warp
+   unsigned wov; // kPartial: shared address such that wide slot w >= TM lives at wov + w * BLOCK * 16
+   static constexpr bool kPartial = TM > 0 && BLOCK == MB_PARTIAL_TM_BLOCK;
    // warp-collective tcgen05.ld/st and the block barriers of specialised kernels need every thread to run every op: the
    // padding lanes of the last tile run the last state again and store the same values to the same addresses
 #if defined(MB_SPEC)
@@ -107,7 +109,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    // register pairs, i.e. on the doubles where they are; scoreboarded like any load).  The narrow area stays in shared memory.
    __device__ __forceinline__ void acc_ld(int slot2, int wslot, double &x0, double &x1, double &x2, double &x3, double &x4, double &x5) const
    {
-      if (TM > 0)
+      if (TM > 0 && (!kPartial || wslot < TM))
       {
          const unsigned t = tm0 + 4u * (unsigned)wslot;
          unsigned r[12];
@@ -121,7 +123,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       }
       else
       {
-         const unsigned t = sb + (unsigned)(slot2 * (BLOCK * 16));
+         const unsigned t = TM > 0 ? wov + (unsigned)(wslot * (BLOCK * 16)) : sb + (unsigned)(slot2 * (BLOCK * 16));
          mb_lds2(t, x0, x1);
          mb_lds2(t + BLOCK * 16, x2, x3);
          mb_lds2(t + 2 * BLOCK * 16, x4, x5);
@@ -129,7 +131,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    }
    __device__ __forceinline__ void acc_st(int slot2, int wslot, double x0, double x1, double x2, double x3, double x4, double x5)
    {
-      if (TM > 0)
+      if (TM > 0 && (!kPartial || wslot < TM))
       {
          const unsigned t = tm0 + 4u * (unsigned)wslot;
          const double x[6] = {x0, x1, x2, x3, x4, x5};
@@ -139,7 +141,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       }
       else
       {
-         const unsigned t = sb + (unsigned)(slot2 * (BLOCK * 16));
+         const unsigned t = TM > 0 ? wov + (unsigned)(wslot * (BLOCK * 16)) : sb + (unsigned)(slot2 * (BLOCK * 16));
          mb_sts2(t, x0, x1);
          mb_sts2(t + BLOCK * 16, x2, x3);
          mb_sts2(t + 2 * BLOCK * 16, x4, x5);
@@ -239,12 +241,13 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
 
 // columns of tensor memory one warp owns when BLOCK / 32 warps share the four lane quarters
 __host__ __device__ constexpr int tm_warp_cols(int block) { return (512 / ((block + 127) / 128)) & ~3; }
+static_assert(MB_PARTIAL_TM_BLOCK == 640, "kCfg / tm_warp_cols assume 20 warps for the partial-TMEM block");
 
 // Skeleton of a block: TMEM allocation, context set-up, the loop over tiles of BLOCK states; `body(ctx)` evaluates one
 // state.  ncst = doubles of constant records staged at the front of shared memory (0 for specialised kernels),
 // stack2 = stack slots (double2) per state.
 template <int ALGO, bool STATE_MAJOR, int BLOCK, int AUXN, int TM, class Body>
-__device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int ncst, const int smem_slots, Body body)
+__device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int ncst, const int smem_slots, const int nstack2, Body body)
 {
    static_assert(TM * 4 <= tm_warp_cols(BLOCK), "TMEM stack slots exceed the columns of one warp");
    static_assert(TM == 0 || ALGO != MB_CRBA, "CRBA keeps its (narrow-only) stack in shared memory");
@@ -276,6 +279,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    c2.sb = c2.cb + 8u * (unsigned)((ncst + 1) & ~1) + 16u * threadIdx.x;
    c2.rb = c2.cb + 8u * (unsigned)(((ncst + 1) & ~1) + 2 * smem_slots * BLOCK) + 8u * threadIdx.x;
    c2.tm0 = 0;
+   c2.wov = c2.sb + (unsigned)((nstack2 - TM) * (BLOCK * 16));
    if (TM > 0)
    {
       const unsigned warp = threadIdx.x >> 5;

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
    for (int i = threadIdx.x; i < ncst; i += BLOCK)
       mb_smem[i] = a.consts[i];
    using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
-   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), [&](Ctx &c2) {
+   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), P.nstack2, [&](Ctx &c2) {
       if constexpr (ALGO == MB_RNEA)
          rnea_state<double, Ctx, FEXT>(P, c2, a.grav);
       else if constexpr (ALGO == MB_ABA)
@@ -54,9 +54,10 @@ struct Cfg
 {
    int block, cls, tm;
 };
-constexpr int kNumCfg = 14;
+constexpr int kNumCfg = 15;
 constexpr Cfg kCfg[kNumCfg] = {{512, 0, 32}, {384, 0, 42}, {320, 0, 42}, {256, 0, 64}, {384, 0, 0}, {320, 0, 0}, {256, 0, 0},
-                               {192, 0, 0},  {128, 0, 0},  {256, 1, 64}, {128, 1, 128}, {128, 1, 0}, {64, 1, 0},  {32, 1, 0}};
+                               {192, 0, 0},  {128, 0, 0},  {256, 1, 64}, {128, 1, 128}, {128, 1, 0}, {64, 1, 0},  {32, 1, 0},
+                               {640, 0, 24}};
 
 typedef void (*KernelFn)(const MbProgram, const KernelArgs);
 
@@ -70,7 +71,7 @@ template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
       // CRBA has no wide stack area: its TMEM configurations are never planned (mb_tm_fits) and alias the shared-memory kernels
 #define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, ALGO == MB_CRBA ? 0 : kCfg[i].tm>;
       MB_CFG_CASE(0) MB_CFG_CASE(1) MB_CFG_CASE(2) MB_CFG_CASE(3) MB_CFG_CASE(4) MB_CFG_CASE(5) MB_CFG_CASE(6)
-      MB_CFG_CASE(7) MB_CFG_CASE(8) MB_CFG_CASE(9) MB_CFG_CASE(10) MB_CFG_CASE(11) MB_CFG_CASE(12)
+      MB_CFG_CASE(7) MB_CFG_CASE(8) MB_CFG_CASE(9) MB_CFG_CASE(10) MB_CFG_CASE(11) MB_CFG_CASE(12) MB_CFG_CASE(14)
 #undef MB_CFG_CASE
       default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, ALGO == MB_CRBA ? 0 : kCfg[13].tm>;
    }
@@ -136,7 +137,11 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
          continue;
       // measured (profiles/r01l_cfg_sweep.jsonl): the TMEM stack buys RNEA 16 warps per SM (0.69 vs 0.99 ms) and ABA 12
       // (384 threads at 168 registers: 1.97 vs 2.10 ms; 512 threads would need 128 registers and spills: 2.96 ms)
-      if (!mb_tm_fits(algo, P, kCfg[cfg].tm))
+      // 640 threads (five warps per sub-partition, 96 registers, deepest wide slots in shared memory) measured slower than
+      // 512 (H37 RNEA 0.694 vs 0.656 ms, profiles/r01n_cfg_sweep.jsonl): kept for sweeps only
+      if (forced < 0 && kCfg[cfg].block == MB_PARTIAL_TM_BLOCK)
+         continue;
+      if (!mb_tm_fits(algo, P, kCfg[cfg].tm, kCfg[cfg].block))
          continue; // the wide stack area (three double2 per level of the tree) exceeds the TMEM columns of one warp
       const int b = kCfg[cfg].block;
       const size_t sm = smem_bytes(algo, P, b, kCfg[cfg].tm);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "kernel_args.h"
 #include "program.h"
 
@@ -32,6 +34,21 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
 bool warp_variant_supports(const MbProgram &P);
 cudaError_t launch_warp_kernel(int algo, const MbProgram *device_program, const KernelArgs &a, int max_children, int max_ndof, int sm_count, cudaStream_t stream);
 cudaError_t warp_kernel_attributes(int algo, bool fext, cudaFuncAttributes *attr);
+
+// batched state integrator (integrate.cu): MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration
+struct IntegrateJoints
+{
+   int32_t nb;
+   uint16_t cfg[MB_MAX_BODIES], dof[MB_MAX_BODIES]; // Mecano configuration / DoF row of each joint
+   uint8_t type[MB_MAX_BODIES];                     // MB_REVOLUTE / MB_PRISMATIC / MB_SIXDOF
+};
+struct IntegrateArgs
+{
+   double *q, *qd, *qdd; // updated in place (qdd: SixDoF linear rows only)
+   long long n, ld;
+   double dt;
+};
+cudaError_t launch_integrate_kernel(const IntegrateJoints &J, const IntegrateArgs &a, int sm_count, cudaStream_t stream);
 
 // roofline denominators
 cudaError_t measure_fp64_peak(double *tflops);

@@ -160,12 +160,21 @@ __host__ __device__
 #endif
 static inline int mb_smem_stack_slots(int algo, const MbProgram &P, int tm)
 {
-   int s = (tm > 0 && algo != MB_CRBA) ? P.nstack2 : P.stack2;
+   int s = P.stack2;
+   if (tm > 0 && algo != MB_CRBA)
+      s = P.nstack2 + (P.wstack2 > tm ? P.wstack2 - tm : 0); // wide slots beyond the TMEM share spill over behind the narrow area
    if (algo == MB_ABA && s < 20)
       s = 20;
    return s < 1 ? 1 : s;
 }
+// Blocks of MB_PARTIAL_TM_BLOCK threads (20 warps: five per TMEM lane quarter, 100 columns each) hold the first tm wide slots
+// in tensor memory and the deeper ones in shared memory, chosen per access by a warp-uniform test; all other block sizes
+// require the whole wide area to fit so that the test folds away at compile time.
+#define MB_PARTIAL_TM_BLOCK 640
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline bool mb_tm_fits(int algo, const MbProgram &P, int tm) { return tm == 0 || (algo != MB_CRBA && P.wstack2 <= tm); }
+static inline bool mb_tm_fits(int algo, const MbProgram &P, int tm, int block)
+{
+   return tm == 0 || (algo != MB_CRBA && (P.wstack2 <= tm || block == MB_PARTIAL_TM_BLOCK));
+}

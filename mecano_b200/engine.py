@@ -129,6 +129,21 @@ class Engine:
         check(lib.mecano_b200_crba(self._h, n, ld, pq, pm, layout, self._stream()), self._h)
         return M
 
+    def integrate(self, dt, q, qd, qdd):
+        """doubleIntegrateFromAcceleration on device matrices, in place."""
+        n = q.shape[1]
+        pq, l0 = _dev_ptr_ld(q, self.nq, n)
+        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
+        pqdd, l2 = _dev_ptr_ld(qdd, self.nv, n)
+        check(lib.mecano_b200_integrate(self._h, n, _same_ld([l0, l1, l2]), float(dt), pq, pqd, pqdd, self._stream()), self._h)
+
+    def integrate_host(self, dt, q, qd, qdd):
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        pqd, l1 = _host_ptr_ld(qd, self.nv, n)
+        pqdd, l2 = _host_ptr_ld(qdd, self.nv, n)
+        check(lib.mecano_b200_integrate_host(self._h, n, _same_ld([l0, l1, l2]), float(dt), pq, pqd, pqdd), self._h)
+
     # ---- host entry points (synchronous; inputs/outputs in host memory, pinned for full speed)
     def rnea_host(self, q, qd, qdd, tau, fext=None, flags=0):
         n = q.shape[1]

@@ -936,6 +936,107 @@ void mo_crba(const mo_tree *t, const double *q, double *M)
  * calculator instance per thread, like one cloned MultiBodySystem + calculator per thread in Java,
  * M/tools/MultiBodySystemFactories.java:310).  Plain pthreads, static contiguous slices. */
 
+/* ------------------------------------------------------------------------------------------------
+ * State integrator: MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration
+ * (tools/MultiBodySystemStateIntegrator.java:365-470 dispatch, :503-560 floating joints, :710-733 one-DoF joints).
+ * q, qd and -- for SixDoF joints -- qdd are updated in place, exactly as the Java code updates the joint objects.
+ * Third-party arithmetic restated from its published definition (Euclid 0.21.0, not vendored):
+ *   Quaternion.setRotationVector (RotationVectorConversion -> QuaternionConversion): q = [r/|r| sin(|r|/2), cos(|r|/2)],
+ *   identity below |r| = 1e-12;  Quaternion.append = Hamilton product q0 * qi;  Quaternion.transform /
+ *   inverseTransform = rotation by the (normalised) quaternion and by its conjugate.
+ * ------------------------------------------------------------------------------------------------ */
+static void quat_mul(const double *a, const double *b, double *c) /* (x y z s) Hamilton product a * b */
+{
+   const double ax = a[0], ay = a[1], az = a[2], as = a[3], bx = b[0], by = b[1], bz = b[2], bs = b[3];
+   c[0] = as * bx + ax * bs + ay * bz - az * by;
+   c[1] = as * by - ax * bz + ay * bs + az * bx;
+   c[2] = as * bz + ax * by - ay * bx + az * bs;
+   c[3] = as * bs - ax * bx - ay * by - az * bz;
+}
+
+static void quat_from_rotation_vector(const double *r, double *q4)
+{
+   const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+   if (n < 1.0e-12)
+   {
+      q4[0] = q4[1] = q4[2] = 0.0;
+      q4[3] = 1.0;
+      return;
+   }
+   const double sh = sin(0.5 * n) / n;
+   q4[0] = r[0] * sh;
+   q4[1] = r[1] * sh;
+   q4[2] = r[2] * sh;
+   q4[3] = cos(0.5 * n);
+}
+
+void mo_integrate(const mo_tree *t, double dt, double *q, double *qd, double *qdd)
+{
+   const double half_dt_dt = 0.5 * dt * dt;
+   for (int i = 0; i < t->nb; i++)
+   {
+      double *qi = q + t->cfg_off[i], *vi = qd + t->dof_off[i], *ai = qdd + t->dof_off[i];
+      if (t->jtype[i] != MO_SIXDOF)
+      {
+         /* :710-733  q += 0.5 dt^2 qdd + dt qd ; qd += dt qdd */
+         const double q0 = qi[0], v0 = vi[0], a0 = ai[0];
+         qi[0] = half_dt_dt * a0 + dt * v0 + q0;
+         vi[0] = dt * a0 + v0;
+         continue;
+      }
+      /* :503-560, doubleIntegrate(spatialAcceleration, initialTwist, initialPose, finalTwist, finalPose) */
+      const double *w0 = vi, *v0 = vi + 3, *wd = ai;
+      double lin[3], R0[9], rv[3], qint[4], Ri[9], dp[3], tmp[3], vfin[3], wfin[3], qfin[4];
+      /* linear acceleration of the body origin (SpatialAccelerationReadOnly.java:197-204): a + w x v */
+      lin[0] = ai[3]; lin[1] = ai[4]; lin[2] = ai[5];
+      v3_add_cross(w0, v0, lin);
+      for (int k = 0; k < 3; k++)
+         rv[k] = dt * w0[k] + half_dt_dt * wd[k];
+      quat_from_rotation_vector(rv, qint);
+      for (int k = 0; k < 3; k++)
+         wfin[k] = dt * wd[k] + w0[k];
+      /* position: p += R(q0) (dt v + 0.5 dt^2 a_origin) */
+      rot_quaternion(qi, R0);
+      for (int k = 0; k < 3; k++)
+         tmp[k] = dt * v0[k] + half_dt_dt * lin[k];
+      m3_mulv(R0, tmp, dp);
+      /* linear velocity: (v + dt a_origin) re-expressed in the new body frame */
+      rot_quaternion(qint, Ri);
+      for (int k = 0; k < 3; k++)
+         tmp[k] = dt * lin[k] + v0[k];
+      m3_tmulv(Ri, tmp, vfin);
+      /* orientation: q0 * q_integrated */
+      quat_mul(qi, qint, qfin);
+      /* acceleration: origin acceleration in the new frame, back to spatial form with the final twist
+       * (FixedFrameSpatialAccelerationBasics.java:81-90): linear = a_origin' + v' x w' */
+      double lin2[3];
+      m3_tmulv(Ri, lin, lin2);
+      v3_add_cross(vfin, wfin, lin2);
+      for (int k = 0; k < 4; k++)
+         qi[k] = qfin[k];
+      for (int k = 0; k < 3; k++)
+      {
+         qi[4 + k] += dp[k];
+         vi[k] = wfin[k];
+         vi[3 + k] = vfin[k];
+         ai[3 + k] = lin2[k];
+      }
+   }
+}
+
+void mo_integrate_batch(const mo_tree *t, double dt, long n, long ld, double *q, double *qd, double *qdd)
+{
+   double qs[512], vs[512], as[512];
+   for (long s = 0; s < n; s++)
+   {
+      for (int k = 0; k < t->nq; k++) qs[k] = q[k * ld + s];
+      for (int k = 0; k < t->nv; k++) { vs[k] = qd[k * ld + s]; as[k] = qdd[k * ld + s]; }
+      mo_integrate(t, dt, qs, vs, as);
+      for (int k = 0; k < t->nq; k++) q[k * ld + s] = qs[k];
+      for (int k = 0; k < t->nv; k++) { qd[k * ld + s] = vs[k]; qdd[k * ld + s] = as[k]; }
+   }
+}
+
 int mo_max_threads(void)
 {
    long n = sysconf(_SC_NPROCESSORS_ONLN);

@@ -73,6 +73,11 @@ void mo_aba_batch(const mo_tree *t, const double *gravity3, long n, long ld, con
                   const double *fext, double *qdd, int nthreads);
 void mo_crba_batch(const mo_tree *t, long n, long ld, const double *q, double *M, int nthreads);
 
+/* MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration (tools/MultiBodySystemStateIntegrator.java:365-470, :503-560,
+ * :710-733): q, qd and the SixDoF rows of qdd are updated in place.  Batched form: same buffer layout as above. */
+void mo_integrate(const mo_tree *t, double dt, double *q, double *qd, double *qdd);
+void mo_integrate_batch(const mo_tree *t, double dt, long n, long ld, double *q, double *qd, double *qdd);
+
 int mo_max_threads(void);
 
 #ifdef __cplusplus

@@ -84,6 +84,18 @@ class Oracle:
         self.lib.mo_crba(ctypes.byref(self.c), _d(q), _d(M))
         return M
 
+    def integrate(self, dt, q, qd, qdd):
+        """doubleIntegrateFromAcceleration on one state; returns the updated (q, qd, qdd) copies."""
+        q, qd, qdd = (np.array(x, dtype=np.float64, copy=True) for x in (q, qd, qdd))
+        self.lib.mo_integrate(ctypes.byref(self.c), ctypes.c_double(dt), _d(q), _d(qd), _d(qdd))
+        return q, qd, qdd
+
+    def integrate_batch(self, dt, q, qd, qdd):
+        q, qd, qdd = (np.array(x, dtype=np.float64, copy=True, order="C") for x in (q, qd, qdd))
+        n = q.shape[1]
+        self.lib.mo_integrate_batch(ctypes.byref(self.c), ctypes.c_double(dt), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(qd), _d(qdd))
+        return q, qd, qdd
+
     # ---- batched, [k, s] buffers
     def rnea_batch(self, q, qd, qdd, fext=None, flags=0, nthreads=0):
         q, qd, qdd, fext = map(self._f64, (q, qd, qdd, fext))
