@@ -276,6 +276,27 @@ def main():
             tf = fl * n / (ms * 1e-3) / 1e12
             entry.update({"algorithmic_flops_per_state": fl, "achieved_tflops": tf, "fp64_frac": tf / fp64_peak})
         kernels[name] = entry
+    # ---- next-row kernels, timed outside the step: the state integrator that follows ABA in a roll-out
+    extras = {}
+    if rank == 0:
+        integ = mb.MultiBodySystemStateIntegrator(system, 1.0e-3, engine=fdyn._engine)
+        iq, iqd, iqdd = q.clone(), qd.clone(), qdd_out.clone()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            integ.doubleIntegrateFromAcceleration(iq, iqd, iqdd)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            integ.doubleIntegrateFromAcceleration(iq, iqd, iqdd)
+        e1.record()
+        torch.cuda.synchronize()
+        ims = e0.elapsed_time(e1) / reps
+        n6 = sum(1 for j in system.getJointsToConsider() if j.getDegreesOfFreedom() == 6)
+        ibytes = 8.0 * (5 * (nb - n6) + 35 * n6)  # one-DoF: read q, qd, qdd, write q, qd; SixDoF: read 19 rows, write 16
+        extras["integrate"] = {"ms": ims, "states_per_s": n / (ims * 1e-3), "algorithmic_bytes_per_state": ibytes,
+                               "achieved_gbs": ibytes * n / (ims * 1e-3) / 1e9, "hbm_frac": ibytes * n / (ims * 1e-3) / 1e9 / hbm_peak,
+                               "what": "MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration, in place, %d states" % n}
+        del iq, iqd, iqdd
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine
     # balance (FP64 pipe), CRBA below it (HBM, write-dominated).  MEASURED_PEAKS.json has no FP64 figure, so the FP64
@@ -311,7 +332,7 @@ def main():
             "config": {"workload": workload_name(args.neck, n), "states_per_gpu": n, "n_dofs": nv, "n_cfg": nq, "n_bodies": nb,
                        "parallelism": "disjoint state slices per GPU, no collective", "l2": "inputs (%.2f GB/step) and outputs larger than L2; no explicit flush"
                        % (8.0 * (3 * nq + 4 * nv) * n / 1e9), "humanoid_seed": HUMANOID_SEED, "mass_matrix_layout": "entry-major [nv*nv][N]"},
-            "roofline": roofline, "kernels": kernels, "gpu_launches": 3 * args.steps, "clocks": clocks,
+            "roofline": roofline, "kernels": kernels, "extras": extras, "gpu_launches": 3 * args.steps, "clocks": clocks,
         }
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload (rank 0, N = 1 only)

@@ -34,6 +34,12 @@ const char *mecano_model_last_error(const mecano_model *m);
 int mecano_model_add_revolute_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12, const double *axis3);
 int mecano_model_add_prismatic_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12, const double *axis3);
 int mecano_model_add_sixdof_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
+/* FixedJoint (M/multiBodySystem/FixedJoint.java:40-62): 0 DoF.  Host-only: at finalize its successor is welded into the nearest
+ * moving ancestor (inertia, children and offsets), so the GPU tables contain moving joints only. */
+#define MECANO_MODEL_FIXED 3
+int mecano_model_add_fixed_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
+/* Configuration a joint keeps when it is ignored (one-DoF: q; SixDoF: qx qy qz qs x y z); default zero / identity. */
+int mecano_model_set_joint_configuration(mecano_model *m, int joint, const double *q, int n);
 /* RigidBody(name, parentJoint, momentOfInertia, mass, inertiaPose).  Returns the body id (= joint id + 1). */
 int mecano_model_add_rigid_body(mecano_model *m, const char *name, int parent_joint, const double *inertia9, double mass, const double *inertia_pose12);
 
@@ -45,6 +51,10 @@ int mecano_model_next_humanoid(mecano_model *m, uint64_t seed, int neck_joints);
 
 /* toMultiBodySystemBasics(rootBody): fixes the joint order / index provider and builds the tables. */
 int mecano_model_finalize(mecano_model *m);
+/* MultiBodySystemBasics.toMultiBodySystemBasics(rootBody, jointsToIgnore) (MultiBodySystemBasics.java:90-142): the listed joints
+ * and their descendants are left out of the index provider; the inertia of each ignored subtree is lumped into its parent body
+ * at the joints' stored configuration (InverseDynamicsCalculator.java:236, :832-860; MultiBodySystemTools.java:32-64). */
+int mecano_model_finalize_ignoring(mecano_model *m, const int32_t *joints_to_ignore, int n_ignore);
 int mecano_model_n_joints(const mecano_model *m);
 int mecano_model_n_dofs(const mecano_model *m);
 int mecano_model_n_cfg(const mecano_model *m);

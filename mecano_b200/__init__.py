@@ -9,5 +9,5 @@ from ._capi import MecanoB200Error  # noqa: F401
 from .calculators import (CompositeRigidBodyMassMatrixCalculator, ForwardDynamicsCalculator, InverseDynamicsCalculator,  # noqa: F401
                           MatrixDimensionException, MultiBodySystemStateIntegrator)
 from .engine import Engine, measure_fp64_peak, measure_hbm_peak  # noqa: F401
-from .multibody import (JointMatrixIndexProvider, MultiBodySystem, MultiBodySystemRandomTools, PrismaticJoint, RevoluteJoint,  # noqa: F401
+from .multibody import (FixedJoint, JointMatrixIndexProvider, MultiBodySystem, MultiBodySystemRandomTools, PrismaticJoint, RevoluteJoint,  # noqa: F401
                         RigidBody, RigidBodyTransform, ScrewTheoryException, SixDoFJoint)

@@ -52,6 +52,9 @@ class _BatchedCalculator:
     def setExternalWrenches(self, wrenches):
         """External wrench on the successor of every joint, [6 * nJoints, N] in JointMatrixIndexProvider order, each
         expressed in its body's CoM frame (setExternalWrench, InverseDynamicsCalculator.java:469-472, :819)."""
+        if wrenches is not None and self._input.hasWeldedBodies():
+            # a wrench on a welded body would have to be re-expressed on the body it was folded into; refuse rather than drop it
+            raise NotImplementedError("external wrenches are not supported on systems with fixed or ignored joints")
         self._fext = wrenches
 
     def setExternalWrenchesToZero(self):

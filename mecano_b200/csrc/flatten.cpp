@@ -307,11 +307,13 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
    }
    if (d->wrench_index)
    {
-      std::vector<char> used(nb, 0);
+      // ranks in the caller's joint list: distinct, and small enough for 6 * w + 5 to stay a 16-bit row (a list may hold more
+      // joints than the tree has bodies: fixed joints are folded away by the host model before the tables are built)
+      std::vector<char> used(10922, 0);
       for (int b = 0; b < nb; b++)
-         if (d->wrench_index[b] < 0 || d->wrench_index[b] >= nb || used[d->wrench_index[b]]++)
+         if (d->wrench_index[b] < 0 || d->wrench_index[b] >= 10922 || used[d->wrench_index[b]]++)
          {
-            err = "wrench_index must be a permutation of 0..n_bodies-1";
+            err = "wrench_index must hold distinct ranks in [0, 10922)";
             return MECANO_B200_ERR_SHAPE;
          }
    }

@@ -91,7 +91,9 @@ static int add_joint(mecano_model *m, int type, const char *name, int pred, cons
       const RigidBodyTransform T = to_transform(t12);
       const std::string n = name ? name : "joint" + std::to_string(m->joints.size());
       Joint *j = nullptr;
-      if (type == MECANO_B200_SIXDOF)
+      if (type == MECANO_MODEL_FIXED)
+         j = m->arena.newJoint<FixedJoint>(n, m->bodies[pred], T);
+      else if (type == MECANO_B200_SIXDOF)
          j = m->arena.newJoint<SixDoFJoint>(n, m->bodies[pred], T);
       else
       {
@@ -119,6 +121,21 @@ int mecano_model_add_prismatic_joint(mecano_model *m, const char *name, int pred
 int mecano_model_add_sixdof_joint(mecano_model *m, const char *name, int pred, const double *t12)
 {
    return add_joint(m, MECANO_B200_SIXDOF, name, pred, t12, nullptr);
+}
+
+int mecano_model_add_fixed_joint(mecano_model *m, const char *name, int pred, const double *t12)
+{
+   return add_joint(m, MECANO_MODEL_FIXED, name, pred, t12, nullptr);
+}
+
+int mecano_model_set_joint_configuration(mecano_model *m, int joint, const double *q, int n)
+{
+   return guarded(m, [&]() -> int {
+      if (joint < 0 || joint >= (int)m->joints.size()) return fail(m, "joint id out of range");
+      if (!q || n != m->joints[joint]->getConfigurationMatrixSize()) return fail(m, "configuration size does not match the joint");
+      m->joints[joint]->setJointConfiguration(q, n);
+      return 0;
+   });
 }
 
 int mecano_model_add_rigid_body(mecano_model *m, const char *name, int joint, const double *inertia9, double mass, const double *pose12)
@@ -178,7 +195,9 @@ int mecano_model_next_humanoid(mecano_model *m, uint64_t seed, int neck_joints)
    });
 }
 
-int mecano_model_finalize(mecano_model *m)
+int mecano_model_finalize(mecano_model *m) { return mecano_model_finalize_ignoring(m, nullptr, 0); }
+
+int mecano_model_finalize_ignoring(mecano_model *m, const int32_t *joints_to_ignore, int n_ignore)
 {
    if (!m) return -1;
    if (m->finalized) return 0;
@@ -186,8 +205,17 @@ int mecano_model_finalize(mecano_model *m)
    {
       for (size_t j = 0; j < m->joints.size(); j++)
          if (!m->bodies[j + 1]) return fail(m, "joint " + m->joints[j]->getName() + " has no successor");
-      m->system = MultiBodySystem::toMultiBodySystemBasics(m->bodies[0]);
-      if (m->system.getJointsToConsider().empty()) return fail(m, "the system has no joints");
+      std::vector<Joint *> ignore;
+      for (int k = 0; k < n_ignore; k++)
+      {
+         if (!joints_to_ignore || joints_to_ignore[k] < 0 || joints_to_ignore[k] >= (int)m->joints.size()) return fail(m, "joint id to ignore out of range");
+         ignore.push_back(m->joints[joints_to_ignore[k]]);
+      }
+      m->system = MultiBodySystem::toMultiBodySystemBasics(m->bodies[0], ignore);
+      bool moving = false;
+      for (const Joint *j : m->system.getJointsToConsider())
+         moving = moving || j->getDegreesOfFreedom() > 0;
+      if (!moving) return fail(m, "the system has no moving joints");
       m->tables = FlatTables::flatten(m->system);
       m->tables.bind(m->system.getNumberOfDoFs(), m->system.getConfigurationMatrixSize());
       m->finalized = true;

@@ -58,7 +58,40 @@ class ScrewTheoryException : public std::runtime_error // M/exceptions/ScrewTheo
 
 class RigidBody;
 
-enum class JointType { Revolute = MECANO_B200_REVOLUTE, Prismatic = MECANO_B200_PRISMATIC, SixDoF = MECANO_B200_SIXDOF };
+// Fixed joints (M/multiBodySystem/FixedJoint.java) exist on the host only: the flattener welds their successor into the
+// nearest moving ancestor, so the kernels never see them.
+enum class JointType { Revolute = MECANO_B200_REVOLUTE, Prismatic = MECANO_B200_PRISMATIC, SixDoF = MECANO_B200_SIXDOF, Fixed = 3 };
+
+// ---- small rigid-transform / inertia algebra used when bodies are welded together at flatten time
+inline Matrix3D matmul(const Matrix3D &A, const Matrix3D &B)
+{
+   Matrix3D C;
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+         C.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+   return C;
+}
+inline Matrix3D transposed(const Matrix3D &A)
+{
+   Matrix3D C;
+   for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+         C.m[3 * i + j] = A.m[3 * j + i];
+   return C;
+}
+inline Vector3D matvec(const Matrix3D &A, const Vector3D &v)
+{
+   return Vector3D{A.m[0] * v.x + A.m[1] * v.y + A.m[2] * v.z, A.m[3] * v.x + A.m[4] * v.y + A.m[5] * v.z, A.m[6] * v.x + A.m[7] * v.y + A.m[8] * v.z};
+}
+// a then b, both "child in parent": x_parent = A (B x + tb) + ta
+inline RigidBodyTransform compose(const RigidBodyTransform &a, const RigidBodyTransform &b)
+{
+   RigidBodyTransform c;
+   c.rotation = matmul(a.rotation, b.rotation);
+   const Vector3D t = matvec(a.rotation, b.translation);
+   c.translation = Vector3D{t.x + a.translation.x, t.y + a.translation.y, t.z + a.translation.z};
+   return c;
+}
 
 class Joint
 {
@@ -74,6 +107,45 @@ class Joint
    // transform from frameBeforeJoint to the predecessor's frameAfterJoint (identity when constructed with null)
    const RigidBodyTransform &getTransformToParent() const { return transformToParent_; }
    void setSuccessor(RigidBody *successor) { successor_ = successor; }
+   // The configuration a joint has when it is ignored (MultiBodySystemBasics.toMultiBodySystemBasics(root, jointsToIgnore)):
+   // Mecano lumps the inertia of an ignored subtree into its parent body at the configuration the joints have when the
+   // calculator is built (InverseDynamicsCalculator.java:236, :832-860).  One-DoF: q; SixDoF: qx qy qz qs x y z.  Default: zero.
+   void setJointConfiguration(const double *q, int n) { q_.assign(q, q + n); }
+   const std::vector<double> &getJointConfiguration() const { return q_; }
+   // frameAfterJoint in frameBeforeJoint at the stored configuration (MecanoFactories.java:231-260,
+   // PrismaticJointReadOnly.java:18-22, FloatingJointReadOnly.java:34-37)
+   RigidBodyTransform getJointTransform() const
+   {
+      RigidBodyTransform X;
+      if (type_ == JointType::Revolute)
+      {
+         const double q = q_.empty() ? 0.0 : q_[0], c = std::cos(q), s = std::sin(q), t = 1.0 - c;
+         const double x = axis_.x, y = axis_.y, z = axis_.z;
+         const double R[9] = {t * x * x + c, t * x * y - s * z, t * x * z + s * y, t * x * y + s * z, t * y * y + c, t * y * z - s * x,
+                              t * x * z - s * y, t * y * z + s * x, t * z * z + c};
+         for (int i = 0; i < 9; i++) X.rotation.m[i] = R[i];
+      }
+      else if (type_ == JointType::Prismatic)
+      {
+         const double q = q_.empty() ? 0.0 : q_[0];
+         X.translation = Vector3D{q * axis_.x, q * axis_.y, q * axis_.z};
+      }
+      else if (type_ == JointType::SixDoF && q_.size() == 7)
+      {
+         double qx = q_[0], qy = q_[1], qz = q_[2], qs = q_[3];
+         const double n = std::sqrt(qx * qx + qy * qy + qz * qz + qs * qs);
+         if (n > 1e-14)
+         {
+            qx /= n; qy /= n; qz /= n; qs /= n;
+            const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qs * qz), 2 * (qx * qz + qs * qy), 2 * (qx * qy + qs * qz),
+                                 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qs * qx), 2 * (qx * qz - qs * qy), 2 * (qy * qz + qs * qx),
+                                 1 - 2 * (qx * qx + qy * qy)};
+            for (int i = 0; i < 9; i++) X.rotation.m[i] = R[i];
+         }
+         X.translation = Vector3D{q_[4], q_[5], q_[6]};
+      }
+      return X;
+   }
 
  protected:
    Joint(std::string name, RigidBody *predecessor, const RigidBodyTransform *transformToParent, JointType type);
@@ -83,6 +155,7 @@ class Joint
    RigidBodyTransform transformToParent_;
    JointType type_;
    Vector3D axis_{0, 0, 1};
+   std::vector<double> q_;
 };
 
 class RigidBody
@@ -183,16 +256,34 @@ class SixDoFJoint : public Joint
    int getConfigurationMatrixSize() const override { return 7; }
 };
 
-// MultiBodySystemBasics.toMultiBodySystemBasics(rootBody) + JointMatrixIndexProvider
+// FixedJoint (M/multiBodySystem/FixedJoint.java:40-62): 0 DoF, welds its successor to its predecessor
+class FixedJoint : public Joint
+{
+ public:
+   FixedJoint(std::string name, RigidBody *predecessor) : Joint(std::move(name), predecessor, nullptr, JointType::Fixed) {}
+   FixedJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform &transformToParent)
+       : Joint(std::move(name), predecessor, &transformToParent, JointType::Fixed) {}
+   int getDegreesOfFreedom() const override { return 0; }
+   int getConfigurationMatrixSize() const override { return 0; }
+};
+
+// MultiBodySystemBasics.toMultiBodySystemBasics(rootBody[, jointsToIgnore]) + JointMatrixIndexProvider
 class MultiBodySystem
 {
  public:
-   static MultiBodySystem toMultiBodySystemBasics(RigidBody *rootBody)
+   // A joint is ignored if it is in jointsToIgnore or a descendant of one (MultiBodySystemReadOnly.java:284-300)
+   static MultiBodySystem toMultiBodySystemBasics(RigidBody *rootBody, const std::vector<Joint *> &jointsToIgnore = {})
    {
       if (!rootBody)
          throw std::invalid_argument("rootBody can not be null");
       MultiBodySystem s;
       s.root_ = rootBody;
+      auto ignored = [&](const Joint *j) {
+         for (const Joint *k : jointsToIgnore)
+            if (k == j)
+               return true;
+         return false;
+      };
       // SubtreeStreams.fromChildren: depth-first pre-order (JointIterator.java:153-162)
       std::vector<Joint *> stack(rootBody->getChildrenJoints().rbegin(), rootBody->getChildrenJoints().rend());
       while (!stack.empty())
@@ -201,6 +292,11 @@ class MultiBodySystem
          stack.pop_back();
          if (!j->getSuccessor())
             throw ScrewTheoryException("joint " + j->getName() + " has no successor");
+         if (ignored(j))
+         {
+            s.ignored_.push_back(j); // the roots of the ignored subtrees
+            continue;
+         }
          s.dofIndex_.push_back(s.nDoFs_);
          s.cfgIndex_.push_back(s.nCfg_);
          s.nDoFs_ += j->getDegreesOfFreedom();
@@ -212,6 +308,14 @@ class MultiBodySystem
       }
       return s;
    }
+   bool isIgnoredSubtreeRoot(const Joint *j) const
+   {
+      for (const Joint *k : ignored_)
+         if (k == j)
+            return true;
+      return false;
+   }
+   const std::vector<Joint *> &getIgnoredSubtreeRoots() const { return ignored_; }
    RigidBody *getRootBody() const { return root_; }
    const std::vector<Joint *> &getJointsToConsider() const { return joints_; } // == getIndexedJointsInOrder()
    int getNumberOfDoFs() const { return nDoFs_; }
@@ -231,7 +335,7 @@ class MultiBodySystem
 
  private:
    RigidBody *root_ = nullptr;
-   std::vector<Joint *> joints_;
+   std::vector<Joint *> joints_, ignored_;
    std::vector<int> dofIndex_, cfgIndex_;
    int nDoFs_ = 0, nCfg_ = 0;
 };
@@ -244,16 +348,69 @@ struct FlatTables
    std::vector<int> body_of_joint; // DFS joint index -> row in the tables
    mecano_b200_tree_desc desc{};
 
+   // mass, first moment and second moment (about the frame origin, frame axes) of a set of bodies welded together
+   struct Lump
+   {
+      double m = 0, h[3] = {0, 0, 0}, I[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      // body with inertia J about its CoM (CoM frame axes), CoM pose P in the body frame, body frame at X in the lump frame
+      void add(const RigidBody &b, const RigidBodyTransform &X)
+      {
+         const RigidBodyTransform C = compose(X, b.getInertiaPose()); // CoM frame in the lump frame
+         const Matrix3D J = matmul(matmul(C.rotation, b.getMomentOfInertia()), transposed(C.rotation));
+         const double mass = b.getMass(), c[3] = {C.translation.x, C.translation.y, C.translation.z};
+         const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+         m += mass;
+         for (int i = 0; i < 3; i++)
+         {
+            h[i] += mass * c[i];
+            for (int j = 0; j < 3; j++)
+               I[3 * i + j] += J.m[3 * i + j] + mass * ((i == j ? cc : 0.0) - c[i] * c[j]);
+         }
+      }
+   };
+
+   // Everything rigidly attached to `body` (whose frame is at X in the lump frame): the body itself, the successors of its
+   // FixedJoint children and -- at their stored configuration -- whole ignored subtrees (computeSubtreeInertia,
+   // M/tools/MultiBodySystemTools.java:32-64; InverseDynamicsCalculator.java:832-860).
+   static void weld(const MultiBodySystem &sys, const RigidBody &body, const RigidBodyTransform &X, bool whole_subtree, Lump &lump)
+   {
+      lump.add(body, X);
+      for (const Joint *c : body.getChildrenJoints())
+      {
+         const bool ign = whole_subtree || sys.isIgnoredSubtreeRoot(c);
+         if (!ign && c->getType() != JointType::Fixed)
+            continue; // a moving, considered joint: its successor is a body of its own
+         if (!c->getSuccessor())
+            continue;
+         RigidBodyTransform Xc = compose(X, c->getTransformToParent());
+         if (ign)
+            Xc = compose(Xc, c->getJointTransform());
+         weld(sys, *c->getSuccessor(), Xc, ign, lump);
+      }
+   }
+
    static FlatTables flatten(const MultiBodySystem &sys)
    {
       FlatTables f;
       const auto &joints = sys.getJointsToConsider();
-      const int nb = (int)joints.size();
-      std::vector<int> depth(nb), parent_dfs(nb);
-      int nlev = 0;
-      for (int i = 0; i < nb; i++)
+      const int nj = (int)joints.size();
+      // moving joints become the bodies of the tables; fixed joints are folded into the offset of the moving joints below them
+      std::vector<int> depth(nj, 0), parent_dfs(nj, -1);
+      std::vector<RigidBodyTransform> offset((size_t)nj);
+      int nlev = 0, nb = 0;
+      for (int i = 0; i < nj; i++)
       {
-         RigidBody *pred = joints[i]->getPredecessor();
+         if (joints[i]->getType() == JointType::Fixed)
+            continue;
+         nb++;
+         RigidBodyTransform X = joints[i]->getTransformToParent();
+         const RigidBody *pred = joints[i]->getPredecessor();
+         while (!pred->isRootBody() && pred->getParentJoint()->getType() == JointType::Fixed)
+         {
+            X = compose(pred->getParentJoint()->getTransformToParent(), X);
+            pred = pred->getParentJoint()->getPredecessor();
+         }
+         offset[(size_t)i] = X;
          parent_dfs[i] = pred->isRootBody() ? -1 : sys.indexOf(pred->getParentJoint());
          depth[i] = parent_dfs[i] < 0 ? 0 : depth[parent_dfs[i]] + 1;
          nlev = std::max(nlev, depth[i] + 1);
@@ -263,12 +420,12 @@ struct FlatTables
       for (int l = 0; l < nlev; l++)
       {
          f.level_start[l] = (int)order.size();
-         for (int i = 0; i < nb; i++)
-            if (depth[i] == l)
+         for (int i = 0; i < nj; i++)
+            if (joints[i]->getType() != JointType::Fixed && depth[i] == l)
                order.push_back(i);
       }
       f.level_start[nlev] = nb;
-      f.body_of_joint.assign(nb, -1);
+      f.body_of_joint.assign(nj, -1);
       for (int r = 0; r < nb; r++)
          f.body_of_joint[order[r]] = r;
       for (int r = 0; r < nb; r++)
@@ -282,14 +439,37 @@ struct FlatTables
          f.cfg_offset.push_back(sys.cfgIndexAt(i));
          f.wrench_index.push_back(i); // external wrenches are handed over in joint (index-provider) order
          f.axis.insert(f.axis.end(), {j->getJointAxis().x, j->getJointAxis().y, j->getJointAxis().z});
-         const RigidBodyTransform &T = j->getTransformToParent();
+         const RigidBodyTransform &T = offset[(size_t)i];
          f.offset_rot.insert(f.offset_rot.end(), T.rotation.m, T.rotation.m + 9);
          f.offset_pos.insert(f.offset_pos.end(), {T.translation.x, T.translation.y, T.translation.z});
-         const RigidBodyTransform &P = b->getInertiaPose();
-         f.com_rot.insert(f.com_rot.end(), P.rotation.m, P.rotation.m + 9);
-         f.com_pos.insert(f.com_pos.end(), {P.translation.x, P.translation.y, P.translation.z});
-         f.inertia.insert(f.inertia.end(), b->getMomentOfInertia().m, b->getMomentOfInertia().m + 9);
-         f.mass.push_back(b->getMass());
+         bool welded = false;
+         for (const Joint *c : b->getChildrenJoints())
+            welded = welded || c->getType() == JointType::Fixed || sys.isIgnoredSubtreeRoot(c);
+         if (!welded)
+         {
+            const RigidBodyTransform &P = b->getInertiaPose();
+            f.com_rot.insert(f.com_rot.end(), P.rotation.m, P.rotation.m + 9);
+            f.com_pos.insert(f.com_pos.end(), {P.translation.x, P.translation.y, P.translation.z});
+            f.inertia.insert(f.inertia.end(), b->getMomentOfInertia().m, b->getMomentOfInertia().m + 9);
+            f.mass.push_back(b->getMass());
+            continue;
+         }
+         // the body plus what is welded to it, as one rigid body: CoM frame = joint frame axes at the common CoM
+         Lump lump;
+         weld(sys, *b, RigidBodyTransform(), false, lump);
+         double c[3] = {0, 0, 0};
+         if (lump.m > 0)
+            for (int k = 0; k < 3; k++)
+               c[k] = lump.h[k] / lump.m;
+         const double cc = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+         Matrix3D Jc, I3;
+         for (int a = 0; a < 3; a++)
+            for (int bq = 0; bq < 3; bq++)
+               Jc.m[3 * a + bq] = lump.I[3 * a + bq] - lump.m * ((a == bq ? cc : 0.0) - c[a] * c[bq]);
+         f.com_rot.insert(f.com_rot.end(), I3.m, I3.m + 9);
+         f.com_pos.insert(f.com_pos.end(), {c[0], c[1], c[2]});
+         f.inertia.insert(f.inertia.end(), Jc.m, Jc.m + 9);
+         f.mass.push_back(lump.m);
       }
       f.bind(sys.getNumberOfDoFs(), sys.getConfigurationMatrixSize());
       return f;

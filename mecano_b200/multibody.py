@@ -29,6 +29,9 @@ lib.mecano_model_last_error.restype = ctypes.c_char_p
 lib.mecano_model_add_revolute_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp, _dp]
 lib.mecano_model_add_prismatic_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp, _dp]
 lib.mecano_model_add_sixdof_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp]
+lib.mecano_model_add_fixed_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp]
+lib.mecano_model_set_joint_configuration.argtypes = [_vp, ctypes.c_int, _dp, ctypes.c_int]
+lib.mecano_model_finalize_ignoring.argtypes = [_vp, _ip, ctypes.c_int]
 lib.mecano_model_add_rigid_body.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp, ctypes.c_double, _dp]
 lib.mecano_model_next_one_dof_joint_chain.argtypes = [_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_double]
 lib.mecano_model_next_one_dof_joint_tree.argtypes = [_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_double]
@@ -49,7 +52,8 @@ lib.mecano_model_table_row.argtypes = [_vp, ctypes.c_int]
 
 MODEL_EXPORTS = [
     "mecano_model_create", "mecano_model_destroy", "mecano_model_last_error", "mecano_model_add_revolute_joint",
-    "mecano_model_add_prismatic_joint", "mecano_model_add_sixdof_joint", "mecano_model_add_rigid_body",
+    "mecano_model_add_prismatic_joint", "mecano_model_add_sixdof_joint", "mecano_model_add_fixed_joint", "mecano_model_add_rigid_body",
+    "mecano_model_set_joint_configuration", "mecano_model_finalize_ignoring",
     "mecano_model_next_one_dof_joint_chain", "mecano_model_next_one_dof_joint_tree", "mecano_model_next_floating_base",
     "mecano_model_next_humanoid", "mecano_model_finalize", "mecano_model_n_joints", "mecano_model_n_dofs", "mecano_model_n_cfg",
     "mecano_model_joint_order", "mecano_model_joint_info", "mecano_model_joint_name", "mecano_model_body_name",
@@ -113,7 +117,7 @@ class _Model:
         for j in range(len(self.joints), n):
             jt, pred = ctypes.c_int32(), ctypes.c_int32()
             lib.mecano_model_joint_info(self.h, j, ctypes.byref(jt), ctypes.byref(pred), None, None, None, None, None)
-            cls = {0: RevoluteJoint, 1: PrismaticJoint, 2: SixDoFJoint}[jt.value]
+            cls = {0: RevoluteJoint, 1: PrismaticJoint, 2: SixDoFJoint, 3: FixedJoint}[jt.value]
             joint = cls.__new__(cls)
             joint._adopt(self, j, self.bodies[pred.value])
             body = RigidBody.__new__(RigidBody)
@@ -184,6 +188,8 @@ class Joint:
         tp = None if t12 is None else t12.ctypes.data_as(_dp)
         if self._type == _capi.SIXDOF:
             jid = lib.mecano_model_add_sixdof_joint(m.h, name.encode(), predecessor._id, tp)
+        elif self._type == FIXED:
+            jid = lib.mecano_model_add_fixed_joint(m.h, name.encode(), predecessor._id, tp)
         else:
             ax = np.ascontiguousarray(jointAxis, dtype=np.float64).reshape(3)
             fn = lib.mecano_model_add_revolute_joint if self._type == _capi.REVOLUTE else lib.mecano_model_add_prismatic_joint
@@ -209,10 +215,20 @@ class Joint:
         return self._successor
 
     def getDegreesOfFreedom(self):
-        return 6 if self._type == _capi.SIXDOF else 1
+        return {_capi.SIXDOF: 6, FIXED: 0}.get(self._type, 1)
 
     def getConfigurationMatrixSize(self):
-        return 7 if self._type == _capi.SIXDOF else 1
+        return {_capi.SIXDOF: 7, FIXED: 0}.get(self._type, 1)
+
+    def setJointConfiguration(self, q):
+        """The configuration this joint keeps if it ends up in jointsToIgnore: Mecano lumps an ignored subtree into its parent
+        body at the configuration the joints have when the calculator is built (InverseDynamicsCalculator.java:236,
+        :832-860).  One-DoF: [q] (also setQ); SixDoF: [qx qy qz qs x y z].  Must be called before toMultiBodySystemBasics."""
+        q = np.ascontiguousarray(np.atleast_1d(q), dtype=np.float64)
+        self._model.check(lib.mecano_model_set_joint_configuration(self._model.h, self._id, q.ctypes.data_as(_dp), int(q.size)))
+
+    def setQ(self, q):
+        self.setJointConfiguration([float(q)])
 
     def _info(self):
         jt, pred = ctypes.c_int32(), ctypes.c_int32()
@@ -250,6 +266,19 @@ class SixDoFJoint(Joint):
         self._create(name, predecessor, transformToParent, None)
 
 
+FIXED = 3  # MECANO_MODEL_FIXED (include/mecano_b200_model.h)
+
+
+class FixedJoint(Joint):
+    """FixedJoint(name, predecessor[, transformToParent])  (M/multiBodySystem/FixedJoint.java:40-62): 0 DoF.  Host-only: the
+    flattener welds its successor (inertia, children, offsets) into the nearest moving ancestor, so the GPU tables hold moving
+    joints only and the calculators need no special case."""
+    _type = FIXED
+
+    def __init__(self, name, predecessor, transformToParent=None):
+        self._create(name, predecessor, transformToParent, None)
+
+
 class JointMatrixIndexProvider:
     def __init__(self, joints, dof, cfg):
         self._joints, self._dof, self._cfg = joints, dof, cfg
@@ -269,24 +298,37 @@ class JointMatrixIndexProvider:
 class MultiBodySystem:
     """MultiBodySystemBasics: the tree below a root body with its joint order fixed."""
 
-    def __init__(self, rootBody):
+    def __init__(self, rootBody, jointsToIgnore=None):
         if not rootBody.isRootBody():
             raise ScrewTheoryException("toMultiBodySystemBasics expects the root body")
         m = rootBody._model
-        m.check(lib.mecano_model_finalize(m.h))
+        ignore = np.ascontiguousarray([j._id for j in (jointsToIgnore or [])], dtype=np.int32)
+        if m.finalized and (ignore.size or getattr(m, "ignored_ids", ())):
+            raise ScrewTheoryException("this model was already turned into a system; build the tree again to choose other jointsToIgnore")
+        m.check(lib.mecano_model_finalize_ignoring(m.h, ignore.ctypes.data_as(_ip), int(ignore.size)))
         m.finalized = True
+        m.ignored_ids = tuple(int(i) for i in ignore)
         self._model, self._root = m, rootBody
-        n = lib.mecano_model_n_joints(m.h)
-        ids, dof, cfg = (np.zeros(n, np.int32) for _ in range(3))
-        lib.mecano_model_joint_order(m.h, ids.ctypes.data_as(_ip), dof.ctypes.data_as(_ip), cfg.ctypes.data_as(_ip))
+        n_all = lib.mecano_model_n_joints(m.h)
+        ids, dof, cfg = (np.zeros(n_all, np.int32) for _ in range(3))
+        n = lib.mecano_model_joint_order(m.h, ids.ctypes.data_as(_ip), dof.ctypes.data_as(_ip), cfg.ctypes.data_as(_ip))
+        ids, dof, cfg = ids[:n], dof[:n], cfg[:n]
         self._joints = [m.joints[i] for i in ids]
+        self._ignored = [j for j in m.joints if j not in self._joints]
         self._provider = JointMatrixIndexProvider(self._joints, dof.tolist(), cfg.tolist())
         self._ndofs = lib.mecano_model_n_dofs(m.h)
         self._ncfg = lib.mecano_model_n_cfg(m.h)
 
     @staticmethod
-    def toMultiBodySystemBasics(rootBody):
-        return MultiBodySystem(rootBody)
+    def toMultiBodySystemBasics(rootBody, jointsToIgnore=None):
+        """MultiBodySystemBasics.toMultiBodySystemBasics(rootBody[, jointsToIgnore]) (MultiBodySystemBasics.java:76-142): a joint
+        is ignored if it is listed or descends from a listed joint; the inertia of every ignored subtree is lumped into its
+        parent body at the joints' stored configuration (Joint.setJointConfiguration)."""
+        return MultiBodySystem(rootBody, jointsToIgnore)
+
+    def hasWeldedBodies(self):
+        """True if fixed joints or ignored subtrees were folded into other bodies at flatten time."""
+        return bool(self._ignored) or any(j._type == FIXED for j in self._joints)
 
     def getRootBody(self):
         return self._root
@@ -298,7 +340,7 @@ class MultiBodySystem:
         return list(self._joints)
 
     def getJointsToIgnore(self):
-        return []
+        return list(self._ignored)
 
     def getJointMatrixIndexProvider(self):
         return self._provider
@@ -320,6 +362,8 @@ class MultiBodySystem:
     def describe(self):
         """Plain numpy description in JointMatrixIndexProvider (depth-first) order, read back through the model
         getters (not through the flattener): used by the tests to feed the oracle."""
+        if self.hasWeldedBodies():
+            raise NotImplementedError("describe() lists one body per joint; this system has fixed / ignored joints folded into other bodies")
         nb = len(self._joints)
         out = {
             "nb": nb, "nv": self._ndofs, "nq": self._ncfg,
