@@ -168,6 +168,31 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def owned_zero_entries(system):
+    """Mass-matrix entries (i * nv + j) that couple joints of unrelated branches: zero for every state."""
+    joints = system.getJointsToConsider()
+    prov = system.getJointMatrixIndexProvider()
+    nv = system.getNumberOfDoFs()
+
+    def ancestors(j):
+        out = set()
+        while j is not None:
+            out.add(j)
+            j = j.getPredecessor().getParentJoint()
+        return out
+
+    anc = {j: ancestors(j) for j in joints}
+    zeros = []
+    for a in joints:
+        for b in joints:
+            if a is b or a in anc[b] or b in anc[a]:
+                continue
+            for r in prov.getJointDoFIndices(a):
+                for c in prov.getJointDoFIndices(b):
+                    zeros.append(r * nv + c)
+    return zeros
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -297,6 +322,25 @@ def main():
                                "achieved_gbs": ibytes * n / (ims * 1e-3) / 1e9, "hbm_frac": ibytes * n / (ims * 1e-3) / 1e9 / hbm_peak,
                                "what": "MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration, in place, %d states" % n}
         del iq, iqd, iqdd
+        # the calculator-owned mass matrix (getMassMatrix(q) without an output argument): structurally zero entries are
+        # written by the first call only
+        owned = mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank)
+        for _ in range(3):
+            owned.getMassMatrix(q)
+        e0.record()
+        for _ in range(reps):
+            owned.getMassMatrix(q)
+        e1.record()
+        torch.cuda.synchronize()
+        oms = e0.elapsed_time(e1) / reps
+        nnz = nv * nv - len(set(owned_zero_entries(system)))
+        obytes = 8.0 * (nq + nnz)
+        extras["crba_owned_buffer"] = {"ms": oms, "states_per_s": n / (oms * 1e-3), "algorithmic_bytes_per_state": obytes,
+                                       "achieved_gbs": obytes * n / (oms * 1e-3) / 1e9, "hbm_frac": obytes * n / (oms * 1e-3) / 1e9 / hbm_peak,
+                                       "nonzero_entries": nnz, "entries": nv * nv,
+                                       "what": "CompositeRigidBodyMassMatrixCalculator.getMassMatrix(q) into the calculator's own matrix: the "
+                                               "%d structurally zero entries are written once, not per call (MECANO_B200_CRBA_ZEROS_PRESENT)" % (nv * nv - nnz)}
+        del owned
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine
     # balance (FP64 pipe), CRBA below it (HBM, write-dominated).  MEASURED_PEAKS.json has no FP64 figure, so the FP64
@@ -377,6 +421,30 @@ def main():
                            "h2d_bytes_per_step": int(8 * (nq * 3 + nv * 4) * hn), "d2h_bytes_per_step": int(8 * (2 * nv + nv * nv) * hn),
                            "api": "InverseDynamicsCalculator.compute / ForwardDynamicsCalculator.compute / CompositeRigidBodyMassMatrixCalculator.getMassMatrix "
                                   "on pinned host matrices -> mecano_b200_{rnea,aba,crba}_host", "check": float(np.abs(ntau).max())}
+        # the same step with the mass matrix in the calculator's own (pinned) matrix: from the second call on the structurally
+        # zero entries are not transferred again (extras only: the headline e2e above rewrites and re-reads the dense matrix)
+        if world == 1:
+            del hM, nM
+            owned_h = mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank)
+
+            def host_step_owned():
+                ident.compute(nq_, nqd_, nqdd_, ntau)
+                fdyn.compute(nq_, nqd_, ntau_in, nqdd_out)
+                return owned_h.getMassMatrix(nq_)
+
+            host_step_owned()
+            host_step_owned()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                Mo = host_step_owned()
+            torch.cuda.synchronize()
+            dto = (time.perf_counter() - t0) / args.e2e_steps
+            nnz = nv * nv - len(set(owned_zero_entries(system)))
+            line["extras"]["e2e_owned_mass_matrix"] = {
+                "value": hn / dto, "unit": UNIT, "ms_per_step": dto * 1e3, "h2d_bytes_per_step": int(8 * (nq * 3 + nv * 4) * hn),
+                "d2h_bytes_per_step": int(8 * (2 * nv + nnz) * hn), "check": float(np.abs(Mo).max()),
+                "what": "as e2e, but getMassMatrix(q) returns the calculator-owned pinned matrix: %d of %d entries are structurally zero, "
+                        "written once and not transferred again" % (nv * nv - nnz, nv * nv)}
     elif rank == 0:
         line["e2e"] = None
 

@@ -62,6 +62,12 @@ extern "C" {
 /* mass-matrix layouts for mecano_b200_crba */
 #define MECANO_B200_CRBA_ENTRY_MAJOR 0x0u /* M[(i*nv + j) * ld + s]   (default, coalesced) */
 #define MECANO_B200_CRBA_STATE_MAJOR 0x1u /* M[s * nv*nv + i*nv + j]  (Mecano's per-state dense DMatrixRMaj) */
+/* The entries coupling joints of unrelated branches are zero for every state (they depend on the topology only; half of the
+ * matrix for a humanoid).  A Mecano calculator owns its mass matrix and hands out a reference to it
+ * (CompositeRigidBodyMassMatrixCalculator.java:344-348); a caller that likewise reuses one buffer for one tree may pass this
+ * flag from the second call on: the structurally zero entries are then neither written (device entry point) nor transferred
+ * (host entry point, entry-major layout), everything else is recomputed.  The first call into a buffer must not set it. */
+#define MECANO_B200_CRBA_ZEROS_PRESENT 0x2u
 
 /* kernel selection */
 #define MECANO_B200_VARIANT_AUTO 0

@@ -25,6 +25,7 @@ c_u32 = ctypes.c_uint32
 REVOLUTE, PRISMATIC, SIXDOF = 0, 1, 2
 RNEA_NO_CORIOLIS, RNEA_NO_ACCELERATIONS = 1, 2
 CRBA_ENTRY_MAJOR, CRBA_STATE_MAJOR = 0, 1
+CRBA_ZEROS_PRESENT = 2  # structurally zero entries already hold zeros (same tree, same buffer): not written / transferred again
 ALGO_RNEA, ALGO_ABA, ALGO_CRBA = 0, 1, 2
 
 

@@ -172,6 +172,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
     def __init__(self, input, device=0):
         super().__init__(input, device)
         self._M = None
+        self._owned = {}
 
     def reset(self):
         """Mecano caches the mass matrix until reset(); the batched calculator recomputes on every getMassMatrix(q)."""
@@ -179,21 +180,51 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
 
     def getMassMatrix(self, q, massMatrix=None, stateMajor=False):
         """Mass matrices for N states.  Default layout [nDoFs*nDoFs, N] (entry (i, j) of state s at [i*nDoFs + j, s]);
-        stateMajor=True gives [N, nDoFs*nDoFs], i.e. one Mecano-style dense row-major nDoFs x nDoFs matrix per state."""
+        stateMajor=True gives [N, nDoFs*nDoFs], i.e. one Mecano-style dense row-major nDoFs x nDoFs matrix per state.
+
+        Without `massMatrix` the calculator owns the result like Mecano's does (getMassMatrix() returns a reference to the
+        internal matrix, CompositeRigidBodyMassMatrixCalculator.java:344-348): one buffer per batch shape, reused by later
+        calls.  The entries coupling joints of unrelated branches depend on the topology only, so they are written once and
+        from the second call on neither rewritten nor (host path) transferred again (MECANO_B200_CRBA_ZEROS_PRESENT).  A
+        caller-supplied `massMatrix` is always written in full."""
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
         n = q.shape[1] if q.ndim == 2 else -1
         self._check("q", q, nq, n)
         shape = (n, nv * nv) if stateMajor else (nv * nv, n)
-        if massMatrix is None:
-            massMatrix = self._empty_like(q, *shape, match_ld=not stateMajor)
-        self._check("massMatrix", massMatrix, *shape)
         layout = _capi.CRBA_STATE_MAJOR if stateMajor else _capi.CRBA_ENTRY_MAJOR
+        if massMatrix is None:
+            # entry-major: [nv*nv, n] sharing the leading dimension of q; state-major: one contiguous [n, nv*nv]
+            ld = shape[1] if stateMajor or q.shape[0] < 2 else max(n, q.stride(0) if _is_torch(q) else q.strides[0] // 8)
+            key = (n, ld, bool(stateMajor), str(q.device) if _is_torch(q) else "host")
+            if key not in self._owned:
+                self._owned.clear()  # one live result, like the reference
+                self._owned[key] = [self._new_owned(q, shape, ld), False]
+            massMatrix, primed = self._owned[key]
+            if primed:
+                layout |= _capi.CRBA_ZEROS_PRESENT
+            self._owned[key][1] = True
+        self._check("massMatrix", massMatrix, *shape)
         if _is_torch(q):
             self._engine.crba(q, massMatrix, layout)
         else:
             self._engine.crba_host(q, massMatrix, layout)
         self._M = massMatrix
         return massMatrix
+
+    @staticmethod
+    def _new_owned(q, shape, ld):
+        """[rows, ld] storage viewed as [rows, n]: all matrices of one call share the leading dimension of q."""
+        rows, n = shape
+        if _is_torch(q):
+            import torch
+
+            return torch.empty((rows, ld), dtype=torch.float64, device=q.device)[:, :n]
+        try:  # page-locked, so that the device -> host copies run at full speed and asynchronously
+            import torch
+
+            return torch.empty((rows, ld), dtype=torch.float64).pin_memory().numpy()[:, :n]
+        except Exception:
+            return np.empty((rows, ld), dtype=np.float64)[:, :n]
 
 
 class MultiBodySystemStateIntegrator:

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mecano_b200.h"
@@ -24,6 +25,7 @@ struct mecano_b200_handle
    double *d_consts = nullptr;
    uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
    MbProgram *d_prog = nullptr; // [3] device copies of the traversal programs (warp-per-state kernels)
+   std::vector<std::pair<int, int>> nonzero_runs; // CRBA: (first entry, count) runs of mass-matrix entries that are not structurally zero
    double *d_zero_row = nullptr; // one row of zeros: stands in for qd / qdd when RNEA ignores velocities / accelerations
    size_t zero_row_doubles = 0;
    double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
@@ -99,7 +101,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.ws = nullptr;
       wa.ws_ld = 0;
       wa.zero_entries = h->d_zero;
-      wa.n_zero = (int32_t)h->tree.zero_entries.size();
+      wa.n_zero = (algo == MB_CRBA && (flags & MECANO_B200_CRBA_ZEROS_PRESENT)) ? 0 : (int32_t)h->tree.zero_entries.size();
       wa.n = n; wa.ld = ld;
       wa.ld_qd = wa.ld_x = ld;
       wa.grav[0] = h->gravity[0]; wa.grav[1] = h->gravity[1]; wa.grav[2] = h->gravity[2];
@@ -134,7 +136,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
    a.zero_entries = h->d_zero;
-   a.n_zero = (int32_t)h->tree.zero_entries.size();
+   a.n_zero = (algo == MB_CRBA && (flags & MECANO_B200_CRBA_ZEROS_PRESENT)) ? 0 : (int32_t)h->tree.zero_entries.size();
    a.n = n; a.ld = ld;
    a.ld_qd = a.ld_x = ld;
    if (algo == MB_RNEA && (flags & (MECANO_B200_RNEA_NO_CORIOLIS | MECANO_B200_RNEA_NO_ACCELERATIONS)))
@@ -260,6 +262,13 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
       if (rc) return rc;
       if (state_major)
          MB_CUDA(h, cudaMemcpyAsync(out + (size_t)s0 * nv * nv, dout, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+      else if (algo == MB_CRBA && (flags & MECANO_B200_CRBA_ZEROS_PRESENT))
+      {
+         // entry-major: a structurally zero entry is a whole row of the host matrix, which already holds zeros
+         for (const auto &run : h->nonzero_runs)
+            MB_CUDA(h, copy_rows(out + (size_t)run.first * (size_t)ld + s0, (size_t)ld, dout + (size_t)run.first * chunk, chunk, w, (size_t)run.second,
+                                 cudaMemcpyDeviceToHost, st));
+      }
       else
          MB_CUDA(h, copy_rows(out + s0, (size_t)ld, dout, chunk, w, out_rows, cudaMemcpyDeviceToHost, st));
    }
@@ -319,6 +328,20 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
    const size_t bytes = h->tree.consts.size() * sizeof(double);
    if ((e = cudaMalloc(&h->d_consts, bytes)) != cudaSuccess) return bail(e, "cudaMalloc(consts)");
    if ((e = cudaMemcpy(h->d_consts, h->tree.consts.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(consts)");
+   {
+      std::vector<char> isz((size_t)h->tree.nv * h->tree.nv, 0);
+      for (uint16_t e : h->tree.zero_entries)
+         isz[e] = 1;
+      for (int e = 0; e < (int)isz.size(); e++)
+      {
+         if (isz[(size_t)e])
+            continue;
+         if (!h->nonzero_runs.empty() && h->nonzero_runs.back().first + h->nonzero_runs.back().second == e)
+            h->nonzero_runs.back().second++;
+         else
+            h->nonzero_runs.emplace_back(e, 1);
+      }
+   }
    if (!h->tree.zero_entries.empty())
    {
       const size_t zb = h->tree.zero_entries.size() * sizeof(uint16_t);

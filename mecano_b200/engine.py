@@ -119,7 +119,7 @@ class Engine:
         """M: [nv*nv, n] (entry-major) or [n, nv*nv] (state-major) float64 CUDA tensor."""
         n = q.shape[1]
         pq, ld = _dev_ptr_ld(q, self.nq, n)
-        if layout == _capi.CRBA_ENTRY_MAJOR:
+        if not (layout & _capi.CRBA_STATE_MAJOR):
             pm, lm = _dev_ptr_ld(M, self.nv * self.nv, n)
             ld = _same_ld([ld, lm])
         else:
@@ -168,7 +168,7 @@ class Engine:
     def crba_host(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
         n = q.shape[1]
         pq, ld = _host_ptr_ld(q, self.nq, n)
-        if layout == _capi.CRBA_ENTRY_MAJOR:
+        if not (layout & _capi.CRBA_STATE_MAJOR):
             pm, lm = _host_ptr_ld(M, self.nv * self.nv, n)
             ld = _same_ld([ld, lm])
         else:

@@ -322,3 +322,42 @@ def test_specialize_policy(torch_dev, tmp_path, monkeypatch):
     s7, _ = build(kind="chain", seed=1, n_joints=7)
     assert mb.InverseDynamicsCalculator(s7).specialize().kernelInfo()["specialized"] >= 1
     assert mb.ForwardDynamicsCalculator(s7).specialize().kernelInfo()["specialized"] >= 1
+
+
+@pytest.mark.parametrize("variant", ["thread", "warp"])
+def test_calculator_owned_mass_matrix_skips_structural_zeros_only(torch_dev, variant):
+    """getMassMatrix(q) without an output argument returns the calculator's own buffer (Mecano hands out a reference to its
+    internal matrix, CompositeRigidBodyMassMatrixCalculator.java:344-348); from the second call on the structurally zero
+    entries are neither rewritten nor re-transferred (MECANO_B200_CRBA_ZEROS_PRESENT).  Every call must still equal the
+    oracle in full, on the device path and on the host path."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build("humanoid", 7, 2)
+    o = ol.Oracle(t)
+    nv = s.getNumberOfDoFs()
+    n = 300
+    rng = np.random.default_rng(77)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant(variant)
+    first = None
+    for it in range(3):
+        q = mb.MultiBodySystemRandomTools.nextState(rng, s, n)[0]
+        ref = o.crba_batch(q)
+        M = crba.getMassMatrix(torch.from_numpy(q).to(dev))
+        if first is None:
+            first = M
+        assert M.data_ptr() == first.data_ptr(), "the calculator-owned buffer is reused"
+        assert rel(M.cpu().numpy().reshape(nv, nv, n), ref) <= TOL, (variant, it, "device")
+    host = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant(variant)
+    for it in range(3):
+        q = mb.MultiBodySystemRandomTools.nextState(rng, s, n)[0]
+        ref = o.crba_batch(q)
+        Mh = host.getMassMatrix(q)
+        assert rel(Mh.reshape(nv, nv, n), ref) <= TOL, (variant, it, "host")
+        if it == 1:
+            Mh[:] = np.where(ref.reshape(nv * nv, n) == 0.0, Mh, np.nan)  # poison everything that must be refreshed
+    # a caller-supplied matrix is always written in full
+    mine = torch.full((nv * nv, n), float("nan"), dtype=torch.float64, device=dev)
+    q = mb.MultiBodySystemRandomTools.nextState(rng, s, n)[0]
+    crba.getMassMatrix(torch.from_numpy(q).to(dev), mine)
+    assert rel(mine.cpu().numpy().reshape(nv, nv, n), o.crba_batch(q)) <= TOL
