@@ -124,16 +124,30 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
          cax = (T)0; cay = (T)0;
          clx = vb.a.y * qd; cly = -(vb.a.x * qd);
       }
-      const AbiT<T> Ia = abi_downdate(IA, U, g); // I^a = I^A - U D^-1 U^T
-      SvT<T> pa = pA;                            // p^a = p^A + I^a c + U D^-1 u
-      pa.a.x += Ia.A.xx * cax + Ia.A.xy * cay + Ia.C.xx * clx + Ia.C.xy * cly + k0 * U.a.x;
-      pa.a.y += Ia.A.xy * cax + Ia.A.yy * cay + Ia.C.yx * clx + Ia.C.yy * cly + k0 * U.a.y;
-      pa.a.z += Ia.A.xz * cax + Ia.A.yz * cay + Ia.C.zx * clx + Ia.C.zy * cly + k0 * U.a.z;
-      pa.l.x += Ia.C.xx * cax + Ia.C.yx * cay + Ia.L.xx * clx + Ia.L.xy * cly + k0 * U.l.x;
-      pa.l.y += Ia.C.xy * cax + Ia.C.yy * cay + Ia.L.xy * clx + Ia.L.yy * cly + k0 * U.l.y;
-      pa.l.z += Ia.C.xz * cax + Ia.C.yz * cay + Ia.L.xz * clx + Ia.L.yz * cly + k0 * U.l.z;
+      constexpr int Z = REV ? 1 : 2;
+      const AbiT<T> Ia = abi_downdate<T, Z>(IA, U, g); // I^a = I^A - U D^-1 U^T: zero along the joint's own direction
+      SvT<T> pa = pA;                               // p^a = p^A + I^a c + U D^-1 u
+      if (REV)
+      {
+         pa.a.x += Ia.A.xx * cax + Ia.A.xy * cay + Ia.C.xx * clx + Ia.C.xy * cly + k0 * U.a.x;
+         pa.a.y += Ia.A.xy * cax + Ia.A.yy * cay + Ia.C.yx * clx + Ia.C.yy * cly + k0 * U.a.y;
+         pa.a.z += k0 * U.a.z;
+         pa.l.x += Ia.C.xx * cax + Ia.C.yx * cay + Ia.L.xx * clx + Ia.L.xy * cly + k0 * U.l.x;
+         pa.l.y += Ia.C.xy * cax + Ia.C.yy * cay + Ia.L.xy * clx + Ia.L.yy * cly + k0 * U.l.y;
+         pa.l.z += Ia.C.xz * cax + Ia.C.yz * cay + Ia.L.xz * clx + Ia.L.yz * cly + k0 * U.l.z;
+      }
+      else
+      {
+         // c = [0; w x e_z qd]: only the linear x / y components
+         pa.a.x += Ia.C.xx * clx + Ia.C.xy * cly + k0 * U.a.x;
+         pa.a.y += Ia.C.yx * clx + Ia.C.yy * cly + k0 * U.a.y;
+         pa.a.z += Ia.C.zx * clx + Ia.C.zy * cly + k0 * U.a.z;
+         pa.l.x += Ia.L.xx * clx + Ia.L.xy * cly + k0 * U.l.x;
+         pa.l.y += Ia.L.xy * clx + Ia.L.yy * cly + k0 * U.l.y;
+         pa.l.z += k0 * U.l.z;
+      }
       const XfT<T> X = joint_xf_1dof<T, REV>(C, s, cs);
-      const AbiT<T> K = abi_to_parent(X, Ia); // :1159-1165
+      const AbiT<T> K = abi_to_parent<T, Z>(X, Ia); // :1159-1165
       const SvT<T> Pp = force_to_parent(X, pa);
       if (o.flags & MB2_FIRST_CHILD)
       {
@@ -434,26 +448,28 @@ MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T
    pp.c = nc;
 }
 
-// ---- run steps: as aba_op / aba_pass3_op with the kind (ASCEND / joint type / SC) fixed at compile time (see rnea.cuh)
+// ---- run steps: as aba_op / aba_pass3_op with the kind (ASCEND / joint type) fixed at compile time (see rnea.cuh); whether
+// the op also evaluates the sin/cos of the next joint (SC) is tested at run time, so that a run covers both
 template <class T, class Ctx, bool FEXT, int KIND>
 MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
 {
-   constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0;
+   constexpr bool ASC = (KIND & MB2_ASCEND) != 0;
    constexpr int JT = (KIND >> 1) & 3;
    const MbOp2 o = P.op2[k];
    aba_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, ASC, v, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
+   if (o.code & MB2_SC)
+      mb_sincos(pp.mq, &ns, &nc);
    if (JT == MB_SIXDOF)
    {
-      if (SC) mb_sincos(pp.mq, &ns, &nc);
       if (ASC) aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
       else aba_descend_6dof<T, Ctx>(c, o, v);
    }
    else if (ASC)
-      aba_ascend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, SC>(c, o, ext, v, acc, pacc, pp, ns, nc);
+      aba_ascend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, false>(c, o, ext, v, acc, pacc, pp, ns, nc);
    else
-      aba_descend_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, v, pp, ns, nc);
+      aba_descend_1dof<T, Ctx, JT == MB_REVOLUTE, false>(c, o, v, pp, ns, nc);
    pp.s = ns;
    pp.c = nc;
 }
@@ -461,19 +477,17 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
 template <class T, class Ctx, int KIND>
 MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
-   constexpr bool SC = (KIND & MB2_SC) != 0;
    constexpr int JT = (KIND >> 1) & 3;
    const MbOp2 o = P.op3[k];
    aba_pass3_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, grav, v, a, pp);
    const int st = k & (MB_PF_STAGES - 1);
    T ns = pp.mq, nc = (T)1;
+   if (o.code & MB2_SC)
+      mb_sincos(pp.mq, &ns, &nc);
    if (JT == MB_SIXDOF)
-   {
-      if (SC) mb_sincos(pp.mq, &ns, &nc);
       aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
-   }
    else
-      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, st, v, a, pp, ns, nc);
+      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, false>(c, o, st, v, a, pp, ns, nc);
    pp.s = ns;
    pp.c = nc;
 }
@@ -499,7 +513,6 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       switch (R.kind)
       {
          MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
-         MB_RUN_CASE(8) MB_RUN_CASE(9) MB_RUN_CASE(10) MB_RUN_CASE(11) MB_RUN_CASE(12) MB_RUN_CASE(13)
          default: break;
       }
 #undef MB_RUN_CASE
@@ -519,7 +532,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       break;
       switch (R.kind)
       {
-         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4) MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
+         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4)
          default: break;
       }
 #undef MB_RUN_CASE

@@ -181,6 +181,48 @@ MB_T M3T<T> rot_gen(const M3T<T> &R, const M3T<T> &C)
    return r;
 }
 
+// The same congruences for the structured matrices left by the rank-one downdate of a 1-DoF joint whose axis is the local z
+// axis (abi_downdate<Z>): the row and column of the joint's own direction are exactly zero.
+// R S R^T for symmetric S with S.xz = S.yz = S.zz = 0
+MB_T S3T<T> rot_sym_z0(const M3T<T> &R, const S3T<T> &S)
+{
+   T t00 = R.xx * S.xx + R.xy * S.xy, t01 = R.xx * S.xy + R.xy * S.yy;
+   T t10 = R.yx * S.xx + R.yy * S.xy, t11 = R.yx * S.xy + R.yy * S.yy;
+   T t20 = R.zx * S.xx + R.zy * S.xy, t21 = R.zx * S.xy + R.zy * S.yy;
+   S3T<T> r;
+   r.xx = t00 * R.xx + t01 * R.xy;
+   r.xy = t00 * R.yx + t01 * R.yy;
+   r.xz = t00 * R.zx + t01 * R.zy;
+   r.yy = t10 * R.yx + t11 * R.yy;
+   r.yz = t10 * R.zx + t11 * R.zy;
+   r.zz = t20 * R.zx + t21 * R.zy;
+   return r;
+}
+// R C R^T for C with a zero third row (C.zx = C.zy = C.zz = 0)
+MB_T M3T<T> rot_gen_rowz0(const M3T<T> &R, const M3T<T> &C)
+{
+   M3T<T> t, r;
+   t.xx = R.xx * C.xx + R.xy * C.yx; t.xy = R.xx * C.xy + R.xy * C.yy; t.xz = R.xx * C.xz + R.xy * C.yz;
+   t.yx = R.yx * C.xx + R.yy * C.yx; t.yy = R.yx * C.xy + R.yy * C.yy; t.yz = R.yx * C.xz + R.yy * C.yz;
+   t.zx = R.zx * C.xx + R.zy * C.yx; t.zy = R.zx * C.xy + R.zy * C.yy; t.zz = R.zx * C.xz + R.zy * C.yz;
+   r.xx = t.xx * R.xx + t.xy * R.xy + t.xz * R.xz; r.xy = t.xx * R.yx + t.xy * R.yy + t.xz * R.yz; r.xz = t.xx * R.zx + t.xy * R.zy + t.xz * R.zz;
+   r.yx = t.yx * R.xx + t.yy * R.xy + t.yz * R.xz; r.yy = t.yx * R.yx + t.yy * R.yy + t.yz * R.yz; r.yz = t.yx * R.zx + t.yy * R.zy + t.yz * R.zz;
+   r.zx = t.zx * R.xx + t.zy * R.xy + t.zz * R.xz; r.zy = t.zx * R.yx + t.zy * R.yy + t.zz * R.yz; r.zz = t.zx * R.zx + t.zy * R.zy + t.zz * R.zz;
+   return r;
+}
+// R C R^T for C with a zero third column (C.xz = C.yz = C.zz = 0)
+MB_T M3T<T> rot_gen_colz0(const M3T<T> &R, const M3T<T> &C)
+{
+   M3T<T> r;
+   T t00 = R.xx * C.xx + R.xy * C.yx + R.xz * C.zx, t01 = R.xx * C.xy + R.xy * C.yy + R.xz * C.zy;
+   T t10 = R.yx * C.xx + R.yy * C.yx + R.yz * C.zx, t11 = R.yx * C.xy + R.yy * C.yy + R.yz * C.zy;
+   T t20 = R.zx * C.xx + R.zy * C.yx + R.zz * C.zx, t21 = R.zx * C.xy + R.zy * C.yy + R.zz * C.zy;
+   r.xx = t00 * R.xx + t01 * R.xy; r.xy = t00 * R.yx + t01 * R.yy; r.xz = t00 * R.zx + t01 * R.zy;
+   r.yx = t10 * R.xx + t11 * R.xy; r.yy = t10 * R.yx + t11 * R.yy; r.yz = t10 * R.zx + t11 * R.zy;
+   r.zx = t20 * R.xx + t21 * R.xy; r.zy = t20 * R.yx + t21 * R.yy; r.zz = t20 * R.zx + t21 * R.zy;
+   return r;
+}
+
 // rigid-body inertia of a child expressed in (and about the origin of) the parent frame.
 // With w = R h + (m/2) p:  I' = R I R^T + 2 (w.p) 1 - (w p^T + p w^T),  h' = R h + m p
 // (same result as SpatialInertiaBasics.applyTransform :222-239 with MecanoTools.translateMomentOfInertia :483-547)
@@ -237,12 +279,13 @@ MB_T AbiT<T> operator+(const AbiT<T> &a, const AbiT<T> &b)
 // (ArticulatedBodyInertia.applyTransform :359-375).  Rotate the three blocks, then with t = p:
 //   C' = C + t~ L,   A' = A + t~ C^T + C' t~^T,   L' = L
 // row_i(M t~^T) = t x row_i(M), and t~ C^T = (C t~^T)^T.
-MB_T AbiT<T> abi_to_parent(const XfT<T> &X, const AbiT<T> &I)
+// Z = 0: general;  Z = 1 / 2: I comes out of abi_downdate<1 / 2> (revolute / prismatic joint about the local z axis)
+template <class T, int Z = 0> MB_HD AbiT<T> abi_to_parent(const XfT<T> &X, const AbiT<T> &I)
 {
    AbiT<T> r;
-   S3T<T> A = rot_sym(X.R, I.A);
-   S3T<T> L = rot_sym(X.R, I.L);
-   M3T<T> C = rot_gen(X.R, I.C);
+   S3T<T> A = Z == 1 ? rot_sym_z0(X.R, I.A) : rot_sym(X.R, I.A);
+   S3T<T> L = Z == 2 ? rot_sym_z0(X.R, I.L) : rot_sym(X.R, I.L);
+   M3T<T> C = Z == 1 ? rot_gen_rowz0(X.R, I.C) : (Z == 2 ? rot_gen_colz0(X.R, I.C) : rot_gen(X.R, I.C));
    V3T<T> t = X.p;
    // columns of t~ L: t x L[:,j]
    V3T<T> l0 = cross(t, v3<T>(L.xx, L.xy, L.xz));
@@ -266,17 +309,40 @@ MB_T AbiT<T> abi_to_parent(const XfT<T> &X, const AbiT<T> &I)
    return r;
 }
 
-// IA - U U^T / D, with g = U / D  (rank-one downdate of the three blocks)
-MB_T AbiT<T> abi_downdate(const AbiT<T> &I, const SvT<T> &U, const SvT<T> &g)
+// IA - U U^T / D, with g = U / D  (rank-one downdate of the three blocks).  U is the column of IA along the joint's motion
+// subspace, so that column (and row) of the result is zero: Z = 1 (revolute about z: U = [A(:,z); C(z,:)^T]) and Z = 2
+// (prismatic along z: U = [C(:,z); L(:,z)]) write exact zeros there instead of computing the cancellation.
+template <class T, int Z = 0> MB_HD AbiT<T> abi_downdate(const AbiT<T> &I, const SvT<T> &U, const SvT<T> &g)
 {
    AbiT<T> r;
-   r.A.xx = I.A.xx - U.a.x * g.a.x; r.A.xy = I.A.xy - U.a.x * g.a.y; r.A.xz = I.A.xz - U.a.x * g.a.z;
-   r.A.yy = I.A.yy - U.a.y * g.a.y; r.A.yz = I.A.yz - U.a.y * g.a.z; r.A.zz = I.A.zz - U.a.z * g.a.z;
-   r.L.xx = I.L.xx - U.l.x * g.l.x; r.L.xy = I.L.xy - U.l.x * g.l.y; r.L.xz = I.L.xz - U.l.x * g.l.z;
-   r.L.yy = I.L.yy - U.l.y * g.l.y; r.L.yz = I.L.yz - U.l.y * g.l.z; r.L.zz = I.L.zz - U.l.z * g.l.z;
-   r.C.xx = I.C.xx - U.a.x * g.l.x; r.C.xy = I.C.xy - U.a.x * g.l.y; r.C.xz = I.C.xz - U.a.x * g.l.z;
-   r.C.yx = I.C.yx - U.a.y * g.l.x; r.C.yy = I.C.yy - U.a.y * g.l.y; r.C.yz = I.C.yz - U.a.y * g.l.z;
-   r.C.zx = I.C.zx - U.a.z * g.l.x; r.C.zy = I.C.zy - U.a.z * g.l.y; r.C.zz = I.C.zz - U.a.z * g.l.z;
+   r.A.xx = I.A.xx - U.a.x * g.a.x; r.A.xy = I.A.xy - U.a.x * g.a.y;
+   r.A.yy = I.A.yy - U.a.y * g.a.y;
+   r.L.xx = I.L.xx - U.l.x * g.l.x; r.L.xy = I.L.xy - U.l.x * g.l.y;
+   r.L.yy = I.L.yy - U.l.y * g.l.y;
+   r.C.xx = I.C.xx - U.a.x * g.l.x; r.C.xy = I.C.xy - U.a.x * g.l.y;
+   r.C.yx = I.C.yx - U.a.y * g.l.x; r.C.yy = I.C.yy - U.a.y * g.l.y;
+   if (Z == 1)
+   {
+      r.A.xz = r.A.yz = r.A.zz = (T)0;
+      r.C.zx = r.C.zy = r.C.zz = (T)0;
+   }
+   else
+   {
+      r.A.xz = I.A.xz - U.a.x * g.a.z; r.A.yz = I.A.yz - U.a.y * g.a.z; r.A.zz = I.A.zz - U.a.z * g.a.z;
+      r.C.zx = I.C.zx - U.a.z * g.l.x; r.C.zy = I.C.zy - U.a.z * g.l.y;
+   }
+   if (Z == 2)
+   {
+      r.L.xz = r.L.yz = r.L.zz = (T)0;
+      r.C.xz = r.C.yz = r.C.zz = (T)0;
+   }
+   else
+   {
+      r.L.xz = I.L.xz - U.l.x * g.l.z; r.L.yz = I.L.yz - U.l.y * g.l.z; r.L.zz = I.L.zz - U.l.z * g.l.z;
+      r.C.xz = I.C.xz - U.a.x * g.l.z; r.C.yz = I.C.yz - U.a.y * g.l.z;
+   }
+   if (Z == 0)
+      r.C.zz = I.C.zz - U.a.z * g.l.z;
    return r;
 }
 
