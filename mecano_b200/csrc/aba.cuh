@@ -129,22 +129,22 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
       SvT<T> pa = pA;                               // p^a = p^A + I^a c + U D^-1 u
       if (REV)
       {
-         pa.a.x += Ia.A.xx * cax + Ia.A.xy * cay + Ia.C.xx * clx + Ia.C.xy * cly + k0 * U.a.x;
-         pa.a.y += Ia.A.xy * cax + Ia.A.yy * cay + Ia.C.yx * clx + Ia.C.yy * cly + k0 * U.a.y;
-         pa.a.z += k0 * U.a.z;
-         pa.l.x += Ia.C.xx * cax + Ia.C.yx * cay + Ia.L.xx * clx + Ia.L.xy * cly + k0 * U.l.x;
-         pa.l.y += Ia.C.xy * cax + Ia.C.yy * cay + Ia.L.xy * clx + Ia.L.yy * cly + k0 * U.l.y;
-         pa.l.z += Ia.C.xz * cax + Ia.C.yz * cay + Ia.L.xz * clx + Ia.L.yz * cly + k0 * U.l.z;
+         pa.a.x = fmad(Ia.A.xx, cax, fmad(Ia.A.xy, cay, fmad(Ia.C.xx, clx, fmad(Ia.C.xy, cly, fmad(k0, U.a.x, pa.a.x)))));
+         pa.a.y = fmad(Ia.A.xy, cax, fmad(Ia.A.yy, cay, fmad(Ia.C.yx, clx, fmad(Ia.C.yy, cly, fmad(k0, U.a.y, pa.a.y)))));
+         pa.a.z = fmad(k0, U.a.z, pa.a.z);
+         pa.l.x = fmad(Ia.C.xx, cax, fmad(Ia.C.yx, cay, fmad(Ia.L.xx, clx, fmad(Ia.L.xy, cly, fmad(k0, U.l.x, pa.l.x)))));
+         pa.l.y = fmad(Ia.C.xy, cax, fmad(Ia.C.yy, cay, fmad(Ia.L.xy, clx, fmad(Ia.L.yy, cly, fmad(k0, U.l.y, pa.l.y)))));
+         pa.l.z = fmad(Ia.C.xz, cax, fmad(Ia.C.yz, cay, fmad(Ia.L.xz, clx, fmad(Ia.L.yz, cly, fmad(k0, U.l.z, pa.l.z)))));
       }
       else
       {
          // c = [0; w x e_z qd]: only the linear x / y components
-         pa.a.x += Ia.C.xx * clx + Ia.C.xy * cly + k0 * U.a.x;
-         pa.a.y += Ia.C.yx * clx + Ia.C.yy * cly + k0 * U.a.y;
-         pa.a.z += Ia.C.zx * clx + Ia.C.zy * cly + k0 * U.a.z;
-         pa.l.x += Ia.L.xx * clx + Ia.L.xy * cly + k0 * U.l.x;
-         pa.l.y += Ia.L.xy * clx + Ia.L.yy * cly + k0 * U.l.y;
-         pa.l.z += k0 * U.l.z;
+         pa.a.x = fmad(Ia.C.xx, clx, fmad(Ia.C.xy, cly, fmad(k0, U.a.x, pa.a.x)));
+         pa.a.y = fmad(Ia.C.yx, clx, fmad(Ia.C.yy, cly, fmad(k0, U.a.y, pa.a.y)));
+         pa.a.z = fmad(Ia.C.zx, clx, fmad(Ia.C.zy, cly, fmad(k0, U.a.z, pa.a.z)));
+         pa.l.x = fmad(Ia.L.xx, clx, fmad(Ia.L.xy, cly, fmad(k0, U.l.x, pa.l.x)));
+         pa.l.y = fmad(Ia.L.xy, clx, fmad(Ia.L.yy, cly, fmad(k0, U.l.y, pa.l.y)));
+         pa.l.z = fmad(k0, U.l.z, pa.l.z);
       }
       const XfT<T> X = joint_xf_1dof<T, REV>(C, s, cs);
       const AbiT<T> K = abi_to_parent<T, Z>(X, Ia); // :1159-1165

@@ -205,8 +205,9 @@ template <class T, bool REV, class CP> MB_HD XfT<T> joint_xf_1dof(const CP C, T 
    return X;
 }
 
-// F expressed in the parent of a 1-DoF joint: (R0 Rz(q), p0) applied to a force vector without forming the matrix
-template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T s, T cs, const SvT<T> &f)
+// acc + F expressed in the parent of a 1-DoF joint: (R0 Rz(q), p0) applied to a force vector without forming the matrix, the
+// parent's accumulator riding on the multiply-add chains
+template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof_add(const CP C, T s, T cs, const SvT<T> &f, const SvT<T> &acc)
 {
    M3T<T> R0;
    V3T<T> p;
@@ -219,9 +220,14 @@ template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T 
    }
    else
       p = p + s * v3<T>(R0.xz, R0.yz, R0.zz);
-   r.l = mul(R0, g.l);
-   r.a = mul(R0, g.a) + cross(p, r.l);
+   const V3T<T> l0 = mul(R0, g.l);
+   r.a = mul_add(R0, g.a, cross_add(p, l0, acc.a));
+   r.l = l0 + acc.l;
    return r;
+}
+template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T s, T cs, const SvT<T> &f)
+{
+   return force_up_1dof_add<T, REV>(C, s, cs, f, sv_zero<T>());
 }
 
 // SixDoF (FloatingJointReadOnly.java:34-37): R = R0 R(quat), p = p0 + R0 pos; configuration rows [qx qy qz qs x y z]

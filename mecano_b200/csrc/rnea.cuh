@@ -87,7 +87,7 @@ MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, SvT<T> &f, RneaPipe<T> &pp, T
          c.jp_ld2(o.slot, o.nslot, 0, s, cs);
       SvT<T> acc;
       c.acc_ld(o.pslot, o.pwslot, acc.a.x, acc.a.y, acc.a.z, acc.l.x, acc.l.y, acc.l.z);
-      f = acc + force_up_1dof<T, REV>(c.cst(o.body), s, cs, f); // addJointWrenchFromChild (:961-966)
+      f = force_up_1dof_add<T, REV>(c.cst(o.body), s, cs, f, acc); // addJointWrenchFromChild (:961-966)
       if (o.flags & MB2_STORE_ACC)
          c.acc_st(o.pslot, o.pwslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
    }

@@ -41,6 +41,32 @@ MB_T V3T<T> cross(const V3T<T> &a, const V3T<T> &b)
 {
    return v3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
+// ---- accumulate forms: the addend rides on the multiply-add chain (one FMA per product) instead of costing an extra add.
+// fmad(a, b, c) = a * b + c; for double it is a real FMA on both sides so that the host emulation follows the same path.
+MB_T T fmad(T a, T b, T c) { return a * b + c; }
+#if defined(__CUDA_ARCH__)
+template <> MB_HD double fmad<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+#else
+template <> inline double fmad<double>(double a, double b, double c) { return fma(a, b, c); }
+#endif
+// c + a x b
+MB_T V3T<T> cross_add(const V3T<T> &a, const V3T<T> &b, const V3T<T> &c)
+{
+   return v3<T>(fmad(a.y, b.z, fmad(-a.z, b.y, c.x)), fmad(a.z, b.x, fmad(-a.x, b.z, c.y)), fmad(a.x, b.y, fmad(-a.y, b.x, c.z)));
+}
+// c + R v
+MB_T V3T<T> mul_add(const M3T<T> &R, const V3T<T> &v, const V3T<T> &c)
+{
+   return v3<T>(fmad(R.xx, v.x, fmad(R.xy, v.y, fmad(R.xz, v.z, c.x))), fmad(R.yx, v.x, fmad(R.yy, v.y, fmad(R.yz, v.z, c.y))),
+                fmad(R.zx, v.x, fmad(R.zy, v.y, fmad(R.zz, v.z, c.z))));
+}
+// c + S v for symmetric S
+MB_T V3T<T> mul_add(const S3T<T> &S, const V3T<T> &v, const V3T<T> &c)
+{
+   return v3<T>(fmad(S.xx, v.x, fmad(S.xy, v.y, fmad(S.xz, v.z, c.x))), fmad(S.xy, v.x, fmad(S.yy, v.y, fmad(S.yz, v.z, c.y))),
+                fmad(S.xz, v.x, fmad(S.yz, v.y, fmad(S.zz, v.z, c.z))));
+}
+
 MB_T V3T<T> mul(const M3T<T> &R, const V3T<T> &v)
 {
    return v3<T>(R.xx * v.x + R.xy * v.y + R.xz * v.z, R.yx * v.x + R.yy * v.y + R.yz * v.z, R.zx * v.x + R.zy * v.y + R.zz * v.z);
@@ -98,14 +124,14 @@ MB_T SvT<T> motion_to_child(const XfT<T> &X, const SvT<T> &m)
 {
    SvT<T> r;
    r.a = mulT(X.R, m.a);
-   r.l = mulT(X.R, m.l + cross(m.a, X.p));
+   r.l = mulT(X.R, cross_add(m.a, X.p, m.l));
    return r;
 }
 MB_T SvT<T> force_to_parent(const XfT<T> &X, const SvT<T> &f) // f.a = moment, f.l = force
 {
    SvT<T> r;
    r.l = mul(X.R, f.l);
-   r.a = mul(X.R, f.a) + cross(X.p, r.l);
+   r.a = mul_add(X.R, f.a, cross(X.p, r.l));
    return r;
 }
 // v x m  (motion cross motion), crm(v) m
@@ -113,14 +139,14 @@ MB_T SvT<T> cross_motion(const SvT<T> &v, const SvT<T> &m)
 {
    SvT<T> r;
    r.a = cross(v.a, m.a);
-   r.l = cross(v.a, m.l) + cross(v.l, m.a);
+   r.l = cross_add(v.l, m.a, cross(v.a, m.l));
    return r;
 }
 // v x* f  (motion cross force), crf(v) f
 MB_T SvT<T> cross_force(const SvT<T> &v, const SvT<T> &f)
 {
    SvT<T> r;
-   r.a = cross(v.a, f.a) + cross(v.l, f.l);
+   r.a = cross_add(v.l, f.l, cross(v.a, f.a));
    r.l = cross(v.a, f.l);
    return r;
 }
@@ -128,8 +154,8 @@ MB_T SvT<T> cross_force(const SvT<T> &v, const SvT<T> &f)
 MB_T SvT<T> mul(const RbiT<T> &I, const SvT<T> &m)
 {
    SvT<T> r;
-   r.a = mul(I.I, m.a) + cross(I.h, m.l);
-   r.l = I.m * m.l + cross(m.a, I.h);
+   r.a = mul_add(I.I, m.a, cross(I.h, m.l));
+   r.l = cross_add(m.a, I.h, I.m * m.l);
    return r;
 }
 // Newton-Euler wrench of a rigid body about the frame origin, from the quantities at its centre of mass
@@ -138,19 +164,19 @@ MB_T SvT<T> mul(const RbiT<T> &I, const SvT<T> &m)
 //   f = m (ac + w x vc),   n = J wd + w x (J w) + c x f      == I a + v x* (I v) with I about the origin, in fewer operations
 MB_T SvT<T> newton_euler(const S3T<T> &J, const V3T<T> &c, T m, const SvT<T> &v, const SvT<T> &a)
 {
-   const V3T<T> vc = v.l + cross(v.a, c);
-   const V3T<T> ac = a.l + cross(a.a, c);
+   const V3T<T> vc = cross_add(v.a, c, v.l);
+   const V3T<T> ac = cross_add(a.a, c, a.l);
    SvT<T> r;
-   r.l = m * (ac + cross(v.a, vc));
-   r.a = mul(J, a.a) + cross(v.a, mul(J, v.a)) + cross(c, r.l);
+   r.l = m * cross_add(v.a, vc, ac);
+   r.a = mul_add(J, a.a, cross_add(v.a, mul(J, v.a), cross(c, r.l)));
    return r;
 }
 // IA * m for an articulated inertia
 MB_T SvT<T> mul(const AbiT<T> &I, const SvT<T> &m)
 {
    SvT<T> r;
-   r.a = mul(I.A, m.a) + mul(I.C, m.l);
-   r.l = mulT(I.C, m.a) + mul(I.L, m.l);
+   r.a = mul_add(I.A, m.a, mul(I.C, m.l));
+   r.l = mul_add(I.L, m.l, mulT(I.C, m.a));
    return r;
 }
 
@@ -287,23 +313,21 @@ template <class T, int Z = 0> MB_HD AbiT<T> abi_to_parent(const XfT<T> &X, const
    S3T<T> L = Z == 2 ? rot_sym_z0(X.R, I.L) : rot_sym(X.R, I.L);
    M3T<T> C = Z == 1 ? rot_gen_rowz0(X.R, I.C) : (Z == 2 ? rot_gen_colz0(X.R, I.C) : rot_gen(X.R, I.C));
    V3T<T> t = X.p;
-   // columns of t~ L: t x L[:,j]
-   V3T<T> l0 = cross(t, v3<T>(L.xx, L.xy, L.xz));
-   V3T<T> l1 = cross(t, v3<T>(L.xy, L.yy, L.yz));
-   V3T<T> l2 = cross(t, v3<T>(L.xz, L.yz, L.zz));
+   // columns of C' = C + t~ L: C'[:,j] = C[:,j] + t x L[:,j]
+   const V3T<T> c0 = cross_add(t, v3<T>(L.xx, L.xy, L.xz), v3<T>(C.xx, C.yx, C.zx));
+   const V3T<T> c1 = cross_add(t, v3<T>(L.xy, L.yy, L.yz), v3<T>(C.xy, C.yy, C.zy));
+   const V3T<T> c2 = cross_add(t, v3<T>(L.xz, L.yz, L.zz), v3<T>(C.xz, C.yz, C.zz));
    M3T<T> Cn;
-   Cn.xx = C.xx + l0.x; Cn.xy = C.xy + l1.x; Cn.xz = C.xz + l2.x;
-   Cn.yx = C.yx + l0.y; Cn.yy = C.yy + l1.y; Cn.yz = C.yz + l2.y;
-   Cn.zx = C.zx + l0.z; Cn.zy = C.zy + l1.z; Cn.zz = C.zz + l2.z;
-   // G = (C + C') t~^T : row_i(G) = t x row_i(C + C');  A' = A + sym-part: A'_ij = A_ij + (t x row_i(C'))_j + (t x row_j(C))_i
-   V3T<T> a0 = cross(t, v3<T>(Cn.xx, Cn.xy, Cn.xz)), a1 = cross(t, v3<T>(Cn.yx, Cn.yy, Cn.yz)), a2 = cross(t, v3<T>(Cn.zx, Cn.zy, Cn.zz));
-   V3T<T> b0 = cross(t, v3<T>(C.xx, C.xy, C.xz)), b1 = cross(t, v3<T>(C.yx, C.yy, C.yz)), b2 = cross(t, v3<T>(C.zx, C.zy, C.zz));
-   r.A.xx = A.xx + a0.x + b0.x;
-   r.A.xy = A.xy + a0.y + b1.x;
-   r.A.xz = A.xz + a0.z + b2.x;
-   r.A.yy = A.yy + a1.y + b1.y;
-   r.A.yz = A.yz + a1.z + b2.y;
-   r.A.zz = A.zz + a2.z + b2.z;
+   Cn.xx = c0.x; Cn.xy = c1.x; Cn.xz = c2.x;
+   Cn.yx = c0.y; Cn.yy = c1.y; Cn.yz = c2.y;
+   Cn.zx = c0.z; Cn.zy = c1.z; Cn.zz = c2.z;
+   // A'_ij = A_ij + (t x row_i(C'))_j + (t x row_j(C))_i, every product on one multiply-add chain
+   r.A.xx = fmad(t.y, Cn.xz, fmad(-t.z, Cn.xy, fmad(t.y, C.xz, fmad(-t.z, C.xy, A.xx))));
+   r.A.xy = fmad(t.z, Cn.xx, fmad(-t.x, Cn.xz, fmad(t.y, C.yz, fmad(-t.z, C.yy, A.xy))));
+   r.A.xz = fmad(t.x, Cn.xy, fmad(-t.y, Cn.xx, fmad(t.y, C.zz, fmad(-t.z, C.zy, A.xz))));
+   r.A.yy = fmad(t.z, Cn.yx, fmad(-t.x, Cn.yz, fmad(t.z, C.yx, fmad(-t.x, C.yz, A.yy))));
+   r.A.yz = fmad(t.x, Cn.yy, fmad(-t.y, Cn.yx, fmad(t.z, C.zx, fmad(-t.x, C.zz, A.yz))));
+   r.A.zz = fmad(t.x, Cn.zy, fmad(-t.y, Cn.zx, fmad(t.x, C.zy, fmad(-t.y, C.zx, A.zz))));
    r.C = Cn;
    r.L = L;
    return r;
