@@ -286,6 +286,8 @@ def main():
     fp64_peak = mb.measure_fp64_peak(local_rank) if rank == 0 else 0.0
     flops_path = os.path.join(ROOT, "profiles", "algorithmic_flops.json")
     flops = json.load(open(flops_path)) if os.path.exists(flops_path) else {}
+    exec_path = os.path.join(ROOT, "profiles", "executed_flops.json")
+    exec_flops = json.load(open(exec_path)) if os.path.exists(exec_path) else {}
     key = "H%d" % nv
     kernels = {}
     for name, calc in (("rnea", ident), ("aba", fdyn), ("crba", crba)):
@@ -300,6 +302,10 @@ def main():
         if fl and fp64_peak:
             tf = fl * n / (ms * 1e-3) / 1e12
             entry.update({"algorithmic_flops_per_state": fl, "achieved_tflops": tf, "fp64_frac": tf / fp64_peak})
+            fe = exec_flops.get(key, {}).get(name)
+            if fe:  # what the current routines execute for the same result (fewer: profiles/executed_flops.json)
+                entry.update({"executed_flops_per_state": fe, "executed_tflops": fe * n / (ms * 1e-3) / 1e12,
+                              "fp64_frac_executed": fe * n / (ms * 1e-3) / 1e12 / fp64_peak})
         kernels[name] = entry
     # ---- next-row kernels, timed outside the step: the state integrator that follows ABA in a roll-out
     extras = {}

@@ -227,7 +227,20 @@ template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof_add(const CP C
 }
 template <class T, bool REV, class CP> MB_HD SvT<T> force_up_1dof(const CP C, T s, T cs, const SvT<T> &f)
 {
-   return force_up_1dof_add<T, REV>(C, s, cs, f, sv_zero<T>());
+   M3T<T> R0;
+   V3T<T> p;
+   ld_xf0<T>(C, R0, p);
+   SvT<T> g = f, r;
+   if (REV)
+   {
+      g.a.x = cs * f.a.x - s * f.a.y; g.a.y = s * f.a.x + cs * f.a.y;
+      g.l.x = cs * f.l.x - s * f.l.y; g.l.y = s * f.l.x + cs * f.l.y;
+   }
+   else
+      p = p + s * v3<T>(R0.xz, R0.yz, R0.zz);
+   r.l = mul(R0, g.l);
+   r.a = mul_add(R0, g.a, cross(p, r.l));
+   return r;
 }
 
 // SixDoF (FloatingJointReadOnly.java:34-37): R = R0 R(quat), p = p0 + R0 pos; configuration rows [qx qy qz qs x y z]
