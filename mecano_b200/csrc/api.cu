@@ -167,7 +167,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    {
       const long long ntiles = (n + sk.opt.block - 1) / sk.opt.block;
       // ABA: persistent grid (workspace column per resident thread); RNEA / CRBA: one block per tile
-      const unsigned grid = algo == MB_ABA ? (unsigned)std::min<long long>(ntiles, sk.grid) : (unsigned)ntiles;
+      const unsigned grid = (algo == MB_ABA || sk.opt.tm > 0) ? (unsigned)std::min<long long>(ntiles, sk.grid) : (unsigned)ntiles;
       a.ws_ld = (long long)sk.grid * sk.opt.block;
       MB_CUDA(h, mb::spec_launch(sk, a, grid, stream));
       return MECANO_B200_OK;
