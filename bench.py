@@ -213,6 +213,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL announces its version (and any NCCL_DEBUG output) on stdout; stdout carries the one JSON line and nothing else
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     system = build_system(args.neck)
