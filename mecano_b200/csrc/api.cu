@@ -376,10 +376,11 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
          if ((e = cudaMalloc(&h->d_prog, 3 * sizeof(MbProgram))) != cudaSuccess) return bail(e, "cudaMalloc(programs)");
          if ((e = cudaMemcpy(h->d_prog, h->tree.prog, 3 * sizeof(MbProgram), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(programs)");
       }
-      // crossover batch sizes: linear in the body count through the measured crossovers of A7 (7 bodies) and H37 (32 bodies),
-      // kernel-only times (profiles/r01h_batch_sweep_graph.jsonl): RNEA 3 k / 8 k, ABA 2 k / 3 k, CRBA 2.5 k / 4 k states.
+      // crossover batch sizes: linear in the body count through the measured crossovers of A7 (7 bodies,
+      // profiles/r01h_batch_sweep_graph.jsonl) and H37 (32 bodies, profiles/r01y_batch_sweep.jsonl: the thread-per-state walk
+      // of one state now takes 49 / 96 / 98 us, the warp kernels cross it at 4.8 k / 3.9 k / 3.4 k states).
       // MECANO_B200_WARP_BELOW overrides all three
-      h->warp_below[MB_RNEA] = 2048 + 192 * P.nb; h->warp_below[MB_ABA] = 1536 + 48 * P.nb; h->warp_below[MB_CRBA] = 2048 + 64 * P.nb;
+      h->warp_below[MB_RNEA] = 2048 + 80 * P.nb; h->warp_below[MB_ABA] = 1536 + 64 * P.nb; h->warp_below[MB_CRBA] = 2048 + 40 * P.nb;
       if (const char *e = getenv("MECANO_B200_WARP_BELOW"))
          h->warp_below[0] = h->warp_below[1] = h->warp_below[2] = atoll(e);
    }
