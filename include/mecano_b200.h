@@ -170,6 +170,17 @@ int mecano_b200_rnea(mecano_b200_handle *h, int64_t n_states, int64_t ld, const 
                      const double *fext, double *tau, uint32_t flags, void *stream);
 int mecano_b200_aba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                     const double *fext, double *qdd, uint32_t flags, void *stream);
+/*
+ * RNEA with its by-products, the two per-body results InverseDynamicsCalculator keeps beside the joint efforts:
+ *   body_acc     (nullable) getBodyAcceleration(body), InverseDynamicsCalculator.java:578-591: the spatial acceleration of each
+ *                body (gravity included as the root's acceleration, :397-403) expressed in its CoM frame, angular part first;
+ *   joint_wrench (nullable) getComputedJointWrench(joint), :593-602: the wrench its joint transmits to each body, expressed in
+ *                the joint's frameAfterJoint, moment first.
+ * Both are [(6 * w + c) * ld + s] with w = wrench_index[b], the row convention of fext.  Bodies welded into an ancestor (fixed
+ * or ignored joints) have no rows written.  Always runs the generic thread-per-state kernel.
+ */
+int mecano_b200_rnea_full(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
+                          const double *fext, double *tau, double *body_acc, double *joint_wrench, uint32_t flags, void *stream);
 int mecano_b200_crba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout,
                      void *stream);
 
@@ -181,6 +192,8 @@ int mecano_b200_crba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const 
  */
 int mecano_b200_rnea_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
                           const double *fext, double *tau, uint32_t flags);
+int mecano_b200_rnea_full_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
+                               const double *fext, double *tau, double *body_acc, double *joint_wrench, uint32_t flags);
 int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                          const double *fext, double *qdd, uint32_t flags);
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);

@@ -60,6 +60,7 @@ EXPORTS = [
     "mecano_b200_rnea", "mecano_b200_aba", "mecano_b200_crba", "mecano_b200_rnea_host", "mecano_b200_aba_host",
     "mecano_b200_crba_host", "mecano_b200_kernel_info_get", "mecano_b200_measure_fp64_peak", "mecano_b200_measure_hbm_peak",
     "mecano_b200_integrate", "mecano_b200_integrate_host", "mecano_b200_host_alloc", "mecano_b200_host_free", "mecano_b200_generate_source", "mecano_b200_jit_check", "mecano_b200_specialize",
+    "mecano_b200_rnea_full", "mecano_b200_rnea_full_host",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -74,6 +75,8 @@ lib.mecano_b200_jit_check.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ct
 for _f in ("mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies"):
     getattr(lib, _f).argtypes = [c_vp]
 lib.mecano_b200_rnea.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp]
+lib.mecano_b200_rnea_full.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp]
+lib.mecano_b200_rnea_full_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
 lib.mecano_b200_aba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32, c_vp]
 lib.mecano_b200_crba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32, c_vp]
 lib.mecano_b200_rnea_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]

@@ -99,6 +99,8 @@ class InverseDynamicsCalculator(_BatchedCalculator):
         self._coriolis = True
         self._accelerations = True
         self._tau = None
+        self._want_acc = self._want_wrench = False
+        self._body_acc = self._joint_wrench = None
 
     def setConsiderCoriolisAndCentrifugalForces(self, value):
         self._coriolis = bool(value)
@@ -111,6 +113,16 @@ class InverseDynamicsCalculator(_BatchedCalculator):
 
     def areJointAccelerationsConsidered(self):
         return self._accelerations
+
+    def setComputeByProducts(self, bodyAccelerations=True, jointWrenches=True):
+        """Mecano's calculator always keeps the rigid-body accelerations and the joint wrenches of its last compute()
+        (getBodyAcceleration, getComputedJointWrench; InverseDynamicsCalculator.java:578-602).  For N states these are two
+        [6 * nJoints, N] matrices (12 * nBodies more rows of HBM traffic than the joint efforts), so the batched calculator
+        writes them only on request.  Returns self."""
+        if (bodyAccelerations or jointWrenches) and self._input.hasWeldedBodies():
+            raise NotImplementedError("per-body results are not supported on systems with fixed or ignored joints")
+        self._want_acc, self._want_wrench = bool(bodyAccelerations), bool(jointWrenches)
+        return self
 
     def compute(self, q, qd, qdd, tau=None):
         """compute(jointAccelerationMatrix) for N states; returns getJointTauMatrix() ([nDoFs, N])."""
@@ -125,15 +137,41 @@ class InverseDynamicsCalculator(_BatchedCalculator):
         if self._fext is not None:
             self._check("externalWrenches", self._fext, 6 * self._input.getNumberOfJoints(), n)
         flags = (0 if self._coriolis else _capi.RNEA_NO_CORIOLIS) | (0 if self._accelerations else _capi.RNEA_NO_ACCELERATIONS)
+        rows = 6 * self._input.getNumberOfJoints()
+        self._body_acc = self._empty_like(q, rows, n) if self._want_acc else None
+        self._joint_wrench = self._empty_like(q, rows, n) if self._want_wrench else None
         if _is_torch(q):
-            self._engine.rnea(q, qd, qdd, tau, fext=self._fext, flags=flags)
+            self._engine.rnea(q, qd, qdd, tau, fext=self._fext, flags=flags, body_acc=self._body_acc, joint_wrench=self._joint_wrench)
         else:
-            self._engine.rnea_host(q, qd, qdd, tau, fext=self._fext, flags=flags)
+            self._engine.rnea_host(q, qd, qdd, tau, fext=self._fext, flags=flags, body_acc=self._body_acc, joint_wrench=self._joint_wrench)
         self._tau = tau
         return tau
 
     def getJointTauMatrix(self):
         return self._tau
+
+    def getBodyAccelerationMatrix(self):
+        """[6 * nJoints, N]: rows [6 j, 6 j + 6) = spatial acceleration (angular, linear) of the successor of joint j
+        (JointMatrixIndexProvider order) expressed in its CoM frame; None unless setComputeByProducts() asked for it."""
+        return self._body_acc
+
+    def getComputedJointWrenchMatrix(self):
+        """[6 * nJoints, N]: rows [6 j, 6 j + 6) = wrench (moment, force) transmitted by joint j, in its frameAfterJoint."""
+        return self._joint_wrench
+
+    def getBodyAcceleration(self, body):
+        """getBodyAcceleration(body) (InverseDynamicsCalculator.java:578-591) for N states: [6, N], None for the root body."""
+        if body.isRootBody() or self._body_acc is None:
+            return None
+        j = self._input.getAllJoints().index(body.getParentJoint())
+        return self._body_acc[6 * j:6 * j + 6]
+
+    def getComputedJointWrench(self, joint):
+        """getComputedJointWrench(joint) (InverseDynamicsCalculator.java:593-602) for N states: [6, N]."""
+        if self._joint_wrench is None:
+            return None
+        j = self._input.getAllJoints().index(joint)
+        return self._joint_wrench[6 * j:6 * j + 6]
 
 
 class ForwardDynamicsCalculator(_BatchedCalculator):

@@ -75,7 +75,7 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    const T qd = pp.qd, tau = pp.x;
    const RbiT<T> I = ld_rbi<T>(C);
    SvT<T> pA = cross_force(vb, mul(I, vb));
-   if (FEXT)
+   if (FEXT && c.has_fext())
       pA = pA - external_wrench<T>(c, ext, C);
    AbiT<T> IA = abi_from_rbi(I);
    if (!(o.flags & MB2_LEAF))
@@ -183,7 +183,7 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
    c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
    const RbiT<T> I = ld_rbi<T>(C);
    SvT<T> pA = cross_force(vb, mul(I, vb));
-   if (FEXT)
+   if (FEXT && c.has_fext())
       pA = pA - external_wrench<T>(c, ext, C);
    AbiT<T> IA = abi_from_rbi(I);
    if (!(o.flags & MB2_LEAF))

@@ -84,19 +84,22 @@ int check_batch(mecano_b200_handle *h, int64_t n, int64_t ld)
 }
 
 int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
-        double *out, uint32_t flags, cudaStream_t stream, int ws_slot = 0)
+        double *out, uint32_t flags, cudaStream_t stream, int ws_slot = 0, double *body_acc = nullptr, double *joint_wrench = nullptr)
 {
    if (n > (int64_t)1 << 28 || ld > (int64_t)1 << 28)
       return fail(h, MECANO_B200_ERR_TOO_LARGE, "more than 2^28 states (or ld > 2^28) in one call: split the batch");
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
-   const bool use_warp = h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]);
+   // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
+   const bool byprod = body_acc || joint_wrench;
+   const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]));
    if (use_warp)
    {
       if (!h->warp_ok)
          return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body)");
       mb::KernelArgs wa;
       wa.q = q; wa.qd = qd; wa.x = x; wa.fext = fext; wa.out = out;
+      wa.body_acc = wa.joint_wrench = nullptr;
       wa.consts = h->d_consts;
       wa.ws = nullptr;
       wa.ws_ld = 0;
@@ -113,7 +116,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    // the tree-specialised kernel covers the common call (no external wrenches, default flags / layout); everything else
    // runs the generic kernels
    const mb::SpecKernel &sk = h->spec[algo];
-   const bool use_spec = sk.ready() && !fext && flags == 0;
+   const bool use_spec = sk.ready() && !fext && !byprod && flags == 0;
    if (algo == MB_ABA)
    {
       const size_t need = use_spec ? (size_t)sk.grid * sk.opt.block * (size_t)std::max(h->tree.prog[MB_ABA].rec_doubles, 1) : h->plan[MB_ABA].ws_doubles;
@@ -132,6 +135,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    }
    mb::KernelArgs a;
    a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
+   a.body_acc = body_acc; a.joint_wrench = joint_wrench;
    a.consts = h->d_consts;
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
@@ -222,7 +226,7 @@ cudaError_t copy_rows(double *dst, size_t dpitch, const double *src, size_t spit
 
 // Host-pointer pipeline: two slots, each with its own stream; H2D of chunk k+1 overlaps the kernel and D2H of chunk k.
 int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
-             double *out, uint32_t flags)
+             double *out, uint32_t flags, double *body_acc = nullptr, double *joint_wrench = nullptr)
 {
    int rc = check_batch(h, n, ld);
    if (rc) return rc;
@@ -234,7 +238,7 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
    const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
    const bool state_major = algo == MB_CRBA && (flags & MECANO_B200_CRBA_STATE_MAJOR);
    const size_t in_rows = algo == MB_CRBA ? nq : nq + 2 * nv + (fext ? 6 * nb : 0);
-   const size_t out_rows = algo == MB_CRBA ? nv * nv : nv;
+   const size_t out_rows = algo == MB_CRBA ? nv * nv : nv + (body_acc ? 6 * nb : 0) + (joint_wrench ? 6 * nb : 0);
    // chunk: ~64 MB of rows per slot, at least 4096 states, multiple of 256
    size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)(in_rows + out_rows));
    chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
@@ -258,8 +262,12 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
       }
       else
          dout = dq + nq * chunk;
-      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, 1 + slot);
+      double *dacc = body_acc ? dout + nv * chunk : nullptr;
+      double *dwr = joint_wrench ? dout + (nv + (body_acc ? 6 * nb : 0)) * chunk : nullptr;
+      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, 1 + slot, dacc, dwr);
       if (rc) return rc;
+      if (dacc) MB_CUDA(h, copy_rows(body_acc + s0, (size_t)ld, dacc, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
+      if (dwr) MB_CUDA(h, copy_rows(joint_wrench + s0, (size_t)ld, dwr, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
       if (state_major)
          MB_CUDA(h, cudaMemcpyAsync(out + (size_t)s0 * nv * nv, dout, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
       else if (algo == MB_CRBA && (flags & MECANO_B200_CRBA_ZEROS_PRESENT))
@@ -270,7 +278,7 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
                                  cudaMemcpyDeviceToHost, st));
       }
       else
-         MB_CUDA(h, copy_rows(out + s0, (size_t)ld, dout, chunk, w, out_rows, cudaMemcpyDeviceToHost, st));
+         MB_CUDA(h, copy_rows(out + s0, (size_t)ld, dout, chunk, w, algo == MB_CRBA ? out_rows : nv, cudaMemcpyDeviceToHost, st));
    }
    MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
    MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
@@ -498,6 +506,17 @@ int mecano_b200_rnea(mecano_b200_handle *h, int64_t n, int64_t ld, const double 
    return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream);
 }
 
+int mecano_b200_rnea_full(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd, const double *fext,
+                          double *tau, double *body_acc, double *joint_wrench, uint32_t flags, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !qdd || !tau) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream, 0, body_acc, joint_wrench);
+}
+
 int mecano_b200_aba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau, const double *fext,
                     double *qdd, uint32_t flags, void *stream)
 {
@@ -523,6 +542,12 @@ int mecano_b200_rnea_host(mecano_b200_handle *h, int64_t n, int64_t ld, const do
                           const double *fext, double *tau, uint32_t flags)
 {
    return run_host(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags);
+}
+
+int mecano_b200_rnea_full_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd,
+                               const double *fext, double *tau, double *body_acc, double *joint_wrench, uint32_t flags)
+{
+   return run_host(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, body_acc, joint_wrench);
 }
 
 int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau,

@@ -441,6 +441,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
       rec[MB_C_M] = m;
       std::memcpy(rec + MB_C_E, E.m, sizeof E.m);
       std::memcpy(rec + MB_C_C, c, sizeof c);
+      std::memcpy(rec + MB_C_Q, Q[i].m, sizeof Q[i].m);
       rec[MB_C_J + 0] = Ib.m[0];
       rec[MB_C_J + 1] = 0.5 * (Ib.m[1] + Ib.m[3]);
       rec[MB_C_J + 2] = 0.5 * (Ib.m[2] + Ib.m[6]);

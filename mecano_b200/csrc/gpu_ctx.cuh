@@ -99,6 +99,14 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(mb_row(xb, (unsigned)r, ld8x)); }
    __device__ __forceinline__ double ld_fext(int b, int k) const { return mb_ldg(mb_row(fb, (unsigned)(6 * b + k), ld8)); }
    __device__ __forceinline__ void st_out(int r, double v) { mb_stg(mb_row(ob, (unsigned)r, ld8), v); }
+   // optional buffers of the FEXT instantiation (nullptr = absent): external wrenches in, RNEA by-products out
+   char *accb, *wrb;
+   bool fext_on, acc_on, wr_on;
+   __device__ __forceinline__ bool has_fext() const { return fext_on; }
+   __device__ __forceinline__ bool has_acc() const { return acc_on; }
+   __device__ __forceinline__ bool has_wr() const { return wr_on; }
+   __device__ __forceinline__ void st_acc(int b, int k, double v) { mb_stg(mb_row(accb, (unsigned)(6 * b + k), ld8), v); }
+   __device__ __forceinline__ void st_wr(int b, int k, double v) { mb_stg(mb_row(wrb, (unsigned)(6 * b + k), ld8), v); }
    // ---- general stack access (CRBA; shared memory)
    __device__ __forceinline__ void stk_ld2(int slot2, int j, double &a, double &b) const { mb_lds2(sb + (unsigned)((slot2 + j) * (BLOCK * 16)), a, b); }
    __device__ __forceinline__ void stk_st2(int slot2, int j, double a, double b) { mb_sts2(sb + (unsigned)((slot2 + j) * (BLOCK * 16)), a, b); }
@@ -288,6 +296,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       c2.tm0 = __shfl_sync(0xffffffffu, c2.tm0, 0);
    }
    c2.active = true;
+   c2.fext_on = a.fext != nullptr; c2.acc_on = a.body_acc != nullptr; c2.wr_on = a.joint_wrench != nullptr;
    c2.aux = aux;
    c2.nv = a.nv;
    c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
@@ -311,6 +320,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
          break;
       c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
       c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
+      c2.accb = (char *)(a.body_acc + s); c2.wrb = (char *)(a.joint_wrench + s);
       c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
       body(c2);
    }

@@ -101,14 +101,35 @@ class InverseDynamicsCalculator : public BatchedCalculatorBase
       if (q.ld != qd.ld || q.ld != qdd.ld || q.ld != tauOut.ld || (fext_.data && fext_.ld != q.ld))
          throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
       const uint32_t flags = (coriolis_ ? 0u : MECANO_B200_RNEA_NO_CORIOLIS) | (accelerations_ ? 0u : MECANO_B200_RNEA_NO_ACCELERATIONS);
-      if (where == Memory::Device)
-         check(mecano_b200_rnea(handle_, n, q.ld, q.data, qd.data, qdd.data, fext_.data, tauOut.data, flags, stream_));
+      const int64_t rows = 6 * (int64_t)tables_.parent.size();
+      if (bodyAcc_.data) checkShape(bodyAcc_, rows, n, "bodyAccelerations");
+      if (jointWrench_.data) checkShape(jointWrench_, rows, n, "jointWrenches");
+      if ((bodyAcc_.data && bodyAcc_.ld != q.ld) || (jointWrench_.data && jointWrench_.ld != q.ld))
+         throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
+      if (!bodyAcc_.data && !jointWrench_.data)
+      {
+         if (where == Memory::Device)
+            check(mecano_b200_rnea(handle_, n, q.ld, q.data, qd.data, qdd.data, fext_.data, tauOut.data, flags, stream_));
+         else
+            check(mecano_b200_rnea_host(handle_, n, q.ld, q.data, qd.data, qdd.data, fext_.data, tauOut.data, flags));
+      }
+      else if (where == Memory::Device)
+         check(mecano_b200_rnea_full(handle_, n, q.ld, q.data, qd.data, qdd.data, fext_.data, tauOut.data, bodyAcc_.data, jointWrench_.data, flags, stream_));
       else
-         check(mecano_b200_rnea_host(handle_, n, q.ld, q.data, qd.data, qdd.data, fext_.data, tauOut.data, flags));
+         check(mecano_b200_rnea_full_host(handle_, n, q.ld, q.data, qd.data, qdd.data, fext_.data, tauOut.data, bodyAcc_.data, jointWrench_.data, flags));
+   }
+   // Where the next compute() leaves getBodyAcceleration(body) / getComputedJointWrench(joint) (InverseDynamicsCalculator.java:
+   // 578-602) of all N states: (6 * nJoints) x N matrices, rows [6 j, 6 j + 6) for joint j / its successor, accelerations in the
+   // body's CoM frame, wrenches in the joint's frameAfterJoint.  Empty views (the default) skip them.
+   void setByProductOutputs(const MatrixView &bodyAccelerations, const MatrixView &jointWrenches)
+   {
+      bodyAcc_ = bodyAccelerations;
+      jointWrench_ = jointWrenches;
    }
 
  private:
    bool coriolis_ = true, accelerations_ = true;
+   MatrixView bodyAcc_, jointWrench_;
 };
 
 class ForwardDynamicsCalculator : public BatchedCalculatorBase

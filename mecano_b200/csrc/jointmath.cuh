@@ -184,6 +184,33 @@ template <class T, class CP> MB_HD void ld_com(const CP C, M3T<T> &E, V3T<T> &cp
    cst_ld2(C, 14, E.zx, E.zy); cst_ld2(C, 15, E.zz, cp.x); cst_ld2(C, 16, cp.y, cp.z);
 }
 
+// rotation canonical frame -> frameAfterJoint: Q (40..48)
+template <class T, class CP> MB_HD M3T<T> ld_q_rot(const CP C)
+{
+   static_assert(MB_C_Q == 40, "record layout");
+   M3T<T> Q;
+   T pad;
+   cst_ld2(C, 20, Q.xx, Q.xy); cst_ld2(C, 21, Q.xz, Q.yx); cst_ld2(C, 22, Q.yy, Q.yz); cst_ld2(C, 23, Q.zx, Q.zy); cst_ld2(C, 24, Q.zz, pad);
+   return Q;
+}
+// RNEA by-products of one body (InverseDynamicsCalculator.java:578-602): its spatial acceleration re-expressed in the CoM
+// frame, the wrench of its joint re-expressed in frameAfterJoint
+template <class T, class Ctx, class CP> MB_HD void rnea_store_body_acc(Ctx &c, int ext, const CP C, const SvT<T> &a)
+{
+   XfT<T> X;
+   ld_com<T>(C, X.R, X.p);
+   const SvT<T> ac = motion_to_child(X, a);
+   c.st_acc(ext, 0, ac.a.x); c.st_acc(ext, 1, ac.a.y); c.st_acc(ext, 2, ac.a.z);
+   c.st_acc(ext, 3, ac.l.x); c.st_acc(ext, 4, ac.l.y); c.st_acc(ext, 5, ac.l.z);
+}
+template <class T, class Ctx, class CP> MB_HD void rnea_store_joint_wrench(Ctx &c, int ext, const CP C, const SvT<T> &f)
+{
+   const M3T<T> Q = ld_q_rot<T>(C);
+   const V3T<T> n = mul(Q, f.a), l = mul(Q, f.l);
+   c.st_wr(ext, 0, n.x); c.st_wr(ext, 1, n.y); c.st_wr(ext, 2, n.z);
+   c.st_wr(ext, 3, l.x); c.st_wr(ext, 4, l.y); c.st_wr(ext, 5, l.z);
+}
+
 // (a1) joint transform X_J(q) composed with the fixed offset, canonical frames (axis = +z):
 // revolute (MecanoFactories.java:231-260): R = R0 Rz(q), p = p0;  prismatic (PrismaticJointReadOnly.java:18-22): R = R0, p = p0 + q R0 e_z
 template <class T, bool REV, class CP> MB_HD XfT<T> joint_xf_1dof(const CP C, T s, T c)

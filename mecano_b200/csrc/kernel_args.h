@@ -9,6 +9,8 @@ struct KernelArgs
 {
    const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
    double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
+   double *body_acc, *joint_wrench; // RNEA by-products (nullable), rows [6 * w + c] like fext: spatial acceleration of each body in its
+                                    // CoM frame, wrench of each joint in its frameAfterJoint
    const double *consts;            // device copy of the per-body constant records
    double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid
    long long ws_ld;

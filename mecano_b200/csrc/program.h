@@ -41,7 +41,8 @@ typedef long long int64_t;
 #define MB_C_E 22   // [9] rotation CoM frame -> internal frame (for external wrenches)
 #define MB_C_C 31   // [3] CoM position in the internal frame
 #define MB_C_J 34   // [6] inertia about the CoM, expressed in the internal frame: xx xy xz yy yz zz
-#define MB_CONST_STRIDE 40
+#define MB_C_Q 40   // [9] rotation internal (canonical) frame -> the joint's frameAfterJoint (per-joint outputs in Mecano's frame)
+#define MB_CONST_STRIDE 50
 
 // op word: bit0 kind, bits 1..7 flags, bits 8..23 body
 #define MB_OP_ASCEND 0x1u

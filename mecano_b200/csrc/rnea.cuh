@@ -58,7 +58,13 @@ MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
    ld_com_inertia<T>(C, J, cp, m);
    f = newton_euler(J, cp, m, v, a);
    if (FEXT)
-      f = f - external_wrench<T>(c, ext, C); // :946
+   {
+      // the FEXT instantiation serves every call with optional buffers: external wrenches in, by-products out
+      if (c.has_fext())
+         f = f - external_wrench<T>(c, ext, C); // :946
+      if (c.has_acc())
+         rnea_store_body_acc<T>(c, ext, C, a);
+   }
    pp.ls = pp.s;
    pp.lc = pp.c;
    if (!(o.flags & MB2_LEAF))
@@ -73,13 +79,15 @@ MB_HD void rnea_descend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
    }
 }
 
-template <class T, class Ctx, bool REV, bool SC>
-MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, SvT<T> &f, RneaPipe<T> &pp, T &ns, T &nc)
+template <class T, class Ctx, bool FEXT, bool REV, bool SC>
+MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &f, RneaPipe<T> &pp, T &ns, T &nc)
 {
    if (SC)
       mb_sincos(pp.mq, &ns, &nc);
    // pass two (:930-966); f holds the wrench of the whole subtree
    c.st_out(o.dof, REV ? f.a.z : f.l.z); // tau = S^T W (:952-958)
+   if (FEXT && c.has_wr())
+      rnea_store_joint_wrench<T>(c, ext, c.cst(o.body), f);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       T s = pp.ls, cs = pp.lc;
@@ -108,7 +116,12 @@ MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
    ld_com_inertia<T>(C, J, cp, m);
    f = newton_euler(J, cp, m, v, a);
    if (FEXT)
-      f = f - external_wrench<T>(c, ext, C);
+   {
+      if (c.has_fext())
+         f = f - external_wrench<T>(c, ext, C);
+      if (c.has_acc())
+         rnea_store_body_acc<T>(c, ext, C, a);
+   }
    c.acc_st(o.slot, o.wslot, f.a.x, f.a.y, f.a.z, f.l.x, f.l.y, f.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))
       jp_st_xf<T>(c, o.slot, o.nslot, X);
@@ -119,8 +132,10 @@ MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
    }
 }
 
-template <class T, class Ctx> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o, SvT<T> &f)
+template <class T, class Ctx, bool FEXT> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &f)
 {
+   if (FEXT && c.has_wr())
+      rnea_store_joint_wrench<T>(c, ext, c.cst(o.body), f);
    c.st_out(o.dof + 0, f.a.x); c.st_out(o.dof + 1, f.a.y); c.st_out(o.dof + 2, f.a.z);
    c.st_out(o.dof + 3, f.l.x); c.st_out(o.dof + 4, f.l.y); c.st_out(o.dof + 5, f.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))
@@ -192,17 +207,17 @@ MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const int ext, const T *g
    {
       case 0 | (MB_REVOLUTE << 1): rnea_descend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, v, a, f, pp, ns, nc); break;
       case 0 | (MB_REVOLUTE << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, v, a, f, pp, ns, nc); break;
-      case 1 | (MB_REVOLUTE << 1): rnea_ascend_1dof<T, Ctx, true, false>(c, o, f, pp, ns, nc); break;
-      case 1 | (MB_REVOLUTE << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, true, true>(c, o, f, pp, ns, nc); break;
+      case 1 | (MB_REVOLUTE << 1): rnea_ascend_1dof<T, Ctx, FEXT, true, false>(c, o, ext, f, pp, ns, nc); break;
+      case 1 | (MB_REVOLUTE << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, FEXT, true, true>(c, o, ext, f, pp, ns, nc); break;
       case 0 | (MB_PRISMATIC << 1): rnea_descend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, v, a, f, pp, ns, nc); break;
       case 0 | (MB_PRISMATIC << 1) | MB2_SC: rnea_descend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, v, a, f, pp, ns, nc); break;
-      case 1 | (MB_PRISMATIC << 1): rnea_ascend_1dof<T, Ctx, false, false>(c, o, f, pp, ns, nc); break;
-      case 1 | (MB_PRISMATIC << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, false, true>(c, o, f, pp, ns, nc); break;
+      case 1 | (MB_PRISMATIC << 1): rnea_ascend_1dof<T, Ctx, FEXT, false, false>(c, o, ext, f, pp, ns, nc); break;
+      case 1 | (MB_PRISMATIC << 1) | MB2_SC: rnea_ascend_1dof<T, Ctx, FEXT, false, true>(c, o, ext, f, pp, ns, nc); break;
       default:
          if (o.code & MB2_SC)
             mb_sincos(pp.mq, &ns, &nc);
          if (o.code & MB2_ASCEND)
-            rnea_ascend_6dof<T, Ctx>(c, o, f);
+            rnea_ascend_6dof<T, Ctx, FEXT>(c, o, ext, f);
          else
             rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f);
          break;
@@ -248,11 +263,11 @@ MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav,
    if (JT == MB_SIXDOF)
    {
       if (SC) mb_sincos(pp.mq, &ns, &nc);
-      if (ASC) rnea_ascend_6dof<T, Ctx>(c, o, f);
+      if (ASC) rnea_ascend_6dof<T, Ctx, FEXT>(c, o, ext, f);
       else rnea_descend_6dof<T, Ctx, FEXT>(c, o, ext, v, a, f);
    }
    else if (ASC)
-      rnea_ascend_1dof<T, Ctx, JT == MB_REVOLUTE, SC>(c, o, f, pp, ns, nc);
+      rnea_ascend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, SC>(c, o, ext, f, pp, ns, nc);
    else
       rnea_descend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, SC>(c, o, ext, v, a, f, pp, ns, nc);
    pp.s = ns;

@@ -95,14 +95,20 @@ class Engine:
         return torch.cuda.current_stream().cuda_stream
 
     # ---- device entry points (asynchronous on torch's current stream)
-    def rnea(self, q, qd, qdd, tau, fext=None, flags=0):
+    def rnea(self, q, qd, qdd, tau, fext=None, flags=0, body_acc=None, joint_wrench=None):
+        """body_acc / joint_wrench ([6 * nb, n], optional): the by-products of mecano_b200_rnea_full."""
         n = q.shape[1]
         pq, l0 = _dev_ptr_ld(q, self.nq, n)
         pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
         pqdd, l2 = _dev_ptr_ld(qdd, self.nv, n)
         pt, l3 = _dev_ptr_ld(tau, self.nv, n)
         pf, l4 = _dev_ptr_ld(fext, 6 * self.nb, n)
-        check(lib.mecano_b200_rnea(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags, self._stream()), self._h)
+        if body_acc is None and joint_wrench is None:
+            check(lib.mecano_b200_rnea(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags, self._stream()), self._h)
+            return tau
+        pa, l5 = _dev_ptr_ld(body_acc, 6 * self.nb, n)
+        pw, l6 = _dev_ptr_ld(joint_wrench, 6 * self.nb, n)
+        check(lib.mecano_b200_rnea_full(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pqdd, pf, pt, pa, pw, flags, self._stream()), self._h)
         return tau
 
     def aba(self, q, qd, tau, qdd, fext=None, flags=0):
@@ -145,14 +151,19 @@ class Engine:
         check(lib.mecano_b200_integrate_host(self._h, n, _same_ld([l0, l1, l2]), float(dt), pq, pqd, pqdd), self._h)
 
     # ---- host entry points (synchronous; inputs/outputs in host memory, pinned for full speed)
-    def rnea_host(self, q, qd, qdd, tau, fext=None, flags=0):
+    def rnea_host(self, q, qd, qdd, tau, fext=None, flags=0, body_acc=None, joint_wrench=None):
         n = q.shape[1]
         pq, l0 = _host_ptr_ld(q, self.nq, n)
         pqd, l1 = _host_ptr_ld(qd, self.nv, n)
         pqdd, l2 = _host_ptr_ld(qdd, self.nv, n)
         pt, l3 = _host_ptr_ld(tau, self.nv, n)
         pf, l4 = _host_ptr_ld(fext, 6 * self.nb, n)
-        check(lib.mecano_b200_rnea_host(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags), self._h)
+        if body_acc is None and joint_wrench is None:
+            check(lib.mecano_b200_rnea_host(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags), self._h)
+            return tau
+        pa, l5 = _host_ptr_ld(body_acc, 6 * self.nb, n)
+        pw, l6 = _host_ptr_ld(joint_wrench, 6 * self.nb, n)
+        check(lib.mecano_b200_rnea_full_host(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pqdd, pf, pt, pa, pw, flags), self._h)
         return tau
 
     def aba_host(self, q, qd, tau, qdd, fext=None, flags=0):

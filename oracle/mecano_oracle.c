@@ -369,7 +369,7 @@ static void dynamic_wrench(const double *J, double m, const sv_t *acc, const sv_
  * M/algorithms/InverseDynamicsCalculator.java:496-501 compute(), :873-917 passOne(), :930-966 passTwo() */
 
 static void rnea_impl(const mo_tree *t, const double *g, const double *q, const double *qd, const double *qdd, const double *fext,
-                      int flags, double *tau, double *acc_out)
+                      int flags, double *tau, double *acc_out, double *wr_out)
 {
    frames_t *F = (frames_t *)malloc(sizeof(frames_t));
    sv_t *acc = (sv_t *)malloc(sizeof(sv_t) * (size_t)t->nb);
@@ -454,6 +454,8 @@ static void rnea_impl(const mo_tree *t, const double *g, const double *q, const 
                sv_add(&W, &Wc);
             }
          wr[i] = W;
+         if (wr_out) /* getComputedJointWrench(joint): the joint wrench, expressed in frameAfterJoint (:947, :593-602) */
+            memcpy(wr_out + 6 * i, &W, sizeof(sv_t));
          /* tau = S^T W, :952-958 */
          int nd = joint_ndof(t, i);
          for (int k = 0; k < nd; k++)
@@ -471,13 +473,19 @@ static void rnea_impl(const mo_tree *t, const double *g, const double *q, const 
 void mo_rnea(const mo_tree *t, const double *g, const double *q, const double *qd, const double *qdd, const double *fext, int flags,
              double *tau)
 {
-   rnea_impl(t, g, q, qd, qdd, fext, flags, tau, NULL);
+   rnea_impl(t, g, q, qd, qdd, fext, flags, tau, NULL, NULL);
+}
+
+void mo_rnea_full(const mo_tree *t, const double *g, const double *q, const double *qd, const double *qdd, const double *fext, int flags,
+                  double *tau, double *body_acc, double *joint_wrench)
+{
+   rnea_impl(t, g, q, qd, qdd, fext, flags, tau, body_acc, joint_wrench);
 }
 
 void mo_rnea_body_accelerations(const mo_tree *t, const double *g, const double *q, const double *qd, const double *qdd, int flags,
                                 double *acc)
 {
-   rnea_impl(t, g, q, qd, qdd, NULL, flags, NULL, acc);
+   rnea_impl(t, g, q, qd, qdd, NULL, flags, NULL, acc, NULL);
 }
 
 /* ================================================================== articulated-body inertia

@@ -65,6 +65,12 @@ void mo_crba(const mo_tree *t, const double *q, double *M /* [nv][nv] row-major 
 void mo_rnea_body_accelerations(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *qdd,
                                 int flags, double *acc);
 
+/* RNEA with its by-products: body_acc [nb][6] = getBodyAcceleration(body), the spatial acceleration of each body expressed in its
+ * CoM frame (InverseDynamicsCalculator.java:578-591, pass one :880-910); joint_wrench [nb][6] = getComputedJointWrench(joint), the
+ * wrench transmitted by each joint expressed in its frameAfterJoint (:593-602, pass two :943-950).  Either may be NULL. */
+void mo_rnea_full(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *qdd, const double *fext,
+                  int flags, double *tau, double *body_acc, double *joint_wrench);
+
 /* Batched drivers, DoF-major / state-minor buffers x[k*ld + s] (same layout as the C-ABI).
  * fext (nullable) is [(6*nb)][ld].  M is entry-major [(i*nv+j)*ld + s].  nthreads<=0 -> all cores. */
 void mo_rnea_batch(const mo_tree *t, const double *gravity3, long n, long ld, const double *q, const double *qd, const double *qdd,

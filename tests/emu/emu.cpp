@@ -61,6 +61,12 @@ template <class T> struct CpuCtx
    T ld_x(int r) const { return (T)x[r * ldx + s]; }
    T ld_fext(int b, int k) const { return (T)fext[(6 * b + k) * ld + s]; }
    void st_out(int r, T v) { out[r * ld + s] = (double)v; }
+   double *acc_out = nullptr, *wr_out = nullptr;
+   bool has_fext() const { return fext != nullptr; }
+   bool has_acc() const { return acc_out != nullptr; }
+   bool has_wr() const { return wr_out != nullptr; }
+   void st_acc(int b, int k, T v) { acc_out[(6 * b + k) * ld + s] = (double)v; }
+   void st_wr(int b, int k, T v) { wr_out[(6 * b + k) * ld + s] = (double)v; }
    void st_M(int e, T v) { M[(long)e * ld + s] = (double)v; }
    int n_dofs() const { return nv; }
    const std::vector<uint16_t> *zl;
@@ -116,7 +122,7 @@ template <class T> struct CpuCtx
 
 template <class T>
 int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *x,
-        const double *fext, double *out, unsigned flags, char *err, int errlen)
+        const double *fext, double *out, unsigned flags, char *err, int errlen, double *acc_out = nullptr, double *wr_out = nullptr)
 {
    mb::FlatTree ft;
    std::string e;
@@ -146,10 +152,12 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       if (algo == MB_RNEA && (flags & 2u)) { c.x = zero_row.data(); c.ldx = 0; }
       c.wide = wide.data();
       c.narrow = narrow.data();
+      c.acc_out = acc_out;
+      c.wr_out = wr_out;
       c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
-         if (fext) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav);
+         if (fext || acc_out || wr_out) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav);
          else mb::rnea_state<T, CpuCtx<T>, false>(P, c, grav);
       }
       else if (algo == MB_ABA)
@@ -169,6 +177,13 @@ extern "C" int emu_run(int algo, int fp32, const mecano_b200_tree_desc *d, const
 {
    return fp32 ? run<float>(algo, d, g, n, ld, q, qd, x, fext, out, flags, err, errlen)
                : run<double>(algo, d, g, n, ld, q, qd, x, fext, out, flags, err, errlen);
+}
+
+// RNEA with its by-products (body accelerations in CoM frames, joint wrenches in frameAfterJoint), rows [6 * w + c]
+extern "C" int emu_rnea_full(const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *x,
+                             const double *fext, double *tau, double *acc, double *wr, unsigned flags, char *err, int errlen)
+{
+   return run<double>(MB_RNEA, d, g, n, ld, q, qd, x, fext, tau, flags, err, errlen, acc, wr);
 }
 
 // Algorithmic operation counts of one state: out5 = {add, mul, div, sincos, flops = add + mul + div}

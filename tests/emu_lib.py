@@ -124,6 +124,21 @@ class Emu:
         n = q.shape[1]
         return self._run(0, q, qd, qdd, self._fext_rows(fext, n), np.full((self.tree.nv, n), np.nan), flags)
 
+    def rnea_full(self, q, qd, qdd, fext=None, flags=0):
+        """(tau [nv, n], body accelerations [nb, 6, n] in CoM frames, joint wrenches [nb, 6, n] in frameAfterJoint), bodies in
+        the order of the tree description."""
+        n = q.shape[1]
+        nb = self.tree.nb
+        tau, acc, wr = np.full((self.tree.nv, n), np.nan), np.full((6 * nb, n), np.nan), np.full((6 * nb, n), np.nan)
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_rnea_full(ctypes.byref(self.desc), _d(self.g), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(qd), _d(qdd),
+                                    _d(self._fext_rows(fext, n)), _d(tau), _d(acc), _d(wr), ctypes.c_uint(flags), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_rnea_full rc=%d: %s" % (rc, err.value.decode()))
+        back = np.empty(nb, dtype=np.int64)
+        back[self.order] = np.arange(nb)
+        return tau, acc.reshape(nb, 6, n)[back], wr.reshape(nb, 6, n)[back]
+
     def aba(self, q, qd, tau, fext=None):
         n = q.shape[1]
         return self._run(1, q, qd, tau, self._fext_rows(fext, n), np.full((self.tree.nv, n), np.nan))

@@ -66,6 +66,13 @@ class Oracle:
         self.lib.mo_rnea(ctypes.byref(self.c), _d(self.g), _d(q), _d(qd), _d(qdd), _d(fext), ctypes.c_int(flags), _d(tau))
         return tau
 
+    def rnea_full(self, q, qd, qdd, fext=None, flags=0):
+        """(tau [nv], body accelerations [nb, 6] in CoM frames, joint wrenches [nb, 6] in frameAfterJoint) of one state."""
+        q, qd, qdd, fext = map(self._f64, (q, qd, qdd, fext))
+        tau, acc, wr = np.zeros(self.t.nv), np.zeros((self.t.nb, 6)), np.zeros((self.t.nb, 6))
+        self.lib.mo_rnea_full(ctypes.byref(self.c), _d(self.g), _d(q), _d(qd), _d(qdd), _d(fext), ctypes.c_int(flags), _d(tau), _d(acc), _d(wr))
+        return tau, acc, wr
+
     def body_accelerations(self, q, qd, qdd, flags=0):
         q, qd, qdd = map(self._f64, (q, qd, qdd))
         acc = np.zeros((self.t.nb, 6))

@@ -46,6 +46,28 @@ def test_emulated_kernels_match_oracle(idx):
     assert rel(M, o.crba_batch(q)) < TOL
 
 
+@pytest.mark.parametrize("idx", range(12))
+def test_emulated_rnea_byproducts_match_oracle(idx):
+    """getBodyAcceleration / getComputedJointWrench (InverseDynamicsCalculator.java:578-602): the kernel routines leave them
+    in the frames the reference returns them in (CoM frame, frameAfterJoint)."""
+    rng = np.random.default_rng(700 + idx)
+    t = trees(rng)[idx]
+    g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
+    o, e = ol.Oracle(t, gravity=g), el.Emu(t, gravity=g)
+    n = 3
+    q, qd, qdd, _ = td.random_states(rng, t, n)
+    fext = rng.uniform(-1, 1, size=(t.nb, 6, n))
+    for f in (None, fext):
+        tau, acc, wr = e.rnea_full(q, qd, qdd, f)
+        assert not (np.isnan(tau).any() or np.isnan(acc).any() or np.isnan(wr).any())
+        for s in range(n):
+            fo = None if f is None else np.ascontiguousarray(f[:, :, s])
+            tau_o, acc_o, wr_o = o.rnea_full(q[:, s], qd[:, s], qdd[:, s], fo)
+            assert rel(tau[:, s], tau_o) < TOL
+            assert rel(acc[:, :, s], acc_o) < TOL
+            assert rel(wr[:, :, s], wr_o) < TOL
+
+
 def test_table_order_does_not_matter():
     """The C-ABI accepts any topological listing of the bodies (level order from the Java host, or DFS)."""
     rng = np.random.default_rng(9)

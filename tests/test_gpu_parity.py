@@ -141,7 +141,7 @@ def test_host_entry_points_and_leading_dimension(torch_dev):
     # empty and single-state batches
     assert ident.compute(tq[:, :0], tqd[:, :0], tqdd[:, :0]).shape == (t.nv, 0)
     one = ident.compute(tq[:, :1], tqd[:, :1], tqdd[:, :1]).cpu().numpy()
-    assert rel(one, out[:, :1]) == 0.0
+    assert rel(one, out[:, :1]) < 1e-13  # AUTO runs a single state on the warp-per-state kernels: same mathematics, other rounding order
 
 
 def test_error_behaviour(torch_dev):
@@ -361,3 +361,55 @@ def test_calculator_owned_mass_matrix_skips_structural_zeros_only(torch_dev, var
     q = mb.MultiBodySystemRandomTools.nextState(rng, s, n)[0]
     crba.getMassMatrix(torch.from_numpy(q).to(dev), mine)
     assert rel(mine.cpu().numpy().reshape(nv, nv, n), o.crba_batch(q)) <= TOL
+
+
+@pytest.mark.parametrize("idx", [0, 3, 5, 6, 8])
+def test_rnea_byproducts_match_oracle(torch_dev, idx):
+    """getBodyAcceleration(body) / getComputedJointWrench(joint) for N states (InverseDynamicsCalculator.java:578-602):
+    mecano_b200_rnea_full on device buffers and mecano_b200_rnea_full_host on host buffers, with and without external
+    wrenches, against the oracle state by state; the joint efforts of the same call must equal the plain kernel's."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(4000 + idx)
+    g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
+    o = ol.Oracle(t, gravity=g)
+    n = 333
+    q, qd, qdd, _ = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    fext = np.ascontiguousarray(rng.uniform(-1, 1, size=(6 * t.nb, n)))
+    tq, tqd, tqdd, tf = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, fext))
+    plain = mb.InverseDynamicsCalculator(s)
+    plain.setGravitationalAcceleration(g)
+    ident = mb.InverseDynamicsCalculator(s).setComputeByProducts()
+    ident.setGravitationalAcceleration(g)
+    for f_host, f_dev in ((None, None), (fext, tf)):
+        plain.setExternalWrenches(f_dev)
+        ident.setExternalWrenches(f_dev)
+        tau = ident.compute(tq, tqd, tqdd).cpu().numpy()
+        assert rel(tau, plain.compute(tq, tqd, tqdd).cpu().numpy()) < 1e-13, name
+        acc = ident.getBodyAccelerationMatrix().cpu().numpy().reshape(t.nb, 6, n)
+        wr = ident.getComputedJointWrenchMatrix().cpu().numpy().reshape(t.nb, 6, n)
+        for k in range(0, n, 11):
+            fo = None if f_host is None else np.ascontiguousarray(f_host[:, k].reshape(t.nb, 6))
+            tau_o, acc_o, wr_o = o.rnea_full(q[:, k], qd[:, k], qdd[:, k], fo)
+            assert rel(tau[:, k], tau_o) < TOL, name
+            assert rel(acc[:, :, k], acc_o) < TOL, name
+            assert rel(wr[:, :, k], wr_o) < TOL, name
+        # the per-object getters are views of the same matrices
+        j = s.getAllJoints()[t.nb // 2]
+        assert torch.equal(ident.getComputedJointWrench(j), ident.getComputedJointWrenchMatrix()[6 * (t.nb // 2):6 * (t.nb // 2) + 6])
+        assert torch.equal(ident.getBodyAcceleration(j.getSuccessor()), ident.getBodyAccelerationMatrix()[6 * (t.nb // 2):6 * (t.nb // 2) + 6])
+        # host path: same kernel behind pinned staging
+        ident.setExternalWrenches(f_host)
+        tau_h = ident.compute(q, qd, qdd)
+        assert rel(tau_h, tau) == 0.0 and rel(ident.getBodyAccelerationMatrix().reshape(t.nb, 6, n), acc) == 0.0
+        assert rel(ident.getComputedJointWrenchMatrix().reshape(t.nb, 6, n), wr) == 0.0
+    # only one of the two by-products
+    only = mb.InverseDynamicsCalculator(s).setComputeByProducts(bodyAccelerations=False)
+    only.setGravitationalAcceleration(g)
+    only.setExternalWrenches(tf)
+    only.compute(tq, tqd, tqdd)
+    assert only.getBodyAccelerationMatrix() is None
+    assert rel(only.getComputedJointWrenchMatrix().cpu().numpy().reshape(t.nb, 6, n), wr) == 0.0
