@@ -171,6 +171,24 @@ int mecano_b200_rnea(mecano_b200_handle *h, int64_t n_states, int64_t ld, const 
 int mecano_b200_aba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                     const double *fext, double *qdd, uint32_t flags, void *stream);
 /*
+ * Joint source modes of forward dynamics (ForwardDynamicsCalculator.JointSourceMode, ForwardDynamicsCalculator.java:45-57;
+ * setJointSourceMode :400-403, resetJointSourceModes :438-444).  accel_source [n_bodies], in the order of the tree description:
+ * non-zero = the joint of that body is an ACCELERATION_SOURCE (its acceleration is an input, its effort an output), zero =
+ * EFFORT_SOURCE (the default).  NULL resets every joint to EFFORT_SOURCE.  A property of the handle like gravity: set it between
+ * calls, not concurrently with them.
+ *
+ * mecano_b200_aba_sources = compute(jointTauInput, jointAccelerationInput) (:508-520) for N states:
+ *   tau     [n_dofs][ld]  efforts; the rows of ACCELERATION_SOURCE joints are not read
+ *   qdd_in  [n_dofs][ld]  accelerations; only the rows of ACCELERATION_SOURCE joints are read (may be NULL if there are none)
+ *   qdd     [n_dofs][ld]  getJointAccelerationMatrix() (:556-564): computed for EFFORT_SOURCE joints, qdd_in repeated for the others
+ *   tau_out [n_dofs][ld]  (nullable) getJointTauMatrix() (:566-590): tau repeated for EFFORT_SOURCE joints, computed for the others
+ *                         (pass four, :1315-1363; costs one additional inverse-dynamics launch).  Must not alias tau.
+ * With joints in ACCELERATION_SOURCE mode plain mecano_b200_aba is refused (it has no acceleration input).
+ */
+int mecano_b200_set_joint_source_modes(mecano_b200_handle *h, const int32_t *accel_source);
+int mecano_b200_aba_sources(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
+                            const double *qdd_in, const double *fext, double *qdd, double *tau_out, void *stream);
+/*
  * RNEA with its by-products, the two per-body results InverseDynamicsCalculator keeps beside the joint efforts:
  *   body_acc     (nullable) getBodyAcceleration(body), InverseDynamicsCalculator.java:578-591: the spatial acceleration of each
  *                body (gravity included as the root's acceleration, :397-403) expressed in its CoM frame, angular part first;
@@ -196,6 +214,8 @@ int mecano_b200_rnea_full_host(mecano_b200_handle *h, int64_t n_states, int64_t 
                                const double *fext, double *tau, double *body_acc, double *joint_wrench, uint32_t flags);
 int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                          const double *fext, double *qdd, uint32_t flags);
+int mecano_b200_aba_sources_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
+                                 const double *qdd_in, const double *fext, double *qdd, double *tau_out);
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
 
 /*

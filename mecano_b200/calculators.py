@@ -174,15 +174,66 @@ class InverseDynamicsCalculator(_BatchedCalculator):
         return self._joint_wrench[6 * j:6 * j + 6]
 
 
+class JointSourceMode:
+    """ForwardDynamicsCalculator.JointSourceMode (ForwardDynamicsCalculator.java:45-57)."""
+    EFFORT_SOURCE = "EFFORT_SOURCE"
+    ACCELERATION_SOURCE = "ACCELERATION_SOURCE"
+
+
 class ForwardDynamicsCalculator(_BatchedCalculator):
     _ALGO = _capi.ALGO_ABA
+    JointSourceMode = JointSourceMode
 
     def __init__(self, input, device=0):
         super().__init__(input, device)
         self._qdd = None
+        self._tau = None
+        self._modes = {}  # joint -> JointSourceMode, ACCELERATION_SOURCE entries only
 
-    def compute(self, q, qd, tau, qdd=None):
-        """compute(jointTauMatrix) for N states; returns getJointAccelerationMatrix() ([nDoFs, N])."""
+    # ---- joint source modes (ForwardDynamicsCalculator.java:400-465)
+    def setJointSourceMode(self, joint, mode):
+        if mode not in (JointSourceMode.EFFORT_SOURCE, JointSourceMode.ACCELERATION_SOURCE):
+            raise ValueError("unknown JointSourceMode %r" % (mode,))
+        if self._input.tableRow(joint) < 0:
+            raise ValueError("joint %s is not considered by this calculator" % joint.getName())
+        if mode == JointSourceMode.ACCELERATION_SOURCE:
+            self._modes[joint] = mode
+        else:
+            self._modes.pop(joint, None)
+        self._push_modes()
+
+    def setJointSourceModes(self, jointSourceModeFunction):
+        """The function may return None for a joint to leave its mode unchanged (:422-433)."""
+        for joint in self._input.getJointsToConsider():
+            if self._input.tableRow(joint) < 0:
+                continue
+            mode = jointSourceModeFunction(joint)
+            if mode == JointSourceMode.ACCELERATION_SOURCE:
+                self._modes[joint] = mode
+            elif mode == JointSourceMode.EFFORT_SOURCE:
+                self._modes.pop(joint, None)
+        self._push_modes()
+
+    def resetJointSourceModes(self):
+        self._modes.clear()
+        self._push_modes()
+
+    def getJointSourceMode(self, joint):
+        return self._modes.get(joint, JointSourceMode.EFFORT_SOURCE)
+
+    def _push_modes(self):
+        if not self._modes:
+            self._engine.set_joint_source_modes(None)
+            return
+        src = np.zeros(self._engine.nb, dtype=np.int32)
+        for joint in self._modes:
+            src[self._input.tableRow(joint)] = 1
+        self._engine.set_joint_source_modes(src)
+
+    def compute(self, q, qd, tau, qdd=None, jointAccelerationInput=None):
+        """compute(jointTauMatrix[, jointAccelerationMatrix]) for N states (:489-520); returns getJointAccelerationMatrix()
+        ([nDoFs, N]).  jointAccelerationInput ([nDoFs, N]) is only read at the rows of ACCELERATION_SOURCE joints, and is
+        required when there are any; the efforts of those joints are then available from getJointTauMatrix()."""
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
         n = q.shape[1] if q.ndim == 2 else -1
         self._check("q", q, nq, n)
@@ -193,15 +244,27 @@ class ForwardDynamicsCalculator(_BatchedCalculator):
         self._check("qdd", qdd, nv, n)
         if self._fext is not None:
             self._check("externalWrenches", self._fext, 6 * self._input.getNumberOfJoints(), n)
-        if _is_torch(q):
-            self._engine.aba(q, qd, tau, qdd, fext=self._fext)
+        if self._modes:
+            self._check("jointAccelerationInput", jointAccelerationInput, nv, n)
+            tau_out = self._empty_like(q, nv, n)
+            run = self._engine.aba_sources if _is_torch(q) else self._engine.aba_sources_host
+            run(q, qd, tau, jointAccelerationInput, qdd, tau_out, fext=self._fext)
+            self._tau = tau_out
         else:
-            self._engine.aba_host(q, qd, tau, qdd, fext=self._fext)
+            if _is_torch(q):
+                self._engine.aba(q, qd, tau, qdd, fext=self._fext)
+            else:
+                self._engine.aba_host(q, qd, tau, qdd, fext=self._fext)
+            self._tau = tau  # every joint is an EFFORT_SOURCE: the efforts are the input
         self._qdd = qdd
         return qdd
 
     def getJointAccelerationMatrix(self):
         return self._qdd
+
+    def getJointTauMatrix(self):
+        """The joint efforts (:566-590): the input for EFFORT_SOURCE joints, computed for ACCELERATION_SOURCE joints."""
+        return self._tau
 
 
 class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):

@@ -58,6 +58,56 @@ MB_HD void aba_descend_1dof(Ctx &c, const MbOp2 o, SvT<T> &v, AbaPipe<T> &pp, T 
    }
 }
 
+// ---- fold a child's articulated inertia / bias wrench (already in the parent frame) into the parent's accumulator
+template <class T, class Ctx> MB_HD void aba_fold(Ctx &c, const MbOp2 o, const AbiT<T> &K, const SvT<T> &Pp, AbiT<T> &acc, SvT<T> &pacc)
+{
+   if (o.flags & MB2_FIRST_CHILD)
+   {
+      acc = K;
+      pacc = Pp;
+   }
+   else
+   {
+      aux_ld_abi<T>(c, o.paux, acc, pacc);
+      acc = acc + K;
+      pacc = pacc + Pp;
+   }
+   if (o.flags & MB2_STORE_ACC)
+      aux_st_abi<T>(c, o.paux, acc, pacc);
+}
+
+// ---- pass two of a joint in JointSourceMode.ACCELERATION_SOURCE (ForwardDynamicsCalculator.java:45-57, :1237-1253): its
+// acceleration is an input, so nothing is removed from the articulated inertia and the known S qdd enters the bias wrench:
+// I^a = I^A, p^a = p^A + I^A (c + S qdd).  Pass three reads qdd back through the same record (g = 0, k0 = qdd).
+template <class T, class Ctx, bool REV, class CP>
+MB_HD void aba_ascend_1dof_locked(Ctx &c, const MbOp2 o, const CP C, const SvT<T> &vb, T qd, T s, T cs, const AbiT<T> &IA, const SvT<T> &pA,
+                                  AbiT<T> &acc, SvT<T> &pacc)
+{
+   const T qdd = c.ld_x2(o.dof);
+   const int r = o.body * (MB_ABA_REC / 2);
+   c.rec_st2(r + 0, (T)0, (T)0);
+   c.rec_st2(r + 1, (T)0, (T)0);
+   c.rec_st2(r + 2, (T)0, (T)0);
+   c.rec_st2(r + 3, qdd, (T)0);
+   if (!(o.flags & MB2_ROOT_PARENT))
+   {
+      SvT<T> cc;
+      if (REV)
+      {
+         cc.a = v3<T>(vb.a.y * qd, -(vb.a.x * qd), qdd);
+         cc.l = v3<T>(vb.l.y * qd, -(vb.l.x * qd), (T)0);
+      }
+      else
+      {
+         cc.a = v3<T>((T)0, (T)0, (T)0);
+         cc.l = v3<T>(vb.a.y * qd, -(vb.a.x * qd), qdd);
+      }
+      const SvT<T> pa = pA + mul(IA, cc);
+      const XfT<T> X = joint_xf_1dof<T, REV>(C, s, cs);
+      aba_fold<T>(c, o, abi_to_parent<T, 0>(X, IA), force_to_parent(X, pa), acc, pacc);
+   }
+}
+
 // ---- pass one quantities (bias wrench / bias acceleration, :1109-1118) and pass two (:1136-1254) for body i
 template <class T, class Ctx, bool FEXT, bool REV, bool SC>
 MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp, T &ns, T &nc)
@@ -82,6 +132,11 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    {
       IA = IA + acc;
       pA = pA + pacc;
+   }
+   if (FEXT && (o.flags & MB2_ACCSRC))
+   {
+      aba_ascend_1dof_locked<T, Ctx, REV>(c, o, C, vb, qd, s, cs, IA, pA, acc, pacc);
+      return;
    }
    SvT<T> U;
    T D, u;
@@ -147,21 +202,7 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
          pa.l.z = fmad(k0, U.l.z, pa.l.z);
       }
       const XfT<T> X = joint_xf_1dof<T, REV>(C, s, cs);
-      const AbiT<T> K = abi_to_parent<T, Z>(X, Ia); // :1159-1165
-      const SvT<T> Pp = force_to_parent(X, pa);
-      if (o.flags & MB2_FIRST_CHILD)
-      {
-         acc = K;
-         pacc = Pp;
-      }
-      else
-      {
-         aux_ld_abi<T>(c, o.paux, acc, pacc);
-         acc = acc + K;
-         pacc = pacc + Pp;
-      }
-      if (o.flags & MB2_STORE_ACC)
-         aux_st_abi<T>(c, o.paux, acc, pacc);
+      aba_fold<T>(c, o, abi_to_parent<T, Z>(X, Ia), force_to_parent(X, pa), acc, pacc); // :1159-1165
    }
 }
 
@@ -191,10 +232,27 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
       IA = IA + acc;
       pA = pA + pacc;
    }
+   const int r = o.body * (MB_ABA_REC / 2);
+   if (FEXT && (o.flags & MB2_ACCSRC))
+   {
+      // ACCELERATION_SOURCE (:1237-1253): the record carries qdd itself, flagged by its last entry (pass three: a = a' + qdd)
+      const SvT<T> qdd6 = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_x2(rr); });
+      c.rec_st2(r + 0, qdd6.a.x, qdd6.a.y);
+      c.rec_st2(r + 1, qdd6.a.z, qdd6.l.x);
+      c.rec_st2(r + 2, qdd6.l.y, qdd6.l.z);
+      c.rec_st2(r + 3, (T)1, (T)0);
+      if (!(o.flags & MB2_ROOT_PARENT))
+      {
+         const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
+         const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
+         const SvT<T> pa = pA + mul(IA, cross_motion(vb, vj) + qdd6);
+         aba_fold<T>(c, o, abi_to_parent<T, 0>(X, IA), force_to_parent(X, pa), acc, pacc);
+      }
+      return;
+   }
    const SvT<T> tau6 = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
    // D = I^A, U = I^A: a_i = D^-1 u, and the joint transmits nothing but tau to its parent
    const SvT<T> x = abi_solve(IA, tau6 - pA);
-   const int r = o.body * (MB_ABA_REC / 2);
    c.rec_st2(r + 0, x.a.x, x.a.y);
    c.rec_st2(r + 1, x.a.z, x.l.x);
    c.rec_st2(r + 2, x.l.y, x.l.z);
@@ -262,11 +320,17 @@ template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, i
    c.pf3_ld2(st, 1, x.a.x, x.a.y);
    c.pf3_ld2(st, 2, x.a.z, x.l.x);
    c.pf3_ld2(st, 3, x.l.y, x.l.z);
+   T locked, pad;
+   c.pf3_ld2(st, 4, locked, pad); // 1 if the record holds the joint's given acceleration (ACCELERATION_SOURCE), else 0
    const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
    const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
    v = motion_to_child(X, v) + vj;
    const SvT<T> a1 = motion_to_child(X, a) + cross_motion(v, vj);
-   const SvT<T> qdd = x - a1;
+   // effort source: a = x, qdd = x - a'; acceleration source: qdd = x, a = a' + x
+   const T keep = (T)1 - locked;
+   SvT<T> qdd;
+   qdd.a = x.a - keep * a1.a; qdd.l = x.l - keep * a1.l;
+   x.a = x.a + locked * a1.a; x.l = x.l + locked * a1.l;
    c.st_out(o.dof + 0, qdd.a.x); c.st_out(o.dof + 1, qdd.a.y); c.st_out(o.dof + 2, qdd.a.z);
    c.st_out(o.dof + 3, qdd.l.x); c.st_out(o.dof + 4, qdd.l.y); c.st_out(o.dof + 5, qdd.l.z);
    a = x;

@@ -35,6 +35,8 @@ struct mecano_b200_handle
    mb::LaunchPlan plan[3];
    int variant = MECANO_B200_VARIANT_AUTO;
    int max_children = 1, max_ndof = 1, sm_count = 148;
+   int n_accel_source = 0;           // joints in ACCELERATION_SOURCE mode (mecano_b200_set_joint_source_modes)
+   std::vector<std::pair<int, int>> effort_dof_runs; // (first DoF row, count) runs of DoF rows whose joints are EFFORT_SOURCE
    bool warp_ok = false;             // the tree fits the warp-per-state variant (<= 32 bodies)
    int64_t warp_below[3] = {0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
    std::string error;
@@ -84,14 +86,18 @@ int check_batch(mecano_b200_handle *h, int64_t n, int64_t ld)
 }
 
 int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
-        double *out, uint32_t flags, cudaStream_t stream, int ws_slot = 0, double *body_acc = nullptr, double *joint_wrench = nullptr)
+        double *out, uint32_t flags, cudaStream_t stream, int ws_slot = 0, double *body_acc = nullptr, double *joint_wrench = nullptr, const double *x2 = nullptr)
 {
    if (n > (int64_t)1 << 28 || ld > (int64_t)1 << 28)
       return fail(h, MECANO_B200_ERR_TOO_LARGE, "more than 2^28 states (or ld > 2^28) in one call: split the batch");
+   if (algo == MB_ABA && h->n_accel_source > 0 && !x2)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "joints in ACCELERATION_SOURCE mode need their accelerations: call mecano_b200_aba_sources");
+   if (h->n_accel_source == 0)
+      x2 = nullptr; // nothing reads it: the plain kernels serve the call
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
    // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
-   const bool byprod = body_acc || joint_wrench;
+   const bool byprod = body_acc || joint_wrench || x2;
    const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]));
    if (use_warp)
    {
@@ -100,6 +106,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       mb::KernelArgs wa;
       wa.q = q; wa.qd = qd; wa.x = x; wa.fext = fext; wa.out = out;
       wa.body_acc = wa.joint_wrench = nullptr;
+      wa.x2 = nullptr;
       wa.consts = h->d_consts;
       wa.ws = nullptr;
       wa.ws_ld = 0;
@@ -136,6 +143,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    mb::KernelArgs a;
    a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
    a.body_acc = body_acc; a.joint_wrench = joint_wrench;
+   a.x2 = x2;
    a.consts = h->d_consts;
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
@@ -177,6 +185,35 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       return MECANO_B200_OK;
    }
    MB_CUDA(h, mb::launch_thread_kernel(algo, h->tree.prog[algo], a, h->plan[algo], stream));
+   return MECANO_B200_OK;
+}
+
+// ForwardDynamicsCalculator.compute(tau, qdd_in) with per-joint source modes (ForwardDynamicsCalculator.java:508-520): passes one to
+// three in the ABA kernel; pass four (:1315-1363, the efforts of the ACCELERATION_SOURCE joints from the joint wrenches) is the upward
+// sweep of inverse dynamics on the accelerations just computed, i.e. one RNEA launch, after which the rows of the EFFORT_SOURCE
+// joints are restored to the caller's input as getJointTauMatrix() returns them (:566-590).
+int run_aba_sources(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau, const double *qdd_in,
+                    const double *fext, double *qdd, double *tau_out, cudaStream_t stream, int ws_slot)
+{
+   if (h->n_accel_source > 0 && !qdd_in)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer (qdd_in) with joints in ACCELERATION_SOURCE mode");
+   int rc = run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, 0u, stream, ws_slot, nullptr, nullptr, qdd_in);
+   if (rc || !tau_out)
+      return rc;
+   const size_t row = (size_t)ld * sizeof(double);
+   if (h->n_accel_source == 0)
+   {
+      if (tau_out != tau)
+         MB_CUDA(h, cudaMemcpy2DAsync(tau_out, row, tau, row, (size_t)n * sizeof(double), (size_t)h->tree.nv, cudaMemcpyDeviceToDevice, stream));
+      return MECANO_B200_OK;
+   }
+   if (tau_out == tau)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "tau_out must not alias tau when joints are in ACCELERATION_SOURCE mode");
+   rc = run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau_out, 0u, stream, ws_slot);
+   if (rc) return rc;
+   for (const auto &r : h->effort_dof_runs)
+      MB_CUDA(h, cudaMemcpy2DAsync(tau_out + (size_t)r.first * ld, row, tau + (size_t)r.first * ld, row, (size_t)n * sizeof(double), (size_t)r.second,
+                                   cudaMemcpyDeviceToDevice, stream));
    return MECANO_B200_OK;
 }
 
@@ -226,7 +263,8 @@ cudaError_t copy_rows(double *dst, size_t dpitch, const double *src, size_t spit
 
 // Host-pointer pipeline: two slots, each with its own stream; H2D of chunk k+1 overlaps the kernel and D2H of chunk k.
 int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
-             double *out, uint32_t flags, double *body_acc = nullptr, double *joint_wrench = nullptr)
+             double *out, uint32_t flags, double *body_acc = nullptr, double *joint_wrench = nullptr, const double *x2 = nullptr,
+             double *tau_out = nullptr)
 {
    int rc = check_batch(h, n, ld);
    if (rc) return rc;
@@ -237,8 +275,9 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
    MB_CUDA(h, cudaSetDevice(h->device));
    const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
    const bool state_major = algo == MB_CRBA && (flags & MECANO_B200_CRBA_STATE_MAJOR);
-   const size_t in_rows = algo == MB_CRBA ? nq : nq + 2 * nv + (fext ? 6 * nb : 0);
-   const size_t out_rows = algo == MB_CRBA ? nv * nv : nv + (body_acc ? 6 * nb : 0) + (joint_wrench ? 6 * nb : 0);
+   const bool sources = algo == MB_ABA && (x2 || tau_out); // mecano_b200_aba_sources_host
+   const size_t in_rows = algo == MB_CRBA ? nq : nq + 2 * nv + (fext ? 6 * nb : 0) + (x2 ? nv : 0);
+   const size_t out_rows = algo == MB_CRBA ? nv * nv : nv + (body_acc ? 6 * nb : 0) + (joint_wrench ? 6 * nb : 0) + (tau_out ? nv : 0);
    // chunk: ~64 MB of rows per slot, at least 4096 states, multiple of 256
    size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)(in_rows + out_rows));
    chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
@@ -259,13 +298,20 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
          MB_CUDA(h, copy_rows(dqd, chunk, qd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
          MB_CUDA(h, copy_rows(dx, chunk, x + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
          if (fext) MB_CUDA(h, copy_rows(df, chunk, fext + s0, (size_t)ld, w, 6 * nb, cudaMemcpyHostToDevice, st));
+         if (x2) MB_CUDA(h, copy_rows(df + (fext ? 6 * nb : 0) * chunk, chunk, x2 + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
       }
       else
          dout = dq + nq * chunk;
       double *dacc = body_acc ? dout + nv * chunk : nullptr;
       double *dwr = joint_wrench ? dout + (nv + (body_acc ? 6 * nb : 0)) * chunk : nullptr;
-      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, 1 + slot, dacc, dwr);
+      double *dtau = tau_out ? dout + nv * chunk : nullptr;
+      if (sources)
+         rc = run_aba_sources(h, (int64_t)w, (int64_t)chunk, dq, dqd, dx, x2 ? df + (fext ? 6 * nb : 0) * chunk : nullptr, fext ? df : nullptr, dout, dtau, st,
+                              1 + slot);
+      else
+         rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, 1 + slot, dacc, dwr);
       if (rc) return rc;
+      if (dtau) MB_CUDA(h, copy_rows(tau_out + s0, (size_t)ld, dtau, chunk, w, nv, cudaMemcpyDeviceToHost, st));
       if (dacc) MB_CUDA(h, copy_rows(body_acc + s0, (size_t)ld, dacc, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
       if (dwr) MB_CUDA(h, copy_rows(joint_wrench + s0, (size_t)ld, dwr, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
       if (state_major)
@@ -526,6 +572,33 @@ int mecano_b200_aba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *
    if (!q || !qd || !tau || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    MB_CUDA(h, cudaSetDevice(h->device));
    return run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, flags, (cudaStream_t)stream);
+}
+
+int mecano_b200_set_joint_source_modes(mecano_b200_handle *h, const int32_t *accel_source)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   std::lock_guard<std::mutex> lk(h->mu);
+   h->n_accel_source = mb::apply_source_modes(h->tree, accel_source, h->effort_dof_runs);
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_aba_sources(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau, const double *qdd_in,
+                            const double *fext, double *qdd, double *tau_out, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !tau || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   return run_aba_sources(h, n, ld, q, qd, tau, qdd_in, fext, qdd, tau_out, (cudaStream_t)stream, 0);
+}
+
+int mecano_b200_aba_sources_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau,
+                                 const double *qdd_in, const double *fext, double *qdd, double *tau_out)
+{
+   if (h && h->n_accel_source > 0 && !qdd_in)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer (qdd_in) with joints in ACCELERATION_SOURCE mode");
+   return run_host(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, 0u, nullptr, nullptr, qdd_in, tau_out);
 }
 
 int mecano_b200_crba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout, void *stream)

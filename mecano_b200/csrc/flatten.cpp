@@ -587,4 +587,36 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
    }
    return MECANO_B200_OK;
 }
+int apply_source_modes(FlatTree &t, const int32_t *accel_source, std::vector<std::pair<int, int>> &effort_dof_runs)
+{
+   MbProgram &P = t.prog[MB_ABA];
+   std::vector<char> locked((size_t)t.nb, 0); // by internal index
+   int count = 0;
+   if (accel_source)
+      for (int b = 0; b < t.nb; b++)
+         if (accel_source[b])
+         {
+            locked[(size_t)t.internal_of[(size_t)b]] = 1;
+            count++;
+         }
+   for (int k = 0; k < P.nops; k++)
+      if (P.op2[k].code & MB2_ASCEND)
+         P.op2[k].flags = (uint8_t)((P.op2[k].flags & ~MB2_ACCSRC) | (locked[P.op2[k].body] ? MB2_ACCSRC : 0u));
+   // DoF rows of the joints that stay EFFORT_SOURCE, as runs of consecutive rows
+   std::vector<char> effort((size_t)t.nv, 1);
+   for (int i = 0; i < t.nb; i++)
+      if (locked[(size_t)i])
+         for (int k = 0; k < P.body[i].ndof; k++)
+            effort[(size_t)(P.body[i].dof_off + k)] = 0;
+   effort_dof_runs.clear();
+   for (int r = 0; r < t.nv;)
+   {
+      if (!effort[(size_t)r]) { r++; continue; }
+      int e = r;
+      while (e < t.nv && effort[(size_t)e]) e++;
+      effort_dof_runs.emplace_back(r, e - r);
+      r = e;
+   }
+   return count;
+}
 } // namespace mb

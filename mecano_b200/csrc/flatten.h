@@ -4,6 +4,7 @@
 //  CompositeRigidBodyMassMatrixCalculator.java:242-266), done once per handle.
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mecano_b200.h"
@@ -25,4 +26,10 @@ struct FlatTree
 
 // Returns MECANO_B200_OK or a negative error code; `err` receives the message.
 int flatten_tree(const mecano_b200_tree_desc *desc, FlatTree &out, std::string &err);
+
+// ForwardDynamicsCalculator.setJointSourceMode (ForwardDynamicsCalculator.java:400-403) on the flattened ABA program:
+// accel_source [nb] in the caller's body order (NULL = every joint back to EFFORT_SOURCE) marks the ASCEND ops of the
+// ACCELERATION_SOURCE joints; effort_dof_runs receives the (first row, count) runs of DoF rows that stay EFFORT_SOURCE.
+// Returns the number of ACCELERATION_SOURCE joints.
+int apply_source_modes(FlatTree &t, const int32_t *accel_source, std::vector<std::pair<int, int>> &effort_dof_runs);
 } // namespace mb

@@ -101,6 +101,8 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    __device__ __forceinline__ void st_out(int r, double v) { mb_stg(mb_row(ob, (unsigned)r, ld8), v); }
    // optional buffers of the FEXT instantiation (nullptr = absent): external wrenches in, RNEA by-products out
    char *accb, *wrb;
+   const char *x2b;
+   __device__ __forceinline__ double ld_x2(int r) const { return mb_ldg(mb_row(x2b, (unsigned)r, ld8)); }
    bool fext_on, acc_on, wr_on;
    __device__ __forceinline__ bool has_fext() const { return fext_on; }
    __device__ __forceinline__ bool has_acc() const { return acc_on; }
@@ -321,6 +323,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
       c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
       c2.accb = (char *)(a.body_acc + s); c2.wrb = (char *)(a.joint_wrench + s);
+      c2.x2b = (const char *)(a.x2 + s);
       c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
       body(c2);
    }

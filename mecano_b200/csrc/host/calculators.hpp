@@ -152,6 +152,54 @@ class ForwardDynamicsCalculator : public BatchedCalculatorBase
       else
          check(mecano_b200_aba_host(handle_, n, q.ld, q.data, qd.data, tau.data, fext_.data, qddOut.data, 0u));
    }
+
+   // ---- joint source modes (ForwardDynamicsCalculator.java:45-57, :400-465)
+   enum class JointSourceMode { EFFORT_SOURCE, ACCELERATION_SOURCE };
+   void setJointSourceMode(const Joint *joint, JointSourceMode mode)
+   {
+      const int j = input_.indexOf(joint);
+      const int row = j < 0 ? -1 : tables_.body_of_joint[(size_t)j];
+      if (row < 0)
+         throw ScrewTheoryException("the joint is not considered by this calculator");
+      accelSource_.resize(tables_.parent.size(), 0);
+      accelSource_[(size_t)row] = mode == JointSourceMode::ACCELERATION_SOURCE ? 1 : 0;
+      check(mecano_b200_set_joint_source_modes(handle_, accelSource_.data()));
+   }
+   void resetJointSourceModes()
+   {
+      accelSource_.assign(tables_.parent.size(), 0);
+      check(mecano_b200_set_joint_source_modes(handle_, nullptr));
+   }
+   JointSourceMode getJointSourceMode(const Joint *joint) const
+   {
+      const int j = input_.indexOf(joint);
+      const int row = j < 0 ? -1 : tables_.body_of_joint[(size_t)j];
+      return row >= 0 && (size_t)row < accelSource_.size() && accelSource_[(size_t)row] ? JointSourceMode::ACCELERATION_SOURCE : JointSourceMode::EFFORT_SOURCE;
+   }
+   // compute(jointTauMatrix, jointAccelerationMatrix) (:508-520) for N states: qddIn is read at the rows of the
+   // ACCELERATION_SOURCE joints only; qddOut = getJointAccelerationMatrix(), tauOut (may be empty) = getJointTauMatrix()
+   void compute(const MatrixView &q, const MatrixView &qd, const MatrixView &tau, const MatrixView &qddIn, const MatrixView &qddOut,
+                const MatrixView &tauOut, Memory where = Memory::Device)
+   {
+      const int64_t n = q.cols, nv = input_.getNumberOfDoFs(), nq = input_.getConfigurationMatrixSize();
+      checkShape(q, nq, n, "q");
+      checkShape(qd, nv, n, "qd");
+      checkShape(tau, nv, n, "tau");
+      if (qddIn.data) checkShape(qddIn, nv, n, "jointAccelerationInput");
+      checkShape(qddOut, nv, n, "qdd");
+      if (tauOut.data) checkShape(tauOut, nv, n, "tauOut");
+      if (fext_.data) checkShape(fext_, 6 * (int64_t)tables_.parent.size(), n, "externalWrenches");
+      if (q.ld != qd.ld || q.ld != tau.ld || q.ld != qddOut.ld || (fext_.data && fext_.ld != q.ld) || (qddIn.data && qddIn.ld != q.ld) ||
+          (tauOut.data && tauOut.ld != q.ld))
+         throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
+      if (where == Memory::Device)
+         check(mecano_b200_aba_sources(handle_, n, q.ld, q.data, qd.data, tau.data, qddIn.data, fext_.data, qddOut.data, tauOut.data, stream_));
+      else
+         check(mecano_b200_aba_sources_host(handle_, n, q.ld, q.data, qd.data, tau.data, qddIn.data, fext_.data, qddOut.data, tauOut.data));
+   }
+
+ private:
+   std::vector<int32_t> accelSource_;
 };
 
 class CompositeRigidBodyMassMatrixCalculator : public BatchedCalculatorBase

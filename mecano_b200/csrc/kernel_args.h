@@ -8,6 +8,7 @@ namespace mb
 struct KernelArgs
 {
    const double *q, *qd, *x, *fext; // x = qdd (RNEA) or tau (ABA)
+   const double *x2;                // ABA: given accelerations of the ACCELERATION_SOURCE joints (nullable), rows like x
    double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
    double *body_acc, *joint_wrench; // RNEA by-products (nullable), rows [6 * w + c] like fext: spatial acceleration of each body in its
                                     // CoM frame, wrench of each joint in its frameAfterJoint

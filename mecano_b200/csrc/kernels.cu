@@ -206,7 +206,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    if (a.n <= 0)
       return cudaSuccess;
    const bool state_major = algo == MB_CRBA && (a.flags & 1u);
-   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr, state_major, plan.size_class);
+   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr, state_major, plan.size_class);
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so
    // does every kernel with a TMEM stack: a block then allocates its tensor memory, stages the constant records and

@@ -103,6 +103,7 @@ struct MbOp2
 #define MB2_ROOT_PARENT 0x8u
 #define MB2_STORE_ACC 0x10u
 #define MB2_FIRST_CHILD 0x20u
+#define MB2_ACCSRC 0x40u // ABA ASCEND: the joint is an ACCELERATION_SOURCE (mecano_b200_set_joint_source_modes); not part of MB_F_*
 
 // per-body record for the CRBA ancestor walk (8 bytes)
 struct MbWalk

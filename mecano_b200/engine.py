@@ -121,6 +121,40 @@ class Engine:
         check(lib.mecano_b200_aba(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pt, pf, pqdd, flags, self._stream()), self._h)
         return qdd
 
+    def set_joint_source_modes(self, accel_source):
+        """accel_source: [n_bodies] ints in the order of the tree description (non-zero = ACCELERATION_SOURCE), or None to reset."""
+        if accel_source is None:
+            check(lib.mecano_b200_set_joint_source_modes(self._h, None), self._h)
+            return
+        src = np.ascontiguousarray(accel_source, dtype=np.int32)
+        if src.shape != (self.nb,):
+            raise ValueError("expected %d source modes" % self.nb)
+        check(lib.mecano_b200_set_joint_source_modes(self._h, src.ctypes.data), self._h)
+
+    def aba_sources(self, q, qd, tau, qdd_in, qdd, tau_out=None, fext=None):
+        n = q.shape[1]
+        pq, l0 = _dev_ptr_ld(q, self.nq, n)
+        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
+        pt, l2 = _dev_ptr_ld(tau, self.nv, n)
+        pi, l3 = _dev_ptr_ld(qdd_in, self.nv, n)
+        pqdd, l4 = _dev_ptr_ld(qdd, self.nv, n)
+        pto, l5 = _dev_ptr_ld(tau_out, self.nv, n)
+        pf, l6 = _dev_ptr_ld(fext, 6 * self.nb, n)
+        check(lib.mecano_b200_aba_sources(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pt, pi, pf, pqdd, pto, self._stream()), self._h)
+        return qdd
+
+    def aba_sources_host(self, q, qd, tau, qdd_in, qdd, tau_out=None, fext=None):
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        pqd, l1 = _host_ptr_ld(qd, self.nv, n)
+        pt, l2 = _host_ptr_ld(tau, self.nv, n)
+        pi, l3 = _host_ptr_ld(qdd_in, self.nv, n)
+        pqdd, l4 = _host_ptr_ld(qdd, self.nv, n)
+        pto, l5 = _host_ptr_ld(tau_out, self.nv, n)
+        pf, l6 = _host_ptr_ld(fext, 6 * self.nb, n)
+        check(lib.mecano_b200_aba_sources_host(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pt, pi, pf, pqdd, pto), self._h)
+        return qdd
+
     def crba(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
         """M: [nv*nv, n] (entry-major) or [n, nv*nv] (state-major) float64 CUDA tensor."""
         n = q.shape[1]

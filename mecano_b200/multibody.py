@@ -359,6 +359,10 @@ class MultiBodySystem:
         """ctypes pointer to the level-ordered mecano_b200_tree_desc (owned by the model)."""
         return lib.mecano_model_tables(self._model.h)
 
+    def tableRow(self, joint):
+        """Row of `joint` in the tree description handed to the engine (-1: fixed, ignored or foreign joint)."""
+        return int(lib.mecano_model_table_row(self._model.h, joint._id))
+
     def describe(self):
         """Plain numpy description in JointMatrixIndexProvider (depth-first) order, read back through the model
         getters (not through the flattener): used by the tests to feed the oracle."""

@@ -668,7 +668,11 @@ typedef struct
    int nd;
 } aba_step_t;
 
-void mo_aba(const mo_tree *t, const double *g, const double *q, const double *qd, const double *tau, const double *fext, double *qdd)
+/* accsrc (nullable, [nb]): non-zero = the joint is an ACCELERATION_SOURCE (ForwardDynamicsCalculator.java:45-57, :400-403):
+ * its acceleration is taken from qdd_in and its effort is computed (pass four, :1315-1363) into tau_out (nullable, [nv]; the
+ * rows of EFFORT_SOURCE joints repeat the input, getJointTauMatrix() :566-590). */
+static void aba_impl(const mo_tree *t, const double *g, const double *q, const double *qd, const double *tau, const double *fext,
+                     const int *accsrc, const double *qdd_in, double *qdd, double *tau_out)
 {
    frames_t *F = (frames_t *)malloc(sizeof(frames_t));
    aba_step_t *st = (aba_step_t *)malloc(sizeof(aba_step_t) * (size_t)t->nb);
@@ -766,7 +770,26 @@ void mo_aba(const mo_tree *t, const double *g, const double *q, const double *qd
          s->u[k] = d + tau[t->dof_off[i] + k];
       }
 
-      if (t->parent[i] >= 0)
+      if (accsrc && accsrc[i])
+      {
+         /* :1237-1253: nothing is removed from the articulated inertia, the known joint acceleration enters the bias wrench */
+         if (t->parent[i] >= 0)
+         {
+            double ca[6], Iac[6];
+            s->Ia = IA;
+            for (int r = 0; r < 6; r++)
+            {
+               double d = 0.0;
+               for (int k = 0; k < nd; k++) d += s->S[6 * k + r] * qdd_in[t->dof_off[i] + k]; /* getJointAcceleration().get(a) */
+               ca[r] = d;
+            }
+            abi_mulv(&s->Ia, s->c, Iac);
+            for (int r = 0; r < 6; r++) s->pa[r] = pAv[r] + Iac[r];
+            abi_mulv(&s->Ia, ca, Iac);
+            for (int r = 0; r < 6; r++) s->pa[r] += Iac[r];
+         }
+      }
+      else if (t->parent[i] >= 0)
       {
          /* :1217-1235 */
          double UD[36]; /* U Dinv, 6 x nd column-wise */
@@ -828,6 +851,8 @@ void mo_aba(const mo_tree *t, const double *g, const double *q, const double *qd
       {
          double d = 0.0;
          for (int m = 0; m < nd; m++) d += s->Dinv[k * nd + m] * tmp[m];
+         if (accsrc && accsrc[i])
+            d = qdd_in[t->dof_off[i] + k]; /* :1286-1298 */
          qddi[k] = d;
          qdd[t->dof_off[i] + k] = d;
       }
@@ -841,7 +866,55 @@ void mo_aba(const mo_tree *t, const double *g, const double *q, const double *qd
       memcpy(acc[i].w, av, 3 * sizeof(double));
       memcpy(acc[i].v, av + 3, 3 * sizeof(double));
    }
+
+   if (tau_out)
+   {
+      /* pass four (:1315-1363): joint wrenches from the body accelerations, leaves to root.  The body inertia is taken in the
+       * body's CoM frame (zero CoM offset), so the velocity terms are the bias wrench of pass one (:1335-1340) */
+      sv_t *wr = (sv_t *)malloc(sizeof(sv_t) * (size_t)t->nb);
+      for (int i = t->nb - 1; i >= 0; i--)
+      {
+         aba_step_t *s = &st[i];
+         sv_t a = acc[i], W;
+         xf_rel(&F->after[i], &F->com[i], &rel);
+         motion_apply(&rel, &a); /* rigidBodyAcceleration.changeFrame(getBodyFixedFrame()) */
+         dynamic_wrench(t->J + 9 * i, t->mass[i], &a, NULL, &W);
+         xf_rel(&F->com[i], &F->after[i], &rel);
+         force_apply(&rel, &W);
+         sv_add(&W, &s->p);
+         for (int c = i + 1; c < t->nb; c++)
+            if (t->parent[c] == i)
+            {
+               sv_t Wc = wr[c]; /* addJointWrenchFromChild :1358-1363 */
+               force_apply(&st[c].X, &Wc);
+               sv_add(&W, &Wc);
+            }
+         wr[i] = W;
+         for (int k = 0; k < s->nd; k++)
+         {
+            if (accsrc && accsrc[i])
+            {
+               const double *col = s->S + 6 * k;
+               tau_out[t->dof_off[i] + k] = col[0] * W.w[0] + col[1] * W.w[1] + col[2] * W.w[2] + col[3] * W.v[0] + col[4] * W.v[1] + col[5] * W.v[2];
+            }
+            else
+               tau_out[t->dof_off[i] + k] = tau[t->dof_off[i] + k];
+         }
+      }
+      free(wr);
+   }
    free(F); free(st); free(acc);
+}
+
+void mo_aba(const mo_tree *t, const double *g, const double *q, const double *qd, const double *tau, const double *fext, double *qdd)
+{
+   aba_impl(t, g, q, qd, tau, fext, NULL, NULL, qdd, NULL);
+}
+
+void mo_aba_sources(const mo_tree *t, const double *g, const double *q, const double *qd, const double *tau, const double *qdd_in,
+                    const double *fext, const int *accel_source, double *qdd, double *tau_out)
+{
+   aba_impl(t, g, q, qd, tau, fext, accel_source, qdd_in, qdd, tau_out);
 }
 
 /* ================================================================== CRBA

@@ -71,6 +71,12 @@ void mo_rnea_body_accelerations(const mo_tree *t, const double *gravity3, const 
 void mo_rnea_full(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *qdd, const double *fext,
                   int flags, double *tau, double *body_acc, double *joint_wrench);
 
+/* ABA with per-joint source modes (ForwardDynamicsCalculator.java:45-57, :400-444, :508-520): accel_source [nb], non-zero = the
+ * joint's acceleration is an input (qdd_in [nv], its rows only) and its effort an output (pass four :1315-1363).  qdd [nv] holds all
+ * joint accelerations, tau_out (nullable, [nv]) all joint efforts as getJointTauMatrix() :566-590 returns them. */
+void mo_aba_sources(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *tau, const double *qdd_in,
+                    const double *fext, const int *accel_source, double *qdd, double *tau_out);
+
 /* Batched drivers, DoF-major / state-minor buffers x[k*ld + s] (same layout as the C-ABI).
  * fext (nullable) is [(6*nb)][ld].  M is entry-major [(i*nv+j)*ld + s].  nthreads<=0 -> all cores. */
 void mo_rnea_batch(const mo_tree *t, const double *gravity3, long n, long ld, const double *q, const double *qd, const double *qdd,

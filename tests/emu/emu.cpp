@@ -62,6 +62,8 @@ template <class T> struct CpuCtx
    T ld_fext(int b, int k) const { return (T)fext[(6 * b + k) * ld + s]; }
    void st_out(int r, T v) { out[r * ld + s] = (double)v; }
    double *acc_out = nullptr, *wr_out = nullptr;
+   const double *x2 = nullptr;
+   T ld_x2(int r) const { return (T)x2[r * ld + s]; }
    bool has_fext() const { return fext != nullptr; }
    bool has_acc() const { return acc_out != nullptr; }
    bool has_wr() const { return wr_out != nullptr; }
@@ -122,7 +124,8 @@ template <class T> struct CpuCtx
 
 template <class T>
 int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *x,
-        const double *fext, double *out, unsigned flags, char *err, int errlen, double *acc_out = nullptr, double *wr_out = nullptr)
+        const double *fext, double *out, unsigned flags, char *err, int errlen, double *acc_out = nullptr, double *wr_out = nullptr,
+        const int32_t *accel_source = nullptr, const double *x2 = nullptr)
 {
    mb::FlatTree ft;
    std::string e;
@@ -132,6 +135,8 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       if (err) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
       return rc;
    }
+   std::vector<std::pair<int, int>> effort_runs;
+   const int n_locked = mb::apply_source_modes(ft, accel_source, effort_runs);
    const MbProgram &P = ft.prog[algo];
    std::vector<T> consts(ft.consts.begin(), ft.consts.end());
    // poison the work areas so that a read-before-write shows up as NaN
@@ -154,6 +159,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       c.narrow = narrow.data();
       c.acc_out = acc_out;
       c.wr_out = wr_out;
+      c.x2 = x2;
       c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
@@ -162,7 +168,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       }
       else if (algo == MB_ABA)
       {
-         if (fext) mb::aba_state<T, CpuCtx<T>, true>(P, c, grav);
+         if (fext || n_locked > 0) mb::aba_state<T, CpuCtx<T>, true>(P, c, grav);
          else mb::aba_state<T, CpuCtx<T>, false>(P, c, grav);
       }
       else
@@ -184,6 +190,13 @@ extern "C" int emu_rnea_full(const mecano_b200_tree_desc *d, const double *g, lo
                              const double *fext, double *tau, double *acc, double *wr, unsigned flags, char *err, int errlen)
 {
    return run<double>(MB_RNEA, d, g, n, ld, q, qd, x, fext, tau, flags, err, errlen, acc, wr);
+}
+
+// ABA with joints in ACCELERATION_SOURCE mode (passes one to three; accel_source [n_bodies] in the order of the description)
+extern "C" int emu_aba_sources(const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *tau,
+                               const double *qdd_in, const double *fext, const int32_t *accel_source, double *qdd, char *err, int errlen)
+{
+   return run<double>(MB_ABA, d, g, n, ld, q, qd, tau, fext, qdd, 0u, err, errlen, nullptr, nullptr, accel_source, qdd_in);
 }
 
 // Algorithmic operation counts of one state: out5 = {add, mul, div, sincos, flops = add + mul + div}

@@ -143,6 +143,18 @@ class Emu:
         n = q.shape[1]
         return self._run(1, q, qd, tau, self._fext_rows(fext, n), np.full((self.tree.nv, n), np.nan))
 
+    def aba_sources(self, q, qd, tau, qdd_in, accel_source, fext=None):
+        """Passes one to three with joints in ACCELERATION_SOURCE mode; accel_source [nb] in the order of the tree."""
+        n = q.shape[1]
+        qdd = np.full((self.tree.nv, n), np.nan)
+        src = np.ascontiguousarray(np.asarray(accel_source)[self.order], dtype=np.int32)
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_aba_sources(ctypes.byref(self.desc), _d(self.g), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(qd), _d(tau), _d(qdd_in),
+                                      _d(self._fext_rows(fext, n)), src.ctypes.data_as(_ip), _d(qdd), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_aba_sources rc=%d: %s" % (rc, err.value.decode()))
+        return qdd
+
     def crba(self, q):
         n = q.shape[1]
         nv = self.tree.nv

@@ -85,6 +85,15 @@ class Oracle:
         self.lib.mo_aba(ctypes.byref(self.c), _d(self.g), _d(q), _d(qd), _d(tau), _d(fext), _d(qdd))
         return qdd
 
+    def aba_sources(self, q, qd, tau, qdd_in, accel_source, fext=None):
+        """ForwardDynamicsCalculator with per-joint source modes: accel_source [nb] (non-zero = ACCELERATION_SOURCE).
+        Returns (getJointAccelerationMatrix(), getJointTauMatrix()) of one state."""
+        q, qd, tau, qdd_in, fext = map(self._f64, (q, qd, tau, qdd_in, fext))
+        src = np.ascontiguousarray(accel_source, dtype=np.int32)
+        qdd, tau_out = np.zeros(self.t.nv), np.zeros(self.t.nv)
+        self.lib.mo_aba_sources(ctypes.byref(self.c), _d(self.g), _d(q), _d(qd), _d(tau), _d(qdd_in), _d(fext), _i(src), _d(qdd), _d(tau_out))
+        return qdd, tau_out
+
     def crba(self, q):
         q = self._f64(q)
         M = np.zeros((self.t.nv, self.t.nv))

@@ -68,6 +68,32 @@ def test_emulated_rnea_byproducts_match_oracle(idx):
             assert rel(wr[:, :, s], wr_o) < TOL
 
 
+@pytest.mark.parametrize("idx", range(12))
+def test_emulated_aba_source_modes_match_oracle(idx):
+    """ForwardDynamicsCalculator with joints in ACCELERATION_SOURCE mode (ForwardDynamicsCalculator.java:1237-1253, :1286-1298)."""
+    rng = np.random.default_rng(800 + idx)
+    t = trees(rng)[idx]
+    g = (rng.uniform(-1, 1), rng.uniform(-1, 1), -rng.uniform(1, 10))
+    o, e = ol.Oracle(t, gravity=g), el.Emu(t, gravity=g)
+    n = 4
+    q, qd, qdd_in, tau = td.random_states(rng, t, n)
+    fext = rng.uniform(-1, 1, size=(t.nb, 6, n))
+    for trial in range(3):
+        locked = np.zeros(t.nb, np.int32)
+        locked[rng.permutation(t.nb)[: rng.integers(1, t.nb + 1)]] = 1
+        if trial == 2:
+            locked[:] = 1
+        for f in (None, fext):
+            got = e.aba_sources(q, qd, tau, qdd_in, locked, f)
+            assert not np.isnan(got).any()
+            for s in range(n):
+                fo = None if f is None else np.ascontiguousarray(f[:, :, s])
+                want, _ = o.aba_sources(q[:, s], qd[:, s], tau[:, s], qdd_in[:, s], locked, fo)
+                assert rel(got[:, s], want) < TOL
+    # no joint locked: the plain algorithm, bit for bit
+    assert np.array_equal(e.aba_sources(q, qd, tau, qdd_in, np.zeros(t.nb, np.int32)), e.aba(q, qd, tau))
+
+
 def test_table_order_does_not_matter():
     """The C-ABI accepts any topological listing of the bodies (level order from the Java host, or DFS)."""
     rng = np.random.default_rng(9)

@@ -413,3 +413,71 @@ def test_rnea_byproducts_match_oracle(torch_dev, idx):
     only.compute(tq, tqd, tqdd)
     assert only.getBodyAccelerationMatrix() is None
     assert rel(only.getComputedJointWrenchMatrix().cpu().numpy().reshape(t.nb, 6, n), wr) == 0.0
+
+
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 6, 8])
+def test_forward_dynamics_joint_source_modes(torch_dev, idx):
+    """ForwardDynamicsCalculator with joints in JointSourceMode.ACCELERATION_SOURCE (ForwardDynamicsCalculator.java:400-444,
+    :1237-1253, :1286-1298, pass four :1315-1363): against the oracle state by state, and through the reference's own invariant
+    (ForwardDynamicsCalculatorTest.testJointMixedSourceModeGeneral :389-488: FD with a random subset of joints locked returns the
+    accelerations and the efforts of ID) on the whole batch."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(5000 + idx)
+    g = (0.0, 0.0, -9.81)
+    o = ol.Oracle(t, gravity=g)
+    n = 1500
+    q, qd, qdd, _ = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    fext = np.ascontiguousarray(rng.uniform(-1, 1, size=(6 * t.nb, n)))
+    tq, tqd, tqdd, tf = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, fext))
+    ident = mb.InverseDynamicsCalculator(s)
+    ident.setGravitationalAcceleration(g)
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    fdyn.setGravitationalAcceleration(g)
+    joints = s.getAllJoints()
+    for trial, f_host, f_dev in ((0, None, None), (1, fext, tf), (2, None, None)):
+        locked = np.zeros(t.nb, np.int32)
+        locked[rng.permutation(t.nb)[: 1 if t.nb == 1 else rng.integers(1, t.nb)]] = 1
+        if trial == 2:
+            locked[:] = 1  # every joint given: forward dynamics degenerates to inverse dynamics
+        fdyn.resetJointSourceModes()
+        fdyn.setJointSourceModes(lambda j: mb.JointSourceMode.ACCELERATION_SOURCE if locked[joints.index(j)] else None)
+        assert [fdyn.getJointSourceMode(j) == mb.JointSourceMode.ACCELERATION_SOURCE for j in joints] == [bool(v) for v in locked]
+        ident.setExternalWrenches(f_dev)
+        fdyn.setExternalWrenches(f_dev)
+        tau = ident.compute(tq, tqd, tqdd)
+        tau_in = tau.clone()
+        for b in np.nonzero(locked)[0]:
+            nd = 6 if t.jtype[b] == td.SIXDOF else 1
+            tau_in[t.dof_off[b]:t.dof_off[b] + nd] = float("nan")  # the efforts of locked joints must not be read
+        with pytest.raises(mb.MatrixDimensionException):
+            fdyn.compute(tq, tqd, tau_in)  # locked joints need their accelerations
+        got_qdd = fdyn.compute(tq, tqd, tau_in, jointAccelerationInput=tqdd).cpu().numpy()
+        got_tau = fdyn.getJointTauMatrix().cpu().numpy()
+        assert not (np.isnan(got_qdd).any() or np.isnan(got_tau).any()), name
+        tol = 4e-11 if (t.jtype == td.SIXDOF).any() else 1.6e-11  # ForwardDynamicsCalculatorTest.java:38-41
+        assert rel(got_qdd, qdd) < tol * max(1, t.nb / 10), name
+        assert rel(got_tau, tau.cpu().numpy()) < tol * max(1, t.nb / 10), name
+        tau_np = tau_in.cpu().numpy()
+        for k in range(0, n, 97):
+            fo = None if f_host is None else np.ascontiguousarray(f_host[:, k].reshape(t.nb, 6))
+            tin = np.nan_to_num(tau_np[:, k])
+            want_qdd, want_tau = o.aba_sources(q[:, k], qd[:, k], tin, qdd[:, k], locked, fo)
+            assert rel(got_qdd[:, k], want_qdd) < TOL, name
+            assert rel(got_tau[:, k], want_tau) < TOL, name
+        # host path
+        fdyn.setExternalWrenches(f_host)
+        h_qdd = fdyn.compute(q, qd, np.nan_to_num(tau_np), jointAccelerationInput=qdd)
+        assert rel(h_qdd, got_qdd) < 1e-13 and rel(fdyn.getJointTauMatrix(), got_tau) < 1e-13, name
+    # back to the default: the plain kernel, bit for bit
+    fdyn.resetJointSourceModes()
+    fdyn.setExternalWrenchesToZero()
+    ident.setExternalWrenchesToZero()
+    tau = ident.compute(tq, tqd, tqdd)
+    plain = mb.ForwardDynamicsCalculator(s)
+    plain.setGravitationalAcceleration(g)
+    assert torch.equal(fdyn.compute(tq, tqd, tau), plain.compute(tq, tqd, tau))
+    assert fdyn.getJointTauMatrix() is tau

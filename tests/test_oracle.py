@@ -72,6 +72,42 @@ def test_reference_invariants(idx):
             assert np.linalg.eigvalsh(M[:, :, s]).min() > 0
 
 
+@pytest.mark.parametrize("idx", range(10))
+def test_reference_invariant_mixed_source_modes(idx):
+    """ForwardDynamicsCalculatorTest.testJointMixedSourceModeGeneral (:389-488) and
+    testJointAccelerationSourceWithZeroVelocityAcceleration (:283-386): with a random subset of joints switched to
+    ACCELERATION_SOURCE (their efforts zeroed so that they cannot be used), forward dynamics returns the accelerations AND
+    the efforts of inverse dynamics, to 1e-12 * max(1, max element).  The reference tests revolute chains; here every tree
+    of the suite, floating joints included, with and without external wrenches."""
+    rng = np.random.default_rng(900 + idx)
+    name, t = cases(rng)[idx]
+    o = ol.Oracle(t, gravity=(0.0, 0.0, -9.81))
+    n = 20
+    q, qd, qdd, _ = td.random_states(rng, t, n)
+    for s in range(n):
+        locked = np.zeros(t.nb, np.int32)
+        locked[rng.permutation(t.nb)[: 1 if t.nb == 1 else rng.integers(1, t.nb)]] = 1
+        qd_s, qdd_s = qd[:, s].copy(), qdd[:, s].copy()
+        if s % 2:  # the zero-velocity / zero-acceleration variant
+            for b in np.nonzero(locked)[0]:
+                nd = 6 if t.jtype[b] == td.SIXDOF else 1
+                qd_s[t.dof_off[b]:t.dof_off[b] + nd] = 0.0
+                qdd_s[t.dof_off[b]:t.dof_off[b] + nd] = 0.0
+        fext = None if s % 3 else rng.uniform(-1, 1, size=(t.nb, 6))
+        tau = o.rnea(q[:, s], qd_s, qdd_s, fext)
+        tau_in = tau.copy()
+        for b in np.nonzero(locked)[0]:
+            nd = 6 if t.jtype[b] == td.SIXDOF else 1
+            tau_in[t.dof_off[b]:t.dof_off[b] + nd] = 0.0
+        qdd_out, tau_out = o.aba_sources(q[:, s], qd_s, tau_in, qdd_s, locked, fext)
+        scale = 4.0 if (t.jtype == td.SIXDOF).any() else 1.0  # the reference's floating-joint tolerances are 5x its one-DoF ones
+        assert np.max(np.abs(qdd_out - qdd_s)) <= scale * 1.0e-12 * max(1.0, np.max(np.abs(qdd_s))), name
+        assert np.max(np.abs(tau_out - tau)) <= scale * 1.0e-12 * max(1.0, np.max(np.abs(tau))), name
+        # nothing locked: the plain algorithm
+        free_qdd, free_tau = o.aba_sources(q[:, s], qd_s, tau, qdd_s, np.zeros(t.nb, np.int32), fext)
+        assert np.array_equal(free_qdd, o.aba(q[:, s], qd_s, tau, fext)) and np.array_equal(free_tau, tau)
+
+
 def test_flags_match_zeroed_inputs():
     """setConsiderCoriolisAndCentrifugalForces(false) == zero velocities; setConsiderJointAccelerations(false) == zero
     accelerations (InverseDynamicsCalculator.java:882-915)."""
