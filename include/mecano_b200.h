@@ -203,6 +203,28 @@ int mecano_b200_crba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const 
                      void *stream);
 
 /*
+ * Centroidal by-products of the mass-matrix calculator (CompositeRigidBodyMassMatrixCalculator.java:380-440, :801-839).
+ * `frame` is the centroidal momentum frame (setCentroidalMomentumFrame, :380-387):
+ *   MECANO_B200_FRAME_WORLD           the inertial frame of the system (the root body's frame);
+ *   MECANO_B200_FRAME_CENTER_OF_MASS  axes of the inertial frame, origin at the centre of mass of the system in each state (what a
+ *                                     CenterOfMassReferenceFrame handed to the Java calculator is).
+ * mecano_b200_crba_centroidal = getMassMatrix() + getCentroidalMomentumMatrix() (:801-809) for N states:
+ *   mass_matrix [n_dofs * n_dofs][ld]  entry-major, every entry written
+ *   cmm         [6 * n_dofs][ld]       entry (r, j) of the 6 x n_dofs matrix at row r * n_dofs + j (the layout of Mecano's row-major
+ *                                      DMatrixRMaj, state-minor); angular momentum rows first.  cmm * qd = momentum in `frame`
+ *   com         [4][ld]                centre of mass in the root frame (x, y, z) and total mass
+ * mecano_b200_centroidal_convective_term = getCentroidalConvectiveTerm() (:811-839), d/dt(cmm) qd:
+ *   out         [6][ld]                moment first; `com` = the rows written by mecano_b200_crba_centroidal for the same q (needed
+ *                                      for MECANO_B200_FRAME_CENTER_OF_MASS only, else may be NULL)
+ */
+#define MECANO_B200_FRAME_WORLD 0
+#define MECANO_B200_FRAME_CENTER_OF_MASS 1
+int mecano_b200_crba_centroidal(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, double *cmm, double *com,
+                                int frame, void *stream);
+int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *com,
+                                           double *out, int frame, void *stream);
+
+/*
  * Host-pointer entry points (what a JNI / Panama binding calls with DMatrixRMaj.data): inputs are
  * staged host -> device in chunks, the kernels run, results are copied back; the call returns when
  * the outputs are complete.  Pinned (page-locked) host memory makes the copies asynchronous and
@@ -217,6 +239,10 @@ int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, co
 int mecano_b200_aba_sources_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                                  const double *qdd_in, const double *fext, double *qdd, double *tau_out);
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
+int mecano_b200_crba_centroidal_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, double *cmm,
+                                     double *com, int frame);
+int mecano_b200_centroidal_convective_term_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd,
+                                                const double *com, double *out, int frame);
 
 /*
  * State integrator: MultiBodySystemStateIntegrator(dt).doubleIntegrateFromAcceleration(joints)

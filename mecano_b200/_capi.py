@@ -27,6 +27,7 @@ RNEA_NO_CORIOLIS, RNEA_NO_ACCELERATIONS = 1, 2
 CRBA_ENTRY_MAJOR, CRBA_STATE_MAJOR = 0, 1
 CRBA_ZEROS_PRESENT = 2  # structurally zero entries already hold zeros (same tree, same buffer): not written / transferred again
 ALGO_RNEA, ALGO_ABA, ALGO_CRBA = 0, 1, 2
+FRAME_WORLD, FRAME_CENTER_OF_MASS = 0, 1
 
 
 class TreeDesc(ctypes.Structure):
@@ -62,6 +63,8 @@ EXPORTS = [
     "mecano_b200_integrate", "mecano_b200_integrate_host", "mecano_b200_host_alloc", "mecano_b200_host_free", "mecano_b200_generate_source", "mecano_b200_jit_check", "mecano_b200_specialize",
     "mecano_b200_rnea_full", "mecano_b200_rnea_full_host",
     "mecano_b200_set_joint_source_modes", "mecano_b200_aba_sources", "mecano_b200_aba_sources_host",
+    "mecano_b200_crba_centroidal", "mecano_b200_centroidal_convective_term", "mecano_b200_crba_centroidal_host",
+    "mecano_b200_centroidal_convective_term_host",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -82,6 +85,10 @@ lib.mecano_b200_aba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp
 lib.mecano_b200_set_joint_source_modes.argtypes = [c_vp, c_vp]
 lib.mecano_b200_aba_sources.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
 lib.mecano_b200_aba_sources_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+lib.mecano_b200_crba_centroidal.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
+lib.mecano_b200_centroidal_convective_term.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
+lib.mecano_b200_crba_centroidal_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int]
+lib.mecano_b200_centroidal_convective_term_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int]
 lib.mecano_b200_crba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32, c_vp]
 lib.mecano_b200_rnea_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
 lib.mecano_b200_aba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]

@@ -270,16 +270,77 @@ class ForwardDynamicsCalculator(_BatchedCalculator):
 class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
     _ALGO = _capi.ALGO_CRBA
 
-    def __init__(self, input, device=0):
+    WORLD_FRAME = "worldFrame"                 # the inertial frame of the system
+    CENTER_OF_MASS_FRAME = "centerOfMassFrame"  # axes of the inertial frame, origin at the centre of mass of each state
+
+    def __init__(self, input, centroidalMomentumFrame=None, device=0):
+        """CompositeRigidBodyMassMatrixCalculator(input[, centroidalMomentumFrame]) (:182-233).  Mecano takes any ReferenceFrame;
+        the batched calculator offers the two that make sense for N states at once: WORLD_FRAME (the default, Mecano's is the
+        inertial frame too, :184) and CENTER_OF_MASS_FRAME (Mecano's CenterOfMassReferenceFrame)."""
         super().__init__(input, device)
         self._M = None
         self._owned = {}
+        self._cmm = self._com = self._convective = None
+        self._frame = self.WORLD_FRAME
+        if centroidalMomentumFrame is not None:
+            self.setCentroidalMomentumFrame(centroidalMomentumFrame)
+
+    def setCentroidalMomentumFrame(self, centroidalMomentumFrame):
+        """setCentroidalMomentumFrame (:380-387)."""
+        if centroidalMomentumFrame not in (self.WORLD_FRAME, self.CENTER_OF_MASS_FRAME):
+            raise ValueError("centroidalMomentumFrame must be WORLD_FRAME or CENTER_OF_MASS_FRAME")
+        if centroidalMomentumFrame != self._frame:
+            self._cmm = self._convective = None
+        self._frame = centroidalMomentumFrame
+
+    def getCentroidalMomentumFrame(self):
+        return self._frame
+
+    def _frame_code(self):
+        return _capi.FRAME_CENTER_OF_MASS if self._frame == self.CENTER_OF_MASS_FRAME else _capi.FRAME_WORLD
+
+    def getCentroidalMomentumMatrix(self, q):
+        """getCentroidalMomentumMatrix() (:411-416, :801-809) for N states: [6 * nDoFs, N], entry (r, j) of the 6 x nDoFs matrix of
+        state s at [r * nDoFs + j, s] (angular rows first); times the joint velocities it gives the momentum of the system in the
+        centroidal momentum frame.  The mass matrix of the same states is computed on the way (getMassMatrix() without an
+        argument returns it), as are the centre of mass and total mass (getCenterOfMass())."""
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        self._check("q", q, nq, n)
+        self._M = self._empty_like(q, nv * nv, n)
+        self._cmm = self._empty_like(q, 6 * nv, n)
+        self._com = self._empty_like(q, 4, n)
+        self._engine.crba_centroidal(q, self._M, self._cmm, self._com, self._frame_code())
+        return self._cmm
+
+    def getCenterOfMass(self):
+        """[4, N]: centre of mass of the system in the root frame (x, y, z) and its total mass, of the states last handed to
+        getCentroidalMomentumMatrix()."""
+        return self._com
+
+    def getCentroidalConvectiveTermMatrix(self, q, qd):
+        """getCentroidalConvectiveTermMatrix() (:423-440, :811-839) for N states: [6, N], moment first, in the centroidal momentum
+        frame.  In CENTER_OF_MASS_FRAME the centre of mass comes from getCentroidalMomentumMatrix(q), which is called first if
+        it has not been for a batch of this size."""
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        self._check("q", q, nq, n)
+        self._check("qd", qd, nv, n)
+        com = None
+        if self._frame == self.CENTER_OF_MASS_FRAME:
+            if self._com is None or self._com.shape[1] != n or _is_torch(self._com) != _is_torch(q):
+                self.getCentroidalMomentumMatrix(q)
+            com = self._com
+        out = self._empty_like(q, 6, n)
+        self._engine.centroidal_convective_term(q, qd, com, out, self._frame_code())
+        self._convective = out
+        return out
 
     def reset(self):
         """Mecano caches the mass matrix until reset(); the batched calculator recomputes on every getMassMatrix(q)."""
         self._M = None
 
-    def getMassMatrix(self, q, massMatrix=None, stateMajor=False):
+    def getMassMatrix(self, q=None, massMatrix=None, stateMajor=False):
         """Mass matrices for N states.  Default layout [nDoFs*nDoFs, N] (entry (i, j) of state s at [i*nDoFs + j, s]);
         stateMajor=True gives [N, nDoFs*nDoFs], i.e. one Mecano-style dense row-major nDoFs x nDoFs matrix per state.
 
@@ -288,6 +349,8 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         calls.  The entries coupling joints of unrelated branches depend on the topology only, so they are written once and
         from the second call on neither rewritten nor (host path) transferred again (MECANO_B200_CRBA_ZEROS_PRESENT).  A
         caller-supplied `massMatrix` is always written in full."""
+        if q is None:
+            return self._M  # the matrices of the last call, like Mecano's cached getMassMatrix()
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
         n = q.shape[1] if q.ndim == 2 else -1
         self._check("q", q, nq, n)

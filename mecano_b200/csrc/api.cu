@@ -28,6 +28,8 @@ struct mecano_b200_handle
    std::vector<std::pair<int, int>> nonzero_runs; // CRBA: (first entry, count) runs of mass-matrix entries that are not structurally zero
    double *d_zero_row = nullptr; // one row of zeros: stands in for qd / qdd when RNEA ignores velocities / accelerations
    size_t zero_row_doubles = 0;
+   double *d_scratch = nullptr; // joint efforts nobody asked for (centroidal convective term = one RNEA launch)
+   size_t scratch_doubles = 0;
    double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
    size_t ws_doubles[3] = {0, 0, 0};
    mb::SpecKernel spec[3];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
@@ -85,9 +87,23 @@ int check_batch(mecano_b200_handle *h, int64_t n, int64_t ld)
    return MECANO_B200_OK;
 }
 
-int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
-        double *out, uint32_t flags, cudaStream_t stream, int ws_slot = 0, double *body_acc = nullptr, double *joint_wrench = nullptr, const double *x2 = nullptr)
+// optional buffers of one launch; any of them routes the call to the generic thread-per-state kernel
+struct RunOpts
 {
+   int ws_slot = 0;                                      // ABA workspace: 0 device entry points, 1 / 2 the host-pipeline slots
+   double *body_acc = nullptr, *joint_wrench = nullptr; // RNEA by-products
+   const double *x2 = nullptr;                           // ABA: accelerations of the ACCELERATION_SOURCE joints
+   double *cmm = nullptr, *com = nullptr;                // CRBA: centroidal momentum matrix (root frame), (mass * CoM, mass)
+   double *root_wrench = nullptr;                        // RNEA: wrench at the root (root frame)
+   bool zero_gravity = false;
+};
+
+int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
+        double *out, uint32_t flags, cudaStream_t stream, const RunOpts &opt = RunOpts())
+{
+   const int ws_slot = opt.ws_slot;
+   double *const body_acc = opt.body_acc, *const joint_wrench = opt.joint_wrench;
+   const double *x2 = opt.x2;
    if (n > (int64_t)1 << 28 || ld > (int64_t)1 << 28)
       return fail(h, MECANO_B200_ERR_TOO_LARGE, "more than 2^28 states (or ld > 2^28) in one call: split the batch");
    if (algo == MB_ABA && h->n_accel_source > 0 && !x2)
@@ -97,7 +113,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
    // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
-   const bool byprod = body_acc || joint_wrench || x2;
+   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench;
    const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]));
    if (use_warp)
    {
@@ -107,6 +123,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.q = q; wa.qd = qd; wa.x = x; wa.fext = fext; wa.out = out;
       wa.body_acc = wa.joint_wrench = nullptr;
       wa.x2 = nullptr;
+      wa.cmm = wa.com = wa.root_wrench = nullptr;
       wa.consts = h->d_consts;
       wa.ws = nullptr;
       wa.ws_ld = 0;
@@ -144,6 +161,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.q = q; a.qd = qd; a.x = x; a.fext = fext; a.out = out;
    a.body_acc = body_acc; a.joint_wrench = joint_wrench;
    a.x2 = x2;
+   a.cmm = opt.cmm; a.com = opt.com; a.root_wrench = opt.root_wrench;
    a.consts = h->d_consts;
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
@@ -173,6 +191,8 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       if (flags & MECANO_B200_RNEA_NO_ACCELERATIONS) { a.x = h->d_zero_row; a.ld_x = 0; }
    }
    a.grav[0] = h->gravity[0]; a.grav[1] = h->gravity[1]; a.grav[2] = h->gravity[2];
+   if (opt.zero_gravity)
+      a.grav[0] = a.grav[1] = a.grav[2] = 0.0;
    a.flags = flags;
    a.nv = h->tree.nv;
    if (use_spec)
@@ -197,7 +217,10 @@ int run_aba_sources(mecano_b200_handle *h, int64_t n, int64_t ld, const double *
 {
    if (h->n_accel_source > 0 && !qdd_in)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer (qdd_in) with joints in ACCELERATION_SOURCE mode");
-   int rc = run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, 0u, stream, ws_slot, nullptr, nullptr, qdd_in);
+   RunOpts opt;
+   opt.ws_slot = ws_slot;
+   opt.x2 = qdd_in;
+   int rc = run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, 0u, stream, opt);
    if (rc || !tau_out)
       return rc;
    const size_t row = (size_t)ld * sizeof(double);
@@ -209,7 +232,7 @@ int run_aba_sources(mecano_b200_handle *h, int64_t n, int64_t ld, const double *
    }
    if (tau_out == tau)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "tau_out must not alias tau when joints are in ACCELERATION_SOURCE mode");
-   rc = run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau_out, 0u, stream, ws_slot);
+   rc = run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau_out, 0u, stream);
    if (rc) return rc;
    for (const auto &r : h->effort_dof_runs)
       MB_CUDA(h, cudaMemcpy2DAsync(tau_out + (size_t)r.first * ld, row, tau + (size_t)r.first * ld, row, (size_t)n * sizeof(double), (size_t)r.second,
@@ -309,7 +332,13 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
          rc = run_aba_sources(h, (int64_t)w, (int64_t)chunk, dq, dqd, dx, x2 ? df + (fext ? 6 * nb : 0) * chunk : nullptr, fext ? df : nullptr, dout, dtau, st,
                               1 + slot);
       else
-         rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, 1 + slot, dacc, dwr);
+      {
+         RunOpts opt;
+         opt.ws_slot = 1 + slot;
+         opt.body_acc = dacc;
+         opt.joint_wrench = dwr;
+         rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, opt);
+      }
       if (rc) return rc;
       if (dtau) MB_CUDA(h, copy_rows(tau_out + s0, (size_t)ld, dtau, chunk, w, nv, cudaMemcpyDeviceToHost, st));
       if (dacc) MB_CUDA(h, copy_rows(body_acc + s0, (size_t)ld, dacc, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
@@ -453,6 +482,7 @@ void mecano_b200_destroy(mecano_b200_handle *h)
       if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
    }
    if (h->d_zero_row) cudaFree(h->d_zero_row);
+   if (h->d_scratch) cudaFree(h->d_scratch);
    if (h->d_consts) cudaFree(h->d_consts);
    if (h->d_zero) cudaFree(h->d_zero);
    if (h->d_prog) cudaFree(h->d_prog);
@@ -560,7 +590,10 @@ int mecano_b200_rnea_full(mecano_b200_handle *h, int64_t n, int64_t ld, const do
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !qdd || !tau) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    MB_CUDA(h, cudaSetDevice(h->device));
-   return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream, 0, body_acc, joint_wrench);
+   RunOpts opt;
+   opt.body_acc = body_acc;
+   opt.joint_wrench = joint_wrench;
+   return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream, opt);
 }
 
 int mecano_b200_aba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau, const double *fext,
@@ -599,6 +632,141 @@ int mecano_b200_aba_sources_host(mecano_b200_handle *h, int64_t n, int64_t ld, c
    if (h && h->n_accel_source > 0 && !qdd_in)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer (qdd_in) with joints in ACCELERATION_SOURCE mode");
    return run_host(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, 0u, nullptr, nullptr, qdd_in, tau_out);
+}
+
+int mecano_b200_crba_centroidal(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, double *cmm, double *com, int frame,
+                                void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !M || !cmm || !com) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   if (frame != MECANO_B200_FRAME_WORLD && frame != MECANO_B200_FRAME_CENTER_OF_MASS)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown centroidal momentum frame");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   cudaStream_t st = (cudaStream_t)stream;
+   // the kernel sums (mass * CoM, mass) over the children of the root body into the com rows
+   MB_CUDA(h, cudaMemset2DAsync(com, (size_t)ld * sizeof(double), 0, (size_t)n * sizeof(double), 4, st));
+   RunOpts opt;
+   opt.cmm = cmm;
+   opt.com = com;
+   rc = run(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, M, MECANO_B200_CRBA_ENTRY_MAJOR, st, opt);
+   if (rc) return rc;
+   mb::CentroidalArgs ca;
+   ca.cols = cmm; ca.com = com; ca.n = n; ca.ld = ld; ca.ncols = h->tree.nv;
+   ca.normalize_com = 1;
+   ca.shift = frame == MECANO_B200_FRAME_CENTER_OF_MASS;
+   MB_CUDA(h, mb::launch_centroidal_finish(ca, st));
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *com,
+                                           double *out, int frame, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !out) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   if (frame != MECANO_B200_FRAME_WORLD && frame != MECANO_B200_FRAME_CENTER_OF_MASS)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown centroidal momentum frame");
+   if (frame == MECANO_B200_FRAME_CENTER_OF_MASS && !com)
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the centre-of-mass frame needs the com rows of mecano_b200_crba_centroidal");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   cudaStream_t st = (cudaStream_t)stream;
+   const size_t need = (size_t)h->tree.nv * (size_t)ld;
+   if (h->scratch_doubles < need)
+   {
+      if (h->d_scratch)
+      {
+         MB_CUDA(h, cudaDeviceSynchronize());
+         MB_CUDA(h, cudaFree(h->d_scratch));
+         h->d_scratch = nullptr;
+         h->scratch_doubles = 0;
+      }
+      MB_CUDA(h, cudaMalloc(&h->d_scratch, need * sizeof(double)));
+      h->scratch_doubles = need;
+   }
+   // :811-839: the net wrench of every body under zero joint accelerations and no gravity, summed in the centroidal frame = the
+   // wrench at the root of inverse dynamics run that way
+   MB_CUDA(h, cudaMemset2DAsync(out, (size_t)ld * sizeof(double), 0, (size_t)n * sizeof(double), 6, st));
+   RunOpts opt;
+   opt.root_wrench = out;
+   opt.zero_gravity = true;
+   rc = run(h, MB_RNEA, n, ld, q, qd, qd, nullptr, h->d_scratch, MECANO_B200_RNEA_NO_ACCELERATIONS, st, opt);
+   if (rc) return rc;
+   if (frame == MECANO_B200_FRAME_CENTER_OF_MASS)
+   {
+      mb::CentroidalArgs ca;
+      ca.cols = out; ca.com = const_cast<double *>(com); ca.n = n; ca.ld = ld; ca.ncols = 1;
+      ca.normalize_com = 0;
+      ca.shift = 1;
+      MB_CUDA(h, mb::launch_centroidal_finish(ca, st));
+   }
+   return MECANO_B200_OK;
+}
+
+// host-pointer variants of the two centroidal calls: plain staging through temporary device buffers, chunk by chunk
+int mecano_b200_crba_centroidal_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, double *cmm, double *com, int frame)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !M || !cmm || !com) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_CUDA(h, cudaSetDevice(h->device));
+   const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + nv * nv + 6 * nv + 4;
+   const size_t chunk = (size_t)std::min<int64_t>(n, 16384);
+   double *d = nullptr;
+   MB_CUDA(h, cudaMalloc(&d, rows * chunk * sizeof(double)));
+   double *dq = d, *dM = dq + nq * chunk, *dA = dM + nv * nv * chunk, *dc = dA + 6 * nv * chunk;
+   cudaError_t e = cudaSuccess;
+   for (int64_t s0 = 0; s0 < n && rc == 0 && e == cudaSuccess; s0 += (int64_t)chunk)
+   {
+      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
+      e = copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, nullptr);
+      if (e != cudaSuccess) break;
+      rc = mecano_b200_crba_centroidal(h, (int64_t)w, (int64_t)chunk, dq, dM, dA, dc, frame, nullptr);
+      if (rc) break;
+      e = copy_rows(M + s0, (size_t)ld, dM, chunk, w, nv * nv, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = copy_rows(cmm + s0, (size_t)ld, dA, chunk, w, 6 * nv, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = copy_rows(com + s0, (size_t)ld, dc, chunk, w, 4, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+   }
+   cudaFree(d);
+   if (e != cudaSuccess) return cuda_fail(h, e, "mecano_b200_crba_centroidal_host");
+   return rc;
+}
+
+int mecano_b200_centroidal_convective_term_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *com,
+                                                double *out, int frame)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !out) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_CUDA(h, cudaSetDevice(h->device));
+   const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + nv + 4 + 6;
+   const size_t chunk = (size_t)std::min<int64_t>(n, 262144);
+   double *d = nullptr;
+   MB_CUDA(h, cudaMalloc(&d, rows * chunk * sizeof(double)));
+   double *dq = d, *dqd = dq + nq * chunk, *dc = dqd + nv * chunk, *dout = dc + 4 * chunk;
+   cudaError_t e = cudaSuccess;
+   for (int64_t s0 = 0; s0 < n && rc == 0 && e == cudaSuccess; s0 += (int64_t)chunk)
+   {
+      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
+      e = copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, nullptr);
+      if (e == cudaSuccess) e = copy_rows(dqd, chunk, qd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, nullptr);
+      if (e == cudaSuccess && com) e = copy_rows(dc, chunk, com + s0, (size_t)ld, w, 4, cudaMemcpyHostToDevice, nullptr);
+      if (e != cudaSuccess) break;
+      rc = mecano_b200_centroidal_convective_term(h, (int64_t)w, (int64_t)chunk, dq, dqd, com ? dc : nullptr, dout, frame, nullptr);
+      if (rc) break;
+      e = copy_rows(out + s0, (size_t)ld, dout, chunk, w, 6, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+   }
+   cudaFree(d);
+   if (e != cudaSuccess) return cuda_fail(h, e, "mecano_b200_centroidal_convective_term_host");
+   return rc;
 }
 
 int mecano_b200_crba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout, void *stream)

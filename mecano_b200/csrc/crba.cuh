@@ -55,7 +55,9 @@ template <class T, class Ctx> MB_HD void crba_project(Ctx &c, int jt, int dj, in
 
 // walk from body b (whose force column F is expressed in its own frame, transform given by (s, cs) / the stack) up to
 // the root, filling the off-diagonal blocks of column `col` (:772-797)
-template <class T, class Ctx> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int b, int col, T s, T cs, SvT<T> F)
+// BY (by-products instantiation): the walk also runs for the children of the root body and ends by re-expressing the unit
+// momentum in the root frame, which is column `col` of the centroidal momentum matrix (computeCentroidalMomentumMatrix(), :801-809)
+template <class T, class Ctx, bool BY = false> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int b, int col, T s, T cs, SvT<T> F)
 {
    MbWalk w = P.walk[b];
    while (!(w.flags & 1u)) // until the parent is the root body
@@ -73,9 +75,22 @@ template <class T, class Ctx> MB_HD void crba_walk(const MbProgram &P, Ctx &c, i
       if (w.jtype != MB_SIXDOF)
          c.stk_ld2(w.slot, 0, s, cs);
    }
+   if (BY)
+   {
+      const auto C = c.cst(b);
+      if (w.jtype == MB_REVOLUTE)
+         F = force_up_1dof<T, true>(C, s, cs, F);
+      else if (w.jtype == MB_PRISMATIC)
+         F = force_up_1dof<T, false>(C, s, cs, F);
+      else
+         F = force_to_parent(stk_ld_xf<T>(c, w.slot), F);
+      const int nv = c.n_dofs();
+      c.st_cmm(0 * nv + col, F.a.x); c.st_cmm(1 * nv + col, F.a.y); c.st_cmm(2 * nv + col, F.a.z);
+      c.st_cmm(3 * nv + col, F.l.x); c.st_cmm(4 * nv + col, F.l.y); c.st_cmm(5 * nv + col, F.l.z);
+   }
 }
 
-template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
+template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbProgram &P, Ctx &c)
 {
    // entries coupling joints of unrelated branches are zero
    c.zero_fill();
@@ -148,8 +163,8 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
             F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
             F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
             c.st_M(d * nv + d, F.a.z);
-            if (!(o.flags & MB2_ROOT_PARENT))
-               crba_walk<T>(P, c, o.body, d, js, jc, F);
+            if (BY || !(o.flags & MB2_ROOT_PARENT))
+               crba_walk<T, Ctx, BY>(P, c, o.body, d, js, jc, F);
          }
          else if (jt == MB_PRISMATIC)
          {
@@ -157,8 +172,8 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
             F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
             F.l = v3<T>((T)0, (T)0, Ic.m);
             c.st_M(d * nv + d, F.l.z);
-            if (!(o.flags & MB2_ROOT_PARENT))
-               crba_walk<T>(P, c, o.body, d, js, jc, F);
+            if (BY || !(o.flags & MB2_ROOT_PARENT))
+               crba_walk<T, Ctx, BY>(P, c, o.body, d, js, jc, F);
          }
          else
          {
@@ -172,9 +187,20 @@ template <class T, class Ctx> MB_HD void crba_state(const MbProgram &P, Ctx &c)
                const int dc = d + col;
                c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
                c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
-               if (!(o.flags & MB2_ROOT_PARENT))
-                  crba_walk<T>(P, c, o.body, dc, js, jc, F);
+               if (BY || !(o.flags & MB2_ROOT_PARENT))
+                  crba_walk<T, Ctx, BY>(P, c, o.body, dc, js, jc, F);
             }
+         }
+         if (BY && (o.flags & MB2_ROOT_PARENT))
+         {
+            // first moment and mass of this subtree in the root frame, summed over the children of the root body into the
+            // centre-of-mass rows (zeroed before the launch): the origin of a centre-of-mass centroidal frame
+            XfT<T> X;
+            if (jt == MB_REVOLUTE) X = joint_xf_1dof<T, true>(C, js, jc);
+            else if (jt == MB_PRISMATIC) X = joint_xf_1dof<T, false>(C, js, jc);
+            else X = stk_ld_xf<T>(c, o.slot);
+            const V3T<T> hw = mul(X.R, Ic.h) + Ic.m * X.p;
+            c.add_com(0, hw.x); c.add_com(1, hw.y); c.add_com(2, hw.z); c.add_com(3, Ic.m);
          }
          if (!(o.flags & MB2_ROOT_PARENT))
          {

@@ -102,6 +102,19 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    // optional buffers of the FEXT instantiation (nullptr = absent): external wrenches in, RNEA by-products out
    char *accb, *wrb;
    const char *x2b;
+   char *cmmb, *comb, *rwb;
+   bool rootw_on;
+   __device__ __forceinline__ bool has_rootw() const { return rootw_on; }
+   __device__ __forceinline__ void st_cmm(int row, double v) { mb_stg(mb_row(cmmb, (unsigned)row, ld8), v); }
+   // read-modify-write by the one thread that owns the state (the padding lanes of a clamped tile repeat the last state: not them)
+   __device__ __forceinline__ void add_com(int r, double v)
+   {
+      if (!kClamp || active) { double *p = (double *)mb_row(comb, (unsigned)r, ld8); *p += v; }
+   }
+   __device__ __forceinline__ void add_rootw(int r, double v)
+   {
+      if (!kClamp || active) { double *p = (double *)mb_row(rwb, (unsigned)r, ld8); *p += v; }
+   }
    __device__ __forceinline__ double ld_x2(int r) const { return mb_ldg(mb_row(x2b, (unsigned)r, ld8)); }
    bool fext_on, acc_on, wr_on;
    __device__ __forceinline__ bool has_fext() const { return fext_on; }
@@ -298,7 +311,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       c2.tm0 = __shfl_sync(0xffffffffu, c2.tm0, 0);
    }
    c2.active = true;
-   c2.fext_on = a.fext != nullptr; c2.acc_on = a.body_acc != nullptr; c2.wr_on = a.joint_wrench != nullptr;
+   c2.fext_on = a.fext != nullptr; c2.acc_on = a.body_acc != nullptr; c2.wr_on = a.joint_wrench != nullptr; c2.rootw_on = a.root_wrench != nullptr;
    c2.aux = aux;
    c2.nv = a.nv;
    c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
@@ -324,6 +337,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
       c2.accb = (char *)(a.body_acc + s); c2.wrb = (char *)(a.joint_wrench + s);
       c2.x2b = (const char *)(a.x2 + s);
+      c2.cmmb = (char *)(a.cmm + s); c2.comb = (char *)(a.com + s); c2.rwb = (char *)(a.root_wrench + s);
       c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
       body(c2);
    }

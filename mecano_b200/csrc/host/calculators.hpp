@@ -225,5 +225,47 @@ class CompositeRigidBodyMassMatrixCalculator : public BatchedCalculatorBase
       else
          check(mecano_b200_crba_host(handle_, n, q.ld, q.data, massMatrixOut.data, layout));
    }
+
+   // ---- centroidal by-products (CompositeRigidBodyMassMatrixCalculator.java:380-440, :801-839)
+   enum class CentroidalMomentumFrame { World = MECANO_B200_FRAME_WORLD, CenterOfMass = MECANO_B200_FRAME_CENTER_OF_MASS };
+   void setCentroidalMomentumFrame(CentroidalMomentumFrame f) { frame_ = f; }
+   CentroidalMomentumFrame getCentroidalMomentumFrame() const { return frame_; }
+   // getMassMatrix() + getCentroidalMomentumMatrix() for N states: massMatrixOut (nDoFs*nDoFs) x N entry-major, cmmOut (6*nDoFs) x N
+   // (entry (r, j) at row r * nDoFs + j), comOut 4 x N (centre of mass in the root frame, total mass)
+   void getCentroidalMomentumMatrix(const MatrixView &q, const MatrixView &massMatrixOut, const MatrixView &cmmOut, const MatrixView &comOut,
+                                    Memory where = Memory::Device)
+   {
+      const int64_t n = q.cols, nv = input_.getNumberOfDoFs(), nq = input_.getConfigurationMatrixSize();
+      checkShape(q, nq, n, "q");
+      checkShape(massMatrixOut, nv * nv, n, "massMatrix");
+      checkShape(cmmOut, 6 * nv, n, "centroidalMomentumMatrix");
+      checkShape(comOut, 4, n, "centerOfMass");
+      if (massMatrixOut.ld != q.ld || cmmOut.ld != q.ld || comOut.ld != q.ld)
+         throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
+      if (where == Memory::Device)
+         check(mecano_b200_crba_centroidal(handle_, n, q.ld, q.data, massMatrixOut.data, cmmOut.data, comOut.data, (int)frame_, stream_));
+      else
+         check(mecano_b200_crba_centroidal_host(handle_, n, q.ld, q.data, massMatrixOut.data, cmmOut.data, comOut.data, (int)frame_));
+   }
+   // getCentroidalConvectiveTermMatrix() for N states: out 6 x N; com = the rows written by getCentroidalMomentumMatrix() for the
+   // same q (read in the centre-of-mass frame only)
+   void getCentroidalConvectiveTermMatrix(const MatrixView &q, const MatrixView &qd, const MatrixView &com, const MatrixView &out,
+                                          Memory where = Memory::Device)
+   {
+      const int64_t n = q.cols, nv = input_.getNumberOfDoFs(), nq = input_.getConfigurationMatrixSize();
+      checkShape(q, nq, n, "q");
+      checkShape(qd, nv, n, "qd");
+      checkShape(out, 6, n, "centroidalConvectiveTerm");
+      if (com.data) checkShape(com, 4, n, "centerOfMass");
+      if (qd.ld != q.ld || out.ld != q.ld || (com.data && com.ld != q.ld))
+         throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
+      if (where == Memory::Device)
+         check(mecano_b200_centroidal_convective_term(handle_, n, q.ld, q.data, qd.data, com.data, out.data, (int)frame_, stream_));
+      else
+         check(mecano_b200_centroidal_convective_term_host(handle_, n, q.ld, q.data, qd.data, com.data, out.data, (int)frame_));
+   }
+
+ private:
+   CentroidalMomentumFrame frame_ = CentroidalMomentumFrame::World;
 };
 } // namespace mecano

@@ -211,6 +211,12 @@ template <class T, class Ctx, class CP> MB_HD void rnea_store_joint_wrench(Ctx &
    c.st_wr(ext, 3, l.x); c.st_wr(ext, 4, l.y); c.st_wr(ext, 5, l.z);
 }
 
+template <class T, class Ctx> MB_HD void rnea_add_root_wrench(Ctx &c, const SvT<T> &f)
+{
+   c.add_rootw(0, f.a.x); c.add_rootw(1, f.a.y); c.add_rootw(2, f.a.z);
+   c.add_rootw(3, f.l.x); c.add_rootw(4, f.l.y); c.add_rootw(5, f.l.z);
+}
+
 // (a1) joint transform X_J(q) composed with the fixed offset, canonical frames (axis = +z):
 // revolute (MecanoFactories.java:231-260): R = R0 Rz(q), p = p0;  prismatic (PrismaticJointReadOnly.java:18-22): R = R0, p = p0 + q R0 e_z
 template <class T, bool REV, class CP> MB_HD XfT<T> joint_xf_1dof(const CP C, T s, T c)

@@ -12,6 +12,9 @@ struct KernelArgs
    double *out;                     // tau (RNEA), qdd (ABA), mass matrix (CRBA)
    double *body_acc, *joint_wrench; // RNEA by-products (nullable), rows [6 * w + c] like fext: spatial acceleration of each body in its
                                     // CoM frame, wrench of each joint in its frameAfterJoint
+   double *cmm, *com;               // CRBA by-products (nullable): centroidal momentum matrix rows [r * nv + col], r = 0..5, in the root frame;
+                                    // com rows 0..3 accumulate (mass * CoM, mass) over the root's children (zeroed before the launch)
+   double *root_wrench;             // RNEA by-product (nullable): rows 0..5 accumulate the wrench at the root in the root frame (zeroed before)
    const double *consts;            // device copy of the per-body constant records
    double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid
    long long ws_ld;

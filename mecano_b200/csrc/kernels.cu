@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
       else if constexpr (ALGO == MB_ABA)
          aba_state<double, Ctx, FEXT>(P, c2, a.grav);
       else
-         crba_state<double, Ctx>(P, c2);
+         crba_state<double, Ctx, FEXT>(P, c2);
    });
 }
 
@@ -81,6 +81,8 @@ KernelFn pick(int algo, bool fext, bool state_major, int cfg)
 {
    if (algo == MB_RNEA) return fext ? pick_cfg<MB_RNEA, true, false>(cfg) : pick_cfg<MB_RNEA, false, false>(cfg);
    if (algo == MB_ABA) return fext ? pick_cfg<MB_ABA, true, false>(cfg) : pick_cfg<MB_ABA, false, false>(cfg);
+   // CRBA: the "FEXT" instantiation is the one with by-products (centroidal momentum matrix, centre of mass), entry-major only
+   if (fext && !state_major) return pick_cfg<MB_CRBA, true, false>(cfg);
    return state_major ? pick_cfg<MB_CRBA, false, true>(cfg) : pick_cfg<MB_CRBA, false, false>(cfg);
 }
 
@@ -206,7 +208,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    if (a.n <= 0)
       return cudaSuccess;
    const bool state_major = algo == MB_CRBA && (a.flags & 1u);
-   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr, state_major, plan.size_class);
+   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, state_major, plan.size_class);
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so
    // does every kernel with a TMEM stack: a block then allocates its tensor memory, stages the constant records and

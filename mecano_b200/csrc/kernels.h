@@ -50,6 +50,18 @@ struct IntegrateArgs
 };
 cudaError_t launch_integrate_kernel(const IntegrateJoints &J, const IntegrateArgs &a, int sm_count, cudaStream_t stream);
 
+// centroidal by-products, last step (centroidal.cu)
+struct CentroidalArgs
+{
+   double *cols;      // [6 * ncols][ld], row r * ncols + j: column j of a 6 x ncols matrix, angular rows first (nullable if !shift)
+   double *com;       // [4][ld]: (mass * CoM, mass) in, (CoM, mass) out if normalize_com; (CoM, mass) in otherwise
+   long long n, ld;
+   int ncols;
+   int normalize_com; // divide the first three com rows by the fourth
+   int shift;         // move the moments of every column from the origin of the root frame to the CoM
+};
+cudaError_t launch_centroidal_finish(const CentroidalArgs &a, cudaStream_t stream);
+
 // roofline denominators
 cudaError_t measure_fp64_peak(double *tflops);
 cudaError_t measure_hbm_peak(double *gbs);

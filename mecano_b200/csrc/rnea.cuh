@@ -88,6 +88,14 @@ MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &f, RneaPipe<
    c.st_out(o.dof, REV ? f.a.z : f.l.z); // tau = S^T W (:952-958)
    if (FEXT && c.has_wr())
       rnea_store_joint_wrench<T>(c, ext, c.cst(o.body), f);
+   if (FEXT && c.has_rootw() && (o.flags & MB2_ROOT_PARENT))
+   {
+      // wrench the root body exerts on this subtree, re-expressed in the root frame and summed over the root's children
+      T s = pp.ls, cs = pp.lc;
+      if (!(o.flags & MB2_LEAF))
+         c.jp_ld2(o.slot, o.nslot, 0, s, cs);
+      rnea_add_root_wrench<T>(c, force_up_1dof<T, REV>(c.cst(o.body), s, cs, f));
+   }
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       T s = pp.ls, cs = pp.lc;
@@ -136,6 +144,8 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_ascend_6dof(Ctx &c, con
 {
    if (FEXT && c.has_wr())
       rnea_store_joint_wrench<T>(c, ext, c.cst(o.body), f);
+   if (FEXT && c.has_rootw() && (o.flags & MB2_ROOT_PARENT))
+      rnea_add_root_wrench<T>(c, force_to_parent(joint_xf_6dof<T>(c, c.cst(o.body), o.cfg), f));
    c.st_out(o.dof + 0, f.a.x); c.st_out(o.dof + 1, f.a.y); c.st_out(o.dof + 2, f.a.z);
    c.st_out(o.dof + 3, f.l.x); c.st_out(o.dof + 4, f.l.y); c.st_out(o.dof + 5, f.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))

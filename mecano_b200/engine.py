@@ -169,6 +169,36 @@ class Engine:
         check(lib.mecano_b200_crba(self._h, n, ld, pq, pm, layout, self._stream()), self._h)
         return M
 
+    def crba_centroidal(self, q, M, cmm, com, frame=_capi.FRAME_WORLD):
+        """M [nv*nv, n] entry-major, cmm [6*nv, n], com [4, n]; torch CUDA tensors or numpy arrays (host path)."""
+        n = q.shape[1]
+        host = isinstance(q, np.ndarray)
+        f = _host_ptr_ld if host else _dev_ptr_ld
+        pq, l0 = f(q, self.nq, n)
+        pm, l1 = f(M, self.nv * self.nv, n)
+        pa, l2 = f(cmm, 6 * self.nv, n)
+        pc, l3 = f(com, 4, n)
+        ld = _same_ld([l0, l1, l2, l3])
+        if host:
+            check(lib.mecano_b200_crba_centroidal_host(self._h, n, ld, pq, pm, pa, pc, int(frame)), self._h)
+        else:
+            check(lib.mecano_b200_crba_centroidal(self._h, n, ld, pq, pm, pa, pc, int(frame), self._stream()), self._h)
+
+    def centroidal_convective_term(self, q, qd, com, out, frame=_capi.FRAME_WORLD):
+        """out [6, n]; com [4, n] as written by crba_centroidal (None allowed for the world frame)."""
+        n = q.shape[1]
+        host = isinstance(q, np.ndarray)
+        f = _host_ptr_ld if host else _dev_ptr_ld
+        pq, l0 = f(q, self.nq, n)
+        pqd, l1 = f(qd, self.nv, n)
+        pc, l2 = f(com, 4, n)
+        po, l3 = f(out, 6, n)
+        ld = _same_ld([l0, l1, l2, l3])
+        if host:
+            check(lib.mecano_b200_centroidal_convective_term_host(self._h, n, ld, pq, pqd, pc, po, int(frame)), self._h)
+        else:
+            check(lib.mecano_b200_centroidal_convective_term(self._h, n, ld, pq, pqd, pc, po, int(frame), self._stream()), self._h)
+
     def integrate(self, dt, q, qd, qdd):
         """doubleIntegrateFromAcceleration on device matrices, in place."""
         n = q.shape[1]

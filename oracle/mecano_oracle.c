@@ -942,7 +942,10 @@ static void si_momentum(const si_t *s, const double *tw6, double *h6)
    memcpy(h6 + 3, lin, sizeof lin);
 }
 
-void mo_crba(const mo_tree *t, const double *q, double *M)
+/* frame: MO_FRAME_WORLD = the inertial (root) frame; MO_FRAME_COM = axes of the inertial frame, origin at the centre of mass of the
+ * whole system (what a CenterOfMassReferenceFrame handed to setCentroidalMomentumFrame() is, :380-387).
+ * cmm (nullable) [6][nv] row-major: getCentroidalMomentumMatrix() :801-809; com4 (nullable): CoM in the root frame, total mass. */
+static void crba_impl(const mo_tree *t, const double *q, double *M, int frame, double *cmm, double *com4)
 {
    frames_t *F = (frames_t *)malloc(sizeof(frames_t));
    si_t *comp = (si_t *)malloc(sizeof(si_t) * (size_t)t->nb);
@@ -975,6 +978,18 @@ void mo_crba(const mo_tree *t, const double *q, double *M)
       {
          joint_S_col(t, i, k, S + 6 * k);
          si_momentum(&comp[i], S + 6 * k, F2 + 6 * k); /* :663-667 */
+         if (cmm) /* computeCentroidalMomentumMatrix() :801-809: F2.changeFrame(centroidalMomentumFrame), here to the root frame first */
+         {
+            sv_t f;
+            memcpy(f.w, F2 + 6 * k, 3 * sizeof(double));
+            memcpy(f.v, F2 + 6 * k + 3, 3 * sizeof(double));
+            force_apply(&F->after[i], &f);
+            for (int r = 0; r < 3; r++)
+            {
+               cmm[r * nv + t->dof_off[i] + k] = f.w[r];
+               cmm[(3 + r) * nv + t->dof_off[i] + k] = f.v[r];
+            }
+         }
       }
       for (int a = 0; a < nd; a++) /* :700-707 */
          for (int b = 0; b < nd; b++)
@@ -1010,7 +1025,74 @@ void mo_crba(const mo_tree *t, const double *q, double *M)
          anc = t->parent[anc];
       }
    }
+   if (cmm || com4)
+   {
+      /* centre of mass of the system = CoM of the composite inertias of the root's children, in the root frame */
+      double c[3] = {0, 0, 0}, m = 0.0;
+      for (int i = 0; i < t->nb; i++)
+         if (t->parent[i] < 0)
+         {
+            si_t w = comp[i];
+            si_apply(&F->after[i], &w);
+            for (int k = 0; k < 3; k++) c[k] += w.m * w.c[k];
+            m += w.m;
+         }
+      for (int k = 0; k < 3; k++) c[k] /= m;
+      if (com4) { memcpy(com4, c, sizeof c); com4[3] = m; }
+      if (cmm && frame == MO_FRAME_COM)
+         for (int j = 0; j < nv; j++)
+         {
+            /* same axes, origin moved to c: n' = n - c x f */
+            double f[3] = {cmm[3 * nv + j], cmm[4 * nv + j], cmm[5 * nv + j]}, cxf[3];
+            v3_cross(c, f, cxf);
+            for (int r = 0; r < 3; r++) cmm[r * nv + j] -= cxf[r];
+         }
+   }
    free(F); free(comp); free(X);
+}
+
+void mo_crba(const mo_tree *t, const double *q, double *M)
+{
+   crba_impl(t, q, M, MO_FRAME_WORLD, NULL, NULL);
+}
+
+void mo_crba_centroidal(const mo_tree *t, const double *q, int frame, double *M, double *cmm, double *com4)
+{
+   crba_impl(t, q, M, frame, cmm, com4);
+}
+
+/* getCentroidalConvectiveTerm() (CompositeRigidBodyMassMatrixCalculator.java:811-839): the accelerations of pass one of inverse
+ * dynamics with zero joint accelerations and no gravity (coriolisBodyAcceleration, :826-829 = InverseDynamicsCalculator.java:880-892),
+ * each body's net wrench (:831) re-expressed in the centroidal frame and summed (:832-833). */
+void mo_centroidal_convective_term(const mo_tree *t, const double *q, const double *qd, int frame, double *out6)
+{
+   const double g0[3] = {0.0, 0.0, 0.0};
+   sv_t *acc = (sv_t *)malloc(sizeof(sv_t) * (size_t)t->nb);
+   frames_t *F = (frames_t *)malloc(sizeof(frames_t));
+   double *zero = (double *)calloc((size_t)t->nv, sizeof(double));
+   sv_t sum;
+   memset(&sum, 0, sizeof sum);
+   rnea_impl(t, g0, q, qd, zero, NULL, MO_NO_ACCELERATIONS, NULL, (double *)acc, NULL);
+   update_frames(t, q, qd, F);
+   for (int i = 0; i < t->nb; i++)
+   {
+      sv_t W;
+      dynamic_wrench(t->J + 9 * i, t->mass[i], &acc[i], &F->tw_com[i], &W);
+      force_apply(&F->com[i], &W);
+      sv_add(&sum, &W);
+   }
+   if (frame == MO_FRAME_COM)
+   {
+      double com4[4], cxf[3];
+      double *M = (double *)malloc(sizeof(double) * (size_t)t->nv * (size_t)t->nv);
+      crba_impl(t, q, M, MO_FRAME_WORLD, NULL, com4);
+      v3_cross(com4, sum.v, cxf);
+      for (int r = 0; r < 3; r++) sum.w[r] -= cxf[r];
+      free(M);
+   }
+   memcpy(out6, sum.w, 3 * sizeof(double));
+   memcpy(out6 + 3, sum.v, 3 * sizeof(double));
+   free(acc); free(F); free(zero);
 }
 
 /* ================================================================== batched drivers (CPU baseline: one

@@ -71,6 +71,15 @@ void mo_rnea_body_accelerations(const mo_tree *t, const double *gravity3, const 
 void mo_rnea_full(const mo_tree *t, const double *gravity3, const double *q, const double *qd, const double *qdd, const double *fext,
                   int flags, double *tau, double *body_acc, double *joint_wrench);
 
+/* CRBA by-products (CompositeRigidBodyMassMatrixCalculator.java:380-440, :801-839).  frame: the centroidal momentum frame.
+ * M [nv][nv]; cmm (nullable) [6][nv] row-major, angular rows first: getCentroidalMomentumMatrix(); com4 (nullable): centre of mass of
+ * the system in the root frame and its total mass. */
+#define MO_FRAME_WORLD 0 /* the inertial (root) frame */
+#define MO_FRAME_COM 1   /* axes of the inertial frame, origin at the centre of mass (CenterOfMassReferenceFrame) */
+void mo_crba_centroidal(const mo_tree *t, const double *q, int frame, double *M, double *cmm, double *com4);
+/* getCentroidalConvectiveTerm(): d/dt(cmm) qd, [6] angular first, in the centroidal frame */
+void mo_centroidal_convective_term(const mo_tree *t, const double *q, const double *qd, int frame, double *out6);
+
 /* ABA with per-joint source modes (ForwardDynamicsCalculator.java:45-57, :400-444, :508-520): accel_source [nb], non-zero = the
  * joint's acceleration is an input (qdd_in [nv], its rows only) and its effort an output (pass four :1315-1363).  qdd [nv] holds all
  * joint accelerations, tau_out (nullable, [nv]) all joint efforts as getJointTauMatrix() :566-590 returns them. */

@@ -63,6 +63,11 @@ template <class T> struct CpuCtx
    void st_out(int r, T v) { out[r * ld + s] = (double)v; }
    double *acc_out = nullptr, *wr_out = nullptr;
    const double *x2 = nullptr;
+   double *cmm = nullptr, *com = nullptr, *rootw = nullptr;
+   bool has_rootw() const { return rootw != nullptr; }
+   void st_cmm(int row, T v) { cmm[(long)row * ld + s] = (double)v; }
+   void add_com(int r, T v) { com[r * ld + s] += (double)v; }
+   void add_rootw(int r, T v) { rootw[r * ld + s] += (double)v; }
    T ld_x2(int r) const { return (T)x2[r * ld + s]; }
    bool has_fext() const { return fext != nullptr; }
    bool has_acc() const { return acc_out != nullptr; }
@@ -125,7 +130,7 @@ template <class T> struct CpuCtx
 template <class T>
 int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *x,
         const double *fext, double *out, unsigned flags, char *err, int errlen, double *acc_out = nullptr, double *wr_out = nullptr,
-        const int32_t *accel_source = nullptr, const double *x2 = nullptr)
+        const int32_t *accel_source = nullptr, const double *x2 = nullptr, double *cmm = nullptr, double *com = nullptr, double *rootw = nullptr)
 {
    mb::FlatTree ft;
    std::string e;
@@ -160,10 +165,11 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       c.acc_out = acc_out;
       c.wr_out = wr_out;
       c.x2 = x2;
+      c.cmm = cmm; c.com = com; c.rootw = rootw;
       c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
-         if (fext || acc_out || wr_out) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav);
+         if (fext || acc_out || wr_out || rootw) mb::rnea_state<T, CpuCtx<T>, true>(P, c, grav);
          else mb::rnea_state<T, CpuCtx<T>, false>(P, c, grav);
       }
       else if (algo == MB_ABA)
@@ -171,6 +177,8 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
          if (fext || n_locked > 0) mb::aba_state<T, CpuCtx<T>, true>(P, c, grav);
          else mb::aba_state<T, CpuCtx<T>, false>(P, c, grav);
       }
+      else if (cmm)
+         mb::crba_state<T, CpuCtx<T>, true>(P, c);
       else
          mb::crba_state<T, CpuCtx<T>>(P, c);
    }
@@ -197,6 +205,26 @@ extern "C" int emu_aba_sources(const mecano_b200_tree_desc *d, const double *g, 
                                const double *qdd_in, const double *fext, const int32_t *accel_source, double *qdd, char *err, int errlen)
 {
    return run<double>(MB_ABA, d, g, n, ld, q, qd, tau, fext, qdd, 0u, err, errlen, nullptr, nullptr, accel_source, qdd_in);
+}
+
+// CRBA with by-products: M [nv * nv][ld], centroidal momentum matrix [6 * nv][ld] in the root frame, com [4][ld] = (mass * CoM, mass)
+// accumulated over the root's children (zeroed here, as the C ABI does before the launch)
+extern "C" int emu_crba_centroidal(const mecano_b200_tree_desc *d, long n, long ld, const double *q, double *M, double *cmm, double *com, char *err,
+                                   int errlen)
+{
+   const double g[3] = {0, 0, 0};
+   std::fill(com, com + 4 * ld, 0.0);
+   return run<double>(MB_CRBA, d, g, n, ld, q, nullptr, nullptr, nullptr, M, 0u, err, errlen, nullptr, nullptr, nullptr, nullptr, cmm, com, nullptr);
+}
+
+// RNEA with zero joint accelerations and no gravity, its wrench at the root summed into rootw [6][ld] (root frame): the centroidal
+// convective term about the origin of the root frame
+extern "C" int emu_rnea_root_wrench(const mecano_b200_tree_desc *d, long n, long ld, const double *q, const double *qd, double *tau, double *rootw,
+                                    char *err, int errlen)
+{
+   const double g[3] = {0, 0, 0};
+   std::fill(rootw, rootw + 6 * ld, 0.0);
+   return run<double>(MB_RNEA, d, g, n, ld, q, qd, qd, nullptr, tau, 2u, err, errlen, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rootw);
 }
 
 // Algorithmic operation counts of one state: out5 = {add, mul, div, sincos, flops = add + mul + div}

@@ -160,6 +160,27 @@ class Emu:
         nv = self.tree.nv
         return self._run(2, q, None, None, None, np.full((nv * nv, n), np.nan)).reshape(nv, nv, n)
 
+    def crba_centroidal(self, q):
+        """(M [nv, nv, n], centroidal momentum matrix [6, nv, n] in the root frame, (mass * CoM, mass) [4, n])."""
+        n = q.shape[1]
+        nv = self.tree.nv
+        M, cmm, com = np.full((nv * nv, n), np.nan), np.full((6 * nv, n), np.nan), np.full((4, n), np.nan)
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_crba_centroidal(ctypes.byref(self.desc), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(M), _d(cmm), _d(com), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_crba_centroidal rc=%d: %s" % (rc, err.value.decode()))
+        return M.reshape(nv, nv, n), cmm.reshape(6, nv, n), com
+
+    def rnea_root_wrench(self, q, qd):
+        """Wrench at the root, in the root frame, of inverse dynamics with zero joint accelerations and no gravity: [6, n]."""
+        n = q.shape[1]
+        tau, rw = np.full((self.tree.nv, n), np.nan), np.full((6, n), np.nan)
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_rnea_root_wrench(ctypes.byref(self.desc), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(qd), _d(tau), _d(rw), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_rnea_root_wrench rc=%d: %s" % (rc, err.value.decode()))
+        return rw
+
     def count_flops(self, algo, q, qd, x):
         """Algorithmic operation counts of one state (counting-scalar instantiation of the kernel routines)."""
         out = (ctypes.c_long * 5)()

@@ -138,6 +138,33 @@ class Model:
                 f[p] = f[p] + X[i].T @ f[i]
         return tau
 
+    def centroidal(self, q, qd, qdd):
+        """Momentum of the whole system and its rate (no gravity) about the origin of the root frame, in root coordinates, plus
+        the centre of mass and total mass: (h [6], hdot [6], com [3], mass), angular parts first.  Independent of the
+        calculators: plain sums over the bodies."""
+        t = self.t
+        nb = t.nb
+        X0, v, a = [None] * nb, [None] * nb, [None] * nb
+        h, hdot, mc, mass = np.zeros(6), np.zeros(6), np.zeros(3), 0.0
+        for i in range(nb):
+            p = t.parent[i]
+            d = t.dof_off[i]
+            nd = self._nd(i)
+            X = self.joint_X(i, q)
+            vJ = self.S[i] @ qd[d:d + nd]
+            v[i] = X @ (v[p] if p >= 0 else np.zeros(6)) + vJ
+            a[i] = X @ (a[p] if p >= 0 else np.zeros(6)) + self.S[i] @ qdd[d:d + nd] + crm(v[i]) @ vJ
+            X0[i] = X @ (X0[p] if p >= 0 else np.eye(6))  # root coordinates -> body coordinates (motion)
+            h += X0[i].T @ (self.I[i] @ v[i])
+            hdot += X0[i].T @ (self.I[i] @ a[i] + crf(v[i]) @ self.I[i] @ v[i])
+            # position of the body's CoM in the root frame: E = X0[:3, :3] (root -> body), -E r~ = X0[3:, :3]
+            E = X0[i][:3, :3]
+            rx = -E.T @ X0[i][3:, :3]
+            r = np.array([rx[2, 1], rx[0, 2], rx[1, 0]])
+            mc += t.mass[i] * (r + E.T @ np.asarray(t.com_p[i]))
+            mass += t.mass[i]
+        return h, hdot, mc / mass, mass
+
     def crba(self, q):
         t = self.t
         nb = t.nb

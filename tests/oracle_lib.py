@@ -100,6 +100,20 @@ class Oracle:
         self.lib.mo_crba(ctypes.byref(self.c), _d(q), _d(M))
         return M
 
+    def crba_centroidal(self, q, frame=0):
+        """(M [nv, nv], centroidal momentum matrix [6, nv], CoM [3], total mass); frame 0 = root frame, 1 = CoM frame."""
+        q = self._f64(q)
+        nv = self.t.nv
+        M, cmm, com4 = np.zeros((nv, nv)), np.zeros((6, nv)), np.zeros(4)
+        self.lib.mo_crba_centroidal(ctypes.byref(self.c), _d(q), ctypes.c_int(frame), _d(M), _d(cmm), _d(com4))
+        return M, cmm, com4[:3].copy(), float(com4[3])
+
+    def centroidal_convective_term(self, q, qd, frame=0):
+        q, qd = map(self._f64, (q, qd))
+        out = np.zeros(6)
+        self.lib.mo_centroidal_convective_term(ctypes.byref(self.c), _d(q), _d(qd), ctypes.c_int(frame), _d(out))
+        return out
+
     def integrate(self, dt, q, qd, qdd):
         """doubleIntegrateFromAcceleration on one state; returns the updated (q, qd, qdd) copies."""
         q, qd, qdd = (np.array(x, dtype=np.float64, copy=True) for x in (q, qd, qdd))

@@ -94,6 +94,26 @@ def test_emulated_aba_source_modes_match_oracle(idx):
     assert np.array_equal(e.aba_sources(q, qd, tau, qdd_in, np.zeros(t.nb, np.int32)), e.aba(q, qd, tau))
 
 
+@pytest.mark.parametrize("idx", range(12))
+def test_emulated_centroidal_byproducts_match_oracle(idx):
+    """getCentroidalMomentumMatrix() / getCentroidalConvectiveTerm() (CompositeRigidBodyMassMatrixCalculator.java:801-839) in the
+    root frame, as the kernels leave them before the centre-of-mass shift."""
+    rng = np.random.default_rng(1200 + idx)
+    t = trees(rng)[idx]
+    o, e = ol.Oracle(t), el.Emu(t)
+    n = 3
+    q, qd, _, _ = td.random_states(rng, t, n)
+    M, cmm, com = e.crba_centroidal(q)
+    rw = e.rnea_root_wrench(q, qd)
+    assert not (np.isnan(M).any() or np.isnan(cmm).any() or np.isnan(com).any() or np.isnan(rw).any())
+    assert np.array_equal(M, e.crba(q)), "the by-products must not change the mass matrix"
+    for s in range(n):
+        Mo, Ao, co, mo = o.crba_centroidal(q[:, s], 0)
+        assert rel(cmm[:, :, s], Ao) < TOL
+        assert rel(com[:3, s] / com[3, s], co) < TOL and abs(com[3, s] - mo) < TOL * mo
+        assert rel(rw[:, s], o.centroidal_convective_term(q[:, s], qd[:, s], 0)) < TOL
+
+
 def test_table_order_does_not_matter():
     """The C-ABI accepts any topological listing of the bodies (level order from the Java host, or DFS)."""
     rng = np.random.default_rng(9)

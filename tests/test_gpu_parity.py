@@ -481,3 +481,72 @@ def test_forward_dynamics_joint_source_modes(torch_dev, idx):
     plain.setGravitationalAcceleration(g)
     assert torch.equal(fdyn.compute(tq, tqd, tau), plain.compute(tq, tqd, tau))
     assert fdyn.getJointTauMatrix() is tau
+
+
+@pytest.mark.parametrize("idx", [0, 3, 5, 6, 8, 9])
+def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
+    """getCentroidalMomentumMatrix() / getCentroidalConvectiveTerm() of the mass-matrix calculator
+    (CompositeRigidBodyMassMatrixCalculator.java:380-440, :801-839) for N states, in the world frame and in the centre-of-mass
+    frame: against the oracle state by state, and on the whole batch through the facts the reference tests
+    (CompositeRigidBodyMassMatrixCalculatorTest.java:62-82): A qd = momentum, A qdd + convective term = momentum rate = the
+    wrench at the root of inverse dynamics without gravity."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(6000 + idx)
+    o = ol.Oracle(t)
+    n = 1100
+    nv = t.nv
+    q, qd, qdd, _ = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    tq, tqd = torch.from_numpy(q).to(dev), torch.from_numpy(qd).to(dev)
+    plain = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant("thread")  # the by-products run thread-per-state
+    M_plain = plain.getMassMatrix(tq, torch.empty((nv * nv, n), dtype=torch.float64, device=dev)).cpu().numpy()
+    for frame_name, frame in (("worldFrame", 0), ("centerOfMassFrame", 1)):
+        calc = mb.CompositeRigidBodyMassMatrixCalculator(s, frame_name)
+        assert calc.getCentroidalMomentumFrame() == frame_name
+        A = calc.getCentroidalMomentumMatrix(tq).cpu().numpy().reshape(6, nv, n)
+        assert np.array_equal(calc.getMassMatrix().cpu().numpy(), M_plain), "the by-products must not change the mass matrix"
+        com = calc.getCenterOfMass().cpu().numpy()
+        b = calc.getCentroidalConvectiveTermMatrix(tq, tqd).cpu().numpy()
+        assert not (np.isnan(A).any() or np.isnan(com).any() or np.isnan(b).any()), name
+        for k in range(0, n, 53):
+            _, Ao, co, mo = o.crba_centroidal(q[:, k], frame)
+            assert rel(A[:, :, k], Ao) < TOL, name
+            assert rel(com[:3, k], co) < TOL and abs(com[3, k] - mo) < TOL * mo, name
+            assert rel(b[:, k], o.centroidal_convective_term(q[:, k], qd[:, k], frame)) < TOL, name
+        # host path: same kernels behind plain staging
+        hc = mb.CompositeRigidBodyMassMatrixCalculator(s, frame_name)
+        Ah = hc.getCentroidalMomentumMatrix(q).reshape(6, nv, n)
+        bh = hc.getCentroidalConvectiveTermMatrix(q, qd)
+        assert rel(Ah, A) == 0.0 and rel(bh, b) == 0.0 and rel(hc.getMassMatrix(), M_plain) == 0.0, name
+    # batch-wide invariant in the world frame: A qdd + b = sum over the root's children of their joint wrench, in the world frame,
+    # which for a single floating root joint is the pelvis wrench rotated / shifted by the pelvis pose; checked through linear
+    # momentum only (frame-origin independent): total force = mass * CoM acceleration = rows 3..5
+    calc = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    A = calc.getCentroidalMomentumMatrix(tq).cpu().numpy().reshape(6, nv, n)
+    b = calc.getCentroidalConvectiveTermMatrix(tq, tqd).cpu().numpy()
+    hdot = np.einsum("rjs,js->rs", A, qdd) + b
+    ident = mb.InverseDynamicsCalculator(s).setComputeByProducts(bodyAccelerations=False)
+    ident.compute(tq, tqd, torch.from_numpy(qdd).to(dev))  # zero gravity (the calculator's default)
+    wr = ident.getComputedJointWrenchMatrix().cpu().numpy().reshape(t.nb, 6, n)
+    for k in range(0, n, 211):
+        total = np.zeros(3)
+        for body in range(t.nb):
+            if t.parent[body] < 0:
+                # rotation frameAfterJoint -> world of a child of the root body
+                qi = q[t.cfg_off[body]:, k]
+                if t.jtype[body] == td.SIXDOF:
+                    x, y, z, w = qi[:4] / np.linalg.norm(qi[:4])
+                    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+                elif t.jtype[body] == td.REVOLUTE:
+                    u, a = t.axis[body] / np.linalg.norm(t.axis[body]), qi[0]
+                    K = np.array([[0, -u[2], u[1]], [u[2], 0, -u[0]], [-u[1], u[0], 0]])
+                    R = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+                else:
+                    R = np.eye(3)
+                total += t.off_R[body] @ R @ wr[body, 3:, k]
+        assert np.max(np.abs(hdot[3:, k] - total)) < 1e-9 * max(1.0, np.max(np.abs(total))), name

@@ -108,6 +108,34 @@ def test_reference_invariant_mixed_source_modes(idx):
         assert np.array_equal(free_qdd, o.aba(q[:, s], qd_s, tau, fext)) and np.array_equal(free_tau, tau)
 
 
+@pytest.mark.parametrize("idx", range(10))
+def test_centroidal_momentum_matrix_and_convective_term(idx):
+    """CompositeRigidBodyMassMatrixCalculatorTest.java:62-82 compares getCentroidalMomentumMatrix() / getCentroidalConvectiveTerm()
+    with CentroidalMomentumRateCalculator at 1e-10 (EPSILON); the same two facts against plain sums over the bodies
+    (featherstone_np.Model.centroidal): A qd = momentum, A qdd + convective term = momentum rate, in the root frame and in the
+    centre-of-mass frame."""
+    rng = np.random.default_rng(1100 + idx)
+    name, t = cases(rng)[idx]
+    o, m = ol.Oracle(t), fs.Model(t)
+    q, qd, qdd, _ = td.random_states(rng, t, 4)
+    for s in range(4):
+        h, hdot, com, mass = m.centroidal(q[:, s], qd[:, s], qdd[:, s])
+        M, A, c, mtot = o.crba_centroidal(q[:, s], 0)
+        assert np.array_equal(M, o.crba(q[:, s]))
+        assert abs(mtot - mass) < 1e-12 * mass and np.max(np.abs(c - com)) < 1e-12, name
+        b = o.centroidal_convective_term(q[:, s], qd[:, s], 0)
+        assert err(A @ qd[:, s], h) < 1e-10, name
+        assert err(A @ qdd[:, s] + b, hdot) < 1e-10, name
+        # centre-of-mass frame: same axes, moments taken about the CoM
+        shift = lambda w: np.concatenate([w[:3] - np.cross(com, w[3:]), w[3:]])
+        _, Ac, _, _ = o.crba_centroidal(q[:, s], 1)
+        bc = o.centroidal_convective_term(q[:, s], qd[:, s], 1)
+        assert err(Ac @ qd[:, s], shift(h)) < 1e-10, name
+        assert err(Ac @ qdd[:, s] + bc, shift(hdot)) < 1e-10, name
+        # linear momentum = mass * CoM velocity: the linear rows of A in the CoM frame do not depend on the frame origin
+        assert np.array_equal(Ac[3:], A[3:])
+
+
 def test_flags_match_zeroed_inputs():
     """setConsiderCoriolisAndCentrifugalForces(false) == zero velocities; setConsiderJointAccelerations(false) == zero
     accelerations (InverseDynamicsCalculator.java:882-915)."""
