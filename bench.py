@@ -50,6 +50,7 @@ def parse_args():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-extras", action="store_true", help="skip the kernels timed outside the step (ncu launch lists of the step alone)")
     return p.parse_args()
 
 
@@ -333,7 +334,7 @@ def main():
         kernels[name] = entry
     # ---- next-row kernels, timed outside the step: the state integrator that follows ABA in a roll-out
     extras = {}
-    if rank == 0:
+    if rank == 0 and not args.no_extras:
         integ = mb.MultiBodySystemStateIntegrator(system, 1.0e-3, engine=fdyn._engine)
         iq, iqd, iqdd = q.clone(), qd.clone(), qdd_out.clone()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -371,6 +372,46 @@ def main():
                                        "what": "CompositeRigidBodyMassMatrixCalculator.getMassMatrix(q) into the calculator's own matrix: the "
                                                "%d structurally zero entries are written once, not per call (MECANO_B200_CRBA_ZEROS_PRESENT)" % (nv * nv - nnz)}
         del owned
+
+        def timed(fn):
+            for _ in range(3):
+                fn()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        def hbm_entry(ms, nbytes, what):
+            return {"ms": ms, "states_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_state": nbytes,
+                    "achieved_gbs": nbytes * n / (ms * 1e-3) / 1e9, "hbm_frac": nbytes * n / (ms * 1e-3) / 1e9 / hbm_peak, "what": what}
+
+        # RNEA with its by-products (getBodyAcceleration / getComputedJointWrench for every body): 12 nb more rows written
+        full = mb.InverseDynamicsCalculator(system, device=local_rank).setComputeByProducts()
+        full.setGravitationalAcceleration(*GRAVITY)
+        extras["rnea_byproducts"] = hbm_entry(timed(lambda: full.compute(q, qd, qdd, tau)), 8.0 * (nq + 3 * nv + 12 * nb),
+                                              "InverseDynamicsCalculator.compute + body accelerations + joint wrenches (mecano_b200_rnea_full)")
+        del full
+        # forward dynamics with every second one-DoF joint an ACCELERATION_SOURCE, efforts of those joints included (pass four)
+        locked = [j for i, j in enumerate(system.getJointsToConsider()) if j.getDegreesOfFreedom() == 1 and i % 2 == 0]
+        mixed = mb.ForwardDynamicsCalculator(system, device=local_rank)
+        mixed.setGravitationalAcceleration(*GRAVITY)
+        mixed.setJointSourceModes(lambda j: mb.JointSourceMode.ACCELERATION_SOURCE if j in locked else None)
+        extras["aba_source_modes"] = hbm_entry(timed(lambda: mixed.compute(q, qd, tau_in, qdd_out, jointAccelerationInput=qdd)),
+                                               8.0 * (2 * nq + 8 * nv),
+                                               "ForwardDynamicsCalculator.compute(tau, qdd) with %d of %d joints in ACCELERATION_SOURCE mode + getJointTauMatrix "
+                                               "(ABA launch + RNEA launch + row copies; mecano_b200_aba_sources)" % (len(locked), nb))
+        del mixed
+        # mass matrix + centroidal momentum matrix + centre of mass, then the convective term, in the centre-of-mass frame
+        cen = mb.CompositeRigidBodyMassMatrixCalculator(system, "centerOfMassFrame", device=local_rank)
+        extras["crba_centroidal"] = hbm_entry(timed(lambda: cen.getCentroidalMomentumMatrix(q)), 8.0 * (nq + nv * nv + 6 * nv + 4),
+                                              "getMassMatrix + getCentroidalMomentumMatrix + centre of mass (mecano_b200_crba_centroidal; the "
+                                              "centre-of-mass shift re-reads and re-writes 9 nv rows, not counted)")
+        extras["centroidal_convective_term"] = hbm_entry(timed(lambda: cen.getCentroidalConvectiveTermMatrix(q, qd)), 8.0 * (nq + nv + 4 + 6),
+                                                         "getCentroidalConvectiveTermMatrix (mecano_b200_centroidal_convective_term: one RNEA launch "
+                                                         "whose joint efforts go to a scratch buffer, + the shift)")
+        del cen
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine
     # balance (FP64 pipe), CRBA below it (HBM, write-dominated).  MEASURED_PEAKS.json has no FP64 figure, so the FP64

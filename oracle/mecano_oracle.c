@@ -1095,6 +1095,198 @@ void mo_centroidal_convective_term(const mo_tree *t, const double *q, const doub
    free(acc); free(F); free(zero);
 }
 
+/* ================================================================== Coriolis and centrifugal matrix
+ * CompositeRigidBodyMassMatrixCalculator with setEnableCoriolisMatrixCalculation(true) (:278-281, getCoriolisMatrix :358-366):
+ * computeMassMatrix() :588-799 with the factorized body inertia of M/algorithms/FactorizedBodyInertia.java (:149-175 construction
+ * from a spatial inertia and the body twist, :295-312 applyTransform, :201-247 transform / addTransform / transposeTransform). */
+
+typedef struct { double A[9], L[9], TR[9], BL[9]; } fbi_t; /* angular, linear, top-right, bottom-left 3x3 blocks */
+
+static void m3_tilde(const double *p, double *T)
+{
+   T[0] = 0; T[1] = -p[2]; T[2] = p[1];
+   T[3] = p[2]; T[4] = 0; T[5] = -p[0];
+   T[6] = -p[1]; T[7] = p[0]; T[8] = 0;
+}
+
+/* FactorizedBodyInertia.tildeTimesTilde :379-391 */
+static void m3_tilde_times_tilde(const double *p1, const double *p2, double *C)
+{
+   C[0] = -p1[2] * p2[2] - p1[1] * p2[1]; C[1] = p1[1] * p2[0]; C[2] = p1[2] * p2[0];
+   C[3] = p1[0] * p2[1]; C[4] = -p1[2] * p2[2] - p1[0] * p2[0]; C[5] = p1[2] * p2[1];
+   C[6] = p1[0] * p2[2]; C[7] = p1[1] * p2[2]; C[8] = -p1[1] * p2[1] - p1[0] * p2[0];
+}
+
+/* setIncludingFrame(spatialInertia, bodyTwist) :149-175 */
+static void fbi_from_si(const si_t *s, const sv_t *tw, fbi_t *b)
+{
+   double T[9], WJ[9];
+   m3_tilde_times_tilde(tw->v, s->c, b->A); /* w x J - m v x c x */
+   for (int k = 0; k < 9; k++) b->A[k] *= -s->m;
+   m3_tilde(tw->w, T);
+   m3_mul(T, s->I, WJ);
+   for (int k = 0; k < 9; k++) b->A[k] += WJ[k];
+   m3_tilde_times_tilde(tw->w, s->c, b->BL); /* -m w x c x */
+   for (int k = 0; k < 9; k++) b->BL[k] *= -s->m;
+   m3_tilde(tw->v, b->TR); /* m v x + m w x c x */
+   for (int k = 0; k < 9; k++) b->TR[k] = b->TR[k] * s->m - b->BL[k];
+   m3_tilde(tw->w, b->L); /* m w x */
+   for (int k = 0; k < 9; k++) b->L[k] *= s->m;
+}
+
+/* applyTransform(RigidBodyTransform) :295-312 */
+static void fbi_apply(const xf_t *x, fbi_t *b)
+{
+   double T[9], P[9];
+   m3_rot_congruence(x->R, b->A);
+   m3_rot_congruence(x->R, b->L);
+   m3_rot_congruence(x->R, b->TR);
+   m3_rot_congruence(x->R, b->BL);
+   m3_tilde(x->t, T);
+   m3_mul(T, b->L, P);  for (int k = 0; k < 9; k++) b->TR[k] += P[k]; /* addTildeTimesMatrix(t, linear, topRight) */
+   m3_mul(T, b->BL, P); for (int k = 0; k < 9; k++) b->A[k] += P[k];  /* addTildeTimesMatrix(t, bottomLeft, angular) */
+   m3_mul(b->TR, T, P); for (int k = 0; k < 9; k++) b->A[k] -= P[k];  /* subMatrixTimesTilde(topRight, t, angular) */
+   m3_mul(b->L, T, P);  for (int k = 0; k < 9; k++) b->BL[k] -= P[k]; /* subMatrixTimesTilde(linear, t, bottomLeft) */
+}
+
+static void fbi_mulv(const fbi_t *b, const double *x6, double *y6, int add) /* transform / addTransform :201-228 */
+{
+   double a[3], c[3];
+   m3_mulv(b->A, x6, a);      m3_mulv(b->TR, x6 + 3, c);
+   for (int k = 0; k < 3; k++) y6[k] = (add ? y6[k] : 0.0) + a[k] + c[k];
+   m3_mulv(b->BL, x6, a);     m3_mulv(b->L, x6 + 3, c);
+   for (int k = 0; k < 3; k++) y6[3 + k] = (add ? y6[3 + k] : 0.0) + a[k] + c[k];
+}
+
+static void fbi_tmulv(const fbi_t *b, const double *x6, double *y6) /* transposeTransform :230-247 */
+{
+   double a[3], c[3];
+   m3_tmulv(b->A, x6, a);     m3_tmulv(b->BL, x6 + 3, c);
+   for (int k = 0; k < 3; k++) y6[k] = a[k] + c[k];
+   m3_tmulv(b->TR, x6, a);    m3_tmulv(b->L, x6 + 3, c);
+   for (int k = 0; k < 3; k++) y6[3 + k] = a[k] + c[k];
+}
+
+static double dot6(const double *a, const double *b)
+{
+   return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+}
+
+static void force6_apply(const xf_t *x, double *f6)
+{
+   sv_t f;
+   memcpy(f.w, f6, 3 * sizeof(double));
+   memcpy(f.v, f6 + 3, 3 * sizeof(double));
+   force_apply(x, &f);
+   memcpy(f6, f.w, 3 * sizeof(double));
+   memcpy(f6 + 3, f.v, 3 * sizeof(double));
+}
+
+void mo_coriolis(const mo_tree *t, const double *q, const double *qd, double *M, double *C)
+{
+   frames_t *F = (frames_t *)malloc(sizeof(frames_t));
+   si_t *comp = (si_t *)malloc(sizeof(si_t) * (size_t)t->nb);
+   fbi_t *fcomp = (fbi_t *)malloc(sizeof(fbi_t) * (size_t)t->nb);
+   xf_t *X = (xf_t *)malloc(sizeof(xf_t) * (size_t)t->nb);
+   double (*Sd)[36] = (double (*)[36])malloc(sizeof(double[36]) * (size_t)t->nb); /* unitTwistDots, per body */
+   int nv = t->nv;
+
+   update_frames(t, q, qd, F);
+   memset(C, 0, sizeof(double) * (size_t)nv * (size_t)nv); /* :298-299 */
+   if (M) memset(M, 0, sizeof(double) * (size_t)nv * (size_t)nv);
+
+   for (int i = 0; i < t->nb; i++)
+   {
+      if (t->parent[i] >= 0)
+         xf_rel(&F->after[i], &F->after[t->parent[i]], &X[i]);
+      else
+         xf_identity(&X[i]);
+      /* unitTwistDots :604-630 (constant motion subspace): [w x s_w ; v x s_w + w x s_v] with the twist of frameAfterJoint */
+      const sv_t *tw = &F->tw_after[i];
+      for (int k = 0; k < joint_ndof(t, i); k++)
+      {
+         double s[6], *d = Sd[i] + 6 * k;
+         joint_S_col(t, i, k, s);
+         v3_cross(tw->w, s, d);
+         v3_cross(tw->v, s, d + 3);
+         v3_add_cross(tw->w, s + 3, d + 3);
+      }
+   }
+
+   for (int i = t->nb - 1; i >= 0; i--)
+   {
+      si_t body;
+      body_inertia_at_after(t, i, F, &body); /* :648-651 */
+      comp[i] = body;
+      fbi_from_si(&body, &F->tw_after[i], &fcomp[i]); /* :671-673 */
+      for (int c = i + 1; c < t->nb; c++)
+         if (t->parent[c] == i)
+         {
+            si_t ch = comp[c]; /* :653-661 */
+            fbi_t fch = fcomp[c]; /* :675-683 */
+            si_apply(&X[c], &ch);
+            si_add(&comp[i], &ch);
+            fbi_apply(&X[c], &fch);
+            for (int k = 0; k < 9; k++)
+            {
+               fcomp[i].A[k] += fch.A[k]; fcomp[i].L[k] += fch.L[k]; fcomp[i].TR[k] += fch.TR[k]; fcomp[i].BL[k] += fch.BL[k];
+            }
+         }
+
+      int nd = joint_ndof(t, i), di = t->dof_off[i];
+      double S[36], F1[36], F2[36], F3[36];
+      for (int k = 0; k < nd; k++)
+      {
+         joint_S_col(t, i, k, S + 6 * k);
+         si_momentum(&comp[i], S + 6 * k, F2 + 6 * k);      /* :663-667 */
+         si_momentum(&comp[i], Sd[i] + 6 * k, F1 + 6 * k);  /* :687-688 */
+         fbi_mulv(&fcomp[i], S + 6 * k, F1 + 6 * k, 1);     /* :689 */
+         fbi_tmulv(&fcomp[i], S + 6 * k, F3 + 6 * k);       /* :692 */
+      }
+      for (int a = 0; a < nd; a++) /* :700-725, in the order of the Java loops (later writes win) */
+         for (int b = 0; b < nd; b++)
+         {
+            if (M)
+            {
+               double m = dot6(S + 6 * a, F2 + 6 * b);
+               M[(di + a) * nv + di + b] = m;
+               M[(di + b) * nv + di + a] = m;
+            }
+            C[(di + a) * nv + di + b] = dot6(S + 6 * a, F1 + 6 * b);
+            if (a != b)
+               C[(di + b) * nv + di + a] = dot6(Sd[i] + 6 * a, F2 + 6 * b) + dot6(S + 6 * a, F3 + 6 * b);
+         }
+      /* :730-766 */
+      int prev = i, anc = t->parent[i];
+      while (anc >= 0)
+      {
+         int nda = joint_ndof(t, anc), da = t->dof_off[anc];
+         for (int j = 0; j < nd; j++)
+         {
+            force6_apply(&X[prev], F1 + 6 * j);
+            force6_apply(&X[prev], F2 + 6 * j);
+            force6_apply(&X[prev], F3 + 6 * j);
+            for (int a = 0; a < nda; a++)
+            {
+               double col[6];
+               joint_S_col(t, anc, a, col);
+               if (M)
+               {
+                  double m = dot6(col, F2 + 6 * j);
+                  M[(da + a) * nv + di + j] = m;
+                  M[(di + j) * nv + da + a] = m;
+               }
+               C[(da + a) * nv + di + j] = dot6(col, F1 + 6 * j);
+               C[(di + j) * nv + da + a] = dot6(Sd[anc] + 6 * a, F2 + 6 * j) + dot6(col, F3 + 6 * j);
+            }
+         }
+         prev = anc;
+         anc = t->parent[anc];
+      }
+   }
+   free(F); free(comp); free(fcomp); free(X); free(Sd);
+}
+
 /* ================================================================== batched drivers (CPU baseline: one
  * calculator instance per thread, like one cloned MultiBodySystem + calculator per thread in Java,
  * M/tools/MultiBodySystemFactories.java:310).  Plain pthreads, static contiguous slices. */

@@ -80,6 +80,11 @@ void mo_crba_centroidal(const mo_tree *t, const double *q, int frame, double *M,
 /* getCentroidalConvectiveTerm(): d/dt(cmm) qd, [6] angular first, in the centroidal frame */
 void mo_centroidal_convective_term(const mo_tree *t, const double *q, const double *qd, int frame, double *out6);
 
+/* Coriolis and centrifugal matrix C(q, qd) [nv][nv] row-major (getCoriolisMatrix(), CompositeRigidBodyMassMatrixCalculator.java:358-366
+ * after setEnableCoriolisMatrixCalculation(true)); C qd = the joint efforts of inverse dynamics with zero joint accelerations and no
+ * gravity.  M (nullable): the mass matrix computed by the same recursion. */
+void mo_coriolis(const mo_tree *t, const double *q, const double *qd, double *M, double *C);
+
 /* ABA with per-joint source modes (ForwardDynamicsCalculator.java:45-57, :400-444, :508-520): accel_source [nb], non-zero = the
  * joint's acceleration is an input (qdd_in [nv], its rows only) and its effort an output (pass four :1315-1363).  qdd [nv] holds all
  * joint accelerations, tau_out (nullable, [nv]) all joint efforts as getJointTauMatrix() :566-590 returns them. */

@@ -12,7 +12,7 @@ echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2>> gpurun_out/${TAG}_bench.err
 cat gpurun_out/${TAG}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
-   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_bench.log 2>&1
+   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-extras > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:thread_kernel -s 3 -c 3 -f -o gpurun_out/${TAG}_prof \
    python scripts/prof_run.py 1048576 2 > gpurun_out/${TAG}_ncu_full.log 2>&1
 tail -3 gpurun_out/${TAG}_ncu_full.log

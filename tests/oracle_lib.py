@@ -114,6 +114,14 @@ class Oracle:
         self.lib.mo_centroidal_convective_term(ctypes.byref(self.c), _d(q), _d(qd), ctypes.c_int(frame), _d(out))
         return out
 
+    def coriolis(self, q, qd):
+        """(M [nv, nv], Coriolis and centrifugal matrix C [nv, nv]) of one state."""
+        q, qd = map(self._f64, (q, qd))
+        nv = self.t.nv
+        M, C = np.zeros((nv, nv)), np.zeros((nv, nv))
+        self.lib.mo_coriolis(ctypes.byref(self.c), _d(q), _d(qd), _d(M), _d(C))
+        return M, C
+
     def integrate(self, dt, q, qd, qdd):
         """doubleIntegrateFromAcceleration on one state; returns the updated (q, qd, qdd) copies."""
         q, qd, qdd = (np.array(x, dtype=np.float64, copy=True) for x in (q, qd, qdd))

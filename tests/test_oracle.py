@@ -136,6 +136,26 @@ def test_centroidal_momentum_matrix_and_convective_term(idx):
         assert np.array_equal(Ac[3:], A[3:])
 
 
+@pytest.mark.parametrize("idx", range(10))
+def test_coriolis_matrix(idx):
+    """CompositeRigidBodyMassMatrixCalculatorTest.testCoriolisMatrix (:85-138): C(q, qd) qd equals the joint efforts of inverse
+    dynamics without joint accelerations (zero gravity, the calculators' default), at 1e-11.  Beyond the reference's test:
+    dM/dt - 2 C is skew-symmetric, i.e. dM/dt = C + C^T (finite difference along qd; one-DoF trees, where q' = qd)."""
+    rng = np.random.default_rng(1300 + idx)
+    name, t = cases(rng)[idx]
+    o = ol.Oracle(t, gravity=(0.0, 0.0, 0.0))
+    q, qd, _, _ = td.random_states(rng, t, 4)
+    for s in range(4):
+        M, C = o.coriolis(q[:, s], qd[:, s])
+        assert np.array_equal(M, o.crba(q[:, s])), name
+        want = o.rnea(q[:, s], qd[:, s], np.zeros(t.nv), flags=2)
+        assert np.max(np.abs(C @ qd[:, s] - want)) < 1e-11 * max(1.0, np.max(np.abs(want))), name
+        if not (t.jtype == td.SIXDOF).any():
+            h = 1e-6
+            Mp, Mm = o.crba(q[:, s] + h * qd[:, s]), o.crba(q[:, s] - h * qd[:, s])
+            assert np.max(np.abs((Mp - Mm) / (2 * h) - (C + C.T))) < 1e-6 * max(1.0, np.max(np.abs(C))), name
+
+
 def test_flags_match_zeroed_inputs():
     """setConsiderCoriolisAndCentrifugalForces(false) == zero velocities; setConsiderJointAccelerations(false) == zero
     accelerations (InverseDynamicsCalculator.java:882-915)."""
