@@ -411,6 +411,9 @@ def main():
         extras["centroidal_convective_term"] = hbm_entry(timed(lambda: cen.getCentroidalConvectiveTermMatrix(q, qd)), 8.0 * (nq + nv + 4 + 6),
                                                          "getCentroidalConvectiveTermMatrix (mecano_b200_centroidal_convective_term: one RNEA launch "
                                                          "whose joint efforts go to a scratch buffer, + the shift)")
+        cen.setEnableCoriolisMatrixCalculation(True)
+        extras["coriolis_matrix"] = hbm_entry(timed(lambda: cen.getCoriolisMatrix(q, qd)), 8.0 * (nq + nv + 2 * nv * nv),
+                                              "getMassMatrix + getCoriolisMatrix, both dense nv x nv (mecano_b200_coriolis)")
         del cen
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine

@@ -225,6 +225,15 @@ int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n_stat
                                            double *out, int frame, void *stream);
 
 /*
+ * Mass matrix and Coriolis / centrifugal matrix together: getMassMatrix() + getCoriolisMatrix() after
+ * setEnableCoriolisMatrixCalculation(true) (CompositeRigidBodyMassMatrixCalculator.java:278-281, :358-366, recursion :588-799,
+ * FactorizedBodyInertia.java).  Both [n_dofs * n_dofs][ld], entry-major, every entry written; coriolis_matrix * qd = the joint
+ * efforts of inverse dynamics with zero joint accelerations and no gravity.
+ */
+int mecano_b200_coriolis(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, double *mass_matrix,
+                         double *coriolis_matrix, void *stream);
+
+/*
  * Host-pointer entry points (what a JNI / Panama binding calls with DMatrixRMaj.data): inputs are
  * staged host -> device in chunks, the kernels run, results are copied back; the call returns when
  * the outputs are complete.  Pinned (page-locked) host memory makes the copies asynchronous and
@@ -239,6 +248,8 @@ int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, co
 int mecano_b200_aba_sources_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                                  const double *qdd_in, const double *fext, double *qdd, double *tau_out);
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
+int mecano_b200_coriolis_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, double *mass_matrix,
+                              double *coriolis_matrix);
 int mecano_b200_crba_centroidal_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, double *cmm,
                                      double *com, int frame);
 int mecano_b200_centroidal_convective_term_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd,

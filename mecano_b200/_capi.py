@@ -64,7 +64,7 @@ EXPORTS = [
     "mecano_b200_rnea_full", "mecano_b200_rnea_full_host",
     "mecano_b200_set_joint_source_modes", "mecano_b200_aba_sources", "mecano_b200_aba_sources_host",
     "mecano_b200_crba_centroidal", "mecano_b200_centroidal_convective_term", "mecano_b200_crba_centroidal_host",
-    "mecano_b200_centroidal_convective_term_host",
+    "mecano_b200_centroidal_convective_term_host", "mecano_b200_coriolis", "mecano_b200_coriolis_host",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -89,6 +89,8 @@ lib.mecano_b200_crba_centroidal.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp
 lib.mecano_b200_centroidal_convective_term.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
 lib.mecano_b200_crba_centroidal_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int]
 lib.mecano_b200_centroidal_convective_term_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int]
+lib.mecano_b200_coriolis.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]
+lib.mecano_b200_coriolis_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]
 lib.mecano_b200_crba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32, c_vp]
 lib.mecano_b200_rnea_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
 lib.mecano_b200_aba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]

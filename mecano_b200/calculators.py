@@ -299,6 +299,26 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
     def _frame_code(self):
         return _capi.FRAME_CENTER_OF_MASS if self._frame == self.CENTER_OF_MASS_FRAME else _capi.FRAME_WORLD
 
+    def setEnableCoriolisMatrixCalculation(self, enableCoriolisMatrixCalculation):
+        """setEnableCoriolisMatrixCalculation (:278-281); disabled by default, like the reference."""
+        self._coriolis_enabled = bool(enableCoriolisMatrixCalculation)
+
+    def getCoriolisMatrix(self, q, qd):
+        """getCoriolisMatrix() (:358-366) for N states: [nDoFs * nDoFs, N], entry (i, j) of state s at [i * nDoFs + j, s]; times
+        the joint velocities it gives the Coriolis and centrifugal joint efforts.  The mass matrix of the same states comes out
+        of the same recursion (getMassMatrix() without an argument returns it).  Raises like the reference
+        (UnsupportedOperationException) unless setEnableCoriolisMatrixCalculation(True) was called."""
+        if not getattr(self, "_coriolis_enabled", False):
+            raise RuntimeError("Coriolis matrix calculation is disabled.")
+        nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
+        n = q.shape[1] if q.ndim == 2 else -1
+        self._check("q", q, nq, n)
+        self._check("qd", qd, nv, n)
+        self._M = self._empty_like(q, nv * nv, n)
+        self._C = self._empty_like(q, nv * nv, n)
+        self._engine.coriolis(q, qd, self._M, self._C)
+        return self._C
+
     def getCentroidalMomentumMatrix(self, q):
         """getCentroidalMomentumMatrix() (:411-416, :801-809) for N states: [6 * nDoFs, N], entry (r, j) of the 6 x nDoFs matrix of
         state s at [r * nDoFs + j, s] (angular rows first); times the joint velocities it gives the momentum of the system in the

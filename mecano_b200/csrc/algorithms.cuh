@@ -14,3 +14,4 @@
 #include "rnea.cuh"
 #include "aba.cuh"
 #include "crba.cuh"
+#include "coriolis.cuh"

@@ -32,15 +32,15 @@ struct mecano_b200_handle
    size_t scratch_doubles = 0;
    double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
    size_t ws_doubles[3] = {0, 0, 0};
-   mb::SpecKernel spec[3];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
+   mb::SpecKernel spec[MB_NUM_ALGOS];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
-   mb::LaunchPlan plan[3];
+   mb::LaunchPlan plan[MB_NUM_ALGOS];
    int variant = MECANO_B200_VARIANT_AUTO;
    int max_children = 1, max_ndof = 1, sm_count = 148;
    int n_accel_source = 0;           // joints in ACCELERATION_SOURCE mode (mecano_b200_set_joint_source_modes)
    std::vector<std::pair<int, int>> effort_dof_runs; // (first DoF row, count) runs of DoF rows whose joints are EFFORT_SOURCE
    bool warp_ok = false;             // the tree fits the warp-per-state variant (<= 32 bodies)
-   int64_t warp_below[3] = {0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
+   int64_t warp_below[MB_NUM_ALGOS] = {0, 0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
    std::string error;
    // host pipeline (lazy)
    cudaStream_t streams[2] = {nullptr, nullptr};
@@ -95,6 +95,7 @@ struct RunOpts
    const double *x2 = nullptr;                           // ABA: accelerations of the ACCELERATION_SOURCE joints
    double *cmm = nullptr, *com = nullptr;                // CRBA: centroidal momentum matrix (root frame), (mass * CoM, mass)
    double *root_wrench = nullptr;                        // RNEA: wrench at the root (root frame)
+   double *cor = nullptr;                                // MB_CORIOLIS: the Coriolis matrix
    bool zero_gravity = false;
 };
 
@@ -113,7 +114,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
    // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
-   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench;
+   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench || algo == MB_CORIOLIS;
    const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]));
    if (use_warp)
    {
@@ -123,7 +124,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.q = q; wa.qd = qd; wa.x = x; wa.fext = fext; wa.out = out;
       wa.body_acc = wa.joint_wrench = nullptr;
       wa.x2 = nullptr;
-      wa.cmm = wa.com = wa.root_wrench = nullptr;
+      wa.cmm = wa.com = wa.root_wrench = wa.cor = nullptr;
       wa.consts = h->d_consts;
       wa.ws = nullptr;
       wa.ws_ld = 0;
@@ -162,6 +163,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.body_acc = body_acc; a.joint_wrench = joint_wrench;
    a.x2 = x2;
    a.cmm = opt.cmm; a.com = opt.com; a.root_wrench = opt.root_wrench;
+   a.cor = opt.cor;
    a.consts = h->d_consts;
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
@@ -431,7 +433,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       if ((e = cudaMalloc(&h->d_zero, zb)) != cudaSuccess) return bail(e, "cudaMalloc(zero entries)");
       if ((e = cudaMemcpy(h->d_zero, h->tree.zero_entries.data(), zb, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(zero entries)");
    }
-   for (int algo = 0; algo < 3; algo++)
+   for (int algo = 0; algo < MB_NUM_ALGOS; algo++)
    {
       bool fits = false;
       if ((e = mb::plan_thread_kernel(algo, h->tree.prog[algo], false, h->plan[algo], &fits)) != cudaSuccess) return bail(e, "kernel planning");
@@ -703,6 +705,49 @@ int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n, int
       MB_CUDA(h, mb::launch_centroidal_finish(ca, st));
    }
    return MECANO_B200_OK;
+}
+
+int mecano_b200_coriolis(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, double *M, double *C, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !M || !C) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_CUDA(h, cudaSetDevice(h->device));
+   RunOpts opt;
+   opt.cor = C;
+   return run(h, MB_CORIOLIS, n, ld, q, qd, qd, nullptr, M, 0u, (cudaStream_t)stream, opt);
+}
+
+int mecano_b200_coriolis_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, double *M, double *C)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !qd || !M || !C) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_CUDA(h, cudaSetDevice(h->device));
+   const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + nv + 2 * nv * nv;
+   const size_t chunk = (size_t)std::min<int64_t>(n, 16384);
+   double *d = nullptr;
+   MB_CUDA(h, cudaMalloc(&d, rows * chunk * sizeof(double)));
+   double *dq = d, *dqd = dq + nq * chunk, *dM = dqd + nv * chunk, *dC = dM + nv * nv * chunk;
+   cudaError_t e = cudaSuccess;
+   for (int64_t s0 = 0; s0 < n && rc == 0 && e == cudaSuccess; s0 += (int64_t)chunk)
+   {
+      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
+      e = copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, nullptr);
+      if (e == cudaSuccess) e = copy_rows(dqd, chunk, qd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, nullptr);
+      if (e != cudaSuccess) break;
+      rc = mecano_b200_coriolis(h, (int64_t)w, (int64_t)chunk, dq, dqd, dM, dC, nullptr);
+      if (rc) break;
+      e = copy_rows(M + s0, (size_t)ld, dM, chunk, w, nv * nv, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = copy_rows(C + s0, (size_t)ld, dC, chunk, w, nv * nv, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+   }
+   cudaFree(d);
+   if (e != cudaSuccess) return cuda_fail(h, e, "mecano_b200_coriolis_host");
+   return rc;
 }
 
 // host-pointer variants of the two centroidal calls: plain staging through temporary device buffers, chunk by chunk

@@ -84,6 +84,7 @@ int slot_size(int algo, int jtype)
    {
       case MB_RNEA: return 6 + jp;       // accumulated wrench + joint parameters
       case MB_ABA: return 6 + jp + nd;   // twist + joint parameters + joint velocity
+      case MB_CORIOLIS: return 6 + jp;   // twist + joint parameters
       default: return jp;                // CRBA: joint parameters only
    }
 }
@@ -94,6 +95,7 @@ int aux_size(int algo)
    {
       case MB_RNEA: return 12; // twist + spatial acceleration of a branching body
       case MB_ABA: return 27;  // articulated inertia (6 + 9 + 6) + bias wrench (6); reused for (v, a) in pass three
+      case MB_CORIOLIS: return 46; // composite inertia (10) + composite factorized inertia (4 x 9)
       default: return 10;      // composite inertia (6 + 3 + 1)
    }
 }
@@ -109,6 +111,8 @@ int slot2_size(int algo, int jtype, bool root_parent)
          return jtype == MB_SIXDOF ? (root_parent ? 3 : 9) : 4;
       case MB_ABA: // twist (3) + sin/cos (1); SixDoF: twist (3) + transform (6) unless attached to the root body
          return jtype == MB_SIXDOF ? (root_parent ? 3 : 9) : 4;
+      case MB_CORIOLIS: // twist (3) + sin/cos (1); SixDoF: twist (3) + transform (6)
+         return jtype == MB_SIXDOF ? 9 : 4;
       default: // CRBA: sin/cos (1); SixDoF: transform (6)
          return jtype == MB_SIXDOF ? 6 : 1;
    }
@@ -129,7 +133,7 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       {
          const MbBody &Bp = P.body[B.parent];
          s = slot2[B.parent] + slot2_size(algo, Bp.jtype, Bp.parent < 0);
-         if (algo != MB_CRBA)
+         if (algo == MB_RNEA || algo == MB_ABA)
          {
             wslot[i] = wslot[B.parent] + 3;
             nslot[i] = nslot[B.parent] + slot2_size(algo, Bp.jtype, Bp.parent < 0) - 3;
@@ -140,7 +144,7 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       if (nchild[i] > 0 || B.jtype == MB_SIXDOF)
       {
          P.stack2 = std::max(P.stack2, s + slot2_size(algo, B.jtype, B.parent < 0));
-         if (algo != MB_CRBA)
+         if (algo == MB_RNEA || algo == MB_ABA)
          {
             P.wstack2 = std::max(P.wstack2, wslot[i] + 3);
             P.nstack2 = std::max(P.nstack2, nslot[i] + slot2_size(algo, B.jtype, B.parent < 0) - 3);
@@ -470,7 +474,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
       out.level_start[l + 1] += out.level_start[l];
 
    // ---- traversal programs
-   for (int algo = 0; algo < 3; algo++)
+   for (int algo = 0; algo < MB_NUM_ALGOS; algo++)
    {
       MbProgram &P = out.prog[algo];
       std::memset(&P, 0, sizeof P);

@@ -21,7 +21,7 @@ struct FlatTree
    std::vector<int> level_order;    // internal indices sorted by level (for the warp-per-state variant)
    std::vector<int> level_start;    // [n_levels + 1] into level_order
    std::vector<uint16_t> zero_entries; // mass-matrix entries (row * nv + col) that are structurally zero, padded to a multiple of 8
-   MbProgram prog[3];               // MB_RNEA, MB_ABA, MB_CRBA
+   MbProgram prog[MB_NUM_ALGOS];    // MB_RNEA, MB_ABA, MB_CRBA, MB_CORIOLIS
 };
 
 // Returns MECANO_B200_OK or a negative error code; `err` receives the message.

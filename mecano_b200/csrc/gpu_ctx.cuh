@@ -235,6 +235,27 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       if (!kClamp || active)
          mb_stg_cs(mb_row(mbase, (unsigned)e, mstride), v);
    }
+   char *corb; // Coriolis matrix (MB_CORIOLIS), entry-major
+   __device__ __forceinline__ void st_C(int e, double v) const
+   {
+      if (!kClamp || active)
+         mb_stg_cs(mb_row(corb, (unsigned)e, ld8), v);
+   }
+   __device__ __forceinline__ void zero_fill_mc() const
+   {
+#pragma unroll 1
+      for (int k = 0; k < nz8; k++)
+      {
+         const uint4 u = __ldg(zlist + k);
+         const unsigned e[8] = {u.x & 0xffffu, u.x >> 16, u.y & 0xffffu, u.y >> 16, u.z & 0xffffu, u.z >> 16, u.w & 0xffffu, u.w >> 16};
+#pragma unroll
+         for (int j = 0; j < 8; j++)
+         {
+            st_M((int)e[j], 0.0);
+            st_C((int)e[j], 0.0);
+         }
+      }
+   }
    __device__ __forceinline__ void zero_fill() const
    {
 #pragma unroll 1
@@ -337,6 +358,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
       c2.accb = (char *)(a.body_acc + s); c2.wrb = (char *)(a.joint_wrench + s);
       c2.x2b = (const char *)(a.x2 + s);
+      c2.corb = (char *)(a.cor + s);
       c2.cmmb = (char *)(a.cmm + s); c2.comb = (char *)(a.com + s); c2.rwb = (char *)(a.root_wrench + s);
       c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
       body(c2);

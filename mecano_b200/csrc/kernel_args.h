@@ -14,6 +14,7 @@ struct KernelArgs
                                     // CoM frame, wrench of each joint in its frameAfterJoint
    double *cmm, *com;               // CRBA by-products (nullable): centroidal momentum matrix rows [r * nv + col], r = 0..5, in the root frame;
                                     // com rows 0..3 accumulate (mass * CoM, mass) over the root's children (zeroed before the launch)
+   double *cor;                     // MB_CORIOLIS: the Coriolis matrix, entry-major like the mass matrix in `out`
    double *root_wrench;             // RNEA by-product (nullable): rows 0..5 accumulate the wrench at the root in the root frame (zeroed before)
    const double *consts;            // device copy of the per-body constant records
    double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid

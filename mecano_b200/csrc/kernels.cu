@@ -37,8 +37,10 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
          rnea_state<double, Ctx, FEXT>(P, c2, a.grav);
       else if constexpr (ALGO == MB_ABA)
          aba_state<double, Ctx, FEXT>(P, c2, a.grav);
-      else
+      else if constexpr (ALGO == MB_CRBA)
          crba_state<double, Ctx, FEXT>(P, c2);
+      else
+         coriolis_state<double, Ctx>(P, c2);
    });
 }
 
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
 constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
 constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
 constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
+constexpr int kCorAux0 = 46 * 4, kCorAux1 = 46 * 16;
 constexpr int kAbaRec0 = MB_ABA_REC * 33, kAbaRec1 = MB_ABA_REC * 128;
 // launch configurations: threads per block, work-area class, stack slots (double2) held in tensor memory
 struct Cfg
@@ -63,17 +66,17 @@ typedef void (*KernelFn)(const MbProgram, const KernelArgs);
 
 template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
 {
-   constexpr int a0 = ALGO == MB_RNEA ? kRnaAux0 : (ALGO == MB_ABA ? kAbaAux0 : kCrbAux0);
-   constexpr int a1 = ALGO == MB_RNEA ? kRnaAux1 : (ALGO == MB_ABA ? kAbaAux1 : kCrbAux1);
+   constexpr int a0 = ALGO == MB_RNEA ? kRnaAux0 : (ALGO == MB_ABA ? kAbaAux0 : (ALGO == MB_CRBA ? kCrbAux0 : kCorAux0));
+   constexpr int a1 = ALGO == MB_RNEA ? kRnaAux1 : (ALGO == MB_ABA ? kAbaAux1 : (ALGO == MB_CRBA ? kCrbAux1 : kCorAux1));
    constexpr int r0 = ALGO == MB_ABA ? kAbaRec0 : 0, r1 = ALGO == MB_ABA ? kAbaRec1 : 0;
    switch (cfg)
    {
       // CRBA has no wide stack area: its TMEM configurations are never planned (mb_tm_fits) and alias the shared-memory kernels
-#define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, ALGO == MB_CRBA ? 0 : kCfg[i].tm>;
+#define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, (ALGO == MB_CRBA || ALGO == MB_CORIOLIS) ? 0 : kCfg[i].tm>;
       MB_CFG_CASE(0) MB_CFG_CASE(1) MB_CFG_CASE(2) MB_CFG_CASE(3) MB_CFG_CASE(4) MB_CFG_CASE(5) MB_CFG_CASE(6)
       MB_CFG_CASE(7) MB_CFG_CASE(8) MB_CFG_CASE(9) MB_CFG_CASE(10) MB_CFG_CASE(11) MB_CFG_CASE(12) MB_CFG_CASE(14)
 #undef MB_CFG_CASE
-      default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, ALGO == MB_CRBA ? 0 : kCfg[13].tm>;
+      default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, (ALGO == MB_CRBA || ALGO == MB_CORIOLIS) ? 0 : kCfg[13].tm>;
    }
 }
 
@@ -81,6 +84,7 @@ KernelFn pick(int algo, bool fext, bool state_major, int cfg)
 {
    if (algo == MB_RNEA) return fext ? pick_cfg<MB_RNEA, true, false>(cfg) : pick_cfg<MB_RNEA, false, false>(cfg);
    if (algo == MB_ABA) return fext ? pick_cfg<MB_ABA, true, false>(cfg) : pick_cfg<MB_ABA, false, false>(cfg);
+   if (algo == MB_CORIOLIS) return pick_cfg<MB_CORIOLIS, false, false>(cfg);
    // CRBA: the "FEXT" instantiation is the one with by-products (centroidal momentum matrix, centre of mass), entry-major only
    if (fext && !state_major) return pick_cfg<MB_CRBA, true, false>(cfg);
    return state_major ? pick_cfg<MB_CRBA, false, true>(cfg) : pick_cfg<MB_CRBA, false, false>(cfg);
@@ -88,8 +92,8 @@ KernelFn pick(int algo, bool fext, bool state_major, int cfg)
 
 int class_of(int algo, const MbProgram &P)
 {
-   const int aux0 = algo == MB_RNEA ? kRnaAux0 : (algo == MB_ABA ? kAbaAux0 : kCrbAux0);
-   const int aux1 = algo == MB_RNEA ? kRnaAux1 : (algo == MB_ABA ? kAbaAux1 : kCrbAux1);
+   const int aux0 = algo == MB_RNEA ? kRnaAux0 : (algo == MB_ABA ? kAbaAux0 : (algo == MB_CRBA ? kCrbAux0 : kCorAux0));
+   const int aux1 = algo == MB_RNEA ? kRnaAux1 : (algo == MB_ABA ? kAbaAux1 : (algo == MB_CRBA ? kCrbAux1 : kCorAux1));
    const int rec0 = algo == MB_ABA ? kAbaRec0 : 0, rec1 = algo == MB_ABA ? kAbaRec1 : 0;
    if (P.aux_doubles <= aux0 && P.rec_doubles <= rec0) return 0;
    if (P.aux_doubles <= aux1 && P.rec_doubles <= rec1) return 1;
@@ -170,7 +174,9 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
          nblk = 1; // cannot happen (smem_bytes), but a TMEM block must be alone on its SM
       // register spills cost more than the extra warps bring: a configuration whose kernel spills beyond its declared
       // work area only competes if nothing else fits
-      const int auxn = algo == MB_RNEA ? (kCfg[cfg].cls ? kRnaAux1 : kRnaAux0) : (algo == MB_ABA ? (kCfg[cfg].cls ? kAbaAux1 : kAbaAux0) : (kCfg[cfg].cls ? kCrbAux1 : kCrbAux0));
+      const int auxn = algo == MB_RNEA ? (kCfg[cfg].cls ? kRnaAux1 : kRnaAux0)
+                                       : (algo == MB_ABA ? (kCfg[cfg].cls ? kAbaAux1 : kAbaAux0)
+                                                         : (algo == MB_CRBA ? (kCfg[cfg].cls ? kCrbAux1 : kCrbAux0) : (kCfg[cfg].cls ? kCorAux1 : kCorAux0)));
       const bool spills = (long)fa.localSizeBytes > 8l * auxn + 128;
       // warps that do not split evenly over the four sub-partitions lose more than they bring (ABA 320 threads: 3.44 ms,
       // 256 threads: 2.23 ms; profiles/r01i_cfg_sweep.jsonl): such block sizes only compete if nothing else fits

@@ -152,7 +152,8 @@ __host__ __device__
 #endif
 static inline int mb_jp_size(int jtype) { return jtype == MB_REVOLUTE ? 2 : (jtype == MB_PRISMATIC ? 1 : 12); }
 
-enum MbAlgo { MB_RNEA = 0, MB_ABA = 1, MB_CRBA = 2 };
+enum MbAlgo { MB_RNEA = 0, MB_ABA = 1, MB_CRBA = 2, MB_CORIOLIS = 3 }; // MB_CORIOLIS: mass matrix + Coriolis matrix (coriolis.cuh)
+#define MB_NUM_ALGOS 4
 
 // Shared-memory stack slots (double2 per state) of a thread-per-state block.  With a tensor-memory stack (tm > 0 slots,
 // RNEA / ABA) the wide area lives in TMEM and only the narrow one in shared memory.  ABA overlays its pass-three ring
@@ -163,7 +164,7 @@ __host__ __device__
 static inline int mb_smem_stack_slots(int algo, const MbProgram &P, int tm)
 {
    int s = P.stack2;
-   if (tm > 0 && algo != MB_CRBA)
+   if (tm > 0 && algo != MB_CRBA && algo != MB_CORIOLIS)
       s = P.nstack2 + (P.wstack2 > tm ? P.wstack2 - tm : 0); // wide slots beyond the TMEM share spill over behind the narrow area
    if (algo == MB_ABA && s < 20)
       s = 20;
@@ -178,5 +179,5 @@ __host__ __device__
 #endif
 static inline bool mb_tm_fits(int algo, const MbProgram &P, int tm, int block)
 {
-   return tm == 0 || (algo != MB_CRBA && (P.wstack2 <= tm || block == MB_PARTIAL_TM_BLOCK));
+   return tm == 0 || (algo != MB_CRBA && algo != MB_CORIOLIS && (P.wstack2 <= tm || block == MB_PARTIAL_TM_BLOCK));
 }

@@ -169,6 +169,21 @@ class Engine:
         check(lib.mecano_b200_crba(self._h, n, ld, pq, pm, layout, self._stream()), self._h)
         return M
 
+    def coriolis(self, q, qd, M, C):
+        """M, C [nv*nv, n] entry-major; torch CUDA tensors or numpy arrays (host path)."""
+        n = q.shape[1]
+        host = isinstance(q, np.ndarray)
+        f = _host_ptr_ld if host else _dev_ptr_ld
+        pq, l0 = f(q, self.nq, n)
+        pqd, l1 = f(qd, self.nv, n)
+        pm, l2 = f(M, self.nv * self.nv, n)
+        pc, l3 = f(C, self.nv * self.nv, n)
+        ld = _same_ld([l0, l1, l2, l3])
+        if host:
+            check(lib.mecano_b200_coriolis_host(self._h, n, ld, pq, pqd, pm, pc), self._h)
+        else:
+            check(lib.mecano_b200_coriolis(self._h, n, ld, pq, pqd, pm, pc, self._stream()), self._h)
+
     def crba_centroidal(self, q, M, cmm, com, frame=_capi.FRAME_WORLD):
         """M [nv*nv, n] entry-major, cmm [6*nv, n], com [4, n]; torch CUDA tensors or numpy arrays (host path)."""
         n = q.shape[1]

@@ -64,6 +64,12 @@ template <class T> struct CpuCtx
    double *acc_out = nullptr, *wr_out = nullptr;
    const double *x2 = nullptr;
    double *cmm = nullptr, *com = nullptr, *rootw = nullptr;
+   double *Cm = nullptr; // Coriolis matrix, entry-major like M
+   void st_C(int e, T v) { Cm[(long)e * ld + s] = (double)v; }
+   void zero_fill_mc()
+   {
+      for (uint16_t e : *zl) { st_M(e, (T)0); st_C(e, (T)0); }
+   }
    bool has_rootw() const { return rootw != nullptr; }
    void st_cmm(int row, T v) { cmm[(long)row * ld + s] = (double)v; }
    void add_com(int r, T v) { com[r * ld + s] += (double)v; }
@@ -130,7 +136,7 @@ template <class T> struct CpuCtx
 template <class T>
 int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long ld, const double *q, const double *qd, const double *x,
         const double *fext, double *out, unsigned flags, char *err, int errlen, double *acc_out = nullptr, double *wr_out = nullptr,
-        const int32_t *accel_source = nullptr, const double *x2 = nullptr, double *cmm = nullptr, double *com = nullptr, double *rootw = nullptr)
+        const int32_t *accel_source = nullptr, const double *x2 = nullptr, double *cmm = nullptr, double *com = nullptr, double *rootw = nullptr, double *Cm = nullptr)
 {
    mb::FlatTree ft;
    std::string e;
@@ -166,6 +172,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       c.wr_out = wr_out;
       c.x2 = x2;
       c.cmm = cmm; c.com = com; c.rootw = rootw;
+      c.Cm = Cm;
       c.zl = &ft.zero_entries;
       if (algo == MB_RNEA)
       {
@@ -177,6 +184,8 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
          if (fext || n_locked > 0) mb::aba_state<T, CpuCtx<T>, true>(P, c, grav);
          else mb::aba_state<T, CpuCtx<T>, false>(P, c, grav);
       }
+      else if (algo == MB_CORIOLIS)
+         mb::coriolis_state<T, CpuCtx<T>>(P, c);
       else if (cmm)
          mb::crba_state<T, CpuCtx<T>, true>(P, c);
       else
@@ -215,6 +224,14 @@ extern "C" int emu_crba_centroidal(const mecano_b200_tree_desc *d, long n, long 
    const double g[3] = {0, 0, 0};
    std::fill(com, com + 4 * ld, 0.0);
    return run<double>(MB_CRBA, d, g, n, ld, q, nullptr, nullptr, nullptr, M, 0u, err, errlen, nullptr, nullptr, nullptr, nullptr, cmm, com, nullptr);
+}
+
+// mass matrix M and Coriolis matrix C, both [nv * nv][ld] entry-major
+extern "C" int emu_coriolis(const mecano_b200_tree_desc *d, long n, long ld, const double *q, const double *qd, double *M, double *C, char *err,
+                            int errlen)
+{
+   const double g[3] = {0, 0, 0};
+   return run<double>(MB_CORIOLIS, d, g, n, ld, q, qd, nullptr, nullptr, M, 0u, err, errlen, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, C);
 }
 
 // RNEA with zero joint accelerations and no gravity, its wrench at the root summed into rootw [6][ld] (root frame): the centroidal

@@ -84,7 +84,7 @@ def lib():
     global _LIB
     if _LIB is None:
         out = os.path.join(_EMU, "libmecano_emu.so")
-        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh", "jointmath.cuh", "rnea.cuh", "aba.cuh", "crba.cuh")]
+        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh", "jointmath.cuh", "rnea.cuh", "aba.cuh", "crba.cuh", "coriolis.cuh")]
         if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(f) for f in deps):
             build()
         _LIB = ctypes.CDLL(out)
@@ -180,6 +180,17 @@ class Emu:
         if rc != 0:
             raise RuntimeError("emu_rnea_root_wrench rc=%d: %s" % (rc, err.value.decode()))
         return rw
+
+    def coriolis(self, q, qd):
+        """(M [nv, nv, n], Coriolis and centrifugal matrix C [nv, nv, n])."""
+        n = q.shape[1]
+        nv = self.tree.nv
+        M, C = np.full((nv * nv, n), np.nan), np.full((nv * nv, n), np.nan)
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_coriolis(ctypes.byref(self.desc), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(qd), _d(M), _d(C), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_coriolis rc=%d: %s" % (rc, err.value.decode()))
+        return M.reshape(nv, nv, n), C.reshape(nv, nv, n)
 
     def count_flops(self, algo, q, qd, x):
         """Algorithmic operation counts of one state (counting-scalar instantiation of the kernel routines)."""

@@ -114,6 +114,24 @@ def test_emulated_centroidal_byproducts_match_oracle(idx):
         assert rel(rw[:, s], o.centroidal_convective_term(q[:, s], qd[:, s], 0)) < TOL
 
 
+@pytest.mark.parametrize("idx", range(12))
+def test_emulated_coriolis_matrix_matches_oracle(idx):
+    """getCoriolisMatrix() (CompositeRigidBodyMassMatrixCalculator.java:358-366, :588-799), with the mass matrix of the same
+    recursion; every entry of both dense matrices written."""
+    rng = np.random.default_rng(1400 + idx)
+    t = trees(rng)[idx]
+    o, e = ol.Oracle(t), el.Emu(t)
+    n = 3
+    q, qd, _, _ = td.random_states(rng, t, n)
+    M, C = e.coriolis(q, qd)
+    assert not (np.isnan(M).any() or np.isnan(C).any())
+    assert rel(M, e.crba(q)) < 1e-13
+    for s in range(n):
+        Mo, Co = o.coriolis(q[:, s], qd[:, s])
+        assert rel(M[:, :, s], Mo) < TOL
+        assert rel(C[:, :, s], Co) < TOL
+
+
 def test_table_order_does_not_matter():
     """The C-ABI accepts any topological listing of the bodies (level order from the Java host, or DFS)."""
     rng = np.random.default_rng(9)

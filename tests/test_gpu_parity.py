@@ -550,3 +550,43 @@ def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
                     R = np.eye(3)
                 total += t.off_R[body] @ R @ wr[body, 3:, k]
         assert np.max(np.abs(hdot[3:, k] - total)) < 1e-9 * max(1.0, np.max(np.abs(total))), name
+
+
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 6, 8, 9])
+def test_coriolis_matrix(torch_dev, idx):
+    """getCoriolisMatrix() (CompositeRigidBodyMassMatrixCalculator.java:278-281, :358-366, :588-799) for N states: against the
+    oracle state by state, and on the whole batch through the reference's own test
+    (CompositeRigidBodyMassMatrixCalculatorTest.testCoriolisMatrix :85-138): C qd = inverse dynamics without joint accelerations,
+    at its 1e-11."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(7000 + idx)
+    o = ol.Oracle(t)
+    n = 900
+    nv = t.nv
+    q, qd, _, _ = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    tq, tqd = torch.from_numpy(q).to(dev), torch.from_numpy(qd).to(dev)
+    calc = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    with pytest.raises(RuntimeError):
+        calc.getCoriolisMatrix(tq, tqd)  # disabled by default (UnsupportedOperationException in the reference)
+    calc.setEnableCoriolisMatrixCalculation(True)
+    C = calc.getCoriolisMatrix(tq, tqd).cpu().numpy().reshape(nv, nv, n)
+    M = calc.getMassMatrix().cpu().numpy().reshape(nv, nv, n)
+    assert not (np.isnan(C).any() or np.isnan(M).any()), "every entry of both dense matrices must be written"
+    plain = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant("thread")
+    assert rel(M, plain.getMassMatrix(tq).cpu().numpy().reshape(nv, nv, n)) < 1e-13, name
+    for k in range(0, n, 41):
+        Mo, Co = o.coriolis(q[:, k], qd[:, k])
+        assert rel(C[:, :, k], Co) < TOL and rel(M[:, :, k], Mo) < TOL, name
+    ident = mb.InverseDynamicsCalculator(s)  # zero gravity, the calculators' default
+    ident.setConsiderJointAccelerations(False)
+    want = ident.compute(tq, tqd, tqd).cpu().numpy()
+    got = np.einsum("ijs,js->is", C, qd)
+    assert np.max(np.abs(got - want)) < 1e-11 * max(1.0, np.max(np.abs(want))) * max(1, t.nb / 10), name
+    # host path
+    hc = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    hc.setEnableCoriolisMatrixCalculation(True)
+    assert rel(hc.getCoriolisMatrix(q, qd).reshape(nv, nv, n), C) == 0.0 and rel(hc.getMassMatrix().reshape(nv, nv, n), M) == 0.0, name
