@@ -226,6 +226,27 @@ class CompositeRigidBodyMassMatrixCalculator : public BatchedCalculatorBase
          check(mecano_b200_crba_host(handle_, n, q.ld, q.data, massMatrixOut.data, layout));
    }
 
+   // ---- Coriolis and centrifugal matrix (CompositeRigidBodyMassMatrixCalculator.java:278-281, :358-366)
+   void setEnableCoriolisMatrixCalculation(bool enable) { coriolisEnabled_ = enable; }
+   // getMassMatrix() + getCoriolisMatrix() for N states: both (nDoFs*nDoFs) x N, entry-major
+   void getCoriolisMatrix(const MatrixView &q, const MatrixView &qd, const MatrixView &massMatrixOut, const MatrixView &coriolisMatrixOut,
+                          Memory where = Memory::Device)
+   {
+      if (!coriolisEnabled_)
+         throw std::runtime_error("Coriolis matrix calculation is disabled."); // UnsupportedOperationException, :360-361
+      const int64_t n = q.cols, nv = input_.getNumberOfDoFs(), nq = input_.getConfigurationMatrixSize();
+      checkShape(q, nq, n, "q");
+      checkShape(qd, nv, n, "qd");
+      checkShape(massMatrixOut, nv * nv, n, "massMatrix");
+      checkShape(coriolisMatrixOut, nv * nv, n, "coriolisMatrix");
+      if (qd.ld != q.ld || massMatrixOut.ld != q.ld || coriolisMatrixOut.ld != q.ld)
+         throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
+      if (where == Memory::Device)
+         check(mecano_b200_coriolis(handle_, n, q.ld, q.data, qd.data, massMatrixOut.data, coriolisMatrixOut.data, stream_));
+      else
+         check(mecano_b200_coriolis_host(handle_, n, q.ld, q.data, qd.data, massMatrixOut.data, coriolisMatrixOut.data));
+   }
+
    // ---- centroidal by-products (CompositeRigidBodyMassMatrixCalculator.java:380-440, :801-839)
    enum class CentroidalMomentumFrame { World = MECANO_B200_FRAME_WORLD, CenterOfMass = MECANO_B200_FRAME_CENTER_OF_MASS };
    void setCentroidalMomentumFrame(CentroidalMomentumFrame f) { frame_ = f; }
@@ -267,5 +288,6 @@ class CompositeRigidBodyMassMatrixCalculator : public BatchedCalculatorBase
 
  private:
    CentroidalMomentumFrame frame_ = CentroidalMomentumFrame::World;
+   bool coriolisEnabled_ = false;
 };
 } // namespace mecano

@@ -185,3 +185,16 @@ def test_tree_specialised_source_generates_and_compiles_without_a_gpu():
 
 def _capi_err(name):
     return {"INVALID_ARGUMENT": -1, "UNSUPPORTED_TOPOLOGY": -2, "SHAPE": -3, "NO_DEVICE": -4, "TOO_LARGE": -5, "JIT": -6}[name]
+
+
+def test_cpp_host_mirror_compiles_and_links(tmp_path):
+    """The C++ face of the calculator API (mecano_b200/csrc/host/calculators.hpp) is header-only: compile a translation unit
+    that names every member and link it against the C-ABI library (no GPU needed)."""
+    import subprocess
+
+    exe = str(tmp_path / "host_mirror_check")
+    libdir = os.path.dirname(_capi.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", "host_mirror_check.cpp"), "-o", exe,
+                           "-L", libdir, "-lmecano_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode()
+    assert "host mirror links: 1" in out
