@@ -198,3 +198,25 @@ def test_cpp_host_mirror_compiles_and_links(tmp_path):
                            "-L", libdir, "-lmecano_b200", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe]).decode()
     assert "host mirror links: 1" in out
+
+
+def test_jvm_exchange_file_round_trip(tmp_path, capsys):
+    """scripts/java_exchange.py: the file handed to baseline/java/MecanoHarness.java reads back to the same tables and states, and
+    the comparison passes when the results are the oracle's own (standing in for the JVM output, which cannot be produced here)."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import java_exchange as jx
+    import oracle_lib as ol
+
+    x, r = str(tmp_path / "exchange.bin"), str(tmp_path / "results.bin")
+    jx.write("tree12", 9, x, seed=5)
+    t, g, (q, qd, qdd, tau) = jx.read(x)
+    assert t.nb == 13 and t.nv == 18 and q.shape == (t.nq, 9) and g == jx.GRAVITY
+    ref = jx.build("tree12", 5).describe()
+    assert np.array_equal(t.parent, ref["parent"]) and np.array_equal(t.J, ref["J"]) and np.array_equal(t.dof_off, ref["dof_off"])
+    o = ol.Oracle(t, gravity=g)
+    np.concatenate([o.rnea_batch(q, qd, qdd).ravel(), o.aba_batch(q, qd, tau).ravel(), o.crba_batch(q).ravel()]).astype("<f8").tofile(r)
+    capsys.readouterr()
+    jx.compare(x, r)
+    assert '"pass": true' in capsys.readouterr().out
