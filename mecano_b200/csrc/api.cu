@@ -908,8 +908,8 @@ int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const do
 
 int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info)
 {
-   if (!h || !info || algo < 0 || algo > 2) return MECANO_B200_ERR_INVALID_ARGUMENT;
-   const bool warp = h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n_states > 0 && n_states < h->warp_below[algo]);
+   if (!h || !info || algo < 0 || algo >= MB_NUM_ALGOS) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   const bool warp = algo != MB_CORIOLIS && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n_states > 0 && n_states < h->warp_below[algo]));
    if (warp)
    {
       std::memset(info, 0, sizeof *info);
@@ -960,7 +960,7 @@ int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_state
    info->stack_doubles = P.stack_doubles;
    info->max_depth = P.max_depth;
    const double nq = P.nq, nv = P.nv;
-   info->bytes_per_state = algo == MB_CRBA ? 8.0 * (nq + nv * nv) : 8.0 * (nq + 3.0 * nv);
+   info->bytes_per_state = algo == MB_CRBA ? 8.0 * (nq + nv * nv) : (algo == MB_CORIOLIS ? 8.0 * (nq + nv + 2.0 * nv * nv) : 8.0 * (nq + 3.0 * nv));
    return MECANO_B200_OK;
 }
 

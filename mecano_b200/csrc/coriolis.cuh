@@ -303,51 +303,8 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
             Bc = Bc + bacc;
          }
          const int d = o.dof;
-         const int ncol = jt == MB_SIXDOF ? 6 : 1;
-#pragma unroll 1
-         for (int col = 0; col < ncol; col++)
-         {
-            // S and Sdot = v x S of this DoF (:604-630)
-            SvT<T> S = sv_zero<T>();
-            if (jt == MB_REVOLUTE) S.a.z = (T)1;
-            else if (jt == MB_PRISMATIC) S.l.z = (T)1;
-            else if (col == 0) S.a.x = (T)1; else if (col == 1) S.a.y = (T)1; else if (col == 2) S.a.z = (T)1;
-            else if (col == 3) S.l.x = (T)1; else if (col == 4) S.l.y = (T)1; else S.l.z = (T)1;
-            const SvT<T> Sd = cross_motion(vb, S);
-            const SvT<T> F2 = mul(Ic, S);                 // :663-667
-            const SvT<T> F1 = mul(Ic, Sd) + mul(Bc, S);   // :687-689
-            const SvT<T> F3 = mulT(Bc, S);                // :692
-            const int dc = d + col;
-            if (jt != MB_SIXDOF)
-            {
-               const T m = jt == MB_REVOLUTE ? F2.a.z : F2.l.z;
-               c.st_M(dc * nv + dc, m);
-               c.st_C(dc * nv + dc, jt == MB_REVOLUTE ? F1.a.z : F1.l.z);
-            }
-            else
-            {
-               // the 6 x 6 block of the joint, as the Java loops leave it (:700-725, later writes win): on and below the diagonal
-               // C[a, b] = S_a . F1_b, above it C[a, b] = Sdot_b . F2_a + S_b . F3_a; this column b = col holds F*_b, i.e. the
-               // entries (a >= col, col) and (col, a > col)
-               const SvT<T> dd = cross_force(vb, F2);
-               const T f1[6] = {F1.a.x, F1.a.y, F1.a.z, F1.l.x, F1.l.y, F1.l.z};
-               const T f2[6] = {F2.a.x, F2.a.y, F2.a.z, F2.l.x, F2.l.y, F2.l.z};
-               const T g[6] = {F3.a.x - dd.a.x, F3.a.y - dd.a.y, F3.a.z - dd.a.z, F3.l.x - dd.l.x, F3.l.y - dd.l.y, F3.l.z - dd.l.z};
-#pragma unroll
-               for (int r = 0; r < 6; r++)
-               {
-                  c.st_M((d + r) * nv + dc, f2[r]);
-                  if (r >= col)
-                     c.st_C((d + r) * nv + dc, f1[r]);
-                  if (r > col)
-                     c.st_C(dc * nv + d + r, g[r]);
-               }
-            }
-            if (!(o.flags & MB2_ROOT_PARENT))
-               cor_walk<T>(P, c, o.body, dc, js, jc, F1, F2, F3);
-         }
-         if (!(o.flags & MB2_ROOT_PARENT))
-         {
+         // fold into the parent: childInertia.applyTransform(child.transformToParent) (:658), childFactorizedInertia (:679)
+         auto fold = [&]() {
             XfT<T> X;
             if (jt == MB_REVOLUTE) X = joint_xf_1dof<T, true>(C, js, jc);
             else if (jt == MB_PRISMATIC) X = joint_xf_1dof<T, false>(C, js, jc);
@@ -369,6 +326,59 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
                aux_st_rbi<T>(c, o.paux, acc);
                aux_st_fbi<T>(c, o.paux + 10, bacc);
             }
+         };
+         if (jt != MB_SIXDOF)
+         {
+            // S = e_z (angular: revolute, linear: prismatic), Sdot = v x S (:604-630); F2 = Ic S (:663-667),
+            // F1 = Ic Sdot + Bc S (:687-689), F3 = Bc^T S (:692)
+            SvT<T> S = sv_zero<T>();
+            if (jt == MB_REVOLUTE) S.a.z = (T)1;
+            else S.l.z = (T)1;
+            const SvT<T> F2 = mul(Ic, S);
+            const SvT<T> F1 = mul(Ic, cross_motion(vb, S)) + mul(Bc, S);
+            const SvT<T> F3 = mulT(Bc, S);
+            c.st_M(d * nv + d, jt == MB_REVOLUTE ? F2.a.z : F2.l.z);
+            c.st_C(d * nv + d, jt == MB_REVOLUTE ? F1.a.z : F1.l.z);
+            if (!(o.flags & MB2_ROOT_PARENT))
+            {
+               // the accumulators first, so that the composite inertias are dead while the three columns walk up the ancestors
+               fold();
+               cor_walk<T>(P, c, o.body, d, js, jc, F1, F2, F3);
+            }
+         }
+         else
+         {
+#pragma unroll 1
+            for (int col = 0; col < 6; col++)
+            {
+               SvT<T> S = sv_zero<T>();
+               if (col == 0) S.a.x = (T)1; else if (col == 1) S.a.y = (T)1; else if (col == 2) S.a.z = (T)1;
+               else if (col == 3) S.l.x = (T)1; else if (col == 4) S.l.y = (T)1; else S.l.z = (T)1;
+               const SvT<T> F2 = mul(Ic, S);
+               const SvT<T> F1 = mul(Ic, cross_motion(vb, S)) + mul(Bc, S);
+               const SvT<T> F3 = mulT(Bc, S);
+               const int dc = d + col;
+               // the 6 x 6 block of the joint, as the Java loops leave it (:700-725, later writes win): on and below the diagonal
+               // C[a, b] = S_a . F1_b, above it C[a, b] = Sdot_b . F2_a + S_b . F3_a; this column b = col holds F*_b, i.e. the
+               // entries (a >= col, col) and (col, a > col)
+               const SvT<T> dd = cross_force(vb, F2);
+               const T f1[6] = {F1.a.x, F1.a.y, F1.a.z, F1.l.x, F1.l.y, F1.l.z};
+               const T f2[6] = {F2.a.x, F2.a.y, F2.a.z, F2.l.x, F2.l.y, F2.l.z};
+               const T g[6] = {F3.a.x - dd.a.x, F3.a.y - dd.a.y, F3.a.z - dd.a.z, F3.l.x - dd.l.x, F3.l.y - dd.l.y, F3.l.z - dd.l.z};
+#pragma unroll
+               for (int r = 0; r < 6; r++)
+               {
+                  c.st_M((d + r) * nv + dc, f2[r]);
+                  if (r >= col)
+                     c.st_C((d + r) * nv + dc, f1[r]);
+                  if (r > col)
+                     c.st_C(dc * nv + d + r, g[r]);
+               }
+               if (!(o.flags & MB2_ROOT_PARENT))
+                  cor_walk<T>(P, c, o.body, dc, js, jc, F1, F2, F3);
+            }
+            if (!(o.flags & MB2_ROOT_PARENT))
+               fold();
          }
       }
    }

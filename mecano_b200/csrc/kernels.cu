@@ -116,7 +116,7 @@ int forced_cfg(int algo)
 {
    const char *e = getenv("MECANO_B200_CFG");
    if (!e) return -1;
-   const char *key = algo == MB_RNEA ? "rnea=" : (algo == MB_ABA ? "aba=" : "crba=");
+   const char *key = algo == MB_RNEA ? "rnea=" : (algo == MB_ABA ? "aba=" : (algo == MB_CRBA ? "crba=" : "cor="));
    const char *p = strstr(e, key);
    return p ? atoi(p + strlen(key)) : -1;
 }
