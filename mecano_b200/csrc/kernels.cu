@@ -177,13 +177,16 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       const int auxn = algo == MB_RNEA ? (kCfg[cfg].cls ? kRnaAux1 : kRnaAux0)
                                        : (algo == MB_ABA ? (kCfg[cfg].cls ? kAbaAux1 : kAbaAux0)
                                                          : (algo == MB_CRBA ? (kCfg[cfg].cls ? kCrbAux1 : kCrbAux0) : (kCfg[cfg].cls ? kCorAux1 : kCorAux0)));
-      const bool spills = (long)fa.localSizeBytes > 8l * auxn + 128;
+      // (the Coriolis kernel keeps two 46-double accumulators and three force columns live: a few hundred bytes of spills are its
+      // normal state at 255 registers)
+      const bool spills = (long)fa.localSizeBytes > 8l * auxn + (algo == MB_CORIOLIS ? 512 : 128);
       // warps that do not split evenly over the four sub-partitions lose more than they bring (ABA 320 threads: 3.44 ms,
       // 256 threads: 2.23 ms; profiles/r01i_cfg_sweep.jsonl): such block sizes only compete if nothing else fits
       const bool uneven = ((nblk * b) % 128) != 0 && nblk * b > 128;
       const int score = (spills || uneven) && forced < 0 ? 1 + (uneven ? 1 : 0) : nblk * b;
-      // prefer more resident states; on ties the first configuration in the table wins
-      if (nblk > 0 && score > best_threads)
+      // prefer more resident states; on ties the first configuration in the table wins -- except for the Coriolis kernel, where
+      // more, smaller blocks win (H37: 2 x 128 threads 5.89 ms, 1 x 256 6.54 ms, profiles/r02h_cor_sweep.jsonl)
+      if (nblk > 0 && (score > best_threads || (algo == MB_CORIOLIS && score == best_threads && b < plan.block)))
       {
          best_threads = score;
          plan.block = b;
