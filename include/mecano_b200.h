@@ -141,6 +141,14 @@ const char *mecano_b200_last_error(const mecano_b200_handle *h); /* h may be NUL
 
 int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double gz);
 int mecano_b200_set_variant(mecano_b200_handle *h, int variant);
+/*
+ * Sharing the device between calculators that run at the same time on different streams (Mecano users run one calculator per
+ * thread, MultiBodySystemFactories.java:310-348; here: one per stream).  The thread-per-state RNEA and ABA kernels are persistent
+ * grids that by default fill every SM, and each of their blocks owns its SM (registers, tensor memory); max_blocks caps the
+ * grid of `algo` (MECANO_B200_ALGO_*) so that a concurrent kernel -- typically the bandwidth-bound mass matrix next to the
+ * FP64-bound forward dynamics -- finds free SMs.  0 = no cap.  Results do not depend on it.
+ */
+int mecano_b200_set_grid_limit(mecano_b200_handle *h, int algo, int max_blocks);
 
 /*
  * Compile kernels specialised for this tree (bit mask of 1 << MECANO_B200_ALGO_*).  A Mecano calculator mirrors the body

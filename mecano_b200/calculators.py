@@ -83,6 +83,12 @@ class _BatchedCalculator:
         self._engine.set_variant({"auto": 0, "thread": 1, "warp": 2}[variant] if isinstance(variant, str) else int(variant))
         return self
 
+    def setGridLimit(self, maxBlocks):
+        """Cap this calculator's persistent grid at maxBlocks blocks (one block owns one SM; 0 = whole device), so that another
+        calculator running at the same time on another stream finds free SMs (mecano_b200_set_grid_limit).  Returns self."""
+        self._engine.set_grid_limit(self._ALGO, maxBlocks)
+        return self
+
     def specialize(self, force=False):
         """Optional second half of the constructor: compile a kernel unrolled for this tree (mecano_b200_specialize).
         Trees whose unrolled code would overflow the instruction caches keep the generic kernel; kernelInfo()["specialized"]

@@ -35,6 +35,7 @@ struct mecano_b200_handle
    mb::SpecKernel spec[MB_NUM_ALGOS];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[MB_NUM_ALGOS];
+   int grid_limit[MB_NUM_ALGOS] = {0, 0, 0, 0}; // mecano_b200_set_grid_limit: cap on the persistent grids (0 = whole device)
    int variant = MECANO_B200_VARIANT_AUTO;
    int max_children = 1, max_ndof = 1, sm_count = 148;
    int n_accel_source = 0;           // joints in ACCELERATION_SOURCE mode (mecano_b200_set_joint_source_modes)
@@ -204,6 +205,13 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       const unsigned grid = (algo == MB_ABA || sk.opt.tm > 0) ? (unsigned)std::min<long long>(ntiles, sk.grid) : (unsigned)ntiles;
       a.ws_ld = (long long)sk.grid * sk.opt.block;
       MB_CUDA(h, mb::spec_launch(sk, a, grid, stream));
+      return MECANO_B200_OK;
+   }
+   if (h->grid_limit[algo] > 0 && h->grid_limit[algo] < h->plan[algo].grid)
+   {
+      mb::LaunchPlan p = h->plan[algo];
+      p.grid = h->grid_limit[algo]; // the workspace keeps one column per thread of the full grid: enough for any smaller one
+      MB_CUDA(h, mb::launch_thread_kernel(algo, h->tree.prog[algo], a, p, stream));
       return MECANO_B200_OK;
    }
    MB_CUDA(h, mb::launch_thread_kernel(algo, h->tree.prog[algo], a, h->plan[algo], stream));
@@ -506,6 +514,13 @@ int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double 
 {
    if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
    h->gravity[0] = gx; h->gravity[1] = gy; h->gravity[2] = gz;
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_set_grid_limit(mecano_b200_handle *h, int algo, int max_blocks)
+{
+   if (!h || algo < 0 || algo >= MB_NUM_ALGOS || max_blocks < 0) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   h->grid_limit[algo] = max_blocks;
    return MECANO_B200_OK;
 }
 

@@ -75,6 +75,10 @@ class Engine:
         """0 = auto (by batch size), 1 = one thread per state, 2 = one warp per state (trees of up to 32 bodies)."""
         check(lib.mecano_b200_set_variant(self._h, int(variant)), self._h)
 
+    def set_grid_limit(self, algo, max_blocks):
+        """Cap the persistent grid of one algorithm (0 = whole device): leaves SMs to kernels running concurrently on other streams."""
+        check(lib.mecano_b200_set_grid_limit(self._h, int(algo), int(max_blocks)), self._h)
+
     def specialize(self, algos=("rnea", "aba", "crba"), force=False):
         """Compile tree-specialised kernels (mecano_b200_specialize): seconds per algorithm, cached on disk.  Algorithms whose
         unrolled code would not fit the instruction caches keep the generic kernel unless force=True."""
