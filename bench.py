@@ -415,6 +415,30 @@ def main():
         extras["coriolis_matrix"] = hbm_entry(timed(lambda: cen.getCoriolisMatrix(q, qd)), 8.0 * (nq + nv + 2 * nv * nv),
                                               "getMassMatrix + getCoriolisMatrix, both dense nv x nv (mecano_b200_coriolis)")
         del cen
+        # the optional fp32 variant of the three kernels (arithmetic in float, buffers fp64), reported separately with its error
+        f32 = {}
+        M32 = torch.empty_like(M)
+        for name, calc32, run32, ref_out in (
+                ("rnea", mb.InverseDynamicsCalculator(system, device=local_rank), lambda c: c.compute(q, qd, qdd), tau),
+                ("aba", mb.ForwardDynamicsCalculator(system, device=local_rank), lambda c: c.compute(q, qd, tau_in), qdd_out),
+                ("crba", mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank), lambda c: c.getMassMatrix(q, M32), M)):
+            calc32.setKernelVariant("thread").setPrecision("fp32")
+            if name != "crba":
+                calc32.setGravitationalAcceleration(*GRAVITY)
+            ms32 = timed(lambda: run32(calc32))
+            out32 = run32(calc32)
+            # per state: max |fp32 - fp64| over the outputs of the state / max(1, max |fp64| of the state)
+            per_state = (out32 - ref_out).abs().amax(dim=0) / ref_out.abs().amax(dim=0).clamp(min=1.0)
+            srt = per_state.sort().values
+            f32[name] = {"ms": ms32, "states_per_s": n / (ms32 * 1e-3), "speedup_vs_fp64": kernels[name]["ms"] / ms32,
+                         "rel_error_vs_fp64": {"median": float(srt[n // 2]), "p99": float(srt[int(n * 0.99)]), "p99.9": float(srt[int(n * 0.999)]),
+                                               "max": float(srt[-1])}}
+            del per_state, srt
+            del calc32, out32
+        del M32
+        extras["fp32_variant"] = dict(f32, what="optional single-precision variant (mecano_b200_set_precision): arithmetic in float, all buffers fp64; "
+                                                "error per state = max |fp32 - fp64| / max(1, max |fp64|), quantiles over the batch (forward dynamics "
+                                                "in fp32 is ill-conditioned for a few random states: the tail is what it is)")
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine
     # balance (FP64 pipe), CRBA below it (HBM, write-dominated).  MEASURED_PEAKS.json has no FP64 figure, so the FP64

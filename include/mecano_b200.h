@@ -142,6 +142,16 @@ const char *mecano_b200_last_error(const mecano_b200_handle *h); /* h may be NUL
 int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double gz);
 int mecano_b200_set_variant(mecano_b200_handle *h, int variant);
 /*
+ * Optional fp32 variant.  MECANO_B200_PRECISION_FP32 makes the plain mecano_b200_rnea / aba / crba calls (device and host entry
+ * points) compute in single precision; every buffer of the ABI stays fp64.  Mecano is double precision throughout: this is a
+ * throughput option with its own, much looser tolerance (RNEA / CRBA ~1e-5 relative, ABA ~1e-3 on a 37-DoF humanoid), reported
+ * separately and never chosen implicitly.  Calls the variant does not cover (external wrenches, flags, by-products, trees
+ * outside the humanoid-sized launch configuration) fail with MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY instead of running in fp64.
+ */
+#define MECANO_B200_PRECISION_FP64 0
+#define MECANO_B200_PRECISION_FP32 1
+int mecano_b200_set_precision(mecano_b200_handle *h, int precision);
+/*
  * Sharing the device between calculators that run at the same time on different streams (Mecano users run one calculator per
  * thread, MultiBodySystemFactories.java:310-348; here: one per stream).  The thread-per-state RNEA and ABA kernels are persistent
  * grids that by default fill every SM, and each of their blocks owns its SM (registers, tensor memory); max_blocks caps the

@@ -64,7 +64,7 @@ EXPORTS = [
     "mecano_b200_rnea_full", "mecano_b200_rnea_full_host",
     "mecano_b200_set_joint_source_modes", "mecano_b200_aba_sources", "mecano_b200_aba_sources_host",
     "mecano_b200_crba_centroidal", "mecano_b200_centroidal_convective_term", "mecano_b200_crba_centroidal_host",
-    "mecano_b200_centroidal_convective_term_host", "mecano_b200_coriolis", "mecano_b200_coriolis_host", "mecano_b200_set_grid_limit",
+    "mecano_b200_centroidal_convective_term_host", "mecano_b200_coriolis", "mecano_b200_coriolis_host", "mecano_b200_set_grid_limit", "mecano_b200_set_precision",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -74,6 +74,7 @@ lib.mecano_b200_last_error.argtypes = [c_vp]
 lib.mecano_b200_last_error.restype = ctypes.c_char_p
 lib.mecano_b200_set_gravity.argtypes = [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
 lib.mecano_b200_set_variant.argtypes = [c_vp, ctypes.c_int]
+lib.mecano_b200_set_precision.argtypes = [c_vp, ctypes.c_int]
 lib.mecano_b200_set_grid_limit.argtypes = [c_vp, ctypes.c_int, ctypes.c_int]
 lib.mecano_b200_specialize.argtypes = [c_vp, c_u32]
 lib.mecano_b200_jit_check.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(c_i64)]

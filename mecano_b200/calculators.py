@@ -83,6 +83,12 @@ class _BatchedCalculator:
         self._engine.set_variant({"auto": 0, "thread": 1, "warp": 2}[variant] if isinstance(variant, str) else int(variant))
         return self
 
+    def setPrecision(self, precision):
+        """"fp64" (Mecano's, the default) or "fp32": the optional single-precision variant (arithmetic in float, matrices stay
+        float64); plain compute() / getMassMatrix() calls only, tolerance ~1e-5 (RNEA, CRBA) / ~1e-3 (ABA).  Returns self."""
+        self._engine.set_precision(precision)
+        return self
+
     def setGridLimit(self, maxBlocks):
         """Cap this calculator's persistent grid at maxBlocks blocks (one block owns one SM; 0 = whole device), so that another
         calculator running at the same time on another stream finds free SMs (mecano_b200_set_grid_limit).  Returns self."""

@@ -35,6 +35,7 @@ struct mecano_b200_handle
    mb::SpecKernel spec[MB_NUM_ALGOS];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[MB_NUM_ALGOS];
+   bool fp32 = false; // mecano_b200_set_precision
    int grid_limit[MB_NUM_ALGOS] = {0, 0, 0, 0}; // mecano_b200_set_grid_limit: cap on the persistent grids (0 = whole device)
    int variant = MECANO_B200_VARIANT_AUTO;
    int max_children = 1, max_ndof = 1, sm_count = 148;
@@ -112,10 +113,18 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "joints in ACCELERATION_SOURCE mode need their accelerations: call mecano_b200_aba_sources");
    if (h->n_accel_source == 0)
       x2 = nullptr; // nothing reads it: the plain kernels serve the call
+   if (h->fp32)
+   {
+      // the optional fp32 variant: plain calls on the thread-per-state kernels only, never a silent fp64 substitute
+      if (algo > MB_CRBA || fext || opt.body_acc || opt.joint_wrench || x2 || opt.cmm || opt.root_wrench || flags != 0)
+         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant covers plain RNEA / ABA / CRBA calls only (no external wrenches, flags, by-products)");
+      if (!h->plan[algo].fp32_ok)
+         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant is compiled for the launch configuration of humanoid-sized trees only");
+   }
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
    // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
-   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench || algo == MB_CORIOLIS;
+   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench || algo == MB_CORIOLIS || h->fp32;
    const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]));
    if (use_warp)
    {
@@ -126,6 +135,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.body_acc = wa.joint_wrench = nullptr;
       wa.x2 = nullptr;
       wa.cmm = wa.com = wa.root_wrench = wa.cor = nullptr;
+      wa.fp32 = 0;
       wa.consts = h->d_consts;
       wa.ws = nullptr;
       wa.ws_ld = 0;
@@ -165,6 +175,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.x2 = x2;
    a.cmm = opt.cmm; a.com = opt.com; a.root_wrench = opt.root_wrench;
    a.cor = opt.cor;
+   a.fp32 = h->fp32 ? 1 : 0;
    a.consts = h->d_consts;
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
@@ -514,6 +525,13 @@ int mecano_b200_set_gravity(mecano_b200_handle *h, double gx, double gy, double 
 {
    if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
    h->gravity[0] = gx; h->gravity[1] = gy; h->gravity[2] = gz;
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_set_precision(mecano_b200_handle *h, int precision)
+{
+   if (!h || (precision != MECANO_B200_PRECISION_FP64 && precision != MECANO_B200_PRECISION_FP32)) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   h->fp32 = precision == MECANO_B200_PRECISION_FP32;
    return MECANO_B200_OK;
 }
 

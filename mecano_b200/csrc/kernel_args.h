@@ -16,6 +16,7 @@ struct KernelArgs
                                     // com rows 0..3 accumulate (mass * CoM, mass) over the root's children (zeroed before the launch)
    double *cor;                     // MB_CORIOLIS: the Coriolis matrix, entry-major like the mass matrix in `out`
    double *root_wrench;             // RNEA by-product (nullable): rows 0..5 accumulate the wrench at the root in the root frame (zeroed before)
+   int fp32;                        // optional fp32 variant (mecano_b200_set_precision): arithmetic in float, buffers stay fp64
    const double *consts;            // device copy of the per-body constant records
    double *ws;                      // ABA: pass-two records [rec][ws_ld], one column per resident thread of the persistent grid
    long long ws_ld;

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <type_traits>
 
+#include "f32_ctx.cuh"
 #include "gpu_ctx.cuh"
 #include "kernels.h"
 
@@ -41,6 +42,28 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
          crba_state<double, Ctx, FEXT>(P, c2);
       else
          coriolis_state<double, Ctx>(P, c2);
+   });
+}
+
+// The optional fp32 variant (f32_ctx.cuh): same skeleton, constant records staged as floats, the per-state routines instantiated
+// with T = float.  Plain calls only (no external wrenches / by-products), one launch configuration per algorithm.
+template <int ALGO, int BLOCK, int AUXN, int RECN, int TM>
+__global__ void __launch_bounds__(BLOCK) thread_kernel_f32(const __grid_constant__ MbProgram P, const KernelArgs a)
+{
+   const int ncst = P.nb * MB_CONST_STRIDE;
+   float *cf = reinterpret_cast<float *>(mb_smem);
+   for (int i = threadIdx.x; i < ncst; i += BLOCK)
+      cf[i] = (float)a.consts[i];
+   using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
+   const float grav[3] = {(float)a.grav[0], (float)a.grav[1], (float)a.grav[2]};
+   thread_block_run<ALGO, false, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), P.nstack2, [&](Ctx &c2) {
+      F32Ctx<Ctx> f(c2);
+      if constexpr (ALGO == MB_RNEA)
+         rnea_state<float, F32Ctx<Ctx>, false>(P, f, grav);
+      else if constexpr (ALGO == MB_ABA)
+         aba_state<float, F32Ctx<Ctx>, false>(P, f, grav);
+      else
+         crba_state<float, F32Ctx<Ctx>, false>(P, f);
    });
 }
 
@@ -88,6 +111,15 @@ KernelFn pick(int algo, bool fext, bool state_major, int cfg)
    // CRBA: the "FEXT" instantiation is the one with by-products (centroidal momentum matrix, centre of mass), entry-major only
    if (fext && !state_major) return pick_cfg<MB_CRBA, true, false>(cfg);
    return state_major ? pick_cfg<MB_CRBA, false, true>(cfg) : pick_cfg<MB_CRBA, false, false>(cfg);
+}
+
+// fp32 variant: the one configuration per algorithm that the planner picks for humanoid-sized trees (kCfg index, class 0)
+constexpr int kF32Cfg[3] = {0, 1, 6}; // RNEA 512 threads + TMEM, ABA 384 threads + TMEM, CRBA 256 threads
+KernelFn pick_f32(int algo)
+{
+   if (algo == MB_RNEA) return thread_kernel_f32<MB_RNEA, kCfg[kF32Cfg[0]].block, kRnaAux0, 0, kCfg[kF32Cfg[0]].tm>;
+   if (algo == MB_ABA) return thread_kernel_f32<MB_ABA, kCfg[kF32Cfg[1]].block, kAbaAux0, kAbaRec0, kCfg[kF32Cfg[1]].tm>;
+   return thread_kernel_f32<MB_CRBA, kCfg[kF32Cfg[2]].block, kCrbAux0, 0, 0>;
 }
 
 int class_of(int algo, const MbProgram &P)
@@ -208,6 +240,17 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    plan.regs = attr.numRegs;
    plan.local_bytes = (int)attr.localSizeBytes;
    plan.static_smem = (int)attr.sharedSizeBytes;
+   // the fp32 variant exists for the configuration the planner picks for humanoid-sized trees
+   plan.fp32_ok = algo <= MB_CRBA && plan.size_class == kF32Cfg[algo];
+   if (plan.fp32_ok)
+   {
+      cudaFuncAttributes fa32;
+      e = cudaFuncGetAttributes(&fa32, (const void *)pick_f32(algo));
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute((const void *)pick_f32(algo), cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - (int)fa32.sharedSizeBytes);
+      if (e != cudaSuccess) return e;
+      plan.fp32_regs = fa32.numRegs;
+   }
    *fits = true;
    return cudaSuccess;
 }
@@ -217,6 +260,16 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    if (a.n <= 0)
       return cudaSuccess;
    const bool state_major = algo == MB_CRBA && (a.flags & 1u);
+   if (a.fp32)
+   {
+      // api.cu checked plan.fp32_ok and that the call has no optional buffers
+      const long long nt = (a.n + plan.block - 1) / plan.block;
+      const unsigned g = (algo == MB_ABA || plan.tm > 0) ? (unsigned)std::min<long long>(nt, plan.grid) : (unsigned)nt;
+      KernelArgs b = a;
+      b.ws_ld = (long long)plan.grid * plan.block;
+      pick_f32(algo)<<<g, plan.block, plan.smem, stream>>>(P, b);
+      return cudaGetLastError();
+   }
    KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, state_major, plan.size_class);
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so

@@ -22,6 +22,8 @@ struct LaunchPlan
    int static_smem = 0;
    int grid = 0;         // persistent grid: resident blocks on the whole device
    size_t ws_doubles = 0; // ABA workspace size for that grid
+   bool fp32_ok = false;  // the optional fp32 variant exists for this configuration
+   int fp32_regs = 0;
 };
 
 // Picks the block size / size class for one algorithm and opts the kernel into large shared memory.

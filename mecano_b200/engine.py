@@ -75,6 +75,10 @@ class Engine:
         """0 = auto (by batch size), 1 = one thread per state, 2 = one warp per state (trees of up to 32 bodies)."""
         check(lib.mecano_b200_set_variant(self._h, int(variant)), self._h)
 
+    def set_precision(self, precision):
+        """"fp64" (default) or "fp32": the optional single-precision variant of the plain RNEA / ABA / CRBA calls."""
+        check(lib.mecano_b200_set_precision(self._h, {"fp64": 0, "fp32": 1}[precision]), self._h)
+
     def set_grid_limit(self, algo, max_blocks):
         """Cap the persistent grid of one algorithm (0 = whole device): leaves SMs to kernels running concurrently on other streams."""
         check(lib.mecano_b200_set_grid_limit(self._h, int(algo), int(max_blocks)), self._h)

@@ -590,3 +590,52 @@ def test_coriolis_matrix(torch_dev, idx):
     hc = mb.CompositeRigidBodyMassMatrixCalculator(s)
     hc.setEnableCoriolisMatrixCalculation(True)
     assert rel(hc.getCoriolisMatrix(q, qd).reshape(nv, nv, n), C) == 0.0 and rel(hc.getMassMatrix().reshape(nv, nv, n), M) == 0.0, name
+
+
+def test_fp32_variant(torch_dev):
+    """The optional fp32 variant (mecano_b200_set_precision): reported separately with its own tolerance (north star), never
+    chosen implicitly, and refusing what it does not cover instead of running in fp64."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="humanoid", seed=7, n_joints=2)
+    rng = np.random.default_rng(8000)
+    o = ol.Oracle(t, gravity=(0.0, 0.0, -9.81))
+    n = 3000
+    nv = t.nv
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    tq, tqd, tqdd, ttau = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, tau))
+    ident = mb.InverseDynamicsCalculator(s).setKernelVariant("thread").setPrecision("fp32")
+    ident.setGravitationalAcceleration(-9.81)
+    fdyn = mb.ForwardDynamicsCalculator(s).setKernelVariant("thread").setPrecision("fp32")
+    fdyn.setGravitationalAcceleration(-9.81)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant("thread").setPrecision("fp32")
+    e_rnea = rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd))
+    e_aba = rel(fdyn.compute(tq, tqd, ttau).cpu().numpy(), o.aba_batch(q, qd, tau))
+    M = crba.getMassMatrix(tq, torch.full((nv * nv, n), float("nan"), dtype=torch.float64, device=dev))
+    assert not torch.isnan(M).any()
+    e_crba = rel(M.cpu().numpy().reshape(nv, nv, n), o.crba_batch(q))
+    print("fp32 variant, H37, relative to the oracle: rnea %.2e aba %.2e crba %.2e" % (e_rnea, e_aba, e_crba))
+    assert 1e-9 < e_rnea < 2e-4, "fp32 arithmetic must actually run (and stay within its tolerance)"
+    assert 1e-9 < e_crba < 2e-4
+    assert 1e-9 < e_aba < 5e-2
+    # host entry points run the same kernels
+    assert rel(ident.compute(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < 2e-4
+    # not covered: external wrenches, flags, by-products, trees outside the compiled configuration -> an error, not fp64
+    ident.setExternalWrenches(torch.zeros((6 * t.nb, n), dtype=torch.float64, device=dev))
+    with pytest.raises(mb.MecanoB200Error):
+        ident.compute(tq, tqd, tqdd)
+    ident.setExternalWrenchesToZero()
+    ident.setConsiderJointAccelerations(False)
+    with pytest.raises(mb.MecanoB200Error):
+        ident.compute(tq, tqd, tqdd)
+    big, _ = build(kind="tree", seed=9, n_joints=100, floating=True)
+    qb, qdb, qddb, _ = mb.MultiBodySystemRandomTools.nextState(rng, big, 64)
+    with pytest.raises(mb.MecanoB200Error):
+        mb.InverseDynamicsCalculator(big).setKernelVariant("thread").setPrecision("fp32").compute(*(torch.from_numpy(x).to(dev) for x in (qb, qdb, qddb)))
+    # back to fp64: bit-identical to a calculator that never left it
+    ident.setConsiderJointAccelerations(True)
+    ident.setPrecision("fp64")
+    ref = mb.InverseDynamicsCalculator(s).setKernelVariant("thread")
+    ref.setGravitationalAcceleration(-9.81)
+    assert torch.equal(ident.compute(tq, tqd, tqdd), ref.compute(tq, tqd, tqdd))
