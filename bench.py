@@ -197,6 +197,29 @@ def owned_zero_entries(system):
 _JSON_FD = None
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal CPU affinity) before any pinned host buffer is allocated, so
+    that the end-to-end path's staging memory is first touched on the GPU's own NUMA node: with several ranks on a two-socket
+    box the host <-> device copies otherwise cross the socket interconnect.  Returns the number of CPUs bound to, or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def claim_stdout():
     """stdout carries the one JSON line and nothing else: libraries that chat on file descriptor 1 (NCCL prints its version
     there) are sent to stderr for the duration of the run, and the line itself goes to the original descriptor."""
@@ -236,6 +259,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # N = 1 keeps every host core for the CPU baseline
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -472,7 +496,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.neck, n), "states_per_gpu": n, "n_dofs": nv, "n_cfg": nq, "n_bodies": nb,
-                       "parallelism": "disjoint state slices per GPU, no collective", "l2": "inputs (%.2f GB/step) and outputs larger than L2; no explicit flush"
+                       "parallelism": "disjoint state slices per GPU, no collective", "cpus_bound_per_rank": numa, "l2": "inputs (%.2f GB/step) and outputs larger than L2; no explicit flush"
                        % (8.0 * (3 * nq + 4 * nv) * n / 1e9), "humanoid_seed": HUMANOID_SEED, "mass_matrix_layout": "entry-major [nv*nv][N]"},
             "roofline": roofline, "kernels": kernels, "extras": extras, "gpu_launches": 3 * args.steps, "clocks": clocks,
         }
