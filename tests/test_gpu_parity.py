@@ -639,3 +639,45 @@ def test_fp32_variant(torch_dev):
     ref = mb.InverseDynamicsCalculator(s).setKernelVariant("thread")
     ref.setGravitationalAcceleration(-9.81)
     assert torch.equal(ident.compute(tq, tqd, tqdd), ref.compute(tq, tqd, tqdd))
+
+
+def test_new_entry_points_with_leading_dimension(torch_dev):
+    """The by-product / source-mode / centroidal / Coriolis entry points on matrices with ld > n (views of wider buffers) and a
+    ragged n: same results as on compact matrices."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="tree", seed=31, n_joints=18, floating=True, prismatic=0.3)
+    rng = np.random.default_rng(31)
+    n, ld = 1237, 1536
+    q, qd, qdd, tau = (torch.from_numpy(x).to(dev) for x in mb.MultiBodySystemRandomTools.nextState(rng, s, ld))
+    wide = lambda x: x[:, :n]  # noqa: E731  (stride ld)
+    compact = lambda x: x[:, :n].contiguous()  # noqa: E731
+
+    def run(view):
+        out = []
+        ident = mb.InverseDynamicsCalculator(s).setComputeByProducts()
+        ident.setGravitationalAcceleration(-9.81)
+        out.append(ident.compute(view(q), view(qd), view(qdd)))
+        out.append(ident.getBodyAccelerationMatrix())
+        out.append(ident.getComputedJointWrenchMatrix())
+        fdyn = mb.ForwardDynamicsCalculator(s)
+        fdyn.setGravitationalAcceleration(-9.81)
+        joints = s.getAllJoints()
+        fdyn.setJointSourceModes(lambda j: mb.JointSourceMode.ACCELERATION_SOURCE if joints.index(j) % 3 == 0 else None)
+        out.append(fdyn.compute(view(q), view(qd), view(tau), jointAccelerationInput=view(qdd)))
+        out.append(fdyn.getJointTauMatrix())
+        crba = mb.CompositeRigidBodyMassMatrixCalculator(s, "centerOfMassFrame")
+        out.append(crba.getCentroidalMomentumMatrix(view(q)))
+        out.append(crba.getCenterOfMass())
+        out.append(crba.getCentroidalConvectiveTermMatrix(view(q), view(qd)))
+        crba.setEnableCoriolisMatrixCalculation(True)
+        out.append(crba.getCoriolisMatrix(view(q), view(qd)))
+        out.append(crba.getMassMatrix())
+        return out
+
+    a, b = run(wide), run(compact)
+    for x, y in zip(a, b):
+        assert x.shape == y.shape and x.shape[1] == n
+        assert torch.equal(x, y)
+    assert a[0].stride(0) == ld and b[0].stride(0) == n
