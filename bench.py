@@ -443,9 +443,9 @@ def main():
         f32 = {}
         M32 = torch.empty_like(M)
         for name, calc32, run32, ref_out in (
-                ("rnea", mb.InverseDynamicsCalculator(system, device=local_rank), lambda c: c.compute(q, qd, qdd), tau),
-                ("aba", mb.ForwardDynamicsCalculator(system, device=local_rank), lambda c: c.compute(q, qd, tau_in), qdd_out),
-                ("crba", mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank), lambda c: c.getMassMatrix(q, M32), M)):
+                ("rnea", mb.InverseDynamicsCalculator(system, device=local_rank), lambda c: c.compute(q, qd, qdd), ident.compute(q, qd, qdd)),
+                ("aba", mb.ForwardDynamicsCalculator(system, device=local_rank), lambda c: c.compute(q, qd, tau_in), fdyn.compute(q, qd, tau_in)),
+                ("crba", mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank), lambda c: c.getMassMatrix(q, M32), crba.getMassMatrix(q, M))):
             calc32.setKernelVariant("thread").setPrecision("fp32")
             if name != "crba":
                 calc32.setGravitationalAcceleration(*GRAVITY)

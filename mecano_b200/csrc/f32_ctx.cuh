@@ -1,14 +1,20 @@
 // f32_ctx.cuh -- the optional fp32 variant (north star: "an optional fp32 variant is reported separately with its stated
 // tolerance"): the same per-state routines instantiated with T = float over a float view of the fp64 context.
 //
-// What changes: the arithmetic (FP32 pipe: twice the lanes of the FP64 pipe, half the registers per value) and the constant
-// records, staged in shared memory as floats.  What does not: the C ABI and the buffers in HBM stay fp64 (q, qd, tau, M ...
-// are converted at the load / store), and so do the per-state stack (TMEM / shared memory), the save area and the ABA
-// records, whose accessors convert on the way -- a handful of F2F per op against a few hundred FFMA.
+// What changes: the arithmetic (FP32 pipe: twice the lanes of the FP64 pipe, half the registers per value), the constant
+// records (staged in shared memory as floats) and the per-state stack, which holds floats in the cells of the fp64 layout
+// (shared memory: the low half of each double2; tensor memory: six of the twelve columns of a wide slot), so the stack
+// traffic needs no conversion.  What does not: the C ABI and the buffers in HBM stay fp64 (q, qd, tau, M ... are converted at
+// the load / store), and so do the branch save area and the ABA records, whose accessors convert on the way.
 // Accuracy (tests/test_gpu_parity.py::test_fp32_variant): RNEA / CRBA ~1e-5 relative, ABA ~1e-3 on the test trees (the
 // articulated-inertia recursion amplifies rounding with depth); tolerances 2e-4 / 2e-4 / 5e-2 as in the emulation test.
 #pragma once
 #include "gpu_ctx.cuh"
+
+// 1: the per-state stack holds floats (no conversion at the access); 0: it holds doubles, converted at the access
+#ifndef MB_F32_NATIVE_STACK
+#define MB_F32_NATIVE_STACK 1
+#endif
 
 namespace mb
 {
@@ -45,7 +51,63 @@ template <class Ctx> struct F32Ctx
    __device__ __forceinline__ void st_cmm(int, float) {}
    __device__ __forceinline__ void add_com(int, float) {}
    __device__ __forceinline__ void add_rootw(int, float) {}
-   // ---- per-state stack, save area, records: fp64 storage
+#if MB_F32_NATIVE_STACK
+   // ---- per-state stack: floats in the cells of the fp64 layout (same addresses, half of each cell used)
+   static constexpr int BLOCK = Ctx::kBlock, TM = Ctx::kTM;
+   static_assert(!Ctx::kPartial, "the fp32 variant is not compiled for the partial-TMEM block size");
+   static __device__ __forceinline__ void lds2f(unsigned addr, float &a, float &b) { asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr)); }
+   static __device__ __forceinline__ void sts2f(unsigned addr, float a, float b) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b)); }
+   __device__ __forceinline__ void stk_ld2(int slot2, int j, float &a, float &b) const { lds2f(c.sb + (unsigned)((slot2 + j) * (BLOCK * 16)), a, b); }
+   __device__ __forceinline__ void stk_st2(int slot2, int j, float a, float b) { sts2f(c.sb + (unsigned)((slot2 + j) * (BLOCK * 16)), a, b); }
+   __device__ __forceinline__ void acc_ld(int slot2, int wslot, float &x0, float &x1, float &x2, float &x3, float &x4, float &x5) const
+   {
+      if (TM > 0)
+      {
+         const unsigned t = c.tm0 + 4u * (unsigned)wslot;
+         unsigned r[6];
+#pragma unroll
+         for (int i = 0; i < 3; i++)
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[2 * i]), "=r"(r[2 * i + 1]) : "r"(t + 2u * i));
+         asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]));
+         x0 = __uint_as_float(r[0]); x1 = __uint_as_float(r[1]); x2 = __uint_as_float(r[2]);
+         x3 = __uint_as_float(r[3]); x4 = __uint_as_float(r[4]); x5 = __uint_as_float(r[5]);
+      }
+      else
+      {
+         const unsigned t = c.sb + (unsigned)(slot2 * (BLOCK * 16));
+         lds2f(t, x0, x1);
+         lds2f(t + BLOCK * 16, x2, x3);
+         lds2f(t + 2 * BLOCK * 16, x4, x5);
+      }
+   }
+   __device__ __forceinline__ void acc_st(int slot2, int wslot, float x0, float x1, float x2, float x3, float x4, float x5)
+   {
+      if (TM > 0)
+      {
+         const unsigned t = c.tm0 + 4u * (unsigned)wslot;
+         const float x[6] = {x0, x1, x2, x3, x4, x5};
+#pragma unroll
+         for (int i = 0; i < 3; i++)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(t + 2u * i), "r"(__float_as_uint(x[2 * i])), "r"(__float_as_uint(x[2 * i + 1])));
+      }
+      else
+      {
+         const unsigned t = c.sb + (unsigned)(slot2 * (BLOCK * 16));
+         sts2f(t, x0, x1);
+         sts2f(t + BLOCK * 16, x2, x3);
+         sts2f(t + 2 * BLOCK * 16, x4, x5);
+      }
+   }
+   __device__ __forceinline__ void jp_ld2(int slot2, int nslot, int j, float &a, float &b) const
+   {
+      lds2f(c.sb + (unsigned)((TM > 0 ? nslot + j : slot2 + 3 + j) * (BLOCK * 16)), a, b);
+   }
+   __device__ __forceinline__ void jp_st2(int slot2, int nslot, int j, float a, float b)
+   {
+      sts2f(c.sb + (unsigned)((TM > 0 ? nslot + j : slot2 + 3 + j) * (BLOCK * 16)), a, b);
+   }
+#else
+   // ---- per-state stack: fp64 storage, converted at the access
    __device__ __forceinline__ void stk_ld2(int slot2, int j, float &a, float &b) const
    {
       double x, y;
@@ -70,6 +132,8 @@ template <class Ctx> struct F32Ctx
       a = (float)x; b = (float)y;
    }
    __device__ __forceinline__ void jp_st2(int slot2, int nslot, int j, float a, float b) { c.jp_st2(slot2, nslot, j, (double)a, (double)b); }
+#endif
+   // ---- save area, records: fp64 storage, converted at the access
    __device__ __forceinline__ float aux_ld(int i) const { return (float)c.aux_ld(i); }
    __device__ __forceinline__ void aux_st(int i, float v) { c.aux_st(i, (double)v); }
    __device__ __forceinline__ void rec_st2(int i2, float a, float b) { c.rec_st2(i2, (double)a, (double)b); }

@@ -83,6 +83,7 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    unsigned cb;  // shared address of the constant records
    unsigned tm0; // TMEM address (lane quarter << 16 | first column) of wide slot 0 of this warp
    unsigned wov; // kPartial: shared address such that wide slot w >= TM lives at wov + w * BLOCK * 16
+   static constexpr int kBlock = BLOCK, kTM = TM;
    static constexpr bool kPartial = TM > 0 && BLOCK == MB_PARTIAL_TM_BLOCK;
    // warp-collective tcgen05.ld/st and the block barriers of specialised kernels need every thread to run every op: the
    // padding lanes of the last tile run the last state again and store the same values to the same addresses
