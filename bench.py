@@ -461,8 +461,7 @@ def main():
             del calc32, out32
         del M32
         extras["fp32_variant"] = dict(f32, what="optional single-precision variant (mecano_b200_set_precision): arithmetic in float, all buffers fp64; "
-                                                "error per state = max |fp32 - fp64| / max(1, max |fp64|), quantiles over the batch (forward dynamics "
-                                                "in fp32 is ill-conditioned for a few random states: the tail is what it is)")
+                                                "error per state = max |fp32 - fp64| / max(1, max |fp64|), quantiles over the batch")
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine
     # balance (FP64 pipe), CRBA below it (HBM, write-dominated).  MEASURED_PEAKS.json has no FP64 figure, so the FP64
