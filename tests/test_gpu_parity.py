@@ -681,3 +681,72 @@ def test_new_entry_points_with_leading_dimension(torch_dev):
         assert x.shape == y.shape and x.shape[1] == n
         assert torch.equal(x, y)
     assert a[0].stride(0) == ld and b[0].stride(0) == n
+
+
+def test_humanoid_1m_states_invariants_of_the_next_rows(torch_dev):
+    """The SURVEY 8f rows at BASELINE.json's full size (H37, 2^20 states), through size-independent properties checked on the
+    device: forward dynamics with half of the joints locked returns the accelerations and efforts of inverse dynamics
+    (ForwardDynamicsCalculatorTest.java:389-488); C(q, qd) qd = inverse dynamics without joint accelerations
+    (CompositeRigidBodyMassMatrixCalculatorTest.java:85-138); the linear rows of A qdd + Adot qd = the force the floating joint
+    transmits, rotated into the world (Newton's law for the whole system, :62-82); the joint wrench of the floating joint
+    projects onto its six efforts."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="humanoid", seed=98, n_joints=2)
+    nv, nq, n = t.nv, t.nq, 1 << 20
+    gen = torch.Generator(device=dev).manual_seed(6)
+    q = (torch.rand((nq, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * np.pi
+    quat = torch.randn((4, n), dtype=torch.float64, device=dev, generator=gen)
+    q[0:4] = quat / quat.norm(dim=0, keepdim=True)
+    q[4:7] = torch.rand((3, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qdd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+
+    def worst(actual, expected):
+        sc = torch.clamp(expected.abs().amax(dim=0), min=1.0)
+        return float(((actual - expected).abs().amax(dim=0) / sc).max())
+
+    # ---- mixed joint source modes
+    ident = mb.InverseDynamicsCalculator(s).setComputeByProducts(bodyAccelerations=False)
+    ident.setGravitationalAcceleration(-9.81)
+    tau = ident.compute(q, qd, qdd)
+    wr = ident.getComputedJointWrenchMatrix()
+    assert worst(wr[0:6], tau[0:6]) < 1e-12, "SixDoF joint: S = identity, the efforts are the joint wrench"
+    joints = s.getAllJoints()
+    locked_rows = [i for i, j in enumerate(joints) if j.getDegreesOfFreedom() == 1 and i % 2 == 0]
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    fdyn.setGravitationalAcceleration(-9.81)
+    fdyn.setJointSourceModes(lambda j: mb.JointSourceMode.ACCELERATION_SOURCE if joints.index(j) in locked_rows else None)
+    tau_in = tau.clone()
+    for i in locked_rows:
+        tau_in[t.dof_off[i]] = float("nan")
+    back = fdyn.compute(q, qd, tau_in, jointAccelerationInput=qdd)
+    assert worst(back, qdd) < 1e-9
+    assert worst(fdyn.getJointTauMatrix(), tau) < 1e-9
+    del back, tau_in, wr
+    # ---- centroidal quantities, world frame: total force = R_pelvis * (force rows of the floating joint's efforts), gravity off
+    ident0 = mb.InverseDynamicsCalculator(s)
+    tau0 = ident0.compute(q, qd, qdd)
+    cen = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    A = cen.getCentroidalMomentumMatrix(q).reshape(6, nv, n)
+    b = cen.getCentroidalConvectiveTermMatrix(q, qd)
+    hdot_lin = torch.einsum("rjs,js->rs", A[3:], qdd) + b[3:]
+    x, y, z, w = q[0], q[1], q[2], q[3]
+    R = torch.stack([torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)]),
+                     torch.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)]),
+                     torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)])])  # [3, 3, n]
+    force_world = torch.einsum("ijs,js->is", R, tau0[3:6])
+    assert worst(hdot_lin, force_world) < 1e-9
+    mass = cen.getCenterOfMass()[3]
+    assert float((mass - mass[0]).abs().max()) < 1e-12 * float(mass[0]), "the total mass does not depend on the state"
+    del A, b, hdot_lin, R, force_world
+    # ---- Coriolis matrix, in chunks to bound memory
+    ident0.setConsiderJointAccelerations(False)
+    want = ident0.compute(q, qd, qdd)
+    cen.setEnableCoriolisMatrixCalculation(True)
+    chunk = 1 << 17
+    for a in range(0, n, chunk):
+        C = cen.getCoriolisMatrix(q[:, a:a + chunk].contiguous(), qd[:, a:a + chunk].contiguous()).reshape(nv, nv, -1)
+        got = torch.einsum("ijs,js->is", C, qd[:, a:a + chunk])
+        assert worst(got, want[:, a:a + chunk]) < 1e-9
