@@ -191,3 +191,55 @@ def test_golden_fixtures():
         assert np.allclose(o.rnea_batch(q, qd, qdd, fext), data[name + "/rnea"], rtol=0, atol=1e-11)
         assert np.allclose(o.aba_batch(q, qd, tau, fext), data[name + "/aba"], rtol=0, atol=1e-10)
         assert np.allclose(o.crba_batch(q), data[name + "/crba"], rtol=0, atol=1e-11)
+
+
+def _planar_two_link(l1, lc1, lc2, m1, m2, i1, i2):
+    """Textbook planar two-link arm (Spong, Hutchinson, Vidyasagar, Robot Modeling and Control, eq. 7.80-7.88): both joints
+    revolute about +z, link 1 along its x axis with length l1, CoMs at lc1 / lc2 along x, gravity along -y."""
+    eye = np.eye(3)
+    return td.TreeDesc(
+        nb=2, nv=2, nq=2, parent=np.array([-1, 0], np.int32), jtype=np.array([td.REVOLUTE, td.REVOLUTE], np.int32),
+        axis=np.array([[0.0, 0.0, 1.0], [0.0, 0.0, 1.0]]), off_R=np.stack([eye, eye]), off_p=np.array([[0.0, 0.0, 0.0], [l1, 0.0, 0.0]]),
+        com_R=np.stack([eye, eye]), com_p=np.array([[lc1, 0.0, 0.0], [lc2, 0.0, 0.0]]),
+        J=np.stack([np.diag([0.01, 0.02, i1]), np.diag([0.03, 0.04, i2])]), mass=np.array([m1, m2]),
+        dof_off=np.array([0, 1], np.int32), cfg_off=np.array([0, 1], np.int32)).contiguous()
+
+
+def test_closed_form_planar_two_link_arm():
+    """Physics pin that depends on neither the reference nor a second recursive formulation: the closed-form equations of motion
+    of the planar two-link arm, M(q) qdd + C(q, qd) qd + g(q) = tau, against the oracle's RNEA, CRBA, Coriolis matrix and ABA."""
+    rng = np.random.default_rng(77)
+    l1, lc1, lc2, m1, m2, i1, i2, g = 0.9, 0.4, 0.35, 2.0, 1.5, 0.11, 0.07, 9.81
+    t = _planar_two_link(l1, lc1, lc2, m1, m2, i1, i2)
+    o = ol.Oracle(t, gravity=(0.0, -g, 0.0))
+    o0 = ol.Oracle(t, gravity=(0.0, 0.0, 0.0))
+    for _ in range(20):
+        q, qd, qdd = rng.uniform(-np.pi, np.pi, 2), rng.uniform(-2, 2, 2), rng.uniform(-3, 3, 2)
+        c2, s2 = np.cos(q[1]), np.sin(q[1])
+        d11 = m1 * lc1 ** 2 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2) + i1 + i2
+        d12 = m2 * (lc2 ** 2 + l1 * lc2 * c2) + i2
+        d22 = m2 * lc2 ** 2 + i2
+        M = np.array([[d11, d12], [d12, d22]])
+        h = -m2 * l1 * lc2 * s2
+        C = np.array([[h * qd[1], h * (qd[0] + qd[1])], [-h * qd[0], 0.0]])
+        grav = np.array([(m1 * lc1 + m2 * l1) * g * np.cos(q[0]) + m2 * lc2 * g * np.cos(q[0] + q[1]), m2 * lc2 * g * np.cos(q[0] + q[1])])
+        tau = M @ qdd + C @ qd + grav
+        assert np.allclose(o.crba(q), M, rtol=0, atol=1e-13)
+        assert np.allclose(o.rnea(q, qd, qdd), tau, rtol=0, atol=1e-12)
+        assert np.allclose(o.aba(q, qd, tau), qdd, rtol=0, atol=1e-11)
+        # the Coriolis matrix is not unique, its product with qd is (and Mecano's factorization also satisfies dM/dt = C + C^T)
+        _, Co = o0.coriolis(q, qd)
+        assert np.allclose(Co @ qd, C @ qd, rtol=0, atol=1e-12)
+        Mdot = np.array([[2 * h * qd[1], h * qd[1]], [h * qd[1], 0.0]])
+        assert np.allclose(Co + Co.T, Mdot, rtol=0, atol=1e-12)
+        # momentum of the system about the base origin, z component = row 2 of the centroidal momentum matrix in the world frame
+        _, A, com, mass = o0.crba_centroidal(q, 0)
+        assert abs(mass - (m1 + m2)) < 1e-14
+        p1 = lc1 * np.array([np.cos(q[0]), np.sin(q[0])])
+        p2 = l1 * np.array([np.cos(q[0]), np.sin(q[0])]) + lc2 * np.array([np.cos(q[0] + q[1]), np.sin(q[0] + q[1])])
+        assert np.allclose(com[:2], (m1 * p1 + m2 * p2) / (m1 + m2), atol=1e-13)
+        v1 = lc1 * qd[0] * np.array([-np.sin(q[0]), np.cos(q[0])])
+        v2 = l1 * qd[0] * np.array([-np.sin(q[0]), np.cos(q[0])]) + lc2 * (qd[0] + qd[1]) * np.array([-np.sin(q[0] + q[1]), np.cos(q[0] + q[1])])
+        Lz = i1 * qd[0] + i2 * (qd[0] + qd[1]) + m1 * (p1[0] * v1[1] - p1[1] * v1[0]) + m2 * (p2[0] * v2[1] - p2[1] * v2[0])
+        hq = A @ qd
+        assert abs(hq[2] - Lz) < 1e-12 and np.allclose(hq[3:5], m1 * v1 + m2 * v2, atol=1e-12)
