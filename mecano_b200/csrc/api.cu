@@ -456,6 +456,11 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
    {
       bool fits = false;
       if ((e = mb::plan_thread_kernel(algo, h->tree.prog[algo], false, h->plan[algo], &fits)) != cudaSuccess) return bail(e, "kernel planning");
+      if (!fits && algo == MB_CORIOLIS)
+      {
+         h->plan[algo].block = 0; // the by-product kernel alone does not fit: mecano_b200_coriolis reports it, everything else works
+         continue;
+      }
       if (!fits)
       {
          cudaFree(h->d_consts);
@@ -746,6 +751,8 @@ int mecano_b200_coriolis(mecano_b200_handle *h, int64_t n, int64_t ld, const dou
    if (rc) return rc;
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !M || !C) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   if (h->plan[MB_CORIOLIS].block == 0)
+      return fail(h, MECANO_B200_ERR_TOO_LARGE, "tree exceeds the per-state work areas of the Coriolis-matrix kernel (branch nesting / depth too large)");
    MB_CUDA(h, cudaSetDevice(h->device));
    RunOpts opt;
    opt.cor = C;
