@@ -220,3 +220,25 @@ def test_jvm_exchange_file_round_trip(tmp_path, capsys):
     capsys.readouterr()
     jx.compare(x, r)
     assert '"pass": true' in capsys.readouterr().out
+
+
+def test_new_entry_points_reject_a_null_handle():
+    """Every entry point added for the SURVEY 8f rows returns MECANO_B200_ERR_INVALID_ARGUMENT for a NULL handle instead of
+    crashing (no GPU needed)."""
+    lib = _capi.lib
+    n, ld = ctypes.c_int64(4), ctypes.c_int64(4)
+    null = ctypes.c_void_p(None)
+    bad = -1  # MECANO_B200_ERR_INVALID_ARGUMENT
+    assert lib.mecano_b200_rnea_full(null, n, ld, null, null, null, null, null, null, null, 0, null) == bad
+    assert lib.mecano_b200_rnea_full_host(null, n, ld, null, null, null, null, null, null, null, 0) == bad
+    assert lib.mecano_b200_set_joint_source_modes(null, null) == bad
+    assert lib.mecano_b200_aba_sources(null, n, ld, null, null, null, null, null, null, null, null) == bad
+    assert lib.mecano_b200_aba_sources_host(null, n, ld, null, null, null, null, null, null, null) == bad
+    assert lib.mecano_b200_crba_centroidal(null, n, ld, null, null, null, null, 0, null) == bad
+    assert lib.mecano_b200_crba_centroidal_host(null, n, ld, null, null, null, null, 0) == bad
+    assert lib.mecano_b200_centroidal_convective_term(null, n, ld, null, null, null, null, 0, null) == bad
+    assert lib.mecano_b200_centroidal_convective_term_host(null, n, ld, null, null, null, null, 0) == bad
+    assert lib.mecano_b200_coriolis(null, n, ld, null, null, null, null, null) == bad
+    assert lib.mecano_b200_coriolis_host(null, n, ld, null, null, null, null) == bad
+    assert lib.mecano_b200_set_precision(null, 1) == bad
+    assert lib.mecano_b200_set_grid_limit(null, 0, 10) == bad
