@@ -13,7 +13,9 @@ Per-GPU work is fixed (weak scaling); ranks own disjoint slices and there is no 
 Rank 0 prints ONE JSON line (see the task contract): metric/value/unit/..., `roofline` for the dominant kernel
 (CRBA, HBM-bound) plus per-kernel details under `kernels`, `cpu_baseline` (the C oracle port timed on the host
 cores on a bounded sample), `e2e` (the same step through the host-pointer C-ABI entry points: pinned host buffers,
-H2D + kernels + D2H inside the timed region) and `clocks`.
+H2D + kernels + D2H inside the timed region) and `clocks`.  `extras` (rank 0, outside the timed step; `--no-extras` skips
+them) times the rows next to the path: state integrator, calculator-owned mass matrix, RNEA by-products, forward dynamics with
+joint source modes, centroidal momentum matrix / convective term, Coriolis matrix, and the optional fp32 variant with its error.
 
 `--impl reference`: Mecano itself is Java and no JVM exists on these boxes, so the reference arm
 times the reference-faithful C restatement (oracle/, "port") multithreaded on all host cores.
