@@ -162,6 +162,13 @@ class InverseDynamicsCalculator(_BatchedCalculator):
     def getJointTauMatrix(self):
         return self._tau
 
+    def getComputedJointTau(self, joint):
+        """getComputedJointTau(joint) (InverseDynamicsCalculator.java:594-604) for N states: the [nDoFs(joint), N] rows of the joint."""
+        if self._tau is None:
+            return None
+        rows = self._input.getJointMatrixIndexProvider().getJointDoFIndices(joint)
+        return self._tau[rows[0]:rows[0] + len(rows)] if rows else self._tau[0:0]
+
     def getBodyAccelerationMatrix(self):
         """[6 * nJoints, N]: rows [6 j, 6 j + 6) = spatial acceleration (angular, linear) of the successor of joint j
         (JointMatrixIndexProvider order) expressed in its CoM frame; None unless setComputeByProducts() asked for it."""
@@ -277,6 +284,21 @@ class ForwardDynamicsCalculator(_BatchedCalculator):
     def getJointTauMatrix(self):
         """The joint efforts (:566-590): the input for EFFORT_SOURCE joints, computed for ACCELERATION_SOURCE joints."""
         return self._tau
+
+    def _rows(self, matrix, joint):
+        if matrix is None:
+            return None
+        rows = self._input.getJointMatrixIndexProvider().getJointDoFIndices(joint)
+        return matrix[rows[0]:rows[0] + len(rows)] if rows else matrix[0:0]
+
+    def getComputedJointAcceleration(self, joint):
+        """getComputedJointAcceleration(joint) (:600-608) for N states: [nDoFs(joint), N]."""
+        return self._rows(self._qdd, joint)
+
+    def getJointTau(self, joint):
+        """getJointTau(joint) (:622-630) for N states: [nDoFs(joint), N].  (The reference returns the joint's acceleration matrix
+        there, `recursionStep.qdd`, against its own documentation; this returns the effort.)"""
+        return self._rows(self._tau, joint)
 
 
 class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):

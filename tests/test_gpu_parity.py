@@ -401,6 +401,7 @@ def test_rnea_byproducts_match_oracle(torch_dev, idx):
         j = s.getAllJoints()[t.nb // 2]
         assert torch.equal(ident.getComputedJointWrench(j), ident.getComputedJointWrenchMatrix()[6 * (t.nb // 2):6 * (t.nb // 2) + 6])
         assert torch.equal(ident.getBodyAcceleration(j.getSuccessor()), ident.getBodyAccelerationMatrix()[6 * (t.nb // 2):6 * (t.nb // 2) + 6])
+        assert torch.equal(ident.getComputedJointTau(j), ident.getJointTauMatrix()[t.dof_off[t.nb // 2]:t.dof_off[t.nb // 2] + j.getDegreesOfFreedom()])
         # host path: same kernel behind pinned staging
         ident.setExternalWrenches(f_host)
         tau_h = ident.compute(q, qd, qdd)
@@ -458,6 +459,10 @@ def test_forward_dynamics_joint_source_modes(torch_dev, idx):
         got_qdd = fdyn.compute(tq, tqd, tau_in, jointAccelerationInput=tqdd).cpu().numpy()
         got_tau = fdyn.getJointTauMatrix().cpu().numpy()
         assert not (np.isnan(got_qdd).any() or np.isnan(got_tau).any()), name
+        jl = joints[-1]
+        rl = slice(t.dof_off[t.nb - 1], t.dof_off[t.nb - 1] + jl.getDegreesOfFreedom())
+        assert torch.equal(fdyn.getComputedJointAcceleration(jl), fdyn.getJointAccelerationMatrix()[rl])
+        assert torch.equal(fdyn.getJointTau(jl), fdyn.getJointTauMatrix()[rl])
         tol = 4e-11 if (t.jtype == td.SIXDOF).any() else 1.6e-11  # ForwardDynamicsCalculatorTest.java:38-41
         assert rel(got_qdd, qdd) < tol * max(1, t.nb / 10), name
         assert rel(got_tau, tau.cpu().numpy()) < tol * max(1, t.nb / 10), name
