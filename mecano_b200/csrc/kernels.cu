@@ -114,7 +114,7 @@ KernelFn pick(int algo, bool fext, bool state_major, int cfg)
 }
 
 // fp32 variant: the one configuration per algorithm that the planner picks for humanoid-sized trees (kCfg index, class 0)
-constexpr int kF32Cfg[3] = {0, 1, 6}; // RNEA 512 threads + TMEM, ABA 384 threads + TMEM, CRBA 256 threads
+constexpr int kF32Cfg[3] = {0, 1, 8}; // RNEA 512 threads + TMEM, ABA 384 threads + TMEM, CRBA 128 threads
 KernelFn pick_f32(int algo)
 {
    if (algo == MB_RNEA) return thread_kernel_f32<MB_RNEA, kCfg[kF32Cfg[0]].block, kRnaAux0, 0, kCfg[kF32Cfg[0]].tm>;
@@ -216,9 +216,12 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       // 256 threads: 2.23 ms; profiles/r01i_cfg_sweep.jsonl): such block sizes only compete if nothing else fits
       const bool uneven = ((nblk * b) % 128) != 0 && nblk * b > 128;
       const int score = (spills || uneven) && forced < 0 ? 1 + (uneven ? 1 : 0) : nblk * b;
-      // prefer more resident states; on ties the first configuration in the table wins -- except for the Coriolis kernel, where
-      // more, smaller blocks win (H37: 2 x 128 threads 5.89 ms, 1 x 256 6.54 ms, profiles/r02h_cor_sweep.jsonl)
-      if (nblk > 0 && (score > best_threads || (algo == MB_CORIOLIS && score == best_threads && b < plan.block)))
+      // prefer more resident states; on ties the first configuration in the table wins -- except for the two store-bound
+      // mass-matrix kernels, where more, smaller blocks win: hardware block scheduling evens out their store bursts (Coriolis,
+      // H37: 2 x 128 threads 5.89 ms, 1 x 256 6.54 ms, profiles/r02h_cor_sweep.jsonl; CRBA, 4 x 128 against 2 x 256 threads:
+      // 7 / 15 / 25 / 32 / 51 bodies -2.9 / -8.4 / -0.8 / -1.4 / -4.3 %, profiles/r03g_crba_block_sweep.jsonl)
+      const bool small_blocks = algo == MB_CORIOLIS || algo == MB_CRBA;
+      if (nblk > 0 && (score > best_threads || (small_blocks && score == best_threads && b < plan.block)))
       {
          best_threads = score;
          plan.block = b;
