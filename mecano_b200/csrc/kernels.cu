@@ -277,8 +277,8 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so
    // does every kernel with a TMEM stack: a block then allocates its tensor memory, stages the constant records and
-   // synchronises once instead of once per tile (H37 RNEA 0.629 -> 0.587 ms).  CRBA (shared-memory stack, two blocks per
-   // SM) measured faster with one block per tile (2.02 vs 2.20 ms): hardware block scheduling evens out its store bursts.
+   // synchronises once instead of once per tile (H37 RNEA 0.629 -> 0.587 ms).  CRBA (shared-memory stack, several small blocks
+   // per SM) measured faster with one block per tile (2.02 vs 2.20 ms): hardware block scheduling evens out its store bursts.
    static const bool persist_all = getenv("MECANO_B200_PERSIST") != nullptr;
    const unsigned grid = (algo == MB_ABA || plan.tm > 0 || persist_all) ? (unsigned)std::min<long long>(ntiles, plan.grid) : (unsigned)ntiles;
    KernelArgs b = a;
