@@ -228,7 +228,8 @@ MB_HD void cor_walk(const MbProgram &P, Ctx &c, int b, int col, T s, T cs, SvT<T
 
 template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx &c)
 {
-   c.zero_fill_mc(); // entries coupling joints of unrelated branches (massMatrix.zero(), coriolisMatrix.zero(), :296-299)
+   // entries coupling joints of unrelated branches (massMatrix.zero(), coriolisMatrix.zero(), :296-299), spread over the ops
+   const int zpart = c.zero_parts(P.nops);
    RbiT<T> acc = RbiT<T>();
    FbiT<T> bacc;
    bacc.A = bacc.TR = bacc.BL = bacc.L = m3_zero<T>();
@@ -241,6 +242,7 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
    {
       const MbOp2 o = P.op2[k];
       c.stk_fence();
+      c.zero_fill_mc_part(k, zpart);
       const int jt = MB2_JT(o.code);
       const auto C = c.cst(o.body);
       if (!(o.code & MB2_ASCEND))

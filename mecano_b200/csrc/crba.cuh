@@ -93,7 +93,8 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_walk(const MbProg
 template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbProgram &P, Ctx &c)
 {
    // entries coupling joints of unrelated branches are zero
-   c.zero_fill();
+   // (the zeros are spread over the ops of the traversal instead of being written in one burst up front: a steadier store stream)
+   const int zpart = c.zero_parts(P.nops);
    RbiT<T> acc = RbiT<T>();
    T s = (T)0, cs = (T)1, ls = (T)0, lc = (T)1, mq = (T)0;
    const int nops = P.nops;
@@ -121,6 +122,7 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbPro
    {
       const MbOp2 o = P.op2[k];
       c.stk_fence();
+      c.zero_fill_part(k, zpart);
       if (o.pf & MB2_PF_D1)
          c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, 1);
       c.pf_commit();

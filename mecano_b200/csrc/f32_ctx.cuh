@@ -39,6 +39,8 @@ template <class Ctx> struct F32Ctx
    __device__ __forceinline__ void st_M(int e, float v) const { c.st_M(e, (double)v); }
    __device__ __forceinline__ int n_dofs() const { return c.n_dofs(); }
    __device__ __forceinline__ void zero_fill() const { c.zero_fill(); }
+   __device__ __forceinline__ int zero_parts(int nops) const { return c.zero_parts(nops); }
+   __device__ __forceinline__ void zero_fill_part(int k, int parts) const { c.zero_fill_part(k, parts); }
    // ---- the optional buffers belong to the fp64 "general" instantiation only
    __device__ __forceinline__ bool has_fext() const { return false; }
    __device__ __forceinline__ bool has_acc() const { return false; }

@@ -242,12 +242,13 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
       if (!kClamp || active)
          mb_stg_cs(mb_row(corb, (unsigned)e, ld8), v);
    }
-   __device__ __forceinline__ void zero_fill_mc() const
+   __device__ __forceinline__ void zero_fill_mc_part(int k, int parts) const
    {
+      const int k1 = min(nz8, (k + 1) * parts);
 #pragma unroll 1
-      for (int k = 0; k < nz8; k++)
+      for (int i = k * parts; i < k1; i++)
       {
-         const uint4 u = __ldg(zlist + k);
+         const uint4 u = __ldg(zlist + i);
          const unsigned e[8] = {u.x & 0xffffu, u.x >> 16, u.y & 0xffffu, u.y >> 16, u.z & 0xffffu, u.z >> 16, u.w & 0xffffu, u.w >> 16};
 #pragma unroll
          for (int j = 0; j < 8; j++)
@@ -255,6 +256,19 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
             st_M((int)e[j], 0.0);
             st_C((int)e[j], 0.0);
          }
+      }
+   }
+   // the zero list in `parts`-sized groups of eight entries, one group range per op of the traversal
+   __device__ __forceinline__ int zero_parts(int nops) const { return (nz8 + nops - 1) / nops; }
+   __device__ __forceinline__ void zero_fill_part(int k, int parts) const
+   {
+      const int k1 = min(nz8, (k + 1) * parts);
+#pragma unroll 1
+      for (int i = k * parts; i < k1; i++)
+      {
+         const uint4 u = __ldg(zlist + i);
+         st_M(u.x & 0xffffu, 0.0); st_M(u.x >> 16, 0.0); st_M(u.y & 0xffffu, 0.0); st_M(u.y >> 16, 0.0);
+         st_M(u.z & 0xffffu, 0.0); st_M(u.z >> 16, 0.0); st_M(u.w & 0xffffu, 0.0); st_M(u.w >> 16, 0.0);
       }
    }
    __device__ __forceinline__ void zero_fill() const

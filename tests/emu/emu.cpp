@@ -66,9 +66,11 @@ template <class T> struct CpuCtx
    double *cmm = nullptr, *com = nullptr, *rootw = nullptr;
    double *Cm = nullptr; // Coriolis matrix, entry-major like M
    void st_C(int e, T v) { Cm[(long)e * ld + s] = (double)v; }
-   void zero_fill_mc()
+   void zero_fill_mc_part(int k, int parts)
    {
-      for (uint16_t e : *zl) { st_M(e, (T)0); st_C(e, (T)0); }
+      const int n8 = (int)zl->size() / 8, k1 = std::min(n8, (k + 1) * parts);
+      for (int i = k * parts; i < k1; i++)
+         for (int j = 0; j < 8; j++) { st_M((*zl)[8 * i + j], (T)0); st_C((*zl)[8 * i + j], (T)0); }
    }
    bool has_rootw() const { return rootw != nullptr; }
    void st_cmm(int row, T v) { cmm[(long)row * ld + s] = (double)v; }
@@ -84,6 +86,13 @@ template <class T> struct CpuCtx
    int n_dofs() const { return nv; }
    const std::vector<uint16_t> *zl;
    void zero_fill() { for (uint16_t e : *zl) st_M(e, (T)0); }
+   int zero_parts(int nops) const { return ((int)zl->size() / 8 + nops - 1) / nops; }
+   void zero_fill_part(int k, int parts)
+   {
+      const int n8 = (int)zl->size() / 8, k1 = std::min(n8, (k + 1) * parts);
+      for (int i = k * parts; i < k1; i++)
+         for (int j = 0; j < 8; j++) st_M((*zl)[8 * i + j], (T)0);
+   }
    void stk_ld2(int slot2, int j, T &a, T &b) const { a = stk[2 * (slot2 + j)]; b = stk[2 * (slot2 + j) + 1]; }
    void stk_st2(int slot2, int j, T a, T b) { stk[2 * (slot2 + j)] = a; stk[2 * (slot2 + j) + 1] = b; }
    // split view of a slot (MbOp2::wslot / nslot): the wide area behind the combined stack so that both index sets are exercised
