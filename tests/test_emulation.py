@@ -169,3 +169,29 @@ def test_stack_sizes_follow_depth_not_body_count():
         assert big.program_info(algo)["stack"] <= per_level * big.program_info(algo)["max_depth"] + 16
     assert h37.program_info(0)["stack"] == 6 + 8 * 9  # pelvis wrench, then 3 spine + 6 non-leaf arm levels
     assert h37.program_info(1)["rec"] == 8 * 32
+
+
+def test_emulated_kernels_match_the_golden_fixtures_of_the_next_rows():
+    """The kernel routines (compiled for the host) against tests/golden/oracle_golden_next.npz."""
+    import importlib.util
+    import os
+
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_next", os.path.join(here, "make_golden_next.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    data = np.load(os.path.join(here, "oracle_golden_next.npz"))
+    for name, t, g, s in gen.load_cases():
+        e, e0 = el.Emu(t, gravity=g), el.Emu(t, gravity=(0.0, 0.0, 0.0))
+        q, qd, qdd, tau = (np.ascontiguousarray(s[k]) for k in ("q", "qd", "qdd", "tau"))
+        n = q.shape[1]
+        fext = np.ascontiguousarray(s["fext"].reshape(t.nb, 6, n))
+        _, acc, wr = e.rnea_full(q, qd, qdd, fext)
+        assert rel(acc, data[name + "/acc"]) < TOL and rel(wr, data[name + "/wr"]) < TOL, name
+        assert rel(e.aba_sources(q, qd, tau, qdd, data[name + "/accel_source"], fext), data[name + "/qdd_src"]) < TOL, name
+        _, cmm, com = e0.crba_centroidal(q)
+        assert rel(cmm, data[name + "/cmm_world"]) < TOL, name
+        assert rel(com[:3] / com[3], data[name + "/com"][:3]) < TOL, name
+        assert rel(e0.rnea_root_wrench(q, qd), data[name + "/conv_world"]) < TOL, name
+        _, C = e0.coriolis(q, qd)
+        assert rel(C, data[name + "/coriolis"]) < TOL, name

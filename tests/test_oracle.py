@@ -243,3 +243,20 @@ def test_closed_form_planar_two_link_arm():
         Lz = i1 * qd[0] + i2 * (qd[0] + qd[1]) + m1 * (p1[0] * v1[1] - p1[1] * v1[0]) + m2 * (p2[0] * v2[1] - p2[1] * v2[0])
         hq = A @ qd
         assert abs(hq[2] - Lz) < 1e-12 and np.allclose(hq[3:5], m1 * v1 + m2 * v2, atol=1e-12)
+
+
+def test_golden_fixtures_of_the_next_rows():
+    """Regression vectors generated by tests/golden/make_golden_next.py from this oracle (NOT from the JVM): RNEA by-products,
+    joint source modes, centroidal quantities, Coriolis matrix, on the trees and states of oracle_golden.npz."""
+    import importlib.util
+
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_next", os.path.join(here, "make_golden_next.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    data = np.load(os.path.join(here, "oracle_golden_next.npz"))
+    for name, t, g, s in gen.load_cases():
+        got = gen.evaluate(t, g, s, data[name + "/accel_source"])
+        for k, v in got.items():
+            want = data["%s/%s" % (name, k)]
+            assert v.shape == want.shape and np.allclose(v, want, rtol=0, atol=1e-10 * max(1.0, np.max(np.abs(want)))), (name, k)
