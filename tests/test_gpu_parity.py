@@ -755,3 +755,55 @@ def test_humanoid_1m_states_invariants_of_the_next_rows(torch_dev):
         C = cen.getCoriolisMatrix(q[:, a:a + chunk].contiguous(), qd[:, a:a + chunk].contiguous()).reshape(nv, nv, -1)
         got = torch.einsum("ijs,js->is", C, qd[:, a:a + chunk])
         assert worst(got, want[:, a:a + chunk]) < 1e-9
+
+
+def test_golden_fixtures_of_the_next_rows_on_gpu(torch_dev):
+    """tests/golden/oracle_golden_next.npz (RNEA by-products, joint source modes, centroidal quantities, Coriolis matrix) through
+    the raw C ABI; body rows in the order of the level-ordered tables (wrench_index = NULL)."""
+    import importlib.util
+
+    import mecano_b200 as mb
+    from mecano_b200 import _capi
+
+    import emu_lib as el
+
+    torch, dev = torch_dev
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden_next", os.path.join(here, "make_golden_next.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    data = np.load(os.path.join(here, "oracle_golden_next.npz"))
+    for name, t, g, s in gen.load_cases():
+        d, keep, order = el.tree_desc_c(t)
+        e = mb.Engine(_capi.TreeDesc.from_buffer_copy(bytes(d)), 0, keepalive=keep)
+        n, nv, nb = s["q"].shape[1], t.nv, t.nb
+        back = np.empty(nb, dtype=np.int64)
+        back[order] = np.arange(nb)
+        fe = np.ascontiguousarray(s["fext"].reshape(nb, 6, n)[order].reshape(6 * nb, n))
+        tq, tqd, tqdd, ttau, tf = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (s["q"], s["qd"], s["qdd"], s["tau"], fe))
+        new = lambda rows: torch.full((rows, n), float("nan"), dtype=torch.float64, device=dev)  # noqa: E731
+        # RNEA by-products
+        e.set_gravity(*g)
+        acc, wr = new(6 * nb), new(6 * nb)
+        e.rnea(tq, tqd, tqdd, new(nv), fext=tf, body_acc=acc, joint_wrench=wr)
+        assert rel(acc.cpu().numpy().reshape(nb, 6, n)[back], data[name + "/acc"]) < TOL, name
+        assert rel(wr.cpu().numpy().reshape(nb, 6, n)[back], data[name + "/wr"]) < TOL, name
+        # joint source modes
+        e.set_joint_source_modes(np.asarray(data[name + "/accel_source"])[order])
+        qdd_out, tau_out = new(nv), new(nv)
+        e.aba_sources(tq, tqd, ttau, tqdd, qdd_out, tau_out, fext=tf)
+        assert rel(qdd_out.cpu().numpy(), data[name + "/qdd_src"]) < TOL, name
+        assert rel(tau_out.cpu().numpy(), data[name + "/tau_src"]) < TOL, name
+        e.set_joint_source_modes(None)
+        # centroidal quantities and the Coriolis matrix (no gravity involved)
+        for frame, key in ((0, "world"), (1, "com")):
+            M, cmm, com, conv = new(nv * nv), new(6 * nv), new(4), new(6)
+            e.crba_centroidal(tq, M, cmm, com, frame)
+            e.centroidal_convective_term(tq, tqd, com, conv, frame)
+            assert rel(cmm.cpu().numpy().reshape(6, nv, n), data["%s/cmm_%s" % (name, key)]) < TOL, name
+            assert rel(com.cpu().numpy(), data[name + "/com"]) < TOL, name
+            assert rel(conv.cpu().numpy(), data["%s/conv_%s" % (name, key)]) < TOL, name
+        M, C = new(nv * nv), new(nv * nv)
+        e.coriolis(tq, tqd, M, C)
+        assert rel(C.cpu().numpy().reshape(nv, nv, n), data[name + "/coriolis"]) < TOL, name
+        e.close()
