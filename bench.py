@@ -48,8 +48,9 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--states", type=int, default=1 << 20, help="states per GPU (weak scaling)")
     p.add_argument("--neck", type=int, default=2, help="2 -> H37 (37 DoF), 1 -> H36 (36 DoF)")
-    p.add_argument("--cpu-sample", type=int, default=32768, help="states in the bounded CPU-baseline sample")
-    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--cpu-sample", type=int, default=0, help="states in the bounded CPU-baseline sample (0: sized from --cpu-budget)")
+    p.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work the reference arm's timed steps may take in total")
+    p.add_argument("--e2e-steps", type=int, default=5)
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the kernels timed outside the step (ncu launch lists of the step alone)")
@@ -124,13 +125,29 @@ def build_system(neck):
     return mb.MultiBodySystem.toMultiBodySystemBasics(elevator)
 
 
-def oracle_for(system):
+def bench_tree(neck):
+    """The humanoid of the benchmark as neutral tables (tests/golden/bench_tree_H*.npz, written by tests/golden/make_bench_tree.py
+    from the host model with HUMANOID_SEED): what the CPU legs build the oracle from, without importing the product package."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib
     import treedesc
 
-    tree = treedesc.TreeDesc(**system.describe()).contiguous()
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bench_tree_H%d.npz" % (35 + neck)))
+    assert int(z["seed"]) == HUMANOID_SEED, "tests/golden/bench_tree_*.npz is stale: run tests/golden/make_bench_tree.py"
+    fields = {k: (int(z[k]) if z[k].ndim == 0 else z[k]) for k in z.files if k != "seed"}
+    return treedesc.TreeDesc(**fields).contiguous()
+
+
+def oracle_for_tree(tree):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+
     return oracle_lib.Oracle(tree, gravity=GRAVITY), oracle_lib
+
+
+def same_tree(system, tree):
+    """The GPU arm's generated system equals the committed tables the CPU arm uses (both arms on the same multi-body system)."""
+    d = system.describe()
+    return all(np.array_equal(np.asarray(d[k]), getattr(tree, k)) for k in ("parent", "jtype", "axis", "off_R", "off_p", "com_R", "com_p", "J", "mass", "dof_off", "cfg_off"))
 
 
 def cpu_step(oracle, q, qd, qdd, tau, nthreads=0):
@@ -141,18 +158,29 @@ def cpu_step(oracle, q, qd, qdd, tau, nthreads=0):
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the CPU implementation of the path on the host cores.  Imports nothing of the product (no
+    mecano_b200, no CUDA library): tree from the committed tables, states from numpy, compute in oracle/."""
     if rank != 0:
         return
-    import mecano_b200 as mb
+    tree = bench_tree(args.neck)  # puts tests/ on the path
+    oracle, oracle_lib = oracle_for_tree(tree)
+    import treedesc
 
-    system = build_system(args.neck)
-    oracle, oracle_lib = oracle_for(system)
     cores = oracle_lib.lib().mo_max_threads()
-    n = args.cpu_sample
     rng = np.random.default_rng(STATE_SEED)
-    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, system, n)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_step(oracle, q[:, :2048].copy(), qd[:, :2048].copy(), qdd[:, :2048].copy(), tau[:, :2048].copy())
+    # warm-up doubles as a rate probe: the sample of each timed step is sized so that the K timed steps take about
+    # --cpu-budget seconds in total (at most the full batch); throughput is per state and states are independent, so the
+    # rate does not depend on the sample size
+    probe = 4096
+    q, qd, qdd, tau = treedesc.random_states(rng, tree, probe)
+    cpu_step(oracle, q, qd, qdd, tau)
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(args.warmup, 3))):
+        cpu_step(oracle, q, qd, qdd, tau)
+    rate = probe * max(1, min(args.warmup, 3)) / (time.perf_counter() - t0)
+    n = args.cpu_sample if args.cpu_sample > 0 else int(min(args.states, max(8192, rate * args.cpu_budget / max(1, args.steps))))
+    n = max(256, n // 256 * 256)
+    q, qd, qdd, tau = treedesc.random_states(rng, tree, n)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_step(oracle, q, qd, qdd, tau)
@@ -163,7 +191,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.neck, args.states), "sample_states_per_step": n,
-                   "note": "Mecano is Java; no JVM on this box: reference arm = reference-faithful C port on host cores"},
+                   "sample_note": "a full %d-state step takes ~%.0f s on these cores; each step is a bounded sample sized for ~%.0f s of CPU work over the "
+                                  "%d timed steps (states are independent: the per-state rate does not depend on the sample size)"
+                                  % (args.states, args.states / value, args.cpu_budget, args.steps),
+                   "note": "Mecano is Java; no JVM on this box: reference arm = reference-faithful C port on host cores (-O2, -ffp-contract=off)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -504,9 +535,11 @@ def main():
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample of the same workload (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_cpu:
-        oracle, oracle_lib = oracle_for(system)
+        tree = bench_tree(args.neck)
+        assert same_tree(system, tree), "tests/golden/bench_tree_*.npz does not match the generated humanoid: run tests/golden/make_bench_tree.py"
+        oracle, oracle_lib = oracle_for_tree(tree)
         cores = oracle_lib.lib().mo_max_threads()
-        ns = args.cpu_sample
+        ns = args.cpu_sample if args.cpu_sample > 0 else 32768
         hq, hqd, hqdd, htau = (x[:, :ns].cpu().numpy().copy() for x in (q, qd, qdd, tau_in))
         cpu_step(oracle, hq[:, :1024].copy(), hqd[:, :1024].copy(), hqdd[:, :1024].copy(), htau[:, :1024].copy())
         t0 = time.perf_counter()

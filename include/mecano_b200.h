@@ -144,7 +144,7 @@ int mecano_b200_set_variant(mecano_b200_handle *h, int variant);
 /*
  * Optional fp32 variant.  MECANO_B200_PRECISION_FP32 makes the plain mecano_b200_rnea / aba / crba calls (device and host entry
  * points) compute in single precision; every buffer of the ABI stays fp64.  Mecano is double precision throughout: this is a
- * throughput option with its own, much looser tolerance (RNEA / CRBA ~1e-5 relative, ABA ~1e-3 on a 37-DoF humanoid), reported
+ * throughput option with its own, much looser tolerance (RNEA / CRBA 1e-5 relative, ABA 1e-4 on a 37-DoF humanoid; measured worst state of 2^20: 3e-6), reported
  * separately and never chosen implicitly.  Calls the variant does not cover (external wrenches, flags, by-products, trees
  * outside the humanoid-sized launch configuration) fail with MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY instead of running in fp64.
  */

@@ -85,7 +85,7 @@ class _BatchedCalculator:
 
     def setPrecision(self, precision):
         """"fp64" (Mecano's, the default) or "fp32": the optional single-precision variant (arithmetic in float, matrices stay
-        float64); plain compute() / getMassMatrix() calls only, tolerance ~1e-5 (RNEA, CRBA) / ~1e-3 (ABA).  Returns self."""
+        float64); plain compute() / getMassMatrix() calls only, tolerance 1e-5 (RNEA, CRBA) / 1e-4 (ABA).  Returns self."""
         self._engine.set_precision(precision)
         return self
 
@@ -314,7 +314,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         super().__init__(input, device)
         self._M = None
         self._owned = {}
-        self._cmm = self._com = self._convective = None
+        self._cmm = self._com = self._convective = self._com_q = None
         self._frame = self.WORLD_FRAME
         if centroidalMomentumFrame is not None:
             self.setCentroidalMomentumFrame(centroidalMomentumFrame)
@@ -365,6 +365,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         self._cmm = self._empty_like(q, 6 * nv, n)
         self._com = self._empty_like(q, 4, n)
         self._engine.crba_centroidal(q, self._M, self._cmm, self._com, self._frame_code())
+        self._com_q = q  # the configuration matrix the centre of mass belongs to (getCentroidalConvectiveTermMatrix)
         return self._cmm
 
     def getCenterOfMass(self):
@@ -372,17 +373,20 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         getCentroidalMomentumMatrix()."""
         return self._com
 
-    def getCentroidalConvectiveTermMatrix(self, q, qd):
+    def getCentroidalConvectiveTermMatrix(self, q, qd, reuseCenterOfMass=False):
         """getCentroidalConvectiveTermMatrix() (:423-440, :811-839) for N states: [6, N], moment first, in the centroidal momentum
-        frame.  In CENTER_OF_MASS_FRAME the centre of mass comes from getCentroidalMomentumMatrix(q), which is called first if
-        it has not been for a batch of this size."""
+        frame.  In CENTER_OF_MASS_FRAME the centre of mass is that of the `q` passed here: getCentroidalMomentumMatrix(q) runs
+        first (the reference derives both from the same joint state after reset()).  reuseCenterOfMass=True skips that when the
+        caller has just called getCentroidalMomentumMatrix() with this very `q` (same object, same batch); it is the caller's
+        statement that the configuration has not changed since."""
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
         n = q.shape[1] if q.ndim == 2 else -1
         self._check("q", q, nq, n)
         self._check("qd", qd, nv, n)
         com = None
         if self._frame == self.CENTER_OF_MASS_FRAME:
-            if self._com is None or self._com.shape[1] != n or _is_torch(self._com) != _is_torch(q):
+            fresh = reuseCenterOfMass and self._com is not None and self._com_q is q and self._com.shape[1] == n
+            if not fresh:
                 self.getCentroidalMomentumMatrix(q)
             com = self._com
         out = self._empty_like(q, 6, n)
@@ -393,6 +397,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
     def reset(self):
         """Mecano caches the mass matrix until reset(); the batched calculator recomputes on every getMassMatrix(q)."""
         self._M = None
+        self._com = self._com_q = None
 
     def getMassMatrix(self, q=None, massMatrix=None, stateMajor=False):
         """Mass matrices for N states.  Default layout [nDoFs*nDoFs, N] (entry (i, j) of state s at [i*nDoFs + j, s]);

@@ -81,6 +81,27 @@ int cuda_fail(mecano_b200_handle *h, cudaError_t e, const char *what)
       if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); \
    } while (0)
 
+// Makes the handle's device current for the duration of an entry point and restores the caller's afterwards (a binding that
+// keeps its own notion of the current device -- torch, a JVM thread pool -- must not find it changed behind its back).
+struct DeviceGuard
+{
+   int prev = -1;
+   cudaError_t err = cudaSuccess;
+   explicit DeviceGuard(int device)
+   {
+      if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+      if (prev != device) err = cudaSetDevice(device);
+      else prev = -1;
+   }
+   ~DeviceGuard()
+   {
+      if (prev >= 0) cudaSetDevice(prev);
+   }
+};
+#define MB_ON_DEVICE(h)                                                            \
+   DeviceGuard device_guard_((h)->device);                                         \
+   if (device_guard_.err != cudaSuccess) return cuda_fail(h, device_guard_.err, "cudaSetDevice")
+
 int check_batch(mecano_b200_handle *h, int64_t n, int64_t ld)
 {
    if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
@@ -316,9 +337,13 @@ int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const doubl
    if (!q || !out || (algo != MB_CRBA && (!qd || !x)))
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    std::lock_guard<std::mutex> lk(h->mu);
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
    const bool state_major = algo == MB_CRBA && (flags & MECANO_B200_CRBA_STATE_MAJOR);
+   // state-major: the whole per-state block is copied back from the staging buffer, which other calls on this handle reuse, so
+   // the kernel must write the structural zeros there every time (the transfer saving of ZEROS_PRESENT is entry-major only)
+   if (state_major)
+      flags &= ~MECANO_B200_CRBA_ZEROS_PRESENT;
    const bool sources = algo == MB_ABA && (x2 || tau_out); // mecano_b200_aba_sources_host
    const size_t in_rows = algo == MB_CRBA ? nq : nq + 2 * nv + (fext ? 6 * nb : 0) + (x2 ? nv : 0);
    const size_t out_rows = algo == MB_CRBA ? nv * nv : nv + (body_acc ? 6 * nb : 0) + (joint_wrench ? 6 * nb : 0) + (tau_out ? nv : 0);
@@ -428,7 +453,8 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       delete h;
       return fail(nullptr, (int)ce, m);
    };
-   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+   DeviceGuard device_guard_(device);
+   if ((e = device_guard_.err) != cudaSuccess) return bail(e, "cudaSetDevice");
    const size_t bytes = h->tree.consts.size() * sizeof(double);
    if ((e = cudaMalloc(&h->d_consts, bytes)) != cudaSuccess) return bail(e, "cudaMalloc(consts)");
    if ((e = cudaMemcpy(h->d_consts, h->tree.consts.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(consts)");
@@ -500,7 +526,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
 void mecano_b200_destroy(mecano_b200_handle *h)
 {
    if (!h) return;
-   cudaSetDevice(h->device);
+   DeviceGuard device_guard_(h->device);
    for (int i = 0; i < 2; i++)
    {
       if (h->stage[i]) cudaFree(h->stage[i]);
@@ -562,7 +588,7 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
 {
    if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
    std::lock_guard<std::mutex> lk(h->mu);
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    for (int algo = 0; algo < 3; algo++)
    {
       if (!(algo_mask & (1u << algo)) || h->spec[algo].ready())
@@ -618,7 +644,7 @@ int mecano_b200_rnea(mecano_b200_handle *h, int64_t n, int64_t ld, const double 
    if (rc) return rc;
    if (n == 0) return MECANO_B200_OK; /* empty batch: nothing to do, pointers may be NULL */
    if (!q || !qd || !qdd || !tau) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    return run(h, MB_RNEA, n, ld, q, qd, qdd, fext, tau, flags, (cudaStream_t)stream);
 }
 
@@ -629,7 +655,7 @@ int mecano_b200_rnea_full(mecano_b200_handle *h, int64_t n, int64_t ld, const do
    if (rc) return rc;
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !qdd || !tau) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    RunOpts opt;
    opt.body_acc = body_acc;
    opt.joint_wrench = joint_wrench;
@@ -643,7 +669,7 @@ int mecano_b200_aba(mecano_b200_handle *h, int64_t n, int64_t ld, const double *
    if (rc) return rc;
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !tau || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    return run(h, MB_ABA, n, ld, q, qd, tau, fext, qdd, flags, (cudaStream_t)stream);
 }
 
@@ -662,7 +688,7 @@ int mecano_b200_aba_sources(mecano_b200_handle *h, int64_t n, int64_t ld, const 
    if (rc) return rc;
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !tau || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    return run_aba_sources(h, n, ld, q, qd, tau, qdd_in, fext, qdd, tau_out, (cudaStream_t)stream, 0);
 }
 
@@ -683,7 +709,7 @@ int mecano_b200_crba_centroidal(mecano_b200_handle *h, int64_t n, int64_t ld, co
    if (!q || !M || !cmm || !com) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    if (frame != MECANO_B200_FRAME_WORLD && frame != MECANO_B200_FRAME_CENTER_OF_MASS)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown centroidal momentum frame");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    cudaStream_t st = (cudaStream_t)stream;
    // the kernel sums (mass * CoM, mass) over the children of the root body into the com rows
    MB_CUDA(h, cudaMemset2DAsync(com, (size_t)ld * sizeof(double), 0, (size_t)n * sizeof(double), 4, st));
@@ -711,7 +737,7 @@ int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n, int
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown centroidal momentum frame");
    if (frame == MECANO_B200_FRAME_CENTER_OF_MASS && !com)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the centre-of-mass frame needs the com rows of mecano_b200_crba_centroidal");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    cudaStream_t st = (cudaStream_t)stream;
    const size_t need = (size_t)h->tree.nv * (size_t)ld;
    if (h->scratch_doubles < need)
@@ -753,7 +779,7 @@ int mecano_b200_coriolis(mecano_b200_handle *h, int64_t n, int64_t ld, const dou
    if (!q || !qd || !M || !C) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    if (h->plan[MB_CORIOLIS].block == 0)
       return fail(h, MECANO_B200_ERR_TOO_LARGE, "tree exceeds the per-state work areas of the Coriolis-matrix kernel (branch nesting / depth too large)");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    RunOpts opt;
    opt.cor = C;
    return run(h, MB_CORIOLIS, n, ld, q, qd, qd, nullptr, M, 0u, (cudaStream_t)stream, opt);
@@ -766,7 +792,7 @@ int mecano_b200_coriolis_host(mecano_b200_handle *h, int64_t n, int64_t ld, cons
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !M || !C) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    std::lock_guard<std::mutex> lk(h->mu);
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + nv + 2 * nv * nv;
    const size_t chunk = (size_t)std::min<int64_t>(n, 16384);
    double *d = nullptr;
@@ -798,7 +824,7 @@ int mecano_b200_crba_centroidal_host(mecano_b200_handle *h, int64_t n, int64_t l
    if (n == 0) return MECANO_B200_OK;
    if (!q || !M || !cmm || !com) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    std::lock_guard<std::mutex> lk(h->mu);
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + nv * nv + 6 * nv + 4;
    const size_t chunk = (size_t)std::min<int64_t>(n, 16384);
    double *d = nullptr;
@@ -830,7 +856,7 @@ int mecano_b200_centroidal_convective_term_host(mecano_b200_handle *h, int64_t n
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !out) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    std::lock_guard<std::mutex> lk(h->mu);
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + nv + 4 + 6;
    const size_t chunk = (size_t)std::min<int64_t>(n, 262144);
    double *d = nullptr;
@@ -860,7 +886,7 @@ int mecano_b200_crba(mecano_b200_handle *h, int64_t n, int64_t ld, const double 
    if (rc) return rc;
    if (n == 0) return MECANO_B200_OK;
    if (!q || !M) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    return run(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, M, layout, (cudaStream_t)stream);
 }
 
@@ -889,7 +915,7 @@ int mecano_b200_integrate(mecano_b200_handle *h, int64_t n, int64_t ld, double d
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    if (!(dt == dt)) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "dt is NaN");
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    mb::IntegrateJoints J;
    const MbProgram &P = h->tree.prog[MB_RNEA];
    J.nb = P.nb;
@@ -914,7 +940,7 @@ int mecano_b200_integrate_host(mecano_b200_handle *h, int64_t n, int64_t ld, dou
    if (n == 0) return MECANO_B200_OK;
    if (!q || !qd || !qdd) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
    std::lock_guard<std::mutex> lk(h->mu);
-   MB_CUDA(h, cudaSetDevice(h->device));
+   MB_ON_DEVICE(h);
    const size_t nq = h->tree.nq, nv = h->tree.nv, rows = nq + 2 * nv;
    size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)rows);
    chunk = std::max<size_t>(4096, chunk & ~(size_t)255);

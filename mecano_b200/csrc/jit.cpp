@@ -133,6 +133,9 @@ uint64_t fnv1a(uint64_t h, const void *p, size_t n)
    return h;
 }
 
+// The cache holds executable code, so it is only used when nobody else can have written it: a directory owned by the
+// calling user that neither group nor others may write.  Directories this function creates are private (0700).  Without
+// $MECANO_B200_CACHE and without $HOME there is no trustworthy place (a shared /tmp can be pre-created by anyone): no cache.
 std::string cache_dir()
 {
    const char *e = getenv("MECANO_B200_CACHE");
@@ -142,21 +145,43 @@ std::string cache_dir()
    else
    {
       const char *home = getenv("HOME");
-      d = std::string(home && *home ? home : "/tmp") + "/.cache/mecano_b200";
+      if (!home || !*home) return "";
+      d = std::string(home) + "/.cache/mecano_b200";
    }
    // mkdir -p
    for (size_t i = 1; i <= d.size(); i++)
       if (i == d.size() || d[i] == '/')
-         mkdir(d.substr(0, i).c_str(), 0755);
+         mkdir(d.substr(0, i).c_str(), 0700);
+   struct stat st;
+   if (lstat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != geteuid() || (st.st_mode & (S_IWGRP | S_IWOTH)))
+      return "";
    return d;
 }
 
+// cache entry = 32-byte header (magic, payload size, two independent 64-bit digests of the payload) + cubin: a truncated,
+// corrupted or foreign file is recognised before it is handed to the driver
+struct CacheHeader
+{
+   uint64_t magic, size, h1, h2;
+};
+constexpr uint64_t kCacheMagic = 0x3130424e4243424dull; // "MBCBNB01"
+constexpr uint64_t kSeed1 = 1469598103934665603ull, kSeed2 = 0x9e3779b97f4a7c15ull;
+
 bool read_file(const std::string &path, std::vector<char> &out)
 {
+   struct stat st;
+   if (lstat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode) || st.st_uid != geteuid()) return false;
    std::ifstream f(path, std::ios::binary);
    if (!f) return false;
-   out.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-   return !out.empty();
+   std::vector<char> raw((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+   CacheHeader hd;
+   if (raw.size() <= sizeof hd) return false;
+   std::memcpy(&hd, raw.data(), sizeof hd);
+   const char *payload = raw.data() + sizeof hd;
+   const size_t n = raw.size() - sizeof hd;
+   if (hd.magic != kCacheMagic || hd.size != n || hd.h1 != fnv1a(kSeed1, payload, n) || hd.h2 != fnv1a(kSeed2, payload, n)) return false;
+   out.assign(payload, payload + n);
+   return true;
 }
 
 void write_file_atomic(const std::string &path, const std::vector<char> &data)
@@ -165,8 +190,11 @@ void write_file_atomic(const std::string &path, const std::vector<char> &data)
    {
       std::ofstream f(tmp, std::ios::binary);
       if (!f) return;
+      const CacheHeader hd = {kCacheMagic, (uint64_t)data.size(), fnv1a(kSeed1, data.data(), data.size()), fnv1a(kSeed2, data.data(), data.size())};
+      f.write((const char *)&hd, sizeof hd);
       f.write(data.data(), (std::streamsize)data.size());
    }
+   chmod(tmp.c_str(), 0600);
    rename(tmp.c_str(), path.c_str());
 }
 
@@ -254,8 +282,14 @@ int spec_build(int algo, const FlatTree &tree, const SpecOptions &opt, SpecKerne
    if (nvrtc().error.empty()) nvrtc().Version(&vmaj, &vmin);
    h = fnv1a(h, &vmaj, sizeof vmaj);
    h = fnv1a(h, &vmin, sizeof vmin);
-   char hex[32];
-   std::snprintf(hex, sizeof hex, "%016llx", (unsigned long long)h);
+   // second, independently seeded pass over the same bytes: a 128-bit key
+   uint64_t h2 = fnv1a(kSeed2, src.data(), src.size());
+   for (const EmbeddedHeader &eh : kEmbeddedHeaders)
+      h2 = fnv1a(h2, eh.text, strlen(eh.text));
+   h2 = fnv1a(h2, &vmaj, sizeof vmaj);
+   h2 = fnv1a(h2, &vmin, sizeof vmin);
+   char hex[40];
+   std::snprintf(hex, sizeof hex, "%016llx%016llx", (unsigned long long)h, (unsigned long long)h2);
    const std::string dir = cache_dir();
    const std::string path = dir.empty() ? "" : dir + "/" + hex + ".cubin";
    std::vector<char> cubin;

@@ -9,14 +9,16 @@ from . import _capi
 from ._capi import check, lib
 
 
-def _dev_ptr_ld(t, rows, n):
-    """(pointer, ld) of a torch CUDA tensor [rows, n] float64 with contiguous states."""
+def _dev_ptr_ld(t, rows, n, device=None):
+    """(pointer, ld) of a torch CUDA tensor [rows, n] float64 with contiguous states (on `device`, if given)."""
     import torch
 
     if t is None:
         return None, None
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64):
         raise TypeError("expected a float64 CUDA tensor")
+    if device is not None and t.device.index != device:
+        raise ValueError("tensor lives on cuda:%s, the engine on cuda:%d" % (t.device.index, device))
     if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != n:
         raise ValueError("expected shape [%d, %d], got %s" % (rows, n, tuple(t.shape)))
     if n > 1 and t.stride(1) != 1:
@@ -96,36 +98,39 @@ class Engine:
         check(lib.mecano_b200_kernel_info_get(self._h, int(algo), int(n_states), ctypes.byref(info)), self._h)
         return info.as_dict()
 
-    @staticmethod
-    def _stream():
+    def _dp(self, t, rows, n):
+        return _dev_ptr_ld(t, rows, n, self.device)
+
+    def _stream(self):
+        """torch's current stream ON THE ENGINE'S DEVICE (not on torch's current device)."""
         import torch
 
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     # ---- device entry points (asynchronous on torch's current stream)
     def rnea(self, q, qd, qdd, tau, fext=None, flags=0, body_acc=None, joint_wrench=None):
         """body_acc / joint_wrench ([6 * nb, n], optional): the by-products of mecano_b200_rnea_full."""
         n = q.shape[1]
-        pq, l0 = _dev_ptr_ld(q, self.nq, n)
-        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
-        pqdd, l2 = _dev_ptr_ld(qdd, self.nv, n)
-        pt, l3 = _dev_ptr_ld(tau, self.nv, n)
-        pf, l4 = _dev_ptr_ld(fext, 6 * self.nb, n)
+        pq, l0 = self._dp(q, self.nq, n)
+        pqd, l1 = self._dp(qd, self.nv, n)
+        pqdd, l2 = self._dp(qdd, self.nv, n)
+        pt, l3 = self._dp(tau, self.nv, n)
+        pf, l4 = self._dp(fext, 6 * self.nb, n)
         if body_acc is None and joint_wrench is None:
             check(lib.mecano_b200_rnea(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags, self._stream()), self._h)
             return tau
-        pa, l5 = _dev_ptr_ld(body_acc, 6 * self.nb, n)
-        pw, l6 = _dev_ptr_ld(joint_wrench, 6 * self.nb, n)
+        pa, l5 = self._dp(body_acc, 6 * self.nb, n)
+        pw, l6 = self._dp(joint_wrench, 6 * self.nb, n)
         check(lib.mecano_b200_rnea_full(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pqdd, pf, pt, pa, pw, flags, self._stream()), self._h)
         return tau
 
     def aba(self, q, qd, tau, qdd, fext=None, flags=0):
         n = q.shape[1]
-        pq, l0 = _dev_ptr_ld(q, self.nq, n)
-        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
-        pt, l2 = _dev_ptr_ld(tau, self.nv, n)
-        pqdd, l3 = _dev_ptr_ld(qdd, self.nv, n)
-        pf, l4 = _dev_ptr_ld(fext, 6 * self.nb, n)
+        pq, l0 = self._dp(q, self.nq, n)
+        pqd, l1 = self._dp(qd, self.nv, n)
+        pt, l2 = self._dp(tau, self.nv, n)
+        pqdd, l3 = self._dp(qdd, self.nv, n)
+        pf, l4 = self._dp(fext, 6 * self.nb, n)
         check(lib.mecano_b200_aba(self._h, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pt, pf, pqdd, flags, self._stream()), self._h)
         return qdd
 
@@ -141,13 +146,13 @@ class Engine:
 
     def aba_sources(self, q, qd, tau, qdd_in, qdd, tau_out=None, fext=None):
         n = q.shape[1]
-        pq, l0 = _dev_ptr_ld(q, self.nq, n)
-        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
-        pt, l2 = _dev_ptr_ld(tau, self.nv, n)
-        pi, l3 = _dev_ptr_ld(qdd_in, self.nv, n)
-        pqdd, l4 = _dev_ptr_ld(qdd, self.nv, n)
-        pto, l5 = _dev_ptr_ld(tau_out, self.nv, n)
-        pf, l6 = _dev_ptr_ld(fext, 6 * self.nb, n)
+        pq, l0 = self._dp(q, self.nq, n)
+        pqd, l1 = self._dp(qd, self.nv, n)
+        pt, l2 = self._dp(tau, self.nv, n)
+        pi, l3 = self._dp(qdd_in, self.nv, n)
+        pqdd, l4 = self._dp(qdd, self.nv, n)
+        pto, l5 = self._dp(tau_out, self.nv, n)
+        pf, l6 = self._dp(fext, 6 * self.nb, n)
         check(lib.mecano_b200_aba_sources(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pt, pi, pf, pqdd, pto, self._stream()), self._h)
         return qdd
 
@@ -166,9 +171,9 @@ class Engine:
     def crba(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
         """M: [nv*nv, n] (entry-major) or [n, nv*nv] (state-major) float64 CUDA tensor."""
         n = q.shape[1]
-        pq, ld = _dev_ptr_ld(q, self.nq, n)
+        pq, ld = self._dp(q, self.nq, n)
         if not (layout & _capi.CRBA_STATE_MAJOR):
-            pm, lm = _dev_ptr_ld(M, self.nv * self.nv, n)
+            pm, lm = self._dp(M, self.nv * self.nv, n)
             ld = _same_ld([ld, lm])
         else:
             if tuple(M.shape) != (n, self.nv * self.nv) or not M.is_contiguous():
@@ -181,7 +186,7 @@ class Engine:
         """M, C [nv*nv, n] entry-major; torch CUDA tensors or numpy arrays (host path)."""
         n = q.shape[1]
         host = isinstance(q, np.ndarray)
-        f = _host_ptr_ld if host else _dev_ptr_ld
+        f = _host_ptr_ld if host else self._dp
         pq, l0 = f(q, self.nq, n)
         pqd, l1 = f(qd, self.nv, n)
         pm, l2 = f(M, self.nv * self.nv, n)
@@ -196,7 +201,7 @@ class Engine:
         """M [nv*nv, n] entry-major, cmm [6*nv, n], com [4, n]; torch CUDA tensors or numpy arrays (host path)."""
         n = q.shape[1]
         host = isinstance(q, np.ndarray)
-        f = _host_ptr_ld if host else _dev_ptr_ld
+        f = _host_ptr_ld if host else self._dp
         pq, l0 = f(q, self.nq, n)
         pm, l1 = f(M, self.nv * self.nv, n)
         pa, l2 = f(cmm, 6 * self.nv, n)
@@ -211,7 +216,7 @@ class Engine:
         """out [6, n]; com [4, n] as written by crba_centroidal (None allowed for the world frame)."""
         n = q.shape[1]
         host = isinstance(q, np.ndarray)
-        f = _host_ptr_ld if host else _dev_ptr_ld
+        f = _host_ptr_ld if host else self._dp
         pq, l0 = f(q, self.nq, n)
         pqd, l1 = f(qd, self.nv, n)
         pc, l2 = f(com, 4, n)
@@ -225,9 +230,9 @@ class Engine:
     def integrate(self, dt, q, qd, qdd):
         """doubleIntegrateFromAcceleration on device matrices, in place."""
         n = q.shape[1]
-        pq, l0 = _dev_ptr_ld(q, self.nq, n)
-        pqd, l1 = _dev_ptr_ld(qd, self.nv, n)
-        pqdd, l2 = _dev_ptr_ld(qdd, self.nv, n)
+        pq, l0 = self._dp(q, self.nq, n)
+        pqd, l1 = self._dp(qd, self.nv, n)
+        pqdd, l2 = self._dp(qdd, self.nv, n)
         check(lib.mecano_b200_integrate(self._h, n, _same_ld([l0, l1, l2]), float(dt), pq, pqd, pqdd, self._stream()), self._h)
 
     def integrate_host(self, dt, q, qd, qdd):

@@ -621,11 +621,12 @@ def test_fp32_variant(torch_dev):
     assert not torch.isnan(M).any()
     e_crba = rel(M.cpu().numpy().reshape(nv, nv, n), o.crba_batch(q))
     print("fp32 variant, H37, relative to the oracle: rnea %.2e aba %.2e crba %.2e" % (e_rnea, e_aba, e_crba))
-    assert 1e-9 < e_rnea < 2e-4, "fp32 arithmetic must actually run (and stay within its tolerance)"
-    assert 1e-9 < e_crba < 2e-4
-    assert 1e-9 < e_aba < 5e-2
+    # tolerances a decade above the worst state of 2^20 (bench.py extras.fp32_variant: 1.7e-6 / 2.7e-6 / 5.7e-7)
+    assert 1e-9 < e_rnea < 1e-5, "fp32 arithmetic must actually run (and stay within its tolerance)"
+    assert 1e-9 < e_crba < 1e-5
+    assert 1e-9 < e_aba < 1e-4
     # host entry points run the same kernels
-    assert rel(ident.compute(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < 2e-4
+    assert rel(ident.compute(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < 1e-5
     # not covered: external wrenches, flags, by-products, trees outside the compiled configuration -> an error, not fp64
     ident.setExternalWrenches(torch.zeros((6 * t.nb, n), dtype=torch.float64, device=dev))
     with pytest.raises(mb.MecanoB200Error):
