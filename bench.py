@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 HUMANOID_SEED = 20251017
 STATE_SEED = 1234
 GRAVITY = (0.0, 0.0, -9.81)
+FP64_NOMINAL_TFLOPS = 37.2  # 148 SMs x 64 DFMA/clk x 2 flop x 1.965 GHz; the measured DFMA-chain figure is ~93 % of it
 METRIC = "RNEA+ABA+CRBA states/sec (37-DoF humanoid, fp64)"
 UNIT = "states/s"
 
@@ -227,6 +228,69 @@ def owned_zero_entries(system):
     return zeros
 
 
+def a7_configs(mb, torch, dev, device_index):
+    """BASELINE.json configs 1 and 2 on the 7-DoF revolute arm (MultiBodySystemRandomTools.nextRevoluteJointChain look-alike):
+    config 1 = InverseDynamicsCalculator on ONE state on the CPU (the C port, one thread; the latency a Mecano user sees per call),
+    next to the GPU's single-state latency (warp-per-state kernel); config 2 = batched RNEA of 65,536 random states on one B200,
+    every state verified against the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    import treedesc
+
+    elevator = mb.RigidBody("elevator")
+    mb.MultiBodySystemRandomTools.nextRevoluteJointChain(7, elevator, 7)
+    arm = mb.MultiBodySystem.toMultiBodySystemBasics(elevator)
+    oracle = oracle_lib.Oracle(treedesc.TreeDesc(**arm.describe()).contiguous(), gravity=GRAVITY)
+    rng = np.random.default_rng(STATE_SEED)
+    n2 = 65536
+    q, qd, qdd, _ = mb.MultiBodySystemRandomTools.nextState(rng, arm, n2)
+    out = {}
+    # config 1: one state per call, single thread
+    q1, qd1, qdd1 = (np.ascontiguousarray(a[:, :1]) for a in (q, qd, qdd))
+    for _ in range(2000):
+        oracle.rnea_batch(q1, qd1, qdd1, nthreads=1)
+    reps = 20000
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.rnea_batch(q1, qd1, qdd1, nthreads=1)
+    cpu_call_us = (time.perf_counter() - t0) / reps * 1e6
+    t0 = time.perf_counter()
+    oracle.rnea_batch(q, qd, qdd, nthreads=1)
+    cpu_state_us = (time.perf_counter() - t0) / n2 * 1e6
+    ident = mb.InverseDynamicsCalculator(arm, device=device_index)
+    ident.setGravitationalAcceleration(*GRAVITY)
+    tq, tqd, tqdd = (torch.from_numpy(a).to(dev) for a in (q, qd, qdd))
+    tau = torch.empty((7, n2), dtype=torch.float64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        for _ in range(5):
+            fn()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    one = timed(lambda: ident.compute(tq[:, :1], tqd[:, :1], tqdd[:, :1], tau[:, :1]), 200)
+    out["config1_a7_single_state"] = {
+        "cpu_us_per_call": cpu_call_us, "cpu_us_per_state_in_a_loop": cpu_state_us, "cpu_kind": "port (C restatement, 1 thread; per call includes the ctypes call)",
+        "gpu_us_per_call_device_resident": one * 1e3, "gpu_variant": ident.kernelInfo(1)["variant"],
+        "what": "BASELINE config 1: InverseDynamicsCalculator, 7-DoF revolute chain, a single state"}
+    ms = timed(lambda: ident.compute(tq, tqd, tqdd, tau), 50)
+    ref = oracle.rnea_batch(q, qd, qdd)
+    got = ident.compute(tq, tqd, tqdd, tau).cpu().numpy()
+    err = np.abs(got - ref).max(axis=0) / np.maximum(1.0, np.abs(ref).max(axis=0))
+    out["config2_a7_rnea_65536"] = {
+        "ms": ms, "states_per_s": n2 / (ms * 1e-3), "algorithmic_bytes_per_state": 224, "achieved_gbs": 224.0 * n2 / (ms * 1e-3) / 1e9,
+        "max_rel_error_vs_oracle_per_state": float(err.max()), "states_verified": n2, "tolerance": 1e-9, "variant": ident.kernelInfo(n2)["variant"],
+        "what": "BASELINE config 2: batched RNEA, 7-DoF revolute arm, 65,536 random states on one B200, every state compared with the oracle "
+                "(launch-latency regime: ~15 MB of traffic)"}
+    assert err.max() < 1e-9
+    return out
+
+
 _JSON_FD = None
 
 
@@ -383,7 +447,8 @@ def main():
         fl = flops.get(key, {}).get(name)
         if fl and fp64_peak:
             tf = fl * n / (ms * 1e-3) / 1e12
-            entry.update({"algorithmic_flops_per_state": fl, "achieved_tflops": tf, "fp64_frac": tf / fp64_peak})
+            entry.update({"algorithmic_flops_per_state": fl, "achieved_tflops": tf, "fp64_frac": tf / fp64_peak,
+                          "fp64_frac_of_nominal": tf / FP64_NOMINAL_TFLOPS})
             fe = exec_flops.get(key, {}).get(name)
             if fe:  # what the current routines execute for the same result (fewer: profiles/executed_flops.json)
                 entry.update({"executed_flops_per_state": fe, "executed_tflops": fe * n / (ms * 1e-3) / 1e12,
@@ -495,6 +560,8 @@ def main():
         del M32
         extras["fp32_variant"] = dict(f32, what="optional single-precision variant (mecano_b200_set_precision): arithmetic in float, all buffers fp64; "
                                                 "error per state = max |fp32 - fp64| / max(1, max |fp64|), quantiles over the batch")
+    if rank == 0 and world == 1 and not args.no_extras and not args.no_cpu:
+        extras.update(a7_configs(mb, torch, dev, local_rank))
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     # The dominant kernel is reported against the roofline that binds it: RNEA / ABA sit above the machine
     # balance (FP64 pipe), CRBA below it (HBM, write-dominated).  MEASURED_PEAKS.json has no FP64 figure, so the FP64
@@ -520,7 +587,7 @@ def main():
         tr = tr_all.get(dom)
         if tr:
             roofline["traffic"] = tr["bytes_per_state"] * n
-            roofline["traffic_note"] = tr.get("note")
+            roofline["traffic_note"] = "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/dram_traffic.json: %s)" % tr.get("note")
 
     line = None
     if rank == 0:
@@ -550,57 +617,85 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
 
-    # ---- end to end: the same step through the host-pointer C-ABI entry points with pinned host buffers
+    # ---- end to end: the same step through the public host API with pinned host matrices, host <-> device copies inside the
+    # timed region.  ONE call per step (MultiBodyDynamicsStep.compute -> mecano_b200_step_host: q / qd cross PCIe once); with
+    # N > 1 rank 0 drives all N GPUs through one multi-device call (mecano_b200_multi_step_host slices the state-minor batch)
+    # while the other ranks wait at the barrier.  The headline `e2e` returns the dense mass matrix as Mecano does; the packed
+    # layout (unique non-zero entries) is reported next to it under extras.
     if not args.no_e2e:
-        hn = n
-        pin = lambda rows: torch.empty((rows, hn), dtype=torch.float64).pin_memory()  # noqa: E731
-        hq, hqd, hqdd, htau_in = pin(nq), pin(nv), pin(nv), pin(nv)
-        hq.copy_(q.cpu()); hqd.copy_(qd.cpu()); hqdd.copy_(qdd.cpu()); htau_in.copy_(tau_in.cpu())
-        htau, hqdd_out, hM = pin(nv), pin(nv), pin(nv * nv)
-        nq_, nqd_, nqdd_, ntau_in, ntau, nqdd_out, nM = (t.numpy() for t in (hq, hqd, hqdd, htau_in, htau, hqdd_out, hM))
-
-        def host_step():
-            ident.compute(nq_, nqd_, nqdd_, ntau)
-            fdyn.compute(nq_, nqd_, ntau_in, nqdd_out)
-            crba.getMassMatrix(nq_, nM)
-
-        host_step()  # warm-up (allocates the staging buffers)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            host_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        dt = sharding.max_over_ranks(dt, dev)
         if rank == 0:
-            line["e2e"] = {"value": hn * world / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
-                           "h2d_bytes_per_step": int(8 * (nq * 3 + nv * 4) * hn), "d2h_bytes_per_step": int(8 * (2 * nv + nv * nv) * hn),
-                           "api": "InverseDynamicsCalculator.compute / ForwardDynamicsCalculator.compute / CompositeRigidBodyMassMatrixCalculator.getMassMatrix "
-                                  "on pinned host matrices -> mecano_b200_{rnea,aba,crba}_host", "check": float(np.abs(ntau).max())}
-        # the same step with the mass matrix in the calculator's own (pinned) matrix: from the second call on the structurally
-        # zero entries are not transferred again (extras only: the headline e2e above rewrites and re-reads the dense matrix)
-        if world == 1:
-            del hM, nM
-            owned_h = mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank)
+            devices = list(range(world)) if world > 1 else local_rank
+            stepc = mb.MultiBodyDynamicsStep(system, device=devices)
+            stepc.setGravitationalAcceleration(*GRAVITY)
+            hn = n * world
+            rows_dense, rows_packed = nv * nv, stepc.getMassMatrixRows(packed=True)
 
-            def host_step_owned():
-                ident.compute(nq_, nqd_, nqdd_, ntau)
-                fdyn.compute(nq_, nqd_, ntau_in, nqdd_out)
-                return owned_h.getMassMatrix(nq_)
+            def pin(rows, cols):
+                return torch.empty((rows, cols), dtype=torch.float64).pin_memory()
 
-            host_step_owned()
-            host_step_owned()
-            t0 = time.perf_counter()
-            for _ in range(args.e2e_steps):
-                Mo = host_step_owned()
-            torch.cuda.synchronize()
-            dto = (time.perf_counter() - t0) / args.e2e_steps
-            nnz = nv * nv - len(set(owned_zero_entries(system)))
-            line["extras"]["e2e_owned_mass_matrix"] = {
-                "value": hn / dto, "unit": UNIT, "ms_per_step": dto * 1e3, "h2d_bytes_per_step": int(8 * (nq * 3 + nv * 4) * hn),
-                "d2h_bytes_per_step": int(8 * (2 * nv + nnz) * hn), "check": float(np.abs(Mo).max()),
-                "what": "as e2e, but getMassMatrix(q) returns the calculator-owned pinned matrix: %d of %d entries are structurally zero, "
-                        "written once and not transferred again" % (nv * nv - nnz, nv * nv)}
+            # pinned host memory for the whole job; if the box cannot pin that much, halve the states per GPU and say so
+            while True:
+                try:
+                    hq, hqd, hqdd, htau_in, htau, hqdd_out, hM = pin(nq, hn), pin(nv, hn), pin(nv, hn), pin(nv, hn), pin(nv, hn), pin(nv, hn), pin(rows_dense, hn)
+                    break
+                except RuntimeError:
+                    hq = hqd = hqdd = htau_in = htau = hqdd_out = hM = None
+                    hn //= 2
+                    if hn < 65536 * world:
+                        raise
+            per = hn // world
+            for g in range(world):  # every GPU's slice holds the same synthetic states as the device-resident run of rank 0
+                sl = slice(g * per, (g + 1) * per)
+                hq[:, sl].copy_(q[:, :per]); hqd[:, sl].copy_(qd[:, :per]); hqdd[:, sl].copy_(qdd[:, :per]); htau_in[:, sl].copy_(tau_in[:, :per])
+            nq_, nqd_, nqdd_, ntau_in, ntau, nqdd_out, nM = (t_.numpy() for t_ in (hq, hqd, hqdd, htau_in, htau, hqdd_out, hM))
+
+            def host_step(packed):
+                Mv = nM[:rows_packed] if packed else nM
+                stepc.compute(nq_, nqd_, qdd=nqdd_, tau=ntau_in, tauOut=ntau, qddOut=nqdd_out, massMatrix=Mv, packed=packed)
+
+            def timed_host(packed):
+                host_step(packed)  # warm-up (allocates the staging buffers)
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    host_step(packed)
+                return (time.perf_counter() - t0) / args.e2e_steps  # the call returns when the outputs are complete on the host
+
+            # PCIe denominators measured live: one large pinned copy each way on device 0
+            pcie = {}
+            probe = torch.empty(1 << 27, dtype=torch.float64, device=dev)  # 1 GiB
+            hprobe = torch.empty(1 << 27, dtype=torch.float64).pin_memory()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for name, (dst, src) in (("d2h", (hprobe, probe)), ("h2d", (probe, hprobe))):
+                best = 0.0
+                for _ in range(3):
+                    ev0.record(); dst.copy_(src, non_blocking=True); ev1.record(); torch.cuda.synchronize()
+                    best = max(best, 8.0 * (1 << 27) / (ev0.elapsed_time(ev1) * 1e-3) / 1e9)
+                pcie[name + "_gbs_peak"] = best
+            del probe, hprobe
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            h2d = int(8 * (nq + 3 * nv) * hn)
+            dt = timed_host(False)
+            d2h = int(8 * (2 * nv + rows_dense) * hn)
+            api = ("MultiBodyDynamicsStep.compute (one call: inverse dynamics, forward dynamics, mass matrix) on pinned host matrices -> "
+                   + ("mecano_b200_multi_step_host over %d GPUs from one thread" % world if world > 1 else "mecano_b200_step_host"))
+            line["e2e"] = {"value": hn / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "steps": args.e2e_steps, "states_per_gpu": per,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "mass_matrix_layout": "dense entry-major [nv*nv][N] (Mecano's symmetric matrix, zeros included)",
+                           "api": api, "check": float(np.abs(ntau).max()), "clock": "host wall clock around the blocking call",
+                           "roofline": {"bound": "pcie", "achieved": d2h / dt / 1e9 / world, "peak": pcie["d2h_gbs_peak"], "unit": "GB/s per GPU, device -> host",
+                                        "frac": d2h / dt / 1e9 / world / pcie["d2h_gbs_peak"], "h2d_gbs_peak": pcie["h2d_gbs_peak"],
+                                        "peak_source": "1 GiB pinned cudaMemcpy each way on GPU 0, measured in this run"}}
+            dtp = timed_host(True)
+            d2hp = int(8 * (2 * nv + rows_packed) * hn)
+            line["extras"]["e2e_packed"] = {
+                "value": hn / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": args.e2e_steps, "states_per_gpu": per, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2hp, "check": float(np.abs(nM[:rows_packed]).max()),
+                "pcie_d2h_frac": d2hp / dtp / 1e9 / world / pcie["d2h_gbs_peak"],
+                "what": "as e2e, mass matrix in the packed layout (MECANO_B200_CRBA_PACKED): the %d unique entries that are not structurally zero "
+                        "instead of %d, with the index map exported for scattering into a DMatrixRMaj" % (rows_packed, rows_dense)}
+        if world > 1:
+            dist.barrier()
     elif rank == 0:
         line["e2e"] = None
 

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MECANO_B200_VERSION 100
+#define MECANO_B200_VERSION 200
 
 /* joint types (M/multiBodySystem/{RevoluteJoint,PrismaticJoint,SixDoFJoint}.java) */
 #define MECANO_B200_REVOLUTE 0
@@ -68,6 +68,15 @@ extern "C" {
  * flag from the second call on: the structurally zero entries are then neither written (device entry point) nor transferred
  * (host entry point, entry-major layout), everything else is recomputed.  The first call into a buffer must not set it. */
 #define MECANO_B200_CRBA_ZEROS_PRESENT 0x2u
+/* Packed layout: one row per UNIQUE entry that is not structurally zero, M[p * ld + s], p = 0 .. mecano_b200_crba_packed_size() - 1
+ * (entry-major like the default, coalesced).  Mecano fills the dense symmetric matrix by writing every computed entry twice
+ * (setSymmetricEntry, CompositeRigidBodyMassMatrixCalculator.java:700-707, :772-797) on top of massMatrix.zero() (:296); the packed
+ * layout carries each computed entry once and no zeros: 362 rows instead of 1,369 for a 37-DoF humanoid, which is what the
+ * host path (PCIe-bound) and a caller that scatters into its own DMatrixRMaj want.  mecano_b200_crba_packed_index() gives the
+ * (row, column) of every packed row: M[row[p]][col[p]] = M[col[p]][row[p]] = packed[p]; rows are grouped by column, and
+ * within a column ordered along the path from the root body to the column's joint.  Not combinable with STATE_MAJOR /
+ * ZEROS_PRESENT; plain mass-matrix calls only (the by-product and fp32 entry points write the dense layout). */
+#define MECANO_B200_CRBA_PACKED 0x4u
 
 /* kernel selection */
 #define MECANO_B200_VARIANT_AUTO 0
@@ -176,6 +185,10 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask);
 int mecano_b200_n_dofs(const mecano_b200_handle *h);
 int mecano_b200_n_cfg(const mecano_b200_handle *h);
 int mecano_b200_n_bodies(const mecano_b200_handle *h);
+/* Packed mass-matrix layout (MECANO_B200_CRBA_PACKED): number of packed rows, and the dense (row, col) of each (arrays of
+ * mecano_b200_crba_packed_size() entries, either may be NULL). */
+int mecano_b200_crba_packed_size(const mecano_b200_handle *h);
+int mecano_b200_crba_packed_index(const mecano_b200_handle *h, int32_t *row, int32_t *col);
 
 /*
  * Device-pointer entry points.  All pointers are device memory on the handle's device, 8-byte
@@ -266,6 +279,48 @@ int mecano_b200_aba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, co
 int mecano_b200_aba_sources_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
                                  const double *qdd_in, const double *fext, double *qdd, double *tau_out);
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
+/*
+ * One host call for the three calculators on the same joint states -- what a controller or simulator does per tick with Mecano:
+ * set the joint state once (MultiBodySystemTools.insertJointsState, M/tools/MultiBodySystemTools.java:1578), updateFramesRecursively()
+ * once (RigidBodyBasics.java:104-112), then InverseDynamicsCalculator.compute(qdd) (:496), ForwardDynamicsCalculator.compute(tau)
+ * (:508) and CompositeRigidBodyMassMatrixCalculator.getMassMatrix() (:344).  q and qd cross PCIe once per chunk instead of once
+ * per calculator, and the three kernels run back to back on the resident chunk.
+ *   qdd_in  [n_dofs][ld]  joint accelerations for inverse dynamics     -> tau_out    [n_dofs][ld]  (both NULL: skip RNEA)
+ *   tau_in  [n_dofs][ld]  joint efforts for forward dynamics           -> qdd_out    [n_dofs][ld]  (both NULL: skip ABA)
+ *   mass_matrix           layout as mecano_b200_crba_host (ENTRY_MAJOR, STATE_MAJOR or PACKED)     (NULL: skip CRBA)
+ * fext (nullable) applies to both dynamics calculators.  Results are bit-identical to the three separate calls.
+ */
+int mecano_b200_step_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd_in,
+                          const double *tau_in, const double *fext, double *tau_out, double *qdd_out, double *mass_matrix, uint32_t layout);
+
+/*
+ * Several GPUs of one box behind one call.  States are independent, so a batch is cut into disjoint contiguous
+ * slices of the state index, one per device; there is no exchange step and no collective (NCCL is not linked).  A multi-device
+ * engine owns one handle (constant tables, traversal programs, staging buffers, two streams) per listed device; its host entry
+ * points slice the state-minor matrices in place (a slice of a DoF-major matrix is the same matrix with an offset pointer and
+ * the same ld: cudaMemcpy2DAsync does the strided copy), issue the chunks of all devices round-robin from the calling thread
+ * and synchronise once at the end.  A device may be listed more than once (each entry gets its own handle and pipeline).
+ * Results are bit-identical to the single-device call whatever the device list: every state is evaluated by the same
+ * instruction sequence, and the thread- / warp-per-state choice of VARIANT_AUTO is made on the size of the whole batch.
+ *   mecano_b200_multi_handle(m, i)   the handle of entry i, for the per-handle setters (variant, precision, source modes, ...);
+ *                                    compute calls on it bypass the slicing
+ *   mecano_b200_multi_slice          the slice [start, start + count) of an n_states batch that entry i evaluates
+ */
+typedef struct mecano_b200_multi mecano_b200_multi;
+int mecano_b200_multi_create(const mecano_b200_tree_desc *desc, const int32_t *devices, int n_devices, mecano_b200_multi **out);
+void mecano_b200_multi_destroy(mecano_b200_multi *m);
+const char *mecano_b200_multi_last_error(const mecano_b200_multi *m);
+int mecano_b200_multi_size(const mecano_b200_multi *m);
+mecano_b200_handle *mecano_b200_multi_handle(mecano_b200_multi *m, int i);
+int mecano_b200_multi_slice(const mecano_b200_multi *m, int64_t n_states, int i, int64_t *start, int64_t *count);
+int mecano_b200_multi_set_gravity(mecano_b200_multi *m, double gx, double gy, double gz);
+int mecano_b200_multi_rnea_host(mecano_b200_multi *m, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd,
+                                const double *fext, double *tau, uint32_t flags);
+int mecano_b200_multi_aba_host(mecano_b200_multi *m, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *tau,
+                               const double *fext, double *qdd, uint32_t flags);
+int mecano_b200_multi_crba_host(mecano_b200_multi *m, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, uint32_t layout);
+int mecano_b200_multi_step_host(mecano_b200_multi *m, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd_in,
+                                const double *tau_in, const double *fext, double *tau_out, double *qdd_out, double *mass_matrix, uint32_t layout);
 int mecano_b200_coriolis_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, double *mass_matrix,
                               double *coriolis_matrix);
 int mecano_b200_crba_centroidal_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *mass_matrix, double *cmm,

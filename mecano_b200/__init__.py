@@ -7,7 +7,7 @@ not been built: there is no CPU fallback.
 from . import _capi  # noqa: F401  (raises ImportError if libmecano_b200.so is missing)
 from ._capi import MecanoB200Error  # noqa: F401
 from .calculators import (CompositeRigidBodyMassMatrixCalculator, ForwardDynamicsCalculator, InverseDynamicsCalculator, JointSourceMode,  # noqa: F401
-                          MatrixDimensionException, MultiBodySystemStateIntegrator)
-from .engine import Engine, measure_fp64_peak, measure_hbm_peak  # noqa: F401
+                          MatrixDimensionException, MultiBodyDynamicsStep, MultiBodySystemStateIntegrator)
+from .engine import Engine, MultiDeviceEngine, measure_fp64_peak, measure_hbm_peak  # noqa: F401
 from .multibody import (FixedJoint, JointMatrixIndexProvider, MultiBodySystem, MultiBodySystemRandomTools, PrismaticJoint, RevoluteJoint,  # noqa: F401
                         RigidBody, RigidBodyTransform, ScrewTheoryException, SixDoFJoint)

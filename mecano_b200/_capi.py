@@ -26,6 +26,7 @@ REVOLUTE, PRISMATIC, SIXDOF = 0, 1, 2
 RNEA_NO_CORIOLIS, RNEA_NO_ACCELERATIONS = 1, 2
 CRBA_ENTRY_MAJOR, CRBA_STATE_MAJOR = 0, 1
 CRBA_ZEROS_PRESENT = 2  # structurally zero entries already hold zeros (same tree, same buffer): not written / transferred again
+CRBA_PACKED = 4  # one row per unique, structurally non-zero entry (mecano_b200_crba_packed_index gives the map)
 ALGO_RNEA, ALGO_ABA, ALGO_CRBA = 0, 1, 2
 FRAME_WORLD, FRAME_CENTER_OF_MASS = 0, 1
 
@@ -65,6 +66,10 @@ EXPORTS = [
     "mecano_b200_set_joint_source_modes", "mecano_b200_aba_sources", "mecano_b200_aba_sources_host",
     "mecano_b200_crba_centroidal", "mecano_b200_centroidal_convective_term", "mecano_b200_crba_centroidal_host",
     "mecano_b200_centroidal_convective_term_host", "mecano_b200_coriolis", "mecano_b200_coriolis_host", "mecano_b200_set_grid_limit", "mecano_b200_set_precision",
+    "mecano_b200_crba_packed_size", "mecano_b200_crba_packed_index", "mecano_b200_step_host",
+    "mecano_b200_multi_create", "mecano_b200_multi_destroy", "mecano_b200_multi_last_error", "mecano_b200_multi_size", "mecano_b200_multi_handle",
+    "mecano_b200_multi_slice", "mecano_b200_multi_set_gravity", "mecano_b200_multi_rnea_host", "mecano_b200_multi_aba_host",
+    "mecano_b200_multi_crba_host", "mecano_b200_multi_step_host",
 ]
 
 lib.mecano_b200_create.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.POINTER(c_vp)]
@@ -104,6 +109,23 @@ lib.mecano_b200_measure_fp64_peak.argtypes = [ctypes.c_int, c_dp]
 lib.mecano_b200_measure_hbm_peak.argtypes = [ctypes.c_int, c_dp]
 lib.mecano_b200_host_alloc.argtypes = [ctypes.POINTER(c_vp), c_i64]
 lib.mecano_b200_host_free.argtypes = [c_vp]
+lib.mecano_b200_crba_packed_size.argtypes = [c_vp]
+lib.mecano_b200_crba_packed_index.argtypes = [c_vp, c_vp, c_vp]
+lib.mecano_b200_step_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
+lib.mecano_b200_multi_create.argtypes = [ctypes.POINTER(TreeDesc), c_vp, ctypes.c_int, ctypes.POINTER(c_vp)]
+lib.mecano_b200_multi_destroy.argtypes = [c_vp]
+lib.mecano_b200_multi_destroy.restype = None
+lib.mecano_b200_multi_last_error.argtypes = [c_vp]
+lib.mecano_b200_multi_last_error.restype = ctypes.c_char_p
+lib.mecano_b200_multi_size.argtypes = [c_vp]
+lib.mecano_b200_multi_handle.argtypes = [c_vp, ctypes.c_int]
+lib.mecano_b200_multi_handle.restype = c_vp
+lib.mecano_b200_multi_slice.argtypes = [c_vp, c_i64, ctypes.c_int, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]
+lib.mecano_b200_multi_set_gravity.argtypes = [c_vp, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+lib.mecano_b200_multi_rnea_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
+lib.mecano_b200_multi_aba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
+lib.mecano_b200_multi_crba_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32]
+lib.mecano_b200_multi_step_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_u32]
 lib.mecano_b200_generate_source.argtypes = [ctypes.POINTER(TreeDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, c_i64, ctypes.POINTER(c_i64)]
 
 

@@ -13,7 +13,7 @@ CPU implementation behind these classes.
 import numpy as np
 
 from . import _capi
-from .engine import Engine
+from .engine import Engine, MultiDeviceEngine
 from .multibody import MultiBodySystem, RigidBody
 
 
@@ -25,12 +25,19 @@ def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
 
+def _make_engine(input, device):
+    """device: one CUDA device index, or a list of them (MultiDeviceEngine: host matrices sliced across the GPUs of the box)."""
+    if isinstance(device, (list, tuple)):
+        return MultiDeviceEngine(input.tables().contents, device, keepalive=input)
+    return Engine(input.tables().contents, device, keepalive=input)
+
+
 class _BatchedCalculator:
     def __init__(self, input, device=0):
         if isinstance(input, RigidBody):  # InverseDynamicsCalculator(RigidBodyReadOnly rootBody), :186
             input = MultiBodySystem.toMultiBodySystemBasics(input)
         self._input = input
-        self._engine = Engine(input.tables().contents, device, keepalive=input)
+        self._engine = _make_engine(input, device)
         self._fext = None
         self._gravity = (0.0, 0.0, 0.0)
 
@@ -399,9 +406,16 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         self._M = None
         self._com = self._com_q = None
 
-    def getMassMatrix(self, q=None, massMatrix=None, stateMajor=False):
+    def getMassMatrixPackedIndex(self):
+        """(row, col) int32 arrays of the packed layout: packed row p of getMassMatrix(q, packed=True) is entry (row[p], col[p])
+        of the symmetric mass matrix, and every entry the arrays do not list (in either order) is structurally zero."""
+        return self._engine.packed_index()
+
+    def getMassMatrix(self, q=None, massMatrix=None, stateMajor=False, packed=False):
         """Mass matrices for N states.  Default layout [nDoFs*nDoFs, N] (entry (i, j) of state s at [i*nDoFs + j, s]);
-        stateMajor=True gives [N, nDoFs*nDoFs], i.e. one Mecano-style dense row-major nDoFs x nDoFs matrix per state.
+        stateMajor=True gives [N, nDoFs*nDoFs], i.e. one Mecano-style dense row-major nDoFs x nDoFs matrix per state;
+        packed=True gives [P, N] with one row per unique entry that is not structurally zero (getMassMatrixPackedIndex() maps
+        rows to entries; 362 rows instead of 1,369 for a 37-DoF humanoid), for callers that scatter into their own matrices.
 
         Without `massMatrix` the calculator owns the result like Mecano's does (getMassMatrix() returns a reference to the
         internal matrix, CompositeRigidBodyMassMatrixCalculator.java:344-348): one buffer per batch shape, reused by later
@@ -413,6 +427,15 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
         n = q.shape[1] if q.ndim == 2 else -1
         self._check("q", q, nq, n)
+        if packed:
+            if stateMajor:
+                raise ValueError("packed and stateMajor are different layouts")
+            if massMatrix is None:
+                massMatrix = self._empty_like(q, self._engine.packed_size(), n)
+            self._check("massMatrix", massMatrix, self._engine.packed_size(), n)
+            (self._engine.crba if _is_torch(q) else self._engine.crba_host)(q, massMatrix, _capi.CRBA_PACKED)
+            self._M = massMatrix
+            return massMatrix
         shape = (n, nv * nv) if stateMajor else (nv * nv, n)
         layout = _capi.CRBA_STATE_MAJOR if stateMajor else _capi.CRBA_ENTRY_MAJOR
         if massMatrix is None:
@@ -448,6 +471,43 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
             return torch.empty((rows, ld), dtype=torch.float64).pin_memory().numpy()[:, :n]
         except Exception:
             return np.empty((rows, ld), dtype=np.float64)[:, :n]
+
+
+class MultiBodyDynamicsStep:
+    """The three calculators on the same joint states behind one host call (mecano_b200_step_host / mecano_b200_multi_step_host):
+    what a Mecano user does per control tick -- insertJointsState once (MultiBodySystemTools.java:1578), updateFramesRecursively()
+    once (RigidBodyBasics.java:104-112), then InverseDynamicsCalculator.compute(qdd), ForwardDynamicsCalculator.compute(tau) and
+    CompositeRigidBodyMassMatrixCalculator.getMassMatrix().  Host (numpy, ideally pinned) matrices; `device` may be a list of
+    GPUs, in which case the batch is sliced across them.  Results are bit-identical to the three calculators called one by one."""
+
+    def __init__(self, input, device=0):
+        if isinstance(input, RigidBody):
+            input = MultiBodySystem.toMultiBodySystemBasics(input)
+        self._input = input
+        self._engine = _make_engine(input, device)
+
+    def setGravitationalAcceleration(self, *gravity):
+        g = (0.0, 0.0, float(gravity[0])) if len(gravity) == 1 and np.isscalar(gravity[0]) else tuple(float(v) for v in (gravity[0] if len(gravity) == 1 else gravity))
+        if len(g) != 3:
+            raise ValueError("gravity must have 3 components")
+        self._engine.set_gravity(*g)
+
+    def setKernelVariant(self, variant):
+        self._engine.set_variant({"auto": 0, "thread": 1, "warp": 2}[variant] if isinstance(variant, str) else int(variant))
+        return self
+
+    def getMassMatrixPackedIndex(self):
+        return self._engine.packed_index()
+
+    def getMassMatrixRows(self, packed=False):
+        return self._engine.packed_size() if packed else self._engine.nv * self._engine.nv
+
+    def compute(self, q, qd, qdd=None, tau=None, tauOut=None, qddOut=None, massMatrix=None, packed=False, stateMajor=False):
+        """qdd -> tauOut (inverse dynamics), tau -> qddOut (forward dynamics), massMatrix (layout as getMassMatrix): each part runs
+        if its matrices are given."""
+        layout = _capi.CRBA_PACKED if packed else (_capi.CRBA_STATE_MAJOR if stateMajor else _capi.CRBA_ENTRY_MAJOR)
+        self._engine.step_host(q, qd, qdd_in=qdd, tau_in=tau, tau_out=tauOut, qdd_out=qddOut, M=massMatrix, layout=layout)
+        return tauOut, qddOut, massMatrix
 
 
 class MultiBodySystemStateIntegrator:

@@ -120,6 +120,8 @@ struct RunOpts
    double *root_wrench = nullptr;                        // RNEA: wrench at the root (root frame)
    double *cor = nullptr;                                // MB_CORIOLIS: the Coriolis matrix
    bool zero_gravity = false;
+   int64_t variant_n = 0; // batch size VARIANT_AUTO decides on (0: n of this launch); the host pipelines pass the size of the whole call so
+                          // that every chunk and every device slice of one call runs the same kernel (bit-identical results)
 };
 
 int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
@@ -134,10 +136,13 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "joints in ACCELERATION_SOURCE mode need their accelerations: call mecano_b200_aba_sources");
    if (h->n_accel_source == 0)
       x2 = nullptr; // nothing reads it: the plain kernels serve the call
+   const bool packed = algo == MB_CRBA && (flags & MECANO_B200_CRBA_PACKED);
+   if (packed && ((flags & (MECANO_B200_CRBA_STATE_MAJOR | MECANO_B200_CRBA_ZEROS_PRESENT)) || opt.cmm || opt.com))
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the packed mass-matrix layout does not combine with STATE_MAJOR / ZEROS_PRESENT or the centroidal by-products");
    if (h->fp32)
    {
       // the optional fp32 variant: plain calls on the thread-per-state kernels only, never a silent fp64 substitute
-      if (algo > MB_CRBA || fext || opt.body_acc || opt.joint_wrench || x2 || opt.cmm || opt.root_wrench || flags != 0)
+      if (algo > MB_CRBA || packed || fext || opt.body_acc || opt.joint_wrench || x2 || opt.cmm || opt.root_wrench || flags != 0)
          return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant covers plain RNEA / ABA / CRBA calls only (no external wrenches, flags, by-products)");
       if (!h->plan[algo].fp32_ok)
          return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant is compiled for the launch configuration of humanoid-sized trees only");
@@ -145,8 +150,10 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
    // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
-   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench || algo == MB_CORIOLIS || h->fp32;
-   const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && n < h->warp_below[algo]));
+   // (so does the packed mass-matrix layout: its row numbering follows the thread-per-state traversal)
+   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench || algo == MB_CORIOLIS || h->fp32 || packed;
+   const int64_t vn = opt.variant_n > 0 ? opt.variant_n : n;
+   const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && vn < h->warp_below[algo]));
    if (use_warp)
    {
       if (!h->warp_ok)
@@ -201,7 +208,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    a.ws = h->d_ws[ws_slot];
    a.ws_ld = 0;
    a.zero_entries = h->d_zero;
-   a.n_zero = (algo == MB_CRBA && (flags & MECANO_B200_CRBA_ZEROS_PRESENT)) ? 0 : (int32_t)h->tree.zero_entries.size();
+   a.n_zero = (algo == MB_CRBA && (flags & (MECANO_B200_CRBA_ZEROS_PRESENT | MECANO_B200_CRBA_PACKED))) ? 0 : (int32_t)h->tree.zero_entries.size();
    a.n = n; a.ld = ld;
    a.ld_qd = a.ld_x = ld;
    if (algo == MB_RNEA && (flags & (MECANO_B200_RNEA_NO_CORIOLIS | MECANO_B200_RNEA_NO_ACCELERATIONS)))
@@ -326,84 +333,240 @@ cudaError_t copy_rows(double *dst, size_t dpitch, const double *src, size_t spit
    return cudaMemcpy2DAsync(dst, dpitch * sizeof(double), src, spitch * sizeof(double), w * sizeof(double), rows, kind, s);
 }
 
-// Host-pointer pipeline: two slots, each with its own stream; H2D of chunk k+1 overlaps the kernel and D2H of chunk k.
+// ------------------------------------------------------------------------------------------------ host-pointer pipeline
+// One host-pointer call on one handle ("lane"): pointers already offset to the lane's first state.  MB_STEP = the fused call
+// of the three calculators (mecano_b200_step_host).
+constexpr int MB_STEP = 100;
+struct HostJob
+{
+   int algo = MB_RNEA;
+   int64_t n = 0, ld = 0;
+   int64_t variant_n = 0;                               // size of the whole call (all lanes)
+   const double *q = nullptr, *qd = nullptr, *x = nullptr, *fext = nullptr, *x2 = nullptr; // x: qdd (RNEA) / tau (ABA); MB_STEP: qdd_in
+   const double *tau_in = nullptr;                       // MB_STEP: efforts for forward dynamics
+   double *out = nullptr;                                // tau (RNEA) / qdd (ABA) / mass matrix (CRBA); MB_STEP: tau_out
+   double *body_acc = nullptr, *joint_wrench = nullptr, *tau_out = nullptr; // by-products (RNEA), efforts of pass four (ABA with source modes)
+   double *qdd_out = nullptr, *M = nullptr;              // MB_STEP
+   uint32_t flags = 0;                                   // RNEA flags / CRBA layout (MB_STEP: layout)
+   // pipeline state
+   size_t chunk = 0, in_rows = 0, out_rows = 0, m_rows = 0;
+   int64_t s0 = 0;
+   int slot = 0;
+};
+
+size_t mass_matrix_rows(const mecano_b200_handle *h, uint32_t layout)
+{
+   return (layout & MECANO_B200_CRBA_PACKED) ? h->tree.packed_row.size() : (size_t)h->tree.nv * (size_t)h->tree.nv;
+}
+
+// argument checks, chunk size, staging buffers.  Two slots per handle, each with its own stream: H2D of chunk k+1 overlaps the
+// kernels and the D2H of chunk k.
+int host_begin(mecano_b200_handle *h, HostJob &j)
+{
+   int rc = check_batch(h, j.n, j.ld);
+   if (rc) return rc;
+   if (j.n == 0) return MECANO_B200_OK;
+   const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
+   if (j.algo == MB_STEP)
+   {
+      const bool rnea = j.x || j.out, aba = j.tau_in || j.qdd_out;
+      if (!j.q || ((rnea || aba) && !j.qd) || (rnea && (!j.x || !j.out)) || (aba && (!j.tau_in || !j.qdd_out)) || (!rnea && !aba && !j.M))
+         return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+      if (aba && h->n_accel_source > 0)
+         return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "joints in ACCELERATION_SOURCE mode need their accelerations: call mecano_b200_aba_sources_host");
+      j.m_rows = j.M ? mass_matrix_rows(h, j.flags) : 0;
+      j.in_rows = nq + (rnea || aba ? nv : 0) + (rnea ? nv : 0) + (aba ? nv : 0) + (j.fext ? 6 * nb : 0);
+      j.out_rows = (rnea ? nv : 0) + (aba ? nv : 0) + j.m_rows;
+   }
+   else
+   {
+      if (!j.q || !j.out || (j.algo != MB_CRBA && (!j.qd || !j.x)))
+         return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+      // state-major: the whole per-state block is copied back from the staging buffer, which other calls on this handle reuse, so
+      // the kernel must write the structural zeros there every time (the transfer saving of ZEROS_PRESENT is entry-major only)
+      if (j.algo == MB_CRBA && (j.flags & MECANO_B200_CRBA_STATE_MAJOR))
+         j.flags &= ~MECANO_B200_CRBA_ZEROS_PRESENT;
+      j.m_rows = j.algo == MB_CRBA ? mass_matrix_rows(h, j.flags) : 0;
+      j.in_rows = j.algo == MB_CRBA ? nq : nq + 2 * nv + (j.fext ? 6 * nb : 0) + (j.x2 ? nv : 0);
+      j.out_rows = j.algo == MB_CRBA ? j.m_rows : nv + (j.body_acc ? 6 * nb : 0) + (j.joint_wrench ? 6 * nb : 0) + (j.tau_out ? nv : 0);
+   }
+   if ((j.flags & MECANO_B200_CRBA_PACKED) && (j.flags & (MECANO_B200_CRBA_STATE_MAJOR | MECANO_B200_CRBA_ZEROS_PRESENT)) && (j.algo == MB_CRBA || j.algo == MB_STEP))
+      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the packed mass-matrix layout does not combine with STATE_MAJOR / ZEROS_PRESENT");
+   // chunk: ~64 MB of rows per slot, at least 4096 states, multiple of 256
+   size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)(j.in_rows + j.out_rows));
+   chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
+   chunk = std::min<size_t>(chunk, ((size_t)j.n + 255) & ~(size_t)255);
+   j.chunk = chunk;
+   j.s0 = 0;
+   j.slot = 0;
+   MB_ON_DEVICE(h);
+   return ensure_pipeline(h, (j.in_rows + j.out_rows) * chunk);
+}
+
+// issues the next chunk of the job (H2D, kernels, D2H on the slot's stream); asynchronous with pinned host memory
+int host_issue_chunk(mecano_b200_handle *h, HostJob &j)
+{
+   if (j.s0 >= j.n) return MECANO_B200_OK;
+   MB_ON_DEVICE(h);
+   const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb, chunk = j.chunk, ld = (size_t)j.ld;
+   const int64_t s0 = j.s0;
+   const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, j.n - s0);
+   const int slot = j.slot;
+   cudaStream_t st = h->streams[slot];
+   j.s0 += (int64_t)chunk;
+   j.slot ^= 1;
+   // the slot is reused every other chunk: stream order already serialises it
+   double *p = h->stage[slot];
+   auto take = [&](size_t rows) { double *r = p; p += rows * chunk; return r; };
+   auto h2d = [&](double *dst, const double *src, size_t rows) { return copy_rows(dst, chunk, src + s0, ld, w, rows, cudaMemcpyHostToDevice, st); };
+   auto d2h = [&](double *dst, const double *src, size_t rows) { return copy_rows(dst + s0, ld, src, chunk, w, rows, cudaMemcpyDeviceToHost, st); };
+   int rc = MECANO_B200_OK;
+   RunOpts opt;
+   opt.ws_slot = 1 + slot;
+   opt.variant_n = j.variant_n > 0 ? j.variant_n : j.n;
+   if (j.algo == MB_STEP)
+   {
+      const bool rnea = j.x != nullptr, aba = j.tau_in != nullptr;
+      double *dq = take(nq), *dqd = (rnea || aba) ? take(nv) : nullptr, *dqdd = rnea ? take(nv) : nullptr, *dtin = aba ? take(nv) : nullptr;
+      double *df = j.fext ? take(6 * nb) : nullptr;
+      double *dtau = rnea ? take(nv) : nullptr, *dqo = aba ? take(nv) : nullptr, *dM = j.M ? take(j.m_rows) : nullptr;
+      MB_CUDA(h, h2d(dq, j.q, nq));
+      if (dqd) MB_CUDA(h, h2d(dqd, j.qd, nv));
+      if (dqdd) MB_CUDA(h, h2d(dqdd, j.x, nv));
+      if (dtin) MB_CUDA(h, h2d(dtin, j.tau_in, nv));
+      if (df) MB_CUDA(h, h2d(df, j.fext, 6 * nb));
+      if (rnea)
+      {
+         rc = run(h, MB_RNEA, (int64_t)w, (int64_t)chunk, dq, dqd, dqdd, df, dtau, 0u, st, opt);
+         if (rc) return rc;
+         MB_CUDA(h, d2h(j.out, dtau, nv));
+      }
+      if (aba)
+      {
+         rc = run(h, MB_ABA, (int64_t)w, (int64_t)chunk, dq, dqd, dtin, df, dqo, 0u, st, opt);
+         if (rc) return rc;
+         MB_CUDA(h, d2h(j.qdd_out, dqo, nv));
+      }
+      if (j.M)
+      {
+         rc = run(h, MB_CRBA, (int64_t)w, (int64_t)chunk, dq, nullptr, nullptr, nullptr, dM, j.flags, st, opt);
+         if (rc) return rc;
+         if (j.flags & MECANO_B200_CRBA_STATE_MAJOR)
+            MB_CUDA(h, cudaMemcpyAsync(j.M + (size_t)s0 * nv * nv, dM, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+         else
+            MB_CUDA(h, d2h(j.M, dM, j.m_rows));
+      }
+      return MECANO_B200_OK;
+   }
+   const int algo = j.algo;
+   const bool state_major = algo == MB_CRBA && (j.flags & MECANO_B200_CRBA_STATE_MAJOR);
+   const bool sources = algo == MB_ABA && (j.x2 || j.tau_out); // mecano_b200_aba_sources_host
+   double *dq = take(nq), *dqd = nullptr, *dx = nullptr, *df = nullptr, *dx2 = nullptr;
+   MB_CUDA(h, h2d(dq, j.q, nq));
+   if (algo != MB_CRBA)
+   {
+      dqd = take(nv);
+      dx = take(nv);
+      MB_CUDA(h, h2d(dqd, j.qd, nv));
+      MB_CUDA(h, h2d(dx, j.x, nv));
+      if (j.fext) { df = take(6 * nb); MB_CUDA(h, h2d(df, j.fext, 6 * nb)); }
+      if (j.x2) { dx2 = take(nv); MB_CUDA(h, h2d(dx2, j.x2, nv)); }
+   }
+   double *dout = take(algo == MB_CRBA ? j.m_rows : nv);
+   double *dacc = j.body_acc ? take(6 * nb) : nullptr;
+   double *dwr = j.joint_wrench ? take(6 * nb) : nullptr;
+   double *dtau = j.tau_out ? take(nv) : nullptr;
+   if (sources)
+      rc = run_aba_sources(h, (int64_t)w, (int64_t)chunk, dq, dqd, dx, dx2, df, dout, dtau, st, 1 + slot);
+   else
+   {
+      opt.body_acc = dacc;
+      opt.joint_wrench = dwr;
+      rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, df, dout, j.flags, st, opt);
+   }
+   if (rc) return rc;
+   if (dtau) MB_CUDA(h, d2h(j.tau_out, dtau, nv));
+   if (dacc) MB_CUDA(h, d2h(j.body_acc, dacc, 6 * nb));
+   if (dwr) MB_CUDA(h, d2h(j.joint_wrench, dwr, 6 * nb));
+   if (state_major)
+      MB_CUDA(h, cudaMemcpyAsync(j.out + (size_t)s0 * nv * nv, dout, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+   else if (algo == MB_CRBA && (j.flags & MECANO_B200_CRBA_ZEROS_PRESENT))
+   {
+      // entry-major: a structurally zero entry is a whole row of the host matrix, which already holds zeros
+      for (const auto &run : h->nonzero_runs)
+         MB_CUDA(h, copy_rows(j.out + (size_t)run.first * ld + s0, ld, dout + (size_t)run.first * chunk, chunk, w, (size_t)run.second, cudaMemcpyDeviceToHost, st));
+   }
+   else
+      MB_CUDA(h, d2h(j.out, dout, algo == MB_CRBA ? j.m_rows : nv));
+   return MECANO_B200_OK;
+}
+
+int host_finish(mecano_b200_handle *h)
+{
+   MB_ON_DEVICE(h);
+   MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
+   MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+   return MECANO_B200_OK;
+}
+
+// Runs one job per lane: the chunks of all lanes are issued round-robin from the calling thread (everything is asynchronous
+// with pinned host memory), then every lane is synchronised once.  lanes.size() == 1 is the single-device host call.
+int run_host_lanes(const std::vector<mecano_b200_handle *> &lanes, std::vector<HostJob> &jobs, int *failed_lane)
+{
+   int rc = MECANO_B200_OK;
+   size_t started = 0;
+   *failed_lane = 0;
+   // a listed handle is locked for the whole call (handles are distinct objects even when they share a device)
+   for (; started < lanes.size(); started++)
+   {
+      lanes[started]->mu.lock();
+      rc = host_begin(lanes[started], jobs[started]);
+      if (rc) { *failed_lane = (int)started; started++; break; }
+   }
+   bool pending = rc == MECANO_B200_OK;
+   while (pending && rc == MECANO_B200_OK)
+   {
+      pending = false;
+      for (size_t i = 0; i < lanes.size() && rc == MECANO_B200_OK; i++)
+      {
+         if (jobs[i].s0 >= jobs[i].n) continue;
+         rc = host_issue_chunk(lanes[i], jobs[i]);
+         if (rc) *failed_lane = (int)i;
+         pending = pending || jobs[i].s0 < jobs[i].n;
+      }
+   }
+   // always drain what was issued, also after an error: the staging buffers and the caller's matrices are in flight
+   for (size_t i = 0; i < started; i++)
+   {
+      if (jobs[i].n > 0 && lanes[i]->streams[0])
+      {
+         const int rf = host_finish(lanes[i]);
+         if (rf && !rc) { rc = rf; *failed_lane = (int)i; }
+      }
+      lanes[i]->mu.unlock();
+   }
+   return rc;
+}
+
+int run_host(mecano_b200_handle *h, HostJob &job)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   std::vector<mecano_b200_handle *> lanes(1, h);
+   std::vector<HostJob> jobs(1, job);
+   int failed = 0;
+   return run_host_lanes(lanes, jobs, &failed);
+}
+
 int run_host(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q, const double *qd, const double *x, const double *fext,
              double *out, uint32_t flags, double *body_acc = nullptr, double *joint_wrench = nullptr, const double *x2 = nullptr,
              double *tau_out = nullptr)
 {
-   int rc = check_batch(h, n, ld);
-   if (rc) return rc;
-   if (n == 0) return MECANO_B200_OK;
-   if (!q || !out || (algo != MB_CRBA && (!qd || !x)))
-      return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
-   std::lock_guard<std::mutex> lk(h->mu);
-   MB_ON_DEVICE(h);
-   const size_t nq = h->tree.nq, nv = h->tree.nv, nb = h->tree.nb;
-   const bool state_major = algo == MB_CRBA && (flags & MECANO_B200_CRBA_STATE_MAJOR);
-   // state-major: the whole per-state block is copied back from the staging buffer, which other calls on this handle reuse, so
-   // the kernel must write the structural zeros there every time (the transfer saving of ZEROS_PRESENT is entry-major only)
-   if (state_major)
-      flags &= ~MECANO_B200_CRBA_ZEROS_PRESENT;
-   const bool sources = algo == MB_ABA && (x2 || tau_out); // mecano_b200_aba_sources_host
-   const size_t in_rows = algo == MB_CRBA ? nq : nq + 2 * nv + (fext ? 6 * nb : 0) + (x2 ? nv : 0);
-   const size_t out_rows = algo == MB_CRBA ? nv * nv : nv + (body_acc ? 6 * nb : 0) + (joint_wrench ? 6 * nb : 0) + (tau_out ? nv : 0);
-   // chunk: ~64 MB of rows per slot, at least 4096 states, multiple of 256
-   size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)(in_rows + out_rows));
-   chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
-   chunk = std::min<size_t>(chunk, ((size_t)n + 255) & ~(size_t)255);
-   rc = ensure_pipeline(h, (in_rows + out_rows) * chunk);
-   if (rc) return rc;
-   int slot = 0;
-   for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk, slot ^= 1)
-   {
-      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
-      cudaStream_t st = h->streams[slot];
-      double *dq = h->stage[slot], *dqd = dq + nq * chunk, *dx = dqd + nv * chunk, *df = dx + nv * chunk;
-      double *dout = h->stage[slot] + in_rows * chunk;
-      // the slot is reused every other chunk: stream order already serialises it
-      MB_CUDA(h, copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, st));
-      if (algo != MB_CRBA)
-      {
-         MB_CUDA(h, copy_rows(dqd, chunk, qd + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
-         MB_CUDA(h, copy_rows(dx, chunk, x + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
-         if (fext) MB_CUDA(h, copy_rows(df, chunk, fext + s0, (size_t)ld, w, 6 * nb, cudaMemcpyHostToDevice, st));
-         if (x2) MB_CUDA(h, copy_rows(df + (fext ? 6 * nb : 0) * chunk, chunk, x2 + s0, (size_t)ld, w, nv, cudaMemcpyHostToDevice, st));
-      }
-      else
-         dout = dq + nq * chunk;
-      double *dacc = body_acc ? dout + nv * chunk : nullptr;
-      double *dwr = joint_wrench ? dout + (nv + (body_acc ? 6 * nb : 0)) * chunk : nullptr;
-      double *dtau = tau_out ? dout + nv * chunk : nullptr;
-      if (sources)
-         rc = run_aba_sources(h, (int64_t)w, (int64_t)chunk, dq, dqd, dx, x2 ? df + (fext ? 6 * nb : 0) * chunk : nullptr, fext ? df : nullptr, dout, dtau, st,
-                              1 + slot);
-      else
-      {
-         RunOpts opt;
-         opt.ws_slot = 1 + slot;
-         opt.body_acc = dacc;
-         opt.joint_wrench = dwr;
-         rc = run(h, algo, (int64_t)w, (int64_t)chunk, dq, dqd, dx, fext ? df : nullptr, dout, flags, st, opt);
-      }
-      if (rc) return rc;
-      if (dtau) MB_CUDA(h, copy_rows(tau_out + s0, (size_t)ld, dtau, chunk, w, nv, cudaMemcpyDeviceToHost, st));
-      if (dacc) MB_CUDA(h, copy_rows(body_acc + s0, (size_t)ld, dacc, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
-      if (dwr) MB_CUDA(h, copy_rows(joint_wrench + s0, (size_t)ld, dwr, chunk, w, 6 * nb, cudaMemcpyDeviceToHost, st));
-      if (state_major)
-         MB_CUDA(h, cudaMemcpyAsync(out + (size_t)s0 * nv * nv, dout, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
-      else if (algo == MB_CRBA && (flags & MECANO_B200_CRBA_ZEROS_PRESENT))
-      {
-         // entry-major: a structurally zero entry is a whole row of the host matrix, which already holds zeros
-         for (const auto &run : h->nonzero_runs)
-            MB_CUDA(h, copy_rows(out + (size_t)run.first * (size_t)ld + s0, (size_t)ld, dout + (size_t)run.first * chunk, chunk, w, (size_t)run.second,
-                                 cudaMemcpyDeviceToHost, st));
-      }
-      else
-         MB_CUDA(h, copy_rows(out + s0, (size_t)ld, dout, chunk, w, algo == MB_CRBA ? out_rows : nv, cudaMemcpyDeviceToHost, st));
-   }
-   MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
-   MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
-   return MECANO_B200_OK;
+   HostJob j;
+   j.algo = algo; j.n = n; j.ld = ld;
+   j.q = q; j.qd = qd; j.x = x; j.fext = fext; j.x2 = x2;
+   j.out = out; j.body_acc = body_acc; j.joint_wrench = joint_wrench; j.tau_out = tau_out;
+   j.flags = flags;
+   return run_host(h, j);
 }
 } // namespace
 
@@ -972,6 +1135,27 @@ int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const do
    return run_host(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, M, layout);
 }
 
+int mecano_b200_crba_packed_size(const mecano_b200_handle *h) { return h ? (int)h->tree.packed_row.size() : -1; }
+
+int mecano_b200_crba_packed_index(const mecano_b200_handle *h, int32_t *row, int32_t *col)
+{
+   if (!h) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   if (row) std::copy(h->tree.packed_row.begin(), h->tree.packed_row.end(), row);
+   if (col) std::copy(h->tree.packed_col.begin(), h->tree.packed_col.end(), col);
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_step_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd_in, const double *tau_in,
+                          const double *fext, double *tau_out, double *qdd_out, double *M, uint32_t layout)
+{
+   HostJob j;
+   j.algo = MB_STEP; j.n = n; j.ld = ld;
+   j.q = q; j.qd = qd; j.x = qdd_in; j.tau_in = tau_in; j.fext = fext;
+   j.out = tau_out; j.qdd_out = qdd_out; j.M = M;
+   j.flags = layout;
+   return run_host(h, j);
+}
+
 int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info)
 {
    if (!h || !info || algo < 0 || algo >= MB_NUM_ALGOS) return MECANO_B200_ERR_INVALID_ARGUMENT;
@@ -1095,6 +1279,154 @@ int mecano_b200_host_free(void *ptr)
 {
    cudaError_t e = cudaFreeHost(ptr);
    return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------ several devices, one call
+#pragma GCC visibility pop
+} // extern "C"
+
+struct mecano_b200_multi
+{
+   std::vector<mecano_b200_handle *> lanes;
+   std::string error;
+};
+
+namespace
+{
+// slice of lane i: contiguous, multiples of 256 states (aligned rows on the device side), the remainder on the last lanes
+void multi_slice(int64_t n, int lanes, int i, int64_t *start, int64_t *count)
+{
+   const int64_t blocks = (n + 255) / 256, base = blocks / lanes, extra = blocks % lanes;
+   const int64_t b0 = (int64_t)i * base + std::min<int64_t>(i, extra), b1 = b0 + base + (i < extra ? 1 : 0);
+   *start = std::min(n, b0 * 256);
+   *count = std::min(n, b1 * 256) - *start;
+}
+
+int multi_fail(mecano_b200_multi *m, int rc, int lane)
+{
+   if (rc && m && lane >= 0 && lane < (int)m->lanes.size())
+      m->error = "device entry " + std::to_string(lane) + " (cuda:" + std::to_string(m->lanes[(size_t)lane]->device) + "): " + m->lanes[(size_t)lane]->error;
+   return rc;
+}
+
+// one job per lane from a whole-batch job: pointers offset to the lane's first state (state-major mass matrices by whole states)
+int multi_run(mecano_b200_multi *m, const HostJob &whole)
+{
+   if (!m) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   if (whole.n < 0 || whole.ld < whole.n)
+   {
+      m->error = "n_states must be >= 0 and ld >= n_states";
+      return MECANO_B200_ERR_SHAPE;
+   }
+   const int L = (int)m->lanes.size();
+   std::vector<HostJob> jobs((size_t)L, whole);
+   for (int i = 0; i < L; i++)
+   {
+      int64_t s0 = 0, cnt = 0;
+      multi_slice(whole.n, L, i, &s0, &cnt);
+      HostJob &j = jobs[(size_t)i];
+      j.n = cnt;
+      j.variant_n = whole.n;
+      auto off = [&](const double *p) { return p ? p + s0 : nullptr; };
+      auto offw = [&](double *p) { return p ? p + s0 : nullptr; };
+      j.q = off(whole.q); j.qd = off(whole.qd); j.x = off(whole.x); j.fext = off(whole.fext); j.x2 = off(whole.x2); j.tau_in = off(whole.tau_in);
+      j.body_acc = offw(whole.body_acc); j.joint_wrench = offw(whole.joint_wrench); j.tau_out = offw(whole.tau_out); j.qdd_out = offw(whole.qdd_out);
+      const size_t nv = (size_t)m->lanes[(size_t)i]->tree.nv;
+      const bool sm = (whole.flags & MECANO_B200_CRBA_STATE_MAJOR) != 0;
+      if (whole.algo == MB_CRBA)
+         j.out = whole.out ? (sm ? whole.out + (size_t)s0 * nv * nv : whole.out + s0) : nullptr;
+      else
+         j.out = offw(whole.out);
+      if (whole.algo == MB_STEP)
+         j.M = whole.M ? (sm ? whole.M + (size_t)s0 * nv * nv : whole.M + s0) : nullptr;
+   }
+   int failed = 0;
+   const int rc = run_host_lanes(m->lanes, jobs, &failed);
+   return multi_fail(m, rc, failed);
+}
+} // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int mecano_b200_multi_create(const mecano_b200_tree_desc *desc, const int32_t *devices, int n_devices, mecano_b200_multi **out)
+{
+   if (!out) return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "out pointer is NULL");
+   *out = nullptr;
+   if (!devices || n_devices <= 0 || n_devices > 64) return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "device list must hold 1 .. 64 entries");
+   mecano_b200_multi *m = new mecano_b200_multi();
+   for (int i = 0; i < n_devices; i++)
+   {
+      mecano_b200_handle *h = nullptr;
+      const int rc = mecano_b200_create(desc, devices[i], &h);
+      if (rc != MECANO_B200_OK)
+      {
+         mecano_b200_multi_destroy(m);
+         return rc; // mecano_b200_last_error(NULL) holds the message of the failed create
+      }
+      m->lanes.push_back(h);
+   }
+   *out = m;
+   return MECANO_B200_OK;
+}
+
+void mecano_b200_multi_destroy(mecano_b200_multi *m)
+{
+   if (!m) return;
+   for (mecano_b200_handle *h : m->lanes) mecano_b200_destroy(h);
+   delete m;
+}
+
+const char *mecano_b200_multi_last_error(const mecano_b200_multi *m) { return m ? m->error.c_str() : mecano_b200_last_error(nullptr); }
+int mecano_b200_multi_size(const mecano_b200_multi *m) { return m ? (int)m->lanes.size() : -1; }
+mecano_b200_handle *mecano_b200_multi_handle(mecano_b200_multi *m, int i) { return (m && i >= 0 && i < (int)m->lanes.size()) ? m->lanes[(size_t)i] : nullptr; }
+
+int mecano_b200_multi_slice(const mecano_b200_multi *m, int64_t n_states, int i, int64_t *start, int64_t *count)
+{
+   if (!m || i < 0 || i >= (int)m->lanes.size() || n_states < 0 || !start || !count) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   multi_slice(n_states, (int)m->lanes.size(), i, start, count);
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_multi_set_gravity(mecano_b200_multi *m, double gx, double gy, double gz)
+{
+   if (!m) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   for (mecano_b200_handle *h : m->lanes) mecano_b200_set_gravity(h, gx, gy, gz);
+   return MECANO_B200_OK;
+}
+
+int mecano_b200_multi_rnea_host(mecano_b200_multi *m, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd, const double *fext,
+                                double *tau, uint32_t flags)
+{
+   HostJob j;
+   j.algo = MB_RNEA; j.n = n; j.ld = ld; j.q = q; j.qd = qd; j.x = qdd; j.fext = fext; j.out = tau; j.flags = flags;
+   return multi_run(m, j);
+}
+
+int mecano_b200_multi_aba_host(mecano_b200_multi *m, int64_t n, int64_t ld, const double *q, const double *qd, const double *tau, const double *fext,
+                               double *qdd, uint32_t flags)
+{
+   HostJob j;
+   j.algo = MB_ABA; j.n = n; j.ld = ld; j.q = q; j.qd = qd; j.x = tau; j.fext = fext; j.out = qdd; j.flags = flags;
+   return multi_run(m, j);
+}
+
+int mecano_b200_multi_crba_host(mecano_b200_multi *m, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout)
+{
+   HostJob j;
+   j.algo = MB_CRBA; j.n = n; j.ld = ld; j.q = q; j.out = M; j.flags = layout;
+   return multi_run(m, j);
+}
+
+int mecano_b200_multi_step_host(mecano_b200_multi *m, int64_t n, int64_t ld, const double *q, const double *qd, const double *qdd_in, const double *tau_in,
+                                const double *fext, double *tau_out, double *qdd_out, double *M, uint32_t layout)
+{
+   HostJob j;
+   j.algo = MB_STEP; j.n = n; j.ld = ld;
+   j.q = q; j.qd = qd; j.x = qdd_in; j.tau_in = tau_in; j.fext = fext;
+   j.out = tau_out; j.qdd_out = qdd_out; j.M = M;
+   j.flags = layout;
+   return multi_run(m, j);
 }
 
 #pragma GCC visibility pop

@@ -28,9 +28,24 @@ template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
 }
 
 // M[dof_j .. , col] = S_j^T F and the mirrored entries (setSymmetricEntry, :704-705, :790-791)
-template <class T, class Ctx> MB_HD void crba_project(Ctx &c, int jt, int dj, int col, const SvT<T> &F)
+// PK (packed layout, MECANO_B200_CRBA_PACKED): one store per unique entry, at packed row pk (+ r for the DoFs of a SixDoF joint):
+// the mirrored entry and the structural zeros are not materialised
+template <class T, class Ctx, bool PK = false> MB_HD void crba_project(Ctx &c, int jt, int dj, int col, int pk, const SvT<T> &F)
 {
    const int nv = c.n_dofs();
+   if (PK)
+   {
+      if (jt == MB_REVOLUTE)
+         c.st_M(pk, F.a.z);
+      else if (jt == MB_PRISMATIC)
+         c.st_M(pk, F.l.z);
+      else
+      {
+         c.st_M(pk + 0, F.a.x); c.st_M(pk + 1, F.a.y); c.st_M(pk + 2, F.a.z);
+         c.st_M(pk + 3, F.l.x); c.st_M(pk + 4, F.l.y); c.st_M(pk + 5, F.l.z);
+      }
+      return;
+   }
    if (jt == MB_REVOLUTE)
    {
       c.st_M(dj * nv + col, F.a.z);
@@ -57,7 +72,8 @@ template <class T, class Ctx> MB_HD void crba_project(Ctx &c, int jt, int dj, in
 // the root, filling the off-diagonal blocks of column `col` (:772-797)
 // BY (by-products instantiation): the walk also runs for the children of the root body and ends by re-expressing the unit
 // momentum in the root frame, which is column `col` of the centroidal momentum matrix (computeCentroidalMomentumMatrix(), :801-809)
-template <class T, class Ctx, bool BY = false> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int b, int col, T s, T cs, SvT<T> F)
+// pcol (PK): first packed row of column `col`
+template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_walk(const MbProgram &P, Ctx &c, int b, int col, int pcol, T s, T cs, SvT<T> F)
 {
    MbWalk w = P.walk[b];
    while (!(w.flags & 1u)) // until the parent is the root body
@@ -71,7 +87,7 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_walk(const MbProg
          F = force_to_parent(stk_ld_xf<T>(c, w.slot), F);
       b = w.parent;
       w = P.walk[b];
-      crba_project<T>(c, w.jtype, w.dof, col, F);
+      crba_project<T, Ctx, PK>(c, w.jtype, w.dof, col, pcol + w.above, F);
       if (w.jtype != MB_SIXDOF)
          c.stk_ld2(w.slot, 0, s, cs);
    }
@@ -90,8 +106,9 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_walk(const MbProg
    }
 }
 
-template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbProgram &P, Ctx &c)
+template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_state(const MbProgram &P, Ctx &c)
 {
+   static_assert(!(BY && PK), "the by-product instantiation writes the dense entry-major matrix");
    // entries coupling joints of unrelated branches are zero
    // (the zeros are spread over the ops of the traversal instead of being written in one burst up front: a steadier store stream)
    const int zpart = c.zero_parts(P.nops);
@@ -122,7 +139,8 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbPro
    {
       const MbOp2 o = P.op2[k];
       c.stk_fence();
-      c.zero_fill_part(k, zpart);
+      if (!PK)
+         c.zero_fill_part(k, zpart);
       if (o.pf & MB2_PF_D1)
          c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, 1);
       c.pf_commit();
@@ -158,27 +176,30 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbPro
          if (jt != MB_SIXDOF && !(o.flags & MB2_LEAF))
             c.stk_ld2(o.slot, 0, js, jc);
          const int d = o.dof;
+         // packed layout: first packed row of this joint's first column, position of the joint's own DoFs within a column
+         const int pcol = PK ? (int)P.walk[o.body].pcol : 0, above = PK ? (int)P.walk[o.body].above : 0;
          // unit momenta F = Ic S (:663-667), diagonal block (:700-707), ancestors (:772-797)
          if (jt == MB_REVOLUTE)
          {
             SvT<T> F;
             F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
             F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
-            c.st_M(d * nv + d, F.a.z);
+            c.st_M(PK ? pcol + above : d * nv + d, F.a.z);
             if (BY || !(o.flags & MB2_ROOT_PARENT))
-               crba_walk<T, Ctx, BY>(P, c, o.body, d, js, jc, F);
+               crba_walk<T, Ctx, BY, PK>(P, c, o.body, d, pcol, js, jc, F);
          }
          else if (jt == MB_PRISMATIC)
          {
             SvT<T> F;
             F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
             F.l = v3<T>((T)0, (T)0, Ic.m);
-            c.st_M(d * nv + d, F.l.z);
+            c.st_M(PK ? pcol + above : d * nv + d, F.l.z);
             if (BY || !(o.flags & MB2_ROOT_PARENT))
-               crba_walk<T, Ctx, BY>(P, c, o.body, d, js, jc, F);
+               crba_walk<T, Ctx, BY, PK>(P, c, o.body, d, pcol, js, jc, F);
          }
          else
          {
+            int pc = pcol; // packed: column `col` of this joint starts at pcol + col * above + col (col + 1) / 2
 #pragma unroll 1
             for (int col = 0; col < 6; col++)
             {
@@ -187,10 +208,23 @@ template <class T, class Ctx, bool BY = false> MB_HD void crba_state(const MbPro
                else if (col == 3) e.l.x = 1; else if (col == 4) e.l.y = 1; else e.l.z = 1;
                const SvT<T> F = mul(Ic, e);
                const int dc = d + col;
-               c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
-               c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
+               if (PK)
+               {
+                  // upper triangle of the diagonal block: rows 0 .. col of this column
+                  const T f6[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+#pragma unroll
+                  for (int r = 0; r < 6; r++)
+                     if (r <= col)
+                        c.st_M(pc + above + r, f6[r]);
+               }
+               else
+               {
+                  c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
+                  c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
+               }
                if (BY || !(o.flags & MB2_ROOT_PARENT))
-                  crba_walk<T, Ctx, BY>(P, c, o.body, dc, js, jc, F);
+                  crba_walk<T, Ctx, BY, PK>(P, c, o.body, dc, pc, js, jc, F);
+               pc += above + col + 1;
             }
          }
          if (BY && (o.flags & MB2_ROOT_PARENT))

@@ -183,6 +183,9 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       w.pad = 0;
       w.dof = (uint16_t)B.dof_off;
       w.slot = (uint16_t)slot2[i];
+      // packed layout: bodies are in depth-first order, so the parent's record is complete
+      w.above = (uint8_t)(B.parent < 0 ? 0 : P.walk[B.parent].above + P.body[B.parent].ndof);
+      w.pcol = (uint16_t)(i == 0 ? 0 : P.walk[i - 1].pcol + P.body[i - 1].ndof * P.walk[i - 1].above + P.body[i - 1].ndof * (P.body[i - 1].ndof + 1) / 2);
    }
    // trailing records: ASCEND of a SixDoF joint can never be mistaken for a 1-DoF DESCEND by the look-ahead
    for (int k = P.nops; k < P.nops + 4; k++)
@@ -588,6 +591,26 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          }
       while (!out.zero_entries.empty() && out.zero_entries.size() % 8 != 0)
          out.zero_entries.push_back(out.zero_entries.back());
+      // packed layout index map: for every column (DoF r of body i) the DoFs on the path from the root down to and including
+      // that DoF, in the order the kernel's packed row numbers follow (MbWalk::pcol / above)
+      for (int i = 0; i < nb; i++)
+         for (int r = 0; r < P.body[i].ndof; r++)
+         {
+            std::vector<int> path;
+            for (int a = i; a >= 0; a = P.body[a].parent)
+               path.push_back(a);
+            for (auto it = path.rbegin(); it != path.rend(); ++it)
+               for (int k = 0; k < (*it == i ? r + 1 : P.body[*it].ndof); k++)
+               {
+                  out.packed_row.push_back(P.body[*it].dof_off + k);
+                  out.packed_col.push_back(P.body[i].dof_off + r);
+               }
+            if (r == 0 && (int)out.packed_row.size() - (P.walk[i].above + 1) != P.walk[i].pcol)
+            {
+               err = "internal error: packed mass-matrix column table";
+               return MECANO_B200_ERR_INVALID_ARGUMENT;
+            }
+         }
    }
    return MECANO_B200_OK;
 }

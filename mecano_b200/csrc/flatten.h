@@ -21,6 +21,9 @@ struct FlatTree
    std::vector<int> level_order;    // internal indices sorted by level (for the warp-per-state variant)
    std::vector<int> level_start;    // [n_levels + 1] into level_order
    std::vector<uint16_t> zero_entries; // mass-matrix entries (row * nv + col) that are structurally zero, padded to a multiple of 8
+   // packed mass-matrix layout (MECANO_B200_CRBA_PACKED): packed row p holds M[packed_row[p]][packed_col[p]] (= the mirrored
+   // entry); one row per unique entry that is not structurally zero, column by column, path from the root first
+   std::vector<int32_t> packed_row, packed_col;
    MbProgram prog[MB_NUM_ALGOS];    // MB_RNEA, MB_ABA, MB_CRBA, MB_CORIOLIS
 };
 

@@ -26,9 +26,11 @@ namespace mb
 {
 namespace
 {
-template <int ALGO, bool FEXT, bool STATE_MAJOR, int BLOCK, int AUXN, int RECN, int TM>
+// LAYOUT (CRBA): 0 entry-major, 1 state-major, 2 packed (unique non-zero entries, entry-major rows)
+template <int ALGO, bool FEXT, int LAYOUT, int BLOCK, int AUXN, int RECN, int TM>
 __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
 {
+   constexpr bool STATE_MAJOR = LAYOUT == 1;
    const int ncst = P.nb * MB_CONST_STRIDE;
    for (int i = threadIdx.x; i < ncst; i += BLOCK)
       mb_smem[i] = a.consts[i];
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
       else if constexpr (ALGO == MB_ABA)
          aba_state<double, Ctx, FEXT>(P, c2, a.grav);
       else if constexpr (ALGO == MB_CRBA)
-         crba_state<double, Ctx, FEXT>(P, c2);
+         crba_state<double, Ctx, FEXT, LAYOUT == 2>(P, c2);
       else
          coriolis_state<double, Ctx>(P, c2);
    });
@@ -87,7 +89,7 @@ constexpr Cfg kCfg[kNumCfg] = {{512, 0, 32}, {384, 0, 42}, {320, 0, 42}, {256, 0
 
 typedef void (*KernelFn)(const MbProgram, const KernelArgs);
 
-template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
+template <int ALGO, bool FEXT, int SM> KernelFn pick_cfg(int cfg)
 {
    constexpr int a0 = ALGO == MB_RNEA ? kRnaAux0 : (ALGO == MB_ABA ? kAbaAux0 : (ALGO == MB_CRBA ? kCrbAux0 : kCorAux0));
    constexpr int a1 = ALGO == MB_RNEA ? kRnaAux1 : (ALGO == MB_ABA ? kAbaAux1 : (ALGO == MB_CRBA ? kCrbAux1 : kCorAux1));
@@ -103,14 +105,15 @@ template <int ALGO, bool FEXT, bool SM> KernelFn pick_cfg(int cfg)
    }
 }
 
-KernelFn pick(int algo, bool fext, bool state_major, int cfg)
+// layout: 0 entry-major, 1 state-major, 2 packed (CRBA only)
+KernelFn pick(int algo, bool fext, int layout, int cfg)
 {
-   if (algo == MB_RNEA) return fext ? pick_cfg<MB_RNEA, true, false>(cfg) : pick_cfg<MB_RNEA, false, false>(cfg);
-   if (algo == MB_ABA) return fext ? pick_cfg<MB_ABA, true, false>(cfg) : pick_cfg<MB_ABA, false, false>(cfg);
-   if (algo == MB_CORIOLIS) return pick_cfg<MB_CORIOLIS, false, false>(cfg);
+   if (algo == MB_RNEA) return fext ? pick_cfg<MB_RNEA, true, 0>(cfg) : pick_cfg<MB_RNEA, false, 0>(cfg);
+   if (algo == MB_ABA) return fext ? pick_cfg<MB_ABA, true, 0>(cfg) : pick_cfg<MB_ABA, false, 0>(cfg);
+   if (algo == MB_CORIOLIS) return pick_cfg<MB_CORIOLIS, false, 0>(cfg);
    // CRBA: the "FEXT" instantiation is the one with by-products (centroidal momentum matrix, centre of mass), entry-major only
-   if (fext && !state_major) return pick_cfg<MB_CRBA, true, false>(cfg);
-   return state_major ? pick_cfg<MB_CRBA, false, true>(cfg) : pick_cfg<MB_CRBA, false, false>(cfg);
+   if (fext && layout == 0) return pick_cfg<MB_CRBA, true, 0>(cfg);
+   return layout == 1 ? pick_cfg<MB_CRBA, false, 1>(cfg) : (layout == 2 ? pick_cfg<MB_CRBA, false, 2>(cfg) : pick_cfg<MB_CRBA, false, 0>(cfg));
 }
 
 // fp32 variant: the one configuration per algorithm that the planner picks for humanoid-sized trees (kCfg index, class 0)
@@ -186,7 +189,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       if (sm > (size_t)max_optin)
          continue;
       // every variant of this configuration gets the opt-in so that later launches cannot fail on it
-      KernelFn fn = pick(algo, fext, false, cfg);
+      KernelFn fn = pick(algo, fext, 0, cfg);
       cudaFuncAttributes fa;
       e = cudaFuncGetAttributes(&fa, (const void *)fn);
       if (e != cudaSuccess) return e;
@@ -194,9 +197,9 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       if (sm > (size_t)max_dyn)
          continue;
       for (int f = 0; f < 2; f++)
-         for (int st = 0; st < 2; st++)
+         for (int st = 0; st < 3; st++)
          {
-            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st != 0, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
             if (e != cudaSuccess) return e;
          }
       int nblk = 0;
@@ -234,7 +237,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    if (best_threads == 0)
       return cudaSuccess; // the stack of even a 32-state block does not fit in shared memory
    cudaFuncAttributes attr;
-   e = cudaFuncGetAttributes(&attr, (const void *)pick(algo, fext, false, plan.size_class));
+   e = cudaFuncGetAttributes(&attr, (const void *)pick(algo, fext, 0, plan.size_class));
    if (e != cudaSuccess) return e;
    int sms = 0;
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -262,7 +265,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
 {
    if (a.n <= 0)
       return cudaSuccess;
-   const bool state_major = algo == MB_CRBA && (a.flags & 1u);
+   const int layout = algo == MB_CRBA ? ((a.flags & 4u) ? 2 : (int)(a.flags & 1u)) : 0; // MECANO_B200_CRBA_PACKED / STATE_MAJOR
    if (a.fp32)
    {
       // api.cu checked plan.fp32_ok and that the call has no optional buffers
@@ -273,7 +276,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
       pick_f32(algo)<<<g, plan.block, plan.smem, stream>>>(P, b);
       return cudaGetLastError();
    }
-   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, state_major, plan.size_class);
+   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, layout, plan.size_class);
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so
    // does every kernel with a TMEM stack: a block then allocates its tensor memory, stages the constant records and

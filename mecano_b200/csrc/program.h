@@ -105,15 +105,20 @@ struct MbOp2
 #define MB2_FIRST_CHILD 0x20u
 #define MB2_ACCSRC 0x40u // ABA ASCEND: the joint is an ACCELERATION_SOURCE (mecano_b200_set_joint_source_modes); not part of MB_F_*
 
-// per-body record for the CRBA ancestor walk (8 bytes)
+// per-body record for the CRBA ancestor walk (16 bytes; the first eight are what the dense layouts read, one aligned 64-bit load)
 struct MbWalk
 {
    uint8_t jtype;
    uint8_t flags;  // bit0: the parent is the root body
    uint8_t parent; // internal index of the parent body
-   uint8_t pad;
+   uint8_t above;  // packed mass-matrix layout: DoFs of the proper ancestors of this body = position of this joint's first DoF
+                   // within a packed column (the non-zero rows of a column are the DoFs on the path from the root, root first)
    uint16_t dof;   // Mecano DoF row
    uint16_t slot;  // stack slot (double2 units)
+   uint16_t pcol;  // packed mass-matrix layout: first packed row of the column of this joint's first DoF; the column of its
+                   // r-th DoF starts at pcol + r * above + r (r + 1) / 2 and holds above + r + 1 entries
+   uint16_t pad;
+   uint32_t pad2;
 };
 
 // A run: consecutive ops of the same kind (code & 0xf: ASCEND bit, joint type, SC bit).  The kernels execute a run as one

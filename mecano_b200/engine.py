@@ -168,12 +168,26 @@ class Engine:
         check(lib.mecano_b200_aba_sources_host(self._h, n, _same_ld([l0, l1, l2, l3, l4, l5, l6]), pq, pqd, pt, pi, pf, pqdd, pto), self._h)
         return qdd
 
+    def packed_size(self):
+        """Rows of the packed mass-matrix layout (CRBA_PACKED): unique entries that are not structurally zero."""
+        return lib.mecano_b200_crba_packed_size(self._h)
+
+    def packed_index(self):
+        """(row, col) int32 arrays: packed row p holds M[row[p], col[p]] (= M[col[p], row[p]])."""
+        n = self.packed_size()
+        row, col = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        check(lib.mecano_b200_crba_packed_index(self._h, row.ctypes.data, col.ctypes.data), self._h)
+        return row, col
+
+    def mass_matrix_rows(self, layout):
+        return self.packed_size() if (layout & _capi.CRBA_PACKED) else self.nv * self.nv
+
     def crba(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
-        """M: [nv*nv, n] (entry-major) or [n, nv*nv] (state-major) float64 CUDA tensor."""
+        """M: [nv*nv, n] (entry-major), [packed_size, n] (packed) or [n, nv*nv] (state-major) float64 CUDA tensor."""
         n = q.shape[1]
         pq, ld = self._dp(q, self.nq, n)
         if not (layout & _capi.CRBA_STATE_MAJOR):
-            pm, lm = self._dp(M, self.nv * self.nv, n)
+            pm, lm = self._dp(M, self.mass_matrix_rows(layout), n)
             ld = _same_ld([ld, lm])
         else:
             if tuple(M.shape) != (n, self.nv * self.nv) or not M.is_contiguous():
@@ -271,15 +285,175 @@ class Engine:
     def crba_host(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
         n = q.shape[1]
         pq, ld = _host_ptr_ld(q, self.nq, n)
-        if not (layout & _capi.CRBA_STATE_MAJOR):
-            pm, lm = _host_ptr_ld(M, self.nv * self.nv, n)
-            ld = _same_ld([ld, lm])
-        else:
-            if M.shape != (n, self.nv * self.nv) or not M.flags.c_contiguous:
-                raise ValueError("state-major mass matrix must be a contiguous [n, nv*nv] array")
-            pm = M.ctypes.data
+        pm, ld = self._host_mass_matrix(M, layout, n, ld)
         check(lib.mecano_b200_crba_host(self._h, n, ld, pq, pm, layout), self._h)
         return M
+
+    def _host_mass_matrix(self, M, layout, n, ld):
+        if M is None:
+            return None, ld
+        if not (layout & _capi.CRBA_STATE_MAJOR):
+            pm, lm = _host_ptr_ld(M, self.mass_matrix_rows(layout), n)
+            return pm, _same_ld([ld, lm])
+        if M.shape != (n, self.nv * self.nv) or not M.flags.c_contiguous:
+            raise ValueError("state-major mass matrix must be a contiguous [n, nv*nv] array")
+        return M.ctypes.data, ld
+
+    def _step_args(self, q, qd, qdd_in, tau_in, tau_out, qdd_out, M, layout, fext):
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        ptrs = [_host_ptr_ld(a, self.nv, n) for a in (qd, qdd_in, tau_in, tau_out, qdd_out)]
+        pf, lf = _host_ptr_ld(fext, 6 * self.nb, n)
+        ld = _same_ld([l0, lf] + [l for _, l in ptrs])
+        pm, ld = self._host_mass_matrix(M, layout, n, ld)
+        (pqd, _), (pqdd, _), (ptin, _), (ptout, _), (pqo, _) = ptrs
+        return n, ld, pq, pqd, pqdd, ptin, pf, ptout, pqo, pm
+
+    def step_host(self, q, qd, qdd_in=None, tau_in=None, tau_out=None, qdd_out=None, M=None, layout=_capi.CRBA_ENTRY_MAJOR, fext=None):
+        """mecano_b200_step_host: inverse dynamics (qdd_in -> tau_out), forward dynamics (tau_in -> qdd_out) and the mass matrix of
+        the same states in one host call; q / qd cross PCIe once.  Any calculator is skipped by leaving its buffers None."""
+        n, ld, pq, pqd, pqdd, ptin, pf, ptout, pqo, pm = self._step_args(q, qd, qdd_in, tau_in, tau_out, qdd_out, M, layout, fext)
+        check(lib.mecano_b200_step_host(self._h, n, ld, pq, pqd, pqdd, ptin, pf, ptout, pqo, pm, layout), self._h)
+
+
+class _BorrowedEngine(Engine):
+    """View of one handle of a multi-device engine (not owned: never destroyed through this object)."""
+
+    def __init__(self, handle, device):
+        self._h = ctypes.c_void_p(handle)
+        self._keep = None
+        self.device = int(device)
+        self.nv = lib.mecano_b200_n_dofs(self._h)
+        self.nq = lib.mecano_b200_n_cfg(self._h)
+        self.nb = lib.mecano_b200_n_bodies(self._h)
+
+    def close(self):
+        self._h = None
+
+
+class MultiDeviceEngine:
+    """mecano_b200_multi_*: one tree on several GPUs of one box behind one host call.  The batch is cut into disjoint contiguous
+    slices of the state index, one per listed device (a device may be listed more than once); no collective, results
+    bit-identical to the single-device call.  Host (numpy / pinned) matrices only: a device matrix lives on one GPU."""
+
+    def __init__(self, desc, devices, keepalive=None):
+        self.devices = [int(d) for d in devices]
+        self._m = ctypes.c_void_p()
+        self._keep = keepalive
+        dev = np.ascontiguousarray(self.devices, dtype=np.int32)
+        rc = lib.mecano_b200_multi_create(ctypes.byref(desc), dev.ctypes.data, len(self.devices), ctypes.byref(self._m))
+        if rc != 0:
+            msg = lib.mecano_b200_last_error(None)
+            raise _capi.MecanoB200Error(rc, msg.decode() if msg else "")
+        self.lanes = [_BorrowedEngine(lib.mecano_b200_multi_handle(self._m, i), d) for i, d in enumerate(self.devices)]
+        self.device = self.devices[0]
+        self.nv, self.nq, self.nb = self.lanes[0].nv, self.lanes[0].nq, self.lanes[0].nb
+
+    def close(self):
+        if getattr(self, "_m", None) is not None and self._m:
+            for lane in self.lanes:
+                lane.close()
+            lib.mecano_b200_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = lib.mecano_b200_multi_last_error(self._m)
+            raise _capi.MecanoB200Error(rc, msg.decode() if msg else "")
+
+    def slices(self, n_states):
+        """[(start, count)] per listed device for a batch of n_states."""
+        out = []
+        for i in range(len(self.devices)):
+            s, c = ctypes.c_int64(), ctypes.c_int64()
+            self._check(lib.mecano_b200_multi_slice(self._m, int(n_states), i, ctypes.byref(s), ctypes.byref(c)))
+            out.append((s.value, c.value))
+        return out
+
+    # setters that are properties of every handle
+    def set_gravity(self, gx, gy, gz):
+        self._check(lib.mecano_b200_multi_set_gravity(self._m, float(gx), float(gy), float(gz)))
+
+    def set_variant(self, variant):
+        for lane in self.lanes:
+            lane.set_variant(variant)
+
+    def set_precision(self, precision):
+        for lane in self.lanes:
+            lane.set_precision(precision)
+
+    def set_grid_limit(self, algo, max_blocks):
+        for lane in self.lanes:
+            lane.set_grid_limit(algo, max_blocks)
+
+    def specialize(self, algos=("rnea", "aba", "crba"), force=False):
+        for lane in self.lanes:
+            lane.specialize(algos, force)
+
+    def kernel_info(self, algo, n_states=0):
+        return self.lanes[0].kernel_info(algo, n_states)
+
+    def packed_size(self):
+        return self.lanes[0].packed_size()
+
+    def packed_index(self):
+        return self.lanes[0].packed_index()
+
+    def mass_matrix_rows(self, layout):
+        return self.lanes[0].mass_matrix_rows(layout)
+
+    @staticmethod
+    def _no_byproducts(body_acc, joint_wrench):
+        if body_acc is not None or joint_wrench is not None:
+            raise NotImplementedError("per-body by-products are served per device (use the engine of one device)")
+
+    def rnea_host(self, q, qd, qdd, tau, fext=None, flags=0, body_acc=None, joint_wrench=None):
+        self._no_byproducts(body_acc, joint_wrench)
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        pqd, l1 = _host_ptr_ld(qd, self.nv, n)
+        pqdd, l2 = _host_ptr_ld(qdd, self.nv, n)
+        pt, l3 = _host_ptr_ld(tau, self.nv, n)
+        pf, l4 = _host_ptr_ld(fext, 6 * self.nb, n)
+        self._check(lib.mecano_b200_multi_rnea_host(self._m, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pqdd, pf, pt, flags))
+        return tau
+
+    def aba_host(self, q, qd, tau, qdd, fext=None, flags=0):
+        n = q.shape[1]
+        pq, l0 = _host_ptr_ld(q, self.nq, n)
+        pqd, l1 = _host_ptr_ld(qd, self.nv, n)
+        pt, l2 = _host_ptr_ld(tau, self.nv, n)
+        pqdd, l3 = _host_ptr_ld(qdd, self.nv, n)
+        pf, l4 = _host_ptr_ld(fext, 6 * self.nb, n)
+        self._check(lib.mecano_b200_multi_aba_host(self._m, n, _same_ld([l0, l1, l2, l3, l4]), pq, pqd, pt, pf, pqdd, flags))
+        return qdd
+
+    def crba_host(self, q, M, layout=_capi.CRBA_ENTRY_MAJOR):
+        n = q.shape[1]
+        pq, ld = _host_ptr_ld(q, self.nq, n)
+        pm, ld = Engine._host_mass_matrix(self.lanes[0], M, layout, n, ld)
+        self._check(lib.mecano_b200_multi_crba_host(self._m, n, ld, pq, pm, layout))
+        return M
+
+    def step_host(self, q, qd, qdd_in=None, tau_in=None, tau_out=None, qdd_out=None, M=None, layout=_capi.CRBA_ENTRY_MAJOR, fext=None):
+        n, ld, pq, pqd, pqdd, ptin, pf, ptout, pqo, pm = Engine._step_args(self.lanes[0], q, qd, qdd_in, tau_in, tau_out, qdd_out, M, layout, fext)
+        self._check(lib.mecano_b200_multi_step_host(self._m, n, ld, pq, pqd, pqdd, ptin, pf, ptout, pqo, pm, layout))
+
+    def _device_only(self, *a, **k):
+        raise TypeError("a multi-device engine takes host (numpy) matrices: a device tensor lives on one GPU")
+
+    rnea = aba = crba = aba_sources = integrate = _device_only
+
+    def _single_device_only(self, *a, **k):
+        raise NotImplementedError("this entry point is served per device: build the calculator on one device")
+
+    aba_sources_host = coriolis = crba_centroidal = centroidal_convective_term = integrate_host = set_joint_source_modes = _single_device_only
 
 
 def measure_fp64_peak(device=0):

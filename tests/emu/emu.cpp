@@ -197,6 +197,8 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
          mb::coriolis_state<T, CpuCtx<T>>(P, c);
       else if (cmm)
          mb::crba_state<T, CpuCtx<T>, true>(P, c);
+      else if (flags & 4u) // MECANO_B200_CRBA_PACKED: out = [packed rows][ld]
+         mb::crba_state<T, CpuCtx<T>, false, true>(P, c);
       else
          mb::crba_state<T, CpuCtx<T>>(P, c);
    }
@@ -267,6 +269,18 @@ extern "C" int emu_count_flops(int algo, const mecano_b200_tree_desc *d, const d
    out5[0] = g_cnt.add; out5[1] = g_cnt.mul; out5[2] = g_cnt.div; out5[3] = g_cnt.sincos;
    out5[4] = g_cnt.add + g_cnt.mul + g_cnt.div;
    return rc;
+}
+
+// packed mass-matrix layout: number of packed rows and the dense (row, col) of each (row / col may be NULL)
+extern "C" int emu_packed_index(const mecano_b200_tree_desc *d, int32_t *row, int32_t *col)
+{
+   mb::FlatTree ft;
+   std::string e;
+   int rc = mb::flatten_tree(d, ft, e);
+   if (rc != 0) return rc;
+   if (row) std::copy(ft.packed_row.begin(), ft.packed_row.end(), row);
+   if (col) std::copy(ft.packed_col.begin(), ft.packed_col.end(), col);
+   return (int)ft.packed_row.size();
 }
 
 extern "C" int emu_program_info(const mecano_b200_tree_desc *d, int algo, int *out8)

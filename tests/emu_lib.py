@@ -160,6 +160,20 @@ class Emu:
         nv = self.tree.nv
         return self._run(2, q, None, None, None, np.full((nv * nv, n), np.nan)).reshape(nv, nv, n)
 
+    def packed_index(self):
+        """(row, col) int32 arrays of the packed mass-matrix layout (MECANO_B200_CRBA_PACKED): packed row p = M[row[p], col[p]]."""
+        n = self.lib.emu_packed_index(ctypes.byref(self.desc), None, None)
+        assert n > 0
+        row, col = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        assert self.lib.emu_packed_index(ctypes.byref(self.desc), row.ctypes.data_as(_ip), col.ctypes.data_as(_ip)) == n
+        return row, col
+
+    def crba_packed(self, q):
+        """[packed rows, n]: every unique structurally non-zero entry once (the kernel's packed instantiation)."""
+        n = q.shape[1]
+        row, _ = self.packed_index()
+        return self._run(2, q, None, None, None, np.full((len(row), n), np.nan), flags=4)
+
     def crba_centroidal(self, q):
         """(M [nv, nv, n], centroidal momentum matrix [6, nv, n] in the root frame, (mass * CoM, mass) [4, n])."""
         n = q.shape[1]

@@ -195,3 +195,41 @@ def test_emulated_kernels_match_the_golden_fixtures_of_the_next_rows():
         assert rel(e0.rnea_root_wrench(q, qd), data[name + "/conv_world"]) < TOL, name
         _, C = e0.coriolis(q, qd)
         assert rel(C, data[name + "/coriolis"]) < TOL, name
+
+
+@pytest.mark.parametrize("kind", ["chain7", "humanoid", "tree40", "floating_chain", "two_floating"])
+def test_packed_mass_matrix_layout(kind):
+    """MECANO_B200_CRBA_PACKED: the packed instantiation of the CRBA routine writes every unique, structurally non-zero entry
+    exactly once; scattered through the exported index map (both triangles) it is the dense matrix of the oracle, and what the
+    map does not cover is structurally zero (CompositeRigidBodyMassMatrixCalculator.java:296, :700-707, :772-797)."""
+    rng = np.random.default_rng(77)
+    if kind == "chain7":
+        t = td.chain(rng, 7)
+    elif kind == "humanoid":
+        t = td.humanoid(rng, 2)
+    elif kind == "tree40":
+        t = td.random_tree(rng, 40, floating=True, prismatic_fraction=0.3)
+    elif kind == "floating_chain":
+        t = td.chain(rng, 5, floating=True)
+    else:  # two SixDoF joints in series: a 6 x 6 diagonal block whose column has SixDoF ancestors
+        t = td.make_tree(rng, [-1, 0, 1, 1], [td.SIXDOF, td.SIXDOF, td.REVOLUTE, td.PRISMATIC])
+    e, o = el.Emu(t), ol.Oracle(t)
+    q = td.random_states(rng, t, 5)[0]
+    row, col = e.packed_index()
+    nv = t.nv
+    assert len(set(zip(row.tolist(), col.tolist()))) == len(row), "an entry is listed twice"
+    assert np.all(row <= col), "Mecano's depth-first DoF order puts ancestors first: the packed entries are the upper triangle"
+    P = e.crba_packed(q)
+    assert not np.isnan(P).any(), "a packed row was not written"
+    M = np.zeros((nv, nv, 5))
+    M[row, col] = P
+    M[col, row] = P
+    ref = o.crba_batch(q)
+    assert rel(M, ref) < 1e-12
+    dense = e.crba(q)
+    assert np.array_equal(M, dense), "packed and dense instantiations must agree bit for bit"
+    covered = np.zeros((nv, nv), bool)
+    covered[row, col] = covered[col, row] = True
+    assert np.all(ref[~covered] == 0.0)
+    if kind == "humanoid":
+        assert len(row) == 362  # 37-DoF humanoid: 362 of 1,369 entries

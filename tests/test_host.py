@@ -101,7 +101,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "missing export " + n
     assert sorted(_capi.EXPORTS) == _declared("mecano_b200.h")
     assert sorted(multibody.MODEL_EXPORTS) == _declared("mecano_b200_model.h")
-    assert lib.mecano_b200_version() == 100
+    assert lib.mecano_b200_version() == 200
 
 
 def test_create_validates_without_a_gpu():
