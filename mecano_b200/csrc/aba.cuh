@@ -12,7 +12,24 @@
 
 namespace mb
 {
-#define MB_ABA_REC 8 // doubles per body in the pass-three record (four double2: g.a, g.l, k0, pad)
+// pass-three record: MB_ABA_REC doubles per body (program.h)
+
+// record of a one-DoF joint: g without its unit component along the joint axis, then k0
+template <class T, class Ctx, bool REV> MB_HD void aba_rec_st_1dof(Ctx &c, int r, const SvT<T> &g, T k0)
+{
+   if (REV)
+   {
+      c.rec_st2(r + 0, g.a.x, g.a.y);
+      c.rec_st2(r + 1, g.l.x, g.l.y);
+      c.rec_st2(r + 2, g.l.z, k0);
+   }
+   else
+   {
+      c.rec_st2(r + 0, g.a.x, g.a.y);
+      c.rec_st2(r + 1, g.a.z, g.l.x);
+      c.rec_st2(r + 2, g.l.y, k0);
+   }
+}
 
 template <class T> struct AbaPipe
 {
@@ -87,8 +104,7 @@ MB_HD void aba_ascend_1dof_locked(Ctx &c, const MbOp2 o, const CP C, const SvT<T
    const int r = o.body * (MB_ABA_REC / 2);
    c.rec_st2(r + 0, (T)0, (T)0);
    c.rec_st2(r + 1, (T)0, (T)0);
-   c.rec_st2(r + 2, (T)0, (T)0);
-   c.rec_st2(r + 3, qdd, (T)0);
+   c.rec_st2(r + 2, (T)0, qdd); // pass three takes k0 as the acceleration (MB2_ACCSRC on its record)
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       SvT<T> cc;
@@ -159,12 +175,8 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    g.a = Dinv * U.a;
    g.l = Dinv * U.l;
    const T k0 = Dinv * u;
-   // record for pass three: qdd = k0 - g . a'
-   const int r = o.body * (MB_ABA_REC / 2);
-   c.rec_st2(r + 0, g.a.x, g.a.y);
-   c.rec_st2(r + 1, g.a.z, g.l.x);
-   c.rec_st2(r + 2, g.l.y, g.l.z);
-   c.rec_st2(r + 3, k0, (T)0);
+   // record for pass three: qdd = k0 - g . a'  (the component of g along the joint axis is D / D = 1 and is not stored)
+   aba_rec_st_1dof<T, Ctx, REV>(c, o.body * (MB_ABA_REC / 2), g, k0);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       // bias acceleration c = v x (S qd): only x / y components
@@ -235,12 +247,11 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
    const int r = o.body * (MB_ABA_REC / 2);
    if (FEXT && (o.flags & MB2_ACCSRC))
    {
-      // ACCELERATION_SOURCE (:1237-1253): the record carries qdd itself, flagged by its last entry (pass three: a = a' + qdd)
+      // ACCELERATION_SOURCE (:1237-1253): the record carries qdd itself (pass three, MB2_ACCSRC on its record: a = a' + qdd)
       const SvT<T> qdd6 = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_x2(rr); });
       c.rec_st2(r + 0, qdd6.a.x, qdd6.a.y);
       c.rec_st2(r + 1, qdd6.a.z, qdd6.l.x);
       c.rec_st2(r + 2, qdd6.l.y, qdd6.l.z);
-      c.rec_st2(r + 3, (T)1, (T)0);
       if (!(o.flags & MB2_ROOT_PARENT))
       {
          const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
@@ -256,7 +267,6 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
    c.rec_st2(r + 0, x.a.x, x.a.y);
    c.rec_st2(r + 1, x.a.z, x.l.x);
    c.rec_st2(r + 2, x.l.y, x.l.z);
-   c.rec_st2(r + 3, (T)0, (T)0);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
@@ -277,17 +287,17 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> 
 }
 
 // ---- pass three (:1259-1310): accelerations, root to leaves
-template <class T, class Ctx, bool REV, bool SC>
+// LOCKS: the instantiation that serves joints in ACCELERATION_SOURCE mode (their records hold the given acceleration)
+template <class T, class Ctx, bool REV, bool SC, bool LOCKS>
 MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp, T &ns, T &nc)
 {
    if (SC)
       mb_sincos(pp.mq, &ns, &nc);
-   SvT<T> g;
-   T k0, pad;
-   c.pf3_ld2(st, 1, g.a.x, g.a.y);
-   c.pf3_ld2(st, 2, g.a.z, g.l.x);
-   c.pf3_ld2(st, 3, g.l.y, g.l.z);
-   c.pf3_ld2(st, 4, k0, pad);
+   T g0, g1, g2, g3, g4, k0;
+   c.pf3_ld2(st, 1, g0, g1);
+   c.pf3_ld2(st, 2, g2, g3);
+   c.pf3_ld2(st, 3, g4, k0);
+   c.rec_discard(o.body * (MB_ABA_REC / 2));
    const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), pp.s, pp.c);
    v = motion_to_child(X, v);
    a = motion_to_child(X, a); // a' = X^-1 a_parent + c
@@ -303,7 +313,14 @@ MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, A
       a.l.x += v.a.y * qd; a.l.y -= v.a.x * qd;
       v.l.z += qd;
    }
-   const T qdd = k0 - (dot(g.a, a.a) + dot(g.l, a.l)); // D^-1 (u - U^T a')
+   // D^-1 (u - U^T a'): the stored five components of g, plus a' along the joint axis (g = 1 there)
+   T qdd;
+   if (REV)
+      qdd = k0 - (fmad(g0, a.a.x, fmad(g1, a.a.y, fmad(g2, a.l.x, fmad(g3, a.l.y, g4 * a.l.z)))) + a.a.z);
+   else
+      qdd = k0 - (fmad(g0, a.a.x, fmad(g1, a.a.y, fmad(g2, a.a.z, fmad(g3, a.l.x, g4 * a.l.y)))) + a.l.z);
+   if (LOCKS && (o.flags & MB2_ACCSRC))
+      qdd = k0; // the joint's given acceleration
    c.st_out(o.dof, qdd);
    if (REV) a.a.z += qdd;
    else a.l.z += qdd;
@@ -314,23 +331,29 @@ MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, A
    }
 }
 
-template <class T, class Ctx> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a)
+template <class T, class Ctx, bool LOCKS> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a)
 {
    SvT<T> x;
    c.pf3_ld2(st, 1, x.a.x, x.a.y);
    c.pf3_ld2(st, 2, x.a.z, x.l.x);
    c.pf3_ld2(st, 3, x.l.y, x.l.z);
-   T locked, pad;
-   c.pf3_ld2(st, 4, locked, pad); // 1 if the record holds the joint's given acceleration (ACCELERATION_SOURCE), else 0
+   c.rec_discard(o.body * (MB_ABA_REC / 2));
    const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
    const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
    v = motion_to_child(X, v) + vj;
    const SvT<T> a1 = motion_to_child(X, a) + cross_motion(v, vj);
-   // effort source: a = x, qdd = x - a'; acceleration source: qdd = x, a = a' + x
-   const T keep = (T)1 - locked;
+   // effort source: a = x, qdd = x - a'; acceleration source (the record holds the given acceleration): qdd = x, a = a' + x
    SvT<T> qdd;
-   qdd.a = x.a - keep * a1.a; qdd.l = x.l - keep * a1.l;
-   x.a = x.a + locked * a1.a; x.l = x.l + locked * a1.l;
+   if (LOCKS && (o.flags & MB2_ACCSRC))
+   {
+      qdd = x;
+      x = a1 + x;
+   }
+   else
+   {
+      qdd.a = x.a - a1.a;
+      qdd.l = x.l - a1.l;
+   }
    c.st_out(o.dof + 0, qdd.a.x); c.st_out(o.dof + 1, qdd.a.y); c.st_out(o.dof + 2, qdd.a.z);
    c.st_out(o.dof + 3, qdd.l.x); c.st_out(o.dof + 4, qdd.l.y); c.st_out(o.dof + 5, qdd.l.z);
    a = x;
@@ -489,7 +512,7 @@ MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof,
    }
 }
 
-template <class T, class Ctx>
+template <class T, class Ctx, bool LOCKS = false>
 MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
    c.op_sync(k);
@@ -498,14 +521,14 @@ MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T
    T ns = pp.mq, nc = (T)1;
    switch (o.code & 0xfu)
    {
-      case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false>(c, o, st, v, a, pp, ns, nc); break;
-      case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true>(c, o, st, v, a, pp, ns, nc); break;
-      case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false>(c, o, st, v, a, pp, ns, nc); break;
-      case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
+      case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
       default:
          if (o.code & MB2_SC)
             mb_sincos(pp.mq, &ns, &nc);
-         aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
+         aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, v, a);
          break;
    }
    pp.s = ns;
@@ -538,7 +561,7 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
    pp.c = nc;
 }
 
-template <class T, class Ctx, int KIND>
+template <class T, class Ctx, bool LOCKS, int KIND>
 MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
    constexpr int JT = (KIND >> 1) & 3;
@@ -549,9 +572,9 @@ MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *
    if (o.code & MB2_SC)
       mb_sincos(pp.mq, &ns, &nc);
    if (JT == MB_SIXDOF)
-      aba_pass3_6dof<T, Ctx>(c, o, st, v, a);
+      aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, v, a);
    else
-      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, false>(c, o, st, v, a, pp, ns, nc);
+      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, false, LOCKS>(c, o, st, v, a, pp, ns, nc);
    pp.s = ns;
    pp.c = nc;
 }
@@ -592,7 +615,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       const int k1 = k + R.n;
 #define MB_RUN_CASE(KIND)                                                                       \
    case KIND:                                                                                    \
-      _Pragma("unroll 1") do { aba_pass3_run_step<T, Ctx, KIND>(P, c, k, grav, v, a, pp); } while (++k < k1); \
+      _Pragma("unroll 1") do { aba_pass3_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a, pp); } while (++k < k1); \
       break;
       switch (R.kind)
       {

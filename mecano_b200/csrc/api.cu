@@ -18,6 +18,9 @@
 #include "kernels.h"
 #include "specialize.h"
 
+#define MB_ABA_DISCARD_DEFAULT 1 // profiles/r04b_aba_records.md: 1.713 -> 1.696 ms, DRAM writes 2.46 -> 1.82 GB per 2^20 H37 states
+#define MB_MAX_SLOTS 4
+
 struct mecano_b200_handle
 {
    int device = 0;
@@ -30,8 +33,8 @@ struct mecano_b200_handle
    size_t zero_row_doubles = 0;
    double *d_scratch = nullptr; // joint efforts nobody asked for (centroidal convective term = one RNEA launch)
    size_t scratch_doubles = 0;
-   double *d_ws[3] = {nullptr, nullptr, nullptr}; // ABA pass-two records: [0] device entry points, [1], [2] the two host-pipeline slots
-   size_t ws_doubles[3] = {0, 0, 0};
+   double *d_ws[1 + MB_MAX_SLOTS] = {}; // ABA pass-two records: [0] device entry points, [1 + s] host-pipeline slot s
+   size_t ws_doubles[1 + MB_MAX_SLOTS] = {};
    mb::SpecKernel spec[MB_NUM_ALGOS];                        // tree-specialised kernels (mecano_b200_specialize), per algorithm
    double gravity[3] = {0.0, 0.0, 0.0}; // Mecano calculators start with zero gravity until setGravitationalAcceleration
    mb::LaunchPlan plan[MB_NUM_ALGOS];
@@ -45,10 +48,11 @@ struct mecano_b200_handle
    int64_t warp_below[MB_NUM_ALGOS] = {0, 0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
    std::string error;
    // host pipeline (lazy)
-   cudaStream_t streams[2] = {nullptr, nullptr};
-   cudaEvent_t done[2] = {nullptr, nullptr};
-   double *stage[2] = {nullptr, nullptr};
+   cudaStream_t streams[MB_MAX_SLOTS] = {};
+   cudaEvent_t done[MB_MAX_SLOTS] = {};
+   double *stage[MB_MAX_SLOTS] = {};
    size_t stage_doubles = 0;
+   int n_slots = 3; // slots (stream + staging buffer) of the host pipeline (profiles/r04b_host_pipe.jsonl: 3 x 128 MB is 15 % faster than 2 x 64 MB)
    std::mutex mu;
 };
 
@@ -236,6 +240,12 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    if (opt.zero_gravity)
       a.grav[0] = a.grav[1] = a.grav[2] = 0.0;
    a.flags = flags;
+   if (algo == MB_ABA)
+   {
+      // pass three discards each record from L2 once read (gpu_ctx.cuh: rec_discard); MECANO_B200_ABA_DISCARD=0 / 1 overrides
+      static const int discard = [] { const char *e = getenv("MECANO_B200_ABA_DISCARD"); return e ? atoi(e) : MB_ABA_DISCARD_DEFAULT; }();
+      if (discard) a.flags |= MB_KFLAG_ABA_DISCARD;
+   }
    a.nv = h->tree.nv;
    if (use_spec)
    {
@@ -307,20 +317,20 @@ bool spec_cfg_from_env(int algo, mb::SpecOptions &opt)
 
 int ensure_pipeline(mecano_b200_handle *h, size_t doubles_per_slot)
 {
-   for (int i = 0; i < 2; i++)
+   for (int i = 0; i < h->n_slots; i++)
    {
       if (!h->streams[i]) MB_CUDA(h, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
       if (!h->done[i]) MB_CUDA(h, cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming));
    }
    if (doubles_per_slot > h->stage_doubles)
    {
-      for (int i = 0; i < 2; i++)
+      for (int i = 0; i < h->n_slots; i++)
       {
          if (h->stage[i]) cudaFree(h->stage[i]);
          h->stage[i] = nullptr;
       }
       h->stage_doubles = 0;
-      for (int i = 0; i < 2; i++)
+      for (int i = 0; i < h->n_slots; i++)
          MB_CUDA(h, cudaMalloc(&h->stage[i], doubles_per_slot * sizeof(double)));
       h->stage_doubles = doubles_per_slot;
    }
@@ -392,8 +402,9 @@ int host_begin(mecano_b200_handle *h, HostJob &j)
    }
    if ((j.flags & MECANO_B200_CRBA_PACKED) && (j.flags & (MECANO_B200_CRBA_STATE_MAJOR | MECANO_B200_CRBA_ZEROS_PRESENT)) && (j.algo == MB_CRBA || j.algo == MB_STEP))
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "the packed mass-matrix layout does not combine with STATE_MAJOR / ZEROS_PRESENT");
-   // chunk: ~64 MB of rows per slot, at least 4096 states, multiple of 256
-   size_t chunk = (size_t)(64.0 * 1024 * 1024 / 8 / (double)(j.in_rows + j.out_rows));
+   // chunk: ~128 MB of rows per slot (MECANO_B200_HOST_CHUNK_MB), at least 4096 states, multiple of 256
+   static const double chunk_mb = [] { const char *e = getenv("MECANO_B200_HOST_CHUNK_MB"); const double v = e ? atof(e) : 0.0; return v >= 1.0 ? v : 128.0; }();
+   size_t chunk = (size_t)(chunk_mb * 1024 * 1024 / 8 / (double)(j.in_rows + j.out_rows));
    chunk = std::max<size_t>(4096, chunk & ~(size_t)255);
    chunk = std::min<size_t>(chunk, ((size_t)j.n + 255) & ~(size_t)255);
    j.chunk = chunk;
@@ -414,8 +425,8 @@ int host_issue_chunk(mecano_b200_handle *h, HostJob &j)
    const int slot = j.slot;
    cudaStream_t st = h->streams[slot];
    j.s0 += (int64_t)chunk;
-   j.slot ^= 1;
-   // the slot is reused every other chunk: stream order already serialises it
+   j.slot = (slot + 1) % h->n_slots;
+   // a slot is reused every n_slots chunks: stream order already serialises it
    double *p = h->stage[slot];
    auto take = [&](size_t rows) { double *r = p; p += rows * chunk; return r; };
    auto h2d = [&](double *dst, const double *src, size_t rows) { return copy_rows(dst, chunk, src + s0, ld, w, rows, cudaMemcpyHostToDevice, st); };
@@ -504,8 +515,8 @@ int host_issue_chunk(mecano_b200_handle *h, HostJob &j)
 int host_finish(mecano_b200_handle *h)
 {
    MB_ON_DEVICE(h);
-   MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
-   MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
+   for (int i = 0; i < h->n_slots; i++)
+      if (h->streams[i]) MB_CUDA(h, cudaStreamSynchronize(h->streams[i]));
    return MECANO_B200_OK;
 }
 
@@ -608,6 +619,8 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       return fail(nullptr, MECANO_B200_ERR_INVALID_ARGUMENT, "device index out of range");
    }
    h->device = device;
+   if (const char *es = getenv("MECANO_B200_HOST_SLOTS"))
+      h->n_slots = std::min(MB_MAX_SLOTS, std::max(1, atoi(es)));
    auto bail = [&](cudaError_t ce, const char *what) {
       std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
       if (h->d_consts) cudaFree(h->d_consts);
@@ -690,7 +703,7 @@ void mecano_b200_destroy(mecano_b200_handle *h)
 {
    if (!h) return;
    DeviceGuard device_guard_(h->device);
-   for (int i = 0; i < 2; i++)
+   for (int i = 0; i < MB_MAX_SLOTS; i++)
    {
       if (h->stage[i]) cudaFree(h->stage[i]);
       if (h->done[i]) cudaEventDestroy(h->done[i]);
@@ -701,11 +714,10 @@ void mecano_b200_destroy(mecano_b200_handle *h)
    if (h->d_consts) cudaFree(h->d_consts);
    if (h->d_zero) cudaFree(h->d_zero);
    if (h->d_prog) cudaFree(h->d_prog);
-   for (int i = 0; i < 3; i++)
-   {
+   for (int i = 0; i < 1 + MB_MAX_SLOTS; i++)
       if (h->d_ws[i]) cudaFree(h->d_ws[i]);
+   for (int i = 0; i < 3; i++)
       mb::spec_unload(h->spec[i]);
-   }
    delete h;
 }
 
@@ -1111,7 +1123,7 @@ int mecano_b200_integrate_host(mecano_b200_handle *h, int64_t n, int64_t ld, dou
    rc = ensure_pipeline(h, rows * chunk);
    if (rc) return rc;
    int slot = 0;
-   for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk, slot ^= 1)
+   for (int64_t s0 = 0; s0 < n; s0 += (int64_t)chunk, slot = (slot + 1) % h->n_slots)
    {
       const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
       cudaStream_t st = h->streams[slot];
@@ -1125,9 +1137,7 @@ int mecano_b200_integrate_host(mecano_b200_handle *h, int64_t n, int64_t ld, dou
       MB_CUDA(h, copy_rows(qd + s0, (size_t)ld, dqd, chunk, w, nv, cudaMemcpyDeviceToHost, st));
       MB_CUDA(h, copy_rows(qdd + s0, (size_t)ld, dx, chunk, w, nv, cudaMemcpyDeviceToHost, st));
    }
-   MB_CUDA(h, cudaStreamSynchronize(h->streams[0]));
-   MB_CUDA(h, cudaStreamSynchronize(h->streams[1]));
-   return MECANO_B200_OK;
+   return host_finish(h);
 }
 
 int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *M, uint32_t layout)

@@ -151,6 +151,7 @@ template <class Ctx> struct F32Ctx
       c.pf3_ld2(stage, row, x, y);
       a = (float)x; b = (float)y;
    }
+   __device__ __forceinline__ void rec_discard(int rec2) const { c.rec_discard(rec2); }
    __device__ __forceinline__ void pass_fence() const { c.pass_fence(); }
    __device__ __forceinline__ void stk_fence() const { c.stk_fence(); }
    __device__ __forceinline__ void op_sync(int k) const { c.op_sync(k); }

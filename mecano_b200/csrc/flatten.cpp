@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace mb
@@ -152,7 +153,7 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       }
    }
    if (algo == MB_ABA)
-      P.stack2 = std::max(P.stack2, 20); // pass three overlays a 4-stage x 5-row ring of double2 on the stack area
+      P.stack2 = std::max(P.stack2, 4 * MB_ABA_RING_ROWS); // pass three overlays a 4-stage ring of double2 rows on the stack area
    std::memset(P.op2, 0, sizeof P.op2);
    for (int k = 0; k < P.nops; k++)
    {
@@ -190,15 +191,45 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
    // trailing records: ASCEND of a SixDoF joint can never be mistaken for a 1-DoF DESCEND by the look-ahead
    for (int k = P.nops; k < P.nops + 4; k++)
       P.op2[k].code = (uint8_t)(MB2_ASCEND | (MB_SIXDOF << 1));
-   // pass-three list: DESCEND records in order
+   // pass-three list: one DESCEND record per body.  Pass two writes the pass-three records of the bodies in post-order; pass
+   // three reads them in the REVERSE of that order -- a pre-order walk that visits the children of a body last child first --
+   // so that the workspace behaves like a stack: what was written last (and is still in L2) is read first, and a record is
+   // dead (and discarded from L2) as soon as it has been read.  The forward order (MECANO_B200_ABA_P3_FORWARD=1, kept for
+   // measurements) reads the records in roughly the order they were written, i.e. each one after the whole workspace has
+   // passed through L2 in between.
    int n3 = 0;
-   for (int k = 0; k < P.nops; k++)
-      if (!(P.op2[k].code & MB2_ASCEND))
-         P.op3[n3++] = P.op2[k];
-   for (int k = n3; k < n3 + 4; k++)
    {
-      std::memset(&P.op3[k], 0, sizeof(MbOp2));
-      P.op3[k].code = (uint8_t)(MB2_ASCEND | (MB_SIXDOF << 1));
+      static const bool forward = getenv("MECANO_B200_ABA_P3_FORWARD") != nullptr;
+      std::vector<int> desc_of(nb, -1);
+      for (int k = 0; k < P.nops; k++)
+         if (!(P.op2[k].code & MB2_ASCEND))
+            desc_of[P.op2[k].body] = k;
+      std::vector<std::vector<int>> kids(nb + 1);
+      for (int i = 0; i < nb; i++)
+         kids[P.body[i].parent + 1].push_back(i);
+      std::vector<int> stack;
+      // a stack pops the last pushed first: push in reverse for the forward order, as listed for the reversed one
+      auto push_kids = [&](int b) {
+         const std::vector<int> &c = kids[b + 1];
+         if (forward && algo == MB_ABA) stack.insert(stack.end(), c.rbegin(), c.rend());
+         else if (algo == MB_ABA) stack.insert(stack.end(), c.begin(), c.end());
+         else stack.insert(stack.end(), c.rbegin(), c.rend());
+      };
+      push_kids(-1);
+      int prev = -2;
+      while (!stack.empty())
+      {
+         const int i = stack.back();
+         stack.pop_back();
+         MbOp2 o = P.op2[desc_of[i]];
+         // the parent's kinematic state is in registers only if the parent was the op just before
+         o.flags = (uint8_t)(o.flags & ~MB2_LOAD_PARENT);
+         if (P.body[i].parent >= 0 && prev != P.body[i].parent)
+            o.flags |= MB2_LOAD_PARENT;
+         P.op3[n3++] = o;
+         prev = i;
+         push_kids(i);
+      }
    }
    auto look_ahead = [](MbOp2 *ops, int n) {
       for (int k = 0; k < n; k++)
@@ -515,7 +546,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          rec += rec_size(B.jtype);
       }
       (void)rec;
-      P.rec_doubles = algo == MB_ABA ? 8 * nb : 0; // MB_ABA_REC per body (aba.cuh)
+      P.rec_doubles = algo == MB_ABA ? MB_ABA_REC * nb : 0;
 
       // ops: iterative DFS emitting DESCEND on entry and ASCEND on exit
       int nops = 0;
@@ -629,6 +660,8 @@ int apply_source_modes(FlatTree &t, const int32_t *accel_source, std::vector<std
    for (int k = 0; k < P.nops; k++)
       if (P.op2[k].code & MB2_ASCEND)
          P.op2[k].flags = (uint8_t)((P.op2[k].flags & ~MB2_ACCSRC) | (locked[P.op2[k].body] ? MB2_ACCSRC : 0u));
+   for (int k = 0; k < P.nb; k++) // pass three: one record per body
+      P.op3[k].flags = (uint8_t)((P.op3[k].flags & ~MB2_ACCSRC) | (locked[P.op3[k].body] ? MB2_ACCSRC : 0u));
    // DoF rows of the joints that stay EFFORT_SOURCE, as runs of consecutive rows
    std::vector<char> effort((size_t)t.nv, 1);
    for (int i = 0; i < t.nb; i++)

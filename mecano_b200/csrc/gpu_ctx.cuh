@@ -203,20 +203,33 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    double2 *wsb;       // workspace + column of this thread
    long long ws_ld;
    __device__ __forceinline__ void rec_st2(int i2, double a, double b) { wsb[i2 * ws_ld] = make_double2(a, b); }
-   // pass-three ring: [stage][(q, qd) | rec0 .. rec3][BLOCK] double2, overlaid on the (then idle) stack area
+   // pass-three ring: [stage][(q, qd) | rec0 .. rec2][BLOCK] double2, overlaid on the (then idle) stack area
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
    {
-      const unsigned dst = sb + (unsigned)(stage * (5 * BLOCK * 16));
+      const unsigned dst = sb + (unsigned)(stage * (MB_ABA_RING_ROWS * BLOCK * 16));
       if (mask & 1)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
       if (mask & 2)
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(mb_row(qdb, (unsigned)dof, ld8d)) : "memory");
       const double2 *src = wsb + rec2 * ws_ld;
 #pragma unroll
-      for (int j = 0; j < 4; j++)
+      for (int j = 0; j < MB_ABA_REC / 2; j++)
          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(src + j * ws_ld) : "memory");
    }
-   __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const { mb_lds2(sb + (unsigned)((stage * 5 + row) * (BLOCK * 16)), a, b); }
+   __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const { mb_lds2(sb + (unsigned)((stage * MB_ABA_RING_ROWS + row) * (BLOCK * 16)), a, b); }
+   // The record of a body is dead once pass three has read it: tell L2 so (discard.global.L2 drops the lines without writing
+   // them back to HBM; the next tile of this thread overwrites them in full).  A warp's double2 row is four whole 128-byte lines.
+   bool discard_on;
+   __device__ __forceinline__ void rec_discard(int rec2) const
+   {
+      if (discard_on && (threadIdx.x & 7u) == 0)
+      {
+         const double2 *src = wsb + rec2 * ws_ld;
+#pragma unroll
+         for (int j = 0; j < MB_ABA_REC / 2; j++)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + j * ws_ld) : "memory");
+      }
+   }
    __device__ __forceinline__ void pass_fence() const { __threadfence(); }
 #if defined(MB_SPEC)
    // tree-specialised kernels: the constant records are literals in the generated source (constant-bank operands)
@@ -354,6 +367,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    c2.zlist = (const uint4 *)a.zero_entries;
    c2.nz8 = a.n_zero >> 3;
    c2.wsb = reinterpret_cast<double2 *>(a.ws) + ((long long)blockIdx.x * BLOCK + threadIdx.x);
+   c2.discard_on = ALGO == MB_ABA && (a.flags & MB_KFLAG_ABA_DISCARD) != 0;
    c2.ws_ld = a.ws_ld;
    // persistent grid: each block walks over tiles of BLOCK states.  The per-state areas (stack, rings) are private to a
    // thread and the constant records are read-only, so the threads of a block never synchronise again.

@@ -3,6 +3,9 @@
 #pragma once
 #include "program.h"
 
+// KernelArgs::flags of an ABA launch (the C ABI passes 0; api.cu sets these)
+#define MB_KFLAG_ABA_DISCARD 0x10000u // pass three discards the L2 lines of each record after reading it
+
 namespace mb
 {
 struct KernelArgs

@@ -103,7 +103,7 @@ struct MbOp2
 #define MB2_ROOT_PARENT 0x8u
 #define MB2_STORE_ACC 0x10u
 #define MB2_FIRST_CHILD 0x20u
-#define MB2_ACCSRC 0x40u // ABA ASCEND: the joint is an ACCELERATION_SOURCE (mecano_b200_set_joint_source_modes); not part of MB_F_*
+#define MB2_ACCSRC 0x40u // ABA ASCEND and pass-three records: the joint is an ACCELERATION_SOURCE (mecano_b200_set_joint_source_modes); not part of MB_F_*
 
 // per-body record for the CRBA ancestor walk (16 bytes; the first eight are what the dense layouts read, one aligned 64-bit load)
 struct MbWalk
@@ -157,12 +157,19 @@ __host__ __device__
 #endif
 static inline int mb_jp_size(int jtype) { return jtype == MB_REVOLUTE ? 2 : (jtype == MB_PRISMATIC ? 1 : 12); }
 
+// ABA pass-three record of one body, in doubles (three double2).  One-DoF joint: g = U / D without its component along the joint
+// axis (which is D / D = 1) and k0 = u / D: revolute (g.ax, g.ay, g.lx, g.ly, g.lz, k0), prismatic (g.ax, g.ay, g.az, g.lx, g.ly, k0).
+// SixDoF joint: the six accelerations.  An ACCELERATION_SOURCE joint stores its given acceleration (k0 / the six) and is
+// recognised in pass three by the MB2_ACCSRC flag of its op.
+#define MB_ABA_REC 6
+#define MB_ABA_RING_ROWS (1 + MB_ABA_REC / 2) // pass-three ring, double2 rows per stage: (q, qd) + the record
+
 enum MbAlgo { MB_RNEA = 0, MB_ABA = 1, MB_CRBA = 2, MB_CORIOLIS = 3 }; // MB_CORIOLIS: mass matrix + Coriolis matrix (coriolis.cuh)
 #define MB_NUM_ALGOS 4
 
 // Shared-memory stack slots (double2 per state) of a thread-per-state block.  With a tensor-memory stack (tm > 0 slots,
 // RNEA / ABA) the wide area lives in TMEM and only the narrow one in shared memory.  ABA overlays its pass-three ring
-// (4 stages x 5 rows) on the stack area.
+// (4 stages x MB_ABA_RING_ROWS rows) on the stack area.
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
@@ -171,8 +178,8 @@ static inline int mb_smem_stack_slots(int algo, const MbProgram &P, int tm)
    int s = P.stack2;
    if (tm > 0 && algo != MB_CRBA && algo != MB_CORIOLIS)
       s = P.nstack2 + (P.wstack2 > tm ? P.wstack2 - tm : 0); // wide slots beyond the TMEM share spill over behind the narrow area
-   if (algo == MB_ABA && s < 20)
-      s = 20;
+   if (algo == MB_ABA && s < 4 * MB_ABA_RING_ROWS)
+      s = 4 * MB_ABA_RING_ROWS; // the pass-three ring (4 stages) is overlaid on the stack area
    return s < 1 ? 1 : s;
 }
 // Blocks of MB_PARTIAL_TM_BLOCK threads (20 warps: five per TMEM lane quarter, 100 columns each) hold the first tm wide slots

@@ -233,13 +233,34 @@ static void joint_transform(const mo_tree *t, int i, const double *q, xf_t *x)
       case MO_PRISMATIC:
          x->t[0] = qi[0] * u[0]; x->t[1] = qi[0] * u[1]; x->t[2] = qi[0] * u[2];
          break;
+      case MO_SPHERICAL: /* SphericalJointReadOnly.java:31-35: setRotationAndZeroTranslation(jointOrientation) */
+         rot_quaternion(qi, x->R);
+         break;
+      case MO_PLANAR:
+      {
+         /* PlanarJointReadOnly.java:40-48 (pitch, x, z) of a planar pose: rotation about y, translation in the x-z plane
+          * (M/tools/MecanoFactories.java newPlanarPose3DBasics) */
+         const double c = cos(qi[0]), s = sin(qi[0]);
+         double T[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
+         memcpy(x->R, T, sizeof T);
+         x->t[0] = qi[1]; x->t[1] = 0.0; x->t[2] = qi[2];
+         break;
+      }
       default:
          rot_quaternion(qi, x->R);
          x->t[0] = qi[4]; x->t[1] = qi[5]; x->t[2] = qi[6];
    }
 }
 
-static int joint_ndof(const mo_tree *t, int i) { return t->jtype[i] == MO_SIXDOF ? 6 : 1; }
+static int joint_ndof(const mo_tree *t, int i)
+{
+   switch (t->jtype[i])
+   {
+      case MO_SIXDOF: return 6;
+      case MO_SPHERICAL: case MO_PLANAR: return 3;
+      default: return 1;
+   }
+}
 
 /* S * x for this joint, expressed in frameAfterJoint (motion subspace: M/multiBodySystem/interfaces/JointReadOnly.java:201-207,
  * M/tools/MecanoTools.java:964-995: revolute [axis;0], prismatic [0;axis], SixDoF identity) */
@@ -254,6 +275,12 @@ static void joint_S_times(const mo_tree *t, int i, const double *x, sv_t *out)
          break;
       case MO_PRISMATIC:
          out->v[0] = u[0] * x[0]; out->v[1] = u[1] * x[0]; out->v[2] = u[2] * x[0];
+         break;
+      case MO_SPHERICAL: /* unit twists = the three angular components (SphericalJoint.java, MecanoTools.computeSphericalJointMotionSubspace) */
+         for (int k = 0; k < 3; k++) out->w[k] = x[k];
+         break;
+      case MO_PLANAR: /* twistComponentIndex = {1, 3, 5}: w_y, v_x, v_z (MecanoTools.java:938) */
+         out->w[1] = x[0]; out->v[0] = x[1]; out->v[2] = x[2];
          break;
       default:
          for (int k = 0; k < 3; k++) { out->w[k] = x[k]; out->v[k] = x[3 + k]; }
@@ -1331,6 +1358,47 @@ void mo_integrate(const mo_tree *t, double dt, double *q, double *qd, double *qd
    for (int i = 0; i < t->nb; i++)
    {
       double *qi = q + t->cfg_off[i], *vi = qd + t->dof_off[i], *ai = qdd + t->dof_off[i];
+      if (t->jtype[i] == MO_SPHERICAL)
+      {
+         /* :449-452, :575-594 doubleIntegrate(angularAcceleration, angularVelocity, orientation):
+          * orientation = orientation * exp(dt w + 0.5 dt^2 wd) ; w += dt wd */
+         double rv[3], qint[4], qfin[4];
+         for (int k = 0; k < 3; k++)
+            rv[k] = dt * vi[k] + half_dt_dt * ai[k];
+         quat_from_rotation_vector(rv, qint);
+         quat_mul(qi, qint, qfin);
+         for (int k = 0; k < 4; k++)
+            qi[k] = qfin[k];
+         for (int k = 0; k < 3; k++)
+            vi[k] = dt * ai[k] + vi[k];
+         continue;
+      }
+      if (t->jtype[i] == MO_PLANAR)
+      {
+         /* a PlanarJoint is a FloatingJointBasics (PlanarJointBasics.java:17): :421-424 runs the floating-joint update :503-560 on its
+          * planar pose / twist / acceleration.  With everything in the x-z plane the rotation vector is along y, so the pitch-only
+          * orientation composes additively; the remaining steps are those of the SixDoF branch below restricted to the plane. */
+         const double th0 = qi[0], wy = vi[0], vx = vi[1], vz = vi[2], wdy = ai[0];
+         /* origin acceleration a + w x v with w = (0, wy, 0), v = (vx, 0, vz): (wy vz, 0, -wy vx) */
+         const double lx = ai[1] + wy * vz, lz = ai[2] - wy * vx;
+         const double dth = dt * wy + half_dt_dt * wdy;
+         const double c0 = cos(th0), s0 = sin(th0), ci = cos(dth), si = sin(dth);
+         const double tx = dt * vx + half_dt_dt * lx, tz = dt * vz + half_dt_dt * lz;
+         /* R_y(th) (x, 0, z) = (c x + s z, 0, -s x + c z) */
+         qi[1] += c0 * tx + s0 * tz;
+         qi[2] += -s0 * tx + c0 * tz;
+         qi[0] = th0 + dth;
+         const double ux = dt * lx + vx, uz = dt * lz + vz;
+         /* R_y(dth)^T (x, 0, z) = (c x - s z, 0, s x + c z) */
+         const double vfx = ci * ux - si * uz, vfz = si * ux + ci * uz;
+         const double wf = dt * wdy + wy;
+         const double l2x = ci * lx - si * lz, l2z = si * lx + ci * lz;
+         vi[0] = wf; vi[1] = vfx; vi[2] = vfz;
+         /* linear = a_origin' + v' x w' with v' = (vfx, 0, vfz), w' = (0, wf, 0): (-vfz wf, 0, vfx wf) */
+         ai[1] = l2x - vfz * wf;
+         ai[2] = l2z + vfx * wf;
+         continue;
+      }
       if (t->jtype[i] != MO_SIXDOF)
       {
          /* :710-733  q += 0.5 dt^2 qdd + dt qd ; qd += dt qdd */

@@ -29,7 +29,10 @@
 extern "C" {
 #endif
 
-enum { MO_REVOLUTE = 0, MO_PRISMATIC = 1, MO_SIXDOF = 2 };
+/* SphericalJoint: configuration [qx qy qz qs], velocity-like rows = angular part in frameAfterJoint
+ * (multiBodySystem/interfaces/SphericalJointReadOnly.java:31-71).  PlanarJoint: configuration [pitch x z], velocity-like rows
+ * [w_y v_x v_z] in frameAfterJoint (PlanarJointReadOnly.java:20-58, tools/MecanoTools.java:920-952). */
+enum { MO_REVOLUTE = 0, MO_PRISMATIC = 1, MO_SIXDOF = 2, MO_SPHERICAL = 3, MO_PLANAR = 4 };
 
 /* flags for mo_rnea (InverseDynamicsCalculator.java:291-306) */
 enum { MO_NO_CORIOLIS = 1, MO_NO_ACCELERATIONS = 2 };
@@ -40,7 +43,7 @@ typedef struct mo_tree
    int nv;              /* degrees of freedom */
    int nq;              /* configuration entries */
    const int *parent;   /* [nb] parent body, -1 = root body (elevator) */
-   const int *jtype;    /* [nb] MO_REVOLUTE / MO_PRISMATIC / MO_SIXDOF */
+   const int *jtype;    /* [nb] MO_REVOLUTE / MO_PRISMATIC / MO_SIXDOF / MO_SPHERICAL / MO_PLANAR */
    const double *axis;  /* [nb][3] unit joint axis (ignored for SixDoF) */
    const double *off_R; /* [nb][9] row-major rotation of frameBeforeJoint in parent's frameAfterJoint */
    const double *off_p; /* [nb][3] translation of the same */

@@ -128,14 +128,20 @@ template <class T> struct CpuCtx
    void aux_st(int i, T v) { aux[i] = v; }
    T rec_ld(int i) const { return rec[i]; }
    void rec_st2(int i2, T a, T b) { rec[2 * i2] = a; rec[2 * i2 + 1] = b; }
-   T ring3[4][10];
+   T ring3[4][2 + MB_ABA_REC];
    void pf3_issue(int stage, int cfg, int dof, int rec2, int mask)
    {
       const T nan = (T)(0.0 / 0.0);
       ring3[stage][0] = (mask & 1) ? ld_q(cfg) : nan;
       ring3[stage][1] = (mask & 2) ? ld_qd(dof) : nan;
-      for (int j = 0; j < 8; j++)
+      for (int j = 0; j < MB_ABA_REC; j++)
          ring3[stage][2 + j] = rec[2 * rec2 + j];
+   }
+   // the GPU context tells L2 that the record is dead; here: poison it, so that a second read shows up as NaN
+   void rec_discard(int rec2)
+   {
+      for (int j = 0; j < MB_ABA_REC; j++)
+         rec[2 * rec2 + j] = (T)(0.0 / 0.0);
    }
    void pf3_ld2(int stage, int row, T &a, T &b) const { a = ring3[stage][2 * row]; b = ring3[stage][2 * row + 1]; }
    void pass_fence() const {}

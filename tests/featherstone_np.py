@@ -9,7 +9,7 @@ Spatial vectors are angular-first [w; v], like Mecano and like Featherstone.
 """
 import numpy as np
 
-REVOLUTE, PRISMATIC, SIXDOF = 0, 1, 2
+REVOLUTE, PRISMATIC, SIXDOF, SPHERICAL, PLANAR = 0, 1, 2, 3, 4
 
 
 def skew(v):
@@ -74,6 +74,12 @@ class Model:
             elif jt == PRISMATIC:
                 S = np.zeros((6, 1))
                 S[3:, 0] = tree.axis[i]
+            elif jt == SPHERICAL:  # angular velocity in the body frame (SphericalJointReadOnly.java:31-60)
+                S = np.zeros((6, 3))
+                S[0, 0] = S[1, 1] = S[2, 2] = 1.0
+            elif jt == PLANAR:  # (w_y, v_x, v_z) in the body frame (MecanoTools.java:920-952)
+                S = np.zeros((6, 3))
+                S[1, 0] = S[3, 1] = S[5, 2] = 1.0
             else:
                 S = np.eye(6)
             self.S.append(S)
@@ -97,6 +103,10 @@ class Model:
             RJ, tJ = rot_axis_angle(t.axis[i], qi[0]), np.zeros(3)
         elif jt == PRISMATIC:
             RJ, tJ = np.eye(3), qi[0] * np.asarray(t.axis[i])
+        elif jt == SPHERICAL:
+            RJ, tJ = rot_quat(*qi[:4]), np.zeros(3)
+        elif jt == PLANAR:  # rotation about y by the pitch, translation in the x-z plane
+            RJ, tJ = rot_axis_angle(np.array([0.0, 1.0, 0.0]), qi[0]), np.array([qi[1], 0.0, qi[2]])
         else:
             RJ, tJ = rot_quat(*qi[:4]), np.asarray(qi[4:7])
         R = t.off_R[i] @ RJ

@@ -33,10 +33,18 @@ def cases(rng):
         ("axis-aligned tree", td.random_tree(rng, 10, floating=True, axis_aligned=True)),
         ("H37", td.humanoid(rng, 2)),
         ("H36", td.humanoid(rng, 1)),
+        # SphericalJoint / PlanarJoint (ForwardDynamicsCalculatorTest.testJointChain, :253-281: chains of every joint type)
+        ("all joint types chain", td.mixed_chain(rng, [td.REVOLUTE, td.SPHERICAL, td.PRISMATIC, td.PLANAR, td.REVOLUTE, td.SPHERICAL, td.PLANAR, td.SIXDOF, td.REVOLUTE])),
+        ("spherical chain 6", td.mixed_chain(rng, [td.SPHERICAL] * 6)),
+        ("floating + mixed tree 30", td.mixed_tree(rng, 30, floating=True, com_rotation=True)),
+        ("planar root + mixed tree 12", td.mixed_tree(rng, 12, weights=(1, 1, 0, 1, 2))),
     ]
 
 
-@pytest.mark.parametrize("idx", range(10))
+N_CASES = 14
+
+
+@pytest.mark.parametrize("idx", range(N_CASES))
 def test_oracle_matches_featherstone(idx):
     rng = np.random.default_rng(100 + idx)
     name, t = cases(rng)[idx]
@@ -50,13 +58,13 @@ def test_oracle_matches_featherstone(idx):
         assert err(o.crba(q[:, s]), m.crba(q[:, s])) < 1e-12, name
 
 
-@pytest.mark.parametrize("idx", range(10))
+@pytest.mark.parametrize("idx", range(N_CASES))
 def test_reference_invariants(idx):
     """FD(ID(qdd)) == qdd and M qdd + ID(qdd = 0) == ID(qdd), with random external wrenches and gravity in [-10, -1]
     (ForwardDynamicsCalculatorTest.java:767-901, 904-1003), at the reference's tolerances."""
     rng = np.random.default_rng(200 + idx)
     name, t = cases(rng)[idx]
-    eps = FLOATING_JOINT_EPSILON if (t.jtype == td.SIXDOF).any() else 2.0 * ONE_DOF_JOINT_EPSILON
+    eps = FLOATING_JOINT_EPSILON if (t.jtype >= td.SIXDOF).any() else 2.0 * ONE_DOF_JOINT_EPSILON
     o = ol.Oracle(t, gravity=(0.0, 0.0, -rng.uniform(1, 10)))
     n = 50
     q, qd, qdd, _ = td.random_states(rng, t, n)
@@ -72,7 +80,7 @@ def test_reference_invariants(idx):
             assert np.linalg.eigvalsh(M[:, :, s]).min() > 0
 
 
-@pytest.mark.parametrize("idx", range(10))
+@pytest.mark.parametrize("idx", range(N_CASES))
 def test_reference_invariant_mixed_source_modes(idx):
     """ForwardDynamicsCalculatorTest.testJointMixedSourceModeGeneral (:389-488) and
     testJointAccelerationSourceWithZeroVelocityAcceleration (:283-386): with a random subset of joints switched to
@@ -90,17 +98,17 @@ def test_reference_invariant_mixed_source_modes(idx):
         qd_s, qdd_s = qd[:, s].copy(), qdd[:, s].copy()
         if s % 2:  # the zero-velocity / zero-acceleration variant
             for b in np.nonzero(locked)[0]:
-                nd = 6 if t.jtype[b] == td.SIXDOF else 1
+                nd = td.NDOF[int(t.jtype[b])]
                 qd_s[t.dof_off[b]:t.dof_off[b] + nd] = 0.0
                 qdd_s[t.dof_off[b]:t.dof_off[b] + nd] = 0.0
         fext = None if s % 3 else rng.uniform(-1, 1, size=(t.nb, 6))
         tau = o.rnea(q[:, s], qd_s, qdd_s, fext)
         tau_in = tau.copy()
         for b in np.nonzero(locked)[0]:
-            nd = 6 if t.jtype[b] == td.SIXDOF else 1
+            nd = td.NDOF[int(t.jtype[b])]
             tau_in[t.dof_off[b]:t.dof_off[b] + nd] = 0.0
         qdd_out, tau_out = o.aba_sources(q[:, s], qd_s, tau_in, qdd_s, locked, fext)
-        scale = 4.0 if (t.jtype == td.SIXDOF).any() else 1.0  # the reference's floating-joint tolerances are 5x its one-DoF ones
+        scale = 4.0 if (t.jtype >= td.SIXDOF).any() else 1.0  # the reference's floating-joint tolerances are 5x its one-DoF ones
         assert np.max(np.abs(qdd_out - qdd_s)) <= scale * 1.0e-12 * max(1.0, np.max(np.abs(qdd_s))), name
         assert np.max(np.abs(tau_out - tau)) <= scale * 1.0e-12 * max(1.0, np.max(np.abs(tau))), name
         # nothing locked: the plain algorithm
@@ -108,7 +116,7 @@ def test_reference_invariant_mixed_source_modes(idx):
         assert np.array_equal(free_qdd, o.aba(q[:, s], qd_s, tau, fext)) and np.array_equal(free_tau, tau)
 
 
-@pytest.mark.parametrize("idx", range(10))
+@pytest.mark.parametrize("idx", range(N_CASES))
 def test_centroidal_momentum_matrix_and_convective_term(idx):
     """CompositeRigidBodyMassMatrixCalculatorTest.java:62-82 compares getCentroidalMomentumMatrix() / getCentroidalConvectiveTerm()
     with CentroidalMomentumRateCalculator at 1e-10 (EPSILON); the same two facts against plain sums over the bodies
@@ -136,7 +144,7 @@ def test_centroidal_momentum_matrix_and_convective_term(idx):
         assert np.array_equal(Ac[3:], A[3:])
 
 
-@pytest.mark.parametrize("idx", range(10))
+@pytest.mark.parametrize("idx", range(N_CASES))
 def test_coriolis_matrix(idx):
     """CompositeRigidBodyMassMatrixCalculatorTest.testCoriolisMatrix (:85-138): C(q, qd) qd equals the joint efforts of inverse
     dynamics without joint accelerations (zero gravity, the calculators' default), at 1e-11.  Beyond the reference's test:
@@ -150,7 +158,7 @@ def test_coriolis_matrix(idx):
         assert np.array_equal(M, o.crba(q[:, s])), name
         want = o.rnea(q[:, s], qd[:, s], np.zeros(t.nv), flags=2)
         assert np.max(np.abs(C @ qd[:, s] - want)) < 1e-11 * max(1.0, np.max(np.abs(want))), name
-        if not (t.jtype == td.SIXDOF).any():
+        if not (t.jtype >= td.SIXDOF).any():  # q + h qd is the configuration after h only when every joint is one-DoF
             h = 1e-6
             Mp, Mm = o.crba(q[:, s] + h * qd[:, s]), o.crba(q[:, s] - h * qd[:, s])
             assert np.max(np.abs((Mp - Mm) / (2 * h) - (C + C.T))) < 1e-6 * max(1.0, np.max(np.abs(C))), name

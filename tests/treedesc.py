@@ -7,7 +7,9 @@ from dataclasses import dataclass
 
 import numpy as np
 
-REVOLUTE, PRISMATIC, SIXDOF = 0, 1, 2
+REVOLUTE, PRISMATIC, SIXDOF, SPHERICAL, PLANAR = 0, 1, 2, 3, 4
+NDOF = {REVOLUTE: 1, PRISMATIC: 1, SIXDOF: 6, SPHERICAL: 3, PLANAR: 3}
+NCFG = {REVOLUTE: 1, PRISMATIC: 1, SIXDOF: 7, SPHERICAL: 4, PLANAR: 3}
 
 
 @dataclass
@@ -106,8 +108,8 @@ def make_tree(rng, parent, jtype, com_rotation=False, axis_aligned=False):
         t.mass[new] = 0.1 + rng.uniform()
         t.dof_off[new] = nv
         t.cfg_off[new] = nq
-        nv += 6 if jtype[old] == SIXDOF else 1
-        nq += 7 if jtype[old] == SIXDOF else 1
+        nv += NDOF[jtype[old]]
+        nq += NCFG[jtype[old]]
     t.nv, t.nq = nv, nq
     return t.contiguous()
 
@@ -138,6 +140,34 @@ def random_tree(rng, n, floating=False, prismatic_fraction=0.0, **kw):
     return make_tree(rng, parent, jtype, **kw)
 
 
+def mixed_chain(rng, types, floating=False, **kw):
+    """A serial chain with the given joint types (ForwardDynamicsCalculatorTest.testJointChain: all joint types)."""
+    parent, jtype = [], []
+    if floating:
+        parent.append(-1)
+        jtype.append(SIXDOF)
+    for jt in types:
+        parent.append(len(parent) - 1)
+        jtype.append(jt)
+    return make_tree(rng, parent, jtype, **kw)
+
+
+def mixed_tree(rng, n, floating=False, weights=(0.4, 0.2, 0.0, 0.2, 0.2), **kw):
+    """Random tree whose joints are drawn from (revolute, prismatic, sixdof, spherical, planar) with the given weights."""
+    parent, jtype = [], []
+    if floating:
+        parent.append(-1)
+        jtype.append(SIXDOF)
+    first = len(parent)
+    pred = len(parent) - 1
+    w = np.asarray(weights, dtype=float) / np.sum(weights)
+    for _ in range(n):
+        parent.append(pred)
+        jtype.append(int(rng.choice(5, p=w)))
+        pred = int(rng.integers(first, len(parent)))
+    return make_tree(rng, parent, jtype, **kw)
+
+
 def humanoid(rng, neck=2, **kw):
     """SixDoF pelvis + 2 legs x 6 + spine 3 + 2 arms x 7 + neck (2 -> H37, 1 -> H36); SURVEY.md 8(d)."""
     parent, jtype = [-1], [SIXDOF]
@@ -163,12 +193,16 @@ def random_states(rng, t, n):
     """DoF-major / state-minor buffers [k, s]; distributions per SURVEY.md 8(d)."""
     q = rng.uniform(-np.pi, np.pi, size=(t.nq, n))
     for i in range(t.nb):
-        if t.jtype[i] == SIXDOF:
+        if t.jtype[i] in (SIXDOF, SPHERICAL):
             c = t.cfg_off[i]
             quat = rng.normal(size=(4, n))
             quat /= np.linalg.norm(quat, axis=0)
             q[c:c + 4] = quat
-            q[c + 4:c + 7] = rng.uniform(-1, 1, size=(3, n))
+            if t.jtype[i] == SIXDOF:
+                q[c + 4:c + 7] = rng.uniform(-1, 1, size=(3, n))
+        elif t.jtype[i] == PLANAR:  # (pitch, x, z)
+            c = t.cfg_off[i]
+            q[c + 1:c + 3] = rng.uniform(-1, 1, size=(2, n))
     qd = rng.uniform(-1, 1, size=(t.nv, n))
     qdd = rng.uniform(-1, 1, size=(t.nv, n))
     tau = rng.uniform(-1, 1, size=(t.nv, n))
