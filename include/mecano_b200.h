@@ -41,10 +41,19 @@ extern "C" {
 
 #define MECANO_B200_VERSION 200
 
-/* joint types (M/multiBodySystem/{RevoluteJoint,PrismaticJoint,SixDoFJoint}.java) */
+/* joint types (M/multiBodySystem/{RevoluteJoint,PrismaticJoint,SixDoFJoint,SphericalJoint,PlanarJoint}.java).
+ * Rows of a joint in the matrices of the ABI (M/multiBodySystem/interfaces/*JointReadOnly.java):
+ *   REVOLUTE / PRISMATIC   configuration [q]                   velocity-like [qd]
+ *   SIXDOF                 configuration [qx qy qz qs x y z]   velocity-like [wx wy wz vx vy vz]  (SixDoFJointReadOnly.java:21-26)
+ *   SPHERICAL              configuration [qx qy qz qs]         velocity-like [wx wy wz]           (SphericalJointReadOnly.java:31-71)
+ *   PLANAR                 configuration [pitch x z]           velocity-like [wy vx vz]           (PlanarJointReadOnly.java:20-58)
+ * velocity-like = velocity, acceleration, effort; all expressed in the joint's frameAfterJoint.  (FixedJoint has no rows: the
+ * host model welds its successor into the parent body before the tables are built.) */
 #define MECANO_B200_REVOLUTE 0
 #define MECANO_B200_PRISMATIC 1
 #define MECANO_B200_SIXDOF 2
+#define MECANO_B200_SPHERICAL 3
+#define MECANO_B200_PLANAR 4
 
 /* status codes */
 #define MECANO_B200_OK 0
@@ -100,12 +109,12 @@ typedef struct mecano_b200_tree_desc
    int32_t struct_size; /* sizeof(mecano_b200_tree_desc), for ABI evolution */
    int32_t n_bodies;
    int32_t n_dofs;   /* MultiBodySystemTools.computeDegreesOfFreedom */
-   int32_t n_cfg;    /* configuration rows: 1 per OneDoF joint, 7 per SixDoF joint */
+   int32_t n_cfg;    /* configuration rows: 1 per OneDoF joint, 7 per SixDoF, 4 per Spherical, 3 per Planar joint */
    int32_t n_levels; /* 0 if level_start == NULL */
    const int32_t *level_start; /* [n_levels + 1] first body of each tree level */
    const int32_t *parent;      /* [n_bodies] */
-   const int32_t *joint_type;  /* [n_bodies] MECANO_B200_REVOLUTE / PRISMATIC / SIXDOF */
-   const double *axis;         /* [n_bodies][3] unit joint axis in frameAfterJoint (ignored for SixDoF) */
+   const int32_t *joint_type;  /* [n_bodies] MECANO_B200_REVOLUTE / PRISMATIC / SIXDOF / SPHERICAL / PLANAR */
+   const double *axis;         /* [n_bodies][3] unit joint axis in frameAfterJoint (one-DoF joints only) */
    const double *offset_rot;   /* [n_bodies][9] row-major rotation: frameBeforeJoint in the parent's frameAfterJoint */
    const double *offset_pos;   /* [n_bodies][3] */
    const double *com_rot;      /* [n_bodies][9] inertia pose: bodyFixedFrame (CoM frame) in frameAfterJoint */

@@ -4,7 +4,7 @@
  * and obtain the level-ordered tables for mecano_b200_create().  A Java host does not need this header:
  * it flattens its own MultiBodySystemReadOnly.
  *
- * Mirrors: RigidBody / RevoluteJoint / PrismaticJoint / SixDoFJoint constructors
+ * Mirrors: RigidBody / RevoluteJoint / PrismaticJoint / SixDoFJoint / SphericalJoint / PlanarJoint / FixedJoint constructors
  * (M/multiBodySystem/*.java), MultiBodySystemBasics.toMultiBodySystemBasics
  * (M/multiBodySystem/interfaces/MultiBodySystemBasics.java:76-142), and the generators of
  * M/tools/MultiBodySystemRandomTools.java.
@@ -34,11 +34,15 @@ const char *mecano_model_last_error(const mecano_model *m);
 int mecano_model_add_revolute_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12, const double *axis3);
 int mecano_model_add_prismatic_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12, const double *axis3);
 int mecano_model_add_sixdof_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
+/* SphericalJoint (M/multiBodySystem/SphericalJoint.java:43-69) and PlanarJoint (PlanarJoint.java:37-61): three DoFs each */
+int mecano_model_add_spherical_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
+int mecano_model_add_planar_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
 /* FixedJoint (M/multiBodySystem/FixedJoint.java:40-62): 0 DoF.  Host-only: at finalize its successor is welded into the nearest
  * moving ancestor (inertia, children and offsets), so the GPU tables contain moving joints only. */
-#define MECANO_MODEL_FIXED 3
+#define MECANO_MODEL_FIXED 5
 int mecano_model_add_fixed_joint(mecano_model *m, const char *name, int predecessor_body, const double *transform12);
-/* Configuration a joint keeps when it is ignored (one-DoF: q; SixDoF: qx qy qz qs x y z); default zero / identity. */
+/* Configuration a joint keeps when it is ignored (one-DoF: q; SixDoF: qx qy qz qs x y z; Spherical: qx qy qz qs; Planar: pitch x z);
+ * default zero / identity. */
 int mecano_model_set_joint_configuration(mecano_model *m, int joint, const double *q, int n);
 /* RigidBody(name, parentJoint, momentOfInertia, mass, inertiaPose).  Returns the body id (= joint id + 1). */
 int mecano_model_add_rigid_body(mecano_model *m, const char *name, int parent_joint, const double *inertia9, double mass, const double *inertia_pose12);
@@ -47,6 +51,9 @@ int mecano_model_add_rigid_body(mecano_model *m, const char *name, int parent_jo
 int mecano_model_next_one_dof_joint_chain(mecano_model *m, uint64_t seed, int predecessor_body, int n_joints, double prismatic_fraction);
 int mecano_model_next_one_dof_joint_tree(mecano_model *m, uint64_t seed, int predecessor_body, int n_joints, double prismatic_fraction);
 int mecano_model_next_floating_base(mecano_model *m, uint64_t seed, int predecessor_body); /* returns the new body id */
+/* nextJointChain / nextJointTree (MultiBodySystemRandomTools.java:424-440, :844-860): joints of random types, all five moving types */
+int mecano_model_next_joint_chain(mecano_model *m, uint64_t seed, int predecessor_body, int n_joints);
+int mecano_model_next_joint_tree(mecano_model *m, uint64_t seed, int predecessor_body, int n_joints);
 int mecano_model_next_humanoid(mecano_model *m, uint64_t seed, int neck_joints);
 
 /* toMultiBodySystemBasics(rootBody): fixes the joint order / index provider and builds the tables. */

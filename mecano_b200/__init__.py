@@ -9,5 +9,5 @@ from ._capi import MecanoB200Error  # noqa: F401
 from .calculators import (CompositeRigidBodyMassMatrixCalculator, ForwardDynamicsCalculator, InverseDynamicsCalculator, JointSourceMode,  # noqa: F401
                           MatrixDimensionException, MultiBodyDynamicsStep, MultiBodySystemStateIntegrator)
 from .engine import Engine, MultiDeviceEngine, measure_fp64_peak, measure_hbm_peak  # noqa: F401
-from .multibody import (FixedJoint, JointMatrixIndexProvider, MultiBodySystem, MultiBodySystemRandomTools, PrismaticJoint, RevoluteJoint,  # noqa: F401
-                        RigidBody, RigidBodyTransform, ScrewTheoryException, SixDoFJoint)
+from .multibody import (FixedJoint, JointMatrixIndexProvider, MultiBodySystem, MultiBodySystemRandomTools, PlanarJoint, PrismaticJoint,  # noqa: F401
+                        RevoluteJoint, RigidBody, RigidBodyTransform, ScrewTheoryException, SixDoFJoint, SphericalJoint)

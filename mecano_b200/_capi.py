@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmecano_b200.so")
+LIB_PATH = os.environ.get("MECANO_B200_LIB") or os.path.join(_HERE, "libmecano_b200.so")  # (override: kernel variants of scripts/build_variants.sh)
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

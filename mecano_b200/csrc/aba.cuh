@@ -93,6 +93,10 @@ template <class T, class Ctx> MB_HD void aba_fold(Ctx &c, const MbOp2 o, const A
       aux_st_abi<T>(c, o.paux, acc, pacc);
 }
 
+} // namespace mb
+#include "multidof_aba.cuh"
+namespace mb
+{
 // ---- pass two of a joint in JointSourceMode.ACCELERATION_SOURCE (ForwardDynamicsCalculator.java:45-57, :1237-1253): its
 // acceleration is an input, so nothing is removed from the articulated inertia and the known S qdd enters the bias wrench:
 // I^a = I^A, p^a = p^A + I^A (c + S qdd).  Pass three reads qdd back through the same record (g = 0, k0 = qdd).
@@ -220,8 +224,9 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
 
 template <class T, class Ctx> MB_HD void aba_descend_6dof(Ctx &c, const MbOp2 o, SvT<T> &v)
 {
-   const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
-   const SvT<T> vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
+   const int sub = mb_sub_of<Ctx>(o);
+   const XfT<T> X = joint_xf_multi<T>(c, c.cst(o.body), o.cfg, sub);
+   const SvT<T> vj = ld_svj<T>(o.dof, sub, [&](int r) { return c.ld_qd(r); });
    v = motion_to_child(X, v) + vj;
    c.acc_st(o.slot, o.wslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
    if (!(o.flags & MB2_ROOT_PARENT))
@@ -229,8 +234,12 @@ template <class T, class Ctx> MB_HD void aba_descend_6dof(Ctx &c, const MbOp2 o,
 }
 
 template <class T, class Ctx, bool FEXT>
-MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, AbiT<T> &acc, SvT<T> &pacc)
+MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &acc, SvT<T> &pacc)
 {
+   if (mb_sub_of<Ctx>(o) == MB_SUB_SPHERICAL)
+      return aba_ascend_3dof<T, Ctx, FEXT, false>(c, o, ext, rec_hi, acc, pacc);
+   if (mb_sub_of<Ctx>(o) == MB_SUB_PLANAR)
+      return aba_ascend_3dof<T, Ctx, FEXT, true>(c, o, ext, rec_hi, acc, pacc);
    const auto C = c.cst(o.body);
    SvT<T> vb;
    c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
@@ -331,8 +340,12 @@ MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, A
    }
 }
 
-template <class T, class Ctx, bool LOCKS> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a)
+template <class T, class Ctx, bool LOCKS> MB_HD void aba_pass3_6dof(Ctx &c, const MbOp2 o, int st, int rec_hi, SvT<T> &v, SvT<T> &a)
 {
+   if (mb_sub_of<Ctx>(o) == MB_SUB_SPHERICAL)
+      return aba_pass3_3dof<T, Ctx, LOCKS, false>(c, o, st, rec_hi, v, a);
+   if (mb_sub_of<Ctx>(o) == MB_SUB_PLANAR)
+      return aba_pass3_3dof<T, Ctx, LOCKS, true>(c, o, st, rec_hi, v, a);
    SvT<T> x;
    c.pf3_ld2(st, 1, x.a.x, x.a.y);
    c.pf3_ld2(st, 2, x.a.z, x.l.x);
@@ -416,7 +429,7 @@ MB_HD void aba_op(Ctx &c, const int k, const MbOp2 o, const int ext, SvT<T> &v, 
          if (o.code & MB2_SC)
             mb_sincos(pp.mq, &ns, &nc);
          if (o.code & MB2_ASCEND)
-            aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
+            aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, -1, acc, pacc); // (tree-specialised kernels: no three-DoF joints, api.cu)
          else
             aba_descend_6dof<T, Ctx>(c, o, v);
          break;
@@ -528,7 +541,7 @@ MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T
       default:
          if (o.code & MB2_SC)
             mb_sincos(pp.mq, &ns, &nc);
-         aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, v, a);
+         aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, -1, v, a);
          break;
    }
    pp.s = ns;
@@ -550,7 +563,7 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
       mb_sincos(pp.mq, &ns, &nc);
    if (JT == MB_SIXDOF)
    {
-      if (ASC) aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, acc, pacc);
+      if (ASC) aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, P.body[o.body].rec, acc, pacc);
       else aba_descend_6dof<T, Ctx>(c, o, v);
    }
    else if (ASC)
@@ -572,7 +585,7 @@ MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *
    if (o.code & MB2_SC)
       mb_sincos(pp.mq, &ns, &nc);
    if (JT == MB_SIXDOF)
-      aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, v, a);
+      aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, P.body[o.body].rec, v, a);
    else
       aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, false, LOCKS>(c, o, st, v, a, pp, ns, nc);
    pp.s = ns;

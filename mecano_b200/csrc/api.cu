@@ -45,6 +45,7 @@ struct mecano_b200_handle
    int n_accel_source = 0;           // joints in ACCELERATION_SOURCE mode (mecano_b200_set_joint_source_modes)
    std::vector<std::pair<int, int>> effort_dof_runs; // (first DoF row, count) runs of DoF rows whose joints are EFFORT_SOURCE
    bool warp_ok = false;             // the tree fits the warp-per-state variant (<= 32 bodies)
+   bool has_3dof = false;            // the tree has spherical / planar joints (generic thread-per-state kernels only)
    int64_t warp_below[MB_NUM_ALGOS] = {0, 0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
    std::string error;
    // host pipeline (lazy)
@@ -148,8 +149,8 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       // the optional fp32 variant: plain calls on the thread-per-state kernels only, never a silent fp64 substitute
       if (algo > MB_CRBA || packed || fext || opt.body_acc || opt.joint_wrench || x2 || opt.cmm || opt.root_wrench || flags != 0)
          return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant covers plain RNEA / ABA / CRBA calls only (no external wrenches, flags, by-products)");
-      if (!h->plan[algo].fp32_ok)
-         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant is compiled for the launch configuration of humanoid-sized trees only");
+      if (!h->plan[algo].fp32_ok || h->has_3dof)
+         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant is compiled for the launch configuration of humanoid-sized trees of one-DoF and SixDoF joints only");
    }
    // thread- or warp-per-state: explicit choice, else by batch size (a warp per state fills the machine from a few hundred
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
@@ -678,6 +679,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       {
          if (P.body[i].parent >= 0) nchild[P.body[i].parent]++;
          h->max_ndof = std::max(h->max_ndof, P.body[i].ndof);
+         h->has_3dof = h->has_3dof || P.body[i].sub != MB_SUB_SIX;
       }
       for (int i = 0; i < P.nb; i++) h->max_children = std::max(h->max_children, nchild[i]);
       cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -754,7 +756,7 @@ int mecano_b200_set_variant(mecano_b200_handle *h, int variant)
    if (variant != MECANO_B200_VARIANT_AUTO && variant != MECANO_B200_VARIANT_THREAD && variant != MECANO_B200_VARIANT_WARP)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown variant");
    if (variant == MECANO_B200_VARIANT_WARP && !h->warp_ok)
-      return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body)");
+      return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body) of one-DoF and SixDoF joints");
    h->variant = variant;
    return MECANO_B200_OK;
 }
@@ -770,6 +772,8 @@ int mecano_b200_specialize(mecano_b200_handle *h, uint32_t algo_mask)
          continue;
       if (algo == MB_CRBA)
          continue; // bound by the HBM write of the mass matrix: the generic kernel is already at the roof
+      if (h->has_3dof)
+         continue; // spherical / planar joints: the generic kernels serve them (two-slot pass-three records, multidof_aba.cuh)
       const MbProgram &P = h->tree.prog[algo];
       // Unrolled code is fetched once per tile of states; beyond ~100 KB it no longer fits the instruction caches and the
       // block becomes fetch-bound (measured: 32-body humanoid RNEA 172 KB -> 0.78x, 15-body tree 81 KB -> 1.42x of the generic
@@ -1099,6 +1103,7 @@ int mecano_b200_integrate(mecano_b200_handle *h, int64_t n, int64_t ld, double d
       J.cfg[i] = (uint16_t)P.body[i].cfg_off;
       J.dof[i] = (uint16_t)P.body[i].dof_off;
       J.type[i] = (uint8_t)P.body[i].jtype;
+      J.sub[i] = (uint8_t)P.body[i].sub;
    }
    mb::IntegrateArgs a;
    a.q = q; a.qd = qd; a.qdd = qdd;

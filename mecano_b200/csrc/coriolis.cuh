@@ -162,8 +162,15 @@ template <class T, class Ctx> MB_HD SvT<T> cor_ld_twist(Ctx &c, int slot2)
 // entries of one column `col` (a DoF of a descendant, force columns F1, F2, F3 expressed in the frame of body `jt`, twist v)
 // against the DoFs of that body: C[i, col] = S_i . F1, C[col, i] = Sdot_i . F2 + S_i . F3, M[i, col] = M[col, i] = S_i . F2
 // (:745-760), with Sdot_i = v x S_i (:604-630) so that Sdot_i . F2 = -(v x* F2)_i
+// element i of a six-array without indexing it at run time (the arrays stay in registers)
+template <class T> MB_HD T pick6(const T f[6], int i)
+{
+   return i == 0 ? f[0] : (i == 1 ? f[1] : (i == 2 ? f[2] : (i == 3 ? f[3] : (i == 4 ? f[4] : f[5]))));
+}
+
+// sub: MB_SUB_* of a multi-DoF joint (DoF r = component mb_sub_component(sub, r) of the spatial vectors, multidof.cuh)
 template <class T, class Ctx>
-MB_HD void cor_project(Ctx &c, int jt, int di, int col, const SvT<T> &v, const SvT<T> &F1, const SvT<T> &F2, const SvT<T> &F3)
+MB_HD void cor_project(Ctx &c, int jt, int sub, int di, int col, const SvT<T> &v, const SvT<T> &F1, const SvT<T> &F2, const SvT<T> &F3)
 {
    const int nv = c.n_dofs();
    if (jt == MB_REVOLUTE)
@@ -186,13 +193,28 @@ MB_HD void cor_project(Ctx &c, int jt, int di, int col, const SvT<T> &v, const S
       const T f1[6] = {F1.a.x, F1.a.y, F1.a.z, F1.l.x, F1.l.y, F1.l.z};
       const T f2[6] = {F2.a.x, F2.a.y, F2.a.z, F2.l.x, F2.l.y, F2.l.z};
       const T g[6] = {F3.a.x - d.a.x, F3.a.y - d.a.y, F3.a.z - d.a.z, F3.l.x - d.l.x, F3.l.y - d.l.y, F3.l.z - d.l.z};
-#pragma unroll
-      for (int r = 0; r < 6; r++)
+      if (sub == MB_SUB_SIX)
       {
-         c.st_C((di + r) * nv + col, f1[r]);
-         c.st_C(col * nv + di + r, g[r]);
-         c.st_M((di + r) * nv + col, f2[r]);
-         c.st_M(col * nv + di + r, f2[r]);
+#pragma unroll
+         for (int r = 0; r < 6; r++)
+         {
+            c.st_C((di + r) * nv + col, f1[r]);
+            c.st_C(col * nv + di + r, g[r]);
+            c.st_M((di + r) * nv + col, f2[r]);
+            c.st_M(col * nv + di + r, f2[r]);
+         }
+      }
+      else
+      {
+#pragma unroll
+         for (int r = 0; r < 3; r++)
+         {
+            const int cr = mb_sub_component(sub, r);
+            c.st_C((di + r) * nv + col, pick6(f1, cr));
+            c.st_C(col * nv + di + r, pick6(g, cr));
+            c.st_M((di + r) * nv + col, pick6(f2, cr));
+            c.st_M(col * nv + di + r, pick6(f2, cr));
+         }
       }
    }
 }
@@ -220,7 +242,7 @@ MB_HD void cor_walk(const MbProgram &P, Ctx &c, int b, int col, T s, T cs, SvT<T
       }
       b = w.parent;
       w = P.walk[b];
-      cor_project<T>(c, w.jtype, w.dof, col, cor_ld_twist<T>(c, w.slot), F1, F2, F3);
+      cor_project<T>(c, w.jtype, mb_sub_of<Ctx>(w), w.dof, col, cor_ld_twist<T>(c, w.slot), F1, F2, F3);
       if (w.jtype != MB_SIXDOF)
          c.stk_ld2(w.slot, MB_COR_JP, s, cs);
    }
@@ -254,8 +276,8 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
             v = cor_ld_twist<T>(c, o.pslot);
          if (jt == MB_SIXDOF)
          {
-            const XfT<T> X = joint_xf_6dof<T>(c, C, o.cfg);
-            v = motion_to_child(X, v) + ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
+            const XfT<T> X = joint_xf_multi<T>(c, C, o.cfg, mb_sub_of<Ctx>(o));
+            v = motion_to_child(X, v) + ld_svj<T>(o.dof, mb_sub_of<Ctx>(o), [&](int r) { return c.ld_qd(r); });
             stk_st_xf<T>(c, o.slot + MB_COR_JP, X);
             cor_st_twist<T>(c, o.slot, v);
          }
@@ -350,12 +372,14 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
          }
          else
          {
+            const int sub = mb_sub_of<Ctx>(o), nd = mb_sub_ndof(sub);
 #pragma unroll 1
-            for (int col = 0; col < 6; col++)
+            for (int col = 0; col < nd; col++)
             {
+               const int cc = mb_sub_component(sub, col);
                SvT<T> S = sv_zero<T>();
-               if (col == 0) S.a.x = (T)1; else if (col == 1) S.a.y = (T)1; else if (col == 2) S.a.z = (T)1;
-               else if (col == 3) S.l.x = (T)1; else if (col == 4) S.l.y = (T)1; else S.l.z = (T)1;
+               if (cc == 0) S.a.x = (T)1; else if (cc == 1) S.a.y = (T)1; else if (cc == 2) S.a.z = (T)1;
+               else if (cc == 3) S.l.x = (T)1; else if (cc == 4) S.l.y = (T)1; else S.l.z = (T)1;
                const SvT<T> F2 = mul(Ic, S);
                const SvT<T> F1 = mul(Ic, cross_motion(vb, S)) + mul(Bc, S);
                const SvT<T> F3 = mulT(Bc, S);
@@ -370,11 +394,14 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
 #pragma unroll
                for (int r = 0; r < 6; r++)
                {
-                  c.st_M((d + r) * nv + dc, f2[r]);
+                  if (r >= nd)
+                     continue;
+                  const int cr = sub == MB_SUB_SIX ? r : mb_sub_component(sub, r);
+                  c.st_M((d + r) * nv + dc, pick6(f2, cr));
                   if (r >= col)
-                     c.st_C((d + r) * nv + dc, f1[r]);
+                     c.st_C((d + r) * nv + dc, pick6(f1, cr));
                   if (r > col)
-                     c.st_C(dc * nv + d + r, g[r]);
+                     c.st_C(dc * nv + d + r, pick6(g, cr));
                }
                if (!(o.flags & MB2_ROOT_PARENT))
                   cor_walk<T>(P, c, o.body, dc, js, jc, F1, F2, F3);

@@ -30,9 +30,26 @@ template <class T, class Ctx> MB_HD RbiT<T> aux_ld_rbi(Ctx &c, int i)
 // M[dof_j .. , col] = S_j^T F and the mirrored entries (setSymmetricEntry, :704-705, :790-791)
 // PK (packed layout, MECANO_B200_CRBA_PACKED): one store per unique entry, at packed row pk (+ r for the DoFs of a SixDoF joint):
 // the mirrored entry and the structural zeros are not materialised
-template <class T, class Ctx, bool PK = false> MB_HD void crba_project(Ctx &c, int jt, int dj, int col, int pk, const SvT<T> &F)
+// sub: MB_SUB_* of a multi-DoF joint j (its DoFs are a selection of the components of F, multidof.cuh)
+template <class T, class Ctx, bool PK = false> MB_HD void crba_project(Ctx &c, int jt, int sub, int dj, int col, int pk, const SvT<T> &F)
 {
    const int nv = c.n_dofs();
+   if (jt == MB_SIXDOF && sub != MB_SUB_SIX)
+   {
+      // three-DoF joint: S^T F picks three components
+      const T e0 = sub == MB_SUB_PLANAR ? F.a.y : F.a.x, e1 = sub == MB_SUB_PLANAR ? F.l.x : F.a.y, e2 = sub == MB_SUB_PLANAR ? F.l.z : F.a.z;
+      if (PK)
+      {
+         c.st_M(pk + 0, e0); c.st_M(pk + 1, e1); c.st_M(pk + 2, e2);
+      }
+      else
+      {
+         c.st_M((dj + 0) * nv + col, e0); c.st_M(col * nv + dj + 0, e0);
+         c.st_M((dj + 1) * nv + col, e1); c.st_M(col * nv + dj + 1, e1);
+         c.st_M((dj + 2) * nv + col, e2); c.st_M(col * nv + dj + 2, e2);
+      }
+      return;
+   }
    if (PK)
    {
       if (jt == MB_REVOLUTE)
@@ -87,7 +104,7 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
          F = force_to_parent(stk_ld_xf<T>(c, w.slot), F);
       b = w.parent;
       w = P.walk[b];
-      crba_project<T, Ctx, PK>(c, w.jtype, w.dof, col, pcol + w.above, F);
+      crba_project<T, Ctx, PK>(c, w.jtype, mb_sub_of<Ctx>(w), w.dof, col, pcol + w.above, F);
       if (w.jtype != MB_SIXDOF)
          c.stk_ld2(w.slot, 0, s, cs);
    }
@@ -157,7 +174,7 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
       {
          // ---- joint transform of body i (the frame update of updateFramesRecursively())
          if (jt == MB_SIXDOF)
-            stk_st_xf<T>(c, o.slot, joint_xf_6dof<T>(c, C, o.cfg));
+            stk_st_xf<T>(c, o.slot, joint_xf_multi<T>(c, C, o.cfg, mb_sub_of<Ctx>(o)));
          else
          {
             ls = s;
@@ -199,28 +216,50 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
          }
          else
          {
+            // multi-DoF joint: one unit momentum per DoF; DoF k is component comp(k) of the spatial vector (all six for a SixDoF
+            // joint, three for a spherical / planar one, multidof.cuh)
+            const int sub = mb_sub_of<Ctx>(o), nd = mb_sub_ndof(sub);
             int pc = pcol; // packed: column `col` of this joint starts at pcol + col * above + col (col + 1) / 2
 #pragma unroll 1
-            for (int col = 0; col < 6; col++)
+            for (int col = 0; col < nd; col++)
             {
+               const int cc = mb_sub_component(sub, col);
                SvT<T> e = sv_zero<T>();
-               if (col == 0) e.a.x = 1; else if (col == 1) e.a.y = 1; else if (col == 2) e.a.z = 1;
-               else if (col == 3) e.l.x = 1; else if (col == 4) e.l.y = 1; else e.l.z = 1;
+               if (cc == 0) e.a.x = 1; else if (cc == 1) e.a.y = 1; else if (cc == 2) e.a.z = 1;
+               else if (cc == 3) e.l.x = 1; else if (cc == 4) e.l.y = 1; else e.l.z = 1;
                const SvT<T> F = mul(Ic, e);
                const int dc = d + col;
-               if (PK)
+               const T f6[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+               if (sub == MB_SUB_SIX)
                {
-                  // upper triangle of the diagonal block: rows 0 .. col of this column
-                  const T f6[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+                  if (PK)
+                  {
+                     // upper triangle of the diagonal block: rows 0 .. col of this column
 #pragma unroll
-                  for (int r = 0; r < 6; r++)
-                     if (r <= col)
-                        c.st_M(pc + above + r, f6[r]);
+                     for (int r = 0; r < 6; r++)
+                        if (r <= col)
+                           c.st_M(pc + above + r, f6[r]);
+                  }
+                  else
+                  {
+                     c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
+                     c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
+                  }
                }
                else
                {
-                  c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
-                  c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
+                  // diagonal block of a three-DoF joint: rows = the joint's own components of F
+                  const T g0 = sub == MB_SUB_PLANAR ? f6[1] : f6[0], g1 = sub == MB_SUB_PLANAR ? f6[3] : f6[1], g2 = sub == MB_SUB_PLANAR ? f6[5] : f6[2];
+                  if (PK)
+                  {
+                     c.st_M(pc + above + 0, g0);
+                     if (col >= 1) c.st_M(pc + above + 1, g1);
+                     if (col >= 2) c.st_M(pc + above + 2, g2);
+                  }
+                  else
+                  {
+                     c.st_M((d + 0) * nv + dc, g0); c.st_M((d + 1) * nv + dc, g1); c.st_M((d + 2) * nv + dc, g2);
+                  }
                }
                if (BY || !(o.flags & MB2_ROOT_PARENT))
                   crba_walk<T, Ctx, BY, PK>(P, c, o.body, dc, pc, js, jc, F);

@@ -29,6 +29,7 @@ __device__ __forceinline__ void cst_ld2(const SmemCstF C, int i2, float &a, floa
 
 template <class Ctx> struct F32Ctx
 {
+   static constexpr bool kM3 = false; // (api.cu refuses the fp32 variant for trees with three-DoF joints)
    Ctx &c;
    __device__ __forceinline__ explicit F32Ctx(Ctx &ctx) : c(ctx) {}
    // ---- inputs / outputs (fp64 in HBM)
@@ -152,6 +153,15 @@ template <class Ctx> struct F32Ctx
       a = (float)x; b = (float)y;
    }
    __device__ __forceinline__ void rec_discard(int rec2) const { c.rec_discard(rec2); }
+   __device__ __forceinline__ void rec_ld2(int i2, float &a, float &b) const
+   {
+      double x, y;
+      c.rec_ld2(i2, x, y);
+      a = (float)x; b = (float)y;
+   }
+   __device__ __forceinline__ void pf_six(int cfg, int dof, int mask) const { c.pf_six(cfg, dof, mask); }
+   __device__ __forceinline__ void pf_six_next_tile(int cfg, int dof, int mask) const { c.pf_six_next_tile(cfg, dof, mask); }
+   __device__ __forceinline__ void rec_prefetch_far(int rec2, int cfg, int dof, int mask) const { c.rec_prefetch_far(rec2, cfg, dof, mask); }
    __device__ __forceinline__ void pass_fence() const { c.pass_fence(); }
    __device__ __forceinline__ void stk_fence() const { c.stk_fence(); }
    __device__ __forceinline__ void op_sync(int k) const { c.op_sync(k); }

@@ -77,6 +77,9 @@ M3 align_z_to(const double *u)
    return r;
 }
 
+int joint_ndof(int api_type) { return api_type == MECANO_B200_SIXDOF ? 6 : (api_type >= MECANO_B200_SPHERICAL ? 3 : 1); }
+int joint_ncfg(int api_type) { return api_type == MECANO_B200_SIXDOF ? 7 : (api_type == MECANO_B200_SPHERICAL ? 4 : (api_type == MECANO_B200_PLANAR ? 3 : 1)); }
+
 int slot_size(int algo, int jtype)
 {
    const int jp = mb_jp_size(jtype);
@@ -101,7 +104,6 @@ int aux_size(int algo)
    }
 }
 
-int rec_size(int jtype) { return jtype == MB_SIXDOF ? 18 : 9; }
 
 // v2 stack slots, in double2 units (rnea.cuh / aba.cuh / crba.cuh)
 int slot2_size(int algo, int jtype, bool root_parent)
@@ -161,7 +163,7 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       const int i = MB_OP_BODY(w);
       const MbBody &B = P.body[i];
       MbOp2 &o = P.op2[k];
-      o.code = (uint8_t)((w & MB_OP_ASCEND) | ((uint32_t)B.jtype << 1));
+      o.code = (uint8_t)((w & MB_OP_ASCEND) | ((uint32_t)B.jtype << 1) | ((uint32_t)B.sub << 4));
       o.flags = (uint8_t)((w & 0xfeu) >> 1);
       o.body = (uint8_t)i;
       o.cfg = (uint16_t)B.cfg_off;
@@ -181,7 +183,8 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
       w.jtype = (uint8_t)B.jtype;
       w.flags = (uint8_t)(B.parent < 0 ? 1 : 0);
       w.parent = (uint8_t)(B.parent < 0 ? 0 : B.parent);
-      w.pad = 0;
+      w.sub = (uint16_t)B.sub;
+      w.pad2 = 0;
       w.dof = (uint16_t)B.dof_off;
       w.slot = (uint16_t)slot2[i];
       // packed layout: bodies are in depth-first order, so the parent's record is complete
@@ -316,10 +319,10 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
    for (int b = 0; b < nb; b++)
    {
       const int jt = d->joint_type[b];
-      if (jt != MECANO_B200_REVOLUTE && jt != MECANO_B200_PRISMATIC && jt != MECANO_B200_SIXDOF)
+      if (jt < MECANO_B200_REVOLUTE || jt > MECANO_B200_PLANAR)
       {
          err = "body " + std::to_string(b) + ": unsupported joint type " + std::to_string(jt)
-               + " (only RevoluteJoint, PrismaticJoint, SixDoFJoint; no CPU fallback)";
+               + " (RevoluteJoint, PrismaticJoint, SixDoFJoint, SphericalJoint, PlanarJoint; no CPU fallback)";
          return MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY;
       }
       if (d->parent[b] < -1 || d->parent[b] >= b)
@@ -327,9 +330,9 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          err = "body " + std::to_string(b) + ": parent index must satisfy -1 <= parent < body (kinematic loops are not supported)";
          return MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY;
       }
-      nv += jt == MECANO_B200_SIXDOF ? 6 : 1;
-      nq += jt == MECANO_B200_SIXDOF ? 7 : 1;
-      if (jt != MECANO_B200_SIXDOF)
+      nv += joint_ndof(jt);
+      nq += joint_ncfg(jt);
+      if (jt == MECANO_B200_REVOLUTE || jt == MECANO_B200_PRISMATIC)
       {
          const double *u = d->axis + 3 * b;
          const double n = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
@@ -368,7 +371,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
       std::vector<char> used_v(nv, 0), used_q(nq, 0);
       for (int b = 0; b < nb; b++)
       {
-         const int nd = d->joint_type[b] == MECANO_B200_SIXDOF ? 6 : 1, nc = d->joint_type[b] == MECANO_B200_SIXDOF ? 7 : 1;
+         const int nd = joint_ndof(d->joint_type[b]), nc = joint_ncfg(d->joint_type[b]);
          if (d->dof_offset[b] < 0 || d->dof_offset[b] + nd > nv || d->cfg_offset[b] < 0 || d->cfg_offset[b] + nc > nq)
          {
             err = "body " + std::to_string(b) + ": dof/cfg offset out of range";
@@ -434,7 +437,7 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
       out.max_depth = std::max(out.max_depth, depth[i] + 1);
 
       double u[3] = {0, 0, 1};
-      if (d->joint_type[b] != MECANO_B200_SIXDOF)
+      if (d->joint_type[b] == MECANO_B200_REVOLUTE || d->joint_type[b] == MECANO_B200_PRISMATIC)
       {
          const double *a = d->axis + 3 * b;
          const double n = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
@@ -516,19 +519,21 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
       P.nv = nv;
       P.nq = nq;
       P.max_depth = out.max_depth;
-      int rec = 0;
+      int rec_extra = 0; // three-DoF joints: second half of the ABA pass-three record, behind the regular records
       for (int i = 0; i < nb; i++)
       {
          MbBody &B = P.body[i];
          const int b = order[i];
          B.parent = parent_i[i];
-         B.jtype = d->joint_type[b];
+         // multi-DoF joints share the SixDoF class of the kernels (transform on the stack, rows read directly) and differ by sub-type
+         B.jtype = d->joint_type[b] >= MECANO_B200_SIXDOF ? MB_SIXDOF : d->joint_type[b];
+         B.sub = d->joint_type[b] == MECANO_B200_SPHERICAL ? MB_SUB_SPHERICAL : (d->joint_type[b] == MECANO_B200_PLANAR ? MB_SUB_PLANAR : MB_SUB_SIX);
          B.dof_off = d->dof_offset[b];
          B.cfg_off = d->cfg_offset[b];
          B.subtree_end = subtree_end[i];
          B.ext_index = d->wrench_index ? d->wrench_index[b] : b;
          B.depth = depth[i];
-         B.ndof = B.jtype == MB_SIXDOF ? 6 : 1;
+         B.ndof = joint_ndof(d->joint_type[b]);
          // stack slot: leaves keep everything in registers; others stack up along the current path
          const int pslot = parent_i[i] < 0 ? 0 : P.body[parent_i[i]].slot + (nchild[parent_i[i]] > 0 ? slot_size(algo, P.body[parent_i[i]].jtype) : 0);
          B.slot = pslot;
@@ -542,11 +547,14 @@ int flatten_tree(const mecano_b200_tree_desc *d, FlatTree &out, std::string &err
          B.aux = nchild[i] >= 2 ? paux : -1;
          if (nchild[i] >= 2)
             P.aux_doubles = std::max(P.aux_doubles, paux + aux_size(algo));
-         B.rec = rec;
-         rec += rec_size(B.jtype);
+         B.rec = -1;
+         if (B.jtype == MB_SIXDOF && B.sub != MB_SUB_SIX)
+         {
+            B.rec = (nb + rec_extra) * (MB_ABA_REC / 2);
+            rec_extra++;
+         }
       }
-      (void)rec;
-      P.rec_doubles = algo == MB_ABA ? MB_ABA_REC * nb : 0;
+      P.rec_doubles = algo == MB_ABA ? MB_ABA_REC * (nb + rec_extra) : 0;
 
       // ops: iterative DFS emitting DESCEND on entry and ASCEND on exit
       int nops = 0;

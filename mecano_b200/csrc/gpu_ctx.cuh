@@ -72,8 +72,9 @@ __device__ __forceinline__ double mb_ldg(const char *p)
 __device__ __forceinline__ void mb_stg(const char *p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ void mb_stg_cs(const char *p, double v) { asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 
-template <int BLOCK, int TM, int ROWS> struct GpuCtx2
+template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
 {
+   static constexpr bool kM3 = M3; // this instantiation handles three-DoF joints (multidof.cuh)
    const char *qb, *qdb, *xb, *fb;
    char *ob;
    unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
@@ -203,6 +204,12 @@ template <int BLOCK, int TM, int ROWS> struct GpuCtx2
    double2 *wsb;       // workspace + column of this thread
    long long ws_ld;
    __device__ __forceinline__ void rec_st2(int i2, double a, double b) { wsb[i2 * ws_ld] = make_double2(a, b); }
+   // direct read of a record slot in pass three (after pass_fence; the second half of a three-DoF joint's record, which
+   // does not travel through the ring): L2 is the coherence point of the earlier stores
+   __device__ __forceinline__ void rec_ld2(int i2, double &a, double &b) const
+   {
+      asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(wsb + i2 * ws_ld) : "memory");
+   }
    // pass-three ring: [stage][(q, qd) | rec0 .. rec2][BLOCK] double2, overlaid on the (then idle) stack area
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
    {
@@ -318,7 +325,7 @@ static_assert(MB_PARTIAL_TM_BLOCK == 640, "kCfg / tm_warp_cols assume 20 warps f
 // Skeleton of a block: TMEM allocation, context set-up, the loop over tiles of BLOCK states; `body(ctx)` evaluates one
 // state.  ncst = doubles of constant records staged at the front of shared memory (0 for specialised kernels),
 // stack2 = stack slots (double2) per state.
-template <int ALGO, bool STATE_MAJOR, int BLOCK, int AUXN, int TM, class Body>
+template <int ALGO, bool STATE_MAJOR, int BLOCK, int AUXN, int TM, bool M3 = false, class Body>
 __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int ncst, const int smem_slots, const int nstack2, Body body)
 {
    static_assert(TM * 4 <= tm_warp_cols(BLOCK), "TMEM stack slots exceed the columns of one warp");
@@ -338,7 +345,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    if (TM > 0)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
    double aux[AUXN > 0 ? AUXN : 1];
-   GpuCtx2<BLOCK, TM, ring_rows(ALGO)> c2;
+   GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3> c2;
    c2.ld8 = (unsigned)(a.ld * 8);
    c2.ld8d = (unsigned)(a.ld_qd * 8);
    c2.ld8x = (unsigned)(a.ld_x * 8);
@@ -375,7 +382,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
    {
       long long s = tile * BLOCK + threadIdx.x;
-      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO)>::kClamp)
+      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kClamp)
       {
          // tcgen05.ld/st are warp-collective (.sync.aligned): padding lanes run a clamped state and store nothing
          c2.active = s < a.n;

@@ -95,6 +95,10 @@ static int add_joint(mecano_model *m, int type, const char *name, int pred, cons
          j = m->arena.newJoint<FixedJoint>(n, m->bodies[pred], T);
       else if (type == MECANO_B200_SIXDOF)
          j = m->arena.newJoint<SixDoFJoint>(n, m->bodies[pred], T);
+      else if (type == MECANO_B200_SPHERICAL)
+         j = m->arena.newJoint<SphericalJoint>(n, m->bodies[pred], T);
+      else if (type == MECANO_B200_PLANAR)
+         j = m->arena.newJoint<PlanarJoint>(n, m->bodies[pred], T);
       else
       {
          if (!axis3) return fail(m, "axis is NULL");
@@ -121,6 +125,15 @@ int mecano_model_add_prismatic_joint(mecano_model *m, const char *name, int pred
 int mecano_model_add_sixdof_joint(mecano_model *m, const char *name, int pred, const double *t12)
 {
    return add_joint(m, MECANO_B200_SIXDOF, name, pred, t12, nullptr);
+}
+
+int mecano_model_add_spherical_joint(mecano_model *m, const char *name, int pred, const double *t12)
+{
+   return add_joint(m, MECANO_B200_SPHERICAL, name, pred, t12, nullptr);
+}
+int mecano_model_add_planar_joint(mecano_model *m, const char *name, int pred, const double *t12)
+{
+   return add_joint(m, MECANO_B200_PLANAR, name, pred, t12, nullptr);
 }
 
 int mecano_model_add_fixed_joint(mecano_model *m, const char *name, int pred, const double *t12)
@@ -169,6 +182,28 @@ int mecano_model_next_one_dof_joint_tree(mecano_model *m, uint64_t seed, int pre
       if (pred < 0 || pred >= (int)m->bodies.size() || !m->bodies[pred]) return fail(m, "predecessor body id out of range");
       Random r(seed);
       MultiBodySystemRandomTools::nextOneDoFJointTree(r, m->arena, "tree" + std::to_string(m->joints.size()), m->bodies[pred], n, prismatic_fraction);
+      register_subtree(m, m->bodies[0]);
+      return (int)m->bodies.size() - 1;
+   });
+}
+
+int mecano_model_next_joint_chain(mecano_model *m, uint64_t seed, int pred, int n)
+{
+   return guarded(m, [&]() -> int {
+      if (pred < 0 || pred >= (int)m->bodies.size() || !m->bodies[pred]) return fail(m, "predecessor body id out of range");
+      Random r(seed);
+      MultiBodySystemRandomTools::nextJointChain(r, m->arena, "chain" + std::to_string(m->joints.size()), m->bodies[pred], n);
+      register_subtree(m, m->bodies[0]);
+      return (int)m->bodies.size() - 1;
+   });
+}
+
+int mecano_model_next_joint_tree(mecano_model *m, uint64_t seed, int pred, int n)
+{
+   return guarded(m, [&]() -> int {
+      if (pred < 0 || pred >= (int)m->bodies.size() || !m->bodies[pred]) return fail(m, "predecessor body id out of range");
+      Random r(seed);
+      MultiBodySystemRandomTools::nextJointTree(r, m->arena, "tree" + std::to_string(m->joints.size()), m->bodies[pred], n);
       register_subtree(m, m->bodies[0]);
       return (int)m->bodies.size() - 1;
    });

@@ -1,5 +1,5 @@
 // multibody.hpp -- host-side mirror (C++) of the part of Mecano's model API that the hot path needs:
-// RigidBody, RevoluteJoint, PrismaticJoint, SixDoFJoint, MultiBodySystem + JointMatrixIndexProvider, the
+// RigidBody, RevoluteJoint, PrismaticJoint, SixDoFJoint, SphericalJoint, PlanarJoint, FixedJoint, MultiBodySystem + JointMatrixIndexProvider, the
 // flattener producing the level-ordered tables of include/mecano_b200.h, and the synthetic generators of
 // MultiBodySystemRandomTools.  ("M/" = /root/reference/src/main/java/us/ihmc/mecano/)
 //
@@ -7,6 +7,8 @@
 //   RevoluteJoint      M/multiBodySystem/RevoluteJoint.java:42-74
 //   PrismaticJoint     M/multiBodySystem/PrismaticJoint.java:34-51
 //   SixDoFJoint        M/multiBodySystem/SixDoFJoint.java:52-70
+//   SphericalJoint     M/multiBodySystem/SphericalJoint.java:43-69, interfaces/SphericalJointReadOnly.java:31-71
+//   PlanarJoint        M/multiBodySystem/PlanarJoint.java:37-61, interfaces/PlanarJointReadOnly.java:20-58
 //   MultiBodySystem    M/multiBodySystem/interfaces/MultiBodySystemBasics.java:76-142, MultiBodySystemReadOnly.java:167-205
 //   index provider     M/multiBodySystem/interfaces/JointMatrixIndexProvider.java:71-123
 //   joint order        M/multiBodySystem/iterators/JointIterator.java:130-177 (depth-first pre-order, children in insertion order)
@@ -60,7 +62,11 @@ class RigidBody;
 
 // Fixed joints (M/multiBodySystem/FixedJoint.java) exist on the host only: the flattener welds their successor into the
 // nearest moving ancestor, so the kernels never see them.
-enum class JointType { Revolute = MECANO_B200_REVOLUTE, Prismatic = MECANO_B200_PRISMATIC, SixDoF = MECANO_B200_SIXDOF, Fixed = 3 };
+enum class JointType
+{
+   Revolute = MECANO_B200_REVOLUTE, Prismatic = MECANO_B200_PRISMATIC, SixDoF = MECANO_B200_SIXDOF, Spherical = MECANO_B200_SPHERICAL,
+   Planar = MECANO_B200_PLANAR, Fixed = 5
+};
 
 // ---- small rigid-transform / inertia algebra used when bodies are welded together at flatten time
 inline Matrix3D matmul(const Matrix3D &A, const Matrix3D &B)
@@ -109,7 +115,8 @@ class Joint
    void setSuccessor(RigidBody *successor) { successor_ = successor; }
    // The configuration a joint has when it is ignored (MultiBodySystemBasics.toMultiBodySystemBasics(root, jointsToIgnore)):
    // Mecano lumps the inertia of an ignored subtree into its parent body at the configuration the joints have when the
-   // calculator is built (InverseDynamicsCalculator.java:236, :832-860).  One-DoF: q; SixDoF: qx qy qz qs x y z.  Default: zero.
+   // calculator is built (InverseDynamicsCalculator.java:236, :832-860).  One-DoF: q; SixDoF: qx qy qz qs x y z; Spherical: qx qy qz qs;
+   // Planar: pitch x z.  Default: zero / identity.
    void setJointConfiguration(const double *q, int n) { q_.assign(q, q + n); }
    const std::vector<double> &getJointConfiguration() const { return q_; }
    // frameAfterJoint in frameBeforeJoint at the stored configuration (MecanoFactories.java:231-260,
@@ -130,7 +137,15 @@ class Joint
          const double q = q_.empty() ? 0.0 : q_[0];
          X.translation = Vector3D{q * axis_.x, q * axis_.y, q * axis_.z};
       }
-      else if (type_ == JointType::SixDoF && q_.size() == 7)
+      else if (type_ == JointType::Planar && q_.size() == 3)
+      {
+         // PlanarJointReadOnly.java:40-48: rotation about y by the pitch, translation in the x-z plane
+         const double c = std::cos(q_[0]), s = std::sin(q_[0]);
+         const double R[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
+         for (int i = 0; i < 9; i++) X.rotation.m[i] = R[i];
+         X.translation = Vector3D{q_[1], 0.0, q_[2]};
+      }
+      else if ((type_ == JointType::SixDoF && q_.size() == 7) || (type_ == JointType::Spherical && q_.size() == 4))
       {
          double qx = q_[0], qy = q_[1], qz = q_[2], qs = q_[3];
          const double n = std::sqrt(qx * qx + qy * qy + qz * qz + qs * qs);
@@ -142,7 +157,8 @@ class Joint
                                  1 - 2 * (qx * qx + qy * qy)};
             for (int i = 0; i < 9; i++) X.rotation.m[i] = R[i];
          }
-         X.translation = Vector3D{q_[4], q_[5], q_[6]};
+         if (type_ == JointType::SixDoF)
+            X.translation = Vector3D{q_[4], q_[5], q_[6]};
       }
       return X;
    }
@@ -254,6 +270,31 @@ class SixDoFJoint : public Joint
        : Joint(std::move(name), predecessor, &transformToParent, JointType::SixDoF) {}
    int getDegreesOfFreedom() const override { return 6; }
    int getConfigurationMatrixSize() const override { return 7; }
+};
+
+// SphericalJoint (M/multiBodySystem/SphericalJoint.java:43-69): 3 DoF, configuration = orientation quaternion (qx qy qz qs),
+// velocity-like rows = angular part in frameAfterJoint (SphericalJointReadOnly.java:31-71)
+class SphericalJoint : public Joint
+{
+ public:
+   SphericalJoint(std::string name, RigidBody *predecessor) : Joint(std::move(name), predecessor, nullptr, JointType::Spherical) {}
+   SphericalJoint(std::string name, RigidBody *predecessor, const Vector3D &jointOffset) : SphericalJoint(std::move(name), predecessor, RigidBodyTransform(jointOffset)) {}
+   SphericalJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform &transformToParent)
+       : Joint(std::move(name), predecessor, &transformToParent, JointType::Spherical) {}
+   int getDegreesOfFreedom() const override { return 3; }
+   int getConfigurationMatrixSize() const override { return 4; }
+};
+
+// PlanarJoint (M/multiBodySystem/PlanarJoint.java:37-61): 3 DoF in the x-z plane of frameBeforeJoint, configuration (pitch, x, z),
+// velocity-like rows (w_y, v_x, v_z) in frameAfterJoint (PlanarJointReadOnly.java:20-58)
+class PlanarJoint : public Joint
+{
+ public:
+   PlanarJoint(std::string name, RigidBody *predecessor) : Joint(std::move(name), predecessor, nullptr, JointType::Planar) {}
+   PlanarJoint(std::string name, RigidBody *predecessor, const RigidBodyTransform &transformToParent)
+       : Joint(std::move(name), predecessor, &transformToParent, JointType::Planar) {}
+   int getDegreesOfFreedom() const override { return 3; }
+   int getConfigurationMatrixSize() const override { return 3; }
 };
 
 // FixedJoint (M/multiBodySystem/FixedJoint.java:40-62): 0 DoF, welds its successor to its predecessor
@@ -615,6 +656,40 @@ inline Joint *nextOneDoFJoint(Random &r, MultiBodyArena &a, const std::string &n
    const RigidBodyTransform T = nextRigidBodyTransform(r);
    if (prismatic) return a.newJoint<PrismaticJoint>(name, predecessor, T, axis);
    return a.newJoint<RevoluteJoint>(name, predecessor, T, axis);
+}
+// nextJoint (:1116-1136 style): a joint of a random type among all the moving joint types
+inline Joint *nextJoint(Random &r, MultiBodyArena &a, const std::string &name, RigidBody *predecessor)
+{
+   const int kind = r.nextInt(5);
+   if (kind < 2)
+      return nextOneDoFJoint(r, a, name, predecessor, kind == 1);
+   const RigidBodyTransform T = predecessor->isRootBody() ? RigidBodyTransform() : nextRigidBodyTransform(r);
+   if (kind == 2) return a.newJoint<SixDoFJoint>(name, predecessor, T);
+   if (kind == 3) return a.newJoint<SphericalJoint>(name, predecessor, T);
+   return a.newJoint<PlanarJoint>(name, predecessor, T);
+}
+// nextJointChain (:424-440): a chain of joints of random types
+inline RigidBody *nextJointChain(Random &r, MultiBodyArena &a, const std::string &prefix, RigidBody *root, int n)
+{
+   RigidBody *pred = root;
+   for (int i = 0; i < n; i++)
+   {
+      Joint *j = nextJoint(r, a, prefix + "Joint" + std::to_string(i), pred);
+      pred = nextRigidBody(r, a, prefix + "Body" + std::to_string(i), j);
+   }
+   return pred;
+}
+// nextJointTree (:844-860): a tree of joints of random types
+inline void nextJointTree(Random &r, MultiBodyArena &a, const std::string &prefix, RigidBody *root, int n)
+{
+   std::vector<RigidBody *> successors;
+   RigidBody *pred = root;
+   for (int i = 0; i < n; i++)
+   {
+      Joint *j = nextJoint(r, a, prefix + "Joint" + std::to_string(i), pred);
+      successors.push_back(nextRigidBody(r, a, prefix + "Body" + std::to_string(i), j));
+      pred = successors[(size_t)r.nextInt((int)successors.size())];
+   }
 }
 // nextRevoluteJointChain / nextOneDoFJointChain, :483-496
 inline RigidBody *nextOneDoFJointChain(Random &r, MultiBodyArena &a, const std::string &prefix, RigidBody *root, int n, double prismaticFraction = 0.0)

@@ -89,6 +89,43 @@ __device__ __forceinline__ void sixdof_update(double dt, double hdt2, double *q7
    a6[5] = mz + (fvx * fwy - fvy * fwx);
 }
 
+// SphericalJoint (:449-452, :575-594): orientation = orientation * exp(dt w + 0.5 dt^2 wd), w += dt wd
+__device__ __forceinline__ void spherical_update(double dt, double hdt2, double *q4, double *w3, const double *a3)
+{
+   double ix, iy, iz, is;
+   quat_from_rv(dt * w3[0] + hdt2 * a3[0], dt * w3[1] + hdt2 * a3[1], dt * w3[2] + hdt2 * a3[2], ix, iy, iz, is);
+   const double ox = q4[0], oy = q4[1], oz = q4[2], os = q4[3];
+   q4[0] = os * ix + ox * is + oy * iz - oz * iy;
+   q4[1] = os * iy - ox * iz + oy * is + oz * ix;
+   q4[2] = os * iz + ox * iy - oy * ix + oz * is;
+   q4[3] = os * is - ox * ix - oy * iy - oz * iz;
+   w3[0] = fma(dt, a3[0], w3[0]); w3[1] = fma(dt, a3[1], w3[1]); w3[2] = fma(dt, a3[2], w3[2]);
+}
+
+// PlanarJoint: a FloatingJointBasics (PlanarJointBasics.java:17), so :421-424 runs the floating-joint update :503-560 on its planar
+// pose / twist / acceleration.  Everything stays in the x-z plane: the rotation vector is along y and the pitch-only orientation
+// composes additively.  q3 = (pitch, x, z), v3 / a3 = (w_y, v_x, v_z) in the body frame; a3's linear rows are updated like SixDoF's.
+__device__ __forceinline__ void planar_update(double dt, double hdt2, double *q3, double *v3, double *a3)
+{
+   const double th0 = q3[0], wy = v3[0], vx = v3[1], vz = v3[2], wdy = a3[0];
+   const double lx = a3[1] + wy * vz, lz = a3[2] - wy * vx; // origin acceleration a + w x v
+   const double dth = dt * wy + hdt2 * wdy;
+   double s0, c0, si, ci;
+   sincos(th0, &s0, &c0);
+   sincos(dth, &si, &ci);
+   const double tx = dt * vx + hdt2 * lx, tz = dt * vz + hdt2 * lz;
+   q3[1] += c0 * tx + s0 * tz; // R_y(th) (x, 0, z) = (c x + s z, 0, -s x + c z)
+   q3[2] += -s0 * tx + c0 * tz;
+   q3[0] = th0 + dth;
+   const double ux = dt * lx + vx, uz = dt * lz + vz;
+   const double vfx = ci * ux - si * uz, vfz = si * ux + ci * uz; // R_y(dth)^T
+   const double wf = dt * wdy + wy;
+   const double l2x = ci * lx - si * lz, l2z = si * lx + ci * lz;
+   v3[0] = wf; v3[1] = vfx; v3[2] = vfz;
+   a3[1] = l2x - vfz * wf; // a_origin' + v' x w'
+   a3[2] = l2z + vfx * wf;
+}
+
 template <bool VEC2> __global__ void __launch_bounds__(256) integrate_kernel(const __grid_constant__ IntegrateJoints J, const IntegrateArgs a)
 {
    const int j = blockIdx.y;
@@ -117,6 +154,29 @@ template <bool VEC2> __global__ void __launch_bounds__(256) integrate_kernel(con
       else
          for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
             onedof_update(dt, hdt2, q[i], v[i], acc[i]);
+      return;
+   }
+   if (J.sub[j] != MB_SUB_SIX)
+   {
+      const bool planar = J.sub[j] == MB_SUB_PLANAR;
+      const int nc = planar ? 3 : 4;
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)
+      {
+         double q4[4], v3[3], a3[3];
+         for (int k = 0; k < nc; k++) q4[k] = a.q[(long long)(cfg + k) * a.ld + i];
+#pragma unroll
+         for (int k = 0; k < 3; k++) { v3[k] = a.qd[(long long)(dof + k) * a.ld + i]; a3[k] = a.qdd[(long long)(dof + k) * a.ld + i]; }
+         if (planar) planar_update(dt, hdt2, q4, v3, a3);
+         else spherical_update(dt, hdt2, q4, v3, a3);
+         for (int k = 0; k < nc; k++) a.q[(long long)(cfg + k) * a.ld + i] = q4[k];
+#pragma unroll
+         for (int k = 0; k < 3; k++) a.qd[(long long)(dof + k) * a.ld + i] = v3[k];
+         if (planar)
+         {
+            a.qdd[(long long)(dof + 1) * a.ld + i] = a3[1];
+            a.qdd[(long long)(dof + 2) * a.ld + i] = a3[2];
+         }
+      }
       return;
    }
    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride)

@@ -368,3 +368,5 @@ template <class T, class Ctx, class CP> MB_HD SvT<T> external_wrench(Ctx &c, int
    return r;
 }
 } // namespace mb
+
+#include "multidof.cuh"

@@ -18,111 +18,30 @@
 #include <cstring>
 #include <type_traits>
 
-#include "f32_ctx.cuh"
-#include "gpu_ctx.cuh"
-#include "kernels.h"
+#include "thread_kernels.cuh"
 
 namespace mb
 {
+// instantiated in kern_inst.cu
+#define MB_X(G, ALGO, FEXT, LAYOUT, M3) extern template KernelFn pick_cfg<ALGO, FEXT, LAYOUT, M3>(int);
+MB_KERNEL_GROUPS(MB_X)
+#undef MB_X
 namespace
 {
-// LAYOUT (CRBA): 0 entry-major, 1 state-major, 2 packed (unique non-zero entries, entry-major rows)
-template <int ALGO, bool FEXT, int LAYOUT, int BLOCK, int AUXN, int RECN, int TM>
-__global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
-{
-   constexpr bool STATE_MAJOR = LAYOUT == 1;
-   const int ncst = P.nb * MB_CONST_STRIDE;
-   for (int i = threadIdx.x; i < ncst; i += BLOCK)
-      mb_smem[i] = a.consts[i];
-   using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
-   thread_block_run<ALGO, STATE_MAJOR, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), P.nstack2, [&](Ctx &c2) {
-      if constexpr (ALGO == MB_RNEA)
-         rnea_state<double, Ctx, FEXT>(P, c2, a.grav);
-      else if constexpr (ALGO == MB_ABA)
-         aba_state<double, Ctx, FEXT>(P, c2, a.grav);
-      else if constexpr (ALGO == MB_CRBA)
-         crba_state<double, Ctx, FEXT, LAYOUT == 2>(P, c2);
-      else
-         coriolis_state<double, Ctx>(P, c2);
-   });
-}
-
-// The optional fp32 variant (f32_ctx.cuh): same skeleton, constant records staged as floats, the per-state routines instantiated
-// with T = float.  Plain calls only (no external wrenches / by-products), one launch configuration per algorithm.
-template <int ALGO, int BLOCK, int AUXN, int RECN, int TM>
-__global__ void __launch_bounds__(BLOCK) thread_kernel_f32(const __grid_constant__ MbProgram P, const KernelArgs a)
-{
-   const int ncst = P.nb * MB_CONST_STRIDE;
-   float *cf = reinterpret_cast<float *>(mb_smem);
-   for (int i = threadIdx.x; i < ncst; i += BLOCK)
-      cf[i] = (float)a.consts[i];
-   using Ctx = GpuCtx2<BLOCK, TM, ring_rows(ALGO)>;
-   const float grav[3] = {(float)a.grav[0], (float)a.grav[1], (float)a.grav[2]};
-   thread_block_run<ALGO, false, BLOCK, AUXN, TM>(a, ncst, mb_smem_stack_slots(ALGO, P, TM), P.nstack2, [&](Ctx &c2) {
-      F32Ctx<Ctx> f(c2);
-      if constexpr (ALGO == MB_RNEA)
-         rnea_state<float, F32Ctx<Ctx>, false>(P, f, grav);
-      else if constexpr (ALGO == MB_ABA)
-         aba_state<float, F32Ctx<Ctx>, false>(P, f, grav);
-      else
-         crba_state<float, F32Ctx<Ctx>, false>(P, f);
-   });
-}
-
-// compiled work-area classes (local memory per thread): {aux, rec}
-//   class 0: up to 4 nested branching bodies, 32 one-DoF-equivalent records (humanoids); blocks of 256 / 128
-//   class 1: up to 16 nested branching bodies, 128 bodies; blocks of 128 / 64 / 32 (deeper stacks)
-constexpr int kRnaAux0 = 12 * 4, kRnaAux1 = 12 * 16;
-constexpr int kAbaAux0 = 27 * 4, kAbaAux1 = 27 * 16;
-constexpr int kCrbAux0 = 10 * 4, kCrbAux1 = 10 * 16;
-constexpr int kCorAux0 = 46 * 4, kCorAux1 = 46 * 16;
-constexpr int kAbaRec0 = MB_ABA_REC * 33, kAbaRec1 = MB_ABA_REC * 128;
-// launch configurations: threads per block, work-area class, stack slots (double2) held in tensor memory
-struct Cfg
-{
-   int block, cls, tm;
-};
-constexpr int kNumCfg = 15;
-constexpr Cfg kCfg[kNumCfg] = {{512, 0, 32}, {384, 0, 42}, {320, 0, 42}, {256, 0, 64}, {384, 0, 0}, {320, 0, 0}, {256, 0, 0},
-                               {192, 0, 0},  {128, 0, 0},  {256, 1, 64}, {128, 1, 128}, {128, 1, 0}, {64, 1, 0},  {32, 1, 0},
-                               {640, 0, 24}};
-
-typedef void (*KernelFn)(const MbProgram, const KernelArgs);
-
-template <int ALGO, bool FEXT, int SM> KernelFn pick_cfg(int cfg)
-{
-   constexpr int a0 = ALGO == MB_RNEA ? kRnaAux0 : (ALGO == MB_ABA ? kAbaAux0 : (ALGO == MB_CRBA ? kCrbAux0 : kCorAux0));
-   constexpr int a1 = ALGO == MB_RNEA ? kRnaAux1 : (ALGO == MB_ABA ? kAbaAux1 : (ALGO == MB_CRBA ? kCrbAux1 : kCorAux1));
-   constexpr int r0 = ALGO == MB_ABA ? kAbaRec0 : 0, r1 = ALGO == MB_ABA ? kAbaRec1 : 0;
-   switch (cfg)
-   {
-      // CRBA has no wide stack area: its TMEM configurations are never planned (mb_tm_fits) and alias the shared-memory kernels
-#define MB_CFG_CASE(i) case i: return thread_kernel<ALGO, FEXT, SM, kCfg[i].block, kCfg[i].cls ? a1 : a0, kCfg[i].cls ? r1 : r0, (ALGO == MB_CRBA || ALGO == MB_CORIOLIS) ? 0 : kCfg[i].tm>;
-      MB_CFG_CASE(0) MB_CFG_CASE(1) MB_CFG_CASE(2) MB_CFG_CASE(3) MB_CFG_CASE(4) MB_CFG_CASE(5) MB_CFG_CASE(6)
-      MB_CFG_CASE(7) MB_CFG_CASE(8) MB_CFG_CASE(9) MB_CFG_CASE(10) MB_CFG_CASE(11) MB_CFG_CASE(12) MB_CFG_CASE(14)
-#undef MB_CFG_CASE
-      default: return thread_kernel<ALGO, FEXT, SM, kCfg[13].block, a1, r1, (ALGO == MB_CRBA || ALGO == MB_CORIOLIS) ? 0 : kCfg[13].tm>;
-   }
-}
-
 // layout: 0 entry-major, 1 state-major, 2 packed (CRBA only)
-KernelFn pick(int algo, bool fext, int layout, int cfg)
+// m3: the tree has three-DoF joints (MbProgram::has_3dof)
+KernelFn pick(int algo, bool fext, int layout, int cfg, bool m3)
 {
-   if (algo == MB_RNEA) return fext ? pick_cfg<MB_RNEA, true, 0>(cfg) : pick_cfg<MB_RNEA, false, 0>(cfg);
-   if (algo == MB_ABA) return fext ? pick_cfg<MB_ABA, true, 0>(cfg) : pick_cfg<MB_ABA, false, 0>(cfg);
-   if (algo == MB_CORIOLIS) return pick_cfg<MB_CORIOLIS, false, 0>(cfg);
+   if (algo == MB_RNEA)
+      return m3 ? (fext ? pick_cfg<MB_RNEA, true, 0, true>(cfg) : pick_cfg<MB_RNEA, false, 0, true>(cfg))
+                : (fext ? pick_cfg<MB_RNEA, true, 0, false>(cfg) : pick_cfg<MB_RNEA, false, 0, false>(cfg));
+   if (algo == MB_ABA)
+      return m3 ? (fext ? pick_cfg<MB_ABA, true, 0, true>(cfg) : pick_cfg<MB_ABA, false, 0, true>(cfg))
+                : (fext ? pick_cfg<MB_ABA, true, 0, false>(cfg) : pick_cfg<MB_ABA, false, 0, false>(cfg));
+   if (algo == MB_CORIOLIS) return pick_cfg<MB_CORIOLIS, false, 0, true>(cfg);
    // CRBA: the "FEXT" instantiation is the one with by-products (centroidal momentum matrix, centre of mass), entry-major only
-   if (fext && layout == 0) return pick_cfg<MB_CRBA, true, 0>(cfg);
-   return layout == 1 ? pick_cfg<MB_CRBA, false, 1>(cfg) : (layout == 2 ? pick_cfg<MB_CRBA, false, 2>(cfg) : pick_cfg<MB_CRBA, false, 0>(cfg));
-}
-
-// fp32 variant: the one configuration per algorithm that the planner picks for humanoid-sized trees (kCfg index, class 0)
-constexpr int kF32Cfg[3] = {0, 1, 8}; // RNEA 512 threads + TMEM, ABA 384 threads + TMEM, CRBA 128 threads
-KernelFn pick_f32(int algo)
-{
-   if (algo == MB_RNEA) return thread_kernel_f32<MB_RNEA, kCfg[kF32Cfg[0]].block, kRnaAux0, 0, kCfg[kF32Cfg[0]].tm>;
-   if (algo == MB_ABA) return thread_kernel_f32<MB_ABA, kCfg[kF32Cfg[1]].block, kAbaAux0, kAbaRec0, kCfg[kF32Cfg[1]].tm>;
-   return thread_kernel_f32<MB_CRBA, kCfg[kF32Cfg[2]].block, kCrbAux0, 0, 0>;
+   if (fext && layout == 0) return pick_cfg<MB_CRBA, true, 0, true>(cfg);
+   return layout == 1 ? pick_cfg<MB_CRBA, false, 1, true>(cfg) : (layout == 2 ? pick_cfg<MB_CRBA, false, 2, true>(cfg) : pick_cfg<MB_CRBA, false, 0, true>(cfg));
 }
 
 int class_of(int algo, const MbProgram &P)
@@ -160,6 +79,10 @@ int forced_cfg(int algo)
 cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPlan &plan, bool *fits)
 {
    *fits = false;
+   bool m3 = false;
+   for (int i = 0; i < P.nb; i++)
+      m3 = m3 || P.body[i].sub != MB_SUB_SIX;
+   plan.m3 = m3;
    const int cls = class_of(algo, P);
    if (cls < 0)
       return cudaSuccess;
@@ -189,7 +112,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       if (sm > (size_t)max_optin)
          continue;
       // every variant of this configuration gets the opt-in so that later launches cannot fail on it
-      KernelFn fn = pick(algo, fext, 0, cfg);
+      KernelFn fn = pick(algo, fext, 0, cfg, m3);
       cudaFuncAttributes fa;
       e = cudaFuncGetAttributes(&fa, (const void *)fn);
       if (e != cudaSuccess) return e;
@@ -199,7 +122,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
       for (int f = 0; f < 2; f++)
          for (int st = 0; st < 3; st++)
          {
-            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
+            e = cudaFuncSetAttribute((const void *)pick(algo, f != 0, st, cfg, m3), cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
             if (e != cudaSuccess) return e;
          }
       int nblk = 0;
@@ -237,7 +160,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    if (best_threads == 0)
       return cudaSuccess; // the stack of even a 32-state block does not fit in shared memory
    cudaFuncAttributes attr;
-   e = cudaFuncGetAttributes(&attr, (const void *)pick(algo, fext, 0, plan.size_class));
+   e = cudaFuncGetAttributes(&attr, (const void *)pick(algo, fext, 0, plan.size_class, m3));
    if (e != cudaSuccess) return e;
    int sms = 0;
    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -247,7 +170,7 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
    plan.local_bytes = (int)attr.localSizeBytes;
    plan.static_smem = (int)attr.sharedSizeBytes;
    // the fp32 variant exists for the configuration the planner picks for humanoid-sized trees
-   plan.fp32_ok = algo <= MB_CRBA && plan.size_class == kF32Cfg[algo];
+   plan.fp32_ok = algo <= MB_CRBA && plan.size_class == kF32Cfg[algo] && !m3;
    if (plan.fp32_ok)
    {
       cudaFuncAttributes fa32;
@@ -276,7 +199,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
       pick_f32(algo)<<<g, plan.block, plan.smem, stream>>>(P, b);
       return cudaGetLastError();
    }
-   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, layout, plan.size_class);
+   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, layout, plan.size_class, plan.m3);
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so
    // does every kernel with a TMEM stack: a block then allocates its tensor memory, stages the constant records and

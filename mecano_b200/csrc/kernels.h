@@ -24,6 +24,7 @@ struct LaunchPlan
    size_t ws_doubles = 0; // ABA workspace size for that grid
    bool fp32_ok = false;  // the optional fp32 variant exists for this configuration
    int fp32_regs = 0;
+   bool m3 = false;       // the tree has three-DoF joints: the kernels instantiated with them (thread_kernels.cuh)
 };
 
 // Picks the block size / size class for one algorithm and opts the kernel into large shared memory.
@@ -43,6 +44,7 @@ struct IntegrateJoints
    int32_t nb;
    uint16_t cfg[MB_MAX_BODIES], dof[MB_MAX_BODIES]; // Mecano configuration / DoF row of each joint
    uint8_t type[MB_MAX_BODIES];                     // MB_REVOLUTE / MB_PRISMATIC / MB_SIXDOF
+   uint8_t sub[MB_MAX_BODIES];                      // MB_SUB_* of a multi-DoF joint
 };
 struct IntegrateArgs
 {

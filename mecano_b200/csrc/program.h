@@ -30,7 +30,11 @@ typedef long long int64_t;
 // joint types (after canonicalisation the 1-DoF axis is always +z)
 #define MB_REVOLUTE 0
 #define MB_PRISMATIC 1
-#define MB_SIXDOF 2
+#define MB_SIXDOF 2 // also the class of the other multi-DoF joints, told apart by their sub-type:
+// sub-type of a multi-DoF joint: which components of the 6-vector [wx wy wz vx vy vz] in frameAfterJoint are its DoFs
+#define MB_SUB_SIX 0       // SixDoFJoint: all six; configuration [qx qy qz qs x y z]
+#define MB_SUB_SPHERICAL 1 // SphericalJoint: (wx wy wz); configuration [qx qy qz qs]
+#define MB_SUB_PLANAR 2    // PlanarJoint: (wy vx vz); configuration [pitch x z]
 
 // per-body constant record, in doubles
 #define MB_C_R 0    // [9] row-major rotation of the joint's zero-configuration frame in the parent frame
@@ -62,18 +66,19 @@ struct MbBody
    int32_t cfg_off;     // Mecano configuration row
    int32_t slot;        // base of this body's stack slot (doubles), shared-memory stack
    int32_t aux;         // base of this body's branch save area (doubles), local memory; -1 if none
-   int32_t rec;         // base of this body's pass-three record (ABA), local memory
+   int32_t rec;         // three-DoF joints: where the second half of the ABA pass-three record lives (double2 units), else -1
    int32_t subtree_end; // one past the last internal index of this body's subtree
    int32_t ext_index;   // index of this body in the caller's tree description (external wrench rows)
    int32_t depth;
    int32_t ndof;
-   int32_t pad;
+   int32_t sub;         // MB_SUB_* of a multi-DoF joint (jtype == MB_SIXDOF), else 0
 };
 
 // Pre-decoded traversal record (28 bytes): everything an op needs, so that the kernels never
 // chase MbBody fields.  Stack offsets are in double2 units (the shared-memory stack is an array of double2,
 // state-minor), save-area offsets in doubles.
-//   code: bit0 ASCEND, bits1-2 joint type, bit3 SC (this op also evaluates sin/cos for the next 1-DoF DESCEND)
+//   code: bit0 ASCEND, bits1-2 joint type, bit3 SC (this op also evaluates sin/cos for the next 1-DoF DESCEND),
+//         bits4-5 sub-type of a multi-DoF joint (MB_SUB_*)
 struct MbOp2
 {
    uint8_t code;
@@ -96,6 +101,7 @@ struct MbOp2
 #define MB2_PF_A1 0x4u    // op k + MB_PF_DIST is a 1-DoF ASCEND
 #define MB2_ASCEND 0x1u
 #define MB2_JT(code) (((code) >> 1) & 3u)
+#define MB2_SUB(code) (((code) >> 4) & 3u)
 #define MB2_SC 0x8u
 #define MB2_LEAF 0x1u
 #define MB2_LOAD_PARENT 0x2u
@@ -117,7 +123,7 @@ struct MbWalk
    uint16_t slot;  // stack slot (double2 units)
    uint16_t pcol;  // packed mass-matrix layout: first packed row of the column of this joint's first DoF; the column of its
                    // r-th DoF starts at pcol + r * above + r (r + 1) / 2 and holds above + r + 1 entries
-   uint16_t pad;
+   uint16_t sub;   // MB_SUB_* of a multi-DoF joint
    uint32_t pad2;
 };
 
@@ -156,6 +162,10 @@ struct MbProgram
 __host__ __device__
 #endif
 static inline int mb_jp_size(int jtype) { return jtype == MB_REVOLUTE ? 2 : (jtype == MB_PRISMATIC ? 1 : 12); }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int mb_sub_ndof(int sub) { return sub == MB_SUB_SIX ? 6 : 3; }
 
 // ABA pass-three record of one body, in doubles (three double2).  One-DoF joint: g = U / D without its component along the joint
 // axis (which is D / D = 1) and k0 = u / D: revolute (g.ax, g.ay, g.lx, g.ly, g.lz, k0), prismatic (g.ax, g.ay, g.az, g.lx, g.ly, k0).

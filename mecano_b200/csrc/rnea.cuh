@@ -109,13 +109,15 @@ MB_HD void rnea_ascend_1dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &f, RneaPipe<
    }
 }
 
+// multi-DoF joints (SixDoF, Spherical, Planar; sub-type in the op code, multidof.cuh): S is a selection of components
 template <class T, class Ctx, bool FEXT>
 MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &a, SvT<T> &f)
 {
    const auto C = c.cst(o.body);
-   const XfT<T> X = joint_xf_6dof<T>(c, C, o.cfg);
-   const SvT<T> vj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_qd(r); });
-   const SvT<T> aj = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
+   const int sub = mb_sub_of<Ctx>(o);
+   const XfT<T> X = joint_xf_multi<T>(c, C, o.cfg, sub);
+   const SvT<T> vj = ld_svj<T>(o.dof, sub, [&](int r) { return c.ld_qd(r); });
+   const SvT<T> aj = ld_svj<T>(o.dof, sub, [&](int r) { return c.ld_x(r); });
    v = motion_to_child(X, v) + vj;
    a = motion_to_child(X, a) + cross_motion(v, vj) + aj;
    S3T<T> J;
@@ -142,12 +144,12 @@ MB_HD void rnea_descend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &v, SvT<T> &
 
 template <class T, class Ctx, bool FEXT> MB_HD void rnea_ascend_6dof(Ctx &c, const MbOp2 o, int ext, SvT<T> &f)
 {
+   const int sub = mb_sub_of<Ctx>(o);
    if (FEXT && c.has_wr())
       rnea_store_joint_wrench<T>(c, ext, c.cst(o.body), f);
    if (FEXT && c.has_rootw() && (o.flags & MB2_ROOT_PARENT))
-      rnea_add_root_wrench<T>(c, force_to_parent(joint_xf_6dof<T>(c, c.cst(o.body), o.cfg), f));
-   c.st_out(o.dof + 0, f.a.x); c.st_out(o.dof + 1, f.a.y); c.st_out(o.dof + 2, f.a.z);
-   c.st_out(o.dof + 3, f.l.x); c.st_out(o.dof + 4, f.l.y); c.st_out(o.dof + 5, f.l.z);
+      rnea_add_root_wrench<T>(c, force_to_parent(joint_xf_multi<T>(c, c.cst(o.body), o.cfg, sub), f));
+   st_svj<T>(o.dof, sub, f, [&](int r, T x) { c.st_out(r, x); }); // tau = S^T W (:952-958)
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);

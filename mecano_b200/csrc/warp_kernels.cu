@@ -510,7 +510,15 @@ __global__ void __launch_bounds__(kWarpBlock) warp_crba_kernel(const MbProgram *
 }
 } // namespace
 
-bool warp_variant_supports(const MbProgram &P) { return P.nb <= 32; }
+bool warp_variant_supports(const MbProgram &P)
+{
+   if (P.nb > 32)
+      return false;
+   for (int i = 0; i < P.nb; i++)
+      if (P.body[i].sub != MB_SUB_SIX)
+         return false; // spherical / planar joints run on the thread-per-state kernels
+   return true;
+}
 
 // P: device copy of the traversal program
 

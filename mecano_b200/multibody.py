@@ -30,6 +30,10 @@ lib.mecano_model_add_revolute_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_i
 lib.mecano_model_add_prismatic_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp, _dp]
 lib.mecano_model_add_sixdof_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp]
 lib.mecano_model_add_fixed_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp]
+lib.mecano_model_add_spherical_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp]
+lib.mecano_model_add_planar_joint.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp]
+lib.mecano_model_next_joint_chain.argtypes = [_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+lib.mecano_model_next_joint_tree.argtypes = [_vp, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
 lib.mecano_model_set_joint_configuration.argtypes = [_vp, ctypes.c_int, _dp, ctypes.c_int]
 lib.mecano_model_finalize_ignoring.argtypes = [_vp, _ip, ctypes.c_int]
 lib.mecano_model_add_rigid_body.argtypes = [_vp, ctypes.c_char_p, ctypes.c_int, _dp, ctypes.c_double, _dp]
@@ -53,6 +57,7 @@ lib.mecano_model_table_row.argtypes = [_vp, ctypes.c_int]
 MODEL_EXPORTS = [
     "mecano_model_create", "mecano_model_destroy", "mecano_model_last_error", "mecano_model_add_revolute_joint",
     "mecano_model_add_prismatic_joint", "mecano_model_add_sixdof_joint", "mecano_model_add_fixed_joint", "mecano_model_add_rigid_body",
+    "mecano_model_add_spherical_joint", "mecano_model_add_planar_joint", "mecano_model_next_joint_chain", "mecano_model_next_joint_tree",
     "mecano_model_set_joint_configuration", "mecano_model_finalize_ignoring",
     "mecano_model_next_one_dof_joint_chain", "mecano_model_next_one_dof_joint_tree", "mecano_model_next_floating_base",
     "mecano_model_next_humanoid", "mecano_model_finalize", "mecano_model_n_joints", "mecano_model_n_dofs", "mecano_model_n_cfg",
@@ -117,7 +122,7 @@ class _Model:
         for j in range(len(self.joints), n):
             jt, pred = ctypes.c_int32(), ctypes.c_int32()
             lib.mecano_model_joint_info(self.h, j, ctypes.byref(jt), ctypes.byref(pred), None, None, None, None, None)
-            cls = {0: RevoluteJoint, 1: PrismaticJoint, 2: SixDoFJoint, 3: FixedJoint}[jt.value]
+            cls = {0: RevoluteJoint, 1: PrismaticJoint, 2: SixDoFJoint, SPHERICAL: SphericalJoint, PLANAR: PlanarJoint, FIXED: FixedJoint}[jt.value]
             joint = cls.__new__(cls)
             joint._adopt(self, j, self.bodies[pred.value])
             body = RigidBody.__new__(RigidBody)
@@ -176,6 +181,10 @@ class RigidBody:
         return list(self._children)
 
 
+SPHERICAL, PLANAR = 3, 4  # MECANO_B200_SPHERICAL / MECANO_B200_PLANAR (include/mecano_b200.h)
+FIXED = 5  # MECANO_MODEL_FIXED (include/mecano_b200_model.h)
+
+
 class Joint:
     _type = None
 
@@ -188,6 +197,10 @@ class Joint:
         tp = None if t12 is None else t12.ctypes.data_as(_dp)
         if self._type == _capi.SIXDOF:
             jid = lib.mecano_model_add_sixdof_joint(m.h, name.encode(), predecessor._id, tp)
+        elif self._type == SPHERICAL:
+            jid = lib.mecano_model_add_spherical_joint(m.h, name.encode(), predecessor._id, tp)
+        elif self._type == PLANAR:
+            jid = lib.mecano_model_add_planar_joint(m.h, name.encode(), predecessor._id, tp)
         elif self._type == FIXED:
             jid = lib.mecano_model_add_fixed_joint(m.h, name.encode(), predecessor._id, tp)
         else:
@@ -215,15 +228,16 @@ class Joint:
         return self._successor
 
     def getDegreesOfFreedom(self):
-        return {_capi.SIXDOF: 6, FIXED: 0}.get(self._type, 1)
+        return {_capi.SIXDOF: 6, SPHERICAL: 3, PLANAR: 3, FIXED: 0}.get(self._type, 1)
 
     def getConfigurationMatrixSize(self):
-        return {_capi.SIXDOF: 7, FIXED: 0}.get(self._type, 1)
+        return {_capi.SIXDOF: 7, SPHERICAL: 4, PLANAR: 3, FIXED: 0}.get(self._type, 1)
 
     def setJointConfiguration(self, q):
         """The configuration this joint keeps if it ends up in jointsToIgnore: Mecano lumps an ignored subtree into its parent
         body at the configuration the joints have when the calculator is built (InverseDynamicsCalculator.java:236,
-        :832-860).  One-DoF: [q] (also setQ); SixDoF: [qx qy qz qs x y z].  Must be called before toMultiBodySystemBasics."""
+        :832-860).  One-DoF: [q] (also setQ); SixDoF: [qx qy qz qs x y z]; Spherical: [qx qy qz qs]; Planar: [pitch x z].  Must be
+        called before toMultiBodySystemBasics."""
         q = np.ascontiguousarray(np.atleast_1d(q), dtype=np.float64)
         self._model.check(lib.mecano_model_set_joint_configuration(self._model.h, self._id, q.ctypes.data_as(_dp), int(q.size)))
 
@@ -266,7 +280,23 @@ class SixDoFJoint(Joint):
         self._create(name, predecessor, transformToParent, None)
 
 
-FIXED = 3  # MECANO_MODEL_FIXED (include/mecano_b200_model.h)
+class SphericalJoint(Joint):
+    """SphericalJoint(name, predecessor[, transformToParent | jointOffset])  (SphericalJoint.java:43-69): 3 DoF; configuration rows
+    [qx qy qz qs], velocity / acceleration / effort rows = the angular part in frameAfterJoint (SphericalJointReadOnly.java:31-71)."""
+    _type = SPHERICAL
+
+    def __init__(self, name, predecessor, transformToParent=None):
+        self._create(name, predecessor, transformToParent, None)
+
+
+class PlanarJoint(Joint):
+    """PlanarJoint(name, predecessor[, transformToParent])  (PlanarJoint.java:37-61): 3 DoF in the x-z plane of frameBeforeJoint;
+    configuration rows [pitch x z], velocity / acceleration / effort rows [w_y v_x v_z] in frameAfterJoint
+    (PlanarJointReadOnly.java:20-58)."""
+    _type = PLANAR
+
+    def __init__(self, name, predecessor, transformToParent=None):
+        self._create(name, predecessor, transformToParent, None)
 
 
 class FixedJoint(Joint):
@@ -422,6 +452,24 @@ class MultiBodySystemRandomTools:
         return m.joints[before:]
 
     @staticmethod
+    def nextJointChain(seed, rootBody, numberOfJoints):
+        """nextJointChain (MultiBodySystemRandomTools.java:424-440): joints of random types, all five moving joint types."""
+        m = rootBody._model
+        m.check(lib.mecano_model_next_joint_chain(m.h, int(seed), rootBody._id, int(numberOfJoints)))
+        before = len(m.joints)
+        m.adopt_generated()
+        return m.joints[before:]
+
+    @staticmethod
+    def nextJointTree(seed, rootBody, numberOfJoints):
+        """nextJointTree (:844-860)."""
+        m = rootBody._model
+        m.check(lib.mecano_model_next_joint_tree(m.h, int(seed), rootBody._id, int(numberOfJoints)))
+        before = len(m.joints)
+        m.adopt_generated()
+        return m.joints[before:]
+
+    @staticmethod
     def nextFloatingBase(seed, rootBody):
         m = rootBody._model
         m.check(lib.mecano_model_next_floating_base(m.h, int(seed), rootBody._id))
@@ -446,10 +494,14 @@ class MultiBodySystemRandomTools:
         q = rng.uniform(-np.pi, np.pi, size=(nq, n))
         prov = system.getJointMatrixIndexProvider()
         for j in system.getJointsToConsider():
-            if isinstance(j, SixDoFJoint):
+            if isinstance(j, (SixDoFJoint, SphericalJoint)):
                 c = prov.getJointConfigurationIndices(j)[0]
                 quat = rng.normal(size=(4, n))
                 quat /= np.linalg.norm(quat, axis=0)
                 q[c:c + 4] = quat
-                q[c + 4:c + 7] = rng.uniform(-1, 1, size=(3, n))
+                if isinstance(j, SixDoFJoint):
+                    q[c + 4:c + 7] = rng.uniform(-1, 1, size=(3, n))
+            elif isinstance(j, PlanarJoint):  # (pitch, x, z)
+                c = prov.getJointConfigurationIndices(j)[0]
+                q[c + 1:c + 3] = rng.uniform(-1, 1, size=(2, n))
         return tuple(np.ascontiguousarray(rng.uniform(-1, 1, size=(nv, n))) if k else np.ascontiguousarray(q) for k in range(4))

@@ -49,6 +49,7 @@ namespace
 {
 template <class T> struct CpuCtx
 {
+   static constexpr bool kM3 = true; // three-DoF joints compiled in (multidof.cuh)
    const double *q, *qd, *x, *fext;
    double *out, *M;
    long ld, s;
@@ -118,6 +119,10 @@ template <class T> struct CpuCtx
       ring[stage][2] = (mask & 4) ? ld_x(dof) : nan;
    }
    void pf_commit() {}
+   // cache warming: nothing to do on the host
+   void pf_six(int, int, int) const {}
+   void pf_six_next_tile(int, int, int) const {}
+   void rec_prefetch_far(int, int, int, int) const {}
    void stk_fence() const {}
    void op_sync(int) const {}
    template <int N> void pf_wait() {}
@@ -128,6 +133,7 @@ template <class T> struct CpuCtx
    void aux_st(int i, T v) { aux[i] = v; }
    T rec_ld(int i) const { return rec[i]; }
    void rec_st2(int i2, T a, T b) { rec[2 * i2] = a; rec[2 * i2 + 1] = b; }
+   void rec_ld2(int i2, T &a, T &b) const { a = rec[2 * i2]; b = rec[2 * i2 + 1]; }
    T ring3[4][2 + MB_ABA_REC];
    void pf3_issue(int stage, int cfg, int dof, int rec2, int mask)
    {

@@ -84,7 +84,7 @@ def lib():
     global _LIB
     if _LIB is None:
         out = os.path.join(_EMU, "libmecano_emu.so")
-        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh", "jointmath.cuh", "rnea.cuh", "aba.cuh", "crba.cuh", "coriolis.cuh")]
+        deps = [os.path.join(_EMU, "emu.cpp")] + [os.path.join(_CSRC, f) for f in ("flatten.cpp", "flatten.h", "program.h", "spatial.cuh", "algorithms.cuh", "jointmath.cuh", "multidof.cuh", "multidof_aba.cuh", "rnea.cuh", "aba.cuh", "crba.cuh", "coriolis.cuh")]
         if not os.path.exists(out) or any(os.path.getmtime(out) < os.path.getmtime(f) for f in deps):
             build()
         _LIB = ctypes.CDLL(out)

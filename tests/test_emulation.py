@@ -21,10 +21,16 @@ def trees(rng):
         td.chain(rng, 0, floating=True), td.chain(rng, 15, floating=True), td.random_tree(rng, 45, floating=True, com_rotation=True, prismatic_fraction=0.2),
         td.random_tree(rng, 12, floating=True, axis_aligned=True), td.humanoid(rng, 2), td.humanoid(rng, 1), td.random_tree(rng, 100, floating=True),
         td.chain(rng, 60),
+        # SphericalJoint / PlanarJoint (multidof.cuh): chains of one type, mixed trees, a floating base above them
+        td.mixed_chain(rng, [td.SPHERICAL] * 5), td.mixed_chain(rng, [td.PLANAR, td.REVOLUTE, td.PLANAR, td.PRISMATIC, td.SPHERICAL]),
+        td.mixed_tree(rng, 14, weights=(2, 1, 1, 2, 2), com_rotation=True), td.mixed_tree(rng, 30, floating=True),
     ]
 
 
-@pytest.mark.parametrize("idx", range(12))
+N_TREES = 16
+
+
+@pytest.mark.parametrize("idx", range(N_TREES))
 def test_emulated_kernels_match_oracle(idx):
     rng = np.random.default_rng(300 + idx)
     t = trees(rng)[idx]
@@ -46,7 +52,7 @@ def test_emulated_kernels_match_oracle(idx):
     assert rel(M, o.crba_batch(q)) < TOL
 
 
-@pytest.mark.parametrize("idx", range(12))
+@pytest.mark.parametrize("idx", range(N_TREES))
 def test_emulated_rnea_byproducts_match_oracle(idx):
     """getBodyAcceleration / getComputedJointWrench (InverseDynamicsCalculator.java:578-602): the kernel routines leave them
     in the frames the reference returns them in (CoM frame, frameAfterJoint)."""
@@ -68,7 +74,7 @@ def test_emulated_rnea_byproducts_match_oracle(idx):
             assert rel(wr[:, :, s], wr_o) < TOL
 
 
-@pytest.mark.parametrize("idx", range(12))
+@pytest.mark.parametrize("idx", range(N_TREES))
 def test_emulated_aba_source_modes_match_oracle(idx):
     """ForwardDynamicsCalculator with joints in ACCELERATION_SOURCE mode (ForwardDynamicsCalculator.java:1237-1253, :1286-1298)."""
     rng = np.random.default_rng(800 + idx)
@@ -94,7 +100,7 @@ def test_emulated_aba_source_modes_match_oracle(idx):
     assert np.array_equal(e.aba_sources(q, qd, tau, qdd_in, np.zeros(t.nb, np.int32)), e.aba(q, qd, tau))
 
 
-@pytest.mark.parametrize("idx", range(12))
+@pytest.mark.parametrize("idx", range(N_TREES))
 def test_emulated_centroidal_byproducts_match_oracle(idx):
     """getCentroidalMomentumMatrix() / getCentroidalConvectiveTerm() (CompositeRigidBodyMassMatrixCalculator.java:801-839) in the
     root frame, as the kernels leave them before the centre-of-mass shift."""
@@ -114,7 +120,7 @@ def test_emulated_centroidal_byproducts_match_oracle(idx):
         assert rel(rw[:, s], o.centroidal_convective_term(q[:, s], qd[:, s], 0)) < TOL
 
 
-@pytest.mark.parametrize("idx", range(12))
+@pytest.mark.parametrize("idx", range(N_TREES))
 def test_emulated_coriolis_matrix_matches_oracle(idx):
     """getCoriolisMatrix() (CompositeRigidBodyMassMatrixCalculator.java:358-366, :588-799), with the mass matrix of the same
     recursion; every entry of both dense matrices written."""

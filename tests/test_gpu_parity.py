@@ -40,6 +40,17 @@ def build(kind, seed, n_joints=0, prismatic=0.0, floating=False):
             base = mb.MultiBodySystemRandomTools.nextFloatingBase(seed + 1000, e).getSuccessor()
         if kind == "chain":
             mb.MultiBodySystemRandomTools.nextOneDoFJointChain(seed, base, n_joints, prismatic)
+        elif kind == "jchain":  # joints of all five moving types (MultiBodySystemRandomTools.nextJointChain)
+            mb.MultiBodySystemRandomTools.nextJointChain(seed, base, n_joints)
+        elif kind == "jtree":
+            mb.MultiBodySystemRandomTools.nextJointTree(seed, base, n_joints)
+        elif kind in ("spherical", "planar"):
+            cls = mb.SphericalJoint if kind == "spherical" else mb.PlanarJoint
+            rng = np.random.default_rng(seed)
+            for k in range(n_joints):
+                T = mb.RigidBodyTransform(td.random_rotation(rng), rng.uniform(-1, 1, size=3))
+                j = cls("j%d" % k, base, T)
+                base = mb.RigidBody("b%d" % k, j, td.random_spd_inertia(rng), 0.1 + rng.uniform(), rng.uniform(-1, 1, size=3))
         else:
             mb.MultiBodySystemRandomTools.nextOneDoFJointTree(seed, base, n_joints, prismatic)
     s = mb.MultiBodySystem.toMultiBodySystemBasics(e)
@@ -57,7 +68,17 @@ CASES = [
     ("H36", dict(kind="humanoid", seed=8, n_joints=1)),
     ("tree 100", dict(kind="tree", seed=9, n_joints=100, floating=True)),
     ("deep chain 60", dict(kind="chain", seed=10, n_joints=60)),
+    # SphericalJoint / PlanarJoint (ForwardDynamicsCalculatorTest.testJointChain / testJointTree: all joint types)
+    ("spherical chain 5", dict(kind="spherical", seed=11, n_joints=5)),
+    ("planar chain 4", dict(kind="planar", seed=12, n_joints=4)),
+    ("joint chain 12", dict(kind="jchain", seed=13, n_joints=12)),
+    ("joint tree 25", dict(kind="jtree", seed=14, n_joints=25)),
+    ("floating + joint tree 40", dict(kind="jtree", seed=15, n_joints=40, floating=True)),
 ]
+
+
+def has_3dof(t):
+    return bool(np.any((np.asarray(t.jtype) == td.SPHERICAL) | (np.asarray(t.jtype) == td.PLANAR)))
 
 
 @pytest.mark.parametrize("variant", ["thread", "warp"])
@@ -68,8 +89,8 @@ def test_kernels_match_oracle(torch_dev, idx, variant):
     torch, dev = torch_dev
     name, kw = CASES[idx]
     s, t = build(**kw)
-    if variant == "warp" and t.nb > 32:
-        # one lane per body: larger trees are refused, never silently rerouted
+    if variant == "warp" and (t.nb > 32 or has_3dof(t)):
+        # one lane per body, one-DoF and SixDoF joints: other trees are refused, never silently rerouted
         with pytest.raises(mb.MecanoB200Error):
             mb.InverseDynamicsCalculator(s).setKernelVariant("warp")
         return
@@ -363,7 +384,7 @@ def test_calculator_owned_mass_matrix_skips_structural_zeros_only(torch_dev, var
     assert rel(mine.cpu().numpy().reshape(nv, nv, n), o.crba_batch(q)) <= TOL
 
 
-@pytest.mark.parametrize("idx", [0, 3, 5, 6, 8])
+@pytest.mark.parametrize("idx", [0, 3, 5, 6, 8, 10, 11, 13, 14])
 def test_rnea_byproducts_match_oracle(torch_dev, idx):
     """getBodyAcceleration(body) / getComputedJointWrench(joint) for N states (InverseDynamicsCalculator.java:578-602):
     mecano_b200_rnea_full on device buffers and mecano_b200_rnea_full_host on host buffers, with and without external
@@ -416,7 +437,7 @@ def test_rnea_byproducts_match_oracle(torch_dev, idx):
     assert rel(only.getComputedJointWrenchMatrix().cpu().numpy().reshape(t.nb, 6, n), wr) == 0.0
 
 
-@pytest.mark.parametrize("idx", [0, 2, 3, 5, 6, 8])
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 6, 8, 10, 11, 13, 14])
 def test_forward_dynamics_joint_source_modes(torch_dev, idx):
     """ForwardDynamicsCalculator with joints in JointSourceMode.ACCELERATION_SOURCE (ForwardDynamicsCalculator.java:400-444,
     :1237-1253, :1286-1298, pass four :1315-1363): against the oracle state by state, and through the reference's own invariant
@@ -488,7 +509,7 @@ def test_forward_dynamics_joint_source_modes(torch_dev, idx):
     assert fdyn.getJointTauMatrix() is tau
 
 
-@pytest.mark.parametrize("idx", [0, 3, 5, 6, 8, 9])
+@pytest.mark.parametrize("idx", [0, 3, 5, 6, 8, 9, 10, 11, 13, 14])
 def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
     """getCentroidalMomentumMatrix() / getCentroidalConvectiveTerm() of the mass-matrix calculator
     (CompositeRigidBodyMassMatrixCalculator.java:380-440, :801-839) for N states, in the world frame and in the centre-of-mass
@@ -557,7 +578,7 @@ def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
         assert np.max(np.abs(hdot[3:, k] - total)) < 1e-9 * max(1.0, np.max(np.abs(total))), name
 
 
-@pytest.mark.parametrize("idx", [0, 2, 3, 5, 6, 8, 9])
+@pytest.mark.parametrize("idx", [0, 2, 3, 5, 6, 8, 9, 10, 11, 13, 14])
 def test_coriolis_matrix(torch_dev, idx):
     """getCoriolisMatrix() (CompositeRigidBodyMassMatrixCalculator.java:278-281, :358-366, :588-799) for N states: against the
     oracle state by state, and on the whole batch through the reference's own test

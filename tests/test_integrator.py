@@ -107,6 +107,39 @@ def test_oracle_batch_equals_single():
         np.testing.assert_array_equal(QDD[:, s], c)
 
 
+def test_oracle_spherical_and_planar_joints_against_the_sixdof_update():
+    """SphericalJoint (MultiBodySystemStateIntegrator.java:449-452, :575-594) and PlanarJoint (a FloatingJointBasics, :421-424 ->
+    :503-560) integrate like a SixDoFJoint whose state is confined to the joint's subspace: the oracle's two branches against its
+    SixDoF branch (pinned by the reference's ballistic test above) on the embedded state."""
+    rng = np.random.default_rng(17)
+    six = ol.Oracle(free_body())
+    sph = ol.Oracle(td.mixed_chain(rng, [td.SPHERICAL]))
+    pla = ol.Oracle(td.mixed_chain(rng, [td.PLANAR]))
+    dt = 3.0e-3
+    for _ in range(20):
+        quat = rng.normal(size=4)
+        quat /= np.linalg.norm(quat)
+        w, wd = rng.uniform(-2, 2, size=3), rng.uniform(-2, 2, size=3)
+        # spherical: SixDoF at the origin with no linear velocity / acceleration
+        q6 = np.concatenate([quat, np.zeros(3)])
+        a, b, c = six.integrate(dt, q6, np.concatenate([w, np.zeros(3)]), np.concatenate([wd, np.zeros(3)]))
+        qs, ws, wds = sph.integrate(dt, quat.copy(), w.copy(), wd.copy())
+        assert np.max(np.abs(qs - a[:4])) < 1e-15 and np.max(np.abs(ws - b[:3])) < 1e-15
+        np.testing.assert_array_equal(wds, wd)
+        assert np.max(np.abs(a[4:])) == 0.0
+        # planar: pitch about y, position / velocity / acceleration in the x-z plane
+        th, x, z = rng.uniform(-np.pi, np.pi), rng.uniform(-1, 1), rng.uniform(-1, 1)
+        v3, a3 = rng.uniform(-2, 2, size=3), rng.uniform(-2, 2, size=3)  # (w_y, v_x, v_z)
+        q6 = np.array([0.0, np.sin(th / 2), 0.0, np.cos(th / 2), x, 0.0, z])
+        a, b, c = six.integrate(dt, q6, np.array([0, v3[0], 0, v3[1], 0, v3[2]]), np.array([0, a3[0], 0, a3[1], 0, a3[2]]))
+        qp, vp, ap = pla.integrate(dt, np.array([th, x, z]), v3.copy(), a3.copy())
+        R = quat_rot(a[:4])
+        assert abs(np.arctan2(R[0, 2], R[0, 0]) - np.arctan2(np.sin(qp[0]), np.cos(qp[0]))) < 1e-14  # R_y(pitch): xz = sin, xx = cos
+        assert np.max(np.abs(qp[1:] - a[[4, 6]])) < 1e-14 and abs(a[5]) < 1e-16
+        assert np.max(np.abs(vp - b[[1, 3, 5]])) < 1e-14 and np.max(np.abs(b[[0, 2, 4]])) < 1e-16
+        assert np.max(np.abs(ap - c[[1, 3, 5]])) < 1e-14 and np.max(np.abs(c[[0, 2, 4]])) < 1e-16
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _rel(a, b):
     return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
@@ -117,6 +150,9 @@ GPU_CASES = [
     dict(kind="tree", seed=4, n_joints=30, prismatic=0.4),
     dict(kind="tree", seed=6, n_joints=50, floating=True, prismatic=0.2),
     dict(kind="humanoid", seed=7, n_joints=2),
+    dict(kind="spherical", seed=11, n_joints=3),
+    dict(kind="planar", seed=12, n_joints=3),
+    dict(kind="jtree", seed=14, n_joints=25),
 ]
 
 
