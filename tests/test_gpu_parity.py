@@ -563,7 +563,7 @@ def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
             if t.parent[body] < 0:
                 # rotation frameAfterJoint -> world of a child of the root body
                 qi = q[t.cfg_off[body]:, k]
-                if t.jtype[body] == td.SIXDOF:
+                if t.jtype[body] in (td.SIXDOF, td.SPHERICAL):
                     x, y, z, w = qi[:4] / np.linalg.norm(qi[:4])
                     R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
                                   [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
@@ -572,6 +572,8 @@ def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
                     u, a = t.axis[body] / np.linalg.norm(t.axis[body]), qi[0]
                     K = np.array([[0, -u[2], u[1]], [u[2], 0, -u[0]], [-u[1], u[0], 0]])
                     R = np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+                elif t.jtype[body] == td.PLANAR:  # rotation about y by the pitch
+                    R = np.array([[np.cos(qi[0]), 0, np.sin(qi[0])], [0, 1, 0], [-np.sin(qi[0]), 0, np.cos(qi[0])]])
                 else:
                     R = np.eye(3)
                 total += t.off_R[body] @ R @ wr[body, 3:, k]
