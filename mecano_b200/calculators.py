@@ -85,8 +85,8 @@ class _BatchedCalculator:
         return self._engine.kernel_info(self._ALGO, n_states)
 
     def setKernelVariant(self, variant):
-        """"auto" (default: by batch size), "thread" (one thread per state) or "warp" (one warp per state, lane = body, trees
-        of up to 32 bodies; for small batches)."""
+        """"auto" (default: by batch size), "thread" (one thread per state) or "warp" (body-parallel, lane = body: one warp per state for
+        trees of up to 32 bodies, a team of two to four warps up to 128; one-DoF and SixDoF joints; for small batches)."""
         self._engine.set_variant({"auto": 0, "thread": 1, "warp": 2}[variant] if isinstance(variant, str) else int(variant))
         return self
 

@@ -44,7 +44,7 @@ struct mecano_b200_handle
    int max_children = 1, max_ndof = 1, sm_count = 148;
    int n_accel_source = 0;           // joints in ACCELERATION_SOURCE mode (mecano_b200_set_joint_source_modes)
    std::vector<std::pair<int, int>> effort_dof_runs; // (first DoF row, count) runs of DoF rows whose joints are EFFORT_SOURCE
-   bool warp_ok = false;             // the tree fits the warp-per-state variant (<= 32 bodies)
+   bool warp_ok = false;             // the body-parallel variant serves this tree (one-DoF / SixDoF joints; <= 32 bodies: a warp per state, else a team of warps)
    bool has_3dof = false;            // the tree has spherical / planar joints (generic thread-per-state kernels only)
    int64_t warp_below[MB_NUM_ALGOS] = {0, 0, 0, 0}; // AUTO: batches smaller than this run warp-per-state
    std::string error;
@@ -162,7 +162,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    if (use_warp)
    {
       if (!h->warp_ok)
-         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body)");
+         return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of one-DoF and SixDoF joints only");
       mb::KernelArgs wa;
       wa.q = q; wa.qd = qd; wa.x = x; wa.fext = fext; wa.out = out;
       wa.body_acc = wa.joint_wrench = nullptr;
@@ -179,7 +179,11 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.grav[0] = h->gravity[0]; wa.grav[1] = h->gravity[1]; wa.grav[2] = h->gravity[2];
       wa.flags = flags;
       wa.nv = h->tree.nv;
-      MB_CUDA(h, mb::launch_warp_kernel(algo, h->d_prog + algo, wa, h->max_children, h->max_ndof, h->sm_count, stream));
+      // one lane per body: a warp per state up to 32 bodies, a team of two to four warps beyond (team_kernels.cu)
+      if (h->tree.prog[algo].nb <= 32)
+         MB_CUDA(h, mb::launch_warp_kernel(algo, h->d_prog + algo, wa, h->max_children, h->max_ndof, h->sm_count, stream));
+      else
+         MB_CUDA(h, mb::launch_team_kernel(algo, h->d_prog + algo, h->tree.prog[algo].nb, wa, h->max_children, h->max_ndof, h->sm_count, stream));
       return MECANO_B200_OK;
    }
    // the tree-specialised kernel covers the common call (no external wrenches, default flags / layout); everything else
@@ -694,6 +698,12 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       // of one state now takes 49 / 96 / 98 us, the warp kernels cross it at 4.8 k / 3.9 k / 3.4 k states).
       // MECANO_B200_WARP_BELOW overrides all three
       h->warp_below[MB_RNEA] = 2048 + 80 * P.nb; h->warp_below[MB_ABA] = 1536 + 64 * P.nb; h->warp_below[MB_CRBA] = 2048 + 40 * P.nb;
+      if (P.nb > 32)
+      {
+         // team-per-state kernels (team_kernels.cu), trees of 51 / 75 / 101 bodies: crossovers at 2.5-2.7 k (RNEA), 1.5-2.0 k (ABA)
+         // and 3.3-4.5 k states (CRBA), profiles/r05b_config5_1gpu.jsonl
+         h->warp_below[MB_RNEA] = 2560; h->warp_below[MB_ABA] = 1792; h->warp_below[MB_CRBA] = 3584;
+      }
       if (const char *e = getenv("MECANO_B200_WARP_BELOW"))
          h->warp_below[0] = h->warp_below[1] = h->warp_below[2] = atoll(e);
    }
@@ -756,7 +766,7 @@ int mecano_b200_set_variant(mecano_b200_handle *h, int variant)
    if (variant != MECANO_B200_VARIANT_AUTO && variant != MECANO_B200_VARIANT_THREAD && variant != MECANO_B200_VARIANT_WARP)
       return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "unknown variant");
    if (variant == MECANO_B200_VARIANT_WARP && !h->warp_ok)
-      return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant handles trees of up to 32 bodies (one lane per body) of one-DoF and SixDoF joints");
+      return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the warp-per-state variant (one lane per body) handles trees of one-DoF and SixDoF joints");
    h->variant = variant;
    return MECANO_B200_OK;
 }
@@ -1179,10 +1189,12 @@ int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_state
    {
       std::memset(info, 0, sizeof *info);
       cudaFuncAttributes fa;
-      MB_CUDA(h, mb::warp_kernel_attributes(algo, false, &fa));
+      const bool team = h->tree.prog[algo].nb > 32;
+      if (team) MB_CUDA(h, mb::team_kernel_attributes(algo, false, &fa));
+      else MB_CUDA(h, mb::warp_kernel_attributes(algo, false, &fa));
       info->variant = MECANO_B200_VARIANT_WARP;
-      info->block_threads = 128;
-      info->states_per_block = 4;
+      info->block_threads = team ? mb::team_threads(h->tree.prog[algo]) : 128;
+      info->states_per_block = team ? 1 : 4;
       info->regs_per_thread = fa.numRegs;
       info->local_bytes_per_thread = (int32_t)fa.localSizeBytes;
       info->static_smem_bytes = (int32_t)fa.sharedSizeBytes;

@@ -33,10 +33,15 @@ cudaError_t plan_thread_kernel(int algo, const MbProgram &P, bool fext, LaunchPl
 
 cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs &a, const LaunchPlan &plan, cudaStream_t stream);
 
-// warp-per-state variant (warp_kernels.cu): lane = body, trees of up to 32 bodies
+// warp-per-state variant (warp_kernels.cu): lane = body, trees of up to 32 bodies; larger trees (up to MB_MAX_BODIES) run the
+// team kernels below.  warp_variant_supports: one of the two serves this tree
 bool warp_variant_supports(const MbProgram &P);
 cudaError_t launch_warp_kernel(int algo, const MbProgram *device_program, const KernelArgs &a, int max_children, int max_ndof, int sm_count, cudaStream_t stream);
 cudaError_t warp_kernel_attributes(int algo, bool fext, cudaFuncAttributes *attr);
+// team-per-state variant (team_kernels.cu): thread = body, two to four warps per state, trees of 33 to 128 bodies
+int team_threads(const MbProgram &P);
+cudaError_t launch_team_kernel(int algo, const MbProgram *device_program, int nb, const KernelArgs &a, int max_children, int max_ndof, int sm_count, cudaStream_t stream);
+cudaError_t team_kernel_attributes(int algo, bool fext, cudaFuncAttributes *attr);
 
 // batched state integrator (integrate.cu): MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration
 struct IntegrateJoints

@@ -89,8 +89,9 @@ def test_kernels_match_oracle(torch_dev, idx, variant):
     torch, dev = torch_dev
     name, kw = CASES[idx]
     s, t = build(**kw)
-    if variant == "warp" and (t.nb > 32 or has_3dof(t)):
-        # one lane per body, one-DoF and SixDoF joints: other trees are refused, never silently rerouted
+    if variant == "warp" and has_3dof(t):
+        # one lane per body (a warp per state up to 32 bodies, a team of two to four warps up to 128), one-DoF and SixDoF joints:
+        # other trees are refused, never silently rerouted
         with pytest.raises(mb.MecanoB200Error):
             mb.InverseDynamicsCalculator(s).setKernelVariant("warp")
         return
