@@ -77,6 +77,18 @@ const mecano_b200_tree_desc *mecano_model_tables(const mecano_model *m);
 /* row of joint `joint` in the level-ordered tables */
 int mecano_model_table_row(const mecano_model *m, int joint);
 
+/* The same system with nothing welded, for external wrenches and per-body results on systems with fixed / ignored joints
+ * (InverseDynamicsCalculator.java:469-472 with :832-860): every joint of the tree is a body of these tables; a FixedJoint is a
+ * revolute joint held at q = 0, an ignored joint keeps its type at its stored configuration.  The held joints' configuration /
+ * DoF rows come BEHIND the system's own (n_extra_cfg / n_extra_dof more rows), the wrench blocks of ignored bodies behind the
+ * considered joints' (n_extra_wrench_blocks more blocks of six rows): the caller's matrices are the leading rows of the expanded
+ * ones.  expanded_fill: q_extra[n_extra_cfg] = what to put into the extra configuration rows (velocities and accelerations of
+ * held joints are zero); locked[n_bodies] = 1 for held joints (forward dynamics: ACCELERATION_SOURCE with zero acceleration,
+ * mecano_b200_set_joint_source_modes); row_of_considered[considered joints] = table row of each considered joint. */
+const mecano_b200_tree_desc *mecano_model_expanded_tables(mecano_model *m);
+int mecano_model_expanded_info(mecano_model *m, int32_t *n_bodies, int32_t *n_extra_dof, int32_t *n_extra_cfg, int32_t *n_extra_wrench_blocks);
+int mecano_model_expanded_fill(mecano_model *m, double *q_extra, int32_t *locked, int32_t *row_of_considered);
+
 #ifdef __cplusplus
 }
 #endif

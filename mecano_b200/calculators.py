@@ -37,7 +37,9 @@ class _BatchedCalculator:
         if isinstance(input, RigidBody):  # InverseDynamicsCalculator(RigidBodyReadOnly rootBody), :186
             input = MultiBodySystem.toMultiBodySystemBasics(input)
         self._input = input
+        self._device = device
         self._engine = _make_engine(input, device)
+        self._xengine = None  # engine over the expanded tables (systems with fixed / ignored joints; lazy)
         self._fext = None
         self._gravity = (0.0, 0.0, 0.0)
 
@@ -59,10 +61,40 @@ class _BatchedCalculator:
     def setExternalWrenches(self, wrenches):
         """External wrench on the successor of every joint, [6 * nJoints, N] in JointMatrixIndexProvider order, each
         expressed in its body's CoM frame (setExternalWrench, InverseDynamicsCalculator.java:469-472, :819)."""
-        if wrenches is not None and self._input.hasWeldedBodies():
-            # a wrench on a welded body would have to be re-expressed on the body it was folded into; refuse rather than drop it
-            raise NotImplementedError("external wrenches are not supported on systems with fixed or ignored joints")
         self._fext = wrenches
+
+    # ---- systems with fixed / ignored joints.  Their tables weld the successors of FixedJoints and the ignored subtrees into the
+    # bodies that carry them (the fast path of every plain call).  A call with external wrenches or per-body results needs those
+    # bodies back -- a wrench on a FixedJoint's successor acts where it is applied, every body reports its acceleration in its
+    # own frame, a FixedJoint transmits a wrench (InverseDynamicsCalculator.java:469-472, :578-602 with :832-860) -- and runs on
+    # the expanded tables instead (MultiBodySystem.expanded(): nothing welded, the fixed / ignored joints held at their
+    # configuration with zero velocity and acceleration, their rows appended behind the system's own).
+    def _expanded(self):
+        if isinstance(self._device, (list, tuple)):
+            raise NotImplementedError("external wrenches / per-body results on systems with fixed or ignored joints run on one device")
+        x = self._input.expanded()
+        if self._xengine is None:
+            self._xengine = Engine(x.tables().contents, self._device, keepalive=self._input)
+        self._xengine.set_gravity(*self._gravity)
+        return self._xengine, x
+
+    @staticmethod
+    def _extended(m, extra_rows, fill=None):
+        """[rows + extra_rows, N]: m on top; below it `fill` (one value per row, the same for every state) or zeros."""
+        rows, n = m.shape
+        if _is_torch(m):
+            import torch
+
+            out = torch.empty((rows + extra_rows, n), dtype=torch.float64, device=m.device)
+            out[:rows] = m
+            if extra_rows:
+                out[rows:] = 0.0 if fill is None else torch.as_tensor(np.asarray(fill), dtype=torch.float64, device=m.device)[:, None]
+            return out
+        out = np.empty((rows + extra_rows, n), dtype=np.float64)
+        out[:rows] = m
+        if extra_rows:
+            out[rows:] = 0.0 if fill is None else np.asarray(fill, dtype=np.float64)[:, None]
+        return out
 
     def setExternalWrenchesToZero(self):
         self._fext = None
@@ -138,8 +170,6 @@ class InverseDynamicsCalculator(_BatchedCalculator):
         (getBodyAcceleration, getComputedJointWrench; InverseDynamicsCalculator.java:578-602).  For N states these are two
         [6 * nJoints, N] matrices (12 * nBodies more rows of HBM traffic than the joint efforts), so the batched calculator
         writes them only on request.  Returns self."""
-        if (bodyAccelerations or jointWrenches) and self._input.hasWeldedBodies():
-            raise NotImplementedError("per-body results are not supported on systems with fixed or ignored joints")
         self._want_acc, self._want_wrench = bool(bodyAccelerations), bool(jointWrenches)
         return self
 
@@ -157,6 +187,23 @@ class InverseDynamicsCalculator(_BatchedCalculator):
             self._check("externalWrenches", self._fext, 6 * self._input.getNumberOfJoints(), n)
         flags = (0 if self._coriolis else _capi.RNEA_NO_CORIOLIS) | (0 if self._accelerations else _capi.RNEA_NO_ACCELERATIONS)
         rows = 6 * self._input.getNumberOfJoints()
+        if self._input.hasWeldedBodies() and (self._fext is not None or self._want_acc or self._want_wrench):
+            # fixed / ignored joints: on the expanded tables (see _expanded)
+            eng, x = self._expanded()
+            q2 = self._extended(q, x.n_extra_cfg, x.q_extra)
+            qd2, qdd2 = self._extended(qd, x.n_extra_dof), self._extended(qdd, x.n_extra_dof)
+            tau2 = self._empty_like(q2, nv + x.n_extra_dof, n, match_ld=False)
+            f2 = None if self._fext is None else self._extended(self._fext, 6 * x.n_extra_wrench_blocks)
+            rows2 = rows + 6 * x.n_extra_wrench_blocks
+            acc2 = self._empty_like(q2, rows2, n, match_ld=False) if self._want_acc else None
+            wr2 = self._empty_like(q2, rows2, n, match_ld=False) if self._want_wrench else None
+            (eng.rnea if _is_torch(q) else eng.rnea_host)(q2, qd2, qdd2, tau2, fext=f2, flags=flags, body_acc=acc2, joint_wrench=wr2)
+            tau[:] = tau2[:nv]
+            # the considered joints' blocks lead (the ignored bodies' follow): [6 * nJoints, N] views
+            self._body_acc = None if acc2 is None else acc2[:rows]
+            self._joint_wrench = None if wr2 is None else wr2[:rows]
+            self._tau = tau
+            return tau
         self._body_acc = self._empty_like(q, rows, n) if self._want_acc else None
         self._joint_wrench = self._empty_like(q, rows, n) if self._want_wrench else None
         if _is_torch(q):
@@ -272,6 +319,28 @@ class ForwardDynamicsCalculator(_BatchedCalculator):
             self._check("externalWrenches", self._fext, 6 * self._input.getNumberOfJoints(), n)
         if self._modes:
             self._check("jointAccelerationInput", jointAccelerationInput, nv, n)
+        if self._fext is not None and self._input.hasWeldedBodies():
+            # fixed / ignored joints with external wrenches: on the expanded tables (see _expanded), the held joints locked
+            # (ACCELERATION_SOURCE with zero acceleration, next to the caller's own ACCELERATION_SOURCE joints)
+            eng, x = self._expanded()
+            locked = x.locked.copy()
+            considered = self._input.getJointsToConsider()
+            for joint in self._modes:
+                locked[x.row_of_considered[considered.index(joint)]] = 1
+            eng.set_joint_source_modes(locked)
+            q2 = self._extended(q, x.n_extra_cfg, x.q_extra)
+            qd2, tau2 = self._extended(qd, x.n_extra_dof), self._extended(tau, x.n_extra_dof)
+            acc_in = jointAccelerationInput if self._modes else (qd * 0.0)
+            acc_in2 = self._extended(acc_in, x.n_extra_dof)
+            qdd2 = self._empty_like(q2, nv + x.n_extra_dof, n, match_ld=False)
+            tau_out2 = self._empty_like(q2, nv + x.n_extra_dof, n, match_ld=False)
+            f2 = self._extended(self._fext, 6 * x.n_extra_wrench_blocks)
+            (eng.aba_sources if _is_torch(q) else eng.aba_sources_host)(q2, qd2, tau2, acc_in2, qdd2, tau_out2, fext=f2)
+            qdd[:] = qdd2[:nv]
+            self._tau = tau_out2[:nv] if self._modes else tau
+            self._qdd = qdd
+            return qdd
+        if self._modes:
             tau_out = self._empty_like(q, nv, n)
             run = self._engine.aba_sources if _is_torch(q) else self._engine.aba_sources_host
             run(q, qd, tau, jointAccelerationInput, qdd, tau_out, fext=self._fext)

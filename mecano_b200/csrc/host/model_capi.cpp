@@ -16,6 +16,9 @@ struct mecano_model
    bool finalized = false;
    MultiBodySystem system;
    FlatTables tables;
+   FlatTables expanded; // nothing welded, fixed / ignored joints held (lazy)
+   FlatTables::Expanded expanded_info;
+   bool has_expanded = false;
    std::string error;
 };
 
@@ -327,6 +330,66 @@ const char *mecano_model_body_name(const mecano_model *m, int body)
 }
 
 const mecano_b200_tree_desc *mecano_model_tables(const mecano_model *m) { return m && m->finalized ? &m->tables.desc : nullptr; }
+
+// ---- the expanded tables (FlatTables::flattenExpanded): nothing welded, the fixed / ignored joints held
+static bool ensure_expanded(mecano_model *m)
+{
+   if (!m || !m->finalized) return false;
+   if (!m->has_expanded)
+   {
+      m->expanded = FlatTables::flattenExpanded(m->system, m->expanded_info);
+      m->expanded.bind(m->system.getNumberOfDoFs() + m->expanded_info.n_extra_dof, m->system.getConfigurationMatrixSize() + m->expanded_info.n_extra_cfg);
+      m->has_expanded = true;
+   }
+   return true;
+}
+
+const mecano_b200_tree_desc *mecano_model_expanded_tables(mecano_model *m)
+{
+   try
+   {
+      return ensure_expanded(m) ? &m->expanded.desc : nullptr;
+   }
+   catch (const std::exception &e)
+   {
+      fail(m, e.what());
+      return nullptr;
+   }
+}
+
+int mecano_model_expanded_info(mecano_model *m, int32_t *n_bodies, int32_t *n_extra_dof, int32_t *n_extra_cfg, int32_t *n_extra_wrench_blocks)
+{
+   try
+   {
+      if (!ensure_expanded(m)) return -1;
+   }
+   catch (const std::exception &e)
+   {
+      return fail(m, e.what());
+   }
+   if (n_bodies) *n_bodies = (int32_t)m->expanded.parent.size();
+   if (n_extra_dof) *n_extra_dof = m->expanded_info.n_extra_dof;
+   if (n_extra_cfg) *n_extra_cfg = m->expanded_info.n_extra_cfg;
+   if (n_extra_wrench_blocks) *n_extra_wrench_blocks = m->expanded_info.n_extra_bodies;
+   return 0;
+}
+
+int mecano_model_expanded_fill(mecano_model *m, double *q_extra, int32_t *locked, int32_t *row_of_considered)
+{
+   try
+   {
+      if (!ensure_expanded(m)) return -1;
+   }
+   catch (const std::exception &e)
+   {
+      return fail(m, e.what());
+   }
+   const auto &x = m->expanded_info;
+   if (q_extra) std::copy(x.q_extra.begin(), x.q_extra.end(), q_extra);
+   if (locked) std::copy(x.locked.begin(), x.locked.end(), locked);
+   if (row_of_considered) std::copy(x.row_of_considered.begin(), x.row_of_considered.end(), row_of_considered);
+   return 0;
+}
 
 int mecano_model_table_row(const mecano_model *m, int joint)
 {

@@ -516,14 +516,107 @@ struct FlatTables
       return f;
    }
 
+   // ---- the same system with nothing welded: every joint of the tree is a body of the tables, and the joints that flatten()
+   // folds away are HELD instead -- a FixedJoint becomes a revolute joint kept at q = 0, an ignored joint keeps its own type at
+   // its stored configuration, all with qd = qdd = 0 (the calculators lock them: ACCELERATION_SOURCE with zero acceleration).
+   // Their configuration / DoF rows are appended BEHIND the system's own rows, their wrench rows behind the considered joints',
+   // so the caller's matrices are the leading rows of the expanded ones.  This is what external wrenches and per-body results
+   // on systems with fixed / ignored joints run on (InverseDynamicsCalculator.java:469-472 with :832-860): the held bodies exist,
+   // so a wrench on a FixedJoint's successor acts where it is applied and every body reports its acceleration in its own frame.
+   struct Expanded
+   {
+      int n_extra_dof = 0, n_extra_cfg = 0, n_extra_bodies = 0; // rows / wrench blocks appended for held joints
+      std::vector<double> q_extra;                              // [n_extra_cfg] configuration of the held joints
+      std::vector<int32_t> locked;                              // [n_bodies] 1 = held joint
+      std::vector<int32_t> row_of_considered;                   // [considered joints] -> row in these tables
+   };
+   static FlatTables flattenExpanded(const MultiBodySystem &sys, Expanded &x)
+   {
+      FlatTables f;
+      const int nv = sys.getNumberOfDoFs(), nq = sys.getConfigurationMatrixSize(), nj = (int)sys.getJointsToConsider().size();
+      x = Expanded();
+      x.row_of_considered.assign((size_t)nj, -1);
+      struct Item
+      {
+         const Joint *j;
+         int parent_row;
+         bool ignored;
+      };
+      std::vector<Item> stack;
+      const auto &rc = sys.getRootBody()->getChildrenJoints();
+      for (auto it = rc.rbegin(); it != rc.rend(); ++it)
+         stack.push_back({*it, -1, sys.isIgnoredSubtreeRoot(*it)});
+      while (!stack.empty())
+      {
+         const Item it = stack.back();
+         stack.pop_back();
+         const Joint *j = it.j;
+         const RigidBody *b = j->getSuccessor();
+         if (!b)
+            throw ScrewTheoryException("joint " + j->getName() + " has no successor");
+         const int row = (int)f.parent.size();
+         const bool fixed = j->getType() == JointType::Fixed;
+         const bool held = fixed || it.ignored;
+         f.parent.push_back(it.parent_row);
+         f.joint_type.push_back(fixed ? (int)JointType::Revolute : (int)j->getType());
+         const int nd = fixed ? 1 : j->getDegreesOfFreedom(), nc = fixed ? 1 : j->getConfigurationMatrixSize();
+         if (held)
+         {
+            f.dof_offset.push_back(nv + x.n_extra_dof);
+            f.cfg_offset.push_back(nq + x.n_extra_cfg);
+            x.n_extra_dof += nd;
+            x.n_extra_cfg += nc;
+            // stored configuration (default: zero / identity orientation)
+            std::vector<double> q0 = fixed ? std::vector<double>{0.0} : j->getJointConfiguration();
+            if ((int)q0.size() != nc)
+            {
+               q0.assign((size_t)nc, 0.0);
+               if (j->getType() == JointType::SixDoF || j->getType() == JointType::Spherical)
+                  q0[3] = 1.0;
+            }
+            x.q_extra.insert(x.q_extra.end(), q0.begin(), q0.end());
+         }
+         else
+         {
+            const int i = sys.indexOf(j);
+            f.dof_offset.push_back(sys.dofIndexAt((size_t)i));
+            f.cfg_offset.push_back(sys.cfgIndexAt((size_t)i));
+         }
+         if (it.ignored)
+            f.wrench_index.push_back(nj + x.n_extra_bodies++); // a zero block behind the caller's wrench rows
+         else
+         {
+            const int i = sys.indexOf(j);
+            f.wrench_index.push_back(i);
+            x.row_of_considered[(size_t)i] = row;
+         }
+         x.locked.push_back(held ? 1 : 0);
+         const Vector3D ax = fixed ? Vector3D{0, 0, 1} : j->getJointAxis();
+         f.axis.insert(f.axis.end(), {ax.x, ax.y, ax.z});
+         const RigidBodyTransform &T = j->getTransformToParent();
+         f.offset_rot.insert(f.offset_rot.end(), T.rotation.m, T.rotation.m + 9);
+         f.offset_pos.insert(f.offset_pos.end(), {T.translation.x, T.translation.y, T.translation.z});
+         const RigidBodyTransform &P = b->getInertiaPose();
+         f.com_rot.insert(f.com_rot.end(), P.rotation.m, P.rotation.m + 9);
+         f.com_pos.insert(f.com_pos.end(), {P.translation.x, P.translation.y, P.translation.z});
+         f.inertia.insert(f.inertia.end(), b->getMomentOfInertia().m, b->getMomentOfInertia().m + 9);
+         f.mass.push_back(b->getMass());
+         const auto &ch = b->getChildrenJoints();
+         for (auto c = ch.rbegin(); c != ch.rend(); ++c)
+            stack.push_back({*c, row, it.ignored || sys.isIgnoredSubtreeRoot(*c)});
+      }
+      f.bind(nv + x.n_extra_dof, nq + x.n_extra_cfg); // depth-first listing, no level table (the C ABI accepts any topological order)
+      return f;
+   }
+
    void bind(int ndofs, int ncfg)
    {
       desc.struct_size = (int32_t)sizeof(mecano_b200_tree_desc);
       desc.n_bodies = (int32_t)parent.size();
       desc.n_dofs = ndofs;
       desc.n_cfg = ncfg;
-      desc.n_levels = (int32_t)level_start.size() - 1;
-      desc.level_start = level_start.data();
+      desc.n_levels = level_start.empty() ? 0 : (int32_t)level_start.size() - 1;
+      desc.level_start = level_start.empty() ? nullptr : level_start.data();
       desc.parent = parent.data();
       desc.joint_type = joint_type.data();
       desc.axis = axis.data();

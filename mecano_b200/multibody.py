@@ -53,6 +53,10 @@ lib.mecano_model_body_name.restype = ctypes.c_char_p
 lib.mecano_model_tables.argtypes = [_vp]
 lib.mecano_model_tables.restype = ctypes.POINTER(_capi.TreeDesc)
 lib.mecano_model_table_row.argtypes = [_vp, ctypes.c_int]
+lib.mecano_model_expanded_tables.argtypes = [_vp]
+lib.mecano_model_expanded_tables.restype = ctypes.POINTER(_capi.TreeDesc)
+lib.mecano_model_expanded_info.argtypes = [_vp, _ip, _ip, _ip, _ip]
+lib.mecano_model_expanded_fill.argtypes = [_vp, _dp, _ip, _ip]
 
 MODEL_EXPORTS = [
     "mecano_model_create", "mecano_model_destroy", "mecano_model_last_error", "mecano_model_add_revolute_joint",
@@ -63,6 +67,7 @@ MODEL_EXPORTS = [
     "mecano_model_next_humanoid", "mecano_model_finalize", "mecano_model_n_joints", "mecano_model_n_dofs", "mecano_model_n_cfg",
     "mecano_model_joint_order", "mecano_model_joint_info", "mecano_model_joint_name", "mecano_model_body_name",
     "mecano_model_tables", "mecano_model_table_row",
+    "mecano_model_expanded_tables", "mecano_model_expanded_info", "mecano_model_expanded_fill",
 ]
 
 
@@ -389,6 +394,16 @@ class MultiBodySystem:
         """ctypes pointer to the level-ordered mecano_b200_tree_desc (owned by the model)."""
         return lib.mecano_model_tables(self._model.h)
 
+    def expanded(self):
+        """The same system with nothing welded (mecano_model_expanded_tables): every joint of the tree is a body, the fixed /
+        ignored joints are held (q = stored configuration, qd = qdd = 0, locked in forward dynamics).  The calculators run
+        external wrenches and per-body results of systems with fixed / ignored joints on it.  Returns an object with
+        tables() (as this system's), n_bodies, n_extra_dof, n_extra_cfg, n_extra_wrench_blocks, q_extra, locked,
+        row_of_considered."""
+        if getattr(self, "_expanded", None) is None:
+            self._expanded = _ExpandedSystem(self)
+        return self._expanded
+
     def tableRow(self, joint):
         """Row of `joint` in the tree description handed to the engine (-1: fixed, ignored or foreign joint)."""
         return int(lib.mecano_model_table_row(self._model.h, joint._id))
@@ -420,6 +435,27 @@ class MultiBodySystem:
             out["dof_off"][i] = self._provider._dof[i]
             out["cfg_off"][i] = self._provider._cfg[i]
         return out
+
+
+class _ExpandedSystem:
+    def __init__(self, system):
+        m = system._model
+        self._system = system  # keeps the model (owner of the tables) alive
+        self._desc = lib.mecano_model_expanded_tables(m.h)
+        if not self._desc:
+            raise ScrewTheoryException(lib.mecano_model_last_error(m.h).decode())
+        v = [ctypes.c_int32() for _ in range(4)]
+        m.check(lib.mecano_model_expanded_info(m.h, *(ctypes.byref(x) for x in v)))
+        self.n_bodies, self.n_extra_dof, self.n_extra_cfg, self.n_extra_wrench_blocks = (int(x.value) for x in v)
+        self.q_extra = np.zeros(max(1, self.n_extra_cfg))
+        self.locked = np.zeros(self.n_bodies, np.int32)
+        self.row_of_considered = np.zeros(max(1, system.getNumberOfJoints()), np.int32)
+        m.check(lib.mecano_model_expanded_fill(m.h, self.q_extra.ctypes.data_as(_dp), self.locked.ctypes.data_as(_ip), self.row_of_considered.ctypes.data_as(_ip)))
+        self.q_extra = self.q_extra[:self.n_extra_cfg]
+        self.row_of_considered = self.row_of_considered[:system.getNumberOfJoints()]
+
+    def tables(self):
+        return self._desc
 
 
 class MultiBodySystemRandomTools:

@@ -90,7 +90,8 @@ def main():
         q, qd, x = states(s, n, dev, 1000 + rank)
         res = torch.empty_like(qd)
         for variant in variants:
-            calcs = {"rnea": mb.InverseDynamicsCalculator(s), "aba": mb.ForwardDynamicsCalculator(s), "crba": mb.CompositeRigidBodyMassMatrixCalculator(s)}
+            calcs = {"rnea": mb.InverseDynamicsCalculator(s, device=local), "aba": mb.ForwardDynamicsCalculator(s, device=local),
+                     "crba": mb.CompositeRigidBodyMassMatrixCalculator(s, device=local)}
             try:
                 for c in calcs.values():
                     c.setKernelVariant(variant)

@@ -209,3 +209,135 @@ def test_welded_systems_match_full_tree_with_held_joints_gpu(idx):
     if CASES[idx]["mode"] == "ignore":
         held = held_closure(full, held)
     check_pair(welded, full, held, run_gpu, n=64, seed=idx)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# External wrenches and per-body results on systems with fixed / ignored joints (InverseDynamicsCalculator.java:469-472, :578-602
+# with :832-860): the calculators run them on the expanded tables (MultiBodySystem.expanded(): nothing welded, the fixed /
+# ignored joints held).  Checked against the oracle on the FULL tree with the held joints kept still, as above.
+def _extended(m, extra, fill=None):
+    out = np.zeros((m.shape[0] + extra, m.shape[1]))
+    out[:m.shape[0]] = m
+    if extra and fill is not None:
+        out[m.shape[0]:] = np.asarray(fill)[:, None]
+    return out
+
+
+def wrenches_emu(welded, q, qd, qdd, tau, fext):
+    """What calculators.py does for such a call, by hand, on the kernel source compiled for the host."""
+    x = welded.expanded()
+    n = q.shape[1]
+    nv, nj = welded.getNumberOfDoFs(), welded.getNumberOfJoints()
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int32)
+    P = lambda a: np.ascontiguousarray(a).ctypes.data_as(dp)  # noqa: E731
+    g = np.ascontiguousarray(G, dtype=np.float64)
+    err = ctypes.create_string_buffer(256)
+    q2, qd2, qdd2, tau2 = _extended(q, x.n_extra_cfg, x.q_extra), _extended(qd, x.n_extra_dof), _extended(qdd, x.n_extra_dof), _extended(tau, x.n_extra_dof)
+    f2 = _extended(fext, 6 * x.n_extra_wrench_blocks)
+    rows2 = 6 * (nj + x.n_extra_wrench_blocks)
+    out, acc, wr = np.full((nv + x.n_extra_dof, n), np.nan), np.full((rows2, n), np.nan), np.full((rows2, n), np.nan)
+    tb = ctypes.cast(x.tables(), ctypes.c_void_p)
+    rc = el.lib().emu_rnea_full(tb, P(g), ctypes.c_long(n), ctypes.c_long(n), P(q2), P(qd2), P(qdd2), P(f2), P(out), P(acc), P(wr), ctypes.c_uint(0), err, 256)
+    assert rc == 0, err.value.decode()
+    qdd_fd = np.full((nv + x.n_extra_dof, n), np.nan)
+    locked = np.ascontiguousarray(x.locked, dtype=np.int32)
+    rc = el.lib().emu_aba_sources(tb, P(g), ctypes.c_long(n), ctypes.c_long(n), P(q2), P(qd2), P(tau2), P(np.zeros_like(qd2)), P(f2), locked.ctypes.data_as(ip),
+                                  P(qdd_fd), err, 256)
+    assert rc == 0, err.value.decode()
+    return out[:nv], acc[:6 * nj], wr[:6 * nj], qdd_fd[:nv]
+
+
+def wrenches_gpu(welded, q, qd, qdd, tau, fext):
+    import torch
+
+    import mecano_b200 as mb
+
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    ident = mb.InverseDynamicsCalculator(welded).setComputeByProducts()
+    ident.setGravitationalAcceleration(*G)
+    ident.setExternalWrenches(t(fext))
+    tau_d = ident.compute(t(q), t(qd), t(qdd)).cpu().numpy()
+    acc_d, wr_d = ident.getBodyAccelerationMatrix().cpu().numpy(), ident.getComputedJointWrenchMatrix().cpu().numpy()
+    # host matrices through the same calculator: the same kernels
+    ident.setExternalWrenches(fext)
+    tau_h = ident.compute(q, qd, qdd)
+    assert np.array_equal(tau_h, tau_d) and np.array_equal(ident.getBodyAccelerationMatrix(), acc_d) and np.array_equal(ident.getComputedJointWrenchMatrix(), wr_d)
+    # getters of the reference API
+    j = welded.getJointsToConsider()[-1]
+    k = welded.getAllJoints().index(j)
+    assert np.array_equal(ident.getComputedJointWrench(j), wr_d[6 * k:6 * k + 6]) and np.array_equal(ident.getBodyAcceleration(j.getSuccessor()), acc_d[6 * k:6 * k + 6])
+    fdyn = mb.ForwardDynamicsCalculator(welded)
+    fdyn.setGravitationalAcceleration(*G)
+    fdyn.setExternalWrenches(t(fext))
+    qdd_fd = fdyn.compute(t(q), t(qd), t(tau)).cpu().numpy()
+    return tau_d, acc_d, wr_d, qdd_fd
+
+
+def check_pair_wrenches(welded, full, held, run, n=4, seed=0):
+    import mecano_b200 as mb
+
+    rng = np.random.default_rng(100 + seed)
+    t_full = td.TreeDesc(**full.describe()).contiguous()
+    oracle = ol.Oracle(t_full, gravity=G)
+    qf, qdf, qddf, tauf = mb.MultiBodySystemRandomTools.nextState(rng, full, n)
+    pw, pf = welded.getJointMatrixIndexProvider(), full.getJointMatrixIndexProvider()
+    by_name = {j.getName(): j for j in full.getJointsToConsider()}
+    full_index = {j.getName(): i for i, j in enumerate(full.getJointsToConsider())}
+    for name, q0 in held.items():
+        r, c = pf.getJointDoFIndices(by_name[name])[0], pf.getJointConfigurationIndices(by_name[name])[0]
+        qf[c], qdf[r], qddf[r] = q0, 0.0, 0.0
+    rows_w, rows_f, cfg_w, cfg_f = [], [], [], []
+    for j in welded.getJointsToConsider():
+        rows_w += pw.getJointDoFIndices(j)
+        cfg_w += pw.getJointConfigurationIndices(j)
+        if j.getDegreesOfFreedom() > 0:
+            rows_f += pf.getJointDoFIndices(by_name[j.getName()])
+            cfg_f += pf.getJointConfigurationIndices(by_name[j.getName()])
+    nvw, nqw, njw = welded.getNumberOfDoFs(), welded.getConfigurationMatrixSize(), welded.getNumberOfJoints()
+    qw, qdw, qddw, tauw = np.zeros((nqw, n)), np.zeros((nvw, n)), np.zeros((nvw, n)), np.zeros((nvw, n))
+    qw[cfg_w], qdw[rows_w], qddw[rows_w], tauw[rows_w] = qf[cfg_f], qdf[rows_f], qddf[rows_f], tauf[rows_f]
+    # a wrench on every body the welded system knows (the successors of FixedJoints included), none on ignored bodies
+    fext_w = rng.uniform(-1, 1, size=(6 * njw, n))
+    fext_f = np.zeros((6 * t_full.nb, n))
+    blocks_f = []
+    for k, j in enumerate(welded.getJointsToConsider()):
+        i = full_index[j.getName()]
+        fext_f[6 * i:6 * i + 6] = fext_w[6 * k:6 * k + 6]
+        blocks_f += list(range(6 * i, 6 * i + 6))
+    tau, acc, wr, qdd_fd = run(welded, qw, qdw, qddw, tauw, fext_w)
+
+    def err(a, b):
+        return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
+
+    assert not (np.isnan(tau).any() or np.isnan(acc).any() or np.isnan(wr).any() or np.isnan(qdd_fd).any())
+    M_ref = oracle.crba_batch(qf)
+    bias = oracle.rnea_batch(qf, qdf, np.zeros_like(qddf), fext_f)
+    for s in range(n):
+        tau_o, acc_o, wr_o = oracle.rnea_full(qf[:, s], qdf[:, s], qddf[:, s], np.ascontiguousarray(fext_f[:, s].reshape(t_full.nb, 6)))
+        assert err(tau[rows_w, s], tau_o[rows_f]) < 1e-10
+        assert err(acc[:, s], acc_o.reshape(-1)[blocks_f]) < 1e-10  # every considered body, in its own CoM frame
+        assert err(wr[:, s], wr_o.reshape(-1)[blocks_f]) < 1e-10    # every considered joint, FixedJoints included
+        ref = np.linalg.solve(M_ref[np.ix_(rows_f, rows_f)][:, :, s], tauf[rows_f, s] - bias[rows_f, s])
+        assert err(qdd_fd[rows_w, s], ref) < 1e-8
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_wrenches_and_byproducts_on_welded_systems_emulated(idx):
+    welded, full, held = build_pair(**CASES[idx])
+    if CASES[idx]["mode"] == "ignore":
+        held = held_closure(full, held)
+    x = welded.expanded()
+    assert x.n_bodies == full.getNumberOfJoints() and int(x.locked.sum()) == len(held)
+    assert x.n_extra_dof == len(held) and x.n_extra_cfg == len(held)
+    assert x.n_extra_wrench_blocks == (len(held) if CASES[idx]["mode"] == "ignore" else 0)
+    check_pair_wrenches(welded, full, held, wrenches_emu, seed=idx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", range(len(CASES)))
+def test_wrenches_and_byproducts_on_welded_systems_gpu(idx):
+    welded, full, held = build_pair(**CASES[idx])
+    if CASES[idx]["mode"] == "ignore":
+        held = held_closure(full, held)
+    check_pair_wrenches(welded, full, held, wrenches_gpu, n=33, seed=idx)
