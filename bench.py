@@ -494,6 +494,25 @@ def main():
                                        "what": "CompositeRigidBodyMassMatrixCalculator.getMassMatrix(q) into the calculator's own matrix: the "
                                                "%d structurally zero entries are written once, not per call (MECANO_B200_CRBA_ZEROS_PRESENT)" % (nv * nv - nnz)}
         del owned
+        # the packed layout on the device (the end-to-end number with it is extras.e2e_packed)
+        pk = mb.CompositeRigidBodyMassMatrixCalculator(system, device=local_rank)
+        prow, _ = pk.getMassMatrixPackedIndex()
+        Pk = torch.empty((len(prow), n), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            pk.getMassMatrix(q, Pk, packed=True)
+        e0.record()
+        for _ in range(reps):
+            pk.getMassMatrix(q, Pk, packed=True)
+        e1.record()
+        torch.cuda.synchronize()
+        pms = e0.elapsed_time(e1) / reps
+        pbytes = 8.0 * (nq + len(prow))
+        extras["crba_packed"] = {"ms": pms, "states_per_s": n / (pms * 1e-3), "algorithmic_bytes_per_state": pbytes,
+                                 "achieved_gbs": pbytes * n / (pms * 1e-3) / 1e9, "hbm_frac": pbytes * n / (pms * 1e-3) / 1e9 / hbm_peak,
+                                 "packed_rows": len(prow), "entries": nv * nv,
+                                 "what": "getMassMatrix(q, packed=True): the unique entries that are not structurally zero (MECANO_B200_CRBA_PACKED), "
+                                         "bit-identical to the dense matrix's entries"}
+        del pk, Pk
 
         def timed(fn):
             for _ in range(3):

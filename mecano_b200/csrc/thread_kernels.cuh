@@ -11,7 +11,7 @@ namespace mb
 // LAYOUT (CRBA): 0 entry-major, 1 state-major, 2 packed (unique non-zero entries, entry-major rows)
 // M3: the instantiation handles three-DoF joints (SphericalJoint, PlanarJoint; multidof.cuh)
 template <int ALGO, bool FEXT, int LAYOUT, int BLOCK, int AUXN, int RECN, int TM, bool M3>
-__global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
+__device__ __forceinline__ void thread_kernel_body(const MbProgram &P, const KernelArgs &a)
 {
    constexpr bool STATE_MAJOR = LAYOUT == 1;
    const int ncst = P.nb * MB_CONST_STRIDE;
@@ -29,7 +29,11 @@ __global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ M
          coriolis_state<double, Ctx>(P, c2);
    });
 }
-
+template <int ALGO, bool FEXT, int LAYOUT, int BLOCK, int AUXN, int RECN, int TM, bool M3>
+__global__ void __launch_bounds__(BLOCK) thread_kernel(const __grid_constant__ MbProgram P, const KernelArgs a)
+{
+   thread_kernel_body<ALGO, FEXT, LAYOUT, BLOCK, AUXN, RECN, TM, M3>(P, a);
+}
 // The optional fp32 variant (f32_ctx.cuh): same skeleton, constant records staged as floats, the per-state routines instantiated
 // with T = float.  Plain calls only (no external wrenches / by-products), one launch configuration per algorithm.
 template <int ALGO, int BLOCK, int AUXN, int RECN, int TM>

@@ -110,15 +110,17 @@ def main():
             nc = min(n, CHUNK)
             M = torch.empty((nv * nv, nc), dtype=torch.float64, device=dev)
             chunks = [(o, min(nc, n - o)) for o in range(0, n, nc)]
+            # (all matrices of one call share their leading dimension: a chunk of q gets its own contiguous copy, outside the timing)
+            qs = [q] if len(chunks) == 1 else [q[:, o:o + m].contiguous() for o, m in chunks]
 
             def crba_all():
-                for o, m in chunks:
-                    calcs["crba"].getMassMatrix(q[:, o:o + m], M[:, :m])
+                for (o, m), qc in zip(chunks, qs):
+                    calcs["crba"].getMassMatrix(qc, M[:, :m] if m == nc else M[:, :m].contiguous())
 
             ms = timed(crba_all, max(3, reps // len(chunks)), world)
             rec["crba_ms"], rec["crba_states_per_s"], rec["crba_chunks"] = ms, B / ms * 1e3, len(chunks)
             rec["step_states_per_s"] = B / (rec["rnea_ms"] + rec["aba_ms"] + rec["crba_ms"]) * 1e3
-            del M
+            del M, qs
             if variant != "warp" and sweep == "batch" and n > CHUNK:
                 # the packed non-zero layout holds the whole batch
                 row, _ = calcs["crba"].getMassMatrixPackedIndex()
