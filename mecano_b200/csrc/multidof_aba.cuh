@@ -37,6 +37,9 @@ MB_HD void aba_ascend_3dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
       c.rec_st2(r + 0, sv_get(qdd6, J[0]), sv_get(qdd6, J[1]));
       c.rec_st2(r + 1, sv_get(qdd6, J[2]), (T)0);
       c.rec_st2(r + 2, (T)0, (T)0);
+      c.rec_st2(rec_hi + 0, (T)0, (T)0); // (pass three reads the whole record before it looks at the flag)
+      c.rec_st2(rec_hi + 1, (T)0, (T)0);
+      c.rec_st2(rec_hi + 2, (T)0, (T)0);
       if (!(o.flags & MB2_ROOT_PARENT))
       {
          const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
