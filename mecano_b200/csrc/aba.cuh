@@ -381,10 +381,14 @@ template <class T, class Ctx, bool LOCKS> MB_HD void aba_pass3_6dof(Ctx &c, cons
 MB_HD int aba_pf_mask(const MbOp2 &o) { return MB2_JT(o.code) == MB_SIXDOF ? 0 : ((o.code & MB2_ASCEND) ? 6 : 3); }
 
 // ---- the part of an op of passes one + two that does not depend on its kind (see rnea_pre)
+// rev1: op k is a revolute DESCEND (its sin/cos were evaluated during the previous op from the raw angle still in pp.mq: rnea_pre)
 template <class T, class Ctx>
-MB_HD void aba_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const bool asc, SvT<T> &v, AbaPipe<T> &pp)
+MB_HD void aba_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const bool asc, const bool rev1, SvT<T> &v, AbaPipe<T> &pp)
 {
-   c.stk_fence();
+   if (rev1 && mb_angle_large(pp.mq))
+      mb_sincos_redo(pp.mq, pp.s, pp.c);
+   if (asc)
+      c.stk_fence(); // an ASCEND reads its twist back from the wide stack (a DESCEND only when it reloads its parent's, below)
    if (o.pf & (MB2_PF_D1 | MB2_PF_A1))
       c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, (o.pf & MB2_PF_A1) ? 6 : 3);
    c.pf_commit();
@@ -397,14 +401,17 @@ MB_HD void aba_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const
          pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
    }
    if (o.pf & MB2_PF_NEXT1)
-      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+      pp.mq = c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0); // raw: checked when op k + 1 starts
    // twist of the parent: carried along a chain, zero for the root body, otherwise on the parent's stack slot
    if (!asc && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
    {
       if (o.flags & MB2_ROOT_PARENT)
          v = sv_zero<T>();
       else
+      {
+         c.stk_fence();
          c.acc_ld(o.pslot, o.pwslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
+      }
    }
 }
 
@@ -413,7 +420,7 @@ template <class T, class Ctx, bool FEXT>
 MB_HD void aba_op(Ctx &c, const int k, const MbOp2 o, const int ext, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
 {
    c.op_sync(k);
-   aba_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, (o.code & MB2_ASCEND) != 0, v, pp);
+   aba_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, (o.code & MB2_ASCEND) != 0, !(o.code & MB2_ASCEND) && MB2_JT(o.code) == MB_REVOLUTE, v, pp);
    T ns = pp.mq, nc = (T)1;
    switch (o.code & 0xfu)
    {
@@ -455,9 +462,9 @@ MB_HD void aba_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT
    c.template pf_wait<0>();
    if (mb2_is_1dof_descend(o0))
    {
-      const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
-      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
-      else pp.s = q0;
+      const T q0 = c.pf_ld(0, 0);
+      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &pp.s, &pp.c);
+      else pp.s = q0; // a prismatic displacement is not an angle
    }
 }
 
@@ -477,22 +484,23 @@ MB_HD void aba_pass3_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o
    c.pf3_issue(2, o2.cfg, o2.dof, o2.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o2) ? 3 : 0);
    c.pf_commit();
    c.template pf_wait<0>();
-   pp.s = (T)0;
+   pp.s = pp.mq = (T)0;
    pp.c = (T)1;
    if (mb2_is_1dof_descend(o0))
    {
       T q0, qd0;
       c.pf3_ld2(0, 0, q0, qd0);
-      q0 = mb_reduce_angle(q0);
-      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
+      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &pp.s, &pp.c);
       else pp.s = q0;
    }
 }
 
 // ---- the kind-independent part of a pass-three op
 template <class T, class Ctx>
-MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const bool rev1, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
+   if (rev1 && mb_angle_large(pp.mq))
+      mb_sincos_redo(pp.mq, pp.s, pp.c);
    c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, o.pfbody * (MB_ABA_REC / 2), (o.pf & MB2_PF_D1) ? 3 : 0);
    c.pf_commit();
    c.template pf_wait<MB_PF_DIST - 1>();
@@ -506,8 +514,7 @@ MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof,
    if (o.pf & MB2_PF_NEXT1)
    {
       T qdn;
-      c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn);
-      pp.mq = mb_reduce_angle(pp.mq);
+      c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn); // raw: checked when op k + 1 starts
    }
    if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
    {
@@ -529,7 +536,7 @@ template <class T, class Ctx, bool LOCKS = false>
 MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
    c.op_sync(k);
-   aba_pass3_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, grav, v, a, pp);
+   aba_pass3_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, MB2_JT(o.code) == MB_REVOLUTE, grav, v, a, pp);
    const int st = k & (MB_PF_STAGES - 1);
    T ns = pp.mq, nc = (T)1;
    switch (o.code & 0xfu)
@@ -548,19 +555,34 @@ MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T
    pp.c = nc;
 }
 
-// ---- run steps: as aba_op / aba_pass3_op with the kind (ASCEND / joint type) fixed at compile time (see rnea.cuh); whether
-// the op also evaluates the sin/cos of the next joint (SC) is tested at run time, so that a run covers both
+// ---- run steps: as aba_op / aba_pass3_op with the kind (ASCEND / joint type) fixed at compile time (see rnea.cuh).  Whether
+// the op also evaluates the sin/cos of the next joint (SC) is part of the kind for the small ops -- DESCEND and pass three, where
+// the sin/cos chain then shares a basic block with the op's own arithmetic instead of running serially in front of it -- and
+// tested at run time for the large ASCEND ops (one loop body per joint type: their code has to stay in the instruction cache)
 template <class T, class Ctx, bool FEXT, int KIND>
 MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT<T> &acc, SvT<T> &pacc, AbaPipe<T> &pp)
 {
-   constexpr bool ASC = (KIND & MB2_ASCEND) != 0;
+   constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SCK = (KIND & MB2_SC) != 0, PLAIN = (KIND & MB_RUN_PLAIN) != 0;
    constexpr int JT = (KIND >> 1) & 3;
-   const MbOp2 o = P.op2[k];
-   aba_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, ASC, v, pp);
+   static_assert(!(ASC && SCK), "ASCEND kinds do not carry the SC bit");
+   MbOp2 o = P.op2[k];
+   // plain runs (rnea.cuh: rnea_run_step): the flags of the op are those of the common case of its kind, i.e. constants
+   if (!ASC && SCK)
+      o.pf |= MB2_PF_NEXT1;
+   if (PLAIN)
+   {
+      o.flags = (uint8_t)mb_run_plain_flags(MB_ABA, KIND & 0xf, false);
+      if (!ASC && !SCK)
+         o.pf &= (uint8_t)~MB2_PF_NEXT1;
+   }
+   aba_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, ASC, !ASC && JT == MB_REVOLUTE, v, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
-   if (o.code & MB2_SC)
-      mb_sincos(pp.mq, &ns, &nc);
+   if (ASC || JT == MB_SIXDOF)
+   {
+      if (ASC ? (o.code & MB2_SC) != 0 : SCK)
+         mb_sincos(pp.mq, &ns, &nc);
+   }
    if (JT == MB_SIXDOF)
    {
       if (ASC) aba_ascend_6dof<T, Ctx, FEXT>(c, o, ext, P.body[o.body].rec, acc, pacc);
@@ -569,7 +591,7 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
    else if (ASC)
       aba_ascend_1dof<T, Ctx, FEXT, JT == MB_REVOLUTE, false>(c, o, ext, v, acc, pacc, pp, ns, nc);
    else
-      aba_descend_1dof<T, Ctx, JT == MB_REVOLUTE, false>(c, o, v, pp, ns, nc);
+      aba_descend_1dof<T, Ctx, JT == MB_REVOLUTE, SCK>(c, o, v, pp, ns, nc);
    pp.s = ns;
    pp.c = nc;
 }
@@ -578,16 +600,27 @@ template <class T, class Ctx, bool LOCKS, int KIND>
 MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
    constexpr int JT = (KIND >> 1) & 3;
-   const MbOp2 o = P.op3[k];
-   aba_pass3_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, grav, v, a, pp);
+   constexpr bool SCK = (KIND & MB2_SC) != 0, PLAIN = (KIND & MB_RUN_PLAIN) != 0;
+   MbOp2 o = P.op3[k];
+   if (SCK)
+      o.pf |= MB2_PF_NEXT1;
+   if (PLAIN)
+   {
+      o.flags = (uint8_t)mb_run_plain_flags(MB_ABA, KIND & 0xf, true);
+      if (!SCK)
+         o.pf &= (uint8_t)~MB2_PF_NEXT1;
+   }
+   aba_pass3_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, JT == MB_REVOLUTE, grav, v, a, pp);
    const int st = k & (MB_PF_STAGES - 1);
    T ns = pp.mq, nc = (T)1;
-   if (o.code & MB2_SC)
-      mb_sincos(pp.mq, &ns, &nc);
    if (JT == MB_SIXDOF)
+   {
+      if (SCK)
+         mb_sincos(pp.mq, &ns, &nc);
       aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, P.body[o.body].rec, v, a);
+   }
    else
-      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, false, LOCKS>(c, o, st, v, a, pp, ns, nc);
+      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, SCK, LOCKS>(c, o, st, v, a, pp, ns, nc);
    pp.s = ns;
    pp.c = nc;
 }
@@ -613,6 +646,8 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       switch (R.kind)
       {
          MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
+         MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
+         MB_RUN_CASE(MB_RUN_PLAIN | 0) MB_RUN_CASE(MB_RUN_PLAIN | 1) MB_RUN_CASE(MB_RUN_PLAIN | 8)
          default: break;
       }
 #undef MB_RUN_CASE
@@ -632,7 +667,8 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       break;
       switch (R.kind)
       {
-         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4)
+         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4) MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
+         MB_RUN_CASE(MB_RUN_PLAIN | 0) MB_RUN_CASE(MB_RUN_PLAIN | 8)
          default: break;
       }
 #undef MB_RUN_CASE

@@ -18,6 +18,7 @@
 #include "kernels.h"
 #include "specialize.h"
 
+#define MB_STAGGER_NS_DEFAULT 0
 #define MB_ABA_DISCARD_DEFAULT 1 // profiles/r04b_aba_records.md: 1.713 -> 1.696 ms, DRAM writes 2.46 -> 1.82 GB per 2^20 H37 states
 #define MB_MAX_SLOTS 4
 
@@ -252,6 +253,11 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       if (discard) a.flags |= MB_KFLAG_ABA_DISCARD;
    }
    a.nv = h->tree.nv;
+   {
+      // MECANO_B200_STAGGER_NS overrides the start offset between the warps of a scheduler (gpu_ctx.cuh: thread_block_run)
+      static const int stagger = [] { const char *e = getenv("MECANO_B200_STAGGER_NS"); return e ? atoi(e) : MB_STAGGER_NS_DEFAULT; }();
+      a.stagger_ns = stagger;
+   }
    if (use_spec)
    {
       const long long ntiles = (n + sk.opt.block - 1) / sk.opt.block;

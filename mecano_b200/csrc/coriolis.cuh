@@ -283,11 +283,11 @@ template <class T, class Ctx> MB_HD void coriolis_state(const MbProgram &P, Ctx 
          }
          else
          {
-            const T q = mb_reduce_angle(c.ld_q(o.cfg)), qd = c.ld_qd(o.dof);
+            const T q = c.ld_q(o.cfg), qd = c.ld_qd(o.dof);
             XfT<T> X;
             if (jt == MB_REVOLUTE)
             {
-               mb_sincos(q, &ls, &lc);
+               mb_sincos(mb_reduce_angle(q), &ls, &lc);
                X = joint_xf_1dof<T, true>(C, ls, lc);
                v = motion_to_child(X, v);
                v.a.z += qd;

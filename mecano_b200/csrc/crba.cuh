@@ -146,9 +146,9 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
       const MbOp2 o0 = P.op2[0];
       if (mb2_is_1dof_descend(o0))
       {
-         const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
-         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &s, &cs);
-         else s = q0;
+         const T q0 = c.pf_ld(0, 0);
+         if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &s, &cs);
+         else s = q0; // a prismatic displacement is not an angle
       }
    }
 #pragma unroll 1
@@ -164,10 +164,10 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
       c.template pf_wait<MB_PF_DIST - 1>();
       mq = (T)0;
       if (o.pf & MB2_PF_NEXT1)
-         mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0));
+         mq = c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0);
       T ns = mq, nc = (T)1;
       if (o.code & MB2_SC)
-         mb_sincos(mq, &ns, &nc);
+         mb_sincos(mb_reduce_angle(mq), &ns, &nc);
       const int jt = MB2_JT(o.code);
       const auto C = c.cst(o.body);
       if (!(o.code & MB2_ASCEND))

@@ -121,6 +121,41 @@ int slot2_size(int algo, int jtype, bool root_parent)
    }
 }
 
+// Runs of consecutive ops of the same kind (MbRun).  RNEA runs are split by the SC bit (its routines schedule the sin/cos of the
+// next joint inside the op's basic block).  ABA splits only its small ops (DESCEND, pass three) that way; its ASCEND ops are large,
+// the SC test there is a warp-uniform branch taken a few times per state, and one loop body per joint type keeps the hot code of
+// the kernel inside the instruction cache (no_instructions was 12.8 % of the stall samples with SC-split ASCEND runs).  Runs whose
+// ops all carry the common flags of their kind are marked MB_RUN_PLAIN (program.h).
+void build_runs(int algo, MbProgram &P, int n3)
+{
+   auto make_runs = [algo](const MbOp2 *ops, int n, MbRun *runs, bool pass3) {
+      int nr = 0;
+      for (int k = 0; k < n; k++)
+      {
+         uint8_t kind = ops[k].code & ((algo == MB_ABA && (ops[k].code & MB2_ASCEND)) ? 0x7u : 0xfu);
+         const unsigned tested = mb_run_plain_tested(algo, kind, pass3);
+         if (tested)
+         {
+            const bool next1 = (ops[k].pf & MB2_PF_NEXT1) != 0, sc = (kind & MB2_SC) != 0;
+            if ((ops[k].flags & tested) == (mb_run_plain_flags(algo, kind, pass3) & tested) && (!mb_run_kind_has_sc(algo, kind) || next1 == sc))
+               kind |= MB_RUN_PLAIN;
+         }
+         if (nr > 0 && runs[nr - 1].kind == kind && runs[nr - 1].n < 255)
+            runs[nr - 1].n++;
+         else
+         {
+            runs[nr].kind = kind;
+            runs[nr].n = 1;
+            runs[nr].k0 = (uint16_t)k;
+            nr++;
+         }
+      }
+      return nr;
+   };
+   P.nruns = make_runs(P.op2, P.nops, P.run, false);
+   P.nruns3 = make_runs(P.op3, n3, P.run3, true);
+}
+
 // Pre-decode the op words into MbOp2 records (program.h).
 void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
 {
@@ -253,29 +288,8 @@ void build_op2(int algo, MbProgram &P, const std::vector<int> &nchild)
    };
    look_ahead(P.op2, P.nops);
    look_ahead(P.op3, n3);
-   // RNEA runs are split by the SC bit (its routines schedule the sin/cos of the next joint inside the op's basic block); ABA
-   // runs are not: its ops are large, the SC test is a warp-uniform branch, and half as many loop bodies keep the hot code of
-   // the kernel inside the instruction cache (no_instructions was 12.8 % of the stall samples with SC-split runs)
-   const uint8_t kind_mask = algo == MB_ABA ? 0x7u : 0xfu;
-   auto make_runs = [kind_mask](const MbOp2 *ops, int n, MbRun *runs) {
-      int nr = 0;
-      for (int k = 0; k < n; k++)
-      {
-         const uint8_t kind = ops[k].code & kind_mask;
-         if (nr > 0 && runs[nr - 1].kind == kind && runs[nr - 1].n < 255)
-            runs[nr - 1].n++;
-         else
-         {
-            runs[nr].kind = kind;
-            runs[nr].n = 1;
-            runs[nr].k0 = (uint16_t)k;
-            nr++;
-         }
-      }
-      return nr;
-   };
-   P.nruns = make_runs(P.op2, P.nops, P.run);
-   P.nruns3 = make_runs(P.op3, n3, P.run3);
+   P.nruns3 = n3; // (the number of pass-three ops until build_runs() replaces it by the number of runs)
+   build_runs(algo, P, n3);
 }
 } // namespace
 
@@ -670,6 +684,7 @@ int apply_source_modes(FlatTree &t, const int32_t *accel_source, std::vector<std
          P.op2[k].flags = (uint8_t)((P.op2[k].flags & ~MB2_ACCSRC) | (locked[P.op2[k].body] ? MB2_ACCSRC : 0u));
    for (int k = 0; k < P.nb; k++) // pass three: one record per body
       P.op3[k].flags = (uint8_t)((P.op3[k].flags & ~MB2_ACCSRC) | (locked[P.op3[k].body] ? MB2_ACCSRC : 0u));
+   build_runs(MB_ABA, P, P.nb); // a locked joint is not a plain op
    // DoF rows of the joints that stay EFFORT_SOURCE, as runs of consecutive rows
    std::vector<char> effort((size_t)t.nv, 1);
    for (int i = 0; i < t.nb; i++)

@@ -379,6 +379,12 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    // persistent grid: each block walks over tiles of BLOCK states.  The per-state areas (stack, rings) are private to a
    // thread and the constant records are read-only, so the threads of a block never synchronise again.
    const long long ntiles = (a.n + BLOCK - 1) / BLOCK;
+   // The warps of a block start together and run the same op sequence, so the warps that share a scheduler (warp % 4) would
+   // stay in phase for good: all of them in the FP64 burst of an op at once (pipe-bound, issue slots idle), then all of them in
+   // its bookkeeping (issue-bound, FP64 pipe idle).  Contention slows them down equally, so an offset given once persists:
+   // slot j of a scheduler starts j * stagger_ns late and the bursts of one warp overlap the bookkeeping of another.
+   if (a.stagger_ns > 0)
+      __nanosleep((threadIdx.x >> 7) * (unsigned)a.stagger_ns);
    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
    {
       long long s = tile * BLOCK + threadIdx.x;

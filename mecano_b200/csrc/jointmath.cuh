@@ -115,6 +115,38 @@ MB_HD double mb_reduce_angle(double x)
 }
 MB_HD float mb_reduce_angle(float x) { return x; }
 
+// The same safeguard off the critical path (RNEA / ABA thread-per-state kernels): the fast sincos is evaluated on the raw
+// angle inside the previous op; when the op that uses it starts -- a basic-block boundary anyway -- the angle is tested with
+// an integer compare on its high word (|x| >= 1e5, NaN and infinities included) and, if it was out of the fast range, sin/cos
+// are redone by the library routine (exact argument reduction, like Java's Math.sin / cos).  A test in front of the sincos costs
+// the latency of the shared-memory load and of a DSETP at the top of every op.
+MB_HD bool mb_angle_large(double x)
+{
+#if defined(__CUDA_ARCH__)
+   return (unsigned)(__double2hiint(x) & 0x7fffffff) >= 0x40F86A00u;
+#else
+   return !(fabs(x) < MB_SINCOS_FAST_LIMIT);
+#endif
+}
+template <class T> MB_HD bool mb_angle_large(T) { return false; } // float: sincosf covers every magnitude
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ static double2 mb_sincos_slow2(double x) // by value: an address-taken sin/cos would live in local memory
+{
+   double2 r;
+   sincos(x, &r.x, &r.y);
+   return r;
+}
+MB_HD void mb_sincos_redo(double x, double &s, double &c)
+{
+   const double2 r = mb_sincos_slow2(x);
+   s = r.x;
+   c = r.y;
+}
+#else
+inline void mb_sincos_redo(double x, double &s, double &c) { s = sin(x); c = cos(x); }
+#endif
+template <class T> MB_HD void mb_sincos_redo(T, T &, T &) {}
+
 // Reciprocal without the library's special-case branch (which would split the basic block of an ABA op): hardware
 // seed (rcp.approx.ftz.f64, ~2^-20) + three Newton steps.  Used for the joint-space inertia D = S^T I^A S of a
 // 1-DoF joint, a well-scaled positive number.

@@ -30,6 +30,7 @@ struct KernelArgs
    double grav[3];
    uint32_t flags;
    int32_t nv;
+   int32_t stagger_ns; // thread-per-state kernels: warp slot j of a scheduler (warp / 4) starts j * stagger_ns late (gpu_ctx.cuh)
 };
 
 } // namespace mb

@@ -130,9 +130,48 @@ struct MbWalk
 // A run: consecutive ops of the same kind (code & 0xf: ASCEND bit, joint type, SC bit).  The kernels execute a run as one
 // tight loop over a routine specialised on the kind, instead of dispatching every op through a switch: the loop-carried
 // spatial quantities then stay in the same registers from op to op (the per-op switch cost ~40 register moves per op).
+// MB_RUN_PLAIN: all ops of the run carry the flags of the common case of their kind (and no one-DoF DESCEND follows unless the SC
+// bit says so), which the run loops then treat as compile-time constants.  Only for the kinds mb_run_has_plain() names.
+#define MB_RUN_PLAIN 0x10u
+// the flags a kind tests (rnea.cuh / aba.cuh), 0 if the kind has no plain form.  kind = MbOp2::code & 0xf; pass3: ABA pass-three list.
+// Plain forms exist for revolute joints: the DESCEND of an interior body (SC set: the next joint of the chain is revolute too), the
+// DESCEND of a leaf (no SC: its own ASCEND follows) and the ASCEND of an interior body with a single child.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline unsigned mb_run_plain_tested(int algo, int kind, bool pass3)
+{
+   if (algo == 0 /* MB_RNEA */)
+      return (kind == 0 || kind == 8) ? (MB2_LEAF | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ROOT_PARENT)
+                                      : (kind == 1 ? (MB2_LEAF | MB2_ROOT_PARENT | MB2_STORE_ACC) : 0u);
+   if (algo == 1 /* MB_ABA */)
+   {
+      if (pass3)
+         return (kind == 0 || kind == 8) ? (MB2_ROOT_PARENT | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ACCSRC) : 0u;
+      return (kind == 0 || kind == 8) ? (MB2_LEAF | MB2_LOAD_PARENT | MB2_ROOT_PARENT)
+                                      : (kind == 1 ? (MB2_LEAF | MB2_ROOT_PARENT | MB2_FIRST_CHILD | MB2_STORE_ACC | MB2_ACCSRC) : 0u);
+   }
+   return 0u;
+}
+// MbOp2::flags of a plain op (bits outside mb_run_plain_tested are don't-cares)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline unsigned mb_run_plain_flags(int algo, int kind, bool pass3)
+{
+   (void)algo;
+   if (pass3)
+      return 0u;
+   return kind == 0 ? MB2_LEAF : (kind == 1 ? MB2_FIRST_CHILD : 0u);
+}
+// whether the kind says if a one-DoF DESCEND follows (SC bit part of the kind; ABA keeps it out of its ASCEND kinds)
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline bool mb_run_kind_has_sc(int algo, int kind) { return !(algo == 1 /* MB_ABA */ && (kind & MB2_ASCEND)); }
 struct MbRun
 {
-   uint8_t kind; // MbOp2::code & 0xf
+   uint8_t kind; // MbOp2::code & 0xf | MB_RUN_PLAIN
    uint8_t n;    // number of ops
    uint16_t k0;  // first op
 };

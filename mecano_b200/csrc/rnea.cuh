@@ -172,10 +172,15 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_ascend_6dof(Ctx &c, con
 
 // The part of an op that does not depend on its kind: prefetch of op k + MB_PF_DIST, scalars of op k, raw angle of op
 // k + 1, kinematic state of the parent.  DESC1: op k is a 1-DoF DESCEND;  DESC: op k is a DESCEND.
+// REV1: op k is a revolute DESCEND (its sin/cos were evaluated during the previous op from the raw angle still in pp.mq)
 template <class T, class Ctx>
-MB_HD void rnea_pre(Ctx &c, const int k, const MbOp2 &o, const bool desc1, const bool desc, const T *grav, SvT<T> &v, SvT<T> &a, RneaPipe<T> &pp)
+MB_HD void rnea_pre(Ctx &c, const int k, const MbOp2 &o, const bool desc1, const bool desc, const bool rev1, const T *grav, SvT<T> &v, SvT<T> &a,
+                    RneaPipe<T> &pp)
 {
-   c.stk_fence();
+   if (rev1 && mb_angle_large(pp.mq))
+      mb_sincos_redo(pp.mq, pp.s, pp.c);
+   if (!desc)
+      c.stk_fence(); // only an ASCEND reads the wide stack back
    if (o.pf & MB2_PF_D1)
       c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, 7);
    c.pf_commit();
@@ -187,7 +192,7 @@ MB_HD void rnea_pre(Ctx &c, const int k, const MbOp2 &o, const bool desc1, const
       pp.x = c.pf_ld(k & (MB_PF_STAGES - 1), 2);
    }
    if (o.pf & MB2_PF_NEXT1) // op k + 1 is a 1-DoF DESCEND
-      pp.mq = mb_reduce_angle(c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0)); // no-op unless |q| > MB_SINCOS_FAST_LIMIT
+      pp.mq = c.pf_ld((k + 1) & (MB_PF_STAGES - 1), 0); // raw: checked when op k + 1 starts (mb_angle_large)
    // kinematic state of the parent: carried in registers along a chain, otherwise the root acceleration
    // (= -gravity, InverseDynamicsCalculator.java:397-403) or the state saved by the branching ancestor
    if (desc && (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT)))
@@ -213,7 +218,7 @@ template <class T, class Ctx, bool FEXT>
 MB_HD void rnea_op(Ctx &c, const int k, const MbOp2 o, const int ext, const T *grav, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
 {
    c.op_sync(k);
-   rnea_pre<T, Ctx>(c, k, o, mb2_is_1dof_descend(o), !(o.code & MB2_ASCEND), grav, v, a, pp);
+   rnea_pre<T, Ctx>(c, k, o, mb2_is_1dof_descend(o), !(o.code & MB2_ASCEND), !(o.code & MB2_ASCEND) && MB2_JT(o.code) == MB_REVOLUTE, grav, v, a, pp);
    T ns = pp.mq, nc = (T)1; // prismatic next op: "s" carries q
    switch (o.code & 0xfu)
    {
@@ -255,21 +260,33 @@ MB_HD void rnea_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, Sv
    c.template pf_wait<0>();
    if (mb2_is_1dof_descend(o0))
    {
-      const T q0 = mb_reduce_angle(c.pf_ld(0, 0));
-      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(q0, &pp.s, &pp.c);
-      else pp.s = q0;
+      const T q0 = c.pf_ld(0, 0);
+      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &pp.s, &pp.c);
+      else pp.s = q0; // a prismatic displacement is not an angle
    }
 }
 
 // One op inside a run: the same steps as rnea_op with the kind (ASCEND / joint type / SC) fixed at compile time, so a run
 // is a tight loop over one straight-line routine.
+// KIND & MB_RUN_PLAIN: every op of the run has the flags of the common case of its kind (mb_run_plain_flags: the interior body of
+// a chain, or the leaf that ends it), so they are compile-time constants here and their tests -- a uniform-datapath test and a
+// branch each, some 15 cycles of latency apiece at the head of the op -- fold away.  The SC bit implies that the next op is a
+// one-DoF DESCEND (MB2_PF_NEXT1) in every kind.
 template <class T, class Ctx, bool FEXT, int KIND>
 MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
 {
-   constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0;
+   constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0, PLAIN = (KIND & MB_RUN_PLAIN) != 0;
    constexpr int JT = (KIND >> 1) & 3;
-   const MbOp2 o = P.op2[k];
-   rnea_pre<T, Ctx>(c, k, o, !ASC && JT != MB_SIXDOF, !ASC, grav, v, a, pp);
+   MbOp2 o = P.op2[k];
+   if (SC)
+      o.pf |= MB2_PF_NEXT1;
+   if (PLAIN)
+   {
+      o.flags = (uint8_t)mb_run_plain_flags(MB_RNEA, KIND & 0xf, false);
+      if (!SC)
+         o.pf &= (uint8_t)~MB2_PF_NEXT1;
+   }
+   rnea_pre<T, Ctx>(c, k, o, !ASC && JT != MB_SIXDOF, !ASC, !ASC && JT == MB_REVOLUTE, grav, v, a, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
    if (JT == MB_SIXDOF)
@@ -306,6 +323,7 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
       {
          MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
          MB_RUN_CASE(8) MB_RUN_CASE(9) MB_RUN_CASE(10) MB_RUN_CASE(11) MB_RUN_CASE(12) MB_RUN_CASE(13)
+         MB_RUN_CASE(MB_RUN_PLAIN | 0) MB_RUN_CASE(MB_RUN_PLAIN | 1) MB_RUN_CASE(MB_RUN_PLAIN | 8)
          default: break;
       }
 #undef MB_RUN_CASE

@@ -62,11 +62,11 @@ __device__ __forceinline__ XfT<double> lane_xf(const Lane &L, const Io &io)
    }
    else
    {
-      const double q = mb_reduce_angle(io.ld_q(L.cfg));
+      const double q = io.ld_q(L.cfg);
       if (L.jt == MB_REVOLUTE)
       {
          double s, c;
-         mb_sincos(q, &s, &c);
+         mb_sincos(mb_reduce_angle(q), &s, &c);
          X.R = mul_rz(L.X0.R, s, c);
       }
       else

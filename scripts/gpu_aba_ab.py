@@ -52,7 +52,7 @@ def child():
     ms = sorted(a.elapsed_time(b) for a, b in evs)
     digest = hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest()[:16]
     print(json.dumps({"algo": algo, "forward": os.environ.get("MECANO_B200_ABA_P3_FORWARD", ""), "discard": os.environ.get("MECANO_B200_ABA_DISCARD", ""),
-                      "cfg": os.environ.get("MECANO_B200_CFG", ""), "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "sha": digest, "info": calc.kernelInfo(N)["regs_per_thread"]}))
+                      "cfg": os.environ.get("MECANO_B200_CFG", ""), "tag": os.environ.get("AB_TAG", ""), "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "sha": digest, "info": calc.kernelInfo(N)["regs_per_thread"]}))
 
 
 def main():

@@ -52,6 +52,33 @@ def test_emulated_kernels_match_oracle(idx):
     assert rel(M, o.crba_batch(q)) < TOL
 
 
+@pytest.mark.parametrize("idx", [1, 3, 8, 13])
+def test_emulated_kernels_with_angles_beyond_the_fast_sincos_range(idx):
+    """Joint angles of any magnitude are legal in Mecano (Math.sin / cos reduce exactly).  The kernels evaluate a fast sin/cos for
+    |q| < 1e5 and redo it with the library routine otherwise (jointmath.cuh: mb_angle_large); prismatic displacements of that
+    size must pass through untouched."""
+    rng = np.random.default_rng(4100 + idx)
+    t = trees(rng)[idx]
+    o, e = ol.Oracle(t), el.Emu(t)
+    n = 8
+    q, qd, qdd, tau = td.random_states(rng, t, n)
+    rev = [int(t.cfg_off[i]) for i in range(t.nb) if t.jtype[i] == td.REVOLUTE]
+    pris = [int(t.cfg_off[i]) for i in range(t.nb) if t.jtype[i] == td.PRISMATIC]
+    for s in range(n):
+        for r in rng.permutation(rev)[: 1 + s % 3]:
+            q[r, s] = rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(5.0, 9.0)
+    q[rev[0], 0] = 1.0e5  # the boundary itself
+    assert rel(e.rnea(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < TOL
+    assert rel(e.aba(q, qd, tau), o.aba_batch(q, qd, tau)) < TOL
+    assert rel(e.crba(q), o.crba_batch(q)) < TOL
+    if pris:
+        # a displacement of that size is not an angle (forward dynamics is too ill-conditioned there to compare at 1e-9)
+        for s in range(n):
+            q[rng.choice(pris), s] = rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(5.0, 6.0)
+        assert rel(e.rnea(q, qd, qdd), o.rnea_batch(q, qd, qdd)) < TOL
+        assert rel(e.crba(q), o.crba_batch(q)) < TOL
+
+
 @pytest.mark.parametrize("idx", range(N_TREES))
 def test_emulated_rnea_byproducts_match_oracle(idx):
     """getBodyAcceleration / getComputedJointWrench (InverseDynamicsCalculator.java:578-602): the kernel routines leave them

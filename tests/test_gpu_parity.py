@@ -131,6 +131,44 @@ def test_kernels_match_oracle(torch_dev, idx, variant):
     assert rel(Ms.cpu().numpy().reshape(n, nv, nv).transpose(1, 2, 0), Mo) < TOL, name
 
 
+@pytest.mark.parametrize("variant", ["thread", "warp"])
+@pytest.mark.parametrize("idx", [0, 3, 8])
+def test_angles_beyond_the_fast_sincos_range(torch_dev, idx, variant):
+    """Joint angles of any magnitude (Math.sin / cos reduce exactly): the fast sin/cos of the kernels covers |q| < 1e5, larger
+    angles are redone by the library routine (jointmath.cuh: mb_angle_large); prismatic displacements of that size pass through."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(5200 + idx)
+    o = ol.Oracle(t, gravity=(0.0, 0.0, -9.81))
+    n = 1500
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    rev = [int(t.cfg_off[i]) for i in range(t.nb) if t.jtype[i] == td.REVOLUTE]
+    pris = [int(t.cfg_off[i]) for i in range(t.nb) if t.jtype[i] == td.PRISMATIC]
+    for st in range(0, n, 3):
+        for r in rng.permutation(rev)[: 1 + st % 4]:
+            q[r, st] = rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(5.0, 9.0)
+    q[rev[0], 1] = 1.0e5
+    ident = mb.InverseDynamicsCalculator(s).setKernelVariant(variant)
+    ident.setGravitationalAcceleration(-9.81)
+    fdyn = mb.ForwardDynamicsCalculator(s).setKernelVariant(variant)
+    fdyn.setGravitationalAcceleration(-9.81)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s).setKernelVariant(variant)
+    tq, tqd, tqdd, ttau = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, tau))
+    assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd)) < TOL, name
+    assert rel(fdyn.compute(tq, tqd, ttau).cpu().numpy(), o.aba_batch(q, qd, tau)) < TOL, name
+    assert rel(crba.getMassMatrix(tq).cpu().numpy().reshape(t.nv, t.nv, n), o.crba_batch(q)) < TOL, name
+    if pris:
+        # a displacement of that size is not an angle (forward dynamics is too ill-conditioned there to compare at 1e-9)
+        for st in range(0, n, 2):
+            q[rng.choice(pris), st] = rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(5.0, 6.0)
+        tq = torch.from_numpy(q).to(dev)
+        assert rel(ident.compute(tq, tqd, tqdd).cpu().numpy(), o.rnea_batch(q, qd, qdd)) < TOL, name
+        assert rel(crba.getMassMatrix(tq).cpu().numpy().reshape(t.nv, t.nv, n), o.crba_batch(q)) < TOL, name
+
+
 def test_host_entry_points_and_leading_dimension(torch_dev):
     """*_host entry points (numpy in, numpy out), with ld > n, plus empty and single-state batches."""
     import mecano_b200 as mb
