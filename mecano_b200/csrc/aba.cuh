@@ -14,8 +14,8 @@ namespace mb
 {
 // pass-three record: MB_ABA_REC doubles per body (program.h)
 
-// record of a one-DoF joint: g without its unit component along the joint axis, then k0
-template <class T, class Ctx, bool REV> MB_HD void aba_rec_st_1dof(Ctx &c, int r, const SvT<T> &g, T k0)
+// record of a one-DoF joint: g without its unit component along the joint axis, k0, sin/cos of the joint angle (prismatic: q, 1)
+template <class T, class Ctx, bool REV> MB_HD void aba_rec_st_1dof(Ctx &c, int r, const SvT<T> &g, T k0, T s, T cs)
 {
    if (REV)
    {
@@ -29,6 +29,7 @@ template <class T, class Ctx, bool REV> MB_HD void aba_rec_st_1dof(Ctx &c, int r
       c.rec_st2(r + 1, g.a.z, g.l.x);
       c.rec_st2(r + 2, g.l.y, k0);
    }
+   c.rec_st2(r + 3, s, cs);
 }
 
 template <class T> struct AbaPipe
@@ -109,6 +110,7 @@ MB_HD void aba_ascend_1dof_locked(Ctx &c, const MbOp2 o, const CP C, const SvT<T
    c.rec_st2(r + 0, (T)0, (T)0);
    c.rec_st2(r + 1, (T)0, (T)0);
    c.rec_st2(r + 2, (T)0, qdd); // pass three takes k0 as the acceleration (MB2_ACCSRC on its record)
+   c.rec_st2(r + 3, s, cs);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       SvT<T> cc;
@@ -144,15 +146,24 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    }
    const T qd = pp.qd, tau = pp.x;
    const RbiT<T> I = ld_rbi<T>(C);
-   SvT<T> pA = cross_force(vb, mul(I, vb));
+   // p^A = v x* (I v) [- f_ext] + the children's, I^A = I + the children's (the accumulated terms ride on the multiply-add chains)
+   SvT<T> pA;
+   AbiT<T> IA;
+   {
+      const SvT<T> Iv = mul(I, vb);
+      if (o.flags & MB2_LEAF)
+      {
+         pA = cross_force(vb, Iv);
+         IA = abi_from_rbi(I);
+      }
+      else
+      {
+         pA = cross_force_add(vb, Iv, pacc);
+         IA = abi_add_rbi(acc, I);
+      }
+   }
    if (FEXT && c.has_fext())
       pA = pA - external_wrench<T>(c, ext, C);
-   AbiT<T> IA = abi_from_rbi(I);
-   if (!(o.flags & MB2_LEAF))
-   {
-      IA = IA + acc;
-      pA = pA + pacc;
-   }
    if (FEXT && (o.flags & MB2_ACCSRC))
    {
       aba_ascend_1dof_locked<T, Ctx, REV>(c, o, C, vb, qd, s, cs, IA, pA, acc, pacc);
@@ -180,7 +191,7 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    g.l = Dinv * U.l;
    const T k0 = Dinv * u;
    // record for pass three: qdd = k0 - g . a'  (the component of g along the joint axis is D / D = 1 and is not stored)
-   aba_rec_st_1dof<T, Ctx, REV>(c, o.body * (MB_ABA_REC / 2), g, k0);
+   aba_rec_st_1dof<T, Ctx, REV>(c, o.body * (MB_ABA_REC / 2), g, k0, s, cs);
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       // bias acceleration c = v x (S qd): only x / y components
@@ -244,15 +255,24 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
    SvT<T> vb;
    c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
    const RbiT<T> I = ld_rbi<T>(C);
-   SvT<T> pA = cross_force(vb, mul(I, vb));
+   // p^A = v x* (I v) [- f_ext] + the children's, I^A = I + the children's (the accumulated terms ride on the multiply-add chains)
+   SvT<T> pA;
+   AbiT<T> IA;
+   {
+      const SvT<T> Iv = mul(I, vb);
+      if (o.flags & MB2_LEAF)
+      {
+         pA = cross_force(vb, Iv);
+         IA = abi_from_rbi(I);
+      }
+      else
+      {
+         pA = cross_force_add(vb, Iv, pacc);
+         IA = abi_add_rbi(acc, I);
+      }
+   }
    if (FEXT && c.has_fext())
       pA = pA - external_wrench<T>(c, ext, C);
-   AbiT<T> IA = abi_from_rbi(I);
-   if (!(o.flags & MB2_LEAF))
-   {
-      IA = IA + acc;
-      pA = pA + pacc;
-   }
    const int r = o.body * (MB_ABA_REC / 2);
    if (FEXT && (o.flags & MB2_ACCSRC))
    {
@@ -261,6 +281,7 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
       c.rec_st2(r + 0, qdd6.a.x, qdd6.a.y);
       c.rec_st2(r + 1, qdd6.a.z, qdd6.l.x);
       c.rec_st2(r + 2, qdd6.l.y, qdd6.l.z);
+      c.rec_st2(r + 3, (T)0, (T)0);
       if (!(o.flags & MB2_ROOT_PARENT))
       {
          const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
@@ -276,6 +297,7 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
    c.rec_st2(r + 0, x.a.x, x.a.y);
    c.rec_st2(r + 1, x.a.z, x.l.x);
    c.rec_st2(r + 2, x.l.y, x.l.z);
+   c.rec_st2(r + 3, (T)0, (T)0); // (the whole record travels through the pass-three ring)
    if (!(o.flags & MB2_ROOT_PARENT))
    {
       const XfT<T> X = jp_ld_xf<T>(c, o.slot, o.nslot);
@@ -297,20 +319,18 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
 
 // ---- pass three (:1259-1310): accelerations, root to leaves
 // LOCKS: the instantiation that serves joints in ACCELERATION_SOURCE mode (their records hold the given acceleration)
-template <class T, class Ctx, bool REV, bool SC, bool LOCKS>
-MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp, T &ns, T &nc)
+template <class T, class Ctx, bool REV, bool LOCKS>
+MB_HD void aba_pass3_1dof(Ctx &c, const MbOp2 o, int st, SvT<T> &v, SvT<T> &a, T qd)
 {
-   if (SC)
-      mb_sincos(pp.mq, &ns, &nc);
-   T g0, g1, g2, g3, g4, k0;
+   T g0, g1, g2, g3, g4, k0, s, cs;
    c.pf3_ld2(st, 1, g0, g1);
    c.pf3_ld2(st, 2, g2, g3);
    c.pf3_ld2(st, 3, g4, k0);
+   c.pf3_ld2(st, 4, s, cs);
    c.rec_discard(o.body * (MB_ABA_REC / 2));
-   const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), pp.s, pp.c);
+   const XfT<T> X = joint_xf_1dof<T, REV>(c.cst(o.body), s, cs);
    v = motion_to_child(X, v);
    a = motion_to_child(X, a); // a' = X^-1 a_parent + c
-   const T qd = pp.qd;
    if (REV)
    {
       a.a.x += v.a.y * qd; a.a.y -= v.a.x * qd;
@@ -469,7 +489,7 @@ MB_HD void aba_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT
 }
 
 // ---- pass three: DESCEND records only.  Same software pipeline, but the ring (Ctx::pf3_*, overlaid on the now idle
-// stack area) also carries the pass-two record of each body
+// stack area) carries the pass-two record of each body -- which includes the sin/cos of its joint -- and its joint velocity
 template <class T, class Ctx>
 MB_HD void aba_pass3_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
@@ -477,44 +497,27 @@ MB_HD void aba_pass3_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o
    c.pass_fence(); // the records written in pass two are read back below (same thread)
    a = sv_zero<T>();
    v = sv_zero<T>();
-   c.pf3_issue(0, o0.cfg, o0.dof, o0.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o0) ? 3 : 0);
+   c.pf3_issue(0, o0.cfg, o0.dof, o0.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o0) ? 2 : 0);
    c.pf_commit();
-   c.pf3_issue(1, o1.cfg, o1.dof, o1.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o1) ? 3 : 0);
+   c.pf3_issue(1, o1.cfg, o1.dof, o1.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o1) ? 2 : 0);
    c.pf_commit();
-   c.pf3_issue(2, o2.cfg, o2.dof, o2.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o2) ? 3 : 0);
+   c.pf3_issue(2, o2.cfg, o2.dof, o2.body * (MB_ABA_REC / 2), mb2_is_1dof_descend(o2) ? 2 : 0);
    c.pf_commit();
-   c.template pf_wait<0>();
-   pp.s = pp.mq = (T)0;
-   pp.c = (T)1;
-   if (mb2_is_1dof_descend(o0))
-   {
-      T q0, qd0;
-      c.pf3_ld2(0, 0, q0, qd0);
-      if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &pp.s, &pp.c);
-      else pp.s = q0;
-   }
+   (void)pp;
 }
 
-// ---- the kind-independent part of a pass-three op
+// ---- the kind-independent part of a pass-three op; returns the joint velocity of a one-DoF joint
 template <class T, class Ctx>
-MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const bool rev1, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+MB_HD T aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof, const T *grav, SvT<T> &v, SvT<T> &a)
 {
-   if (rev1 && mb_angle_large(pp.mq))
-      mb_sincos_redo(pp.mq, pp.s, pp.c);
-   c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, o.pfbody * (MB_ABA_REC / 2), (o.pf & MB2_PF_D1) ? 3 : 0);
+   c.pf3_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, o.pfbody * (MB_ABA_REC / 2), (o.pf & MB2_PF_D1) ? 2 : 0);
    c.pf_commit();
    c.template pf_wait<MB_PF_DIST - 1>();
-   const int st = k & (MB_PF_STAGES - 1);
-   pp.qd = pp.mq = (T)0;
+   T qd = (T)0;
    if (onedof)
    {
-      T qq;
-      c.pf3_ld2(st, 0, qq, pp.qd);
-   }
-   if (o.pf & MB2_PF_NEXT1)
-   {
-      T qdn;
-      c.pf3_ld2((k + 1) & (MB_PF_STAGES - 1), 0, pp.mq, qdn); // raw: checked when op k + 1 starts
+      T unused;
+      c.pf3_ld2(k & (MB_PF_STAGES - 1), 0, unused, qd);
    }
    if (o.flags & (MB2_ROOT_PARENT | MB2_LOAD_PARENT))
    {
@@ -530,29 +533,22 @@ MB_HD void aba_pass3_pre(Ctx &c, const int k, const MbOp2 &o, const bool onedof,
          a = aux_ld_sv<T>(c, o.paux + 6);
       }
    }
+   return qd;
 }
 
 template <class T, class Ctx, bool LOCKS = false>
 MB_HD void aba_pass3_op(Ctx &c, const int k, const MbOp2 o, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
 {
+   (void)pp;
    c.op_sync(k);
-   aba_pass3_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, MB2_JT(o.code) == MB_REVOLUTE, grav, v, a, pp);
+   const T qd = aba_pass3_pre<T, Ctx>(c, k, o, MB2_JT(o.code) != MB_SIXDOF, grav, v, a);
    const int st = k & (MB_PF_STAGES - 1);
-   T ns = pp.mq, nc = (T)1;
-   switch (o.code & 0xfu)
+   switch ((o.code >> 1) & 3u)
    {
-      case (MB_REVOLUTE << 1): aba_pass3_1dof<T, Ctx, true, false, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
-      case (MB_REVOLUTE << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, true, true, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
-      case (MB_PRISMATIC << 1): aba_pass3_1dof<T, Ctx, false, false, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
-      case (MB_PRISMATIC << 1) | MB2_SC: aba_pass3_1dof<T, Ctx, false, true, LOCKS>(c, o, st, v, a, pp, ns, nc); break;
-      default:
-         if (o.code & MB2_SC)
-            mb_sincos(pp.mq, &ns, &nc);
-         aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, -1, v, a);
-         break;
+      case MB_REVOLUTE: aba_pass3_1dof<T, Ctx, true, LOCKS>(c, o, st, v, a, qd); break;
+      case MB_PRISMATIC: aba_pass3_1dof<T, Ctx, false, LOCKS>(c, o, st, v, a, qd); break;
+      default: aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, -1, v, a); break;
    }
-   pp.s = ns;
-   pp.c = nc;
 }
 
 // ---- run steps: as aba_op / aba_pass3_op with the kind (ASCEND / joint type) fixed at compile time (see rnea.cuh).  Whether
@@ -567,14 +563,13 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
    static_assert(!(ASC && SCK), "ASCEND kinds do not carry the SC bit");
    MbOp2 o = P.op2[k];
    // plain runs (rnea.cuh: rnea_run_step): the flags of the op are those of the common case of its kind, i.e. constants
-   if (!ASC && SCK)
-      o.pf |= MB2_PF_NEXT1;
    if (PLAIN)
    {
       o.flags = (uint8_t)mb_run_plain_flags(MB_ABA, KIND & 0xf, false);
-      if (!ASC && !SCK)
-         o.pf &= (uint8_t)~MB2_PF_NEXT1;
+      o.pf = (!ASC && SCK) ? (uint8_t)(o.pf | MB2_PF_NEXT1) : (ASC ? o.pf : (uint8_t)(o.pf & ~MB2_PF_NEXT1));
    }
+   else if (!ASC && SCK)
+      o.pf |= MB2_PF_NEXT1; // the SC bit implies that a one-DoF DESCEND follows
    aba_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, ASC, !ASC && JT == MB_REVOLUTE, v, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
@@ -597,32 +592,19 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
 }
 
 template <class T, class Ctx, bool LOCKS, int KIND>
-MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, AbaPipe<T> &pp)
+MB_HD void aba_pass3_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a)
 {
    constexpr int JT = (KIND >> 1) & 3;
-   constexpr bool SCK = (KIND & MB2_SC) != 0, PLAIN = (KIND & MB_RUN_PLAIN) != 0;
+   constexpr bool PLAIN = (KIND & MB_RUN_PLAIN) != 0;
    MbOp2 o = P.op3[k];
-   if (SCK)
-      o.pf |= MB2_PF_NEXT1;
    if (PLAIN)
-   {
       o.flags = (uint8_t)mb_run_plain_flags(MB_ABA, KIND & 0xf, true);
-      if (!SCK)
-         o.pf &= (uint8_t)~MB2_PF_NEXT1;
-   }
-   aba_pass3_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, JT == MB_REVOLUTE, grav, v, a, pp);
+   const T qd = aba_pass3_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, grav, v, a);
    const int st = k & (MB_PF_STAGES - 1);
-   T ns = pp.mq, nc = (T)1;
    if (JT == MB_SIXDOF)
-   {
-      if (SCK)
-         mb_sincos(pp.mq, &ns, &nc);
       aba_pass3_6dof<T, Ctx, LOCKS>(c, o, st, P.body[o.body].rec, v, a);
-   }
    else
-      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, SCK, LOCKS>(c, o, st, v, a, pp, ns, nc);
-   pp.s = ns;
-   pp.c = nc;
+      aba_pass3_1dof<T, Ctx, JT == MB_REVOLUTE, LOCKS>(c, o, st, v, a, qd);
 }
 
 template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P, Ctx &c, const T *grav)
@@ -643,14 +625,22 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
    case KIND:                                                                                       \
       _Pragma("unroll 1") do { aba_run_step<T, Ctx, FEXT, KIND>(P, c, k, v, acc, pacc, pp); } while (++k < k1); \
       break;
+#define MB_RUN_CASE_IF(COND, KIND)                                                                 \
+   case KIND:                                                                                       \
+      if constexpr ((COND) != 0)                                                                    \
+         _Pragma("unroll 1") do { aba_run_step<T, Ctx, FEXT, KIND>(P, c, k, v, acc, pacc, pp); } while (++k < k1); \
+      break;
       switch (R.kind)
       {
          MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
          MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
-         MB_RUN_CASE(MB_RUN_PLAIN | 0) MB_RUN_CASE(MB_RUN_PLAIN | 1) MB_RUN_CASE(MB_RUN_PLAIN | 8)
+#if MB_PLAIN_ABA & 7
+         MB_RUN_CASE_IF(MB_PLAIN_ABA & 1, MB_RUN_PLAIN | 0) MB_RUN_CASE_IF(MB_PLAIN_ABA & 2, MB_RUN_PLAIN | 1) MB_RUN_CASE_IF(MB_PLAIN_ABA & 4, MB_RUN_PLAIN | 8)
+#endif
          default: break;
       }
 #undef MB_RUN_CASE
+#undef MB_RUN_CASE_IF
    }
    // =========================== pass three
    aba_pass3_begin<T, Ctx>(c, P.op3[0], P.op3[1], P.op3[2], v, a, pp);
@@ -663,15 +653,23 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       const int k1 = k + R.n;
 #define MB_RUN_CASE(KIND)                                                                       \
    case KIND:                                                                                    \
-      _Pragma("unroll 1") do { aba_pass3_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a, pp); } while (++k < k1); \
+      _Pragma("unroll 1") do { aba_pass3_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a); } while (++k < k1); \
+      break;
+#define MB_RUN_CASE_IF(COND, KIND)                                                              \
+   case KIND:                                                                                    \
+      if constexpr ((COND) != 0)                                                                 \
+         _Pragma("unroll 1") do { aba_pass3_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a); } while (++k < k1); \
       break;
       switch (R.kind)
       {
-         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4) MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
-         MB_RUN_CASE(MB_RUN_PLAIN | 0) MB_RUN_CASE(MB_RUN_PLAIN | 8)
+         MB_RUN_CASE(0) MB_RUN_CASE(2) MB_RUN_CASE(4)
+#if MB_PLAIN_ABA & 8
+         MB_RUN_CASE_IF(MB_PLAIN_ABA & 8, MB_RUN_PLAIN | 0)
+#endif
          default: break;
       }
 #undef MB_RUN_CASE
+#undef MB_RUN_CASE_IF
    }
    c.template pf_wait<0>();
 }

@@ -122,7 +122,8 @@ int slot2_size(int algo, int jtype, bool root_parent)
 }
 
 // Runs of consecutive ops of the same kind (MbRun).  RNEA runs are split by the SC bit (its routines schedule the sin/cos of the
-// next joint inside the op's basic block).  ABA splits only its small ops (DESCEND, pass three) that way; its ASCEND ops are large,
+// next joint inside the op's basic block).  ABA splits only its DESCEND ops that way (pass three evaluates no sin/cos: they
+// travel in the pass-two records); its ASCEND ops are large,
 // the SC test there is a warp-uniform branch taken a few times per state, and one loop body per joint type keeps the hot code of
 // the kernel inside the instruction cache (no_instructions was 12.8 % of the stall samples with SC-split ASCEND runs).  Runs whose
 // ops all carry the common flags of their kind are marked MB_RUN_PLAIN (program.h).
@@ -132,12 +133,12 @@ void build_runs(int algo, MbProgram &P, int n3)
       int nr = 0;
       for (int k = 0; k < n; k++)
       {
-         uint8_t kind = ops[k].code & ((algo == MB_ABA && (ops[k].code & MB2_ASCEND)) ? 0x7u : 0xfu);
+         uint8_t kind = ops[k].code & ((algo == MB_ABA && (pass3 || (ops[k].code & MB2_ASCEND))) ? 0x7u : 0xfu);
          const unsigned tested = mb_run_plain_tested(algo, kind, pass3);
          if (tested)
          {
             const bool next1 = (ops[k].pf & MB2_PF_NEXT1) != 0, sc = (kind & MB2_SC) != 0;
-            if ((ops[k].flags & tested) == (mb_run_plain_flags(algo, kind, pass3) & tested) && (!mb_run_kind_has_sc(algo, kind) || next1 == sc))
+            if ((ops[k].flags & tested) == (mb_run_plain_flags(algo, kind, pass3) & tested) && (!mb_run_kind_has_sc(algo, kind, pass3) || next1 == sc))
                kind |= MB_RUN_PLAIN;
          }
          if (nr > 0 && runs[nr - 1].kind == kind && runs[nr - 1].n < 255)

@@ -18,15 +18,24 @@ MB_HD void aba_ascend_3dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
    SvT<T> vb;
    c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
    const RbiT<T> I = ld_rbi<T>(C);
-   SvT<T> pA = cross_force(vb, mul(I, vb));
+   // p^A = v x* (I v) [- f_ext] + the children's, I^A = I + the children's (the accumulated terms ride on the multiply-add chains)
+   SvT<T> pA;
+   AbiT<T> IA;
+   {
+      const SvT<T> Iv = mul(I, vb);
+      if (o.flags & MB2_LEAF)
+      {
+         pA = cross_force(vb, Iv);
+         IA = abi_from_rbi(I);
+      }
+      else
+      {
+         pA = cross_force_add(vb, Iv, pacc);
+         IA = abi_add_rbi(acc, I);
+      }
+   }
    if (FEXT && c.has_fext())
       pA = pA - external_wrench<T>(c, ext, C);
-   AbiT<T> IA = abi_from_rbi(I);
-   if (!(o.flags & MB2_LEAF))
-   {
-      IA = IA + acc;
-      pA = pA + pacc;
-   }
    const int r = o.body * (MB_ABA_REC / 2);
    const SvT<T> vj = ld_svj<T>(o.dof, sub, [&](int rr) { return c.ld_qd(rr); });
    if (FEXT && (o.flags & MB2_ACCSRC))
@@ -37,6 +46,7 @@ MB_HD void aba_ascend_3dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
       c.rec_st2(r + 0, sv_get(qdd6, J[0]), sv_get(qdd6, J[1]));
       c.rec_st2(r + 1, sv_get(qdd6, J[2]), (T)0);
       c.rec_st2(r + 2, (T)0, (T)0);
+      c.rec_st2(r + 3, (T)0, (T)0);
       c.rec_st2(rec_hi + 0, (T)0, (T)0); // (pass three reads the whole record before it looks at the flag)
       c.rec_st2(rec_hi + 1, (T)0, (T)0);
       c.rec_st2(rec_hi + 2, (T)0, (T)0);
@@ -72,6 +82,7 @@ MB_HD void aba_ascend_3dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
    c.rec_st2(r + 0, k0[0], k0[1]);
    c.rec_st2(r + 1, k0[2], G[0][0]);
    c.rec_st2(r + 2, G[0][1], G[0][2]);
+   c.rec_st2(r + 3, (T)0, (T)0); // (the whole first slot travels through the pass-three ring)
    c.rec_st2(rec_hi + 0, G[1][0], G[1][1]);
    c.rec_st2(rec_hi + 1, G[1][2], G[2][0]);
    c.rec_st2(rec_hi + 2, G[2][1], G[2][2]);

@@ -133,6 +133,16 @@ struct MbWalk
 // MB_RUN_PLAIN: all ops of the run carry the flags of the common case of their kind (and no one-DoF DESCEND follows unless the SC
 // bit says so), which the run loops then treat as compile-time constants.  Only for the kinds mb_run_has_plain() names.
 #define MB_RUN_PLAIN 0x10u
+// which kinds have a plain form (bit masks; every plain loop body is more hot code for the instruction caches):
+// RNEA 1 DESCEND of a leaf, 2 ASCEND, 4 DESCEND with SC;  ABA 1 DESCEND of a leaf, 2 ASCEND, 4 DESCEND with SC, 8 pass three
+// Measured on 2^20 H37 states (profiles/r06d_plain_kinds.md): RNEA ASCEND -1.4 %; the RNEA DESCEND forms are neutral or slower
+// (code placement), and every ABA form is slower (+1 ... +18 %: the hot loops of ABA already fill the 32 KB instruction cache).
+#ifndef MB_PLAIN_RNEA
+#define MB_PLAIN_RNEA 2
+#endif
+#ifndef MB_PLAIN_ABA
+#define MB_PLAIN_ABA 0
+#endif
 // the flags a kind tests (rnea.cuh / aba.cuh), 0 if the kind has no plain form.  kind = MbOp2::code & 0xf; pass3: ABA pass-three list.
 // Plain forms exist for revolute joints: the DESCEND of an interior body (SC set: the next joint of the chain is revolute too), the
 // DESCEND of a leaf (no SC: its own ASCEND follows) and the ASCEND of an interior body with a single child.
@@ -142,14 +152,17 @@ __host__ __device__
 static inline unsigned mb_run_plain_tested(int algo, int kind, bool pass3)
 {
    if (algo == 0 /* MB_RNEA */)
-      return (kind == 0 || kind == 8) ? (MB2_LEAF | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ROOT_PARENT)
-                                      : (kind == 1 ? (MB2_LEAF | MB2_ROOT_PARENT | MB2_STORE_ACC) : 0u);
+   {
+      if (kind == 0 && (MB_PLAIN_RNEA & 1)) return MB2_LEAF | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ROOT_PARENT;
+      if (kind == 1 && (MB_PLAIN_RNEA & 2)) return MB2_LEAF | MB2_ROOT_PARENT | MB2_STORE_ACC;
+      if (kind == 8 && (MB_PLAIN_RNEA & 4)) return MB2_LEAF | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ROOT_PARENT;
+   }
    if (algo == 1 /* MB_ABA */)
    {
       if (pass3)
-         return (kind == 0 || kind == 8) ? (MB2_ROOT_PARENT | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ACCSRC) : 0u;
-      return (kind == 0 || kind == 8) ? (MB2_LEAF | MB2_LOAD_PARENT | MB2_ROOT_PARENT)
-                                      : (kind == 1 ? (MB2_LEAF | MB2_ROOT_PARENT | MB2_FIRST_CHILD | MB2_STORE_ACC | MB2_ACCSRC) : 0u);
+         return (kind == 0 && (MB_PLAIN_ABA & 8)) ? (MB2_ROOT_PARENT | MB2_LOAD_PARENT | MB2_SAVE_STATE | MB2_ACCSRC) : 0u;
+      if ((kind == 0 && (MB_PLAIN_ABA & 1)) || (kind == 8 && (MB_PLAIN_ABA & 4))) return MB2_LEAF | MB2_LOAD_PARENT | MB2_ROOT_PARENT;
+      if (kind == 1 && (MB_PLAIN_ABA & 2)) return MB2_LEAF | MB2_ROOT_PARENT | MB2_FIRST_CHILD | MB2_STORE_ACC | MB2_ACCSRC;
    }
    return 0u;
 }
@@ -168,7 +181,7 @@ static inline unsigned mb_run_plain_flags(int algo, int kind, bool pass3)
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline bool mb_run_kind_has_sc(int algo, int kind) { return !(algo == 1 /* MB_ABA */ && (kind & MB2_ASCEND)); }
+static inline bool mb_run_kind_has_sc(int algo, int kind, bool pass3) { return !(algo == 1 /* MB_ABA */ && (pass3 || (kind & MB2_ASCEND))); }
 struct MbRun
 {
    uint8_t kind; // MbOp2::code & 0xf | MB_RUN_PLAIN
@@ -206,12 +219,13 @@ __host__ __device__
 #endif
 static inline int mb_sub_ndof(int sub) { return sub == MB_SUB_SIX ? 6 : 3; }
 
-// ABA pass-three record of one body, in doubles (three double2).  One-DoF joint: g = U / D without its component along the joint
-// axis (which is D / D = 1) and k0 = u / D: revolute (g.ax, g.ay, g.lx, g.ly, g.lz, k0), prismatic (g.ax, g.ay, g.az, g.lx, g.ly, k0).
-// SixDoF joint: the six accelerations.  An ACCELERATION_SOURCE joint stores its given acceleration (k0 / the six) and is
-// recognised in pass three by the MB2_ACCSRC flag of its op.
-#define MB_ABA_REC 6
-#define MB_ABA_RING_ROWS (1 + MB_ABA_REC / 2) // pass-three ring, double2 rows per stage: (q, qd) + the record
+// ABA pass-three record of one body, in doubles (four double2).  One-DoF joint: g = U / D without its component along the joint
+// axis (which is D / D = 1), k0 = u / D, and the sin/cos of the joint angle (prismatic: q, 1) so that pass three neither reads q nor
+// evaluates sin/cos again: revolute (g.ax, g.ay, g.lx, g.ly, g.lz, k0, s, c), prismatic (g.ax, g.ay, g.az, g.lx, g.ly, k0, q, 1).
+// SixDoF joint: the six accelerations (last double2 unused, written as zeros).  An ACCELERATION_SOURCE joint stores its given
+// acceleration (k0 / the six) and is recognised in pass three by the MB2_ACCSRC flag of its op.
+#define MB_ABA_REC 8
+#define MB_ABA_RING_ROWS (1 + MB_ABA_REC / 2) // pass-three ring, double2 rows per stage: (-, qd) + the record
 
 enum MbAlgo { MB_RNEA = 0, MB_ABA = 1, MB_CRBA = 2, MB_CORIOLIS = 3 }; // MB_CORIOLIS: mass matrix + Coriolis matrix (coriolis.cuh)
 #define MB_NUM_ALGOS 4

@@ -319,14 +319,20 @@ template <class T, class Ctx, bool FEXT> MB_HD void rnea_state(const MbProgram &
    case KIND:                                                                                               \
       _Pragma("unroll 1") do { rnea_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a, f, pp); } while (++k < k1); \
       break;
+#define MB_RUN_CASE_IF(COND, KIND)                                                                          \
+   case KIND:                                                                                               \
+      if constexpr ((COND) != 0)                                                                            \
+         _Pragma("unroll 1") do { rnea_run_step<T, Ctx, FEXT, KIND>(P, c, k, grav, v, a, f, pp); } while (++k < k1); \
+      break;
       switch (R.kind)
       {
          MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
          MB_RUN_CASE(8) MB_RUN_CASE(9) MB_RUN_CASE(10) MB_RUN_CASE(11) MB_RUN_CASE(12) MB_RUN_CASE(13)
-         MB_RUN_CASE(MB_RUN_PLAIN | 0) MB_RUN_CASE(MB_RUN_PLAIN | 1) MB_RUN_CASE(MB_RUN_PLAIN | 8)
+         MB_RUN_CASE_IF(MB_PLAIN_RNEA & 1, MB_RUN_PLAIN | 0) MB_RUN_CASE_IF(MB_PLAIN_RNEA & 2, MB_RUN_PLAIN | 1) MB_RUN_CASE_IF(MB_PLAIN_RNEA & 4, MB_RUN_PLAIN | 8)
          default: break;
       }
 #undef MB_RUN_CASE
+#undef MB_RUN_CASE_IF
    }
    c.template pf_wait<0>();
 }

@@ -150,6 +150,14 @@ MB_T SvT<T> cross_force(const SvT<T> &v, const SvT<T> &f)
    r.l = cross(v.a, f.l);
    return r;
 }
+// p + v x* f: the addend rides on the multiply-add chains
+MB_T SvT<T> cross_force_add(const SvT<T> &v, const SvT<T> &f, const SvT<T> &p)
+{
+   SvT<T> r;
+   r.a = cross_add(v.l, f.l, cross_add(v.a, f.a, p.a));
+   r.l = cross_add(v.a, f.l, p.l);
+   return r;
+}
 // I * m for a rigid-body inertia about the frame origin
 MB_T SvT<T> mul(const RbiT<T> &I, const SvT<T> &m)
 {
@@ -290,6 +298,18 @@ MB_T AbiT<T> abi_from_rbi(const RbiT<T> &I)
    r.L.xx = I.m; r.L.yy = I.m; r.L.zz = I.m; r.L.xy = 0; r.L.xz = 0; r.L.yz = 0;
    return r;
 }
+// acc + abi_from_rbi(I) without the additions of the structural zeros (a compiler may not fold x + 0.0) and with the negated
+// entries of h~ as subtractions: 15 additions instead of 27 and three negations
+MB_T AbiT<T> abi_add_rbi(const AbiT<T> &a, const RbiT<T> &I)
+{
+   AbiT<T> r;
+   r.A.xx = a.A.xx + I.I.xx; r.A.xy = a.A.xy + I.I.xy; r.A.xz = a.A.xz + I.I.xz; r.A.yy = a.A.yy + I.I.yy; r.A.yz = a.A.yz + I.I.yz; r.A.zz = a.A.zz + I.I.zz;
+   r.C.xx = a.C.xx;           r.C.xy = a.C.xy - I.h.z; r.C.xz = a.C.xz + I.h.y;
+   r.C.yx = a.C.yx + I.h.z;  r.C.yy = a.C.yy;           r.C.yz = a.C.yz - I.h.x;
+   r.C.zx = a.C.zx - I.h.y;  r.C.zy = a.C.zy + I.h.x;  r.C.zz = a.C.zz;
+   r.L.xx = a.L.xx + I.m; r.L.yy = a.L.yy + I.m; r.L.zz = a.L.zz + I.m; r.L.xy = a.L.xy; r.L.xz = a.L.xz; r.L.yz = a.L.yz;
+   return r;
+}
 MB_T AbiT<T> operator+(const AbiT<T> &a, const AbiT<T> &b)
 {
    AbiT<T> r;
@@ -372,6 +392,13 @@ template <class T, int Z = 0> MB_HD AbiT<T> abi_downdate(const AbiT<T> &I, const
 
 // Solve IA x = b for a symmetric positive-definite 6x6 (LDL^T, fully unrolled => registers).
 // Replaces EJML's LinearSolverFactory_DDRM.symmPosDef(6) used for SixDoF joints (ForwardDynamicsCalculator.java:1040, :1193-1197).
+// (MB_SOLVE_ROLLED: the loops stay loops and the factor lives in local memory -- a SixDoF joint is solved once per state, and the
+// unrolled solve is several KB of code that evicts the hot one-DoF loops from the instruction cache)
+#if defined(MB_SOLVE_ROLLED) && defined(__CUDA_ARCH__)
+#define MB_SOLVE_UNROLL _Pragma("unroll 1")
+#else
+#define MB_SOLVE_UNROLL _Pragma("unroll")
+#endif
 MB_T SvT<T> abi_solve(const AbiT<T> &I, const SvT<T> &b)
 {
    T a[6][6];
@@ -382,12 +409,12 @@ MB_T SvT<T> abi_solve(const AbiT<T> &I, const SvT<T> &b)
    a[3][3] = I.L.xx; a[4][3] = I.L.xy; a[5][3] = I.L.xz; a[4][4] = I.L.yy; a[5][4] = I.L.yz; a[5][5] = I.L.zz;
    T x[6] = {b.a.x, b.a.y, b.a.z, b.l.x, b.l.y, b.l.z};
    T dinv[6], w[6];
-#pragma unroll
+MB_SOLVE_UNROLL
    for (int j = 0; j < 6; j++)
    {
       // after column j is done a[i][j] (i > j) holds L[i][j]; w[k] = L[j][k] * D[k]
       T d = a[j][j];
-#pragma unroll
+MB_SOLVE_UNROLL
       for (int k = 0; k < j; k++)
       {
          w[k] = a[j][k] * a[k][k];
@@ -395,30 +422,30 @@ MB_T SvT<T> abi_solve(const AbiT<T> &I, const SvT<T> &b)
       }
       a[j][j] = d; // D[j]
       dinv[j] = (T)1 / d;
-#pragma unroll
+MB_SOLVE_UNROLL
       for (int i = j + 1; i < 6; i++)
       {
          T s = a[i][j];
-#pragma unroll
+MB_SOLVE_UNROLL
          for (int k = 0; k < j; k++)
             s -= a[i][k] * w[k];
          a[i][j] = s * dinv[j];
       }
    }
    // forward: L y = b
-#pragma unroll
+MB_SOLVE_UNROLL
    for (int i = 0; i < 6; i++)
-#pragma unroll
+MB_SOLVE_UNROLL
       for (int k = 0; k < i; k++)
          x[i] -= a[i][k] * x[k];
    // diagonal
-#pragma unroll
+MB_SOLVE_UNROLL
    for (int i = 0; i < 6; i++)
       x[i] *= dinv[i];
    // backward: L^T x = y
-#pragma unroll
+MB_SOLVE_UNROLL
    for (int i = 5; i >= 0; i--)
-#pragma unroll
+MB_SOLVE_UNROLL
       for (int k = i + 1; k < 6; k++)
          x[i] -= a[k][i] * x[k];
    SvT<T> r;
@@ -427,5 +454,6 @@ MB_T SvT<T> abi_solve(const AbiT<T> &I, const SvT<T> &b)
    return r;
 }
 
+#undef MB_SOLVE_UNROLL
 #undef MB_T
 } // namespace mb

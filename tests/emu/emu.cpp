@@ -295,6 +295,24 @@ extern "C" int emu_packed_index(const mecano_b200_tree_desc *d, int32_t *row, in
    return (int)ft.packed_row.size();
 }
 
+// the run table of a traversal program (program.h: MbRun): kinds and lengths; pass3 != 0: the ABA pass-three list
+extern "C" int emu_program_runs(const mecano_b200_tree_desc *d, int algo, int pass3, int *kinds, int *lens, int cap)
+{
+   mb::FlatTree ft;
+   std::string e;
+   int rc = mb::flatten_tree(d, ft, e);
+   if (rc != 0) return -1;
+   const MbProgram &P = ft.prog[algo];
+   const int n = pass3 ? P.nruns3 : P.nruns;
+   for (int r = 0; r < n && r < cap; r++)
+   {
+      const MbRun &R = pass3 ? P.run3[r] : P.run[r];
+      kinds[r] = R.kind;
+      lens[r] = R.n;
+   }
+   return n;
+}
+
 extern "C" int emu_program_info(const mecano_b200_tree_desc *d, int algo, int *out8)
 {
    mb::FlatTree ft;

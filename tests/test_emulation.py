@@ -201,7 +201,7 @@ def test_stack_sizes_follow_depth_not_body_count():
         assert info["stack"] <= per_level * (info["max_depth"] - 1) + 16
         assert big.program_info(algo)["stack"] <= per_level * big.program_info(algo)["max_depth"] + 16
     assert h37.program_info(0)["stack"] == 6 + 8 * 9  # pelvis wrench, then 3 spine + 6 non-leaf arm levels
-    assert h37.program_info(1)["rec"] == 6 * 32  # pass-three records: three double2 per body (program.h: MB_ABA_REC)
+    assert h37.program_info(1)["rec"] == 8 * 32  # pass-three records: four double2 per body (program.h: MB_ABA_REC)
 
 
 def test_emulated_kernels_match_the_golden_fixtures_of_the_next_rows():
