@@ -21,6 +21,7 @@
 #define MB_STAGGER_NS_DEFAULT 0
 #define MB_ABA_DISCARD_DEFAULT 1 // profiles/r04b_aba_records.md: 1.713 -> 1.696 ms, DRAM writes 2.46 -> 1.82 GB per 2^20 H37 states
 #define MB_MAX_SLOTS 4
+#define MB_COUNTERS 256
 
 struct mecano_b200_handle
 {
@@ -30,6 +31,8 @@ struct mecano_b200_handle
    uint16_t *d_zero = nullptr; // CRBA: structurally zero entries
    MbProgram *d_prog = nullptr; // [3] device copies of the traversal programs (warp-per-state kernels)
    std::vector<std::pair<int, int>> nonzero_runs; // CRBA: (first entry, count) runs of mass-matrix entries that are not structurally zero
+   unsigned *d_counters = nullptr; // work counters of the persistent launches (kernels.cu: launch_thread_kernel): a ring of MB_COUNTERS,
+   unsigned counter_seq = 0;       // a fresh one per launch, so that launches in flight on different streams never share one
    double *d_zero_row = nullptr; // one row of zeros: stands in for qd / qdd when RNEA ignores velocities / accelerations
    size_t zero_row_doubles = 0;
    double *d_scratch = nullptr; // joint efforts nobody asked for (centroidal convective term = one RNEA launch)
@@ -169,6 +172,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       wa.body_acc = wa.joint_wrench = nullptr;
       wa.x2 = nullptr;
       wa.cmm = wa.com = wa.root_wrench = wa.cor = nullptr;
+      wa.work_counter = nullptr;
       wa.fp32 = 0;
       wa.consts = h->d_consts;
       wa.ws = nullptr;
@@ -253,6 +257,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
       if (discard) a.flags |= MB_KFLAG_ABA_DISCARD;
    }
    a.nv = h->tree.nv;
+   a.work_counter = (h->d_counters && !use_spec) ? h->d_counters + 2 * (h->counter_seq++ % MB_COUNTERS) : nullptr;
    {
       // MECANO_B200_STAGGER_NS overrides the start offset between the warps of a scheduler (gpu_ctx.cuh: thread_block_run)
       static const int stagger = [] { const char *e = getenv("MECANO_B200_STAGGER_NS"); return e ? atoi(e) : MB_STAGGER_NS_DEFAULT; }();
@@ -635,6 +640,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
    auto bail = [&](cudaError_t ce, const char *what) {
       std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
       if (h->d_consts) cudaFree(h->d_consts);
+      if (h->d_counters) cudaFree(h->d_counters);
       if (h->d_zero) cudaFree(h->d_zero);
       if (h->d_prog) cudaFree(h->d_prog);
       delete h;
@@ -644,6 +650,8 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
    if ((e = device_guard_.err) != cudaSuccess) return bail(e, "cudaSetDevice");
    const size_t bytes = h->tree.consts.size() * sizeof(double);
    if ((e = cudaMalloc(&h->d_consts, bytes)) != cudaSuccess) return bail(e, "cudaMalloc(consts)");
+   if ((e = cudaMalloc(&h->d_counters, 2 * sizeof(unsigned) * MB_COUNTERS)) != cudaSuccess) return bail(e, "cudaMalloc(counters)");
+   if ((e = cudaMemset(h->d_counters, 0, 2 * sizeof(unsigned) * MB_COUNTERS)) != cudaSuccess) return bail(e, "cudaMemset(counters)");
    if ((e = cudaMemcpy(h->d_consts, h->tree.consts.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(consts)");
    {
       std::vector<char> isz((size_t)h->tree.nv * h->tree.nv, 0);
@@ -677,6 +685,7 @@ int mecano_b200_create(const mecano_b200_tree_desc *desc, int device, mecano_b20
       if (!fits)
       {
          cudaFree(h->d_consts);
+         if (h->d_counters) cudaFree(h->d_counters);
          if (h->d_zero) cudaFree(h->d_zero);
          delete h;
          return fail(nullptr, MECANO_B200_ERR_TOO_LARGE, "tree exceeds the compiled per-state work areas (branch nesting / depth too large)");
@@ -730,6 +739,7 @@ void mecano_b200_destroy(mecano_b200_handle *h)
    if (h->d_zero_row) cudaFree(h->d_zero_row);
    if (h->d_scratch) cudaFree(h->d_scratch);
    if (h->d_consts) cudaFree(h->d_consts);
+   if (h->d_counters) cudaFree(h->d_counters);
    if (h->d_zero) cudaFree(h->d_zero);
    if (h->d_prog) cudaFree(h->d_prog);
    for (int i = 0; i < 1 + MB_MAX_SLOTS; i++)

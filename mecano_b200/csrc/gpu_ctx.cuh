@@ -376,25 +376,57 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    c2.wsb = reinterpret_cast<double2 *>(a.ws) + ((long long)blockIdx.x * BLOCK + threadIdx.x);
    c2.discard_on = ALGO == MB_ABA && (a.flags & MB_KFLAG_ABA_DISCARD) != 0;
    c2.ws_ld = a.ws_ld;
-   // persistent grid: each block walks over tiles of BLOCK states.  The per-state areas (stack, rings) are private to a
-   // thread and the constant records are read-only, so the threads of a block never synchronise again.
-   const long long ntiles = (a.n + BLOCK - 1) / BLOCK;
-   // The warps of a block start together and run the same op sequence, so the warps that share a scheduler (warp % 4) would
-   // stay in phase for good: all of them in the FP64 burst of an op at once (pipe-bound, issue slots idle), then all of them in
-   // its bookkeeping (issue-bound, FP64 pipe idle).  Contention slows them down equally, so an offset given once persists:
-   // slot j of a scheduler starts j * stagger_ns late and the bursts of one warp overlap the bookkeeping of another.
+   // The warps of a block start together and run the same op sequence; MECANO_B200_STAGGER_NS starts slot j of a scheduler
+   // (warp / 4) j * stagger_ns late.  Measured: no effect (profiles/r06d_plain_kinds.md), the warps are not marching in phase.
    if (a.stagger_ns > 0)
       __nanosleep((threadIdx.x >> 7) * (unsigned)a.stagger_ns);
-   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+   // Work distribution.  One block per tile of BLOCK states, or -- persistent grids (TMEM stack, ABA workspace) -- every warp
+   // draws the next 32 states from a counter (a.work_counter, zeroed by the launcher).  Drawing keeps the states in flight one
+   // compact, advancing stretch of every row however far the warps drift apart (a static round-robin over tiles lets slow blocks
+   // fall rounds behind; contiguous ranges per block -- 148 streams 57 KB apart in every row -- measured 10-12 % slower), and it
+   // ends without a partial last round (2^20 states are 18.45 rounds of 148 tiles of 384: 81 SMs idle during the last one).
+   // The per-state areas (stack, rings) are private to a thread and the constant records are read-only, so the threads of a block
+   // never synchronise again.
+   const long long ntiles = (a.n + BLOCK - 1) / BLOCK;
+   long long tile = blockIdx.x;
+   for (;;)
    {
-      long long s = tile * BLOCK + threadIdx.x;
+      long long s;
+      const long long hi = a.n;
+      if (a.work_counter != nullptr)
+      {
+         unsigned first = 0;
+         if ((threadIdx.x & 31) == 0)
+            first = atomicAdd(a.work_counter, 32u);
+         first = __shfl_sync(0xffffffffu, first, 0);
+         if ((long long)first >= hi)
+         {
+            // the last warp of the grid to run dry re-arms the counter pair for the next launch (no memset between launches)
+            if ((threadIdx.x & 31) == 0 && atomicAdd(a.work_counter + 1, 1u) == gridDim.x * (BLOCK / 32) - 1)
+            {
+               a.work_counter[0] = 0;
+               a.work_counter[1] = 0;
+            }
+            break;
+         }
+         s = (long long)first + (threadIdx.x & 31);
+      }
+      else
+      {
+         if (tile >= ntiles)
+            break;
+         s = tile * BLOCK + threadIdx.x;
+         tile += gridDim.x;
+      }
+      // (every exit of this loop above is warp-uniform and visibly so -- a kernel parameter, the block index, a value shuffled from
+      // lane 0: with a thread-dependent exit ptxas gives up the uniform datapath for the whole traversal, +12 % on RNEA and ABA)
       if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kClamp)
       {
          // tcgen05.ld/st are warp-collective (.sync.aligned): padding lanes run a clamped state and store nothing
-         c2.active = s < a.n;
-         s = min(s, a.n - 1);
+         c2.active = s < hi;
+         s = s < hi ? s : hi - 1;
       }
-      else if (s >= a.n)
+      else if (s >= hi)
          break;
       c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
       c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);

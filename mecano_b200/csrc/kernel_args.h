@@ -30,6 +30,8 @@ struct KernelArgs
    double grav[3];
    uint32_t flags;
    int32_t nv;
+   unsigned *work_counter; // persistent thread-per-state launches (nullable): [0] next unassigned state -- warps draw 32 states at a time --,
+                           // [1] warps that have run dry; both zero between launches (gpu_ctx.cuh: thread_block_run)
    int32_t stagger_ns; // thread-per-state kernels: warp slot j of a scheduler (warp / 4) starts j * stagger_ns late (gpu_ctx.cuh)
 };
 

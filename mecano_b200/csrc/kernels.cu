@@ -196,6 +196,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
       const unsigned g = (algo == MB_ABA || plan.tm > 0) ? (unsigned)std::min<long long>(nt, plan.grid) : (unsigned)nt;
       KernelArgs b = a;
       b.ws_ld = (long long)plan.grid * plan.block;
+      b.work_counter = nullptr;
       pick_f32(algo)<<<g, plan.block, plan.smem, stream>>>(P, b);
       return cudaGetLastError();
    }
@@ -209,6 +210,11 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    const unsigned grid = (algo == MB_ABA || plan.tm > 0 || persist_all) ? (unsigned)std::min<long long>(ntiles, plan.grid) : (unsigned)ntiles;
    KernelArgs b = a;
    b.ws_ld = (long long)plan.grid * plan.block;
+   const bool persistent = grid < (unsigned)ntiles;
+   static const bool draw = [] { const char *e = getenv("MECANO_B200_DRAW"); return !e || atoi(e) != 0; }();
+   // the warps of a persistent grid draw their states from a counter that the kernel itself re-arms (gpu_ctx.cuh: thread_block_run)
+   if (!(persistent && draw))
+      b.work_counter = nullptr;
    fn<<<grid, plan.block, plan.smem, stream>>>(P, b);
    return cudaGetLastError();
 }

@@ -12,7 +12,8 @@ while [ $# -ge 2 ]; do
    for g in 0 2; do
       nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden $FLAGS -DMB_INST=$g -c kern_inst.cu -o build/var/${NAME}_kinst_$g.o &
    done
-   g++ -O2 -std=c++17 -fPIC -fvisibility=hidden $FLAGS -c flatten.cpp -o build/var/${NAME}_flatten.o &
+   CXXDEFS=$(echo " $FLAGS" | grep -o ' -D[^ ]*' | tr '\n' ' ') # only the -D switches go to the host compiler
+   g++ -O2 -std=c++17 -fPIC -fvisibility=hidden $CXXDEFS -c flatten.cpp -o build/var/${NAME}_flatten.o &
    wait
    OTHERS=$(ls build/*.o | grep -v "build/kinst_0.o\|build/kinst_2.o\|build/flatten.o\|build/kernels_")
    nvcc $ARCH -shared -o ../variants/$NAME.so $OTHERS build/var/${NAME}_kinst_0.o build/var/${NAME}_kinst_2.o build/var/${NAME}_flatten.o -ldl
