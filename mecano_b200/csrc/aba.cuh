@@ -137,9 +137,16 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
    if (SC)
       mb_sincos(pp.mq, &ns, &nc);
    const auto C = c.cst(o.body);
-   T s = pp.ls, cs = pp.lc;
-   SvT<T> vb = v;
-   if (!(o.flags & MB2_LEAF))
+   // twist and sin/cos of the body: still in registers for a leaf (its DESCEND was the op before), otherwise on the stack
+   T s, cs;
+   SvT<T> vb;
+   if (o.flags & MB2_LEAF)
+   {
+      vb = v;
+      s = pp.ls;
+      cs = pp.lc;
+   }
+   else
    {
       c.acc_ld(o.slot, o.wslot, vb.a.x, vb.a.y, vb.a.z, vb.l.x, vb.l.y, vb.l.z);
       c.jp_ld2(o.slot, o.nslot, 0, s, cs);

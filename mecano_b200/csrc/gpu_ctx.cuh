@@ -63,6 +63,13 @@ __device__ __forceinline__ const char *mb_row(const char *base, unsigned r, unsi
    return (const char *)p;
 }
 
+// the same for a base pointer shared by the grid plus a per-thread byte offset: base + r * ld8 stays on the uniform datapath, the
+// thread adds its 32-bit offset (one IADD3 pair), and no 64-bit per-thread pointer has to be kept (or spilled) per buffer
+__device__ __forceinline__ const char *mb_row_s(const char *ubase, unsigned r, unsigned ld8, unsigned s8)
+{
+   return (const char *)((unsigned long long)ubase + (unsigned long long)r * ld8 + s8);
+}
+
 __device__ __forceinline__ double mb_ldg(const char *p)
 {
    double v;
@@ -75,8 +82,21 @@ __device__ __forceinline__ void mb_stg_cs(const char *p, double v) { asm volatil
 template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
 {
    static constexpr bool kM3 = M3; // this instantiation handles three-DoF joints (multidof.cuh)
-   const char *qb, *qdb, *xb, *fb;
+   // Two ways to address a row of an input / output buffer.  Per-thread 64-bit pointers (base + state), one IMAD.WIDE per access:
+   // RNEA, CRBA.  Or the launch's base pointers (kernel parameters: uniform) plus this thread's state as a 32-bit byte offset, so that
+   // base + row * ld stays on the uniform datapath and five 64-bit pointers per thread become one register: ABA, whose 168 registers
+   // otherwise spill them (a reload in front of every prefetch).  Measured (r06n): ABA -0.7 %, RNEA +5 % -- hence per algorithm.
+   static constexpr bool kUBase = ROWS == 2; // ring_rows(MB_ABA)
+   const char *q0, *qd0, *x0;
+   char *o0;
+   unsigned s8; // (the launcher keeps n * 8 < 2^31)
+   const char *qb, *qdb, *xb;
    char *ob;
+   __device__ __forceinline__ const char *row_q(unsigned r) const { return kUBase ? mb_row_s(q0, r, ld8, s8) : mb_row(qb, r, ld8); }
+   __device__ __forceinline__ const char *row_qd(unsigned r) const { return kUBase ? mb_row_s(qd0, r, ld8d, s8) : mb_row(qdb, r, ld8d); }
+   __device__ __forceinline__ const char *row_x(unsigned r) const { return kUBase ? mb_row_s(x0, r, ld8x, s8) : mb_row(xb, r, ld8x); }
+   __device__ __forceinline__ const char *row_o(unsigned r) const { return kUBase ? mb_row_s(o0, r, ld8, s8) : mb_row(ob, r, ld8); }
+   const char *fb;
    unsigned ld8; // bytes between consecutive rows (the launcher keeps ld * 8 < 2^32)
    unsigned ld8d, ld8x; // the same for qd and x (0: one row of zeros stands in for every row)
    unsigned sb;  // shared address of this thread's element of shared-memory stack slot 0
@@ -96,11 +116,11 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    bool active;  // false for the padding lanes of the last tile (CRBA: they store nothing)
    double *aux; // local memory
 
-   __device__ __forceinline__ double ld_q(int r) const { return mb_ldg(mb_row(qb, (unsigned)r, ld8)); }
-   __device__ __forceinline__ double ld_qd(int r) const { return mb_ldg(mb_row(qdb, (unsigned)r, ld8d)); }
-   __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(mb_row(xb, (unsigned)r, ld8x)); }
+   __device__ __forceinline__ double ld_q(int r) const { return mb_ldg(row_q((unsigned)r)); }
+   __device__ __forceinline__ double ld_qd(int r) const { return mb_ldg(row_qd((unsigned)r)); }
+   __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(row_x((unsigned)r)); }
    __device__ __forceinline__ double ld_fext(int b, int k) const { return mb_ldg(mb_row(fb, (unsigned)(6 * b + k), ld8)); }
-   __device__ __forceinline__ void st_out(int r, double v) { mb_stg(mb_row(ob, (unsigned)r, ld8), v); }
+   __device__ __forceinline__ void st_out(int r, double v) { mb_stg(row_o((unsigned)r), v); }
    // optional buffers of the FEXT instantiation (nullptr = absent): external wrenches in, RNEA by-products out
    char *accb, *wrb;
    const char *x2b;
@@ -201,27 +221,28 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
    // ABA pass-two records: global workspace of double2, one column per resident thread (coalesced 16-byte accesses),
    // read back in pass three through the ring below with cp.async.cg (L2, the coherence point of the earlier stores)
-   double2 *wsb;       // workspace + column of this thread
-   long long ws_ld;
-   __device__ __forceinline__ void rec_st2(int i2, double a, double b) { wsb[i2 * ws_ld] = make_double2(a, b); }
+   const char *ws0;   // workspace (uniform)
+   unsigned ws_ld16;  // bytes between consecutive record slots (the launcher keeps the workspace below 4 GB)
+   unsigned w16;      // byte offset of this thread's column
+   __device__ __forceinline__ const char *rec_at(int i2) const { return mb_row_s(ws0, (unsigned)i2, ws_ld16, w16); }
+   __device__ __forceinline__ void rec_st2(int i2, double a, double b) { *reinterpret_cast<double2 *>(const_cast<char *>(rec_at(i2))) = make_double2(a, b); }
    // direct read of a record slot in pass three (after pass_fence; the second half of a three-DoF joint's record, which
    // does not travel through the ring): L2 is the coherence point of the earlier stores
    __device__ __forceinline__ void rec_ld2(int i2, double &a, double &b) const
    {
-      asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(wsb + i2 * ws_ld) : "memory");
+      asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(rec_at(i2)) : "memory");
    }
    // pass-three ring: [stage][(q, qd) | rec0 .. rec2][BLOCK] double2, overlaid on the (then idle) stack area
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
    {
       const unsigned dst = sb + (unsigned)(stage * (MB_ABA_RING_ROWS * BLOCK * 16));
       if (mask & 1)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(row_q((unsigned)cfg)) : "memory");
       if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(mb_row(qdb, (unsigned)dof, ld8d)) : "memory");
-      const double2 *src = wsb + rec2 * ws_ld;
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(row_qd((unsigned)dof)) : "memory");
 #pragma unroll
       for (int j = 0; j < MB_ABA_REC / 2; j++)
-         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(src + j * ws_ld) : "memory");
+         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(rec_at(rec2 + j)) : "memory");
    }
    __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const { mb_lds2(sb + (unsigned)((stage * MB_ABA_RING_ROWS + row) * (BLOCK * 16)), a, b); }
    // The record of a body is dead once pass three has read it: tell L2 so (discard.global.L2 drops the lines without writing
@@ -231,10 +252,9 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    {
       if (discard_on && (threadIdx.x & 7u) == 0)
       {
-         const double2 *src = wsb + rec2 * ws_ld;
 #pragma unroll
          for (int j = 0; j < MB_ABA_REC / 2; j++)
-            asm volatile("discard.global.L2 [%0], 128;" ::"l"(src + j * ws_ld) : "memory");
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(rec_at(rec2 + j)) : "memory");
       }
    }
    __device__ __forceinline__ void pass_fence() const { __threadfence(); }
@@ -307,11 +327,11 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    {
       const unsigned dst = rb + (unsigned)(stage * (ROWS * BLOCK * 8));
       if (mask & 1)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(mb_row(qb, (unsigned)cfg, ld8)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(row_q((unsigned)cfg)) : "memory");
       if (mask & 2)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(mb_row(qdb, (unsigned)dof, ld8d)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + BLOCK * 8), "l"(row_qd((unsigned)dof)) : "memory");
       if (mask & 4)
-         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(mb_row(xb, (unsigned)dof, ld8x)) : "memory");
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (ROWS == 3 ? 2 : 0) * BLOCK * 8), "l"(row_x((unsigned)dof)) : "memory");
    }
    __device__ __forceinline__ void pf_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
    template <int N> __device__ __forceinline__ void pf_wait() const { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -373,9 +393,11 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    c2.mstride = STATE_MAJOR ? 8u : c2.ld8;
    c2.zlist = (const uint4 *)a.zero_entries;
    c2.nz8 = a.n_zero >> 3;
-   c2.wsb = reinterpret_cast<double2 *>(a.ws) + ((long long)blockIdx.x * BLOCK + threadIdx.x);
+   c2.ws0 = reinterpret_cast<const char *>(a.ws);
+   c2.w16 = (blockIdx.x * BLOCK + threadIdx.x) * 16u;
+   c2.ws_ld16 = (unsigned)(a.ws_ld * 16);
+   c2.q0 = (const char *)a.q; c2.qd0 = (const char *)a.qd; c2.x0 = (const char *)a.x; c2.o0 = (char *)a.out;
    c2.discard_on = ALGO == MB_ABA && (a.flags & MB_KFLAG_ABA_DISCARD) != 0;
-   c2.ws_ld = a.ws_ld;
    // The warps of a block start together and run the same op sequence; MECANO_B200_STAGGER_NS starts slot j of a scheduler
    // (warp / 4) j * stagger_ns late.  Measured: no effect (profiles/r06d_plain_kinds.md), the warps are not marching in phase.
    if (a.stagger_ns > 0)
@@ -428,8 +450,9 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       }
       else if (s >= hi)
          break;
-      c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s);
-      c2.fb = (const char *)(a.fext + s); c2.ob = (char *)(a.out + s);
+      c2.s8 = (unsigned)s * 8u;
+      c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s); c2.ob = (char *)(a.out + s);
+      c2.fb = (const char *)(a.fext + s);
       c2.accb = (char *)(a.body_acc + s); c2.wrb = (char *)(a.joint_wrench + s);
       c2.x2b = (const char *)(a.x2 + s);
       c2.corb = (char *)(a.cor + s);
