@@ -568,6 +568,7 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
    constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SCK = (KIND & MB2_SC) != 0, PLAIN = (KIND & MB_RUN_PLAIN) != 0;
    constexpr int JT = (KIND >> 1) & 3;
    static_assert(!(ASC && SCK), "ASCEND kinds do not carry the SC bit");
+   constexpr bool DYN_SC = ASC || !MB_ABA_D_SC_SPLIT; // SC tested at run time (not part of the run kind)
    MbOp2 o = P.op2[k];
    // plain runs (rnea.cuh: rnea_run_step): the flags of the op are those of the common case of its kind, i.e. constants
    if (PLAIN)
@@ -575,14 +576,14 @@ MB_HD void aba_run_step(const MbProgram &P, Ctx &c, const int k, SvT<T> &v, AbiT
       o.flags = (uint8_t)mb_run_plain_flags(MB_ABA, KIND & 0xf, false);
       o.pf = (!ASC && SCK) ? (uint8_t)(o.pf | MB2_PF_NEXT1) : (ASC ? o.pf : (uint8_t)(o.pf & ~MB2_PF_NEXT1));
    }
-   else if (!ASC && SCK)
+   else if (!DYN_SC && SCK)
       o.pf |= MB2_PF_NEXT1; // the SC bit implies that a one-DoF DESCEND follows
    aba_pre<T, Ctx>(c, k, o, JT != MB_SIXDOF, ASC, !ASC && JT == MB_REVOLUTE, v, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
-   if (ASC || JT == MB_SIXDOF)
+   if (DYN_SC || JT == MB_SIXDOF)
    {
-      if (ASC ? (o.code & MB2_SC) != 0 : SCK)
+      if (DYN_SC ? (o.code & MB2_SC) != 0 : SCK)
          mb_sincos(pp.mq, &ns, &nc);
    }
    if (JT == MB_SIXDOF)
@@ -640,7 +641,9 @@ template <class T, class Ctx, bool FEXT> MB_HD void aba_state(const MbProgram &P
       switch (R.kind)
       {
          MB_RUN_CASE(0) MB_RUN_CASE(1) MB_RUN_CASE(2) MB_RUN_CASE(3) MB_RUN_CASE(4) MB_RUN_CASE(5)
+#if MB_ABA_D_SC_SPLIT
          MB_RUN_CASE(8) MB_RUN_CASE(10) MB_RUN_CASE(12)
+#endif
 #if MB_PLAIN_ABA & 7
          MB_RUN_CASE_IF(MB_PLAIN_ABA & 1, MB_RUN_PLAIN | 0) MB_RUN_CASE_IF(MB_PLAIN_ABA & 2, MB_RUN_PLAIN | 1) MB_RUN_CASE_IF(MB_PLAIN_ABA & 4, MB_RUN_PLAIN | 8)
 #endif

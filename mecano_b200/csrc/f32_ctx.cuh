@@ -145,6 +145,7 @@ template <class Ctx> struct F32Ctx
    __device__ __forceinline__ void pf_commit() const { c.pf_commit(); }
    template <int N> __device__ __forceinline__ void pf_wait() const { c.template pf_wait<N>(); }
    __device__ __forceinline__ float pf_ld(int stage, int j) const { return (float)c.pf_ld(stage, j); }
+   static constexpr bool kFastQuat = false;
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const { c.pf3_issue(stage, cfg, dof, rec2, mask); }
    __device__ __forceinline__ void pf3_ld2(int stage, int row, float &a, float &b) const
    {

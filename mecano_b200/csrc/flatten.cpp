@@ -133,7 +133,7 @@ void build_runs(int algo, MbProgram &P, int n3)
       int nr = 0;
       for (int k = 0; k < n; k++)
       {
-         uint8_t kind = ops[k].code & ((algo == MB_ABA && (pass3 || (ops[k].code & MB2_ASCEND))) ? 0x7u : 0xfu);
+         uint8_t kind = ops[k].code & (mb_run_kind_has_sc(algo, ops[k].code & 0xf, pass3) ? 0xfu : 0x7u);
          const unsigned tested = mb_run_plain_tested(algo, kind, pass3);
          if (tested)
          {

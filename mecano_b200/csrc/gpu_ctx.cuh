@@ -87,6 +87,7 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    // base + row * ld stays on the uniform datapath and five 64-bit pointers per thread become one register: ABA, whose 168 registers
    // otherwise spill them (a reload in front of every prefetch).  Measured (r06n): ABA -0.7 %, RNEA +5 % -- hence per algorithm.
    static constexpr bool kUBase = ROWS == 2; // ring_rows(MB_ABA)
+   static constexpr bool kFastQuat = ROWS == 2; // spatial.cuh: quat_to_rot
    const char *q0, *qd0, *x0;
    char *o0;
    unsigned s8; // (the launcher keeps n * 8 < 2^31)

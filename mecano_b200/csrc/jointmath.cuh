@@ -147,23 +147,7 @@ inline void mb_sincos_redo(double x, double &s, double &c) { s = sin(x); c = cos
 #endif
 template <class T> MB_HD void mb_sincos_redo(T, T &, T &) {}
 
-// Reciprocal without the library's special-case branch (which would split the basic block of an ABA op): hardware
-// seed (rcp.approx.ftz.f64, ~2^-20) + three Newton steps.  Used for the joint-space inertia D = S^T I^A S of a
-// 1-DoF joint, a well-scaled positive number.
-MB_HD double mb_rcp(double x)
-{
-#if defined(__CUDA_ARCH__)
-   double r;
-   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-   r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
-   r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
-   r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
-   return r;
-#else
-   return 1.0 / x;
-#endif
-}
-MB_HD float mb_rcp(float x) { return 1.0f / x; }
+// (mb_rcp: spatial.cuh)
 
 MB_HD bool mb2_is_1dof_descend(const MbOp2 &o) { return !(o.code & MB2_ASCEND) && MB2_JT(o.code) != MB_SIXDOF; }
 
@@ -317,7 +301,7 @@ template <class T, class Ctx, class CP> MB_HD XfT<T> joint_xf_6dof(Ctx &c, const
    M3T<T> R0;
    V3T<T> p0;
    ld_xf0<T>(C, R0, p0);
-   const M3T<T> Rq = quat_to_rot(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3));
+   const M3T<T> Rq = quat_to_rot<T, Ctx::kFastQuat>(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3));
    X.R = mul(R0, Rq);
    X.p = p0 + mul(R0, v3<T>(c.ld_q(r + 4), c.ld_q(r + 5), c.ld_q(r + 6)));
    return X;

@@ -35,7 +35,7 @@ template <class T, class Ctx, class CP> MB_HD XfT<T> joint_xf_multi(Ctx &c, cons
    if (sub == MB_SUB_SPHERICAL)
    {
       // SphericalJointReadOnly.java:31-35: setRotationAndZeroTranslation(jointOrientation)
-      X.R = mul(R0, quat_to_rot(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3)));
+      X.R = mul(R0, quat_to_rot<T, Ctx::kFastQuat>(c.ld_q(r), c.ld_q(r + 1), c.ld_q(r + 2), c.ld_q(r + 3)));
       X.p = p0;
    }
    else

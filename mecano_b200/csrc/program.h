@@ -143,6 +143,17 @@ struct MbWalk
 #ifndef MB_PLAIN_ABA
 #define MB_PLAIN_ABA 0
 #endif
+// whether the ABA DESCEND runs are split by the SC bit (sin/cos of the next joint evaluated inside the op's basic block): 1, or
+// tested at run time like in its ASCEND runs (one loop body less): 0
+// Measured (r06o, 2^20 H37 states): 1.575 -> 1.550 ms without the split -- once pass three had lost its sin/cos (records), one loop body
+// less is worth more to ABA than the overlap of the sin/cos chain with the twist propagation.
+#ifndef MB_ABA_D_SC_SPLIT
+#define MB_ABA_D_SC_SPLIT 0
+#endif
+// the same switch for RNEA (all its runs)
+#ifndef MB_RNEA_SC_SPLIT
+#define MB_RNEA_SC_SPLIT 1
+#endif
 // the flags a kind tests (rnea.cuh / aba.cuh), 0 if the kind has no plain form.  kind = MbOp2::code & 0xf; pass3: ABA pass-three list.
 // Plain forms exist for revolute joints: the DESCEND of an interior body (SC set: the next joint of the chain is revolute too), the
 // DESCEND of a leaf (no SC: its own ASCEND follows) and the ASCEND of an interior body with a single child.
@@ -181,7 +192,12 @@ static inline unsigned mb_run_plain_flags(int algo, int kind, bool pass3)
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-static inline bool mb_run_kind_has_sc(int algo, int kind, bool pass3) { return !(algo == 1 /* MB_ABA */ && (pass3 || (kind & MB2_ASCEND))); }
+static inline bool mb_run_kind_has_sc(int algo, int kind, bool pass3)
+{
+   if (algo == 0 /* MB_RNEA */)
+      return MB_RNEA_SC_SPLIT != 0;
+   return !(algo == 1 /* MB_ABA */ && (pass3 || (kind & MB2_ASCEND) || !MB_ABA_D_SC_SPLIT));
+}
 struct MbRun
 {
    uint8_t kind; // MbOp2::code & 0xf | MB_RUN_PLAIN

@@ -276,19 +276,25 @@ template <class T, class Ctx, bool FEXT, int KIND>
 MB_HD void rnea_run_step(const MbProgram &P, Ctx &c, const int k, const T *grav, SvT<T> &v, SvT<T> &a, SvT<T> &f, RneaPipe<T> &pp)
 {
    constexpr bool ASC = (KIND & MB2_ASCEND) != 0, SC = (KIND & MB2_SC) != 0, PLAIN = (KIND & MB_RUN_PLAIN) != 0;
+   constexpr bool DYN_SC = !MB_RNEA_SC_SPLIT; // SC tested at run time instead of being part of the run kind
    constexpr int JT = (KIND >> 1) & 3;
    MbOp2 o = P.op2[k];
-   if (SC)
+   if (!DYN_SC && SC)
       o.pf |= MB2_PF_NEXT1;
    if (PLAIN)
    {
       o.flags = (uint8_t)mb_run_plain_flags(MB_RNEA, KIND & 0xf, false);
-      if (!SC)
+      if (!DYN_SC && !SC)
          o.pf &= (uint8_t)~MB2_PF_NEXT1;
    }
    rnea_pre<T, Ctx>(c, k, o, !ASC && JT != MB_SIXDOF, !ASC, !ASC && JT == MB_REVOLUTE, grav, v, a, pp);
    const int ext = FEXT ? P.body[o.body].ext_index : 0;
    T ns = pp.mq, nc = (T)1;
+   if (DYN_SC)
+   {
+      if (o.code & MB2_SC)
+         mb_sincos(pp.mq, &ns, &nc);
+   }
    if (JT == MB_SIXDOF)
    {
       if (SC) mb_sincos(pp.mq, &ns, &nc);

@@ -50,6 +50,7 @@ namespace
 template <class T> struct CpuCtx
 {
    static constexpr bool kM3 = true; // three-DoF joints compiled in (multidof.cuh)
+   static constexpr bool kFastQuat = false;
    const double *q, *qd, *x, *fext;
    double *out, *M;
    long ld, s;
