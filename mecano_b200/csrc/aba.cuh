@@ -243,12 +243,16 @@ MB_HD void aba_ascend_1dof(Ctx &c, const MbOp2 o, int ext, const SvT<T> &v, AbiT
 template <class T, class Ctx> MB_HD void aba_descend_6dof(Ctx &c, const MbOp2 o, SvT<T> &v)
 {
    const int sub = mb_sub_of<Ctx>(o);
-   const XfT<T> X = joint_xf_multi<T>(c, c.cst(o.body), o.cfg, sub);
    const SvT<T> vj = ld_svj<T>(o.dof, sub, [&](int r) { return c.ld_qd(r); });
-   v = motion_to_child(X, v) + vj;
-   c.acc_st(o.slot, o.wslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
-   if (!(o.flags & MB2_ROOT_PARENT))
+   if (o.flags & MB2_ROOT_PARENT)
+      v = vj; // a floating base: the root body is at rest, and nothing is folded into it, so passes one and two need no transform
+   else
+   {
+      const XfT<T> X = joint_xf_multi<T>(c, c.cst(o.body), o.cfg, sub);
+      v = motion_to_child(X, v) + vj;
       jp_st_xf<T>(c, o.slot, o.nslot, X);
+   }
+   c.acc_st(o.slot, o.wslot, v.a.x, v.a.y, v.a.z, v.l.x, v.l.y, v.l.z);
 }
 
 template <class T, class Ctx, bool FEXT>
@@ -380,8 +384,19 @@ template <class T, class Ctx, bool LOCKS> MB_HD void aba_pass3_6dof(Ctx &c, cons
    c.rec_discard(o.body * (MB_ABA_REC / 2));
    const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
    const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
-   v = motion_to_child(X, v) + vj;
-   const SvT<T> a1 = motion_to_child(X, a) + cross_motion(v, vj);
+   SvT<T> a1;
+   if (o.flags & MB2_ROOT_PARENT)
+   {
+      // a floating base: the root body is at rest and its acceleration is -gravity, purely linear: v = vj, v x vj = 0
+      v = vj;
+      a1.a = v3<T>((T)0, (T)0, (T)0);
+      a1.l = mulT(X.R, a.l);
+   }
+   else
+   {
+      v = motion_to_child(X, v) + vj;
+      a1 = motion_to_child(X, a) + cross_motion(v, vj);
+   }
    // effort source: a = x, qdd = x - a'; acceleration source (the record holds the given acceleration): qdd = x, a = a' + x
    SvT<T> qdd;
    if (LOCKS && (o.flags & MB2_ACCSRC))
