@@ -174,7 +174,9 @@ int mecano_b200_set_precision(mecano_b200_handle *h, int precision);
  * thread, MultiBodySystemFactories.java:310-348; here: one per stream).  The thread-per-state RNEA and ABA kernels are persistent
  * grids that by default fill every SM, and each of their blocks owns its SM (registers, tensor memory); max_blocks caps the
  * grid of `algo` (MECANO_B200_ALGO_*) so that a concurrent kernel -- typically the bandwidth-bound mass matrix next to the
- * FP64-bound forward dynamics -- finds free SMs.  0 = no cap.  Results do not depend on it.
+ * FP64-bound forward dynamics -- finds free SMs.  0 = no cap.  Results do not depend on it.  (The warps of a persistent grid draw
+ * their states, 32 at a time, from a counter owned by the handle -- a fresh one per launch out of a ring of 256 -- instead of taking
+ * tiles in a fixed order; which warp evaluates a state has no influence on its result.)
  */
 int mecano_b200_set_grid_limit(mecano_b200_handle *h, int algo, int max_blocks);
 

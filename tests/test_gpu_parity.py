@@ -169,6 +169,33 @@ def test_angles_beyond_the_fast_sincos_range(torch_dev, idx, variant):
         assert rel(crba.getMassMatrix(tq).cpu().numpy().reshape(t.nv, t.nv, n), o.crba_batch(q)) < TOL, name
 
 
+def test_work_distribution_of_the_persistent_grids_is_result_neutral(torch_dev):
+    """The warps of a persistent grid (RNEA / ABA with the stack in tensor memory) draw their states from a counter; MECANO_B200_DRAW=0
+    falls back to tiles taken round-robin.  Which warp evaluates a state must not show in the result: both settings, twice each (the
+    counter re-arms itself between launches), bit for bit; and a batch that is not a multiple of the warp size."""
+    import subprocess
+    import sys
+
+    code = (
+        "import hashlib, numpy as np, torch, mecano_b200 as mb\n"
+        "e = mb.RigidBody('elevator'); mb.MultiBodySystemRandomTools.nextHumanoid(11, e, 2)\n"
+        "s = mb.MultiBodySystem.toMultiBodySystemBasics(e); n = 300007\n"
+        "rng = np.random.default_rng(5); q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, n)\n"
+        "d = torch.device('cuda:0'); tq, tqd, tqdd, ttau = (torch.from_numpy(x).to(d) for x in (q, qd, qdd, tau))\n"
+        "i = mb.InverseDynamicsCalculator(s); f = mb.ForwardDynamicsCalculator(s)\n"
+        "assert i.kernelInfo(n)['tmem_stack_slots'] > 0 and f.kernelInfo(n)['tmem_stack_slots'] > 0\n"
+        "for k in range(2):\n"
+        "    a = i.compute(tq, tqd, tqdd).cpu().numpy(); b = f.compute(tq, tqd, ttau).cpu().numpy()\n"
+        "    print(hashlib.sha256(a.tobytes() + b.tobytes()).hexdigest())\n")
+    out = []
+    for draw in ("1", "0"):
+        env = dict(os.environ, MECANO_B200_DRAW=draw, PYTHONPATH=os.pathsep.join([os.path.dirname(os.path.dirname(os.path.abspath(__file__)))] + sys.path))
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out += r.stdout.split()
+    assert len(out) == 4 and len(set(out)) == 1, out
+
+
 def test_host_entry_points_and_leading_dimension(torch_dev):
     """*_host entry points (numpy in, numpy out), with ld > n, plus empty and single-state batches."""
     import mecano_b200 as mb
