@@ -4,9 +4,10 @@
 //
 // Passes one and two are interleaved along the depth-first traversal (DESCEND = twist of the body, ASCEND =
 // articulated inertia / bias force folded into the parent), so only the current root-to-leaf path is live on the
-// shared-memory stack; pass three is a second, DESCEND-only sweep.  What pass three needs from pass two
-// (g = U / D and k0 = u / D, seven doubles per body) goes through per-thread local memory, whose footprint is
-// bounded by the resident threads and therefore stays in L2; sin/cos and the twists are recomputed instead.
+// stack (wide part in tensor memory, narrow part in shared memory); pass three is a second, DESCEND-only sweep.  What
+// pass three needs from pass two (g = U / D, k0 = u / D and the sin/cos of the joint: eight doubles per body, program.h:
+// MB_ABA_REC) goes through a global workspace with one column per resident thread of the persistent grid, streamed back by
+// cp.async through a ring; the twists are recomputed instead of stored.
 #pragma once
 #include "jointmath.cuh"
 

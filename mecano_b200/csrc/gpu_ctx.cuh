@@ -114,6 +114,9 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
 #else
    static constexpr bool kClamp = TM > 0;
 #endif
+   // padding lanes of the last warp can be running a clamped state: kernels with a TMEM stack, and every persistent RNEA / ABA grid
+   // (drawn states, thread_block_run); the mass-matrix kernels (one ring row) never draw, their stores stay unguarded
+   static constexpr bool kMayClamp = kClamp || ROWS != 1;
    bool active;  // false for the padding lanes of the last tile (CRBA: they store nothing)
    double *aux; // local memory
 
@@ -132,11 +135,11 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    // read-modify-write by the one thread that owns the state (the padding lanes of a clamped tile repeat the last state: not them)
    __device__ __forceinline__ void add_com(int r, double v)
    {
-      if (!kClamp || active) { double *p = (double *)mb_row(comb, (unsigned)r, ld8); *p += v; }
+      if (!kMayClamp || active) { double *p = (double *)mb_row(comb, (unsigned)r, ld8); *p += v; }
    }
    __device__ __forceinline__ void add_rootw(int r, double v)
    {
-      if (!kClamp || active) { double *p = (double *)mb_row(rwb, (unsigned)r, ld8); *p += v; }
+      if (!kMayClamp || active) { double *p = (double *)mb_row(rwb, (unsigned)r, ld8); *p += v; }
    }
    __device__ __forceinline__ double ld_x2(int r) const { return mb_ldg(mb_row(x2b, (unsigned)r, ld8)); }
    bool fext_on, acc_on, wr_on;
@@ -274,13 +277,13 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    __device__ __forceinline__ int n_dofs() const { return nv; }
    __device__ __forceinline__ void st_M(int e, double v) const
    {
-      if (!kClamp || active)
+      if (!kMayClamp || active)
          mb_stg_cs(mb_row(mbase, (unsigned)e, mstride), v);
    }
    char *corb; // Coriolis matrix (MB_CORIOLIS), entry-major
    __device__ __forceinline__ void st_C(int e, double v) const
    {
-      if (!kClamp || active)
+      if (!kMayClamp || active)
          mb_stg_cs(mb_row(corb, (unsigned)e, ld8), v);
    }
    __device__ __forceinline__ void zero_fill_mc_part(int k, int parts) const
@@ -416,7 +419,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    {
       long long s;
       const long long hi = a.n;
-      if (a.work_counter != nullptr)
+      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kMayClamp && a.work_counter != nullptr)
       {
          unsigned first = 0;
          if ((threadIdx.x & 31) == 0)
@@ -443,14 +446,15 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       }
       // (every exit of this loop above is warp-uniform and visibly so -- a kernel parameter, the block index, a value shuffled from
       // lane 0: with a thread-dependent exit ptxas gives up the uniform datapath for the whole traversal, +12 % on RNEA and ABA)
-      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kClamp)
+      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kClamp || (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kMayClamp && a.work_counter != nullptr))
       {
-         // tcgen05.ld/st are warp-collective (.sync.aligned): padding lanes run a clamped state and store nothing
+         // tcgen05.ld/st and the draw above are warp-collective: the padding lanes of the last warp run a clamped state (and store
+         // nothing, or the same values to the same addresses) instead of leaving the loop on their own
          c2.active = s < hi;
          s = s < hi ? s : hi - 1;
       }
       else if (s >= hi)
-         break;
+         break; // (one block per tile, shared-memory stack: CRBA measured 1.3 - 9 % slower with clamped padding lanes, r06y)
       c2.s8 = (unsigned)s * 8u;
       c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s); c2.ob = (char *)(a.out + s);
       c2.fb = (const char *)(a.fext + s);

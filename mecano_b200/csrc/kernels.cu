@@ -213,7 +213,8 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
    const bool persistent = grid < (unsigned)ntiles;
    static const bool draw = [] { const char *e = getenv("MECANO_B200_DRAW"); return !e || atoi(e) != 0; }();
    // the warps of a persistent grid draw their states from a counter that the kernel itself re-arms (gpu_ctx.cuh: thread_block_run)
-   if (!(persistent && draw))
+   // (RNEA / ABA only: the mass-matrix kernels are launched one block per tile, and their stores carry no guard for clamped lanes)
+   if (!(persistent && draw) || algo == MB_CRBA || algo == MB_CORIOLIS)
       b.work_counter = nullptr;
    fn<<<grid, plan.block, plan.smem, stream>>>(P, b);
    return cudaGetLastError();

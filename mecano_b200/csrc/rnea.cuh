@@ -4,12 +4,14 @@
 // (RigidBodyBasics.java:104-112, MovingReferenceFrame.java:279-311).
 //
 // Shape of the code (what the sm_100a kernel needs; the host emulation harness compiles the same source):
-//   * the traversal program is pre-decoded into 16-byte records (MbOp2); each record is dispatched to a
-//     straight-line routine specialised on <joint type, SC>, so the FP64 work of one op sits in one basic block;
-//   * scalars are software-pipelined two ops deep: while op k runs, the q/qd/qdd of op k+2 are in flight from
-//     HBM and the sin/cos of op k+1 (the only long serial FP64 chain) is evaluated next to op k's spatial
-//     algebra (the SC variants), which gives the in-order SM independent work to issue;
-//   * per-level data (accumulated wrench + sin/cos) lives on a shared-memory stack of double2, state-minor.
+//   * the traversal program is pre-decoded into 28-byte records (MbOp2) and cut into runs of same-kind ops (MbRun); a run
+//     is one tight loop over a straight-line routine specialised on <ASCEND, joint type, SC[, plain flags]>, so the FP64 work
+//     of one op sits in one basic block;
+//   * scalars are software-pipelined: while op k runs, the q/qd/qdd of op k+3 are in flight from HBM (cp.async ring) and the
+//     sin/cos of op k+1 (the only long serial FP64 chain) is evaluated next to op k's spatial algebra (the SC variants), which
+//     gives the in-order SM independent work to issue;
+//   * per-level data lives on a per-state stack of double2, state-minor: the accumulated wrench in tensor memory (or shared
+//     memory), sin/cos in shared memory.
 #pragma once
 #include "program.h"
 #include "spatial.cuh"

@@ -196,6 +196,35 @@ def test_work_distribution_of_the_persistent_grids_is_result_neutral(torch_dev):
     assert len(out) == 4 and len(set(out)) == 1, out
 
 
+@pytest.mark.parametrize("idx", [8, 9])
+def test_persistent_grids_on_ragged_batches_of_deep_trees(torch_dev, idx):
+    """Trees too deep for the tensor-memory stack run the shared-memory kernels; forward dynamics is a persistent grid there too, and
+    its warps draw their states from the counter: a batch that is neither a multiple of the block size nor of the warp size, large
+    enough for the grid to be persistent, first and last states against the oracle, the rest against a second launch."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    name, kw = CASES[idx]
+    s, t = build(**kw)
+    rng = np.random.default_rng(6100 + idx)
+    o = ol.Oracle(t, gravity=(0.0, 0.0, -9.81))
+    n = 148 * 384 * 2 + 77
+    q, qd, qdd, tau = mb.MultiBodySystemRandomTools.nextState(rng, s, n)
+    tq, tqd, tqdd, ttau = (torch.from_numpy(x).to(dev) for x in (q, qd, qdd, tau))
+    ident = mb.InverseDynamicsCalculator(s)
+    ident.setGravitationalAcceleration(-9.81)
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    fdyn.setGravitationalAcceleration(-9.81)
+    got_tau = ident.compute(tq, tqd, tqdd).cpu().numpy()
+    got_qdd = fdyn.compute(tq, tqd, ttau).cpu().numpy()
+    assert not (np.isnan(got_tau).any() or np.isnan(got_qdd).any())
+    for sl in (slice(0, 200), slice(n - 200, n)):
+        assert rel(got_tau[:, sl], o.rnea_batch(np.ascontiguousarray(q[:, sl]), np.ascontiguousarray(qd[:, sl]), np.ascontiguousarray(qdd[:, sl]))) < TOL, name
+        assert rel(got_qdd[:, sl], o.aba_batch(np.ascontiguousarray(q[:, sl]), np.ascontiguousarray(qd[:, sl]), np.ascontiguousarray(tau[:, sl]))) < TOL, name
+    assert np.array_equal(fdyn.compute(tq, tqd, ttau).cpu().numpy(), got_qdd)
+    assert np.array_equal(ident.compute(tq, tqd, tqdd).cpu().numpy(), got_tau)
+
+
 def test_host_entry_points_and_leading_dimension(torch_dev):
     """*_host entry points (numpy in, numpy out), with ld > n, plus empty and single-state batches."""
     import mecano_b200 as mb
