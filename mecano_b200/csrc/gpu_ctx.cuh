@@ -414,47 +414,8 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    // The per-state areas (stack, rings) are private to a thread and the constant records are read-only, so the threads of a block
    // never synchronise again.
    const long long ntiles = (a.n + BLOCK - 1) / BLOCK;
-   long long tile = blockIdx.x;
-   for (;;)
-   {
-      long long s;
-      const long long hi = a.n;
-      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kMayClamp && a.work_counter != nullptr)
-      {
-         unsigned first = 0;
-         if ((threadIdx.x & 31) == 0)
-            first = atomicAdd(a.work_counter, 32u);
-         first = __shfl_sync(0xffffffffu, first, 0);
-         if ((long long)first >= hi)
-         {
-            // the last warp of the grid to run dry re-arms the counter pair for the next launch (no memset between launches)
-            if ((threadIdx.x & 31) == 0 && atomicAdd(a.work_counter + 1, 1u) == gridDim.x * (BLOCK / 32) - 1)
-            {
-               a.work_counter[0] = 0;
-               a.work_counter[1] = 0;
-            }
-            break;
-         }
-         s = (long long)first + (threadIdx.x & 31);
-      }
-      else
-      {
-         if (tile >= ntiles)
-            break;
-         s = tile * BLOCK + threadIdx.x;
-         tile += gridDim.x;
-      }
-      // (every exit of this loop above is warp-uniform and visibly so -- a kernel parameter, the block index, a value shuffled from
-      // lane 0: with a thread-dependent exit ptxas gives up the uniform datapath for the whole traversal, +12 % on RNEA and ABA)
-      if (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kClamp || (GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>::kMayClamp && a.work_counter != nullptr))
-      {
-         // tcgen05.ld/st and the draw above are warp-collective: the padding lanes of the last warp run a clamped state (and store
-         // nothing, or the same values to the same addresses) instead of leaving the loop on their own
-         c2.active = s < hi;
-         s = s < hi ? s : hi - 1;
-      }
-      else if (s >= hi)
-         break; // (one block per tile, shared-memory stack: CRBA measured 1.3 - 9 % slower with clamped padding lanes, r06y)
+   using C2 = GpuCtx2<BLOCK, TM, ring_rows(ALGO), M3>;
+   auto run_state = [&](long long s) {
       c2.s8 = (unsigned)s * 8u;
       c2.qb = (const char *)(a.q + s); c2.qdb = (const char *)(a.qd + s); c2.xb = (const char *)(a.x + s); c2.ob = (char *)(a.out + s);
       c2.fb = (const char *)(a.fext + s);
@@ -464,6 +425,64 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
       c2.cmmb = (char *)(a.cmm + s); c2.comb = (char *)(a.com + s); c2.rwb = (char *)(a.root_wrench + s);
       c2.mbase = STATE_MAJOR ? (char *)(a.out + s * (long long)a.nv * a.nv) : (char *)(a.out + s);
       body(c2);
+   };
+   if constexpr (!C2::kMayClamp)
+   {
+      // the mass-matrix kernels (shared-memory stack, one block per tile): the plain loop they have had since round 1 -- at 255
+      // registers the Coriolis kernel pays 16 % for any other shape of it (80 more bytes of spills, r06za)
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      {
+         const long long s = tile * BLOCK + threadIdx.x;
+         if (s >= a.n)
+            break;
+         run_state(s);
+      }
+   }
+   else
+   {
+      long long tile = blockIdx.x;
+      for (;;)
+      {
+         long long s;
+         const long long hi = a.n;
+         if (a.work_counter != nullptr)
+         {
+            unsigned first = 0;
+            if ((threadIdx.x & 31) == 0)
+               first = atomicAdd(a.work_counter, 32u);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if ((long long)first >= hi)
+            {
+               // the last warp of the grid to run dry re-arms the counter pair for the next launch (no memset between launches)
+               if ((threadIdx.x & 31) == 0 && atomicAdd(a.work_counter + 1, 1u) == gridDim.x * (BLOCK / 32) - 1)
+               {
+                  a.work_counter[0] = 0;
+                  a.work_counter[1] = 0;
+               }
+               break;
+            }
+            s = (long long)first + (threadIdx.x & 31);
+         }
+         else
+         {
+            if (tile >= ntiles)
+               break;
+            s = tile * BLOCK + threadIdx.x;
+            tile += gridDim.x;
+         }
+         // (every exit of this loop above is warp-uniform and visibly so -- a kernel parameter, the block index, a value shuffled
+         // from lane 0: with a thread-dependent exit ptxas gives up the uniform datapath for the whole traversal, +12 % on RNEA / ABA)
+         if (C2::kClamp || a.work_counter != nullptr)
+         {
+            // tcgen05.ld/st and the draw above are warp-collective: the padding lanes of the last warp run a clamped state (and
+            // store nothing, or the same values to the same addresses) instead of leaving the loop on their own
+            c2.active = s < hi;
+            s = s < hi ? s : hi - 1;
+         }
+         else if (s >= hi)
+            break;
+         run_state(s);
+      }
    }
    if (TM > 0)
    {
