@@ -383,18 +383,24 @@ template <class T, class Ctx, bool LOCKS> MB_HD void aba_pass3_6dof(Ctx &c, cons
    c.pf3_ld2(st, 2, x.a.z, x.l.x);
    c.pf3_ld2(st, 3, x.l.y, x.l.z);
    c.rec_discard(o.body * (MB_ABA_REC / 2));
-   const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
    const SvT<T> vj = ld_sv6<T>(o.dof, [&](int rr) { return c.ld_qd(rr); });
    SvT<T> a1;
    if (o.flags & MB2_ROOT_PARENT)
    {
-      // a floating base: the root body is at rest and its acceleration is -gravity, purely linear: v = vj, v x vj = 0
+      // a floating base: the root body is at rest and its acceleration is -gravity, purely linear: v = vj, v x vj = 0, and only
+      // the rotation of the joint is needed
+      const auto C = c.cst(o.body);
+      M3T<T> R0;
+      V3T<T> p0;
+      ld_xf0<T>(C, R0, p0);
+      const M3T<T> R = mul(R0, quat_to_rot<T, Ctx::kFastQuat>(c.ld_q(o.cfg), c.ld_q(o.cfg + 1), c.ld_q(o.cfg + 2), c.ld_q(o.cfg + 3)));
       v = vj;
       a1.a = v3<T>((T)0, (T)0, (T)0);
-      a1.l = mulT(X.R, a.l);
+      a1.l = mulT(R, a.l);
    }
    else
    {
+      const XfT<T> X = joint_xf_6dof<T>(c, c.cst(o.body), o.cfg);
       v = motion_to_child(X, v) + vj;
       a1 = motion_to_child(X, a) + cross_motion(v, vj);
    }

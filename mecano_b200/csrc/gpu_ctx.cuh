@@ -254,7 +254,7 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    bool discard_on;
    __device__ __forceinline__ void rec_discard(int rec2) const
    {
-      if (discard_on && (threadIdx.x & 7u) == 0)
+      if (discard_on) // (set for one thread in eight: a 128-byte line holds the double2 of eight threads)
       {
 #pragma unroll
          for (int j = 0; j < MB_ABA_REC / 2; j++)
@@ -401,7 +401,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    c2.w16 = (blockIdx.x * BLOCK + threadIdx.x) * 16u;
    c2.ws_ld16 = (unsigned)(a.ws_ld * 16);
    c2.q0 = (const char *)a.q; c2.qd0 = (const char *)a.qd; c2.x0 = (const char *)a.x; c2.o0 = (char *)a.out;
-   c2.discard_on = ALGO == MB_ABA && (a.flags & MB_KFLAG_ABA_DISCARD) != 0;
+   c2.discard_on = ALGO == MB_ABA && (a.flags & MB_KFLAG_ABA_DISCARD) != 0 && (threadIdx.x & 7u) == 0;
    // The warps of a block start together and run the same op sequence; MECANO_B200_STAGGER_NS starts slot j of a scheduler
    // (warp / 4) j * stagger_ns late.  Measured: no effect (profiles/r06d_plain_kinds.md), the warps are not marching in phase.
    if (a.stagger_ns > 0)
