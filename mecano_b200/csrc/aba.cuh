@@ -304,6 +304,13 @@ MB_HD void aba_ascend_6dof(Ctx &c, const MbOp2 o, int ext, int rec_hi, AbiT<T> &
       return;
    }
    const SvT<T> tau6 = ld_sv6<T>(o.dof, [&](int r) { return c.ld_x(r); });
+   if (o.flags & MB2_ROOT_PARENT)
+   {
+      // a floating base ascends last: pass three starts with it and reads its quaternion and velocity rows directly -- ask L2 for
+      // them now (the wait for them was the largest single stall of the kernel, 2.4 % of its samples)
+      c.warm_q(o.cfg); c.warm_q(o.cfg + 1); c.warm_q(o.cfg + 2); c.warm_q(o.cfg + 3);
+      c.warm_qd(o.dof); c.warm_qd(o.dof + 1); c.warm_qd(o.dof + 2); c.warm_qd(o.dof + 3); c.warm_qd(o.dof + 4); c.warm_qd(o.dof + 5);
+   }
    // D = I^A, U = I^A: a_i = D^-1 u, and the joint transmits nothing but tau to its parent
    const SvT<T> x = abi_solve(IA, tau6 - pA);
    c.rec_st2(r + 0, x.a.x, x.a.y);

@@ -146,6 +146,9 @@ template <class Ctx> struct F32Ctx
    template <int N> __device__ __forceinline__ void pf_wait() const { c.template pf_wait<N>(); }
    __device__ __forceinline__ float pf_ld(int stage, int j) const { return (float)c.pf_ld(stage, j); }
    static constexpr bool kFastQuat = false;
+   __device__ __forceinline__ void warm_q(int r) const { c.warm_q(r); }
+   __device__ __forceinline__ void warm_qd(int r) const { c.warm_qd(r); }
+   __device__ __forceinline__ void warm_x(int r) const { c.warm_x(r); }
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const { c.pf3_issue(stage, cfg, dof, rec2, mask); }
    __device__ __forceinline__ void pf3_ld2(int stage, int row, float &a, float &b) const
    {

@@ -124,6 +124,10 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    __device__ __forceinline__ double ld_qd(int r) const { return mb_ldg(row_qd((unsigned)r)); }
    __device__ __forceinline__ double ld_x(int r) const { return mb_ldg(row_x((unsigned)r)); }
    __device__ __forceinline__ double ld_fext(int b, int k) const { return mb_ldg(mb_row(fb, (unsigned)(6 * b + k), ld8)); }
+   // warm L2 with a row that a later op of this state reads directly (the floating base's rows: no ring in front of them)
+   __device__ __forceinline__ void warm_q(int r) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(row_q((unsigned)r))); }
+   __device__ __forceinline__ void warm_qd(int r) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(row_qd((unsigned)r))); }
+   __device__ __forceinline__ void warm_x(int r) const { asm volatile("prefetch.global.L2 [%0];" ::"l"(row_x((unsigned)r))); }
    __device__ __forceinline__ void st_out(int r, double v) { mb_stg(row_o((unsigned)r), v); }
    // optional buffers of the FEXT instantiation (nullptr = absent): external wrenches in, RNEA by-products out
    char *accb, *wrb;

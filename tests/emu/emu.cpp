@@ -51,6 +51,9 @@ template <class T> struct CpuCtx
 {
    static constexpr bool kM3 = true; // three-DoF joints compiled in (multidof.cuh)
    static constexpr bool kFastQuat = false;
+   void warm_q(int) const {}
+   void warm_qd(int) const {}
+   void warm_x(int) const {}
    const double *q, *qd, *x, *fext;
    double *out, *M;
    long ld, s;
