@@ -515,9 +515,11 @@ MB_HD void aba_begin(Ctx &c, const MbOp2 o0, const MbOp2 o1, const MbOp2 o2, SvT
    c.pf_commit();
    if (aba_pf_mask(o2)) c.pf_issue(2, o2.cfg, o2.dof, aba_pf_mask(o2));
    c.pf_commit();
-   c.template pf_wait<0>();
    if (mb2_is_1dof_descend(o0))
    {
+      // (only a one-DoF first op needs its angle now; a floating base reads its rows directly, and waiting here would put the latency
+      // of the ring in front of the latency of those loads instead of next to it)
+      c.template pf_wait<0>();
       const T q0 = c.pf_ld(0, 0);
       if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &pp.s, &pp.c);
       else pp.s = q0; // a prismatic displacement is not an angle
