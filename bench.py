@@ -44,8 +44,8 @@ UNIT = "states/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=50)
-    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--states", type=int, default=1 << 20, help="states per GPU (weak scaling)")
     p.add_argument("--neck", type=int, default=2, help="2 -> H37 (37 DoF), 1 -> H36 (36 DoF)")
@@ -434,6 +434,13 @@ def main():
     # ---- roofline (rank 0 numbers; every rank runs the same kernels on the same amount of work)
     peaks, peak_src = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
+    # FP64 denominators, measured right after the timed region: the burst figure (best of five 4.6 ms launches of an FMA chain) and
+    # the sustained one (the same chain back to back for as long as the timed region, at least 0.25 s, rate over the second half).
+    # They agree (34.8 TFLOP/s, profiles/r06zm): the FMA chain alone does not reach the board's power cap.  The step does -- CRBA
+    # writing at 6 TB/s next to two FP64-bound kernels: over 100 steps the SM clock settles at ~1830 of 1965 MHz (sw_power_cap) and
+    # every FP64-bound time stretches with it -- so each kernel's fraction is also given against the peak scaled to the SM clock
+    # sampled during the timed region (fp64_frac_at_sampled_clock).
+    fp64_sustained = mb.measure_fp64_sustained(local_rank, max(0.25, min(2.0, ms_total * 1e-3))) if rank == 0 else 0.0
     fp64_peak = mb.measure_fp64_peak(local_rank) if rank == 0 else 0.0
     flops_path = os.path.join(ROOT, "profiles", "algorithmic_flops.json")
     flops = json.load(open(flops_path)) if os.path.exists(flops_path) else {}
@@ -453,6 +460,9 @@ def main():
         if fl and fp64_peak:
             tf = fl * n / (ms * 1e-3) / 1e12
             entry.update({"algorithmic_flops_per_state": fl, "achieved_tflops": tf, "fp64_frac": tf / fp64_peak,
+                          "fp64_frac_of_sustained_peak": tf / fp64_sustained if fp64_sustained else None,
+                          "fp64_frac_at_sampled_clock": (tf / (fp64_peak * clocks["sm_mhz"] / clocks["sm_max_mhz"])
+                                                         if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") else None),
                           "fp64_frac_of_nominal": tf / FP64_NOMINAL_TFLOPS})
             fe = exec_flops.get(key, {}).get(name)
             if fe:  # what the current routines execute for the same result (fewer: profiles/executed_flops.json)
@@ -599,7 +609,12 @@ def main():
                     "hbm": {"achieved": kd["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kd["hbm_frac"], "peak_source": peak_src}}
     else:
         roofline = {"kernel": dom, "bound": "hbm", "achieved": kd["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kd["hbm_frac"], "traffic": None, "peak_source": peak_src, "fp64_peak_tflops_measured_live": fp64_peak}
+                    "frac": kd["hbm_frac"], "traffic": None, "peak_source": peak_src, "fp64_peak_tflops_measured_live": fp64_peak,
+                    "fp64_peak_tflops_sustained_live": fp64_sustained,
+                    "fp64_note": "kernels[*].fp64_frac is against the burst figure (best of five 4.6 ms launches of an FMA chain), "
+                                 "fp64_frac_of_sustained_peak against the same chain run back to back for the length of the timed region, "
+                                 "fp64_frac_at_sampled_clock against the burst figure scaled by clocks.sm_mhz / clocks.sm_max_mhz (the step, "
+                                 "unlike the FMA chain, reaches the power cap when it runs for long)"}
     roofline["flop_per_byte"] = intensity
     roofline["machine_balance_flop_per_byte"] = balance
     traffic_path = os.path.join(ROOT, "profiles", "dram_traffic.json")

@@ -356,8 +356,10 @@ int mecano_b200_integrate_host(mecano_b200_handle *h, int64_t n_states, int64_t 
 /* Introspection for the benchmark / roofline report. */
 int mecano_b200_kernel_info_get(mecano_b200_handle *h, int algo, int64_t n_states, mecano_b200_kernel_info *info);
 
-/* Roofline denominators measured on the handle-less device: FP64 FMA chain and a read+write copy. */
+/* Roofline denominators measured on the handle-less device: FP64 FMA chain (best of five short launches: the burst figure; back to
+ * back for `seconds`, rate over the second half: the sustained figure under the board's power management) and a read+write copy. */
 int mecano_b200_measure_fp64_peak(int device, double *tflops);
+int mecano_b200_measure_fp64_sustained(int device, double seconds, double *tflops);
 int mecano_b200_measure_hbm_peak(int device, double *gbytes_per_s);
 
 /*

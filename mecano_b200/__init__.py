@@ -8,6 +8,6 @@ from . import _capi  # noqa: F401  (raises ImportError if libmecano_b200.so is m
 from ._capi import MecanoB200Error  # noqa: F401
 from .calculators import (CompositeRigidBodyMassMatrixCalculator, ForwardDynamicsCalculator, InverseDynamicsCalculator, JointSourceMode,  # noqa: F401
                           MatrixDimensionException, MultiBodyDynamicsStep, MultiBodySystemStateIntegrator)
-from .engine import Engine, MultiDeviceEngine, measure_fp64_peak, measure_hbm_peak  # noqa: F401
+from .engine import Engine, MultiDeviceEngine, measure_fp64_peak, measure_fp64_sustained, measure_hbm_peak  # noqa: F401
 from .multibody import (FixedJoint, JointMatrixIndexProvider, MultiBodySystem, MultiBodySystemRandomTools, PlanarJoint, PrismaticJoint,  # noqa: F401
                         RevoluteJoint, RigidBody, RigidBodyTransform, ScrewTheoryException, SixDoFJoint, SphericalJoint)

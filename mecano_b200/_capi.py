@@ -60,7 +60,7 @@ EXPORTS = [
     "mecano_b200_version", "mecano_b200_device_count", "mecano_b200_create", "mecano_b200_destroy", "mecano_b200_last_error",
     "mecano_b200_set_gravity", "mecano_b200_set_variant", "mecano_b200_n_dofs", "mecano_b200_n_cfg", "mecano_b200_n_bodies",
     "mecano_b200_rnea", "mecano_b200_aba", "mecano_b200_crba", "mecano_b200_rnea_host", "mecano_b200_aba_host",
-    "mecano_b200_crba_host", "mecano_b200_kernel_info_get", "mecano_b200_measure_fp64_peak", "mecano_b200_measure_hbm_peak",
+    "mecano_b200_crba_host", "mecano_b200_kernel_info_get", "mecano_b200_measure_fp64_peak", "mecano_b200_measure_fp64_sustained", "mecano_b200_measure_hbm_peak",
     "mecano_b200_integrate", "mecano_b200_integrate_host", "mecano_b200_host_alloc", "mecano_b200_host_free", "mecano_b200_generate_source", "mecano_b200_jit_check", "mecano_b200_specialize",
     "mecano_b200_rnea_full", "mecano_b200_rnea_full_host",
     "mecano_b200_set_joint_source_modes", "mecano_b200_aba_sources", "mecano_b200_aba_sources_host",
@@ -106,6 +106,7 @@ lib.mecano_b200_integrate.argtypes = [c_vp, c_i64, c_i64, ctypes.c_double, c_vp,
 lib.mecano_b200_integrate_host.argtypes = [c_vp, c_i64, c_i64, ctypes.c_double, c_vp, c_vp, c_vp]
 lib.mecano_b200_kernel_info_get.argtypes = [c_vp, ctypes.c_int, c_i64, ctypes.POINTER(KernelInfo)]
 lib.mecano_b200_measure_fp64_peak.argtypes = [ctypes.c_int, c_dp]
+lib.mecano_b200_measure_fp64_sustained.argtypes = [ctypes.c_int, ctypes.c_double, c_dp]
 lib.mecano_b200_measure_hbm_peak.argtypes = [ctypes.c_int, c_dp]
 lib.mecano_b200_host_alloc.argtypes = [ctypes.POINTER(c_vp), c_i64]
 lib.mecano_b200_host_free.argtypes = [c_vp]

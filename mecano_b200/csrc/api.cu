@@ -1266,6 +1266,14 @@ int mecano_b200_measure_fp64_peak(int device, double *tflops)
    return e == cudaSuccess ? MECANO_B200_OK : (int)e;
 }
 
+int mecano_b200_measure_fp64_sustained(int device, double seconds, double *tflops)
+{
+   if (!tflops || !(seconds > 0.0) || seconds > 30.0) return MECANO_B200_ERR_INVALID_ARGUMENT;
+   cudaError_t e = cudaSetDevice(device);
+   if (e == cudaSuccess) e = mb::measure_fp64_sustained(seconds, tflops);
+   return e == cudaSuccess ? MECANO_B200_OK : (int)e;
+}
+
 int mecano_b200_measure_hbm_peak(int device, double *gbs)
 {
    if (!gbs) return MECANO_B200_ERR_INVALID_ARGUMENT;

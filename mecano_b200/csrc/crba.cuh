@@ -141,11 +141,11 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
          c.pf_issue(k, o.cfg, o.dof, 1);
       c.pf_commit();
    }
-   c.template pf_wait<0>();
    {
       const MbOp2 o0 = P.op2[0];
       if (mb2_is_1dof_descend(o0))
       {
+         c.template pf_wait<0>(); // (only a one-DoF first op needs its angle now, see rnea_begin)
          const T q0 = c.pf_ld(0, 0);
          if (MB2_JT(o0.code) == MB_REVOLUTE) mb_sincos(mb_reduce_angle(q0), &s, &cs);
          else s = q0; // a prismatic displacement is not an angle

@@ -277,6 +277,40 @@ cudaError_t measure_fp64_peak(double *tflops)
    return e;
 }
 
+// The same chain back to back for `seconds`: the rate over the second half, i.e. what the FP64 pipe delivers once the power
+// management has settled (the denominator for kernels timed inside a long step; measure_fp64_peak above is the burst figure).
+cudaError_t measure_fp64_sustained(double seconds, double *tflops)
+{
+   int dev = 0, sms = 0;
+   cudaError_t e = cudaGetDevice(&dev);
+   if (e != cudaSuccess) return e;
+   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+   const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+   double *out = nullptr;
+   e = cudaMalloc(&out, sizeof(double) * blocks * threads);
+   if (e != cudaSuccess) return e;
+   cudaEvent_t t0, t1;
+   cudaEventCreate(&t0);
+   cudaEventCreate(&t1);
+   // one launch is ~4.6 ms at the burst rate
+   const int launches = std::max(4, (int)(seconds / 4.6e-3)), half = launches / 2;
+   for (int rep = 0; rep < launches; rep++)
+   {
+      if (rep == half) cudaEventRecord(t0);
+      dfma_chain_kernel<<<blocks, threads>>>(out, iters, 1.0 + rep);
+   }
+   cudaEventRecord(t1);
+   e = cudaEventSynchronize(t1);
+   float ms = 0;
+   if (e == cudaSuccess) cudaEventElapsedTime(&ms, t0, t1);
+   const double flops = 2.0 * 8.0 * (double)iters * blocks * threads * (launches - half);
+   *tflops = ms > 0 ? flops / (ms * 1e-3) / 1e12 : 0.0;
+   cudaEventDestroy(t0);
+   cudaEventDestroy(t1);
+   cudaFree(out);
+   return e;
+}
+
 cudaError_t measure_hbm_peak(double *gbs)
 {
    const long long bytes = 1ll << 31; // 2 GiB each way, far beyond L2

@@ -73,5 +73,6 @@ cudaError_t launch_centroidal_finish(const CentroidalArgs &a, cudaStream_t strea
 
 // roofline denominators
 cudaError_t measure_fp64_peak(double *tflops);
+cudaError_t measure_fp64_sustained(double seconds, double *tflops);
 cudaError_t measure_hbm_peak(double *gbs);
 } // namespace mb

@@ -462,6 +462,13 @@ def measure_fp64_peak(device=0):
     return v.value
 
 
+def measure_fp64_sustained(device=0, seconds=1.0):
+    """FP64 FMA chain back to back for `seconds`: TFLOP/s over the second half (the board's power management has settled)."""
+    v = ctypes.c_double()
+    check(lib.mecano_b200_measure_fp64_sustained(device, float(seconds), ctypes.byref(v)))
+    return v.value
+
+
 def measure_hbm_peak(device=0):
     v = ctypes.c_double()
     check(lib.mecano_b200_measure_hbm_peak(device, ctypes.byref(v)))
