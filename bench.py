@@ -564,9 +564,13 @@ def main():
         extras["crba_centroidal"] = hbm_entry(timed(lambda: cen.getCentroidalMomentumMatrix(q)), 8.0 * (nq + nv * nv + 6 * nv + 4),
                                               "getMassMatrix + getCentroidalMomentumMatrix + centre of mass (mecano_b200_crba_centroidal; the "
                                               "centre-of-mass shift re-reads and re-writes 9 nv rows, not counted)")
-        extras["centroidal_convective_term"] = hbm_entry(timed(lambda: cen.getCentroidalConvectiveTermMatrix(q, qd)), 8.0 * (nq + nv + 4 + 6),
-                                                         "getCentroidalConvectiveTermMatrix (mecano_b200_centroidal_convective_term: one RNEA launch "
-                                                         "whose joint efforts go to a scratch buffer, + the shift)")
+        extras["center_of_mass"] = hbm_entry(timed(lambda: cen.getCenterOfMass(q)), 8.0 * (nq + 4),
+                                             "CenterOfMassCalculator.getCenterOfMass + getTotalMass (mecano_b200_center_of_mass: the by-product "
+                                             "mass-matrix kernel launched without a matrix -- composite inertias only, no unit momenta, no stores)")
+        extras["centroidal_convective_term"] = hbm_entry(timed(lambda: cen.getCentroidalConvectiveTermMatrix(q, qd)), 8.0 * (2 * nq + nv + 2 * 4 + 6),
+                                                         "getCentroidalConvectiveTermMatrix in the centre-of-mass frame (mecano_b200_center_of_mass for the q "
+                                                         "passed + mecano_b200_centroidal_convective_term: one RNEA launch whose joint efforts go to a scratch "
+                                                         "buffer, + the shift)")
         cen.setEnableCoriolisMatrixCalculation(True)
         extras["coriolis_matrix"] = hbm_entry(timed(lambda: cen.getCoriolisMatrix(q, qd)), 8.0 * (nq + nv + 2 * nv * nv),
                                               "getMassMatrix + getCoriolisMatrix, both dense nv x nv (mecano_b200_coriolis)")

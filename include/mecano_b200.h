@@ -256,8 +256,12 @@ int mecano_b200_crba(mecano_b200_handle *h, int64_t n_states, int64_t ld, const 
  *                                      DMatrixRMaj, state-minor); angular momentum rows first.  cmm * qd = momentum in `frame`
  *   com         [4][ld]                centre of mass in the root frame (x, y, z) and total mass
  * mecano_b200_centroidal_convective_term = getCentroidalConvectiveTerm() (:811-839), d/dt(cmm) qd:
- *   out         [6][ld]                moment first; `com` = the rows written by mecano_b200_crba_centroidal for the same q (needed
- *                                      for MECANO_B200_FRAME_CENTER_OF_MASS only, else may be NULL)
+ *   out         [6][ld]                moment first; `com` = the rows written by mecano_b200_crba_centroidal or
+ *                                      mecano_b200_center_of_mass for the same q (needed for MECANO_B200_FRAME_CENTER_OF_MASS only,
+ *                                      else may be NULL)
+ * mecano_b200_center_of_mass = CenterOfMassCalculator.getCenterOfMass() + getTotalMass() (CenterOfMassCalculator.java:70-124), the
+ * origin a CenterOfMassReferenceFrame moves to on update (CenterOfMassReferenceFrame.java:45-50), for N states: the `com` rows
+ * alone, bit-identical to those of mecano_b200_crba_centroidal, without computing or writing a matrix
  */
 #define MECANO_B200_FRAME_WORLD 0
 #define MECANO_B200_FRAME_CENTER_OF_MASS 1
@@ -265,6 +269,7 @@ int mecano_b200_crba_centroidal(mecano_b200_handle *h, int64_t n_states, int64_t
                                 int frame, void *stream);
 int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *com,
                                            double *out, int frame, void *stream);
+int mecano_b200_center_of_mass(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *com, void *stream);
 
 /*
  * Mass matrix and Coriolis / centrifugal matrix together: getMassMatrix() + getCoriolisMatrix() after
@@ -338,6 +343,7 @@ int mecano_b200_crba_centroidal_host(mecano_b200_handle *h, int64_t n_states, in
                                      double *com, int frame);
 int mecano_b200_centroidal_convective_term_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd,
                                                 const double *com, double *out, int frame);
+int mecano_b200_center_of_mass_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, double *com);
 
 /*
  * State integrator: MultiBodySystemStateIntegrator(dt).doubleIntegrateFromAcceleration(joints)

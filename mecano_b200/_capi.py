@@ -65,7 +65,7 @@ EXPORTS = [
     "mecano_b200_rnea_full", "mecano_b200_rnea_full_host",
     "mecano_b200_set_joint_source_modes", "mecano_b200_aba_sources", "mecano_b200_aba_sources_host",
     "mecano_b200_crba_centroidal", "mecano_b200_centroidal_convective_term", "mecano_b200_crba_centroidal_host",
-    "mecano_b200_centroidal_convective_term_host", "mecano_b200_coriolis", "mecano_b200_coriolis_host", "mecano_b200_set_grid_limit", "mecano_b200_set_precision",
+    "mecano_b200_centroidal_convective_term_host", "mecano_b200_center_of_mass", "mecano_b200_center_of_mass_host", "mecano_b200_coriolis", "mecano_b200_coriolis_host", "mecano_b200_set_grid_limit", "mecano_b200_set_precision",
     "mecano_b200_crba_packed_size", "mecano_b200_crba_packed_index", "mecano_b200_step_host",
     "mecano_b200_multi_create", "mecano_b200_multi_destroy", "mecano_b200_multi_last_error", "mecano_b200_multi_size", "mecano_b200_multi_handle",
     "mecano_b200_multi_slice", "mecano_b200_multi_set_gravity", "mecano_b200_multi_rnea_host", "mecano_b200_multi_aba_host",
@@ -96,6 +96,8 @@ lib.mecano_b200_crba_centroidal.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp
 lib.mecano_b200_centroidal_convective_term.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]
 lib.mecano_b200_crba_centroidal_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int]
 lib.mecano_b200_centroidal_convective_term_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int]
+lib.mecano_b200_center_of_mass.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]
+lib.mecano_b200_center_of_mass_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp]
 lib.mecano_b200_coriolis.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]
 lib.mecano_b200_coriolis_host.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]
 lib.mecano_b200_crba.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_u32, c_vp]

@@ -444,15 +444,25 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         self._com_q = q  # the configuration matrix the centre of mass belongs to (getCentroidalConvectiveTermMatrix)
         return self._cmm
 
-    def getCenterOfMass(self):
-        """[4, N]: centre of mass of the system in the root frame (x, y, z) and its total mass, of the states last handed to
-        getCentroidalMomentumMatrix()."""
+    def getCenterOfMass(self, q=None):
+        """[4, N]: centre of mass of the system in the root frame (x, y, z) and its total mass.  Without an argument: of the
+        states last handed to getCentroidalMomentumMatrix() / getCentroidalConvectiveTermMatrix().  With `q`: computed for these
+        states by the centre-of-mass-only launch (CenterOfMassCalculator.getCenterOfMass() + getTotalMass(),
+        CenterOfMassCalculator.java:70-124; mecano_b200_center_of_mass) -- no matrix is computed or written, the rows are
+        bit-identical to those getCentroidalMomentumMatrix(q) leaves."""
+        if q is not None:
+            nq = self._input.getConfigurationMatrixSize()
+            n = q.shape[1] if q.ndim == 2 else -1
+            self._check("q", q, nq, n)
+            self._com = self._empty_like(q, 4, n)
+            self._engine.center_of_mass(q, self._com)
+            self._com_q = q
         return self._com
 
     def getCentroidalConvectiveTermMatrix(self, q, qd, reuseCenterOfMass=False):
         """getCentroidalConvectiveTermMatrix() (:423-440, :811-839) for N states: [6, N], moment first, in the centroidal momentum
-        frame.  In CENTER_OF_MASS_FRAME the centre of mass is that of the `q` passed here: getCentroidalMomentumMatrix(q) runs
-        first (the reference derives both from the same joint state after reset()).  reuseCenterOfMass=True skips that when the
+        frame.  In CENTER_OF_MASS_FRAME the centre of mass is that of the `q` passed here: getCenterOfMass(q) runs first (the
+        reference derives both from the same joint state after reset()).  reuseCenterOfMass=True skips that when the
         caller has just called getCentroidalMomentumMatrix() with this very `q` (same object, same batch); it is the caller's
         statement that the configuration has not changed since."""
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
@@ -463,7 +473,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         if self._frame == self.CENTER_OF_MASS_FRAME:
             fresh = reuseCenterOfMass and self._com is not None and self._com_q is q and self._com.shape[1] == n
             if not fresh:
-                self.getCentroidalMomentumMatrix(q)
+                self.getCenterOfMass(q)
             com = self._com
         out = self._empty_like(q, 6, n)
         self._engine.centroidal_convective_term(q, qd, com, out, self._frame_code())

@@ -160,7 +160,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    // states on; a thread per state needs tens of thousands but then has 10-30x the throughput)
    // calls with by-product buffers (mecano_b200_rnea_full) always run the generic thread-per-state kernel
    // (so does the packed mass-matrix layout: its row numbering follows the thread-per-state traversal)
-   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.root_wrench || algo == MB_CORIOLIS || h->fp32 || packed;
+   const bool byprod = body_acc || joint_wrench || x2 || opt.cmm || opt.com || opt.root_wrench || algo == MB_CORIOLIS || h->fp32 || packed;
    const int64_t vn = opt.variant_n > 0 ? opt.variant_n : n;
    const bool use_warp = !byprod && (h->variant == MECANO_B200_VARIANT_WARP || (h->variant == MECANO_B200_VARIANT_AUTO && h->warp_ok && vn < h->warp_below[algo]));
    if (use_warp)
@@ -932,6 +932,31 @@ int mecano_b200_crba_centroidal(mecano_b200_handle *h, int64_t n, int64_t ld, co
    return MECANO_B200_OK;
 }
 
+// The centre of mass alone (CenterOfMassCalculator.getCenterOfMass() / getTotalMass(), CenterOfMassCalculator.java:70-124; what
+// CenterOfMassReferenceFrame.updateTransformToParent(), CenterOfMassReferenceFrame.java:45-50, asks for): the by-product CRBA kernel
+// launched without a matrix keeps the composite-inertia recursion and drops the unit momenta, their ancestor walks and every
+// matrix store (crba.cuh: com_only) -- the same arithmetic, hence the same bits, as the com rows of mecano_b200_crba_centroidal.
+int mecano_b200_center_of_mass(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *com, void *stream)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !com) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   MB_ON_DEVICE(h);
+   cudaStream_t st = (cudaStream_t)stream;
+   MB_CUDA(h, cudaMemset2DAsync(com, (size_t)ld * sizeof(double), 0, (size_t)n * sizeof(double), 4, st));
+   RunOpts opt;
+   opt.com = com;
+   rc = run(h, MB_CRBA, n, ld, q, nullptr, nullptr, nullptr, nullptr, MECANO_B200_CRBA_ENTRY_MAJOR, st, opt);
+   if (rc) return rc;
+   mb::CentroidalArgs ca;
+   ca.cols = nullptr; ca.com = com; ca.n = n; ca.ld = ld; ca.ncols = 0;
+   ca.normalize_com = 1;
+   ca.shift = 0;
+   MB_CUDA(h, mb::launch_centroidal_finish(ca, st));
+   return MECANO_B200_OK;
+}
+
 int mecano_b200_centroidal_convective_term(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, const double *qd, const double *com,
                                            double *out, int frame, void *stream)
 {
@@ -1083,6 +1108,35 @@ int mecano_b200_centroidal_convective_term_host(mecano_b200_handle *h, int64_t n
    }
    cudaFree(d);
    if (e != cudaSuccess) return cuda_fail(h, e, "mecano_b200_centroidal_convective_term_host");
+   return rc;
+}
+
+int mecano_b200_center_of_mass_host(mecano_b200_handle *h, int64_t n, int64_t ld, const double *q, double *com)
+{
+   int rc = check_batch(h, n, ld);
+   if (rc) return rc;
+   if (n == 0) return MECANO_B200_OK;
+   if (!q || !com) return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
+   std::lock_guard<std::mutex> lk(h->mu);
+   MB_ON_DEVICE(h);
+   const size_t nq = h->tree.nq, rows = nq + 4;
+   const size_t chunk = (size_t)std::min<int64_t>(n, 262144);
+   double *d = nullptr;
+   MB_CUDA(h, cudaMalloc(&d, rows * chunk * sizeof(double)));
+   double *dq = d, *dc = dq + nq * chunk;
+   cudaError_t e = cudaSuccess;
+   for (int64_t s0 = 0; s0 < n && rc == 0 && e == cudaSuccess; s0 += (int64_t)chunk)
+   {
+      const size_t w = (size_t)std::min<int64_t>((int64_t)chunk, n - s0);
+      e = copy_rows(dq, chunk, q + s0, (size_t)ld, w, nq, cudaMemcpyHostToDevice, nullptr);
+      if (e != cudaSuccess) break;
+      rc = mecano_b200_center_of_mass(h, (int64_t)w, (int64_t)chunk, dq, dc, nullptr);
+      if (rc) break;
+      e = copy_rows(com + s0, (size_t)ld, dc, chunk, w, 4, cudaMemcpyDeviceToHost, nullptr);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+   }
+   cudaFree(d);
+   if (e != cudaSuccess) return cuda_fail(h, e, "mecano_b200_center_of_mass_host");
    return rc;
 }
 

@@ -129,6 +129,10 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
    // entries coupling joints of unrelated branches are zero
    // (the zeros are spread over the ops of the traversal instead of being written in one burst up front: a steadier store stream)
    const int zpart = c.zero_parts(P.nops);
+   // BY: a launch without a matrix (mecano_b200_center_of_mass) keeps the composite-inertia recursion and the com rows only
+   bool full = true;
+   if constexpr (BY)
+      full = !c.com_only();
    RbiT<T> acc = RbiT<T>();
    T s = (T)0, cs = (T)1, ls = (T)0, lc = (T)1, mq = (T)0;
    const int nops = P.nops;
@@ -156,7 +160,7 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
    {
       const MbOp2 o = P.op2[k];
       c.stk_fence();
-      if (!PK)
+      if (!PK && full)
          c.zero_fill_part(k, zpart);
       if (o.pf & MB2_PF_D1)
          c.pf_issue((k + MB_PF_DIST) & (MB_PF_STAGES - 1), o.pfcfg, o.pfdof, 1);
@@ -196,74 +200,78 @@ template <class T, class Ctx, bool BY = false, bool PK = false> MB_HD void crba_
          // packed layout: first packed row of this joint's first column, position of the joint's own DoFs within a column
          const int pcol = PK ? (int)P.walk[o.body].pcol : 0, above = PK ? (int)P.walk[o.body].above : 0;
          // unit momenta F = Ic S (:663-667), diagonal block (:700-707), ancestors (:772-797)
-         if (jt == MB_REVOLUTE)
+         // (not for a centre-of-mass-only launch: the composite inertias are all it needs)
+         if (full)
          {
-            SvT<T> F;
-            F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
-            F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
-            c.st_M(PK ? pcol + above : d * nv + d, F.a.z);
-            if (BY || !(o.flags & MB2_ROOT_PARENT))
-               crba_walk<T, Ctx, BY, PK>(P, c, o.body, d, pcol, js, jc, F);
-         }
-         else if (jt == MB_PRISMATIC)
-         {
-            SvT<T> F;
-            F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
-            F.l = v3<T>((T)0, (T)0, Ic.m);
-            c.st_M(PK ? pcol + above : d * nv + d, F.l.z);
-            if (BY || !(o.flags & MB2_ROOT_PARENT))
-               crba_walk<T, Ctx, BY, PK>(P, c, o.body, d, pcol, js, jc, F);
-         }
-         else
-         {
-            // multi-DoF joint: one unit momentum per DoF; DoF k is component comp(k) of the spatial vector (all six for a SixDoF
-            // joint, three for a spherical / planar one, multidof.cuh)
-            const int sub = mb_sub_of<Ctx>(o), nd = mb_sub_ndof(sub);
-            int pc = pcol; // packed: column `col` of this joint starts at pcol + col * above + col (col + 1) / 2
-#pragma unroll 1
-            for (int col = 0; col < nd; col++)
+            if (jt == MB_REVOLUTE)
             {
-               const int cc = mb_sub_component(sub, col);
-               SvT<T> e = sv_zero<T>();
-               if (cc == 0) e.a.x = 1; else if (cc == 1) e.a.y = 1; else if (cc == 2) e.a.z = 1;
-               else if (cc == 3) e.l.x = 1; else if (cc == 4) e.l.y = 1; else e.l.z = 1;
-               const SvT<T> F = mul(Ic, e);
-               const int dc = d + col;
-               const T f6[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
-               if (sub == MB_SUB_SIX)
-               {
-                  if (PK)
-                  {
-                     // upper triangle of the diagonal block: rows 0 .. col of this column
-#pragma unroll
-                     for (int r = 0; r < 6; r++)
-                        if (r <= col)
-                           c.st_M(pc + above + r, f6[r]);
-                  }
-                  else
-                  {
-                     c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
-                     c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
-                  }
-               }
-               else
-               {
-                  // diagonal block of a three-DoF joint: rows = the joint's own components of F
-                  const T g0 = sub == MB_SUB_PLANAR ? f6[1] : f6[0], g1 = sub == MB_SUB_PLANAR ? f6[3] : f6[1], g2 = sub == MB_SUB_PLANAR ? f6[5] : f6[2];
-                  if (PK)
-                  {
-                     c.st_M(pc + above + 0, g0);
-                     if (col >= 1) c.st_M(pc + above + 1, g1);
-                     if (col >= 2) c.st_M(pc + above + 2, g2);
-                  }
-                  else
-                  {
-                     c.st_M((d + 0) * nv + dc, g0); c.st_M((d + 1) * nv + dc, g1); c.st_M((d + 2) * nv + dc, g2);
-                  }
-               }
+               SvT<T> F;
+               F.a = v3<T>(Ic.I.xz, Ic.I.yz, Ic.I.zz);
+               F.l = v3<T>(-Ic.h.y, Ic.h.x, (T)0);
+               c.st_M(PK ? pcol + above : d * nv + d, F.a.z);
                if (BY || !(o.flags & MB2_ROOT_PARENT))
-                  crba_walk<T, Ctx, BY, PK>(P, c, o.body, dc, pc, js, jc, F);
-               pc += above + col + 1;
+                  crba_walk<T, Ctx, BY, PK>(P, c, o.body, d, pcol, js, jc, F);
+            }
+            else if (jt == MB_PRISMATIC)
+            {
+               SvT<T> F;
+               F.a = v3<T>(Ic.h.y, -Ic.h.x, (T)0);
+               F.l = v3<T>((T)0, (T)0, Ic.m);
+               c.st_M(PK ? pcol + above : d * nv + d, F.l.z);
+               if (BY || !(o.flags & MB2_ROOT_PARENT))
+                  crba_walk<T, Ctx, BY, PK>(P, c, o.body, d, pcol, js, jc, F);
+            }
+            else
+            {
+               // multi-DoF joint: one unit momentum per DoF; DoF k is component comp(k) of the spatial vector (all six for a SixDoF
+               // joint, three for a spherical / planar one, multidof.cuh)
+               const int sub = mb_sub_of<Ctx>(o), nd = mb_sub_ndof(sub);
+               int pc = pcol; // packed: column `col` of this joint starts at pcol + col * above + col (col + 1) / 2
+   #pragma unroll 1
+               for (int col = 0; col < nd; col++)
+               {
+                  const int cc = mb_sub_component(sub, col);
+                  SvT<T> e = sv_zero<T>();
+                  if (cc == 0) e.a.x = 1; else if (cc == 1) e.a.y = 1; else if (cc == 2) e.a.z = 1;
+                  else if (cc == 3) e.l.x = 1; else if (cc == 4) e.l.y = 1; else e.l.z = 1;
+                  const SvT<T> F = mul(Ic, e);
+                  const int dc = d + col;
+                  const T f6[6] = {F.a.x, F.a.y, F.a.z, F.l.x, F.l.y, F.l.z};
+                  if (sub == MB_SUB_SIX)
+                  {
+                     if (PK)
+                     {
+                        // upper triangle of the diagonal block: rows 0 .. col of this column
+   #pragma unroll
+                        for (int r = 0; r < 6; r++)
+                           if (r <= col)
+                              c.st_M(pc + above + r, f6[r]);
+                     }
+                     else
+                     {
+                        c.st_M((d + 0) * nv + dc, F.a.x); c.st_M((d + 1) * nv + dc, F.a.y); c.st_M((d + 2) * nv + dc, F.a.z);
+                        c.st_M((d + 3) * nv + dc, F.l.x); c.st_M((d + 4) * nv + dc, F.l.y); c.st_M((d + 5) * nv + dc, F.l.z);
+                     }
+                  }
+                  else
+                  {
+                     // diagonal block of a three-DoF joint: rows = the joint's own components of F
+                     const T g0 = sub == MB_SUB_PLANAR ? f6[1] : f6[0], g1 = sub == MB_SUB_PLANAR ? f6[3] : f6[1], g2 = sub == MB_SUB_PLANAR ? f6[5] : f6[2];
+                     if (PK)
+                     {
+                        c.st_M(pc + above + 0, g0);
+                        if (col >= 1) c.st_M(pc + above + 1, g1);
+                        if (col >= 2) c.st_M(pc + above + 2, g2);
+                     }
+                     else
+                     {
+                        c.st_M((d + 0) * nv + dc, g0); c.st_M((d + 1) * nv + dc, g1); c.st_M((d + 2) * nv + dc, g2);
+                     }
+                  }
+                  if (BY || !(o.flags & MB2_ROOT_PARENT))
+                     crba_walk<T, Ctx, BY, PK>(P, c, o.body, dc, pc, js, jc, F);
+                  pc += above + col + 1;
+               }
             }
          }
          if (BY && (o.flags & MB2_ROOT_PARENT))

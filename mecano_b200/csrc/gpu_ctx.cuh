@@ -133,8 +133,10 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    char *accb, *wrb;
    const char *x2b;
    char *cmmb, *comb, *rwb;
-   bool rootw_on;
+   bool rootw_on, com_only_on;
    __device__ __forceinline__ bool has_rootw() const { return rootw_on; }
+   // by-product CRBA launched without a matrix: centre of mass only (mecano_b200_center_of_mass)
+   __device__ __forceinline__ bool com_only() const { return com_only_on; }
    __device__ __forceinline__ void st_cmm(int row, double v) { mb_stg(mb_row(cmmb, (unsigned)row, ld8), v); }
    // read-modify-write by the one thread that owns the state (the padding lanes of a clamped tile repeat the last state: not them)
    __device__ __forceinline__ void add_com(int r, double v)
@@ -396,6 +398,7 @@ __device__ __forceinline__ void thread_block_run(const KernelArgs &a, const int 
    }
    c2.active = true;
    c2.fext_on = a.fext != nullptr; c2.acc_on = a.body_acc != nullptr; c2.wr_on = a.joint_wrench != nullptr; c2.rootw_on = a.root_wrench != nullptr;
+   c2.com_only_on = ALGO == MB_CRBA && a.out == nullptr;
    c2.aux = aux;
    c2.nv = a.nv;
    c2.mstride = STATE_MAJOR ? 8u : c2.ld8;

@@ -268,8 +268,22 @@ class CompositeRigidBodyMassMatrixCalculator : public BatchedCalculatorBase
       else
          check(mecano_b200_crba_centroidal_host(handle_, n, q.ld, q.data, massMatrixOut.data, cmmOut.data, comOut.data, (int)frame_));
    }
-   // getCentroidalConvectiveTermMatrix() for N states: out 6 x N; com = the rows written by getCentroidalMomentumMatrix() for the
-   // same q (read in the centre-of-mass frame only)
+   // the centre of mass and total mass alone (CenterOfMassCalculator.getCenterOfMass() / getTotalMass(), CenterOfMassCalculator.java:
+   // 70-124), comOut 4 x N: no matrix computed or written, the rows getCentroidalMomentumMatrix() leaves bit for bit
+   void getCenterOfMass(const MatrixView &q, const MatrixView &comOut, Memory where = Memory::Device)
+   {
+      const int64_t n = q.cols, nq = input_.getConfigurationMatrixSize();
+      checkShape(q, nq, n, "q");
+      checkShape(comOut, 4, n, "centerOfMass");
+      if (comOut.ld != q.ld)
+         throw MatrixDimensionException("all matrices of one call must share the same leading dimension");
+      if (where == Memory::Device)
+         check(mecano_b200_center_of_mass(handle_, n, q.ld, q.data, comOut.data, stream_));
+      else
+         check(mecano_b200_center_of_mass_host(handle_, n, q.ld, q.data, comOut.data));
+   }
+   // getCentroidalConvectiveTermMatrix() for N states: out 6 x N; com = the rows written by getCentroidalMomentumMatrix() or
+   // getCenterOfMass() for the same q (read in the centre-of-mass frame only)
    void getCentroidalConvectiveTermMatrix(const MatrixView &q, const MatrixView &qd, const MatrixView &com, const MatrixView &out,
                                           Memory where = Memory::Device)
    {

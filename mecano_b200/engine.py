@@ -226,6 +226,19 @@ class Engine:
         else:
             check(lib.mecano_b200_crba_centroidal(self._h, n, ld, pq, pm, pa, pc, int(frame), self._stream()), self._h)
 
+    def center_of_mass(self, q, com):
+        """com [4, n]: centre of mass in the root frame and total mass per state, without a matrix (the com rows of crba_centroidal)."""
+        n = q.shape[1]
+        host = isinstance(q, np.ndarray)
+        f = _host_ptr_ld if host else self._dp
+        pq, l0 = f(q, self.nq, n)
+        pc, l1 = f(com, 4, n)
+        ld = _same_ld([l0, l1])
+        if host:
+            check(lib.mecano_b200_center_of_mass_host(self._h, n, ld, pq, pc), self._h)
+        else:
+            check(lib.mecano_b200_center_of_mass(self._h, n, ld, pq, pc, self._stream()), self._h)
+
     def centroidal_convective_term(self, q, qd, com, out, frame=_capi.FRAME_WORLD):
         """out [6, n]; com [4, n] as written by crba_centroidal (None allowed for the world frame)."""
         n = q.shape[1]
@@ -453,7 +466,7 @@ class MultiDeviceEngine:
     def _single_device_only(self, *a, **k):
         raise NotImplementedError("this entry point is served per device: build the calculator on one device")
 
-    aba_sources_host = coriolis = crba_centroidal = centroidal_convective_term = integrate_host = set_joint_source_modes = _single_device_only
+    aba_sources_host = coriolis = crba_centroidal = centroidal_convective_term = center_of_mass = integrate_host = set_joint_source_modes = _single_device_only
 
 
 def measure_fp64_peak(device=0):

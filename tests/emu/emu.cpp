@@ -78,6 +78,7 @@ template <class T> struct CpuCtx
          for (int j = 0; j < 8; j++) { st_M((*zl)[8 * i + j], (T)0); st_C((*zl)[8 * i + j], (T)0); }
    }
    bool has_rootw() const { return rootw != nullptr; }
+   bool com_only() const { return M == nullptr; } // gpu_ctx.cuh: a by-product CRBA launch without a matrix
    void st_cmm(int row, T v) { cmm[(long)row * ld + s] = (double)v; }
    void add_com(int r, T v) { com[r * ld + s] += (double)v; }
    void add_rootw(int r, T v) { rootw[r * ld + s] += (double)v; }
@@ -211,7 +212,7 @@ int run(int algo, const mecano_b200_tree_desc *d, const double *g, long n, long 
       }
       else if (algo == MB_CORIOLIS)
          mb::coriolis_state<T, CpuCtx<T>>(P, c);
-      else if (cmm)
+      else if (cmm || com)
          mb::crba_state<T, CpuCtx<T>, true>(P, c);
       else if (flags & 4u) // MECANO_B200_CRBA_PACKED: out = [packed rows][ld]
          mb::crba_state<T, CpuCtx<T>, false, true>(P, c);
@@ -251,6 +252,15 @@ extern "C" int emu_crba_centroidal(const mecano_b200_tree_desc *d, long n, long 
    const double g[3] = {0, 0, 0};
    std::fill(com, com + 4 * ld, 0.0);
    return run<double>(MB_CRBA, d, g, n, ld, q, nullptr, nullptr, nullptr, M, 0u, err, errlen, nullptr, nullptr, nullptr, nullptr, cmm, com, nullptr);
+}
+
+// the centre-of-mass-only launch of the by-product CRBA routine (mecano_b200_center_of_mass): no matrix, no momentum matrix (a
+// write through either would fault here), com [4][ld] = (mass * CoM, mass)
+extern "C" int emu_center_of_mass(const mecano_b200_tree_desc *d, long n, long ld, const double *q, double *com, char *err, int errlen)
+{
+   const double g[3] = {0, 0, 0};
+   std::fill(com, com + 4 * ld, 0.0);
+   return run<double>(MB_CRBA, d, g, n, ld, q, nullptr, nullptr, nullptr, nullptr, 0u, err, errlen, nullptr, nullptr, nullptr, nullptr, nullptr, com, nullptr);
 }
 
 // mass matrix M and Coriolis matrix C, both [nv * nv][ld] entry-major

@@ -185,6 +185,16 @@ class Emu:
             raise RuntimeError("emu_crba_centroidal rc=%d: %s" % (rc, err.value.decode()))
         return M.reshape(nv, nv, n), cmm.reshape(6, nv, n), com
 
+    def center_of_mass(self, q):
+        """(mass * CoM, mass) [4, n] from the centre-of-mass-only launch of the by-product CRBA routine (no matrix buffers)."""
+        n = q.shape[1]
+        com = np.full((4, n), np.nan)
+        err = ctypes.create_string_buffer(256)
+        rc = self.lib.emu_center_of_mass(ctypes.byref(self.desc), ctypes.c_long(n), ctypes.c_long(n), _d(q), _d(com), err, 256)
+        if rc != 0:
+            raise RuntimeError("emu_center_of_mass rc=%d: %s" % (rc, err.value.decode()))
+        return com
+
     def rnea_root_wrench(self, q, qd):
         """Wrench at the root, in the root frame, of inverse dynamics with zero joint accelerations and no gravity: [6, n]."""
         n = q.shape[1]

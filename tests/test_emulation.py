@@ -140,6 +140,8 @@ def test_emulated_centroidal_byproducts_match_oracle(idx):
     rw = e.rnea_root_wrench(q, qd)
     assert not (np.isnan(M).any() or np.isnan(cmm).any() or np.isnan(com).any() or np.isnan(rw).any())
     assert np.array_equal(M, e.crba(q)), "the by-products must not change the mass matrix"
+    # the centre-of-mass-only launch (no matrix buffers: a store to either would fault in the emulator) gives the same rows
+    assert np.array_equal(e.center_of_mass(q), com)
     for s in range(n):
         Mo, Ao, co, mo = o.crba_centroidal(q[:, s], 0)
         assert rel(cmm[:, :, s], Ao) < TOL

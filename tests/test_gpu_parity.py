@@ -632,6 +632,10 @@ def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
         com = calc.getCenterOfMass().cpu().numpy()
         b = calc.getCentroidalConvectiveTermMatrix(tq, tqd).cpu().numpy()
         assert not (np.isnan(A).any() or np.isnan(com).any() or np.isnan(b).any()), name
+        # the convective term took its centre of mass from the centre-of-mass-only launch (mecano_b200_center_of_mass: the
+        # by-product kernel without a matrix): the same rows, bit for bit, as the full launch left
+        assert calc.getCenterOfMass() is not None and np.array_equal(calc.getCenterOfMass().cpu().numpy(), com), name
+        assert np.array_equal(mb.CompositeRigidBodyMassMatrixCalculator(s, frame_name).getCenterOfMass(tq).cpu().numpy(), com), name
         for k in range(0, n, 53):
             _, Ao, co, mo = o.crba_centroidal(q[:, k], frame)
             assert rel(A[:, :, k], Ao) < TOL, name
@@ -642,6 +646,7 @@ def test_centroidal_momentum_matrix_and_convective_term(torch_dev, idx):
         Ah = hc.getCentroidalMomentumMatrix(q).reshape(6, nv, n)
         bh = hc.getCentroidalConvectiveTermMatrix(q, qd)
         assert rel(Ah, A) == 0.0 and rel(bh, b) == 0.0 and rel(hc.getMassMatrix(), M_plain) == 0.0, name
+        assert np.array_equal(hc.getCenterOfMass(q), com), name
     # batch-wide invariant in the world frame: A qdd + b = sum over the root's children of their joint wrench, in the world frame,
     # which for a single floating root joint is the pelvis wrench rotated / shifted by the pelvis pose; checked through linear
     # momentum only (frame-origin independent): total force = mass * CoM acceleration = rows 3..5

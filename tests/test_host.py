@@ -238,6 +238,8 @@ def test_new_entry_points_reject_a_null_handle():
     assert lib.mecano_b200_crba_centroidal_host(null, n, ld, null, null, null, null, 0) == bad
     assert lib.mecano_b200_centroidal_convective_term(null, n, ld, null, null, null, null, 0, null) == bad
     assert lib.mecano_b200_centroidal_convective_term_host(null, n, ld, null, null, null, null, 0) == bad
+    assert lib.mecano_b200_center_of_mass(null, n, ld, null, null, null) == bad
+    assert lib.mecano_b200_center_of_mass_host(null, n, ld, null, null) == bad
     assert lib.mecano_b200_coriolis(null, n, ld, null, null, null, null, null) == bad
     assert lib.mecano_b200_coriolis_host(null, n, ld, null, null, null, null) == bad
     assert lib.mecano_b200_set_precision(null, 1) == bad
