@@ -151,7 +151,7 @@ int run(mecano_b200_handle *h, int algo, int64_t n, int64_t ld, const double *q,
    if (h->fp32)
    {
       // the optional fp32 variant: plain calls on the thread-per-state kernels only, never a silent fp64 substitute
-      if (algo > MB_CRBA || packed || fext || opt.body_acc || opt.joint_wrench || x2 || opt.cmm || opt.root_wrench || flags != 0)
+      if (algo > MB_CRBA || packed || fext || opt.body_acc || opt.joint_wrench || x2 || opt.cmm || opt.com || opt.root_wrench || flags != 0)
          return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant covers plain RNEA / ABA / CRBA calls only (no external wrenches, flags, by-products)");
       if (!h->plan[algo].fp32_ok || h->has_3dof)
          return fail(h, MECANO_B200_ERR_UNSUPPORTED_TOPOLOGY, "the fp32 variant is compiled for the launch configuration of humanoid-sized trees of one-DoF and SixDoF joints only");

@@ -200,7 +200,7 @@ cudaError_t launch_thread_kernel(int algo, const MbProgram &P, const KernelArgs 
       pick_f32(algo)<<<g, plan.block, plan.smem, stream>>>(P, b);
       return cudaGetLastError();
    }
-   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.root_wrench != nullptr, layout, plan.size_class, plan.m3);
+   KernelFn fn = pick(algo, a.fext != nullptr || a.body_acc != nullptr || a.joint_wrench != nullptr || a.x2 != nullptr || a.cmm != nullptr || a.com != nullptr || a.root_wrench != nullptr, layout, plan.size_class, plan.m3);
    const long long ntiles = (a.n + plan.block - 1) / plan.block;
    // ABA runs as a persistent grid (its pass-two records live in a workspace with one column per resident thread), and so
    // does every kernel with a TMEM stack: a block then allocates its tensor memory, stages the constant records and
