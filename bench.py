@@ -693,15 +693,16 @@ def main():
                 hq[:, sl].copy_(q[:, :per]); hqd[:, sl].copy_(qd[:, :per]); hqdd[:, sl].copy_(qdd[:, :per]); htau_in[:, sl].copy_(tau_in[:, :per])
             nq_, nqd_, nqdd_, ntau_in, ntau, nqdd_out, nM = (t_.numpy() for t_ in (hq, hqd, hqdd, htau_in, htau, hqdd_out, hM))
 
-            def host_step(packed):
+            def host_step(packed, zeros_present=False):
                 Mv = nM[:rows_packed] if packed else nM
-                stepc.compute(nq_, nqd_, qdd=nqdd_, tau=ntau_in, tauOut=ntau, qddOut=nqdd_out, massMatrix=Mv, packed=packed)
+                stepc.compute(nq_, nqd_, qdd=nqdd_, tau=ntau_in, tauOut=ntau, qddOut=nqdd_out, massMatrix=Mv, packed=packed,
+                              massMatrixZerosPresent=zeros_present)
 
-            def timed_host(packed):
-                host_step(packed)  # warm-up (allocates the staging buffers)
+            def timed_host(packed, zeros_present=False):
+                host_step(packed)  # warm-up (allocates the staging buffers; dense: writes every entry, structural zeros included)
                 t0 = time.perf_counter()
                 for _ in range(args.e2e_steps):
-                    host_step(packed)
+                    host_step(packed, zeros_present)
                 return (time.perf_counter() - t0) / args.e2e_steps  # the call returns when the outputs are complete on the host
 
             # PCIe denominators measured live: one large pinned copy each way on device 0
@@ -730,6 +731,19 @@ def main():
                            "roofline": {"bound": "pcie", "achieved": d2h / dt / 1e9 / world, "peak": pcie["d2h_gbs_peak"], "unit": "GB/s per GPU, device -> host",
                                         "frac": d2h / dt / 1e9 / world / pcie["d2h_gbs_peak"], "h2d_gbs_peak": pcie["h2d_gbs_peak"],
                                         "peak_source": "1 GiB pinned cudaMemcpy each way on GPU 0, measured in this run"}}
+            # the dense matrix kept in one host buffer across steps, as Mecano's calculator keeps its own: structurally zero
+            # entries written (and transferred) by the warm-up call only
+            nnz_rows = rows_dense - len(set(owned_zero_entries(system)))
+            dto = timed_host(False, True)
+            d2ho = int(8 * (2 * nv + nnz_rows) * hn)
+            line["extras"]["e2e_dense_kept"] = {
+                "value": hn / dto, "unit": UNIT, "ms_per_step": dto * 1e3, "steps": args.e2e_steps, "states_per_gpu": per, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2ho, "check": float(np.abs(nM).max()), "zero_entries_still_zero": bool(not nM[sorted(set(owned_zero_entries(system)))[:8]].any()),
+                "pcie_d2h_frac": d2ho / dto / 1e9 / world / pcie["d2h_gbs_peak"],
+                "what": "as e2e, the dense entry-major matrix kept in the same host buffer from step to step (what Mecano's calculator-owned "
+                        "DMatrixRMaj is): the %d of %d entries that are structurally zero are written by the first call and neither recomputed nor "
+                        "transferred again (MECANO_B200_CRBA_ZEROS_PRESENT through MultiBodyDynamicsStep.compute(massMatrixZerosPresent=True)); the "
+                        "result in host memory is the same dense matrix bit for bit" % (rows_dense - nnz_rows, rows_dense)}
             dtp = timed_host(True)
             d2hp = int(8 * (2 * nv + rows_packed) * hn)
             line["extras"]["e2e_packed"] = {

@@ -303,7 +303,7 @@ int mecano_b200_crba_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, c
  * per calculator, and the three kernels run back to back on the resident chunk.
  *   qdd_in  [n_dofs][ld]  joint accelerations for inverse dynamics     -> tau_out    [n_dofs][ld]  (both NULL: skip RNEA)
  *   tau_in  [n_dofs][ld]  joint efforts for forward dynamics           -> qdd_out    [n_dofs][ld]  (both NULL: skip ABA)
- *   mass_matrix           layout as mecano_b200_crba_host (ENTRY_MAJOR, STATE_MAJOR or PACKED)     (NULL: skip CRBA)
+ *   mass_matrix           layout as mecano_b200_crba_host (ENTRY_MAJOR [| ZEROS_PRESENT], STATE_MAJOR or PACKED)   (NULL: skip CRBA)
  * fext (nullable) applies to both dynamics calculators.  Results are bit-identical to the three separate calls.
  */
 int mecano_b200_step_host(mecano_b200_handle *h, int64_t n_states, int64_t ld, const double *q, const double *qd, const double *qdd_in,

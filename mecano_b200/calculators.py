@@ -581,10 +581,33 @@ class MultiBodyDynamicsStep:
     def getMassMatrixRows(self, packed=False):
         return self._engine.packed_size() if packed else self._engine.nv * self._engine.nv
 
-    def compute(self, q, qd, qdd=None, tau=None, tauOut=None, qddOut=None, massMatrix=None, packed=False, stateMajor=False):
+    def compute(self, q, qd, qdd=None, tau=None, tauOut=None, qddOut=None, massMatrix=None, packed=False, stateMajor=False, ownedMassMatrix=False,
+                massMatrixZerosPresent=False):
         """qdd -> tauOut (inverse dynamics), tau -> qddOut (forward dynamics), massMatrix (layout as getMassMatrix): each part runs
-        if its matrices are given."""
+        if its matrices are given.  ownedMassMatrix=True (dense entry-major layout, no `massMatrix`): the step owns the dense
+        matrix like Mecano's calculator does (getMassMatrix() returns a reference to the internal matrix,
+        CompositeRigidBodyMassMatrixCalculator.java:344-348) -- one page-locked [nDoFs*nDoFs, N] buffer per batch shape, reused by
+        later calls, whose structurally zero entries are written by the first call and from the second on neither recomputed nor
+        sent over PCIe again (MECANO_B200_CRBA_ZEROS_PRESENT): the same dense matrix for about half the bytes on a humanoid.
+        massMatrixZerosPresent=True is the same for a caller-owned dense entry-major `massMatrix`: the caller's statement that an
+        earlier call for this tree filled this very buffer (so its structurally zero entries hold zeros)."""
         layout = _capi.CRBA_PACKED if packed else (_capi.CRBA_STATE_MAJOR if stateMajor else _capi.CRBA_ENTRY_MAJOR)
+        if massMatrixZerosPresent:
+            if massMatrix is None or packed or stateMajor or ownedMassMatrix:
+                raise ValueError("massMatrixZerosPresent: a caller-owned dense entry-major massMatrix filled by an earlier call")
+            layout |= _capi.CRBA_ZEROS_PRESENT
+        if ownedMassMatrix:
+            if massMatrix is not None or packed or stateMajor:
+                raise ValueError("ownedMassMatrix: the dense entry-major matrix of the step itself (no massMatrix / packed / stateMajor)")
+            nv, n = self._engine.nv, q.shape[1]
+            ld = n if q.shape[0] < 2 else max(n, q.strides[0] // 8)
+            key = (n, ld)
+            if getattr(self, "_owned_key", None) != key:
+                self._owned_key, self._owned_M, self._owned_primed = key, CompositeRigidBodyMassMatrixCalculator._new_owned(q, (nv * nv, n), ld), False
+            massMatrix = self._owned_M
+            if self._owned_primed:
+                layout |= _capi.CRBA_ZEROS_PRESENT
+            self._owned_primed = True
         self._engine.step_host(q, qd, qdd_in=qdd, tau_in=tau, tau_out=tauOut, qdd_out=qddOut, M=massMatrix, layout=layout)
         return tauOut, qddOut, massMatrix
 

@@ -400,6 +400,9 @@ int host_begin(mecano_b200_handle *h, HostJob &j)
          return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "NULL buffer");
       if (aba && h->n_accel_source > 0)
          return fail(h, MECANO_B200_ERR_INVALID_ARGUMENT, "joints in ACCELERATION_SOURCE mode need their accelerations: call mecano_b200_aba_sources_host");
+      // (state-major: as below, the kernel rewrites the structural zeros in the staging buffer every time)
+      if (j.flags & MECANO_B200_CRBA_STATE_MAJOR)
+         j.flags &= ~MECANO_B200_CRBA_ZEROS_PRESENT;
       j.m_rows = j.M ? mass_matrix_rows(h, j.flags) : 0;
       j.in_rows = nq + (rnea || aba ? nv : 0) + (rnea ? nv : 0) + (aba ? nv : 0) + (j.fext ? 6 * nb : 0);
       j.out_rows = (rnea ? nv : 0) + (aba ? nv : 0) + j.m_rows;
@@ -481,6 +484,13 @@ int host_issue_chunk(mecano_b200_handle *h, HostJob &j)
          if (rc) return rc;
          if (j.flags & MECANO_B200_CRBA_STATE_MAJOR)
             MB_CUDA(h, cudaMemcpyAsync(j.M + (size_t)s0 * nv * nv, dM, w * nv * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+         else if (j.flags & MECANO_B200_CRBA_ZEROS_PRESENT)
+         {
+            // entry-major: a structurally zero entry is a whole row of the host matrix, which already holds zeros (and which the
+            // kernel did not write in the staging buffer)
+            for (const auto &run : h->nonzero_runs)
+               MB_CUDA(h, copy_rows(j.M + (size_t)run.first * ld + s0, ld, dM + (size_t)run.first * chunk, chunk, w, (size_t)run.second, cudaMemcpyDeviceToHost, st));
+         }
          else
             MB_CUDA(h, d2h(j.M, dM, j.m_rows));
       }

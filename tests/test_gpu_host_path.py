@@ -241,3 +241,45 @@ def test_host_state_major_owned_matrix_survives_other_calls(torch_dev):
         junk = states(mb, s, rng, n)[0]
         big = crba.getMassMatrix(junk, pinned((nv * nv, n)))
         assert np.isfinite(big).all()
+
+
+def test_fused_host_step_owned_mass_matrix(torch_dev):
+    """MultiBodyDynamicsStep.compute(ownedMassMatrix=True): the step's own dense matrix, structurally zero entries written by the
+    first call and neither recomputed nor transferred from the second on (mecano_b200_step_host with ENTRY_MAJOR | ZEROS_PRESENT).
+    Every call must return the full dense matrix bit for bit, with other host calls dirtying the staging buffers in between; the
+    state-major layout ignores the flag (the kernel rewrites the zeros) instead of returning stale entries."""
+    import mecano_b200 as mb
+    from mecano_b200 import _capi
+
+    torch, dev = torch_dev
+    s, t = build(kind="humanoid", seed=7, n_joints=2)
+    rng = np.random.default_rng(21)
+    n, ld, nv = 9001, 9216, t.nv
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    ident = mb.InverseDynamicsCalculator(s)
+    step = mb.MultiBodyDynamicsStep(s)
+    new = lambda rows: pinned((rows, ld))[:, :n]  # noqa: E731
+    zero_rows = None
+    for k in range(3):
+        q, qd, qdd, tau = states(mb, s, rng, n, ld)
+        M_ref = crba.getMassMatrix(q, new(nv * nv)).copy()
+        tau_out, qdd_out = new(nv), new(nv)
+        _, _, M = step.compute(q, qd, qdd=qdd, tau=tau, tauOut=tau_out, qddOut=qdd_out, ownedMassMatrix=True)
+        assert np.array_equal(M, M_ref), k
+        assert np.array_equal(tau_out, ident.compute(q, qd, qdd, new(nv))), k
+        if zero_rows is None:
+            zero_rows = np.flatnonzero(~M_ref.any(axis=1))
+            assert len(zero_rows) > 0  # a humanoid has unrelated branches
+        # the step hands out the same buffer every time; dirty the staging buffers of the handle with a full dense call
+        assert step.compute(q, None, ownedMassMatrix=True)[2] is M
+        junk = new(nv * nv)
+        step.compute(states(mb, s, rng, n, ld)[0], None, massMatrix=junk)
+        assert np.isfinite(junk).all()
+    # raw C ABI, state-major with the flag set: the zeros come back as zeros although the host buffer held garbage
+    q = states(mb, s, rng, n, ld)[0]
+    Ms = pinned((n, nv * nv))
+    Ms[:] = 7.0
+    step._engine.step_host(q, None, M=Ms, layout=_capi.CRBA_STATE_MAJOR | _capi.CRBA_ZEROS_PRESENT)
+    assert np.array_equal(Ms, crba.getMassMatrix(q, pinned((n, nv * nv)), stateMajor=True))
+    with pytest.raises(ValueError):
+        step.compute(q, None, massMatrix=Ms, ownedMassMatrix=True)
