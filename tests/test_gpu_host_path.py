@@ -275,6 +275,11 @@ def test_fused_host_step_owned_mass_matrix(torch_dev):
         junk = new(nv * nv)
         step.compute(states(mb, s, rng, n, ld)[0], None, massMatrix=junk)
         assert np.isfinite(junk).all()
+    # the same through the multi-device engine (three slices on one GPU: mecano_b200_multi_step_host)
+    multi = mb.MultiBodyDynamicsStep(s, device=[0, 0, 0])
+    for k in range(2):
+        q = states(mb, s, rng, n, ld)[0]
+        assert np.array_equal(multi.compute(q, None, ownedMassMatrix=True)[2], crba.getMassMatrix(q, new(nv * nv))), k
     # raw C ABI, state-major with the flag set: the zeros come back as zeros although the host buffer held garbage
     q = states(mb, s, rng, n, ld)[0]
     Ms = pinned((n, nv * nv))
