@@ -230,7 +230,7 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
    __device__ __forceinline__ double aux_ld(int i) const { return aux[i]; }
    __device__ __forceinline__ void aux_st(int i, double v) { aux[i] = v; }
    // ABA pass-two records: global workspace of double2, one column per resident thread (coalesced 16-byte accesses),
-   // read back in pass three through the ring below with cp.async.cg (L2, the coherence point of the earlier stores)
+   // read back in pass three through the ring below with cp.async (every thread reads only its own earlier stores)
    const char *ws0;   // workspace (uniform)
    unsigned ws_ld16;  // bytes between consecutive record slots (the launcher keeps the workspace below 4 GB)
    unsigned w16;      // byte offset of this thread's column
@@ -243,6 +243,14 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
       asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(rec_at(i2)) : "memory");
    }
    // pass-three ring: [stage][(q, qd) | rec0 .. rec2][BLOCK] double2, overlaid on the (then idle) stack area
+   // MB_ABA_REC_VIA_L1 (default): the records come through L1 (cp.async.ca) instead of around it (.cg, = 0).  ncu counts 12
+   // shared-memory wavefronts per LDGSTS.BYPASS.128 against 4 for the 512 contiguous bytes a warp writes -- 90 % of the kernel's
+   // excess wavefronts, a quarter of all its shared-memory wavefronts; through L1 the fill arrives as whole lines: 1.5037 ->
+   // 1.4925 ms, bit-identical (profiles/r06zu_shared_wavefronts.md).  A thread reads back only what it stored itself earlier
+   // in program order (same SM, same L1: write-through, updated on a store hit), so the copy in L1 is never stale.
+#ifndef MB_ABA_REC_VIA_L1
+#define MB_ABA_REC_VIA_L1 1
+#endif
    __device__ __forceinline__ void pf3_issue(int stage, int cfg, int dof, int rec2, int mask) const
    {
       const unsigned dst = sb + (unsigned)(stage * (MB_ABA_RING_ROWS * BLOCK * 16));
@@ -252,7 +260,13 @@ template <int BLOCK, int TM, int ROWS, bool M3 = false> struct GpuCtx2
          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8), "l"(row_qd((unsigned)dof)) : "memory");
 #pragma unroll
       for (int j = 0; j < MB_ABA_REC / 2; j++)
+      {
+#if MB_ABA_REC_VIA_L1
+         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(rec_at(rec2 + j)) : "memory");
+#else
          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (1 + j) * BLOCK * 16), "l"(rec_at(rec2 + j)) : "memory");
+#endif
+      }
    }
    __device__ __forceinline__ void pf3_ld2(int stage, int row, double &a, double &b) const { mb_lds2(sb + (unsigned)((stage * MB_ABA_RING_ROWS + row) * (BLOCK * 16)), a, b); }
    // The record of a body is dead once pass three has read it: tell L2 so (discard.global.L2 drops the lines without writing
