@@ -463,7 +463,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
         """getCentroidalConvectiveTermMatrix() (:423-440, :811-839) for N states: [6, N], moment first, in the centroidal momentum
         frame.  In CENTER_OF_MASS_FRAME the centre of mass is that of the `q` passed here: getCenterOfMass(q) runs first (the
         reference derives both from the same joint state after reset()).  reuseCenterOfMass=True skips that when the
-        caller has just called getCentroidalMomentumMatrix() with this very `q` (same object, same batch); it is the caller's
+        caller has just called getCentroidalMomentumMatrix() or getCenterOfMass() with this very `q` (same object, same batch); it is the caller's
         statement that the configuration has not changed since."""
         nv, nq = self._input.getNumberOfDoFs(), self._input.getConfigurationMatrixSize()
         n = q.shape[1] if q.ndim == 2 else -1
@@ -517,6 +517,7 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
             return massMatrix
         shape = (n, nv * nv) if stateMajor else (nv * nv, n)
         layout = _capi.CRBA_STATE_MAJOR if stateMajor else _capi.CRBA_ENTRY_MAJOR
+        owned_key = None
         if massMatrix is None:
             # entry-major: [nv*nv, n] sharing the leading dimension of q; state-major: one contiguous [n, nv*nv]
             ld = shape[1] if stateMajor or q.shape[0] < 2 else max(n, q.stride(0) if _is_torch(q) else q.strides[0] // 8)
@@ -527,12 +528,14 @@ class CompositeRigidBodyMassMatrixCalculator(_BatchedCalculator):
             massMatrix, primed = self._owned[key]
             if primed:
                 layout |= _capi.CRBA_ZEROS_PRESENT
-            self._owned[key][1] = True
+            owned_key = key
         self._check("massMatrix", massMatrix, *shape)
         if _is_torch(q):
             self._engine.crba(q, massMatrix, layout)
         else:
             self._engine.crba_host(q, massMatrix, layout)
+        if owned_key is not None:
+            self._owned[owned_key][1] = True  # (only once a call has been issued without error: a failed first call wrote no zeros)
         self._M = massMatrix
         return massMatrix
 
@@ -607,8 +610,9 @@ class MultiBodyDynamicsStep:
             massMatrix = self._owned_M
             if self._owned_primed:
                 layout |= _capi.CRBA_ZEROS_PRESENT
-            self._owned_primed = True
         self._engine.step_host(q, qd, qdd_in=qdd, tau_in=tau, tau_out=tauOut, qdd_out=qddOut, M=massMatrix, layout=layout)
+        if ownedMassMatrix:
+            self._owned_primed = True  # (only once a call has completed: a failed first call has not written the zeros)
         return tauOut, qddOut, massMatrix
 
 
