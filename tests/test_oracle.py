@@ -187,6 +187,77 @@ def test_body_accelerations_consistent():
     assert np.allclose(acc[:, :3], 0, atol=1e-14)
 
 
+@pytest.mark.parametrize("idx", [1, 2, 3])
+def test_body_accelerations_against_numerical_differentiation_of_the_twists(idx):
+    """The Coriolis-aware change of frame of a spatial acceleration (SpatialAccelerationBasics.changeFrame, the a4 row of SURVEY 8)
+    the way the reference tests it (SpatialAccelerationTest.testChangeFrameUsingNumericalDifferentiationVersusAnalytical,
+    T/spatial/SpatialAccelerationTest.java:28-46): analytical against numerically differentiated twists.  The twist of every body,
+    expressed in its own centre-of-mass frame, comes from the same propagation run at rest (at zero velocity the acceleration of
+    a body is S qdd carried up the tree, so `qdd := qd` and no gravity gives the twist); its coordinates differentiated along
+    q(t) = q + t qd + t^2 qdd / 2 are the spatial acceleration (v x v = 0).  One-DoF trees, where q(t) is exact."""
+    rng = np.random.default_rng(700 + idx)
+    name, t = cases(rng)[idx]
+    o = ol.Oracle(t, gravity=(0.0, 0.0, 0.0))
+    q, qd, qdd, _ = td.random_states(rng, t, 3)
+    zero = np.zeros(t.nv)
+    h = 1.0e-5
+    for s in range(3):
+        twist = lambda dt: o.body_accelerations(q[:, s] + dt * qd[:, s] + 0.5 * dt * dt * qdd[:, s], zero, qd[:, s] + dt * qdd[:, s])  # noqa: E731
+        numerical = (twist(h) - twist(-h)) / (2.0 * h)
+        analytical = o.body_accelerations(q[:, s], qd[:, s], qdd[:, s])
+        assert np.max(np.abs(numerical - analytical)) < 2.0e-8 * max(1.0, np.max(np.abs(analytical))), name
+        # and the flags: without the velocity terms the acceleration is the twist propagation itself
+        assert np.allclose(o.body_accelerations(q[:, s], qd[:, s], qdd[:, s], flags=1), o.body_accelerations(q[:, s], zero, qdd[:, s]), atol=1e-13)
+
+
+@pytest.mark.parametrize("idx", [5, 6, 8, 10, 12])
+def test_body_accelerations_against_differentiated_twists_along_the_integrator(idx):
+    """The same for trees with SixDoF / spherical / planar joints, where q(t) is not a polynomial: the configurations at t +- h come
+    from the oracle's state integrator (MultiBodySystemStateIntegrator.doubleIntegrateFromAcceleration, second-order accurate), so
+    the test also ties the integrator's multi-DoF updates to the acceleration convention of the dynamics (the joint acceleration of
+    a floating joint is a spatial acceleration in the frame after the joint)."""
+    rng = np.random.default_rng(720 + idx)
+    name, t = cases(rng)[idx]
+    o = ol.Oracle(t, gravity=(0.0, 0.0, 0.0))
+    q, qd, qdd, _ = td.random_states(rng, t, 2)
+    zero = np.zeros(t.nv)
+    h = 1.0e-5
+
+    def twist(s, dt):
+        q1, qd1, _ = o.integrate(dt, q[:, s], qd[:, s], qdd[:, s])
+        return o.body_accelerations(q1, zero, qd1)
+
+    for s in range(2):
+        numerical = (twist(s, h) - twist(s, -h)) / (2.0 * h)
+        analytical = o.body_accelerations(q[:, s], qd[:, s], qdd[:, s])
+        assert np.max(np.abs(numerical - analytical)) < 5.0e-8 * max(1.0, np.max(np.abs(analytical))), name
+
+
+@pytest.mark.parametrize("idx", [1, 3, 5, 6, 8, 10, 12, 13])
+def test_power_balance_along_the_integrator(idx):
+    """A law of mechanics that no recursion enters: along the motion, d/dt (qd^T M(q) qd / 2) = qd^T (tau - g(q)).  Left: the mass
+    matrix (CRBA) at the configurations the state integrator reaches at t +- h under the accelerations of forward dynamics (ABA),
+    differentiated numerically; right: the applied efforts minus the gravity efforts of inverse dynamics at rest (RNEA).  Holds
+    only if the three calculators, the integrator and the conventions for multi-DoF joints (velocities of a floating joint = the
+    twist in the frame after the joint, efforts = the wrench there) agree with one another and with physics."""
+    rng = np.random.default_rng(740 + idx)
+    name, t = cases(rng)[idx]
+    o = ol.Oracle(t, gravity=(0.3, -0.2, -9.81))
+    q, qd, _, tau = td.random_states(rng, t, 2)
+    zero = np.zeros(t.nv)
+    h = 1.0e-5
+    for s in range(2):
+        qdd = o.aba(q[:, s], qd[:, s], tau[:, s])
+
+        def kinetic(dt):
+            q1, qd1, _ = o.integrate(dt, q[:, s], qd[:, s], qdd)
+            return 0.5 * qd1 @ o.crba(q1) @ qd1
+
+        numerical = (kinetic(h) - kinetic(-h)) / (2.0 * h)
+        power = qd[:, s] @ (tau[:, s] - o.rnea(q[:, s], zero, zero))
+        assert abs(numerical - power) < 2.0e-8 * max(1.0, abs(power)), (name, numerical, power)
+
+
 def test_golden_fixtures():
     """Regression vectors generated by tests/golden/make_golden.py from this oracle (NOT from the JVM)."""
     path = os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.npz")
