@@ -371,6 +371,55 @@ def test_baseline_configs_3_4_humanoid_1m_states_invariants(torch_dev, neck):
     assert rel(Ms, o.crba_batch(hq)) < TOL
 
 
+def test_power_balance_on_device_1m_states(torch_dev):
+    """A size-independent property that involves every kernel of the path and the integrator, at BASELINE's full batch: along the
+    motion d/dt (qd^T M(q) qd / 2) = qd^T (tau - g(q)).  Forward dynamics (ABA) gives the accelerations, the state integrator the
+    states at t +- h, the mass matrix (CRBA) their kinetic energy, inverse dynamics at rest (RNEA) the gravity efforts -- all on
+    the device; the same check runs on the oracle in tests/test_oracle.py::test_power_balance_along_the_integrator."""
+    import mecano_b200 as mb
+
+    torch, dev = torch_dev
+    s, t = build(kind="humanoid", seed=99, n_joints=2)
+    nv, nq, n = t.nv, t.nq, 1 << 20
+    gen = torch.Generator(device=dev).manual_seed(8)
+    q = (torch.rand((nq, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * np.pi
+    quat = torch.randn((4, n), dtype=torch.float64, device=dev, generator=gen)
+    q[0:4] = quat / quat.norm(dim=0, keepdim=True)
+    q[4:7] = torch.rand((3, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    qd = torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+    tau = (torch.rand((nv, n), dtype=torch.float64, device=dev, generator=gen) * 2 - 1) * 10.0
+    g = (0.3, -0.2, -9.81)
+    ident = mb.InverseDynamicsCalculator(s)
+    fdyn = mb.ForwardDynamicsCalculator(s)
+    crba = mb.CompositeRigidBodyMassMatrixCalculator(s)
+    ident.setGravitationalAcceleration(g)
+    fdyn.setGravitationalAcceleration(g)
+    qdd = fdyn.compute(q, qd, tau)
+    zero = torch.zeros_like(qd)
+    gravity_efforts = ident.compute(q, zero, zero)
+    power = (qd * (tau - gravity_efforts)).sum(dim=0)
+    # central differences with h = 1e-5: truncation (h^2 times the third derivative) and rounding (eps |T| / h) meet there; on the
+    # oracle the worst of 1e5 such states is off by 5e-7 .. 9e-7 of max(1, |power|), the median by 1e-9 (h = 3e-5: 3e-6, 1e-6: 1.5e-6)
+    h = 1.0e-5
+    chunk = 1 << 17
+    worst = 0.0
+    medians = []
+    integrators = {dt: mb.MultiBodySystemStateIntegrator(s, dt) for dt in (h, -h)}
+    for a in range(0, n, chunk):
+        kinetic = []
+        for dt in (h, -h):
+            q1, qd1, qdd1 = (x[:, a:a + chunk].clone(memory_format=torch.contiguous_format) for x in (q, qd, qdd))
+            integrators[dt].doubleIntegrateFromAcceleration(q1, qd1, qdd1)
+            M = crba.getMassMatrix(q1).reshape(nv, nv, -1)
+            kinetic.append(0.5 * torch.einsum("is,ijs,js->s", qd1, M, qd1))
+        numerical = (kinetic[0] - kinetic[1]) / (2.0 * h)
+        p = power[a:a + chunk]
+        e = (numerical - p).abs() / torch.clamp(p.abs(), min=1.0)
+        worst = max(worst, float(e.max()))
+        medians.append(float(e.median()))
+    assert worst < 5.0e-5 and max(medians) < 1.0e-7, (worst, medians)
+
+
 SPEC_CASES = [
     ("A7 revolute chain", dict(kind="chain", seed=1, n_joints=7)),
     ("prismatic chain", dict(kind="chain", seed=3, n_joints=6, prismatic=1.0)),
