@@ -338,3 +338,100 @@ extern "C" int emu_program_info(const mecano_b200_tree_desc *d, int algo, int *o
    out8[6] = P.nv; out8[7] = P.nq;
    return 0;
 }
+
+// ---- the spatial-algebra primitives of the kernels (spatial.cuh), one call each, for unit tests against dense 6 x 6 numpy
+// (the reference tests its own unrolled helpers the same way: ArticulatedBodyInertiaTest.java:21-64, SpatialInertiaBasicsTest,
+// MecanoToolsTest.testComputeDynamicWrench).  Flat layouts: X = R row-major (9), p (3); spatial vector = angular (3), linear (3);
+// rigid-body inertia = I (xx xy xz yy yz zz), h (3), m; articulated inertia = A (6, symmetric), C (9, row-major), L (6).
+namespace
+{
+using D = double;
+mb::XfT<D> rd_xf(const D *p)
+{
+   mb::XfT<D> X;
+   X.R.xx = p[0]; X.R.xy = p[1]; X.R.xz = p[2]; X.R.yx = p[3]; X.R.yy = p[4]; X.R.yz = p[5]; X.R.zx = p[6]; X.R.zy = p[7]; X.R.zz = p[8];
+   X.p = mb::v3<D>(p[9], p[10], p[11]);
+   return X;
+}
+mb::SvT<D> rd_sv(const D *p)
+{
+   mb::SvT<D> v;
+   v.a = mb::v3<D>(p[0], p[1], p[2]);
+   v.l = mb::v3<D>(p[3], p[4], p[5]);
+   return v;
+}
+mb::S3T<D> rd_s3(const D *p)
+{
+   mb::S3T<D> s;
+   s.xx = p[0]; s.xy = p[1]; s.xz = p[2]; s.yy = p[3]; s.yz = p[4]; s.zz = p[5];
+   return s;
+}
+mb::RbiT<D> rd_rbi(const D *p)
+{
+   mb::RbiT<D> I;
+   I.I = rd_s3(p);
+   I.h = mb::v3<D>(p[6], p[7], p[8]);
+   I.m = p[9];
+   return I;
+}
+mb::AbiT<D> rd_abi(const D *p)
+{
+   mb::AbiT<D> I;
+   I.A = rd_s3(p);
+   I.C.xx = p[6]; I.C.xy = p[7]; I.C.xz = p[8]; I.C.yx = p[9]; I.C.yy = p[10]; I.C.yz = p[11]; I.C.zx = p[12]; I.C.zy = p[13]; I.C.zz = p[14];
+   I.L = rd_s3(p + 15);
+   return I;
+}
+void wr_sv(D *o, const mb::SvT<D> &v) { o[0] = v.a.x; o[1] = v.a.y; o[2] = v.a.z; o[3] = v.l.x; o[4] = v.l.y; o[5] = v.l.z; }
+void wr_s3(D *o, const mb::S3T<D> &s) { o[0] = s.xx; o[1] = s.xy; o[2] = s.xz; o[3] = s.yy; o[4] = s.yz; o[5] = s.zz; }
+void wr_abi(D *o, const mb::AbiT<D> &I)
+{
+   wr_s3(o, I.A);
+   o[6] = I.C.xx; o[7] = I.C.xy; o[8] = I.C.xz; o[9] = I.C.yx; o[10] = I.C.yy; o[11] = I.C.yz; o[12] = I.C.zx; o[13] = I.C.zy; o[14] = I.C.zz;
+   wr_s3(o + 15, I.L);
+}
+} // namespace
+
+extern "C" int emu_spatial(int op, const double *in, double *out)
+{
+   using namespace mb;
+   switch (op)
+   {
+      case 0: wr_sv(out, motion_to_child(rd_xf(in), rd_sv(in + 12))); return 6;
+      case 1: wr_sv(out, force_to_parent(rd_xf(in), rd_sv(in + 12))); return 6;
+      case 2:
+      {
+         const RbiT<D> r = rbi_to_parent(rd_xf(in), rd_rbi(in + 12));
+         wr_s3(out, r.I);
+         out[6] = r.h.x; out[7] = r.h.y; out[8] = r.h.z; out[9] = r.m;
+         return 10;
+      }
+      case 3: wr_abi(out, abi_to_parent<D, 0>(rd_xf(in), rd_abi(in + 12))); return 21;
+      case 4: wr_sv(out, newton_euler(rd_s3(in), v3<D>(in[6], in[7], in[8]), in[9], rd_sv(in + 10), rd_sv(in + 16))); return 6;
+      case 5: wr_sv(out, abi_solve(rd_abi(in), rd_sv(in + 21))); return 6;
+      case 6: wr_sv(out, mul(rd_abi(in), rd_sv(in + 21))); return 6;
+      case 7: wr_sv(out, mul(rd_rbi(in), rd_sv(in + 10))); return 6;
+      case 8: wr_sv(out, cross_motion(rd_sv(in), rd_sv(in + 6))); return 6;
+      case 9: wr_sv(out, cross_force(rd_sv(in), rd_sv(in + 6))); return 6;
+      case 10: wr_abi(out, abi_downdate<D, 0>(rd_abi(in), rd_sv(in + 21), rd_sv(in + 27))); return 21;
+      // the zero-structured pair the one-DoF joints use: downdate along z (1: revolute, 2: prismatic), then the congruence that
+      // skips the zero row / column; in = X (12), IA (21), U (6), g (6); out = downdated (21), transformed (21)
+      case 11:
+      {
+         const AbiT<D> d = abi_downdate<D, 1>(rd_abi(in + 12), rd_sv(in + 33), rd_sv(in + 39));
+         wr_abi(out, d);
+         wr_abi(out + 21, abi_to_parent<D, 1>(rd_xf(in), d));
+         return 42;
+      }
+      case 12:
+      {
+         const AbiT<D> d = abi_downdate<D, 2>(rd_abi(in + 12), rd_sv(in + 33), rd_sv(in + 39));
+         wr_abi(out, d);
+         wr_abi(out + 21, abi_to_parent<D, 2>(rd_xf(in), d));
+         return 42;
+      }
+      case 13: wr_sv(out, cross_force_add(rd_sv(in), rd_sv(in + 6), rd_sv(in + 12))); return 6;
+      case 14: wr_abi(out, abi_add_rbi(rd_abi(in), rd_rbi(in + 21))); return 21;
+      default: return -1;
+   }
+}
