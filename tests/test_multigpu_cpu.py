@@ -45,3 +45,47 @@ def test_two_rank_slicing_and_reductions(tmp_path):
     assert r0[0] == 2.0 and r1[0] == 2.0          # max over ranks
     assert r0[1] == n and r1[1] == n              # the slices add up to the batch
     assert r0[3] == r1[2]                         # contiguous
+
+
+def _engine_worker(rank, world, port, seed, n, out_dir):
+    """One rank of the data path as bench.py / the multi-device engine run it: its slice of the batch through the kernels' own
+    per-state code (compiled for the host by tests/emu), results gathered on rank 0."""
+    import emu_lib as el
+    import treedesc as td
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)  # every rank builds the same tree and the same batch, then keeps its slice
+    t = td.humanoid(rng, 2)
+    q, qd, qdd, tau = td.random_states(rng, t, n)
+    a, b = sharding.slice_for_rank(n, rank, world)
+    e = el.Emu(t)
+    sl = lambda x: np.ascontiguousarray(x[:, a:b])  # noqa: E731
+    parts = {"rnea": e.rnea(sl(q), sl(qd), sl(qdd)), "aba": e.aba(sl(q), sl(qd), sl(tau)), "crba": e.crba(sl(q)).reshape(t.nv * t.nv, b - a)}
+    for name, mine in parts.items():
+        full = torch.zeros((mine.shape[0], n), dtype=torch.float64)
+        full[:, a:b] = torch.from_numpy(np.ascontiguousarray(mine))
+        dist.reduce(full, dst=0, op=dist.ReduceOp.SUM)  # disjoint slices: the sum is the concatenation, bit for bit
+        if rank == 0:
+            np.save(os.path.join(out_dir, name + ".npy"), full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_slices_concatenate_to_the_single_process_result(tmp_path):
+    """the slices of N ranks concatenate to the bit-identical single-device result -- checked here on the CPU with
+    the kernels' per-state code under gloo (on hardware: tests/test_gpu_host_path.py::test_multi_device_slices_are_bit_identical)."""
+    import emu_lib as el
+    import treedesc as td
+
+    world, n, seed = 2, 37, 4242
+    mp.spawn(_engine_worker, args=(world, _free_port(), seed, n, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(seed)
+    t = td.humanoid(rng, 2)
+    q, qd, qdd, tau = td.random_states(rng, t, n)
+    e = el.Emu(t)
+    whole = {"rnea": e.rnea(q, qd, qdd), "aba": e.aba(q, qd, tau), "crba": e.crba(q).reshape(t.nv * t.nv, n)}
+    for name, want in whole.items():
+        got = np.load(os.path.join(str(tmp_path), name + ".npy"))
+        assert np.array_equal(got, want), name
