@@ -435,3 +435,19 @@ extern "C" int emu_spatial(int op, const double *in, double *out)
       default: return -1;
    }
 }
+
+// the kernels' branch-free sin/cos (jointmath.cuh: mb_sincos, with the large-angle handling of the ops around it) on n angles
+extern "C" void emu_sincos(long n, const double *x, double *s, double *c)
+{
+   for (long i = 0; i < n; i++)
+   {
+      mb::mb_sincos(mb::mb_reduce_angle(x[i]), s + i, c + i);
+      // the off-critical-path form of the same safeguard (RNEA / ABA thread-per-state kernels): fast path on the raw angle, redone if large
+      double s2, c2;
+      mb::mb_sincos(x[i], &s2, &c2);
+      if (mb::mb_angle_large(x[i]))
+         mb::mb_sincos_redo(x[i], s2, c2);
+      if (!(fabs(s2 - s[i]) <= 4.0e-16 && fabs(c2 - c[i]) <= 4.0e-16))
+         s[i] = c[i] = 0.0 / 0.0; // the two forms disagree: poison, the test fails
+   }
+}

@@ -195,3 +195,28 @@ def test_articulated_inertia_congruence_downdate_and_solve(seed):
         assert close(down, want)
         assert not down[axis, :].any() and not down[:, axis].any(), "the joint's row / column is written as exact zeros"
         assert close(up, X.T @ want @ X)
+
+
+def test_branch_free_sincos_accuracy():
+    """The kernels' own sin/cos (jointmath.cuh: Cody-Waite reduction + fdlibm polynomials, no branch) against libm over the fast
+    range |x| < 1e5, at quadrant boundaries, and -- through the large-angle safeguards of the ops -- far beyond it.  Mecano calls
+    Math.sin / Math.cos (1 ulp); the bound here is an absolute 3e-16, i.e. about one ulp of a value near one."""
+    rng = np.random.default_rng(0)
+    k = np.arange(-2000, 2001, dtype=np.float64)
+    x = np.concatenate([
+        rng.uniform(-np.pi, np.pi, 200000), rng.uniform(-1.0e5, 1.0e5, 200000), rng.uniform(-1.0e-3, 1.0e-3, 20000),
+        k * (np.pi / 2), np.nextafter(k * (np.pi / 2), np.inf), np.nextafter(k * (np.pi / 4), -np.inf),
+        [0.0, -0.0, 1.0e5 - 1.0e-9, -(1.0e5 - 1.0e-9), 99999.99999, 7.0e-310],
+        rng.uniform(-1.0e9, 1.0e9, 20000), [1.0e5, -1.0e5, 1.0e15, -3.0e18, 1.0e300]])
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib = el.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.emu_sincos.argtypes = [ctypes.c_long, dp, dp, dp]
+    lib.emu_sincos.restype = None
+    lib.emu_sincos(len(x), x.ctypes.data_as(dp), s.ctypes.data_as(dp), c.ctypes.data_as(dp))
+    assert not (np.isnan(s).any() or np.isnan(c).any()), "the two large-angle forms disagree somewhere"
+    assert np.max(np.abs(s - np.sin(x))) < 3.0e-16 and np.max(np.abs(c - np.cos(x))) < 3.0e-16
+    assert np.max(np.abs(s * s + c * c - 1.0)) < 5.0e-16
+    # relative accuracy where sin is small (the linear term must survive): one-DoF joints near their zero position
+    small = np.abs(x) < 1.0e-3
+    assert np.max(np.abs(s[small] - np.sin(x[small])) / np.maximum(np.abs(x[small]), 1e-300)) < 3.0e-16
