@@ -15,7 +15,9 @@ Rank 0 prints ONE JSON line (see the task contract): metric/value/unit/..., `roo
 cores on a bounded sample), `e2e` (the same step through the host-pointer C-ABI entry points: pinned host buffers,
 H2D + kernels + D2H inside the timed region) and `clocks`.  `extras` (rank 0, outside the timed step; `--no-extras` skips
 them) times the rows next to the path: state integrator, calculator-owned mass matrix, RNEA by-products, forward dynamics with
-joint source modes, centroidal momentum matrix / convective term, Coriolis matrix, and the optional fp32 variant with its error.
+joint source modes, centroidal momentum matrix / centre of mass alone / convective term, Coriolis matrix, the optional fp32 variant
+with its error, BASELINE configs 1 and 2, and the end-to-end step with the packed mass matrix (`e2e_packed`) and with the dense matrix kept
+in one host buffer from step to step (`e2e_dense_kept`).
 
 `--impl reference`: Mecano itself is Java and no JVM exists on these boxes, so the reference arm
 times the reference-faithful C restatement (oracle/, "port") multithreaded on all host cores.
