@@ -268,3 +268,24 @@ def test_packed_mass_matrix_layout(kind):
     assert np.all(ref[~covered] == 0.0)
     if kind == "humanoid":
         assert len(row) == 362  # 37-DoF humanoid: 362 of 1,369 entries
+
+
+def test_fuzz_of_random_trees():
+    """A fixed slice of scripts/fuzz_emulation.py (random trees of every joint type and shape, all emulated entry points against the
+    oracle; on ill-conditioned trees the equation-of-motion residual decides): 150 seeds, a few seconds."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "fuzz_emulation.py")
+    spec = importlib.util.spec_from_file_location("fuzz_emulation", path)
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    for seed in range(400000, 400150):
+        rng = np.random.default_rng(seed)
+        name, t = fz.random_case(rng)
+        try:
+            ok, _ = fz.check(rng, "%s seed %d" % (name, seed), t)
+        except RuntimeError as ex:  # a tree the flattener refuses
+            assert "rc=" in str(ex)
+            continue
+        assert ok, (name, seed)
