@@ -22,7 +22,8 @@ int main(int argc, char **argv)
       auto f = &CompositeRigidBodyMassMatrixCalculator::getCentroidalMomentumMatrix;
       auto g = &CompositeRigidBodyMassMatrixCalculator::getCentroidalConvectiveTermMatrix;
       auto h = &CompositeRigidBodyMassMatrixCalculator::getCoriolisMatrix;
-      std::printf("host mirror links: %d\n", (int)(a && b && c && d && e && f && g && h));
+      auto i = &CompositeRigidBodyMassMatrixCalculator::getCenterOfMass;
+      std::printf("host mirror links: %d\n", (int)(a && b && c && d && e && f && g && h && i));
       return 0;
    }
    return 0;
